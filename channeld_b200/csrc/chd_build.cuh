@@ -1,0 +1,141 @@
+// chd_build.cuh — spatial-hash build: GetChannelId per entity (spatial.go:161-180) and a STABLE LSD radix
+// sort of entity indices by cell (<= 2 passes of <= 10-bit digits: the spatial id space has < 2^19 cells,
+// settings.go:94-95), then cell boundaries.  Result: cell_start[C+2], sorted_entity[N] ordered (cell asc,
+// entity index asc) — the canonical order of SURVEY.md §8c'.  Invalid (out-of-world) entities get key C and
+// sort to the tail [cell_start[C], cell_start[C+1]).
+//
+// Work decomposition: a fixed grid (multiple of the SM count); each block owns a CONTIGUOUS slice of the
+// input processed in order, so global histograms are bins x nblocks (small) and stability is preserved.
+// HBM traffic per pass: read key(+val) / write key+val, coalesced reads; per entity 16 B of positions are
+// read once in the assign kernel.
+#pragma once
+#include "chd_device.cuh"
+
+namespace chd {
+
+constexpr int BUILD_THREADS = 256;
+constexpr int BUILD_WARPS = BUILD_THREADS / 32;
+constexpr int BUILD_ROUNDS = 8;
+constexpr int BUILD_TILE = BUILD_THREADS * BUILD_ROUNDS;  // 2048 entities per tile
+constexpr int BUILD_MAX_BINS = 1024;
+
+struct HandoverOut {
+    uint32_t* entity;
+    uint32_t* src_cell;
+    uint32_t* dst_cell;
+    uint32_t* count;  // device counter (may exceed cap: required size)
+    uint32_t cap;
+};
+
+// cell key per entity (+ optional handover detection against the previous build's keys:
+// the prefix of Notify, spatial.go:612-626: GetChannelId(old) != GetChannelId(new)).
+__global__ void __launch_bounds__(256) assign_cells_kernel(GridDev g, const double* __restrict__ x, const double* __restrict__ z,
+                                                           uint32_t n, uint32_t* __restrict__ key,
+                                                           const uint32_t* __restrict__ prev_key, HandoverOut ho) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t c = cell_index(g, x[i], z[i]);
+    if (c == CHD_INVALID_CELL) c = g.cells;
+    if (prev_key) {
+        const uint32_t p = prev_key[i];
+        if (p != c) {
+            const uint32_t slot = atomicAdd(ho.count, 1u);
+            if (slot < ho.cap) {  // channel ids; 0 = outside the world (GetChannelId error, spatial.go:613-622)
+                ho.entity[slot] = i;
+                ho.src_cell[slot] = p >= g.cells ? 0u : p + g.id_start;
+                ho.dst_cell[slot] = c >= g.cells ? 0u : c + g.id_start;
+            }
+        }
+    }
+    key[i] = c;
+}
+
+// per-block digit histogram; hist layout [digit][block]
+template <int BINS>
+__global__ void __launch_bounds__(BUILD_THREADS)
+    radix_hist_kernel(const uint32_t* __restrict__ key, uint32_t n, uint32_t per_block, uint32_t shift, uint32_t mask,
+                      uint32_t* __restrict__ hist, uint32_t nblocks) {
+    __shared__ uint32_t s_hist[BINS];
+    for (int d = threadIdx.x; d < BINS; d += BUILD_THREADS) s_hist[d] = 0;
+    __syncthreads();
+    const uint32_t lo = blockIdx.x * per_block;
+    const uint32_t hi = min(n, lo + per_block);
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += BUILD_THREADS) atomicAdd(&s_hist[(key[i] >> shift) & mask], 1u);
+    __syncthreads();
+    for (int d = threadIdx.x; d < BINS; d += BUILD_THREADS) hist[(uint32_t)d * nblocks + blockIdx.x] = s_hist[d];
+}
+
+// stable scatter of one pass.  val_in == nullptr means "value = index" (first pass).
+template <int BINS>
+__global__ void __launch_bounds__(BUILD_THREADS)
+    radix_scatter_kernel(const uint32_t* __restrict__ key_in, const uint32_t* __restrict__ val_in, uint32_t n,
+                         uint32_t per_block, uint32_t shift, uint32_t mask, const uint32_t* __restrict__ hist_scanned,
+                         uint32_t nblocks, uint32_t* __restrict__ key_out, uint32_t* __restrict__ val_out) {
+    __shared__ uint32_t s_base[BINS];
+    __shared__ uint32_t s_tot[BINS];
+    __shared__ uint32_t s_wcnt[BUILD_WARPS][BINS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (int d = threadIdx.x; d < BINS; d += BUILD_THREADS) s_base[d] = hist_scanned[(uint32_t)d * nblocks + blockIdx.x];
+    const uint32_t lo = blockIdx.x * per_block;
+    const uint32_t hi = min(n, lo + per_block);
+    for (uint32_t tile = lo; tile < hi; tile += BUILD_TILE) {
+        for (int d = threadIdx.x; d < BINS * BUILD_WARPS; d += BUILD_THREADS) (&s_wcnt[0][0])[d] = 0;
+        __syncthreads();
+        uint32_t k[BUILD_ROUNDS], v[BUILD_ROUNDS], rk[BUILD_ROUNDS];
+#pragma unroll
+        for (int r = 0; r < BUILD_ROUNDS; r++) {
+            const uint32_t i = tile + w * (32 * BUILD_ROUNDS) + r * 32 + lane;
+            const bool valid = i < hi;
+            k[r] = valid ? key_in[i] : 0u;
+            v[r] = valid ? (val_in ? val_in[i] : i) : 0u;
+            const uint32_t d = valid ? ((k[r] >> shift) & mask) : 0xFFFFFFFFu;
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            const uint32_t rank = __popc(peers & lt_mask);
+            uint32_t cnt = 0;
+            if (valid) cnt = s_wcnt[w][d];
+            __syncwarp();
+            if (valid && rank == 0) s_wcnt[w][d] = cnt + __popc(peers);
+            __syncwarp();
+            rk[r] = cnt + rank;
+        }
+        __syncthreads();
+        for (int d = threadIdx.x; d < BINS; d += BUILD_THREADS) {
+            uint32_t run = 0;
+#pragma unroll
+            for (int ww = 0; ww < BUILD_WARPS; ww++) {
+                const uint32_t c = s_wcnt[ww][d];
+                s_wcnt[ww][d] = run;
+                run += c;
+            }
+            s_tot[d] = run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < BUILD_ROUNDS; r++) {
+            const uint32_t i = tile + w * (32 * BUILD_ROUNDS) + r * 32 + lane;
+            if (i < hi) {
+                const uint32_t d = (k[r] >> shift) & mask;
+                const uint32_t dst = s_base[d] + s_wcnt[w][d] + rk[r];
+                val_out[dst] = v[r];
+                if (key_out) key_out[dst] = k[r];
+            }
+        }
+        __syncthreads();
+        for (int d = threadIdx.x; d < BINS; d += BUILD_THREADS) s_base[d] += s_tot[d];
+        __syncthreads();
+    }
+}
+
+// cell_start[c] = first sorted position whose key >= c, for c in [0, C+1]; cell_start[C+1] = n.
+__global__ void __launch_bounds__(256)
+    cell_bounds_kernel(const uint32_t* __restrict__ sorted_key, uint32_t n, uint32_t cells, uint32_t* __restrict__ cell_start) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    // position i: keys (prev, cur]; prev = -1 at i == 0; cur = C+1 at i == n
+    const int64_t prev = i == 0 ? -1 : (int64_t)sorted_key[i - 1];
+    const int64_t cur = i == n ? (int64_t)cells + 1 : (int64_t)sorted_key[i];
+    for (int64_t c = prev + 1; c <= cur; c++) cell_start[c] = i;
+}
+
+}  // namespace chd

@@ -1,0 +1,1142 @@
+// chd_engine.cu — the engine behind include/chd_gpu.h: device memory, launch sequences, C ABI.
+// All device buffers are allocated once in chd_create; the tick path allocates nothing and — apart from
+// chd_summary / the chd_get_* copies — never synchronises with the host.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "chd_build.cuh"
+#include "chd_emit.cuh"
+#include "chd_fanout.cuh"
+#include "chd_misc.cuh"
+#include "chd_scan.cuh"
+
+using namespace chd;
+
+static thread_local std::string g_create_error;
+
+struct chd_engine {
+    chd_grid_cfg cfg;
+    chd_limits lim;
+    GridDev g;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::mutex mu;
+    mutable std::string err;
+    std::vector<void*> allocs;
+    int sm_count = 148;
+    uint64_t n_launch = 0;  // kernels launched by this engine (bench.py reports it as gpu_launches)
+    // optional per-stage CUDA-event timing (chd_profile_*): [stage][0=start,1=stop]
+    bool profiling = false;
+    static constexpr int EV_RING = 1024;
+    cudaEvent_t* ev = nullptr;  // [CHD_STAGE_COUNT][EV_RING][2]
+    uint64_t stage_n[CHD_STAGE_COUNT] = {};
+    cudaEvent_t& evt(int stage, uint64_t i, int which) { return ev[((size_t)stage * EV_RING + (size_t)(i % EV_RING)) * 2 + which]; }
+
+    // ---- entities
+    uint32_t n_own = 0, n_halo = 0;  // entities with positions / appended halo records
+    bool have_gid = false;
+    double *d_x = nullptr, *d_z = nullptr;
+    uint32_t *d_gid = nullptr;            // [max_entities] global ids (multi-GPU) of own + halo
+    uint32_t *d_key = nullptr, *d_prev_key = nullptr;  // [max_entities] cell key per entity
+    uint32_t *d_tmp_key = nullptr, *d_tmp_val = nullptr, *d_sorted_key = nullptr, *d_sorted_ent = nullptr;
+    uint32_t *d_cell_start = nullptr;     // [C+2]
+    uint32_t *d_hist = nullptr;           // [BUILD_MAX_BINS * nblocks + 1]
+    uint32_t *d_scan_scratch = nullptr;   // u32 scan scratch
+    uint64_t *d_scan_scratch64 = nullptr;
+    uint32_t build_blocks = 0;
+    bool assigned = false, built = false, have_prev_key = false, entities_dirty = false;
+    uint32_t n_sorted = 0;
+    // handover
+    uint32_t *d_ho_entity = nullptr, *d_ho_src = nullptr, *d_ho_dst = nullptr;
+    uint32_t ho_cap = 0;
+
+    // ---- subscribers / pairs
+    uint32_t n_slots = 0;
+    uint32_t* d_conn = nullptr;
+    PairBuf pairs[2];
+    int cur = 0;
+    // ---- query scratch
+    struct {
+        uint32_t *sub; uint8_t* kind;
+        double *sph_cx, *sph_cz, *sph_r, *box_cx, *box_cz, *box_ex, *box_ez, *cone_cx, *cone_cz, *cone_dx, *cone_dz, *cone_angle, *cone_r;
+        uint32_t *spot_off, *spot_ndist; double *spot_x, *spot_z; uint32_t* spot_dist;
+    } dq{};
+    Bbox* d_bbox = nullptr;
+    uint32_t *d_win_size = nullptr, *d_window = nullptr, *d_side_cell = nullptr, *d_side_dist = nullptr, *d_side_cnt = nullptr;
+    uint64_t* d_win_off = nullptr;
+    uint32_t *d_status = nullptr, *d_qcount = nullptr;
+    uint64_t* d_qoff = nullptr;  // stateless query CSR offsets
+    uint32_t *d_qout_id = nullptr, *d_qout_dist = nullptr;
+    int32_t* d_slot_query = nullptr;
+    uint32_t* d_slot_cnt = nullptr;
+    uint32_t last_nq = 0;
+    // diff
+    uint32_t *d_new_flag = nullptr, *d_gone_flag = nullptr, *d_new_off = nullptr, *d_gone_off = nullptr;
+    uint32_t *d_new_sub = nullptr, *d_new_ch = nullptr, *d_gone_sub = nullptr, *d_gone_ch = nullptr;
+    // emit
+    uint32_t *d_vcnt = nullptr, *d_first_pair = nullptr, *d_vis = nullptr;
+    uint64_t *d_voff = nullptr, *d_vis_off = nullptr;
+    uint64_t max_tiles = 0;
+    // fanout
+    uint32_t *d_ring_off = nullptr, *d_ring_sender = nullptr;
+    int64_t* d_ring_arrival = nullptr;
+    uint64_t *d_ring_index = nullptr, *d_ch_msg_index = nullptr;
+    bool have_ch_msg_index = false;
+    uint32_t *d_due_cnt = nullptr, *d_due_off = nullptr;
+    chd_due* d_due = nullptr;
+    // counters
+    Counters* d_ctr = nullptr;
+    Counters* h_ctr = nullptr;  // pinned
+    // border export scratch
+    uint32_t *d_bflag = nullptr, *d_boff = nullptr;
+    uint32_t* h_u32 = nullptr;  // pinned scalar
+
+    bool fail(const char* fmt, ...) const {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return false;
+    }
+};
+
+#define CU(e, call)                                                                                  \
+    do {                                                                                             \
+        cudaError_t _r = (call);                                                                     \
+        if (_r != cudaSuccess) {                                                                     \
+            (e)->fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_r), __FILE__, __LINE__);   \
+            return CHD_ERR_CUDA;                                                                     \
+        }                                                                                            \
+    } while (0)
+
+// one kernel launch precedes every KCHECK; scans report their own launch count through SCAN()
+#define KCHECK(e)                    \
+    do {                             \
+        (e)->n_launch++;             \
+        CU(e, cudaGetLastError());   \
+    } while (0)
+#define SCAN(e, ...)                                  \
+    do {                                              \
+        (e)->n_launch += (uint64_t)(__VA_ARGS__);     \
+        CU(e, cudaGetLastError());                    \
+    } while (0)
+
+struct StageTimer {  // records a CUDA-event pair around a stage on the engine stream when profiling is on
+    chd_engine* e;
+    int stage;
+    StageTimer(chd_engine* e_, int stage_) : e(e_), stage(stage_) {
+        if (e->profiling) cudaEventRecord(e->evt(stage, e->stage_n[stage], 0), e->stream);
+    }
+    ~StageTimer() {
+        if (e->profiling) {
+            cudaEventRecord(e->evt(stage, e->stage_n[stage], 1), e->stream);
+            e->stage_n[stage]++;
+        }
+    }
+};
+
+template <typename T>
+static bool dalloc(chd_engine* e, T** p, uint64_t count) {
+    void* q = nullptr;
+    const uint64_t bytes = (count ? count : 1) * sizeof(T);
+    cudaError_t r = cudaMalloc(&q, bytes);
+    if (r != cudaSuccess) {
+        e->fail("cudaMalloc(%llu bytes) failed: %s", (unsigned long long)bytes, cudaGetErrorString(r));
+        return false;
+    }
+    e->allocs.push_back(q);
+    *p = (T*)q;
+    return true;
+}
+
+static inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+extern "C" {
+
+uint32_t chd_abi_version(void) { return CHD_ABI_VERSION; }
+
+uint32_t chd_damping_interval_ms(uint32_t dist, uint32_t default_ms) { return damping_interval_ms(dist, default_ms); }
+
+void chd_default_limits(const chd_grid_cfg* cfg, uint32_t n_entities, uint32_t n_subscribers, chd_limits* lim) {
+    memset(lim, 0, sizeof *lim);
+    const uint64_t cells = (uint64_t)cfg->grid_cols * cfg->grid_rows;
+    lim->max_entities = n_entities ? n_entities : 1;
+    lim->max_subscribers = n_subscribers ? n_subscribers : 1;
+    lim->max_queries = lim->max_subscribers;
+    lim->max_spots = 1024;
+    lim->max_pairs = (uint64_t)lim->max_subscribers * 16 + 1024;
+    lim->max_window_cells = (uint64_t)lim->max_queries * 32 + 65536;
+    const double per_cell = (double)n_entities / (double)(cells ? cells : 1);
+    double v = (double)n_subscribers * 1.6 * per_cell * 1.5 + 1048576.0;
+    if (v > 3.0e9) v = 3.0e9;
+    lim->max_visible = (uint64_t)v;
+    lim->max_ring_entries = (uint32_t)(cells * 64 < 1048576 ? 1048576 : (cells * 64 > 0x7fffffffull ? 0x7fffffffull : cells * 64));
+    lim->max_due = (uint32_t)(lim->max_pairs * 2 > 0x7fffffffull ? 0x7fffffffull : lim->max_pairs * 2);
+    lim->default_fanout_interval_ms = 20;  // GLOBAL defaults, settings.go:97-103
+    lim->default_fanout_delay_ms = 0;
+}
+
+const char* chd_last_error(const chd_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+void* chd_alloc_pinned(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void chd_free_pinned(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+void chd_destroy(chd_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (void* p : e->allocs) cudaFree(p);
+    if (e->ev) {
+        for (size_t i = 0; i < (size_t)CHD_STAGE_COUNT * chd_engine::EV_RING * 2; i++)
+            if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+        delete[] e->ev;
+    }
+    if (e->h_ctr) cudaFreeHost(e->h_ctr);
+    if (e->h_u32) cudaFreeHost(e->h_u32);
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+static bool alloc_pairbuf(chd_engine* e, PairBuf& pb) {
+    const uint64_t P = e->lim.max_pairs;
+    return dalloc(e, &pb.off, (uint64_t)e->lim.max_subscribers + 1) && dalloc(e, &pb.sub, P) && dalloc(e, &pb.cell, P) &&
+           dalloc(e, &pb.dist, P) && dalloc(e, &pb.interval, P) && dalloc(e, &pb.flags, P) && dalloc(e, &pb.last, P) &&
+           dalloc(e, &pb.last_index, P);
+}
+
+chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int device, chd_engine** out) {
+    if (!cfg || !out) {
+        g_create_error = "null argument";
+        return CHD_ERR_INVALID;
+    }
+    *out = nullptr;
+    // LoadConfig validation (spatial.go:146-154); ServerInterestBorderSize == 0 tolerated (see header)
+    if (!(cfg->grid_width > 0) || !(cfg->grid_height > 0)) {
+        g_create_error = "GridWidth and GridHeight should be positive";
+        return CHD_ERR_INVALID;
+    }
+    if (cfg->grid_cols == 0 || cfg->grid_rows == 0) {
+        g_create_error = "GridCols and GridRows should be positive";
+        return CHD_ERR_INVALID;
+    }
+    if (cfg->server_cols == 0 || cfg->server_rows == 0) {
+        g_create_error = "ServerCols and ServerRows should be positive";
+        return CHD_ERR_INVALID;
+    }
+    const uint64_t cells64 = (uint64_t)cfg->grid_cols * cfg->grid_rows;
+    if (cells64 >= (1ull << 20)) {  // spatial id space is [0x10000, 0x80000) (settings.go:94-95): < 2^19 cells
+        g_create_error = "too many cells (GridCols*GridRows must be < 2^20)";
+        return CHD_ERR_INVALID;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        g_create_error = "no CUDA device: this engine has no CPU fallback";
+        return CHD_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        g_create_error = "bad device ordinal";
+        return CHD_ERR_INVALID;
+    }
+    chd_engine* e = new (std::nothrow) chd_engine();
+    if (!e) return CHD_ERR_INVALID;
+    e->cfg = *cfg;
+    if (lim_in)
+        e->lim = *lim_in;
+    else
+        chd_default_limits(cfg, 1u << 20, 1u << 17, &e->lim);
+    chd_limits& L = e->lim;
+    if (!L.max_entities) L.max_entities = 1;
+    if (!L.max_subscribers) L.max_subscribers = 1;
+    if (!L.max_queries) L.max_queries = L.max_subscribers;
+    if (!L.max_pairs) L.max_pairs = 1024;
+    if (!L.max_window_cells) L.max_window_cells = 65536;
+    if (!L.max_visible) L.max_visible = 1u << 20;
+    if (!L.max_ring_entries) L.max_ring_entries = 1u << 16;
+    if (!L.max_due) L.max_due = 1u << 16;
+    if (L.max_pairs >= 0xFFFFFFF0ull || L.max_window_cells >= (1ull << 40)) {
+        g_create_error = "limits too large (pairs are indexed with 32 bits)";
+        delete e;
+        return CHD_ERR_INVALID;
+    }
+    e->device = device;
+#define CCU(call)                                                                       \
+    do {                                                                                \
+        cudaError_t _r = (call);                                                        \
+        if (_r != cudaSuccess) {                                                        \
+            g_create_error = std::string(#call " failed: ") + cudaGetErrorString(_r);   \
+            chd_destroy(e);                                                             \
+            return CHD_ERR_CUDA;                                                        \
+        }                                                                               \
+    } while (0)
+    CCU(cudaSetDevice(device));
+    CCU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    e->own_stream = true;
+    CCU(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device));
+
+    GridDev& g = e->g;
+    g.off_x = cfg->world_offset_x; g.off_z = cfg->world_offset_z; g.w = cfg->grid_width; g.h = cfg->grid_height;
+    g.grid_size = std::sqrt(g.w * g.w + g.h * g.h);                  // spatial.go:134-139
+    g.world_x_hi = g.off_x + g.w * (double)cfg->grid_cols;           // spatial.go:126-132,287
+    g.world_z_hi = g.off_z + g.h * (double)cfg->grid_rows;
+    g.fcols = (double)cfg->grid_cols; g.frows = (double)cfg->grid_rows;
+    g.cols = cfg->grid_cols; g.rows = cfg->grid_rows; g.cells = (uint32_t)cells64; g.id_start = cfg->channel_id_start;
+    g.col_lo = 0; g.col_hi = g.cols; g.halo = 0;
+    g.default_interval_ms = L.default_fanout_interval_ms; g.default_delay_ms = L.default_fanout_delay_ms;
+
+    const uint64_t N = L.max_entities, S = L.max_subscribers, Q = L.max_queries, P = L.max_pairs, C = g.cells;
+    e->build_blocks = (uint32_t)e->sm_count * 4;
+    e->ho_cap = L.max_entities;
+    e->max_tiles = (L.max_visible + EMIT_TILE - 1) / EMIT_TILE + 1;
+    uint64_t scan_n = (uint64_t)BUILD_MAX_BINS * e->build_blocks + 1;
+    if (P + 1 > scan_n) scan_n = P + 1;
+    if (Q + 1 > scan_n) scan_n = Q + 1;
+    if (S + 1 > scan_n) scan_n = S + 1;
+    if (N + 1 > scan_n) scan_n = N + 1;
+    bool ok = true;
+    ok = ok && dalloc(e, &e->d_x, N) && dalloc(e, &e->d_z, N) && dalloc(e, &e->d_gid, N) && dalloc(e, &e->d_key, N) &&
+         dalloc(e, &e->d_prev_key, N) && dalloc(e, &e->d_tmp_key, N) && dalloc(e, &e->d_tmp_val, N) &&
+         dalloc(e, &e->d_sorted_key, N) && dalloc(e, &e->d_sorted_ent, N) && dalloc(e, &e->d_cell_start, C + 2) &&
+         dalloc(e, &e->d_hist, (uint64_t)BUILD_MAX_BINS * e->build_blocks + 2) &&
+         dalloc(e, &e->d_scan_scratch, scan_scratch_elems(scan_n) + 8) && dalloc(e, &e->d_scan_scratch64, scan_scratch_elems(scan_n) + 8) &&
+         dalloc(e, &e->d_ho_entity, N) && dalloc(e, &e->d_ho_src, N) && dalloc(e, &e->d_ho_dst, N) &&
+         dalloc(e, &e->d_bflag, N + 1) && dalloc(e, &e->d_boff, N + 2);
+    ok = ok && dalloc(e, &e->d_conn, S) && alloc_pairbuf(e, e->pairs[0]) && alloc_pairbuf(e, e->pairs[1]);
+    ok = ok && dalloc(e, &e->dq.sub, Q) && dalloc(e, &e->dq.kind, Q) && dalloc(e, &e->dq.sph_cx, Q) && dalloc(e, &e->dq.sph_cz, Q) &&
+         dalloc(e, &e->dq.sph_r, Q) && dalloc(e, &e->dq.box_cx, Q) && dalloc(e, &e->dq.box_cz, Q) && dalloc(e, &e->dq.box_ex, Q) &&
+         dalloc(e, &e->dq.box_ez, Q) && dalloc(e, &e->dq.cone_cx, Q) && dalloc(e, &e->dq.cone_cz, Q) && dalloc(e, &e->dq.cone_dx, Q) &&
+         dalloc(e, &e->dq.cone_dz, Q) && dalloc(e, &e->dq.cone_angle, Q) && dalloc(e, &e->dq.cone_r, Q) &&
+         dalloc(e, &e->dq.spot_off, Q + 1) && dalloc(e, &e->dq.spot_ndist, Q) && dalloc(e, &e->dq.spot_x, (uint64_t)L.max_spots) &&
+         dalloc(e, &e->dq.spot_z, (uint64_t)L.max_spots) && dalloc(e, &e->dq.spot_dist, (uint64_t)L.max_spots);
+    ok = ok && dalloc(e, &e->d_bbox, Q) && dalloc(e, &e->d_win_size, Q) && dalloc(e, &e->d_win_off, Q + 1) &&
+         dalloc(e, &e->d_window, L.max_window_cells) && dalloc(e, &e->d_side_cell, (uint64_t)L.max_spots) &&
+         dalloc(e, &e->d_side_dist, (uint64_t)L.max_spots) && dalloc(e, &e->d_side_cnt, Q) && dalloc(e, &e->d_status, Q) &&
+         dalloc(e, &e->d_qcount, Q) && dalloc(e, &e->d_qoff, Q + 1) && dalloc(e, &e->d_qout_id, P) && dalloc(e, &e->d_qout_dist, P) &&
+         dalloc(e, &e->d_slot_query, S) && dalloc(e, &e->d_slot_cnt, S);
+    ok = ok && dalloc(e, &e->d_new_flag, P) && dalloc(e, &e->d_gone_flag, P) && dalloc(e, &e->d_new_off, P + 1) &&
+         dalloc(e, &e->d_gone_off, P + 1) && dalloc(e, &e->d_new_sub, P) && dalloc(e, &e->d_new_ch, P) && dalloc(e, &e->d_gone_sub, P) &&
+         dalloc(e, &e->d_gone_ch, P);
+    ok = ok && dalloc(e, &e->d_vcnt, P) && dalloc(e, &e->d_voff, P + 1) && dalloc(e, &e->d_first_pair, e->max_tiles + 1) &&
+         dalloc(e, &e->d_vis_off, S + 1) && dalloc(e, &e->d_vis, L.max_visible);
+    ok = ok && dalloc(e, &e->d_ring_off, C + 1) && dalloc(e, &e->d_ring_arrival, (uint64_t)L.max_ring_entries) &&
+         dalloc(e, &e->d_ring_sender, (uint64_t)L.max_ring_entries) && dalloc(e, &e->d_ring_index, (uint64_t)L.max_ring_entries) &&
+         dalloc(e, &e->d_ch_msg_index, C) && dalloc(e, &e->d_due_cnt, P) && dalloc(e, &e->d_due_off, P + 1) &&
+         dalloc(e, &e->d_due, (uint64_t)L.max_due) && dalloc(e, &e->d_ctr, 1);
+    if (!ok) {
+        g_create_error = e->err;
+        chd_destroy(e);
+        return CHD_ERR_CUDA;
+    }
+    CCU(cudaHostAlloc((void**)&e->h_ctr, sizeof(Counters), cudaHostAllocDefault));
+    CCU(cudaHostAlloc((void**)&e->h_u32, 64, cudaHostAllocDefault));
+    CCU(cudaMemsetAsync(e->d_ctr, 0, sizeof(Counters), e->stream));
+    CCU(cudaMemsetAsync(e->pairs[0].off, 0, (S + 1) * 4, e->stream));
+    CCU(cudaMemsetAsync(e->pairs[1].off, 0, (S + 1) * 4, e->stream));
+    CCU(cudaMemsetAsync(e->d_ring_off, 0, (C + 1) * 4, e->stream));
+    CCU(cudaMemsetAsync(e->d_cell_start, 0, (C + 2) * 4, e->stream));
+    CCU(cudaMemsetAsync(e->d_vis_off, 0, (S + 1) * 8, e->stream));
+    CCU(cudaStreamSynchronize(e->stream));
+#undef CCU
+    *out = e;
+    return CHD_OK;
+}
+
+chd_status chd_set_stream(chd_engine* e, void* cuda_stream) {
+    if (!e) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    CU(e, cudaStreamSynchronize(e->stream));
+    if (e->own_stream) {
+        cudaStreamDestroy(e->stream);
+        e->own_stream = false;
+    }
+    e->stream = (cudaStream_t)cuda_stream;
+    return CHD_OK;
+}
+
+chd_status chd_sync(chd_engine* e) {
+    if (!e) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    CU(e, cudaStreamSynchronize(e->stream));
+    return CHD_OK;
+}
+
+/* ------------------------------------------------------------------ entities / build ---- */
+
+chd_status chd_cell_of(chd_engine* e, const double* x, const double* z, uint32_t n, uint32_t* out) {
+    if (!e || (n && (!x || !z || !out))) return CHD_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(e, cudaSetDevice(e->device));
+    // chunked through the tmp buffers (they are free outside chd_build)
+    double *dx = nullptr, *dz = nullptr;
+    uint32_t* dk = nullptr;
+    const uint32_t chunk = 1u << 20;
+    CU(e, cudaMallocAsync((void**)&dx, sizeof(double) * chunk, e->stream));
+    CU(e, cudaMallocAsync((void**)&dz, sizeof(double) * chunk, e->stream));
+    CU(e, cudaMallocAsync((void**)&dk, sizeof(uint32_t) * chunk, e->stream));
+    HandoverOut ho{};
+    for (uint32_t b = 0; b < n; b += chunk) {
+        const uint32_t m = n - b < chunk ? n - b : chunk;
+        CU(e, cudaMemcpyAsync(dx, x + b, sizeof(double) * m, cudaMemcpyDefault, e->stream));
+        CU(e, cudaMemcpyAsync(dz, z + b, sizeof(double) * m, cudaMemcpyDefault, e->stream));
+        assign_cells_kernel<<<blocks_for(m, 256), 256, 0, e->stream>>>(e->g, dx, dz, m, dk, nullptr, ho);
+        KCHECK(e);
+        cell_key_to_id_kernel<<<blocks_for(m, 256), 256, 0, e->stream>>>(dk, m, e->g.cells, e->g.id_start);
+        KCHECK(e);
+        CU(e, cudaMemcpyAsync(out + b, dk, sizeof(uint32_t) * m, cudaMemcpyDefault, e->stream));
+    }
+    CU(e, cudaFreeAsync(dx, e->stream));
+    CU(e, cudaFreeAsync(dz, e->stream));
+    CU(e, cudaFreeAsync(dk, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    return CHD_OK;
+}
+
+chd_status chd_set_entities(chd_engine* e, const double* x, const double* z, uint32_t n) {
+    if (!e || (n && (!x || !z))) return CHD_ERR_INVALID;
+    if (n > e->lim.max_entities) {
+        e->fail("chd_set_entities: %u > max_entities %u", n, e->lim.max_entities);
+        return CHD_ERR_CAPACITY;
+    }
+    CU(e, cudaSetDevice(e->device));
+    if (n != e->n_own) e->have_prev_key = false;
+    CU(e, cudaMemcpyAsync(e->d_x, x, sizeof(double) * n, cudaMemcpyDefault, e->stream));
+    CU(e, cudaMemcpyAsync(e->d_z, z, sizeof(double) * n, cudaMemcpyDefault, e->stream));
+    e->n_own = n;
+    e->n_halo = 0;
+    e->assigned = false;
+    e->entities_dirty = true;
+    return CHD_OK;
+}
+
+chd_status chd_entity_buffers(chd_engine* e, double** d_x, double** d_z, uint32_t* n) {
+    if (!e) return CHD_ERR_INVALID;
+    if (d_x) *d_x = e->d_x;
+    if (d_z) *d_z = e->d_z;
+    if (n) *n = e->n_own;
+    e->assigned = false;  // the caller may write positions
+    e->entities_dirty = true;
+    return CHD_OK;
+}
+
+chd_status chd_set_entity_count(chd_engine* e, uint32_t n) {
+    if (!e || n > e->lim.max_entities) return CHD_ERR_INVALID;
+    if (n != e->n_own) e->have_prev_key = false;
+    e->n_own = n;
+    e->n_halo = 0;
+    e->assigned = false;
+    e->entities_dirty = true;
+    return CHD_OK;
+}
+
+chd_status chd_set_entity_ids(chd_engine* e, const uint32_t* gid, uint32_t n) {
+    if (!e || n > e->lim.max_entities) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    if (!gid) {
+        e->have_gid = false;
+        return CHD_OK;
+    }
+    CU(e, cudaMemcpyAsync(e->d_gid, gid, sizeof(uint32_t) * n, cudaMemcpyDefault, e->stream));
+    e->have_gid = true;
+    e->entities_dirty = true;
+    return CHD_OK;
+}
+
+chd_status chd_assign_cells(chd_engine* e) {
+    if (!e) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    if (e->assigned) return CHD_OK;
+    // handover detection compares against the keys of the previous assignment (same entity count):
+    // the buffers are swapped, never copied.
+    uint32_t* prev = nullptr;
+    if (e->have_prev_key) {
+        uint32_t* t = e->d_key;
+        e->d_key = e->d_prev_key;
+        e->d_prev_key = t;
+        prev = e->d_prev_key;
+    }
+    HandoverOut ho{e->d_ho_entity, e->d_ho_src, e->d_ho_dst, &e->d_ctr->n_handover, e->ho_cap};
+    CU(e, cudaMemsetAsync(&e->d_ctr->n_handover, 0, 4, e->stream));
+    if (e->n_own) {
+        assign_cells_kernel<<<blocks_for(e->n_own, 256), 256, 0, e->stream>>>(e->g, e->d_x, e->d_z, e->n_own, e->d_key, prev, ho);
+        KCHECK(e);
+        e->have_prev_key = true;
+    }
+    e->n_halo = 0;
+    e->assigned = true;
+    return CHD_OK;
+}
+
+extern "C++" {
+template <int BINS>
+static chd_status sort_pass(chd_engine* e, const uint32_t* key_in, const uint32_t* val_in, uint32_t n, uint32_t per_block,
+                            uint32_t nblocks, uint32_t shift, uint32_t bits, uint32_t* key_out, uint32_t* val_out) {
+    const uint32_t mask = (1u << bits) - 1u;
+    radix_hist_kernel<BINS><<<nblocks, BUILD_THREADS, 0, e->stream>>>(key_in, n, per_block, shift, mask, e->d_hist, nblocks);
+    KCHECK(e);
+    SCAN(e, exclusive_scan<uint32_t, uint32_t>(e->d_hist, e->d_hist, (uint64_t)BINS * nblocks, e->d_scan_scratch, e->stream));
+    radix_scatter_kernel<BINS><<<nblocks, BUILD_THREADS, 0, e->stream>>>(key_in, val_in, n, per_block, shift, mask, e->d_hist, nblocks,
+                                                                        key_out, val_out);
+    KCHECK(e);
+    return CHD_OK;
+}
+}  // extern "C++"
+
+static chd_status sort_pass_any(chd_engine* e, const uint32_t* key_in, const uint32_t* val_in, uint32_t n, uint32_t per_block,
+                                uint32_t nblocks, uint32_t shift, uint32_t bits, uint32_t* key_out, uint32_t* val_out) {
+    if (bits <= 8) return sort_pass<256>(e, key_in, val_in, n, per_block, nblocks, shift, bits, key_out, val_out);
+    return sort_pass<1024>(e, key_in, val_in, n, per_block, nblocks, shift, bits, key_out, val_out);
+}
+
+chd_status chd_build(chd_engine* e) {
+    if (!e) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    StageTimer timer(e, CHD_STAGE_BUILD);
+    chd_status st = chd_assign_cells(e);
+    if (st != CHD_OK) return st;
+    const uint32_t n = e->n_own + e->n_halo;
+    const uint32_t C = e->g.cells;
+    uint32_t bits = 1;
+    while ((1u << bits) < C + 1) bits++;  // keys are in [0, C]
+    const uint32_t passes = bits <= 10 ? 1 : 2;
+    const uint32_t bits0 = passes == 1 ? bits : (bits + 1) / 2, bits1 = bits - bits0;
+    // contiguous slice per block, multiple of the tile
+    uint32_t per_block = (n + e->build_blocks - 1) / e->build_blocks;
+    per_block = ((per_block + BUILD_TILE - 1) / BUILD_TILE) * BUILD_TILE;
+    if (per_block == 0) per_block = BUILD_TILE;
+    uint32_t nblocks = (n + per_block - 1) / per_block;
+    if (nblocks == 0) nblocks = 1;
+    const uint32_t* vals = e->have_gid ? e->d_gid : nullptr;
+    if (passes == 1) {
+        st = sort_pass_any(e, e->d_key, vals, n, per_block, nblocks, 0, bits0, e->d_sorted_key, e->d_sorted_ent);
+        if (st != CHD_OK) return st;
+    } else {
+        st = sort_pass_any(e, e->d_key, vals, n, per_block, nblocks, 0, bits0, e->d_tmp_key, e->d_tmp_val);
+        if (st != CHD_OK) return st;
+        st = sort_pass_any(e, e->d_tmp_key, e->d_tmp_val, n, per_block, nblocks, bits0, bits1, e->d_sorted_key, e->d_sorted_ent);
+        if (st != CHD_OK) return st;
+    }
+    cell_bounds_kernel<<<blocks_for((uint64_t)n + 1, 256), 256, 0, e->stream>>>(e->d_sorted_key, n, C, e->d_cell_start);
+    KCHECK(e);
+    set_in_world_kernel<<<1, 1, 0, e->stream>>>(e->d_cell_start, C, e->d_ctr);
+    KCHECK(e);
+    e->n_sorted = n;
+    e->built = true;
+    e->entities_dirty = false;
+    return CHD_OK;
+}
+
+/* ------------------------------------------------------------------ subscribers / queries ---- */
+
+chd_status chd_set_subscribers(chd_engine* e, const uint32_t* conn_id, uint32_t n) {
+    if (!e || (n && !conn_id)) return CHD_ERR_INVALID;
+    if (n > e->lim.max_subscribers) {
+        e->fail("chd_set_subscribers: %u > max_subscribers %u", n, e->lim.max_subscribers);
+        return CHD_ERR_CAPACITY;
+    }
+    CU(e, cudaSetDevice(e->device));
+    CU(e, cudaMemcpyAsync(e->d_conn, conn_id, sizeof(uint32_t) * n, cudaMemcpyDefault, e->stream));
+    CU(e, cudaMemsetAsync(e->pairs[0].off, 0, ((uint64_t)e->lim.max_subscribers + 1) * 4, e->stream));
+    CU(e, cudaMemsetAsync(e->pairs[1].off, 0, ((uint64_t)e->lim.max_subscribers + 1) * 4, e->stream));
+    CU(e, cudaMemsetAsync(e->d_vis_off, 0, ((uint64_t)e->lim.max_subscribers + 1) * 8, e->stream));
+    e->n_slots = n;
+    e->cur = 0;
+    return CHD_OK;
+}
+
+// copies the batch into the engine's device SoA and returns the device view
+static chd_status upload_queries(chd_engine* e, const chd_query_batch* q, QueryDev* out, bool need_sub) {
+    if (!q) return CHD_ERR_INVALID;
+    const uint32_t n = q->n;
+    if (n > e->lim.max_queries) {
+        e->fail("query batch of %u > max_queries %u", n, e->lim.max_queries);
+        return CHD_ERR_CAPACITY;
+    }
+    QueryDev d{};
+    d.n = n;
+    cudaStream_t st = e->stream;
+#define UP(field, T)                                                                                      \
+    if (q->field) {                                                                                       \
+        CU(e, cudaMemcpyAsync(e->dq.field, q->field, sizeof(T) * n, cudaMemcpyDefault, st));              \
+        d.field = e->dq.field;                                                                            \
+    }
+    if (need_sub) {
+        if (!q->sub && n) {
+            e->fail("query batch without subscriber slots");
+            return CHD_ERR_INVALID;
+        }
+        UP(sub, uint32_t);
+    }
+    UP(kind, uint8_t);
+    UP(sph_cx, double); UP(sph_cz, double); UP(sph_r, double);
+    UP(box_cx, double); UP(box_cz, double); UP(box_ex, double); UP(box_ez, double);
+    UP(cone_cx, double); UP(cone_cz, double); UP(cone_dx, double); UP(cone_dz, double); UP(cone_angle, double); UP(cone_r, double);
+    UP(spot_ndist, uint32_t);
+#undef UP
+    if (!q->kind && n && (!q->sph_cx || !q->sph_cz || !q->sph_r)) {
+        e->fail("kind == NULL means all-sphere: sph_cx/sph_cz/sph_r are required");
+        return CHD_ERR_INVALID;
+    }
+    if (q->spot_off) {
+        // spot_off may live on the host or on the device; its last element sizes the spot arrays
+        uint32_t total = 0;
+        CU(e, cudaMemcpyAsync(e->dq.spot_off, q->spot_off, sizeof(uint32_t) * ((uint64_t)n + 1), cudaMemcpyDefault, st));
+        CU(e, cudaMemcpyAsync(e->h_u32, e->dq.spot_off + n, 4, cudaMemcpyDeviceToHost, st));
+        CU(e, cudaStreamSynchronize(st));
+        total = *e->h_u32;
+        if (total > e->lim.max_spots) {
+            e->fail("%u spots > max_spots %u", total, e->lim.max_spots);
+            return CHD_ERR_CAPACITY;
+        }
+        if (total && (!q->spot_x || !q->spot_z)) return CHD_ERR_INVALID;
+        CU(e, cudaMemcpyAsync(e->dq.spot_x, q->spot_x, sizeof(double) * total, cudaMemcpyDefault, st));
+        CU(e, cudaMemcpyAsync(e->dq.spot_z, q->spot_z, sizeof(double) * total, cudaMemcpyDefault, st));
+        if (q->spot_dist) CU(e, cudaMemcpyAsync(e->dq.spot_dist, q->spot_dist, sizeof(uint32_t) * total, cudaMemcpyDefault, st));
+        else CU(e, cudaMemsetAsync(e->dq.spot_dist, 0, sizeof(uint32_t) * total, st));
+        d.spot_off = e->dq.spot_off; d.spot_x = e->dq.spot_x; d.spot_z = e->dq.spot_z; d.spot_dist = e->dq.spot_dist;
+        if (!q->spot_ndist) {
+            CU(e, cudaMemsetAsync(e->dq.spot_ndist, 0, sizeof(uint32_t) * n, st));
+            d.spot_ndist = e->dq.spot_ndist;
+        }
+    }
+    *out = d;
+    return CHD_OK;
+}
+
+// Q1 + scan + Q2: fills bbox / window / side lists / status / qcount for the batch
+static chd_status run_query_kernels(chd_engine* e, const QueryDev& d) {
+    const uint32_t n = d.n;
+    if (n == 0) return CHD_OK;
+    query_bbox_kernel<<<blocks_for(n, 256), 256, 0, e->stream>>>(e->g, d, e->d_bbox, e->d_win_size);
+    KCHECK(e);
+    SCAN(e, exclusive_scan<uint32_t, uint64_t>(e->d_win_size, e->d_win_off, n, e->d_scan_scratch64, e->stream));
+    window_overflow_kernel<<<1, 1, 0, e->stream>>>(e->d_win_off, n, e->lim.max_window_cells, e->d_ctr);
+    KCHECK(e);
+    query_sample_kernel<<<blocks_for(n, 128), 128, 0, e->stream>>>(e->g, d, e->d_bbox, e->d_win_off, e->lim.max_window_cells, e->d_window,
+                                                                   e->d_side_cell, e->d_side_dist, e->d_side_cnt, e->d_status, e->d_qcount);
+    KCHECK(e);
+    return CHD_OK;
+}
+
+chd_status chd_query_channel_ids(chd_engine* e, const chd_query_batch* q, uint32_t* out_status, uint32_t* out_off,
+                                 uint32_t* out_channel_id, uint32_t* out_dist, uint64_t cap) {
+    if (!e || !q) return CHD_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(e, cudaSetDevice(e->device));
+    QueryDev d;
+    chd_status st = upload_queries(e, q, &d, false);
+    if (st != CHD_OK) return st;
+    const uint32_t n = d.n;
+    if (n == 0) {
+        if (out_off) {
+            const uint32_t zero = 0;
+            CU(e, cudaMemcpyAsync(out_off, &zero, 4, cudaMemcpyDefault, e->stream));
+            CU(e, cudaStreamSynchronize(e->stream));
+        }
+        return CHD_OK;
+    }
+    st = run_query_kernels(e, d);
+    if (st != CHD_OK) return st;
+    SCAN(e, exclusive_scan<uint32_t, uint64_t>(e->d_qcount, e->d_qoff, n, e->d_scan_scratch64, e->stream));
+    const uint64_t dev_cap = e->lim.max_pairs;
+    query_write_kernel<<<blocks_for(n, 128), 128, 0, e->stream>>>(e->g, n, e->d_status, e->d_bbox, e->d_win_off, e->d_window, e->d_side_cell,
+                                                                  e->d_side_dist, e->d_side_cnt, d.spot_off, e->d_qoff, dev_cap,
+                                                                  e->d_qout_id, e->d_qout_dist);
+    KCHECK(e);
+    // totals
+    uint64_t* h64 = (uint64_t*)e->h_u32;
+    CU(e, cudaMemcpyAsync(h64, e->d_qoff + n, 8, cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(h64 + 1, e->d_win_off + n, 8, cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    const uint64_t total = h64[0], wtotal = h64[1];
+    if (wtotal > e->lim.max_window_cells) {
+        e->fail("query windows need %llu cells > max_window_cells %llu", (unsigned long long)wtotal,
+                (unsigned long long)e->lim.max_window_cells);
+        return CHD_ERR_CAPACITY;
+    }
+    if (total > dev_cap || total > cap) {
+        e->fail("query result has %llu entries > capacity %llu", (unsigned long long)total,
+                (unsigned long long)(total > dev_cap ? dev_cap : cap));
+        return CHD_ERR_CAPACITY;
+    }
+    if (out_status) CU(e, cudaMemcpyAsync(out_status, e->d_status, sizeof(uint32_t) * n, cudaMemcpyDefault, e->stream));
+    if (out_off) {
+        // u64 device offsets -> u32 caller offsets
+        narrow_offsets_kernel<<<blocks_for((uint64_t)n + 1, 256), 256, 0, e->stream>>>(e->d_qoff, n + 1, e->d_new_off);
+        KCHECK(e);
+        CU(e, cudaMemcpyAsync(out_off, e->d_new_off, sizeof(uint32_t) * ((uint64_t)n + 1), cudaMemcpyDefault, e->stream));
+    }
+    if (out_channel_id) CU(e, cudaMemcpyAsync(out_channel_id, e->d_qout_id, sizeof(uint32_t) * total, cudaMemcpyDefault, e->stream));
+    if (out_dist) CU(e, cudaMemcpyAsync(out_dist, e->d_qout_dist, sizeof(uint32_t) * total, cudaMemcpyDefault, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    return CHD_OK;
+}
+
+chd_status chd_update_interest(chd_engine* e, const chd_query_batch* q, int64_t now_ns) {
+    if (!e || !q) return CHD_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(e, cudaSetDevice(e->device));
+    StageTimer timer(e, CHD_STAGE_INTEREST);
+    QueryDev d;
+    chd_status st = upload_queries(e, q, &d, true);
+    if (st != CHD_OK) return st;
+    const uint32_t n = d.n, S = e->n_slots;
+    cudaStream_t s = e->stream;
+    st = run_query_kernels(e, d);
+    if (st != CHD_OK) return st;
+    PairBuf& prev = e->pairs[e->cur];
+    PairBuf& cur = e->pairs[e->cur ^ 1];
+    const uint64_t P = e->lim.max_pairs;
+    CU(e, cudaMemsetAsync(e->d_slot_query, 0xFF, sizeof(int32_t) * (uint64_t)(S ? S : 1), s));
+    CU(e, cudaMemsetAsync(&e->d_ctr->n_query_errors, 0, 4 * 4, s));  // n_query_errors, n_sub_new, n_unsub, n_kept
+    if (n) {
+        slot_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(d.sub, n, S, e->d_slot_query);
+        KCHECK(e);
+    }
+    if (S) {
+        slot_count_kernel<<<blocks_for(S, 256), 256, 0, s>>>(S, e->d_slot_query, e->d_status, e->d_qcount, prev.off, e->d_slot_cnt, e->d_ctr);
+        KCHECK(e);
+    }
+    SCAN(e, exclusive_scan<uint32_t, uint32_t>(e->d_slot_cnt, cur.off, S, e->d_scan_scratch, s));
+    pairs_total_kernel<<<1, 1, 0, s>>>(cur.off, S, P, e->d_ctr);
+    KCHECK(e);
+    if (S) {
+        interest_fill_kernel<<<blocks_for(S, 128), 128, 0, s>>>(e->g, S, e->d_slot_query, e->d_status, e->d_bbox, e->d_win_off, e->d_window,
+                                                                e->d_side_cell, e->d_side_dist, e->d_side_cnt, d.spot_off, prev, cur, P,
+                                                                now_ns, e->d_new_flag, e->d_gone_flag, e->d_ctr);
+        KCHECK(e);
+    }
+    // diff lists: compact flagged pairs (deterministic order)
+    SCAN(e, exclusive_scan<uint32_t, uint32_t>(e->d_new_flag, e->d_new_off, P, e->d_scan_scratch, s, cur.off + S));
+    SCAN(e, exclusive_scan<uint32_t, uint32_t>(e->d_gone_flag, e->d_gone_off, P, e->d_scan_scratch, s, prev.off + S));
+    const unsigned grid = (unsigned)e->sm_count * 4;
+    diff_compact_kernel<<<grid, 256, 0, s>>>(e->d_new_flag, e->d_new_off, cur.off + S, P, cur.sub, cur.cell, e->g.id_start, e->d_new_sub, e->d_new_ch);
+    KCHECK(e);
+    diff_compact_kernel<<<grid, 256, 0, s>>>(e->d_gone_flag, e->d_gone_off, prev.off + S, P, prev.sub, prev.cell, e->g.id_start, e->d_gone_sub, e->d_gone_ch);
+    KCHECK(e);
+    e->cur ^= 1;
+    e->last_nq = n;
+    return CHD_OK;
+}
+
+chd_status chd_emit_visible(chd_engine* e) {
+    if (!e) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    if (!e->built) {
+        e->fail("chd_emit_visible before chd_build");
+        return CHD_ERR_STATE;
+    }
+    cudaStream_t s = e->stream;
+    PairBuf& pb = e->pairs[e->cur];
+    const uint32_t S = e->n_slots;
+    const uint64_t P = e->lim.max_pairs;
+    StageTimer timer(e, CHD_STAGE_EMIT);
+    const unsigned grid = (unsigned)e->sm_count * 8;
+    pair_vcount_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, pb.cell, e->d_cell_start, e->d_vcnt);
+    KCHECK(e);
+    SCAN(e, exclusive_scan<uint32_t, uint64_t>(e->d_vcnt, e->d_voff, P, e->d_scan_scratch64, s, pb.off + S));
+    vis_off_kernel<<<blocks_for((uint64_t)S + 1, 256), 256, 0, s>>>(S, pb.off, P, e->d_voff, e->d_vis_off, e->lim.max_visible, e->d_ctr);
+    KCHECK(e);
+    emit_partition_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, e->d_voff, e->d_first_pair, e->max_tiles);
+    KCHECK(e);
+    {
+        StageTimer kt(e, CHD_STAGE_EMIT_KERNEL);
+        emit_visible_kernel<<<grid, EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted_ent,
+                                                          e->d_first_pair, e->d_vis, e->lim.max_visible);
+        KCHECK(e);
+    }
+    return CHD_OK;
+}
+
+chd_status chd_set_rings(chd_engine* e, const uint32_t* ring_off, uint32_t n_entries, const int64_t* arrival, const uint32_t* sender,
+                         const uint64_t* index, const uint64_t* ch_msg_index) {
+    if (!e || !ring_off) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    const uint32_t C = e->g.cells;
+    const uint32_t total = n_entries;
+    if (total > e->lim.max_ring_entries) {
+        e->fail("%u ring entries > max_ring_entries %u", total, e->lim.max_ring_entries);
+        return CHD_ERR_CAPACITY;
+    }
+    if (total && (!arrival || !sender || !index)) return CHD_ERR_INVALID;
+    CU(e, cudaMemcpyAsync(e->d_ring_off, ring_off, sizeof(uint32_t) * ((uint64_t)C + 1), cudaMemcpyDefault, e->stream));
+    if (total) {
+        CU(e, cudaMemcpyAsync(e->d_ring_arrival, arrival, sizeof(int64_t) * total, cudaMemcpyDefault, e->stream));
+        CU(e, cudaMemcpyAsync(e->d_ring_sender, sender, sizeof(uint32_t) * total, cudaMemcpyDefault, e->stream));
+        CU(e, cudaMemcpyAsync(e->d_ring_index, index, sizeof(uint64_t) * total, cudaMemcpyDefault, e->stream));
+    }
+    // ring_off[C] must equal n_entries: clamp on the device so a lying caller cannot cause out-of-bounds reads
+    clamp_ring_off_kernel<<<blocks_for((uint64_t)C + 1, 256), 256, 0, e->stream>>>(e->d_ring_off, C + 1, total);
+    KCHECK(e);
+    if (ch_msg_index) {
+        CU(e, cudaMemcpyAsync(e->d_ch_msg_index, ch_msg_index, sizeof(uint64_t) * C, cudaMemcpyDefault, e->stream));
+        e->have_ch_msg_index = true;
+    } else
+        e->have_ch_msg_index = false;
+    return CHD_OK;
+}
+
+chd_status chd_fanout_tick(chd_engine* e, int64_t t_ns) {
+    if (!e) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    cudaStream_t s = e->stream;
+    PairBuf& pb = e->pairs[e->cur];
+    const uint32_t S = e->n_slots;
+    const uint64_t P = e->lim.max_pairs;
+    StageTimer timer(e, CHD_STAGE_FANOUT);
+    RingDev ring{e->d_ring_off, e->d_ring_arrival, e->d_ring_sender, e->d_ring_index, e->have_ch_msg_index ? e->d_ch_msg_index : nullptr};
+    const unsigned grid = (unsigned)e->sm_count * 16;
+    fanout_kernel<false><<<grid, 128, 0, s>>>(pb.off + S, P, pb, e->d_conn, ring, t_ns, e->g.id_start, e->d_due_cnt, nullptr, nullptr, 0);
+    KCHECK(e);
+    SCAN(e, exclusive_scan<uint32_t, uint32_t>(e->d_due_cnt, e->d_due_off, P, e->d_scan_scratch, s, pb.off + S));
+    due_total_kernel<<<1, 1, 0, s>>>(pb.off + S, P, e->d_due_off, e->lim.max_due, e->d_ctr);
+    KCHECK(e);
+    fanout_kernel<true><<<grid, 128, 0, s>>>(pb.off + S, P, pb, e->d_conn, ring, t_ns, e->g.id_start, e->d_due_cnt, e->d_due_off, e->d_due,
+                                             e->lim.max_due);
+    KCHECK(e);
+    return CHD_OK;
+}
+
+chd_status chd_summary(chd_engine* e, chd_tick_summary* out) {
+    if (!e || !out) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    CU(e, cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    const Counters& c = *e->h_ctr;
+    out->n_pairs = c.n_pairs; out->n_visible = c.n_visible; out->n_entities_in_world = c.n_entities_in_world;
+    out->n_query_errors = c.n_query_errors; out->n_sub_new = c.n_sub_new; out->n_unsub = c.n_unsub; out->n_kept = c.n_kept;
+    out->n_due = c.n_due; out->n_handover = c.n_handover; out->overflow = c.overflow; out->required_pairs = c.required_pairs;
+    out->required_window_cells = c.required_window_cells; out->required_visible = c.required_visible; out->required_due = c.required_due;
+    out->reserved = 0;
+    if (c.overflow) {
+        e->fail("capacity overflow mask 0x%x (pairs %llu, window cells %llu, visible %llu, due %u required)", c.overflow,
+                (unsigned long long)c.required_pairs, (unsigned long long)c.required_window_cells,
+                (unsigned long long)c.required_visible, c.required_due);
+        // sticky bits are cleared so the caller can retry after raising limits
+        CU(e, cudaMemsetAsync(&e->d_ctr->overflow, 0, 4, e->stream));
+        return CHD_ERR_CAPACITY;
+    }
+    return CHD_OK;
+}
+
+chd_status chd_tick(chd_engine* e, const chd_query_batch* q, int64_t t_ns, uint32_t flags, chd_tick_summary* out) {
+    if (!e) return CHD_ERR_INVALID;
+    chd_status st;
+    if ((flags & CHD_TICK_BUILD) && (e->entities_dirty || !e->built)) {
+        st = chd_build(e);
+        if (st != CHD_OK) return st;
+    }
+    if (q) {
+        st = chd_update_interest(e, q, t_ns);
+        if (st != CHD_OK) return st;
+    }
+    if (flags & CHD_TICK_EMIT) {
+        st = chd_emit_visible(e);
+        if (st != CHD_OK) return st;
+    }
+    if (flags & CHD_TICK_FANOUT) {
+        st = chd_fanout_tick(e, t_ns);
+        if (st != CHD_OK) return st;
+    }
+    if (out) return chd_summary(e, out);
+    return CHD_OK;
+}
+
+/* ------------------------------------------------------------------ results ---- */
+
+static chd_status read_u32(chd_engine* e, const uint32_t* d, uint32_t* v) {
+    CU(e, cudaMemcpyAsync(e->h_u32, d, 4, cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    *v = *e->h_u32;
+    return CHD_OK;
+}
+
+chd_status chd_get_cells(chd_engine* e, uint32_t* cell_start, uint32_t* sorted_entity) {
+    if (!e) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    const uint32_t C = e->g.cells;
+    if (cell_start) CU(e, cudaMemcpyAsync(cell_start, e->d_cell_start, sizeof(uint32_t) * ((uint64_t)C + 1), cudaMemcpyDefault, e->stream));
+    if (sorted_entity) {
+        uint32_t nin = 0;
+        chd_status st = read_u32(e, e->d_cell_start + C, &nin);
+        if (st != CHD_OK) return st;
+        CU(e, cudaMemcpyAsync(sorted_entity, e->d_sorted_ent, sizeof(uint32_t) * nin, cudaMemcpyDefault, e->stream));
+    }
+    CU(e, cudaStreamSynchronize(e->stream));
+    return CHD_OK;
+}
+
+chd_status chd_get_pairs(chd_engine* e, uint32_t* pair_off, uint32_t* channel_id, uint32_t* dist, uint32_t* interval_ms, uint8_t* flags,
+                         int64_t* last_fanout_ns, uint64_t* last_message_index) {
+    if (!e) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    PairBuf& pb = e->pairs[e->cur];
+    const uint32_t S = e->n_slots;
+    uint32_t P = 0;
+    chd_status st = read_u32(e, pb.off + S, &P);
+    if (st != CHD_OK) return st;
+    if (P > e->lim.max_pairs) return CHD_ERR_CAPACITY;
+    cudaStream_t s = e->stream;
+    if (pair_off) CU(e, cudaMemcpyAsync(pair_off, pb.off, sizeof(uint32_t) * ((uint64_t)S + 1), cudaMemcpyDefault, s));
+    if (channel_id) {
+        add_const_kernel<<<blocks_for(P ? P : 1, 256), 256, 0, s>>>(pb.cell, P, e->g.id_start, e->d_vcnt);
+        KCHECK(e);
+        CU(e, cudaMemcpyAsync(channel_id, e->d_vcnt, sizeof(uint32_t) * P, cudaMemcpyDefault, s));
+    }
+    if (dist) CU(e, cudaMemcpyAsync(dist, pb.dist, sizeof(uint32_t) * P, cudaMemcpyDefault, s));
+    if (interval_ms) CU(e, cudaMemcpyAsync(interval_ms, pb.interval, sizeof(uint32_t) * P, cudaMemcpyDefault, s));
+    if (flags) CU(e, cudaMemcpyAsync(flags, pb.flags, P, cudaMemcpyDefault, s));
+    if (last_fanout_ns) CU(e, cudaMemcpyAsync(last_fanout_ns, pb.last, sizeof(int64_t) * P, cudaMemcpyDefault, s));
+    if (last_message_index) CU(e, cudaMemcpyAsync(last_message_index, pb.last_index, sizeof(uint64_t) * P, cudaMemcpyDefault, s));
+    CU(e, cudaStreamSynchronize(s));
+    return CHD_OK;
+}
+
+chd_status chd_get_query_status(chd_engine* e, uint32_t* status, uint32_t n) {
+    if (!e || !status) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    if (n > e->last_nq) n = e->last_nq;
+    CU(e, cudaMemcpyAsync(status, e->d_status, sizeof(uint32_t) * n, cudaMemcpyDefault, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    return CHD_OK;
+}
+
+chd_status chd_get_diff(chd_engine* e, uint32_t* new_sub, uint32_t* new_channel, uint32_t* unsub_sub, uint32_t* unsub_channel) {
+    if (!e) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    CU(e, cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    const uint32_t nn = e->h_ctr->n_sub_new, nu = e->h_ctr->n_unsub;
+    cudaStream_t s = e->stream;
+    if (new_sub) CU(e, cudaMemcpyAsync(new_sub, e->d_new_sub, sizeof(uint32_t) * nn, cudaMemcpyDefault, s));
+    if (new_channel) CU(e, cudaMemcpyAsync(new_channel, e->d_new_ch, sizeof(uint32_t) * nn, cudaMemcpyDefault, s));
+    if (unsub_sub) CU(e, cudaMemcpyAsync(unsub_sub, e->d_gone_sub, sizeof(uint32_t) * nu, cudaMemcpyDefault, s));
+    if (unsub_channel) CU(e, cudaMemcpyAsync(unsub_channel, e->d_gone_ch, sizeof(uint32_t) * nu, cudaMemcpyDefault, s));
+    CU(e, cudaStreamSynchronize(s));
+    return CHD_OK;
+}
+
+chd_status chd_get_visible(chd_engine* e, uint64_t* vis_off, uint32_t* vis_entity) {
+    if (!e) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    const uint32_t S = e->n_slots;
+    cudaStream_t s = e->stream;
+    if (vis_off) CU(e, cudaMemcpyAsync(vis_off, e->d_vis_off, sizeof(uint64_t) * ((uint64_t)S + 1), cudaMemcpyDefault, s));
+    if (vis_entity) {
+        uint64_t* h64 = (uint64_t*)e->h_u32;
+        CU(e, cudaMemcpyAsync(h64, e->d_vis_off + S, 8, cudaMemcpyDeviceToHost, s));
+        CU(e, cudaStreamSynchronize(s));
+        const uint64_t V = *h64;
+        if (V > e->lim.max_visible) return CHD_ERR_CAPACITY;
+        CU(e, cudaMemcpyAsync(vis_entity, e->d_vis, sizeof(uint32_t) * V, cudaMemcpyDefault, s));
+    }
+    CU(e, cudaStreamSynchronize(s));
+    return CHD_OK;
+}
+
+chd_status chd_get_due(chd_engine* e, chd_due* out, uint32_t cap) {
+    if (!e || !out) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    CU(e, cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    uint32_t n = e->h_ctr->n_due;
+    if (n > e->lim.max_due) return CHD_ERR_CAPACITY;
+    if (n > cap) n = cap;
+    CU(e, cudaMemcpyAsync(out, e->d_due, sizeof(chd_due) * n, cudaMemcpyDefault, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    return CHD_OK;
+}
+
+chd_status chd_get_handover(chd_engine* e, uint32_t* entity, uint32_t* src_channel, uint32_t* dst_channel, uint32_t cap) {
+    if (!e) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    uint32_t n = 0;
+    chd_status st = read_u32(e, &e->d_ctr->n_handover, &n);
+    if (st != CHD_OK) return st;
+    if (n > e->ho_cap) n = e->ho_cap;
+    if (n > cap) n = cap;
+    cudaStream_t s = e->stream;
+    if (entity) CU(e, cudaMemcpyAsync(entity, e->d_ho_entity, sizeof(uint32_t) * n, cudaMemcpyDefault, s));
+    if (src_channel) CU(e, cudaMemcpyAsync(src_channel, e->d_ho_src, sizeof(uint32_t) * n, cudaMemcpyDefault, s));
+    if (dst_channel) CU(e, cudaMemcpyAsync(dst_channel, e->d_ho_dst, sizeof(uint32_t) * n, cudaMemcpyDefault, s));
+    CU(e, cudaStreamSynchronize(s));
+    return CHD_OK;
+}
+
+chd_status chd_device_view(chd_engine* e, int which, void** d_ptr, uint64_t* count) {
+    if (!e || !d_ptr) return CHD_ERR_INVALID;
+    PairBuf& pb = e->pairs[e->cur];
+    uint64_t c = 0;
+    void* p = nullptr;
+    switch (which) {
+        case CHD_VIEW_CELL_START: p = e->d_cell_start; c = (uint64_t)e->g.cells + 2; break;
+        case CHD_VIEW_SORTED_ENTITY: p = e->d_sorted_ent; c = e->n_sorted; break;
+        case CHD_VIEW_ENT_CELL: p = e->d_key; c = e->n_own + e->n_halo; break;
+        case CHD_VIEW_PAIR_OFF: p = pb.off; c = (uint64_t)e->n_slots + 1; break;
+        case CHD_VIEW_PAIR_CHANNEL: p = pb.cell; c = e->lim.max_pairs; break;
+        case CHD_VIEW_PAIR_DIST: p = pb.dist; c = e->lim.max_pairs; break;
+        case CHD_VIEW_VIS_OFF: p = e->d_vis_off; c = (uint64_t)e->n_slots + 1; break;
+        case CHD_VIEW_VIS_ENTITY: p = e->d_vis; c = e->lim.max_visible; break;
+        case CHD_VIEW_DUE: p = e->d_due; c = e->lim.max_due; break;
+        default: return CHD_ERR_INVALID;
+    }
+    *d_ptr = p;
+    if (count) *count = c;
+    return CHD_OK;
+}
+
+/* ------------------------------------------------------------------ multi-GPU slab ---- */
+
+chd_status chd_set_slab(chd_engine* e, uint32_t col_lo, uint32_t col_hi, uint32_t halo) {
+    if (!e || col_lo >= col_hi || col_hi > e->g.cols) return CHD_ERR_INVALID;
+    e->g.col_lo = col_lo;
+    e->g.col_hi = col_hi;
+    e->g.halo = halo;
+    return CHD_OK;
+}
+
+chd_status chd_export_border(chd_engine* e, uint32_t* d_records, uint32_t cap_records, uint32_t* out_count) {
+    if (!e || !d_records || !out_count) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    chd_status st = chd_assign_cells(e);
+    if (st != CHD_OK) return st;
+    cudaStream_t s = e->stream;
+    const uint32_t n = e->n_own;
+    border_flag_kernel<<<blocks_for(n ? n : 1, 256), 256, 0, s>>>(e->g, e->d_key, n, e->d_bflag);
+    KCHECK(e);
+    SCAN(e, exclusive_scan<uint32_t, uint32_t>(e->d_bflag, e->d_boff, n, e->d_scan_scratch, s));
+    border_write_kernel<<<blocks_for(n ? n : 1, 256), 256, 0, s>>>(e->d_key, e->have_gid ? e->d_gid : nullptr, n, e->d_bflag, e->d_boff,
+                                                                    d_records, cap_records);
+    KCHECK(e);
+    st = read_u32(e, e->d_boff + n, out_count);
+    if (st != CHD_OK) return st;
+    if (*out_count > cap_records) {
+        e->fail("border export needs %u records > capacity %u", *out_count, cap_records);
+        return CHD_ERR_CAPACITY;
+    }
+    return CHD_OK;
+}
+
+chd_status chd_import_halo(chd_engine* e, const uint32_t* d_records, uint32_t n_records, uint32_t skip_first, uint32_t skip_count) {
+    if (!e || (n_records && !d_records)) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    if (!e->assigned) {
+        e->fail("chd_import_halo before chd_export_border / chd_assign_cells");
+        return CHD_ERR_STATE;
+    }
+    cudaStream_t s = e->stream;
+    if (n_records > e->lim.max_entities) {
+        e->fail("halo import of %u records > max_entities scratch %u", n_records, e->lim.max_entities);
+        return CHD_ERR_CAPACITY;
+    }
+    halo_flag_kernel<<<blocks_for(n_records ? n_records : 1, 256), 256, 0, s>>>(e->g, d_records, n_records, skip_first, skip_count, e->d_bflag);
+    KCHECK(e);
+    SCAN(e, exclusive_scan<uint32_t, uint32_t>(e->d_bflag, e->d_boff, n_records, e->d_scan_scratch, s));
+    uint32_t n_keep = 0;
+    chd_status st = read_u32(e, e->d_boff + n_records, &n_keep);
+    if (st != CHD_OK) return st;
+    if ((uint64_t)e->n_own + n_keep > e->lim.max_entities) {
+        e->fail("own %u + halo %u entities > max_entities %u", e->n_own, n_keep, e->lim.max_entities);
+        return CHD_ERR_CAPACITY;
+    }
+    if (!e->have_gid) {
+        e->fail("chd_import_halo requires global entity ids (chd_set_entity_ids)");
+        return CHD_ERR_STATE;
+    }
+    halo_append_kernel<<<blocks_for(n_records ? n_records : 1, 256), 256, 0, s>>>(d_records, n_records, e->d_bflag, e->d_boff, e->n_own, e->d_key,
+                                                                                  e->d_gid);
+    KCHECK(e);
+    e->n_halo = n_keep;
+    e->entities_dirty = true;
+    return CHD_OK;
+}
+
+/* ------------------------------------------------------------------ instrumentation ---- */
+
+uint64_t chd_launch_count(const chd_engine* e) { return e ? e->n_launch : 0; }
+
+chd_status chd_profile_enable(chd_engine* e, int on) {
+    if (!e) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    if (on && !e->ev) {
+        const size_t n = (size_t)CHD_STAGE_COUNT * chd_engine::EV_RING * 2;
+        e->ev = new cudaEvent_t[n]();
+        for (size_t i = 0; i < n; i++) CU(e, cudaEventCreate(&e->ev[i]));
+    }
+    CU(e, cudaStreamSynchronize(e->stream));
+    for (int s = 0; s < CHD_STAGE_COUNT; s++) e->stage_n[s] = 0;
+    e->profiling = on != 0;
+    return CHD_OK;
+}
+
+chd_status chd_profile_get(chd_engine* e, int stage, double* total_ms, uint64_t* samples) {
+    if (!e || stage < 0 || stage >= CHD_STAGE_COUNT || !total_ms || !samples) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    CU(e, cudaStreamSynchronize(e->stream));
+    const uint64_t n = e->stage_n[stage];
+    const uint64_t m = n < (uint64_t)chd_engine::EV_RING ? n : (uint64_t)chd_engine::EV_RING;
+    double tot = 0;
+    for (uint64_t i = n - m; i < n; i++) {
+        float ms = 0;
+        CU(e, cudaEventElapsedTime(&ms, e->evt(stage, i, 0), e->evt(stage, i, 1)));
+        tot += ms;
+    }
+    *total_ms = tot;
+    *samples = m;
+    return CHD_OK;
+}
+
+/* ------------------------------------------------------------------ host helpers ---- */
+
+uint32_t chd_get_adjacent_channels(const chd_grid_cfg* cfg, uint32_t channel_id, uint32_t* out8) {  // spatial.go:358-381
+    if (!cfg || !out8 || cfg->grid_cols == 0) return 0;
+    const uint32_t index = channel_id - cfg->channel_id_start;
+    const int64_t gx = index % cfg->grid_cols, gy = index / cfg->grid_cols;
+    uint32_t n = 0;
+    for (int64_t y = gy - 1; y <= gy + 1; y++) {
+        if (y < 0 || y >= (int64_t)cfg->grid_rows) continue;
+        for (int64_t x = gx - 1; x <= gx + 1; x++) {
+            if (x < 0 || x >= (int64_t)cfg->grid_cols) continue;
+            if (x == gx && y == gy) continue;
+            out8[n++] = (uint32_t)x + (uint32_t)y * cfg->grid_cols + cfg->channel_id_start;
+        }
+    }
+    return n;
+}
+
+chd_status chd_get_regions(const chd_grid_cfg* cfg, double* min_x, double* min_z, double* max_x, double* max_z, uint32_t* channel_id,
+                           uint32_t* server_index) {  // spatial.go:319-356
+    if (!cfg || cfg->server_cols == 0 || cfg->server_rows == 0) return CHD_ERR_INVALID;
+    uint32_t sgc = cfg->grid_cols / cfg->server_cols;
+    if (cfg->grid_cols % cfg->server_cols) sgc++;
+    uint32_t sgr = cfg->grid_rows / cfg->server_rows;
+    if (cfg->grid_rows % cfg->server_rows) sgr++;
+    for (uint32_t y = 0; y < cfg->grid_rows; y++)
+        for (uint32_t x = 0; x < cfg->grid_cols; x++) {
+            const uint32_t i = x + y * cfg->grid_cols;
+            if (min_x) min_x[i] = cfg->world_offset_x + cfg->grid_width * (double)x;
+            if (min_z) min_z[i] = cfg->world_offset_z + cfg->grid_height * (double)y;
+            if (max_x) max_x[i] = cfg->world_offset_x + cfg->grid_width * (double)(x + 1);
+            if (max_z) max_z[i] = cfg->world_offset_z + cfg->grid_height * (double)(y + 1);
+            if (channel_id) channel_id[i] = cfg->channel_id_start + i;
+            if (server_index) server_index[i] = (x / sgc) + (y / sgr) * cfg->server_cols;
+        }
+    return CHD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+// chd_fanout.cuh — Channel.tickData (data.go:175-291) for ALL spatial channels in one launch: one thread per
+// (subscriber, cell) subscription pair runs the reference's per-connection state machine
+//   while t >= lastFanOutTime + interval:           (the queue re-sort at data.go:270-286 re-visits a
+//       first time  -> FULL, last = t                connection until it is no longer due: an effective loop)
+//       otherwise   -> scan the cell's update ring in insertion order, select entries with
+//                      lastUpdateTime <= arrival <= nextFanOutTime (skipping own updates), lastUpdateTime
+//                      advancing to every picked arrival; last += interval
+// Two passes over the same code: COUNT (no side effects) -> exclusive scan -> WRITE (emits chd_due records in
+// (slot, cell, step) order and commits the state).
+#pragma once
+#include "chd_interest.cuh"
+
+namespace chd {
+
+struct RingDev {
+    const uint32_t* off;        // [C+1]
+    const int64_t* arrival;     // insertion order per cell
+    const uint32_t* sender;
+    const uint64_t* index;
+    const uint64_t* channel_msg_index;  // [C] or nullptr
+};
+
+constexpr uint32_t FANOUT_MAX_STEPS = 1u << 16;
+
+template <bool WRITE>
+__global__ void __launch_bounds__(128)
+    fanout_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, PairBuf pb, const uint32_t* __restrict__ conn_id,
+                  RingDev ring, int64_t t, uint32_t id_start, uint32_t* __restrict__ due_cnt, const uint32_t* __restrict__ due_off,
+                  chd_due* __restrict__ due, uint32_t due_cap) {
+    const uint64_t n = min((uint64_t)*n_pairs_ptr, pair_cap);
+    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < n; p += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t interval = pb.interval[p];
+        const int64_t step_ns = (int64_t)interval * 1000000ll;  // ChannelTime.AddMs (channel.go:30-32)
+        int64_t last = pb.last[p];
+        uint32_t n_out = 0;
+        if (t < last + step_ns) {  // not due: the common case, no further state is read
+            if (!WRITE) due_cnt[p] = 0;
+            continue;
+        }
+        uint8_t flags = pb.flags[p];
+        uint64_t last_index = pb.last_index[p];
+        const uint32_t c = pb.cell[p];
+        const uint32_t s = pb.sub[p];
+        const uint32_t me = conn_id[s];
+        const bool skip_self = flags & PF_SKIP_SELF;
+        const uint32_t r0 = ring.off[c], r1 = ring.off[c + 1];
+        uint32_t o = WRITE ? due_off[p] : 0u;
+        const bool can_write = WRITE && due_off[n] <= due_cap;
+        const uint32_t max_steps = interval ? FANOUT_MAX_STEPS : 1u;  // interval 0: the reference never terminates
+        for (uint32_t step = 0; step < max_steps; step++) {
+            const int64_t next = last + step_ns;  // data.go:205
+            if (t < next) break;
+            int64_t latest = next;
+            if (!(flags & PF_HAD_FIRST)) {  // data.go:218-224: whole channel data
+                flags |= PF_HAD_FIRST;
+                last_index = ring.channel_msg_index ? ring.channel_msg_index[c] : 0ull;
+                latest = t;
+                if (can_write) {
+                    chd_due d;
+                    d.sub = s; d.channel_id = c + id_start; d.kind = 0; d.n_selected = 0; d.first_sel = 0; d.last_sel = 0;
+                    d.sel_hash = 0; d.last_message_index = last_index; d.window_hi = next;
+                    due[o] = d;
+                }
+                o++;
+                n_out++;
+            } else if (r1 > r0) {  // data.go:225-265
+                int64_t last_update = 0;
+                if (last >= last_update) last_update = last;
+                uint32_t nsel = 0, first = 0, lastsel = 0;
+                uint64_t hash = 0;
+                for (uint32_t k = r0; k < r1; k++) {
+                    if (skip_self && ring.sender[k] == me) continue;
+                    const int64_t a = ring.arrival[k];
+                    if (a >= last_update && a <= next) {
+                        if (!nsel) first = k - r0;
+                        lastsel = k - r0;
+                        nsel++;
+                        const uint64_t mi = ring.index[k];
+                        hash += mi;
+                        last_update = a;
+                        last_index = mi;
+                    }
+                }
+                if (nsel) {
+                    if (can_write) {
+                        chd_due d;
+                        d.sub = s; d.channel_id = c + id_start; d.kind = 1; d.n_selected = nsel; d.first_sel = first; d.last_sel = lastsel;
+                        d.sel_hash = hash; d.last_message_index = last_index; d.window_hi = next;
+                        due[o] = d;
+                    }
+                    o++;
+                    n_out++;
+                }
+            }
+            last = latest;  // data.go:268
+        }
+        if (WRITE) {
+            if (!can_write) continue;  // due list overflow: keep the state so the tick can be retried with a larger cap
+            pb.last[p] = last;
+            pb.flags[p] = flags;
+            pb.last_index[p] = last_index;
+        } else {
+            due_cnt[p] = n_out;
+        }
+    }
+}
+
+__global__ void due_total_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, const uint32_t* __restrict__ due_off,
+                                 uint32_t due_cap, Counters* __restrict__ ctr) {
+    const uint64_t n = min((uint64_t)*n_pairs_ptr, pair_cap);
+    const uint32_t total = due_off[n];
+    ctr->n_due = total;
+    ctr->required_due = total;
+    if (total > due_cap) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_DUE);
+}
+
+}  // namespace chd

@@ -1,0 +1,99 @@
+// chd_misc.cuh — small bookkeeping kernels (counters, id conversion, multi-GPU border records).
+#pragma once
+#include "chd_interest.cuh"
+
+namespace chd {
+
+__global__ void cell_key_to_id_kernel(uint32_t* __restrict__ k, uint32_t n, uint32_t cells, uint32_t id_start) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) k[i] = k[i] >= cells ? 0u : k[i] + id_start;
+}
+
+__global__ void set_in_world_kernel(const uint32_t* __restrict__ cell_start, uint32_t cells, Counters* __restrict__ ctr) {
+    ctr->n_entities_in_world = cell_start[cells];
+}
+
+__global__ void window_overflow_kernel(const uint64_t* __restrict__ win_off, uint32_t n, uint64_t cap, Counters* __restrict__ ctr) {
+    const uint64_t need = win_off[n];
+    ctr->required_window_cells = need;
+    if (need > cap) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_WINDOW);
+}
+
+__global__ void pairs_total_kernel(const uint32_t* __restrict__ off, uint32_t n_slots, uint64_t cap, Counters* __restrict__ ctr) {
+    const uint64_t p = off[n_slots];
+    ctr->n_pairs = p;
+    ctr->required_pairs = p;
+    if (p > cap) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_PAIRS);
+}
+
+__global__ void narrow_offsets_kernel(const uint64_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)in[i];
+}
+
+__global__ void add_const_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t c, uint32_t* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] + c;
+}
+
+__global__ void clamp_ring_off_kernel(uint32_t* __restrict__ off, uint32_t n, uint32_t total) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && off[i] > total) off[i] = total;
+}
+
+// ---- X-slab sharding.  A record is (global entity id, cell index).
+// An own entity is exported when another rank may need it: its column is not strictly interior to this slab.
+__global__ void border_flag_kernel(GridDev g, const uint32_t* __restrict__ key, uint32_t n, uint32_t* __restrict__ flag) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t k = key[i];
+    uint32_t f = 0;
+    if (k < g.cells) {
+        const uint32_t col = k % g.cols;
+        const bool interior = col >= g.col_lo + g.halo && col + g.halo < g.col_hi;
+        const bool left_edge_open = g.col_lo > 0, right_edge_open = g.col_hi < g.cols;
+        if (!interior) {
+            // columns near a world edge with no neighbour beyond need no export
+            const bool near_left = col < g.col_lo + g.halo, near_right = col + g.halo >= g.col_hi;
+            f = (near_left && left_edge_open) || (near_right && right_edge_open) || col < g.col_lo || col >= g.col_hi;
+        }
+    }
+    flag[i] = f;
+}
+
+__global__ void border_write_kernel(const uint32_t* __restrict__ key, const uint32_t* __restrict__ gid, uint32_t n,
+                                    const uint32_t* __restrict__ flag, const uint32_t* __restrict__ off, uint32_t* __restrict__ out,
+                                    uint32_t cap) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flag[i]) return;
+    const uint32_t o = off[i];
+    if (o < cap) {
+        out[2 * o] = gid ? gid[i] : i;
+        out[2 * o + 1] = key[i];
+    }
+}
+
+// keep gathered records whose column lies in this rank's extended range and which another rank exported
+__global__ void halo_flag_kernel(GridDev g, const uint32_t* __restrict__ rec, uint32_t n, uint32_t skip_first, uint32_t skip_count,
+                                 uint32_t* __restrict__ flag) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t cell = rec[2 * i + 1];
+    uint32_t f = 0;
+    if (cell < g.cells && !(i >= skip_first && i - skip_first < skip_count)) {
+        const uint32_t col = cell % g.cols;
+        f = (col + g.halo >= g.col_lo) && (col < g.col_hi + g.halo);
+    }
+    flag[i] = f;
+}
+
+__global__ void halo_append_kernel(const uint32_t* __restrict__ rec, uint32_t n, const uint32_t* __restrict__ flag,
+                                   const uint32_t* __restrict__ off, uint32_t base, uint32_t* __restrict__ key, uint32_t* __restrict__ gid) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flag[i]) return;
+    const uint32_t o = base + off[i];
+    gid[o] = rec[2 * i];
+    key[o] = rec[2 * i + 1];
+}
+
+}  // namespace chd

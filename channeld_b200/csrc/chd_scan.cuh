@@ -1,0 +1,121 @@
+// chd_scan.cuh — device-wide exclusive prefix sums (u32 counts -> u32/u64 offsets), reduce-then-scan.
+// out has n+1 entries (out[n] = total).  Deterministic.  Scratch comes from the caller's arena.
+// exclusive_scan returns the number of kernels it launched.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace chd {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;  // 4096
+
+template <typename T>
+__device__ __forceinline__ T warp_incl_scan(T v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T o = __shfl_up_sync(0xffffffffu, v, d);
+        if ((threadIdx.x & 31) >= d) v += o;
+    }
+    return v;
+}
+
+// block-wide exclusive scan of one value per thread; returns exclusive prefix, total in `total`
+template <typename T>
+__device__ __forceinline__ T block_excl_scan(T v, T& total) {
+    __shared__ T warp_sums[SCAN_THREADS / 32];
+    __shared__ T tot;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    T incl = warp_incl_scan(v);
+    if (lane == 31) warp_sums[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        T s = lane < SCAN_THREADS / 32 ? warp_sums[lane] : T(0);
+        T si = warp_incl_scan(s);
+        if (lane < SCAN_THREADS / 32) warp_sums[lane] = si - s;
+        if (lane == SCAN_THREADS / 32 - 1) tot = si;
+    }
+    __syncthreads();
+    T res = incl - v + warp_sums[w];
+    total = tot;
+    __syncthreads();
+    return res;
+}
+
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(SCAN_THREADS)
+    scan_tile_sums(const TIn* __restrict__ in, TOut* __restrict__ sums, uint64_t n, const uint32_t* __restrict__ n_ptr) {
+    if (n_ptr) n = min(n, (uint64_t)*n_ptr);
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
+    TOut acc = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        const uint64_t i = base + (uint64_t)k * SCAN_THREADS + threadIdx.x;
+        if (i < n) acc += (TOut)in[i];
+    }
+    TOut total;
+    block_excl_scan<TOut>(acc, total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+// Scans tile `blockIdx.x`; adds tile_base[blockIdx.x] (exclusive tile offsets) when given.
+// The block that owns element n-1 also writes out[n] = total.
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(SCAN_THREADS)
+    scan_tiles(const TIn* __restrict__ in, TOut* __restrict__ out, uint64_t n, const TOut* __restrict__ tile_base,
+               const uint32_t* __restrict__ n_ptr) {
+    if (n_ptr) n = min(n, (uint64_t)*n_ptr);
+    if ((uint64_t)blockIdx.x * SCAN_TILE >= n && !(n == 0 && blockIdx.x == 0)) return;
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    TOut v[SCAN_ITEMS];
+    TOut acc = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        const uint64_t i = base + k;
+        v[k] = i < n ? (TOut)in[i] : TOut(0);
+        acc += v[k];
+    }
+    TOut total;
+    TOut pre = block_excl_scan<TOut>(acc, total);
+    if (tile_base) pre += tile_base[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        const uint64_t i = base + k;
+        if (i < n) out[i] = pre;
+        pre += v[k];
+        if (i + 1 == n) out[n] = pre;
+    }
+    if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) out[0] = 0;
+}
+
+// scratch must hold scan_scratch_elems<TOut>(n) elements of TOut
+inline uint64_t scan_scratch_elems(uint64_t n) {
+    uint64_t total = 0;
+    uint64_t t = (n + SCAN_TILE - 1) / SCAN_TILE;
+    while (t > 1) {
+        total += t + 1;
+        t = (t + SCAN_TILE - 1) / SCAN_TILE;
+    }
+    return total + 2;
+}
+
+template <typename TIn, typename TOut>
+inline int exclusive_scan(const TIn* in, TOut* out, uint64_t n, TOut* scratch, cudaStream_t st,
+                          const uint32_t* n_ptr = nullptr) {
+    // n is the host-known upper bound; when n_ptr is given the live length is min(n, *n_ptr) (device side),
+    // so no host sync is needed to size the launch.  Tiles beyond the live length contribute zeros.
+    const uint64_t tiles = n == 0 ? 1 : (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (tiles == 1) {
+        scan_tiles<TIn, TOut><<<1, SCAN_THREADS, 0, st>>>(in, out, n, nullptr, n_ptr);
+        return 1;
+    }
+    TOut* sums = scratch;             // [tiles+1]: after the recursive scan, exclusive tile offsets
+    TOut* next = scratch + tiles + 1;
+    scan_tile_sums<TIn, TOut><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, sums, n, n_ptr);
+    const int inner = exclusive_scan<TOut, TOut>(sums, sums, tiles, next, st);  // in-place is safe: items are read before written
+    scan_tiles<TIn, TOut><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, out, n, sums, n_ptr);
+    return inner + 2;  // kernels launched
+}
+
+}  // namespace chd

@@ -1,0 +1,271 @@
+/*
+ * chd_gpu.h — C ABI of the B200-native spatial interest-management + fan-out engine (libchd_b200.so).
+ *
+ * This is the drop-in boundary behind channeld's SpatialController plugin surface
+ * (reference: channeldorg/channeld @ 61fa8add, pkg/channeld/spatial.go:17-35).  A cgo shim binds exactly
+ * these entry points (go/gpucontroller.go).  Plain pointers and sizes only; no C++/torch
+ * types; integer status codes; no exceptions cross the ABI; the engine never retains caller pointers after
+ * a call returns (cgo rule).  Pointer arguments may be host (pageable or pinned) or device pointers unless
+ * stated otherwise: copies use cudaMemcpyDefault (UVA) on the engine's stream.
+ *
+ * Threading: one tick driver per engine handle (thread-compatible).  chd_cell_of / chd_query_channel_ids
+ * take an internal mutex and may be called from any thread (the reference calls GetChannelId /
+ * QueryChannelIds concurrently from channel goroutines, spatial.go:20-29).
+ *
+ * There is NO CPU fallback: every compute entry point runs sm_100a kernels and returns CHD_ERR_CUDA if no
+ * device is usable.
+ */
+#ifndef CHD_GPU_H
+#define CHD_GPU_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHD_ABI_VERSION 1
+
+typedef struct chd_engine chd_engine;
+
+typedef enum chd_status {
+    CHD_OK = 0,
+    CHD_ERR_INVALID = 1,  /* bad argument / config (LoadConfig validation, spatial.go:146-157) */
+    CHD_ERR_CUDA = 2,     /* CUDA runtime failure or no device; see chd_last_error */
+    CHD_ERR_CAPACITY = 3, /* an output or scratch capacity in chd_limits was exceeded; summary.required_* says by how much */
+    CHD_ERR_STATE = 4     /* call order violated (e.g. emit before build) */
+} chd_status;
+
+/* Grid constants.  Replaces StaticGrid2DSpatialController's config fields (spatial.go:89-124, JSON in
+ * config/spatial_static_*.json) + GlobalSettings.SpatialChannelIdStart (settings.go:94). */
+typedef struct chd_grid_cfg {
+    double   world_offset_x, world_offset_z;
+    double   grid_width, grid_height;
+    uint32_t grid_cols, grid_rows;
+    uint32_t server_cols, server_rows;
+    uint32_t server_interest_border_size;
+    uint32_t channel_id_start; /* 0x10000 */
+} chd_grid_cfg;
+
+/* Capacities (device allocations are made once in chd_create; nothing allocates on the tick path). */
+typedef struct chd_limits {
+    uint32_t max_entities;
+    uint32_t max_subscribers;
+    uint32_t max_queries;       /* per chd_update_interest / chd_query_channel_ids batch */
+    uint32_t max_spots;         /* total SpotsAOI spots per batch */
+    uint64_t max_pairs;         /* (subscriber, cell) subscriptions alive at once */
+    uint64_t max_window_cells;  /* query scratch: sum over the batch of each query's cell bounding box */
+    uint64_t max_visible;       /* expanded visible-entity list entries per tick */
+    uint32_t max_ring_entries;  /* total update-ring entries over all cells */
+    uint32_t max_due;           /* fan-out decisions per tick */
+    /* SPATIAL channel-type settings the reference reads from GlobalSettings.ChannelSettings
+     * (settings.go:97-103,237-243; subscription.go:21-31): */
+    uint32_t default_fanout_interval_ms; /* used when dist matches no damping row (message_spatial.go:68-72) */
+    int32_t  default_fanout_delay_ms;
+} chd_limits;
+
+/* Fills `lim` with capacities sized for n_entities / n_subscribers (helper; edit before chd_create). */
+void chd_default_limits(const chd_grid_cfg* cfg, uint32_t n_entities, uint32_t n_subscribers, chd_limits* lim);
+
+/* Replaces InitSpatialController + LoadConfig (spatial.go:40-74,141-159).  Validates like LoadConfig except
+ * that ServerInterestBorderSize == 0 is accepted: the reference discards that error (spatial.go:68) and both
+ * benchmark configs rely on it.  `device` = CUDA ordinal. */
+chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim, int device, chd_engine** out);
+void chd_destroy(chd_engine* e);
+/* Last error text of this engine (or of chd_create when e == NULL).  Valid until the next call. */
+const char* chd_last_error(const chd_engine* e);
+/* Run all work on this cudaStream_t (default: a private non-blocking stream).  torch passes its current stream. */
+chd_status chd_set_stream(chd_engine* e, void* cuda_stream);
+/* Blocks until all work queued on the engine stream has finished. */
+chd_status chd_sync(chd_engine* e);
+
+/* Pinned host memory for the per-tick staging buffers (plain C memory, legal to hold from Go). */
+void* chd_alloc_pinned(uint64_t bytes);
+void chd_free_pinned(void* p);
+
+/* ---- GetChannelId, batched (spatial.go:161-180; the batch form is handleQuerySpatialChannel,
+ * message_spatial.go:335-370).  out_channel_id[i] = channel id, or 0 where the reference returns an error
+ * (outside [0,cols) x [0,rows), NaN, +-Inf, huge).  Synchronous. */
+chd_status chd_cell_of(chd_engine* e, const double* x, const double* z, uint32_t n, uint32_t* out_channel_id);
+
+/* ---- entity positions (SoA).  Replaces the per-cell entity maps the reference keeps in
+ * SpatialChannelData.Entities (pkg/unrealpb/extension.go:38-62) fed by AddEntity/RemoveEntity
+ * (spatial.go:606-609,702-736).  Entity i has id i (the host maps it to EntityChannelIdStart + i). */
+chd_status chd_set_entities(chd_engine* e, const double* x, const double* z, uint32_t n);
+/* Device pointers of the resident position arrays, for producers that write positions on the GPU. */
+chd_status chd_entity_buffers(chd_engine* e, double** d_x, double** d_z, uint32_t* n);
+
+/* Declares that the resident position arrays hold n entities (after writing them through chd_entity_buffers). */
+chd_status chd_set_entity_count(chd_engine* e, uint32_t n);
+
+/* GetChannelId for every resident entity (the first half of chd_build; idempotent until positions change).
+ * Also runs handover detection against the previous assignment. */
+chd_status chd_assign_cells(chd_engine* e);
+
+/* Spatial-hash build: cell id per entity (GetChannelId), stable counting sort into the cell CSR
+ * (cell asc, entity id asc), and — when a previous build exists — handover detection, the prefix of
+ * Notify (spatial.go:612-626): entities whose cell changed since the previous build. */
+chd_status chd_build(chd_engine* e);
+
+/* ---- subscribers: slot s in [0,n) <-> connection id (Connection.Id(), used for SkipSelfUpdateFanOut,
+ * data.go:240).  Resets all subscriptions. */
+chd_status chd_set_subscribers(chd_engine* e, const uint32_t* conn_id, uint32_t n);
+
+enum { CHD_AOI_SPOTS = 1, CHD_AOI_BOX = 2, CHD_AOI_SPHERE = 4, CHD_AOI_CONE = 8 };
+
+/* A batch of SpatialInterestQuery (channeld.proto:436-469), SoA.  Arrays of kinds no query uses may be
+ * NULL.  Y components are not carried: the 2-D grid never reads them (spatial.go:205,237,272).
+ * At most one query per subscriber slot per batch (the host coalesces; the reference would apply them
+ * in arrival order and only the last one's subscriptions survive). */
+typedef struct chd_query_batch {
+    uint32_t        n;
+    const uint32_t* sub;   /* [n] subscriber slot (UpdateSpatialInterestMessage.connId -> slot); ignored by chd_query_channel_ids */
+    const uint8_t*  kind;  /* [n] CHD_AOI_* mask, or NULL = all CHD_AOI_SPHERE */
+    const double *sph_cx, *sph_cz, *sph_r;
+    const double *box_cx, *box_cz, *box_ex, *box_ez;
+    const double *cone_cx, *cone_cz, *cone_dx, *cone_dz, *cone_angle, *cone_r;
+    const uint32_t* spot_off;    /* [n+1] CSR into spot_* (NULL when no query has spots) */
+    const uint32_t* spot_ndist;  /* [n] how many leading spots of query i carry an explicit dist (len(Dists)) */
+    const double *  spot_x, *spot_z;
+    const uint32_t* spot_dist;   /* [spot_off[n]]; 0xFFFFFFFF is reserved */
+} chd_query_batch;
+
+/* Per-query status (the reference's error returns, spatial.go:208-215,228-231,...). */
+enum {
+    CHD_Q_OK = 0,
+    CHD_Q_ERR_OUT_OF_WORLD = 1, /* centre of a box/sphere/cone outside the world: (nil, err) */
+    CHD_Q_ERR_BAD_STEP = 2,     /* radius / extent <= 0 */
+    CHD_Q_ERR_ITER_BOUND = 5,   /* step absorbed by a huge coordinate: the reference would loop forever */
+    CHD_Q_ERR_ANGLE_RANGE = 6   /* |cone angle| >= 2^29: Go switches to Payne-Hanek reduction, not reproduced */
+};
+
+/* ---- QueryChannelIds, batched and stateless (spatial.go:182-317).  CSR output, entries of one query sorted
+ * by channel id ascending (the reference returns a Go map: order is unspecified, parity is on keys+dists).
+ * out_off[n+1], out_status[n]; out_channel_id/out_dist sized `cap`.  Synchronous. */
+chd_status chd_query_channel_ids(chd_engine* e, const chd_query_batch* q, uint32_t* out_status, uint32_t* out_off,
+                                 uint32_t* out_channel_id, uint32_t* out_dist, uint64_t cap);
+
+/* ---- handleUpdateSpatialInterest, batched (message_spatial.go:41-129): query -> damping
+ * (message_spatial.go:16-38) -> diff against the subscriber's current spatial subscriptions (util.go:105-113)
+ * -> SubscribeToChannel / UnsubscribeFromChannel state changes (subscription.go:34-125): new pairs start with
+ * lastFanOutTime = now_ns + delay, hadFirstFanOut = false; kept pairs keep their fan-out state and take the
+ * new interval; a query that errors leaves that subscriber's subscriptions untouched (message_spatial.go:60-63).
+ * Asynchronous (stream-ordered). */
+chd_status chd_update_interest(chd_engine* e, const chd_query_batch* q, int64_t now_ns);
+
+/* ---- expanded per-subscriber visible-entity lists: for each subscriber the concatenation, in channel-id
+ * order, of the entity lists of its subscribed cells.  Asynchronous. */
+chd_status chd_emit_visible(chd_engine* e);
+
+/* ---- update rings: the per-channel updateMsgBuffer metadata (data.go:46-51) in insertion order, CSR by cell
+ * index (channel id - channel_id_start): ring_off[cells+1], n_entries = ring_off[cells].  channel_msg_index[cells] = ChannelData.msgIndex
+ * (data.go:25,158) or NULL for zeros.  The host owns OnUpdate/eviction (data.go:149-173): payload merging is
+ * opaque protobuf work. */
+chd_status chd_set_rings(chd_engine* e, const uint32_t* ring_off, uint32_t n_entries, const int64_t* arrival_ns,
+                         const uint32_t* sender_conn_id, const uint64_t* message_index, const uint64_t* channel_msg_index);
+
+/* One fan-out decision = one fanOutDataUpdate call of the reference (data.go:221,263). */
+typedef struct chd_due {
+    uint32_t sub;          /* subscriber slot */
+    uint32_t channel_id;   /* spatial channel */
+    uint32_t kind;         /* 0 = FULL channel data (first fan-out, data.go:218-224), 1 = accumulated UPDATE */
+    uint32_t n_selected;   /* UPDATE: ring entries merged (data.go:246-256) */
+    uint32_t first_sel, last_sel; /* ring positions (0-based within the cell's ring) of the first/last merged entry */
+    uint64_t sel_hash;     /* sum of merged entries' messageIndex mod 2^64 (lets the host verify its own selection) */
+    uint64_t last_message_index; /* foc.lastMessageIndex after the step */
+    int64_t  window_hi;    /* nextFanOutTime of the step: entries with lastUpdateTime <= arrival <= window_hi */
+} chd_due;
+
+/* ---- Channel.tickData for every spatial channel in one launch (data.go:175-291; replaces the per-channel
+ * goroutine loop channel.go:358-387).  Per (subscriber, cell) pair: while t >= lastFanOutTime + interval
+ * { first time: FULL, last = t; else select ring entries in [max(last,prev picked), last+interval] skipping
+ * own updates, last += interval }.  All cells share one time origin (documented deviation: the reference
+ * gives each channel its own startTime, channel.go:178).  Asynchronous. */
+chd_status chd_fanout_tick(chd_engine* e, int64_t t_ns);
+
+/* Counters of the work queued since the last summary; read back with ONE small device->host copy. */
+typedef struct chd_tick_summary {
+    uint64_t n_pairs;          /* live (subscriber, cell) subscriptions */
+    uint64_t n_visible;        /* entries of the expanded visible list */
+    uint32_t n_entities_in_world;
+    uint32_t n_query_errors;
+    uint32_t n_sub_new, n_unsub, n_kept;
+    uint32_t n_due;
+    uint32_t n_handover;
+    uint32_t overflow;         /* bitmask of CHD_OVF_*; outputs of an overflowed stage are truncated/invalid */
+    uint64_t required_pairs, required_window_cells, required_visible;
+    uint32_t required_due;
+    uint32_t reserved;
+} chd_tick_summary;
+enum { CHD_OVF_PAIRS = 1, CHD_OVF_WINDOW = 2, CHD_OVF_VISIBLE = 4, CHD_OVF_DUE = 8 };
+
+/* Synchronises the stream and returns the counters.  CHD_ERR_CAPACITY if any overflow bit is set. */
+chd_status chd_summary(chd_engine* e, chd_tick_summary* out);
+
+/* ---- Channel.Tick for all spatial channels (channel.go:358-387), batched: build (if entities changed) ->
+ * update_interest(q) (if q != NULL) -> emit_visible (flags & CHD_TICK_EMIT) -> fanout_tick(t_ns)
+ * (flags & CHD_TICK_FANOUT) -> summary.  One stream, no intermediate host sync. */
+enum { CHD_TICK_BUILD = 1, CHD_TICK_EMIT = 2, CHD_TICK_FANOUT = 4, CHD_TICK_ALL = 7 };
+chd_status chd_tick(chd_engine* e, const chd_query_batch* q, int64_t t_ns, uint32_t flags, chd_tick_summary* out);
+
+/* ---- results.  Each copies to caller memory (host or device) on the engine stream and synchronises.
+ * Pass NULL for arrays you do not need.  Counts come from chd_summary. */
+/* cell CSR: cell_start[cells+1], sorted_entity[n_entities_in_world] */
+chd_status chd_get_cells(chd_engine* e, uint32_t* cell_start, uint32_t* sorted_entity);
+/* subscriptions CSR by subscriber slot: pair_off[n_subscribers+1]; per pair channel id, dist, interval ms,
+ * flags (bit0 hadFirstFanOut, bit1 subscribed by the last update_interest, bit2 skipSelf), lastFanOutTime */
+chd_status chd_get_pairs(chd_engine* e, uint32_t* pair_off, uint32_t* channel_id, uint32_t* dist, uint32_t* interval_ms,
+                         uint8_t* flags, int64_t* last_fanout_ns, uint64_t* last_message_index);
+/* status per query of the last chd_update_interest batch */
+chd_status chd_get_query_status(chd_engine* e, uint32_t* status, uint32_t n);
+/* interest diff of the last update: (subscriber slot, channel id) lists, (slot asc, channel asc) */
+chd_status chd_get_diff(chd_engine* e, uint32_t* new_sub, uint32_t* new_channel, uint32_t* unsub_sub, uint32_t* unsub_channel);
+/* visible lists: vis_off[n_subscribers+1] (u64), vis_entity[n_visible] */
+chd_status chd_get_visible(chd_engine* e, uint64_t* vis_off, uint32_t* vis_entity);
+/* fan-out decisions of the last chd_fanout_tick, ordered by (slot asc, channel asc, step asc) */
+chd_status chd_get_due(chd_engine* e, chd_due* out, uint32_t cap);
+/* handover candidates of the last build: entity, src channel id, dst channel id (0 = left/entered the world) */
+chd_status chd_get_handover(chd_engine* e, uint32_t* entity, uint32_t* src_channel, uint32_t* dst_channel, uint32_t cap);
+
+/* Device-resident views (valid until the next call that rewrites them) for consumers that stay on the GPU. */
+enum {
+    CHD_VIEW_CELL_START = 0, CHD_VIEW_SORTED_ENTITY, CHD_VIEW_ENT_CELL, CHD_VIEW_PAIR_OFF, CHD_VIEW_PAIR_CHANNEL,
+    CHD_VIEW_PAIR_DIST, CHD_VIEW_VIS_OFF, CHD_VIEW_VIS_ENTITY, CHD_VIEW_DUE
+};
+chd_status chd_device_view(chd_engine* e, int which, void** d_ptr, uint64_t* count);
+
+/* ---- multi-GPU X-slab sharding.  The engine owns grid columns [col_lo, col_hi) and serves
+ * queries whose cells lie in [col_lo-halo, col_hi+halo).  After chd_build, chd_export_border writes the
+ * (entity id, cell index) records of the entities in this rank's outermost `halo` columns on each side into a
+ * caller-provided DEVICE buffer (2 x u32 per record; pre-fill with 0xFFFFFFFF as padding) for the all-gather;
+ * chd_import_halo takes the gathered records of all ranks (records [skip_first, skip_first+skip_count) are this
+ * rank's own and ignored), keeps those whose column lies in [col_lo-halo, col_hi+halo) and appends them as
+ * position-less halo entities; the following chd_build sorts own + halo entities into the cell CSR.
+ * Call order per tick: chd_set_entities -> chd_export_border (runs chd_assign_cells) -> all-gather ->
+ * chd_import_halo -> chd_build.  Entity ids are global: set with chd_set_entity_ids. */
+chd_status chd_set_slab(chd_engine* e, uint32_t col_lo, uint32_t col_hi, uint32_t halo);
+chd_status chd_set_entity_ids(chd_engine* e, const uint32_t* global_id, uint32_t n);
+chd_status chd_export_border(chd_engine* e, uint32_t* d_records, uint32_t cap_records, uint32_t* out_count);
+chd_status chd_import_halo(chd_engine* e, const uint32_t* d_records, uint32_t n_records, uint32_t skip_first, uint32_t skip_count);
+
+/* ---- control-plane helpers kept for interface completeness (pure integer/config math on the host; not part
+ * of the data-parallel path): GetAdjacentChannels (spatial.go:358-381) and GetRegions (spatial.go:319-356). */
+uint32_t chd_get_adjacent_channels(const chd_grid_cfg* cfg, uint32_t channel_id, uint32_t* out8);
+chd_status chd_get_regions(const chd_grid_cfg* cfg, double* min_x, double* min_z, double* max_x, double* max_z,
+                           uint32_t* channel_id, uint32_t* server_index);
+/* dist -> FanOutIntervalMs (message_spatial.go:16-38); the same table the kernels use. */
+uint32_t chd_damping_interval_ms(uint32_t dist, uint32_t default_ms);
+
+/* ---- instrumentation.  chd_launch_count: kernels launched by this engine so far.  chd_profile_enable(1)
+ * makes every stage record a CUDA-event pair on the engine stream (the last 1024 samples are kept);
+ * chd_profile_get synchronises and returns the summed device time of a stage.  CHD_STAGE_EMIT_KERNEL brackets
+ * exactly the emit_visible kernel (the dominant HBM term; bench.py's roofline uses it). */
+enum { CHD_STAGE_BUILD = 0, CHD_STAGE_INTEREST, CHD_STAGE_EMIT, CHD_STAGE_EMIT_KERNEL, CHD_STAGE_FANOUT, CHD_STAGE_COUNT };
+uint64_t chd_launch_count(const chd_engine* e);
+chd_status chd_profile_enable(chd_engine* e, int on);
+chd_status chd_profile_get(chd_engine* e, int stage, double* total_ms, uint64_t* samples);
+
+uint32_t chd_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,89 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds for sm_100a, loads, and exports every
+symbol include/chd_gpu.h declares.  No compute calls (there is no GPU in the build container)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "chd_gpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(chd_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from channeld_b200 import capi
+
+    L = capi.lib()
+    names = _declared()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(L, n), "libchd_b200.so does not export %s" % n
+    assert sorted(capi.SYMBOLS) == names
+    assert L.chd_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    from channeld_b200 import capi
+
+    assert C.sizeof(capi.GridCfg) == 4 * 8 + 6 * 4
+    assert C.sizeof(capi.Limits) == 4 * 4 + 3 * 8 + 4 * 4
+    assert C.sizeof(capi.Due) == 48
+    assert C.sizeof(capi.TickSummary) == 2 * 8 + 8 * 4 + 3 * 8 + 2 * 4
+    assert C.sizeof(capi.QueryBatch) == 8 + 20 * 8
+
+
+def test_host_helpers_match_oracle(oracle):
+    """GetAdjacentChannels / GetRegions / damping are plain host integer math in the library: checked here."""
+    from channeld_b200 import capi
+    from channeld_b200.engine import grid_cfg
+    from tests._oracle import make_grid
+
+    L = capi.lib()
+    for g in [(0, 0, 10, 10, 1, 1, 1, 1), (-5, -5, 5, 5, 2, 2, 1, 1), (-40, -60, 20, 40, 4, 3, 2, 3), (-15000, -15000, 2000, 2000, 15, 15, 3, 3)]:
+        cfg = grid_cfg(*g)
+        og = make_grid(*g)
+        n = g[4] * g[5]
+        for cid in range(65536, 65536 + n):
+            out = np.zeros(8, np.uint32)
+            k = L.chd_get_adjacent_channels(C.byref(cfg), cid, capi.ptr(out))
+            assert [int(v) for v in out[:k]] == oracle.adjacent(og, cid)
+        a = [np.zeros(n) for _ in range(4)]
+        cid, srv = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        assert L.chd_get_regions(C.byref(cfg), *[capi.ptr(v) for v in a], capi.ptr(cid), capi.ptr(srv)) == 0
+        want = oracle.regions(og)
+        for got, w in zip(a + [cid, srv], want):
+            np.testing.assert_array_equal(got, w)
+    for d in range(6):
+        assert L.chd_damping_interval_ms(d, 33) == oracle.damping(d, 33)
+
+
+def test_create_without_gpu_fails_loudly():
+    import torch
+
+    if torch.cuda.is_available():
+        return
+    from channeld_b200 import capi
+    from channeld_b200.engine import Engine, grid_cfg
+
+    try:
+        Engine(grid_cfg(0, 0, 10, 10, 1, 1), 16, 16)
+    except capi.ChdError as e:
+        assert e.status == capi.ERR_CUDA and "no CPU fallback" in str(e)
+    else:
+        raise AssertionError("engine creation must fail without a CUDA device")
+
+
+def test_create_validates_like_load_config():
+    from channeld_b200 import capi
+    from channeld_b200.engine import grid_cfg
+
+    L = capi.lib()
+    h = C.c_void_p()
+    for bad in [grid_cfg(0, 0, 0, 10, 1, 1), grid_cfg(0, 0, 10, -1, 1, 1), grid_cfg(0, 0, 10, 10, 0, 1), grid_cfg(0, 0, 10, 10, 1, 1, 0, 1)]:
+        assert L.chd_create(C.byref(bad), None, 0, C.byref(h)) == capi.ERR_INVALID
+        assert b"should be positive" in L.chd_last_error(None)

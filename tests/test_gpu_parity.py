@@ -1,0 +1,459 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+Bit-exact: integer/index work, and FP64 work that must reproduce Go's rounding operation by operation.
+Run on the B200 box:  python -m pytest tests -m gpu
+"""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+S0 = 65536
+MS = 1_000_000
+
+
+@pytest.fixture(scope="module")
+def chd():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from channeld_b200 import capi, controller, engine, synth
+
+    capi.lib()
+
+    class NS:
+        pass
+
+    ns = NS()
+    ns.capi, ns.controller, ns.engine, ns.synth = capi, controller, engine, synth
+    return ns
+
+
+def _ctl(chd, offx, offz, w, h, cols, rows, scols=1, srows=1, border=0):
+    c = chd.controller.GpuStaticGrid2DSpatialController(max_entities=4096, max_subscribers=256)
+    c.LoadConfig(dict(WorldOffsetX=offx, WorldOffsetZ=offz, GridWidth=w, GridHeight=h, GridCols=cols, GridRows=rows,
+                      ServerCols=scols, ServerRows=srows, ServerInterestBorderSize=border))
+    return c
+
+
+def _sphere(cx, cz, r):
+    C = __import__("channeld_b200.controller", fromlist=["x"])
+    return C.SpatialInterestQuery(SphereAOI=C.SphereAOI(Center=C.SpatialInfo(X=cx, Z=cz), Radius=r))
+
+
+def _box(cx, cz, ex, ez):
+    C = __import__("channeld_b200.controller", fromlist=["x"])
+    return C.SpatialInterestQuery(BoxAOI=C.BoxAOI(Center=C.SpatialInfo(X=cx, Z=cz), Extent=C.SpatialInfo(X=ex, Z=ez)))
+
+
+def _cone(cx, cz, dx, dz, angle, r):
+    C = __import__("channeld_b200.controller", fromlist=["x"])
+    return C.SpatialInterestQuery(ConeAOI=C.ConeAOI(Center=C.SpatialInfo(X=cx, Z=cz), Direction=C.SpatialInfo(X=dx, Z=dz),
+                                                    Angle=angle, Radius=r))
+
+
+# ----------------------------------------------------------------- the reference's own KATs, through the C ABI
+
+def test_kat_get_channel_id(chd):  # spatial_test.go:762-848
+    SI, SE = chd.controller.SpatialInfo, chd.controller.SpatialError
+    c = _ctl(chd, -450, -200, 100, 50, 9, 8, 3, 4, 2)
+    assert c.GetChannelId(SI(X=-450, Z=-200)) == S0
+    assert c.GetChannelId(SI(X=-350, Z=-200)) == S0 + 1
+    assert c.GetChannelId(SI(X=-450, Z=-150)) == S0 + 9
+    assert c.GetChannelId(SI(X=0, Z=0)) == S0 + 9 * 4 + 4
+    assert c.GetChannelId(SI(X=449.99, Z=199.99)) == S0 + 9 * 8 - 1
+    for x, z in [(-500, 0), (500, 0), (0, -300), (0, 300), (450, 200)]:
+        with pytest.raises(SE):
+            c.GetChannelId(SI(X=x, Z=z))
+    c = _ctl(chd, 0, 0, 100, 50, 9, 8, 3, 4, 2)
+    assert c.GetChannelId(SI(X=0, Z=0)) == S0
+    assert c.GetChannelId(SI(X=100, Z=0)) == S0 + 1
+    assert c.GetChannelId(SI(X=0, Z=50)) == S0 + 9
+    assert c.GetChannelId(SI(X=899.99, Z=399.99)) == S0 + 9 * 8 - 1
+    for x, z in [(-1, 0), (1.7976931348623157e308, 0), (0, -1), (900, 400), (float("nan"), 0), (float("inf"), 0), (0, float("-inf"))]:
+        with pytest.raises(SE):
+            c.GetChannelId(SI(X=x, Z=z))
+
+
+def test_kat_sphere_box_cone(chd):  # spatial_test.go:21-491
+    c1 = _ctl(chd, 0, 0, 10, 10, 1, 1)
+    assert S0 in c1.QueryChannelIds(_sphere(5, 5, 1))
+    assert S0 in c1.QueryChannelIds(_sphere(5, 5, 100))
+    assert S0 in c1.QueryChannelIds(_box(5, 5, 1, 1))
+    assert S0 in c1.QueryChannelIds(_box(5, 5, 100, 100))
+    assert S0 in c1.QueryChannelIds(_cone(5, 5, 1, 0, math.pi / 4, 1))
+    c2 = _ctl(chd, -5, -5, 5, 5, 2, 2)
+    assert len(c2.QueryChannelIds(_sphere(0, 0, 1))) == 4
+    assert set(c2.QueryChannelIds(_sphere(4.9, 4.9, 1))) == {65539}
+    assert len(c2.QueryChannelIds(_sphere(4.9, 4.9, 4.9))) == 1
+    assert len(c2.QueryChannelIds(_sphere(4.9, 4.9, 10))) == 4
+    assert len(c2.QueryChannelIds(_box(0, 0, 1, 1))) == 4
+    assert set(c2.QueryChannelIds(_box(4.9, 4.9, 1, 1))) == {65539}
+    assert len(c2.QueryChannelIds(_box(4.9, 4.9, 4.9, 4.9))) == 1
+    assert set(c2.QueryChannelIds(_box(4.9, 4.9, 4.9, 10))) == {65539, 65537}
+    c3 = _ctl(chd, -150, -150, 100, 100, 3, 3)
+    assert len(c3.QueryChannelIds(_sphere(0, 0, 150))) == 9
+    assert len(c3.QueryChannelIds(_sphere(0, 0, 99))) == 5
+    assert len(c3.QueryChannelIds(_box(0, 0, 150, 150))) == 9
+    assert len(c3.QueryChannelIds(_box(0, 0, 100, 100))) == 9
+    g2 = _ctl(chd, 0, 0, 10, 10, 4, 1)
+    assert S0 in g2.QueryChannelIds(_cone(0, 5, 1, 0, math.pi / 4, 1))
+    assert len(g2.QueryChannelIds(_cone(0, 5, 1, 0, math.pi / 4, 25))) == 3
+    assert len(g2.QueryChannelIds(_cone(0, 5, 1, 0, math.pi / 4, 100))) == 4
+    assert len(g2.QueryChannelIds(_cone(0, 5, 0, 1, math.pi / 4, 100))) == 1
+    g3 = _ctl(chd, 0, 0, 10, 10, 3, 3)
+    assert set(g3.QueryChannelIds(_cone(5, 5, 1, 0, 0.1, 100))) == {65536, 65537, 65538}
+    assert set(g3.QueryChannelIds(_cone(5, 5, 1, 0, math.pi / 4, 100))) == {65536, 65537, 65538, 65540, 65541, 65544}
+    assert set(g3.QueryChannelIds(_cone(15, 15, -1, 0, math.pi / 4, 100))) == {65536, 65539, 65540, 65542}
+    assert set(g3.QueryChannelIds(_cone(5, 15, 0, -1, math.pi / 4, 100))) == {65536, 65537, 65539}
+    g4 = _ctl(chd, -2000, -500, 1000, 1000, 4, 1, 2, 1, 1)
+    assert len(g4.QueryChannelIds(_cone(1250, 0, -0.087, 0.996, 0.5236, 30000))) == 1
+
+
+def test_kat_adjacent_regions(chd, oracle):  # spatial_test.go:493-526 + GetRegions vs the oracle
+    from tests._oracle import make_grid
+
+    assert _ctl(chd, 0, 0, 10, 10, 1, 1, 1, 1, 1).GetAdjacentChannels(S0) == []
+    assert len(_ctl(chd, -5, -5, 5, 5, 2, 2).GetAdjacentChannels(S0)) == 3
+    c = _ctl(chd, -40, -60, 20, 40, 4, 3, 2, 3, 1)
+    g = make_grid(-40, -60, 20, 40, 4, 3, 2, 3, 1)
+    for cid in range(S0, S0 + 12):
+        assert c.GetAdjacentChannels(cid) == oracle.adjacent(g, cid)
+    regs = c.GetRegions()
+    minx, minz, maxx, maxz, cid, srv = oracle.regions(g)
+    for i, r in enumerate(regs):
+        assert (r.Min.X, r.Min.Z, r.Max.X, r.Max.Z, r.ChannelId, r.ServerIndex) == (minx[i], minz[i], maxx[i], maxz[i], cid[i], srv[i])
+
+
+# ----------------------------------------------------------------- randomized bit-exact parity of QueryChannelIds
+
+GRIDS = [
+    (-150, -150, 100, 100, 3, 3), (-5, -5, 5, 5, 2, 2), (0, 0, 10, 10, 4, 1), (-2000, -2000, 2000, 2000, 2, 2),
+    (-15000, -15000, 2000, 2000, 15, 15), (-450, -200, 100, 50, 9, 8), (-12.5, 3.25, 7.3, 11.9, 13, 7), (0, 0, 33, 77, 2, 2),
+]
+
+
+def _random_queries(rng, g, n):
+    offx, offz, w, h, cols, rows = g
+    ww, wh = w * cols, h * rows
+    C = __import__("channeld_b200.controller", fromlist=["x"])
+    qs = []
+    for _ in range(n):
+        kind = rng.integers(0, 8)
+        cx = offx + rng.uniform(-0.1, 1.1) * ww
+        cz = offz + rng.uniform(-0.1, 1.1) * wh
+        r = float(rng.choice([rng.uniform(0.01, 0.4) * min(w, h), rng.uniform(0.4, 3.0) * max(w, h), w * 0.5, h, 0.0, -1.0],
+                             p=[0.4, 0.35, 0.1, 0.1, 0.03, 0.02]))
+        q = C.SpatialInterestQuery()
+        if kind in (0, 1, 2, 6):
+            q.SphereAOI = C.SphereAOI(Center=C.SpatialInfo(X=cx, Z=cz), Radius=r)
+        if kind in (3, 6, 7):
+            q.BoxAOI = C.BoxAOI(Center=C.SpatialInfo(X=cx + rng.uniform(-1, 1) * w, Z=cz), Extent=C.SpatialInfo(
+                X=abs(r) * rng.uniform(0.2, 1.5) if r > 0 else r, Z=rng.uniform(0.05, 2.5) * h))
+        if kind in (4, 7):
+            ang = rng.uniform(0, 2 * math.pi)
+            q.ConeAOI = C.ConeAOI(Center=C.SpatialInfo(X=cx, Z=cz), Direction=C.SpatialInfo(X=math.cos(ang), Z=math.sin(ang)),
+                                  Angle=float(rng.choice([0.1, math.pi / 4, 0.5236, rng.uniform(0, 3.2)])), Radius=abs(r) + 0.5 * w)
+        if kind in (5, 6):
+            k = int(rng.integers(1, 7))
+            spots = [C.SpatialInfo(X=offx + rng.uniform(-0.05, 1.05) * ww, Z=offz + rng.uniform(-0.05, 1.05) * wh) for _ in range(k)]
+            q.SpotsAOI = C.SpotsAOI(Spots=spots, Dists=[int(v) for v in rng.integers(0, 5, size=int(rng.integers(0, k + 1)))])
+        qs.append(q)
+    return qs
+
+
+def _oracle_query(oracle, og, q):
+    kw = {}
+    if q.SpotsAOI is not None:
+        kw["spots"] = [(s.X, s.Z) for s in q.SpotsAOI.Spots]
+        kw["spot_dists"] = list(q.SpotsAOI.Dists)
+    if q.BoxAOI is not None:
+        kw["box"] = (q.BoxAOI.Center.X, q.BoxAOI.Center.Z, q.BoxAOI.Extent.X, q.BoxAOI.Extent.Z)
+    if q.SphereAOI is not None:
+        kw["sphere"] = (q.SphereAOI.Center.X, q.SphereAOI.Center.Z, q.SphereAOI.Radius)
+    if q.ConeAOI is not None:
+        c = q.ConeAOI
+        kw["cone"] = (c.Center.X, c.Center.Z, c.Direction.X, c.Direction.Z, c.Angle, c.Radius)
+    return oracle.query(og, **kw)
+
+
+@pytest.mark.parametrize("gi", range(len(GRIDS)))
+def test_random_query_parity(chd, oracle, gi):
+    from tests._oracle import make_grid
+
+    g = GRIDS[gi]
+    rng = np.random.default_rng(1234 + gi)
+    c = chd.controller.GpuStaticGrid2DSpatialController(max_entities=16, max_subscribers=2048, max_queries=2048, max_spots=1 << 15,
+                                                        max_window_cells=1 << 22, max_pairs=1 << 20)
+    c.LoadConfig(dict(WorldOffsetX=g[0], WorldOffsetZ=g[1], GridWidth=g[2], GridHeight=g[3], GridCols=g[4], GridRows=g[5],
+                      ServerCols=1, ServerRows=1))
+    og = make_grid(*g)
+    qs = _random_queries(rng, g, 1500)
+    got = c.QueryChannelIdsBatch(qs)
+    n_err = 0
+    for q, res in zip(qs, got):
+        want, st = _oracle_query(oracle, og, q)
+        if st != 0:
+            assert isinstance(res, chd.controller.SpatialError), (q, st)
+            n_err += 1
+        else:
+            assert res == want, (q, res, want)
+    assert 0 < n_err < len(qs)
+
+
+def test_cell_of_parity_edges(chd, oracle):
+    from tests._oracle import make_grid
+
+    g = (-450, -200, 100, 50, 9, 8)
+    c = _ctl(chd, *g)
+    og = make_grid(*g)
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-600, 600, 20000)
+    z = rng.uniform(-300, 300, 20000)
+    # exact cell boundaries and neighbours one ulp either side
+    bx = -450 + 100.0 * np.arange(-1, 11)
+    bz = -200 + 50.0 * np.arange(-1, 10)
+    ex = np.concatenate([bx, np.nextafter(bx, -np.inf), np.nextafter(bx, np.inf), [np.nan, np.inf, -np.inf, 1e308, -1e308, 0.0, -0.0]])
+    ez = np.concatenate([bz, np.nextafter(bz, -np.inf), np.nextafter(bz, np.inf)])
+    xs = np.concatenate([x, np.repeat(ex, len(ez))])
+    zs = np.concatenate([z, np.tile(ez, len(ex))])
+    np.testing.assert_array_equal(c.GetChannelIds(xs, zs), oracle.cell_of(og, xs, zs))
+
+
+# ----------------------------------------------------------------- build + full tick on BASELINE config #1
+
+def _oracle_grid(wc):
+    from tests._oracle import make_grid
+
+    return make_grid(wc.offx, wc.offz, wc.w, wc.h, wc.cols, wc.rows, wc.server_cols, wc.server_rows)
+
+
+@pytest.mark.parametrize("radius", [50.0, 500.0, 2500.0])
+def test_tick_config1_full_parity(chd, oracle, radius):
+    """config #1: spatial_static_2x2, 1K entities / 256 subscribers: pairs + visible lists bit-identical."""
+    wc = chd.synth.CONFIGS["2x2"]
+    ex, ez = chd.synth.entities(wc)
+    conn, cx, cz, r = chd.synth.subscribers(wc, ex, ez, radius)
+    want = oracle.sphere_tick(_oracle_grid(wc), ex, ez, cx, cz, r)
+    e = chd.engine.Engine(wc.cfg(), wc.n_entities, wc.n_subscribers, max_visible=1 << 20)
+    e.set_entities(ex, ez)
+    e.set_subscribers(conn)
+    batch, keep = chd.engine.make_batch(len(cx), sub=np.arange(len(cx), dtype=np.uint32), sphere=(cx, cz, r))
+    s = e.tick(batch, 0, chd.capi.TICK_BUILD | chd.capi.TICK_EMIT)
+    assert s.n_pairs == len(want["pair_cell"]) and s.n_visible == len(want["vis_entity"])
+    assert s.n_query_errors == int((want["status"] != 0).sum())
+    pairs = e.get_pairs()
+    np.testing.assert_array_equal(pairs["off"].astype(np.uint64), want["pair_off"])
+    np.testing.assert_array_equal(pairs["channel"], want["pair_cell"])
+    np.testing.assert_array_equal(pairs["dist"], want["pair_dist"])
+    np.testing.assert_array_equal(pairs["interval"], [oracle.damping(int(d), 20) for d in want["pair_dist"]])
+    voff, vis = e.get_visible()
+    np.testing.assert_array_equal(voff, want["vis_off"])
+    np.testing.assert_array_equal(vis, want["vis_entity"])
+    np.testing.assert_array_equal(e.get_query_status(len(cx)), want["status"])
+    # cell CSR against a stable CPU sort of the oracle's cell ids
+    cs, se = e.get_cells()
+    ids = oracle.cell_of(_oracle_grid(wc), ex, ez)
+    valid = np.nonzero(ids)[0]
+    order = valid[np.argsort(ids[valid], kind="stable")]
+    np.testing.assert_array_equal(se, order.astype(np.uint32))
+    np.testing.assert_array_equal(cs, np.concatenate([[0], np.cumsum(np.bincount(ids[valid] - S0, minlength=wc.cells))]))
+    assert s.n_entities_in_world == len(valid)
+
+
+@pytest.mark.parametrize("name,n_ent,n_sub", [("benchmark", 200_000, 20_000), ("10m", 300_000, 30_000), ("handover", 400_000, 4_000)])
+def test_tick_scaled_configs_parity(chd, oracle, name, n_ent, n_sub):
+    """The grids of configs #2/#3/#5 (1- and 2-pass radix build, 225 / 4096 / 65536 cells) at sizes the oracle
+    finishes in seconds: pairs + visible lists bit-identical."""
+    wc = chd.synth.scaled(chd.synth.CONFIGS[name], n_ent, n_sub)
+    ex, ez = chd.synth.entities(wc)
+    # push some entities out of the world / onto the max edge
+    ex[::1013] = wc.offx + wc.w * wc.cols
+    ez[::2027] = wc.offz - 1.0
+    conn, cx, cz, r = chd.synth.subscribers(wc, ex, ez)
+    want = oracle.sphere_tick(_oracle_grid(wc), ex, ez, cx, cz, r)
+    e = chd.engine.Engine(wc.cfg(), n_ent, n_sub, max_visible=int(len(want["vis_entity"]) + 4096))
+    e.set_entities(ex, ez)
+    e.set_subscribers(conn)
+    batch, keep = chd.engine.make_batch(n_sub, sub=np.arange(n_sub, dtype=np.uint32), sphere=(cx, cz, r))
+    s = e.tick(batch, 0, chd.capi.TICK_BUILD | chd.capi.TICK_EMIT)
+    assert s.n_pairs == len(want["pair_cell"]) and s.n_visible == len(want["vis_entity"])
+    pairs = e.get_pairs()
+    np.testing.assert_array_equal(pairs["off"].astype(np.uint64), want["pair_off"])
+    np.testing.assert_array_equal(pairs["channel"], want["pair_cell"])
+    np.testing.assert_array_equal(pairs["dist"], want["pair_dist"])
+    voff, vis = e.get_visible()
+    np.testing.assert_array_equal(voff, want["vis_off"])
+    np.testing.assert_array_equal(vis, want["vis_entity"])
+    np.testing.assert_array_equal(e.get_query_status(n_sub), want["status"])
+
+
+def test_visible_overflow_reported(chd):
+    wc = chd.synth.CONFIGS["2x2"]
+    ex, ez = chd.synth.entities(wc)
+    conn, cx, cz, r = chd.synth.subscribers(wc, ex, ez, 2500.0)
+    e = chd.engine.Engine(wc.cfg(), wc.n_entities, wc.n_subscribers, max_visible=1000)
+    e.set_entities(ex, ez)
+    e.set_subscribers(conn)
+    batch, keep = chd.engine.make_batch(len(cx), sub=np.arange(len(cx), dtype=np.uint32), sphere=(cx, cz, r))
+    with pytest.raises(chd.capi.ChdError) as ei:
+        e.tick(batch, 0, chd.capi.TICK_BUILD | chd.capi.TICK_EMIT)
+    assert ei.value.status == chd.capi.ERR_CAPACITY
+
+
+# ----------------------------------------------------------------- interest diff + fan-out over several ticks
+
+def test_interest_diff_and_fanout_parity(chd, oracle):
+    """Moving subscribers on a 6x5 grid over 12 ticks: per tick the sub/unsub/kept sets match
+    oracle.interest_diff, and every fan-out decision matches the literal emulation of Channel.tickData
+    (one oracle channel per cell, fed the same subscriptions and update rings)."""
+    g = (-300.0, -250.0, 100.0, 100.0, 6, 5)
+    from tests._oracle import make_grid
+
+    og = make_grid(*g)
+    rng = np.random.default_rng(99)
+    S, N = 60, 500
+    cfg = chd.engine.grid_cfg(*g)
+    e = chd.engine.Engine(cfg, N, S, max_visible=1 << 20)
+    conn = np.arange(101, 101 + S, dtype=np.uint32)
+    e.set_subscribers(conn)
+    ex, ez = rng.uniform(-300, 300, N), rng.uniform(-250, 250, N)
+    e.set_entities(ex, ez)
+    e.build()
+    cells = g[4] * g[5]
+    chans = [oracle.channel() for _ in range(cells)]
+    rings = [[] for _ in range(cells)]  # (arrival, sender, index)
+    msg_index = np.zeros(cells, np.uint64)
+    cx, cz = rng.uniform(-320, 320, S), rng.uniform(-270, 270, S)  # a few start outside the world
+    rad = rng.choice([30.0, 60.0, 120.0, 260.0], S)
+    subs_now = [dict() for _ in range(S)]  # channel id -> dist, the oracle-side spatialSubscriptions
+    t = 0
+    tick_ns = 33 * MS
+    total_due = 0
+    for tick in range(12):
+        t += tick_ns if tick % 4 else 70 * MS  # irregular ticks exercise multi-step catch-up
+        cx += rng.uniform(-45, 45, S)
+        cz += rng.uniform(-45, 45, S)
+        moving = rng.random(S) < 0.8  # the others send no UPDATE_SPATIAL_INTEREST this tick
+        qi = np.nonzero(moving)[0].astype(np.uint32)
+        batch, keep = chd.engine.make_batch(len(qi), sub=qi, sphere=(cx[qi], cz[qi], rad[qi]))
+        e.update_interest(batch, t)
+        s = e.summary()
+        (new_s, new_c), (un_s, un_c) = e.get_diff(s.n_sub_new, s.n_unsub)
+        want_new, want_un, n_kept = set(), set(), 0
+        for j in qi:
+            res, st = oracle.query(og, sphere=(cx[j], cz[j], rad[j]))
+            if st != 0:
+                continue
+            un, sn, kp = oracle.interest_diff(list(subs_now[j].keys()), list(res.keys()))
+            for c in un:
+                want_un.add((int(j), int(c)))
+                chans[c - S0].unsubscribe(int(conn[j]))
+                del subs_now[j][int(c)]
+            for c in list(sn) + list(kp):
+                iv = oracle.damping(res[int(c)], 20)
+                chans[c - S0].subscribe(int(conn[j]), t, iv, 0, True, False)
+                subs_now[j][int(c)] = res[int(c)]
+            want_new |= {(int(j), int(c)) for c in sn}
+            n_kept += len(kp)
+        assert set(zip(new_s.tolist(), new_c.tolist())) == want_new
+        assert set(zip(un_s.tolist(), un_c.tolist())) == want_un
+        assert (s.n_sub_new, s.n_unsub, s.n_kept) == (len(want_new), len(want_un), n_kept)
+        pairs = e.get_pairs()
+        for j in range(S):
+            sl = slice(pairs["off"][j], pairs["off"][j + 1])
+            assert dict(zip(pairs["channel"][sl].tolist(), pairs["dist"][sl].tolist())) == subs_now[j]
+        # updates arrive (some sent by subscribers themselves -> SkipSelfUpdateFanOut)
+        for _ in range(int(rng.integers(5, 40))):
+            c = int(rng.integers(0, cells))
+            arrival = t - int(rng.integers(0, 80)) * MS  # not time-sorted on purpose (data_test.go:70-94)
+            sender = int(rng.choice(conn)) if rng.random() < 0.5 else 7
+            msg_index[c] += 1
+            rings[c].append((arrival, sender, int(msg_index[c])))
+            chans[c].on_update(arrival, sender)
+        ring_off = np.concatenate([[0], np.cumsum([len(r) for r in rings])]).astype(np.uint32)
+        flat = [x for r in rings for x in r]
+        e.set_rings(ring_off, np.array([f[0] for f in flat], np.int64), np.array([f[1] for f in flat], np.uint32),
+                    np.array([f[2] for f in flat], np.uint64), msg_index)
+        e.fanout_tick(t)
+        s = e.summary()
+        due = e.get_due(s.n_due)
+        want = []
+        for c in range(cells):
+            for d in chans[c].tick_data(t):
+                want.append((d["conn"], S0 + c, d["kind"], d["n"], d["first"], d["last"], d["hash"], d["last_index"], d["window_hi"]))
+        got = [(int(conn[d["sub"]]), int(d["channel_id"]), int(d["kind"]), int(d["n_selected"]), int(d["first_sel"]), int(d["last_sel"]),
+                int(d["sel_hash"]), int(d["last_message_index"]), int(d["window_hi"])) for d in due]
+        assert sorted(got) == sorted(want)
+        total_due += len(got)
+        # committed state matches the oracle's fanOutConnection
+        pairs = e.get_pairs()
+        for j in range(S):
+            for p in range(pairs["off"][j], pairs["off"][j + 1]):
+                last, had, idx = chans[int(pairs["channel"][p]) - S0].state(int(conn[j]))
+                assert (int(pairs["last"][p]), bool(pairs["flags"][p] & 1), int(pairs["last_index"][p])) == (last, had, idx)
+    assert total_due > 200
+
+
+def test_fanout_kat_through_engine(chd):
+    """data_test.go:98-166 (F0, F7, F2, F8=U1+U2, F3) replayed through chd_fanout_tick on a 1x1 grid."""
+    cfg = chd.engine.grid_cfg(0, 0, 10, 10, 1, 1)
+    e = chd.engine.Engine(cfg, 4, 4, default_fanout_interval_ms=50)
+    e.set_entities(np.array([5.0]), np.array([5.0]))
+    e.build()
+    e.set_subscribers(np.array([1, 2, 3], np.uint32))  # slots: c0=server(sender), c1, c2
+
+    def interest(slots, t):
+        # dist 0 -> 20 ms would apply; use a cone-free trick: SpotsAOI with explicit dists selects the interval:
+        # dist 1 -> 50 ms (c1), dist 2 -> 100 ms (c2)   (message_spatial.go:16-38)
+        n = len(slots)
+        off = np.arange(n + 1, dtype=np.uint32)
+        b, keep = chd.engine.make_batch(n, sub=np.array([s for s, _ in slots], np.uint32), kind=np.full(n, chd.capi.AOI_SPOTS, np.uint8),
+                                        spots=(off, np.ones(n, np.uint32), np.full(n, 5.0), np.full(n, 5.0),
+                                               np.array([d for _, d in slots], np.uint32)))
+        e.update_interest(b, t)
+
+    def tick(t, ring):
+        off = np.array([0, len(ring)], np.uint32)
+        e.set_rings(off, np.array([r[0] for r in ring], np.int64), np.array([r[1] for r in ring], np.uint32),
+                    np.array([r[2] for r in ring], np.uint64), np.array([len(ring)], np.uint64))
+        e.fanout_tick(t)
+        s = e.summary()
+        return e.get_due(s.n_due)
+
+    t0 = 100 * MS
+    interest([(1, 1)], 0)  # c1 subscribes at ~0 with 50 ms
+    due = tick(t0, [])
+    assert [(int(d["sub"]), int(d["kind"])) for d in due] == [(1, 0)]  # F0 = whole data
+    interest([(2, 2)], 0)  # c2 subscribes with 100 ms (channel time ~0 in the reference test)
+    due = tick(t0 + 50 * MS, [])
+    assert [(int(d["sub"]), int(d["kind"])) for d in due] == [(2, 0)]  # F1 nothing, F7 whole data
+    ring = [(t0 + 60 * MS, 1, 1)]  # U1 from c0 (conn id 1)
+    due = tick(t0 + 100 * MS, ring)
+    assert [(int(d["sub"]), int(d["kind"]), int(d["n_selected"]), int(d["sel_hash"])) for d in due] == [(1, 1, 1, 1)]  # F2 = U1
+    ring.append((t0 + 120 * MS, 1, 2))  # U2
+    due = tick(t0 + 150 * MS, ring)
+    assert sorted((int(d["sub"]), int(d["n_selected"]), int(d["sel_hash"])) for d in due) == [(1, 1, 2), (2, 2, 3)]  # F3=U2, F8=U1+U2
+
+
+def test_handover_detection(chd, oracle):
+    wc = chd.synth.scaled(chd.synth.CONFIGS["handover"], 50_000, 16)
+    ex, ez = chd.synth.entities(wc)
+    og = _oracle_grid(wc)
+    c = chd.controller.GpuStaticGrid2DSpatialController(max_entities=50_000, max_subscribers=16)
+    c.LoadConfig(dict(WorldOffsetX=wc.offx, WorldOffsetZ=wc.offz, GridWidth=wc.w, GridHeight=wc.h, GridCols=wc.cols, GridRows=wc.rows,
+                      ServerCols=1, ServerRows=1))
+    ent, src, dst = c.NotifyBatch(ex, ez)
+    assert len(ent) == 0
+    nx, nz = chd.synth.move_entities(wc, ex, ez, 1, 60.0)
+    nx[:5] = wc.offx - 10.0  # leave the world: the reference logs "failed to calculate dstChannelId"
+    ent, src, dst = c.NotifyBatch(nx, nz)
+    old, new = oracle.cell_of(og, ex, ez), oracle.cell_of(og, nx, nz)
+    moved = np.nonzero(old != new)[0]
+    order = np.argsort(ent)
+    np.testing.assert_array_equal(ent[order], moved.astype(np.uint32))
+    np.testing.assert_array_equal(src[order], old[moved])
+    np.testing.assert_array_equal(dst[order], new[moved])
+    assert len(moved) > 1000
