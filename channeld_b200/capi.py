@@ -89,7 +89,7 @@ SYMBOLS = [
     "chd_alloc_pinned", "chd_free_pinned", "chd_cell_of", "chd_set_entities", "chd_entity_buffers", "chd_set_entity_count",
     "chd_assign_cells", "chd_build", "chd_set_subscribers", "chd_query_channel_ids", "chd_update_interest",
     "chd_emit_visible", "chd_set_rings", "chd_fanout_tick", "chd_summary", "chd_tick", "chd_get_cells", "chd_get_pairs",
-    "chd_get_query_status", "chd_get_diff", "chd_get_visible", "chd_get_due", "chd_get_handover", "chd_device_view",
+    "chd_get_query_status", "chd_get_diff", "chd_get_visible", "chd_get_visible_slot", "chd_get_due", "chd_get_handover", "chd_device_view",
     "chd_set_slab", "chd_set_entity_ids", "chd_export_border", "chd_import_halo", "chd_get_adjacent_channels",
     "chd_get_regions", "chd_damping_interval_ms", "chd_launch_count", "chd_profile_enable", "chd_profile_get",
 ]
@@ -161,6 +161,8 @@ def lib():
     L.chd_get_diff.argtypes = [vp, vp, vp, vp, vp]
     L.chd_get_visible.restype = C.c_int
     L.chd_get_visible.argtypes = [vp, vp, vp]
+    L.chd_get_visible_slot.restype = C.c_int
+    L.chd_get_visible_slot.argtypes = [vp, C.c_uint32, vp, C.c_uint64, u64p]
     L.chd_get_due.restype = C.c_int
     L.chd_get_due.argtypes = [vp, vp, C.c_uint32]
     L.chd_get_handover.restype = C.c_int

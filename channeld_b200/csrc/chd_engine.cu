@@ -949,6 +949,23 @@ chd_status chd_get_visible(chd_engine* e, uint64_t* vis_off, uint32_t* vis_entit
     return CHD_OK;
 }
 
+chd_status chd_get_visible_slot(chd_engine* e, uint32_t slot, uint32_t* out, uint64_t cap, uint64_t* count) {
+    if (!e || !count || slot >= e->n_slots) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    uint64_t* h64 = (uint64_t*)e->h_u32;
+    CU(e, cudaMemcpyAsync(h64, e->d_vis_off + slot, 16, cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    const uint64_t b = h64[0], n = h64[1] - h64[0];
+    *count = n;
+    if (h64[1] > e->lim.max_visible) return CHD_ERR_CAPACITY;
+    const uint64_t m = n < cap ? n : cap;
+    if (m && out) {
+        CU(e, cudaMemcpyAsync(out, e->d_vis + b, sizeof(uint32_t) * m, cudaMemcpyDefault, e->stream));
+        CU(e, cudaStreamSynchronize(e->stream));
+    }
+    return CHD_OK;
+}
+
 chd_status chd_get_due(chd_engine* e, chd_due* out, uint32_t cap) {
     if (!e || !out) return CHD_ERR_INVALID;
     CU(e, cudaSetDevice(e->device));

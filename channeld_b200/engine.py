@@ -228,6 +228,14 @@ class Engine:
         self._ck(self.L.chd_get_visible(self.h, None, ptr(ve)))
         return off, ve
 
+    def get_visible_slot(self, slot, cap=1 << 20):
+        out = np.zeros(cap, np.uint32)
+        n = C.c_uint64()
+        self._ck(self.L.chd_get_visible_slot(self.h, int(slot), ptr(out), cap, C.byref(n)))
+        if n.value > cap:
+            return self.get_visible_slot(slot, int(n.value))
+        return out[:n.value].copy()
+
     def get_due(self, n_due):
         out = np.zeros(int(n_due), capi.DUE_DTYPE)
         if n_due:

@@ -220,6 +220,8 @@ chd_status chd_get_query_status(chd_engine* e, uint32_t* status, uint32_t n);
 chd_status chd_get_diff(chd_engine* e, uint32_t* new_sub, uint32_t* new_channel, uint32_t* unsub_sub, uint32_t* unsub_channel);
 /* visible lists: vis_off[n_subscribers+1] (u64), vis_entity[n_visible] */
 chd_status chd_get_visible(chd_engine* e, uint64_t* vis_off, uint32_t* vis_entity);
+/* one subscriber's visible list: copies min(count, cap) entries, *count = its full length */
+chd_status chd_get_visible_slot(chd_engine* e, uint32_t slot, uint32_t* out, uint64_t cap, uint64_t* count);
 /* fan-out decisions of the last chd_fanout_tick, ordered by (slot asc, channel asc, step asc) */
 chd_status chd_get_due(chd_engine* e, chd_due* out, uint32_t cap);
 /* handover candidates of the last build: entity, src channel id, dst channel id (0 = left/entered the world) */
