@@ -216,7 +216,7 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)
     e = engine.Engine(wc.cfg(), max_ent, max(S, 1), device=local,
                       max_visible=int(max(S, 1) * 1.3 * max(per_cell, 1.0) * (1.0 + 4.0 * (wc.radius / wc.w) ** 1) + (1 << 22)),
-                      max_ring_entries=wc.cells * args.ring_len + 1024)
+                      max_ring_entries=wc.cells * args.ring_len + 1024, max_due=int(max(S, 1) * 8 + 4096))
     e.set_stream(stream.cuda_stream)
     if world > 1:
         e.set_slab(col_lo, col_hi, halo)
@@ -239,12 +239,18 @@ def run_ours(args):
     a_sub[:] = sub_idx.view(np.int32)
     d_sub = t_sub.to(dev)
 
-    n_steps_total = args.warmup + args.steps + 64
+    n_e2e = args.e2e_steps or min(args.steps, 10)
+    n_steps_total = 1 + args.warmup + args.steps + 2 + n_e2e + 2 + args.expanded_steps + 2
+    # one ring snapshot per step (arrival times follow the tick clock); bound the staging memory for huge grids
+    ring_len, upc = args.ring_len, args.updates_per_cell
+    while wc.cells * ring_len * 20 * n_steps_total > (768 << 20) and ring_len > 4:
+        ring_len //= 2
+        upc = max(1, upc // 2)
     ring_state = None
     rings_host, rings_dev = [], []
-    for i in range(min(n_steps_total, 48)):
-        ring_state, off, arr, snd, idx, cmi = synth.update_rings(wc, i, (i + 1) * TICK_NS, TICK_NS, args.updates_per_cell, S_total,
-                                                                 ring_len=args.ring_len, state=ring_state)
+    for i in range(n_steps_total):
+        ring_state, off, arr, snd, idx, cmi = synth.update_rings(wc, i, (i + 1) * TICK_NS, TICK_NS, upc, S_total,
+                                                                 ring_len=ring_len, state=ring_state)
         hh = {}
         for k, a_, dt in (("off", off.view(np.int32), torch.int32), ("arr", arr, torch.int64), ("snd", snd.view(np.int32), torch.int32),
                           ("idx", idx.view(np.int64), torch.int64), ("cmi", cmi.view(np.int64), torch.int64)):
@@ -284,7 +290,7 @@ def run_ours(args):
     def step(i, inputs, batches, rings):
         """One tick, enqueue only (no host sync at world == 1)."""
         d = inputs[i % 2]
-        rg = rings[i % len(rings)]
+        rg = rings[i]
         t_ns = (i + 1) * TICK_NS
         ck(L.chd_set_entities(e.h, capi.ptr(d["x"]), capi.ptr(d["z"]), n_own))
         if world > 1:
@@ -371,7 +377,7 @@ def run_ours(args):
 
         def e2e_step(i, expanded=False):
             d = host_in[i % 2]
-            rg = rings_host[i % len(rings_host)]
+            rg = rings_host[i]
             t_ns = (i + 1) * TICK_NS
             ck(L.chd_set_entities(e.h, capi.ptr(d["x"]), capi.ptr(d["z"]), n_own))
             if world > 1:
@@ -395,7 +401,6 @@ def run_ours(args):
                    + (wc.cells + 1) * 4 + 4 * int(summ.n_entities_in_world) + (S + 1) * 8 + (4 * int(summ.n_visible) if expanded else 0))
             return h2d, d2h
 
-        n_e2e = args.e2e_steps or min(args.steps, 10)
         base = args.warmup + 1 + args.steps
         for i in range(2):
             e2e_step(base + i)

@@ -91,7 +91,8 @@ SYMBOLS = [
     "chd_emit_visible", "chd_set_rings", "chd_fanout_tick", "chd_summary", "chd_tick", "chd_get_cells", "chd_get_pairs",
     "chd_get_query_status", "chd_get_diff", "chd_get_visible", "chd_get_visible_slot", "chd_get_due", "chd_get_handover", "chd_device_view",
     "chd_set_slab", "chd_set_entity_ids", "chd_export_border", "chd_import_halo", "chd_get_adjacent_channels",
-    "chd_get_regions", "chd_damping_interval_ms", "chd_launch_count", "chd_profile_enable", "chd_profile_get",
+    "chd_get_regions", "chd_damping_interval_ms", "chd_launch_count", "chd_profile_enable", "chd_profile_get", "chd_enable_graphs",
+    "chd_graph_launch_count",
 ]
 STAGE_BUILD, STAGE_INTEREST, STAGE_EMIT, STAGE_EMIT_KERNEL, STAGE_FANOUT = range(5)
 
@@ -185,6 +186,10 @@ def lib():
     L.chd_damping_interval_ms.argtypes = [C.c_uint32, C.c_uint32]
     L.chd_launch_count.restype = C.c_uint64
     L.chd_launch_count.argtypes = [vp]
+    L.chd_enable_graphs.restype = C.c_int
+    L.chd_enable_graphs.argtypes = [vp, C.c_int]
+    L.chd_graph_launch_count.restype = C.c_uint64
+    L.chd_graph_launch_count.argtypes = [vp]
     L.chd_profile_enable.restype = C.c_int
     L.chd_profile_enable.argtypes = [vp, C.c_int]
     L.chd_profile_get.restype = C.c_int

@@ -129,13 +129,17 @@ __global__ void __launch_bounds__(BUILD_THREADS)
 
 // cell_start[c] = first sorted position whose key >= c, for c in [0, C+1]; cell_start[C+1] = n.
 __global__ void __launch_bounds__(256)
-    cell_bounds_kernel(const uint32_t* __restrict__ sorted_key, uint32_t n, uint32_t cells, uint32_t* __restrict__ cell_start) {
+    cell_bounds_kernel(const uint32_t* __restrict__ sorted_key, uint32_t n, uint32_t cells, uint32_t* __restrict__ cell_start,
+                       uint32_t* __restrict__ n_in_world) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i > n) return;
     // position i: keys (prev, cur]; prev = -1 at i == 0; cur = C+1 at i == n
     const int64_t prev = i == 0 ? -1 : (int64_t)sorted_key[i - 1];
     const int64_t cur = i == n ? (int64_t)cells + 1 : (int64_t)sorted_key[i];
-    for (int64_t c = prev + 1; c <= cur; c++) cell_start[c] = i;
+    for (int64_t c = prev + 1; c <= cur; c++) {
+        cell_start[c] = i;
+        if (c == (int64_t)cells) *n_in_world = i;  // entities with a valid cell precede the key == cells tail
+    }
 }
 
 }  // namespace chd

@@ -4,18 +4,34 @@
 //
 // Decomposition: the OUTPUT array is cut into fixed tiles of EMIT_TILE entries (load-balanced regardless of
 // how entities are distributed over cells).  A partition pass records the first pair of each tile; a
-// persistent grid (multiple of the SM count) then walks tiles round-robin.  Stores are fully coalesced and
-// 128 B-aligned (tile bases are multiples of 4096 entries); loads are coalesced runs out of the L2-resident
-// cell CSR (sorted_entity is 4 B x N: 4 MB at 1 M entities, far below the 126 MB L2).
+// persistent grid (multiple of the SM count) then walks tiles round-robin.  Every thread moves 16-byte chunks:
+// stores are fully coalesced and 128 B-aligned (tile bases are multiples of 8192 entries); loads are co-aligned
+// 16-byte reads out of the L2-resident phase copies of the cell CSR (4 x 4 B x N: 16 MB at 1 M entities, far
+// below the 126 MB L2).  v1 of this kernel moved 4 bytes per thread-iteration and was instruction-issue bound
+// (ncu: 73 % issue-active, 30 % DRAM): see profiles/r1_v1_emit_ncu_details.txt.
 #pragma once
 #include "chd_interest.cuh"
 
 namespace chd {
 
 constexpr int EMIT_THREADS = 256;
-constexpr int EMIT_ITEMS = 16;
-constexpr int EMIT_TILE = EMIT_THREADS * EMIT_ITEMS;  // 4096 entries = 16 KB of output per tile
+constexpr int EMIT_CHUNKS = 8;                            // 16-byte chunks per thread per tile
+constexpr int EMIT_TILE = EMIT_THREADS * EMIT_CHUNKS * 4;  // 8192 entries = 32 KB of output per tile
 constexpr int EMIT_SMEM_PAIRS = 1024;
+
+// The cell CSR's entity array is kept in FOUR phase-shifted copies: copy k stores element i at index
+// k*stride + k + i (stride % 4 == 0), i.e. at 16-byte phase (k + i) % 4.  Output chunks are 16-byte aligned, so
+// for a run that starts at source index s the copy k = (-s) & 3 makes source and destination co-aligned and
+// the whole run moves as LDG.128 -> STG.128 with no realignment shuffles.  Cost: 12 extra bytes per entity
+// written once per build (L2-resident), against 8 bytes per VISIBLE entry saved from 4-byte accesses.
+__global__ void __launch_bounds__(256)
+    replicate_phases_kernel(const uint32_t* src, uint32_t n, uint32_t stride, uint32_t* dst4) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t v = src[i];
+#pragma unroll
+    for (uint32_t k = 1; k < 4; k++) dst4[(size_t)k * stride + k + i] = v;  // copy 0 is src itself (dst4 == src)
+}
 
 // per pair: number of visible entities = size of the cell's list
 __global__ void __launch_bounds__(256)
@@ -60,7 +76,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(EMIT_THREADS)
     emit_visible_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, const uint64_t* __restrict__ voff,
                         const uint32_t* __restrict__ pair_cell, const uint32_t* __restrict__ cell_start,
-                        const uint32_t* __restrict__ sorted_entity, const uint32_t* __restrict__ first_pair,
+                        const uint32_t* __restrict__ sorted4, uint32_t stride, const uint32_t* __restrict__ first_pair,
                         uint32_t* __restrict__ vis_entity, uint64_t vis_cap) {
     __shared__ uint32_t s_end[EMIT_SMEM_PAIRS];  // end of pair (p0+k) relative to the tile base, clamped to EMIT_TILE
     __shared__ uint32_t s_src[EMIT_SMEM_PAIRS];  // source index of the pair's entry that lands on max(voff[p], tile base)
@@ -69,55 +85,66 @@ __global__ void __launch_bounds__(EMIT_THREADS)
     const uint64_t V = voff[np];
     if (V > vis_cap) return;
     const uint64_t n_tiles = (V + EMIT_TILE - 1) / EMIT_TILE;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const uint64_t base = t * EMIT_TILE;
         const uint32_t p0 = first_pair[t];
         const uint32_t p1 = (t + 1 < n_tiles) ? first_pair[t + 1] : (uint32_t)(np - 1);
         const uint32_t cnt = p1 - p0 + 1;
         const uint32_t tile_len = (uint32_t)min((uint64_t)EMIT_TILE, V - base);
+        uint32_t* __restrict__ out = vis_entity + base;
         if (cnt <= EMIT_SMEM_PAIRS) {
             __syncthreads();  // previous tile's readers are done
             for (uint32_t k = threadIdx.x; k < cnt; k += EMIT_THREADS) {
                 const uint64_t b = voff[p0 + k], e = voff[p0 + k + 1];
                 const uint32_t c = pair_cell[p0 + k];
                 s_end[k] = (uint32_t)min((uint64_t)EMIT_TILE, e > base ? e - base : 0);
-                // source position for relative output position max(b,base)-base
                 s_src[k] = cell_start[c] + (uint32_t)(b < base ? base - b : 0);
             }
             __syncthreads();
-            // warp w covers relative outputs [w*512, w*512+512)
-            const uint32_t seg = w * (32 * EMIT_ITEMS);
-            // uniform binary search: first k with s_end[k] > seg
-            uint32_t lo = 0, hi = cnt;
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (s_end[mid] > seg) hi = mid; else lo = mid + 1;
+            uint32_t k = 0;  // segment cursor of this thread (its chunks ascend)
+            if (cnt > 8) {   // many short segments: start from a binary search instead of a linear walk
+                const uint32_t o0 = threadIdx.x * 4;
+                uint32_t lo = 0, hi = cnt - 1;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (s_end[mid] > o0) hi = mid; else lo = mid + 1;
+                }
+                k = lo;
             }
-            uint32_t k = lo;
-#pragma unroll 4
-            for (int it = 0; it < EMIT_ITEMS; it++) {
-                const uint32_t o = seg + it * 32 + lane;
+#pragma unroll
+            for (int it = 0; it < EMIT_CHUNKS; it++) {
+                const uint32_t o = (it * EMIT_THREADS + threadIdx.x) * 4;  // first entry of this 16-byte chunk
                 if (o < tile_len) {
-                    while (s_end[k] <= o) k++;  // o < tile_len guarantees termination (s_end[cnt-1] >= tile_len)
-                    const uint32_t beg = k == 0 ? 0u : s_end[k - 1];  // relative start of pair k inside the tile
-                    vis_entity[base + o] = sorted_entity[s_src[k] + (o - beg)];
+                    while (s_end[k] <= o) k++;  // terminates: s_end[cnt-1] >= tile_len > o
+                    const uint32_t beg = k == 0 ? 0u : s_end[k - 1];
+                    const uint32_t sidx = s_src[k] + (o - beg);
+                    if (o + 4 <= s_end[k]) {
+                        // whole chunk inside one segment: co-aligned 16-byte move out of phase copy (-sidx)&3
+                        const uint32_t ph = (0u - sidx) & 3u;
+                        const uint4 v = *reinterpret_cast<const uint4*>(sorted4 + (size_t)ph * stride + ph + sidx);
+                        *reinterpret_cast<uint4*>(out + o) = v;
+                    } else {
+                        // the chunk straddles a segment boundary (or the end of the list): entry by entry
+                        uint32_t kk = k;
+                        for (uint32_t j = 0; j < 4 && o + j < tile_len; j++) {
+                            while (s_end[kk] <= o + j) kk++;
+                            const uint32_t bb = kk == 0 ? 0u : s_end[kk - 1];
+                            out[o + j] = sorted4[s_src[kk] + (o + j - bb)];
+                        }
+                    }
                 }
             }
         } else {
-            // many tiny/empty cells inside one tile: per-lane binary search over the global offsets
-            for (int it = 0; it < EMIT_ITEMS; it++) {
-                const uint32_t o = threadIdx.x + it * EMIT_THREADS;
-                if (o < tile_len) {
-                    const uint64_t go = base + o;
-                    uint64_t lo = p0, hi = p1;  // last p in [p0,p1] with voff[p] <= go
-                    while (lo < hi) {
-                        const uint64_t mid = (lo + hi + 1) >> 1;
-                        if (voff[mid] <= go) lo = mid; else hi = mid - 1;
-                    }
-                    const uint32_t c = pair_cell[lo];
-                    vis_entity[go] = sorted_entity[cell_start[c] + (uint32_t)(go - voff[lo])];
+            // more than EMIT_SMEM_PAIRS pairs inside one tile (tiny / empty cells): per-entry binary search
+            for (uint32_t o = threadIdx.x; o < tile_len; o += EMIT_THREADS) {
+                const uint64_t go = base + o;
+                uint64_t lo = p0, hi = p1;  // last p in [p0,p1] with voff[p] <= go
+                while (lo < hi) {
+                    const uint64_t mid = (lo + hi + 1) >> 1;
+                    if (voff[mid] <= go) lo = mid; else hi = mid - 1;
                 }
+                const uint32_t c = pair_cell[lo];
+                vis_entity[go] = sorted4[cell_start[c] + (uint32_t)(go - voff[lo])];
             }
         }
     }

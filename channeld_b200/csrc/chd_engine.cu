@@ -34,6 +34,18 @@ struct chd_engine {
     std::vector<void*> allocs;
     int sm_count = 148;
     uint64_t n_launch = 0;  // kernels launched by this engine (bench.py reports it as gpu_launches)
+    // CUDA graphs: the launch-bound small-kernel stages are captured once per (shape, parity) and replayed.
+    struct GraphSlot {
+        cudaGraphExec_t exec = nullptr;
+        uint64_t key = 0, pending_key = 0;
+        uint64_t nodes = 0;
+    };
+    bool use_graphs = true;
+    GraphSlot g_build[2], g_interest[2], g_emit_prep[2], g_fanout[2];
+    uint64_t graph_launches = 0, graph_captures = 0;
+    uint32_t* d_key_a = nullptr;  // identity of the first key buffer (graph slot selection)
+    int64_t* d_time = nullptr;      // [0] = now_ns of the last update_interest, [1] = t_ns of the last fanout_tick
+    uint32_t* d_ring_total = nullptr;
     // optional per-stage CUDA-event timing (chd_profile_*): [stage][0=start,1=stop]
     bool profiling = false;
     static constexpr int EV_RING = 1024;
@@ -49,6 +61,8 @@ struct chd_engine {
     uint32_t *d_key = nullptr, *d_prev_key = nullptr;  // [max_entities] cell key per entity
     uint32_t *d_tmp_key = nullptr, *d_tmp_val = nullptr, *d_sorted_key = nullptr, *d_sorted_ent = nullptr;
     uint32_t *d_cell_start = nullptr;     // [C+2]
+    uint32_t *d_sorted4 = nullptr;        // 4 phase-shifted copies of d_sorted_ent (chd_emit.cuh), stride = phase_stride
+    uint32_t phase_stride = 0;
     uint32_t *d_hist = nullptr;           // [BUILD_MAX_BINS * nblocks + 1]
     uint32_t *d_scan_scratch = nullptr;   // u32 scan scratch
     uint64_t *d_scan_scratch64 = nullptr;
@@ -80,7 +94,8 @@ struct chd_engine {
     uint32_t* d_slot_cnt = nullptr;
     uint32_t last_nq = 0;
     // diff
-    uint32_t *d_new_flag = nullptr, *d_gone_flag = nullptr, *d_new_off = nullptr, *d_gone_off = nullptr;
+    uint32_t *d_new_flag = nullptr, *d_gone_flag = nullptr, *d_new_off = nullptr, *d_diff_len = nullptr;
+    uint64_t *d_diff_packed = nullptr, *d_diff_off = nullptr;
     uint32_t *d_new_sub = nullptr, *d_new_ch = nullptr, *d_gone_sub = nullptr, *d_gone_ch = nullptr;
     // emit
     uint32_t *d_vcnt = nullptr, *d_first_pair = nullptr, *d_vis = nullptr;
@@ -162,6 +177,70 @@ static bool dalloc(chd_engine* e, T** p, uint64_t count) {
 
 static inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 
+__global__ void set_i64_kernel(int64_t* dst, int64_t v) { *dst = v; }
+__global__ void set_u32_kernel(uint32_t* dst, uint32_t v) { *dst = v; }
+
+static inline uint64_t mix_key(uint64_t h, uint64_t v) {
+    h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    return h;
+}
+
+// Runs `enqueue` (kernel launches + memsets only, no host sync) either directly or as a replayed CUDA graph.
+// A graph is captured only after the same key was seen twice in a row, so workloads whose batch shape changes
+// every tick simply run direct launches.
+template <typename F>
+static chd_status run_stage(chd_engine* e, chd_engine::GraphSlot& slot, uint64_t key, F&& enqueue) {
+    key |= 1;  // never 0
+    if (!e->use_graphs || e->stream == nullptr) return enqueue();
+    if (slot.exec && slot.key == key) {
+        CU(e, cudaGraphLaunch(slot.exec, e->stream));
+        e->n_launch += slot.nodes;
+        e->graph_launches++;
+        return CHD_OK;
+    }
+    if (slot.pending_key != key) {  // first sighting: run direct, capture next time
+        slot.pending_key = key;
+        return enqueue();
+    }
+    if (slot.exec) {
+        cudaGraphExecDestroy(slot.exec);
+        slot.exec = nullptr;
+    }
+    const uint64_t l0 = e->n_launch;
+    CU(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    chd_status st = enqueue();
+    cudaGraph_t g = nullptr;
+    cudaError_t r = cudaStreamEndCapture(e->stream, &g);
+    if (st != CHD_OK || r != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        if (st == CHD_OK) {
+            e->fail("graph capture failed: %s", cudaGetErrorString(r));
+            st = CHD_ERR_CUDA;
+        }
+        e->use_graphs = false;  // fall back to direct launches for the rest of this engine's life
+        cudaGetLastError();
+        e->n_launch = l0;
+        return st == CHD_OK ? enqueue() : st;
+    }
+    r = cudaGraphInstantiate(&slot.exec, g, 0);
+    cudaGraphDestroy(g);
+    if (r != cudaSuccess) {
+        slot.exec = nullptr;
+        e->use_graphs = false;
+        cudaGetLastError();
+        e->n_launch = l0;
+        return enqueue();
+    }
+    slot.nodes = e->n_launch - l0;
+    e->n_launch = l0;
+    slot.key = key;
+    e->graph_captures++;
+    CU(e, cudaGraphLaunch(slot.exec, e->stream));
+    e->n_launch += slot.nodes;
+    e->graph_launches++;
+    return CHD_OK;
+}
+
 extern "C" {
 
 uint32_t chd_abi_version(void) { return CHD_ABI_VERSION; }
@@ -203,6 +282,9 @@ void chd_destroy(chd_engine* e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (void* p : e->allocs) cudaFree(p);
+    for (auto* arr : {e->g_build, e->g_interest, e->g_emit_prep, e->g_fanout})
+        for (int i = 0; i < 2; i++)
+            if (arr[i].exec) cudaGraphExecDestroy(arr[i].exec);
     if (e->ev) {
         for (size_t i = 0; i < (size_t)CHD_STAGE_COUNT * chd_engine::EV_RING * 2; i++)
             if (e->ev[i]) cudaEventDestroy(e->ev[i]);
@@ -302,6 +384,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
 
     const uint64_t N = L.max_entities, S = L.max_subscribers, Q = L.max_queries, P = L.max_pairs, C = g.cells;
     e->build_blocks = (uint32_t)e->sm_count * 4;
+    e->phase_stride = (uint32_t)(((N + 3) / 4) * 4 + 8);
     e->ho_cap = L.max_entities;
     e->max_tiles = (L.max_visible + EMIT_TILE - 1) / EMIT_TILE + 1;
     uint64_t scan_n = (uint64_t)BUILD_MAX_BINS * e->build_blocks + 1;
@@ -312,11 +395,13 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
     bool ok = true;
     ok = ok && dalloc(e, &e->d_x, N) && dalloc(e, &e->d_z, N) && dalloc(e, &e->d_gid, N) && dalloc(e, &e->d_key, N) &&
          dalloc(e, &e->d_prev_key, N) && dalloc(e, &e->d_tmp_key, N) && dalloc(e, &e->d_tmp_val, N) &&
-         dalloc(e, &e->d_sorted_key, N) && dalloc(e, &e->d_sorted_ent, N) && dalloc(e, &e->d_cell_start, C + 2) &&
+         dalloc(e, &e->d_sorted_key, N) && dalloc(e, &e->d_sorted4, 4 * (((N + 3) / 4) * 4 + 8)) && dalloc(e, &e->d_cell_start, C + 2) &&
          dalloc(e, &e->d_hist, (uint64_t)BUILD_MAX_BINS * e->build_blocks + 2) &&
          dalloc(e, &e->d_scan_scratch, scan_scratch_elems(scan_n) + 8) && dalloc(e, &e->d_scan_scratch64, scan_scratch_elems(scan_n) + 8) &&
          dalloc(e, &e->d_ho_entity, N) && dalloc(e, &e->d_ho_src, N) && dalloc(e, &e->d_ho_dst, N) &&
          dalloc(e, &e->d_bflag, N + 1) && dalloc(e, &e->d_boff, N + 2);
+    e->d_sorted_ent = e->d_sorted4;  // phase copy 0 IS the plain sorted entity array
+    e->d_key_a = e->d_key;
     ok = ok && dalloc(e, &e->d_conn, S) && alloc_pairbuf(e, e->pairs[0]) && alloc_pairbuf(e, e->pairs[1]);
     ok = ok && dalloc(e, &e->dq.sub, Q) && dalloc(e, &e->dq.kind, Q) && dalloc(e, &e->dq.sph_cx, Q) && dalloc(e, &e->dq.sph_cz, Q) &&
          dalloc(e, &e->dq.sph_r, Q) && dalloc(e, &e->dq.box_cx, Q) && dalloc(e, &e->dq.box_cz, Q) && dalloc(e, &e->dq.box_ex, Q) &&
@@ -330,14 +415,15 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
          dalloc(e, &e->d_qcount, Q) && dalloc(e, &e->d_qoff, Q + 1) && dalloc(e, &e->d_qout_id, P) && dalloc(e, &e->d_qout_dist, P) &&
          dalloc(e, &e->d_slot_query, S) && dalloc(e, &e->d_slot_cnt, S);
     ok = ok && dalloc(e, &e->d_new_flag, P) && dalloc(e, &e->d_gone_flag, P) && dalloc(e, &e->d_new_off, P + 1) &&
-         dalloc(e, &e->d_gone_off, P + 1) && dalloc(e, &e->d_new_sub, P) && dalloc(e, &e->d_new_ch, P) && dalloc(e, &e->d_gone_sub, P) &&
+         dalloc(e, &e->d_diff_packed, P + 1) && dalloc(e, &e->d_diff_off, P + 2) && dalloc(e, &e->d_diff_len, 4) && dalloc(e, &e->d_new_sub, P) && dalloc(e, &e->d_new_ch, P) && dalloc(e, &e->d_gone_sub, P) &&
          dalloc(e, &e->d_gone_ch, P);
     ok = ok && dalloc(e, &e->d_vcnt, P) && dalloc(e, &e->d_voff, P + 1) && dalloc(e, &e->d_first_pair, e->max_tiles + 1) &&
          dalloc(e, &e->d_vis_off, S + 1) && dalloc(e, &e->d_vis, L.max_visible);
     ok = ok && dalloc(e, &e->d_ring_off, C + 1) && dalloc(e, &e->d_ring_arrival, (uint64_t)L.max_ring_entries) &&
          dalloc(e, &e->d_ring_sender, (uint64_t)L.max_ring_entries) && dalloc(e, &e->d_ring_index, (uint64_t)L.max_ring_entries) &&
          dalloc(e, &e->d_ch_msg_index, C) && dalloc(e, &e->d_due_cnt, P) && dalloc(e, &e->d_due_off, P + 1) &&
-         dalloc(e, &e->d_due, (uint64_t)L.max_due) && dalloc(e, &e->d_ctr, 1);
+         dalloc(e, &e->d_due, (uint64_t)L.max_due) && dalloc(e, &e->d_ctr, 1) && dalloc(e, &e->d_time, 2) &&
+         dalloc(e, &e->d_ring_total, 1);
     if (!ok) {
         g_create_error = e->err;
         chd_destroy(e);
@@ -346,6 +432,8 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
     CCU(cudaHostAlloc((void**)&e->h_ctr, sizeof(Counters), cudaHostAllocDefault));
     CCU(cudaHostAlloc((void**)&e->h_u32, 64, cudaHostAllocDefault));
     CCU(cudaMemsetAsync(e->d_ctr, 0, sizeof(Counters), e->stream));
+    CCU(cudaMemsetAsync(e->d_time, 0, 16, e->stream));
+    CCU(cudaMemsetAsync(e->d_ring_total, 0, 4, e->stream));
     CCU(cudaMemsetAsync(e->pairs[0].off, 0, (S + 1) * 4, e->stream));
     CCU(cudaMemsetAsync(e->pairs[1].off, 0, (S + 1) * 4, e->stream));
     CCU(cudaMemsetAsync(e->d_ring_off, 0, (C + 1) * 4, e->stream));
@@ -503,12 +591,12 @@ static chd_status sort_pass_any(chd_engine* e, const uint32_t* key_in, const uin
     return sort_pass<1024>(e, key_in, val_in, n, per_block, nblocks, shift, bits, key_out, val_out);
 }
 
-chd_status chd_build(chd_engine* e) {
-    if (!e) return CHD_ERR_INVALID;
-    CU(e, cudaSetDevice(e->device));
-    StageTimer timer(e, CHD_STAGE_BUILD);
-    chd_status st = chd_assign_cells(e);
-    if (st != CHD_OK) return st;
+static chd_status build_enqueue(chd_engine* e, bool with_assign) {
+    chd_status st;
+    if (with_assign) {
+        st = chd_assign_cells(e);
+        if (st != CHD_OK) return st;
+    }
     const uint32_t n = e->n_own + e->n_halo;
     const uint32_t C = e->g.cells;
     uint32_t bits = 1;
@@ -531,11 +619,44 @@ chd_status chd_build(chd_engine* e) {
         st = sort_pass_any(e, e->d_tmp_key, e->d_tmp_val, n, per_block, nblocks, bits0, bits1, e->d_sorted_key, e->d_sorted_ent);
         if (st != CHD_OK) return st;
     }
-    cell_bounds_kernel<<<blocks_for((uint64_t)n + 1, 256), 256, 0, e->stream>>>(e->d_sorted_key, n, C, e->d_cell_start);
+    if (n) {
+        replicate_phases_kernel<<<blocks_for(n, 256), 256, 0, e->stream>>>(e->d_sorted_ent, n, e->phase_stride, e->d_sorted4);
+        KCHECK(e);
+    }
+    cell_bounds_kernel<<<blocks_for((uint64_t)n + 1, 256), 256, 0, e->stream>>>(e->d_sorted_key, n, C, e->d_cell_start,
+                                                                                  &e->d_ctr->n_entities_in_world);
     KCHECK(e);
-    set_in_world_kernel<<<1, 1, 0, e->stream>>>(e->d_cell_start, C, e->d_ctr);
-    KCHECK(e);
-    e->n_sorted = n;
+    return CHD_OK;
+}
+
+chd_status chd_build(chd_engine* e) {
+    if (!e) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    StageTimer timer(e, CHD_STAGE_BUILD);
+    chd_status st;
+    if (!e->assigned && e->n_halo == 0) {
+        // single-GPU flow: assign + sort as one replayable graph.  The key buffers swap every assignment
+        // (handover detection compares against the previous keys), so there are two graph variants.
+        uint32_t* target = e->have_prev_key ? e->d_prev_key : e->d_key;  // buffer the new keys will be written to
+        const int slot = target == e->d_key_a ? 0 : 1;
+        uint64_t key = mix_key(mix_key(mix_key(0x6275696c64ull, e->n_own), e->have_gid), e->have_prev_key);
+        key = mix_key(key, (uint64_t)(uintptr_t)target);
+        st = run_stage(e, e->g_build[slot], key, [&]() { return build_enqueue(e, true); });
+        if (st == CHD_OK && !e->assigned) {  // replayed graph: mirror the host-side bookkeeping of chd_assign_cells
+            if (e->have_prev_key) {
+                uint32_t* t = e->d_key;
+                e->d_key = e->d_prev_key;
+                e->d_prev_key = t;
+            }
+            if (e->n_own) e->have_prev_key = true;
+            e->n_halo = 0;
+            e->assigned = true;
+        }
+    } else {
+        st = build_enqueue(e, !e->assigned);
+    }
+    if (st != CHD_OK) return st;
+    e->n_sorted = e->n_own + e->n_halo;
     e->built = true;
     e->entities_dirty = false;
     return CHD_OK;
@@ -625,10 +746,9 @@ static chd_status run_query_kernels(chd_engine* e, const QueryDev& d) {
     query_bbox_kernel<<<blocks_for(n, 256), 256, 0, e->stream>>>(e->g, d, e->d_bbox, e->d_win_size);
     KCHECK(e);
     SCAN(e, exclusive_scan<uint32_t, uint64_t>(e->d_win_size, e->d_win_off, n, e->d_scan_scratch64, e->stream));
-    window_overflow_kernel<<<1, 1, 0, e->stream>>>(e->d_win_off, n, e->lim.max_window_cells, e->d_ctr);
-    KCHECK(e);
     query_sample_kernel<<<blocks_for(n, 128), 128, 0, e->stream>>>(e->g, d, e->d_bbox, e->d_win_off, e->lim.max_window_cells, e->d_window,
-                                                                   e->d_side_cell, e->d_side_dist, e->d_side_cnt, e->d_status, e->d_qcount);
+                                                                   e->d_side_cell, e->d_side_dist, e->d_side_cnt, e->d_status, e->d_qcount,
+                                                                   &e->d_ctr->required_window_cells, &e->d_ctr->overflow);
     KCHECK(e);
     return CHD_OK;
 }
@@ -687,17 +807,10 @@ chd_status chd_query_channel_ids(chd_engine* e, const chd_query_batch* q, uint32
     return CHD_OK;
 }
 
-chd_status chd_update_interest(chd_engine* e, const chd_query_batch* q, int64_t now_ns) {
-    if (!e || !q) return CHD_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(e->mu);
-    CU(e, cudaSetDevice(e->device));
-    StageTimer timer(e, CHD_STAGE_INTEREST);
-    QueryDev d;
-    chd_status st = upload_queries(e, q, &d, true);
-    if (st != CHD_OK) return st;
+static chd_status interest_enqueue(chd_engine* e, const QueryDev& d) {
     const uint32_t n = d.n, S = e->n_slots;
     cudaStream_t s = e->stream;
-    st = run_query_kernels(e, d);
+    chd_status st = run_query_kernels(e, d);
     if (st != CHD_OK) return st;
     PairBuf& prev = e->pairs[e->cur];
     PairBuf& cur = e->pairs[e->cur ^ 1];
@@ -713,24 +826,41 @@ chd_status chd_update_interest(chd_engine* e, const chd_query_batch* q, int64_t 
         KCHECK(e);
     }
     SCAN(e, exclusive_scan<uint32_t, uint32_t>(e->d_slot_cnt, cur.off, S, e->d_scan_scratch, s));
-    pairs_total_kernel<<<1, 1, 0, s>>>(cur.off, S, P, e->d_ctr);
-    KCHECK(e);
     if (S) {
         interest_fill_kernel<<<blocks_for(S, 128), 128, 0, s>>>(e->g, S, e->d_slot_query, e->d_status, e->d_bbox, e->d_win_off, e->d_window,
                                                                 e->d_side_cell, e->d_side_dist, e->d_side_cnt, d.spot_off, prev, cur, P,
-                                                                now_ns, e->d_new_flag, e->d_gone_flag, e->d_ctr);
+                                                                e->d_time, e->d_new_flag, e->d_gone_flag, e->d_ctr);
         KCHECK(e);
     }
-    // diff lists: compact flagged pairs (deterministic order)
-    SCAN(e, exclusive_scan<uint32_t, uint32_t>(e->d_new_flag, e->d_new_off, P, e->d_scan_scratch, s, cur.off + S));
-    SCAN(e, exclusive_scan<uint32_t, uint32_t>(e->d_gone_flag, e->d_gone_off, P, e->d_scan_scratch, s, prev.off + S));
+    // diff lists: compact flagged pairs (deterministic order); one packed prefix sum serves both lists
     const unsigned grid = (unsigned)e->sm_count * 4;
-    diff_compact_kernel<<<grid, 256, 0, s>>>(e->d_new_flag, e->d_new_off, cur.off + S, P, cur.sub, cur.cell, e->g.id_start, e->d_new_sub, e->d_new_ch);
+    diff_pack_kernel<<<grid, 256, 0, s>>>(e->d_new_flag, cur.off + S, e->d_gone_flag, prev.off + S, P, e->d_diff_packed, e->d_diff_len);
     KCHECK(e);
-    diff_compact_kernel<<<grid, 256, 0, s>>>(e->d_gone_flag, e->d_gone_off, prev.off + S, P, prev.sub, prev.cell, e->g.id_start, e->d_gone_sub, e->d_gone_ch);
+    SCAN(e, exclusive_scan<uint64_t, uint64_t>(e->d_diff_packed, e->d_diff_off, P, e->d_scan_scratch64, s, e->d_diff_len));
+    diff_compact_kernel<<<grid, 256, 0, s>>>(e->d_diff_off, e->d_new_flag, cur.off + S, e->d_gone_flag, prev.off + S, P, cur, prev, e->g.id_start,
+                                             e->d_new_sub, e->d_new_ch, e->d_gone_sub, e->d_gone_ch);
     KCHECK(e);
+    return CHD_OK;
+}
+
+chd_status chd_update_interest(chd_engine* e, const chd_query_batch* q, int64_t now_ns) {
+    if (!e || !q) return CHD_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    CU(e, cudaSetDevice(e->device));
+    StageTimer timer(e, CHD_STAGE_INTEREST);
+    QueryDev d;
+    chd_status st = upload_queries(e, q, &d, true);  // H2D / D2D copies into the engine's SoA: outside the graph
+    if (st != CHD_OK) return st;
+    set_i64_kernel<<<1, 1, 0, e->stream>>>(e->d_time, now_ns);
+    KCHECK(e);
+    // the graph bakes in which staging arrays are live, the batch size and the pair-buffer parity
+    uint64_t key = mix_key(mix_key(mix_key(0x696e74ull, d.n), e->n_slots), (uint64_t)e->cur);
+    const void* present[] = {d.sub, d.kind, d.sph_cx, d.box_cx, d.cone_cx, d.spot_off, d.spot_ndist};
+    for (const void* p : present) key = mix_key(key, p != nullptr);
+    st = run_stage(e, e->g_interest[e->cur], key, [&]() { return interest_enqueue(e, d); });
+    if (st != CHD_OK) return st;
     e->cur ^= 1;
-    e->last_nq = n;
+    e->last_nq = d.n;
     return CHD_OK;
 }
 
@@ -747,16 +877,21 @@ chd_status chd_emit_visible(chd_engine* e) {
     const uint64_t P = e->lim.max_pairs;
     StageTimer timer(e, CHD_STAGE_EMIT);
     const unsigned grid = (unsigned)e->sm_count * 8;
-    pair_vcount_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, pb.cell, e->d_cell_start, e->d_vcnt);
-    KCHECK(e);
-    SCAN(e, exclusive_scan<uint32_t, uint64_t>(e->d_vcnt, e->d_voff, P, e->d_scan_scratch64, s, pb.off + S));
-    vis_off_kernel<<<blocks_for((uint64_t)S + 1, 256), 256, 0, s>>>(S, pb.off, P, e->d_voff, e->d_vis_off, e->lim.max_visible, e->d_ctr);
-    KCHECK(e);
-    emit_partition_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, e->d_voff, e->d_first_pair, e->max_tiles);
-    KCHECK(e);
+    const uint64_t key = mix_key(mix_key(0x656d6974ull, S), (uint64_t)e->cur);
+    chd_status st = run_stage(e, e->g_emit_prep[e->cur], key, [&]() -> chd_status {
+        pair_vcount_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, pb.cell, e->d_cell_start, e->d_vcnt);
+        KCHECK(e);
+        SCAN(e, exclusive_scan<uint32_t, uint64_t>(e->d_vcnt, e->d_voff, P, e->d_scan_scratch64, s, pb.off + S));
+        vis_off_kernel<<<blocks_for((uint64_t)S + 1, 256), 256, 0, s>>>(S, pb.off, P, e->d_voff, e->d_vis_off, e->lim.max_visible, e->d_ctr);
+        KCHECK(e);
+        emit_partition_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, e->d_voff, e->d_first_pair, e->max_tiles);
+        KCHECK(e);
+        return CHD_OK;
+    });
+    if (st != CHD_OK) return st;
     {
         StageTimer kt(e, CHD_STAGE_EMIT_KERNEL);
-        emit_visible_kernel<<<grid, EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted_ent,
+        emit_visible_kernel<<<grid, EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4, e->phase_stride,
                                                           e->d_first_pair, e->d_vis, e->lim.max_visible);
         KCHECK(e);
     }
@@ -780,8 +915,8 @@ chd_status chd_set_rings(chd_engine* e, const uint32_t* ring_off, uint32_t n_ent
         CU(e, cudaMemcpyAsync(e->d_ring_sender, sender, sizeof(uint32_t) * total, cudaMemcpyDefault, e->stream));
         CU(e, cudaMemcpyAsync(e->d_ring_index, index, sizeof(uint64_t) * total, cudaMemcpyDefault, e->stream));
     }
-    // ring_off[C] must equal n_entries: clamp on the device so a lying caller cannot cause out-of-bounds reads
-    clamp_ring_off_kernel<<<blocks_for((uint64_t)C + 1, 256), 256, 0, e->stream>>>(e->d_ring_off, C + 1, total);
+    // the fan-out kernel clamps ring_off to this: a lying caller cannot cause out-of-bounds reads
+    set_u32_kernel<<<1, 1, 0, e->stream>>>(e->d_ring_total, total);
     KCHECK(e);
     if (ch_msg_index) {
         CU(e, cudaMemcpyAsync(e->d_ch_msg_index, ch_msg_index, sizeof(uint64_t) * C, cudaMemcpyDefault, e->stream));
@@ -799,17 +934,22 @@ chd_status chd_fanout_tick(chd_engine* e, int64_t t_ns) {
     const uint32_t S = e->n_slots;
     const uint64_t P = e->lim.max_pairs;
     StageTimer timer(e, CHD_STAGE_FANOUT);
-    RingDev ring{e->d_ring_off, e->d_ring_arrival, e->d_ring_sender, e->d_ring_index, e->have_ch_msg_index ? e->d_ch_msg_index : nullptr};
+    set_i64_kernel<<<1, 1, 0, s>>>(e->d_time + 1, t_ns);
+    KCHECK(e);
+    RingDev ring{e->d_ring_off, e->d_ring_arrival, e->d_ring_sender, e->d_ring_index, e->have_ch_msg_index ? e->d_ch_msg_index : nullptr,
+                 e->d_ring_total};
     const unsigned grid = (unsigned)e->sm_count * 16;
-    fanout_kernel<false><<<grid, 128, 0, s>>>(pb.off + S, P, pb, e->d_conn, ring, t_ns, e->g.id_start, e->d_due_cnt, nullptr, nullptr, 0);
-    KCHECK(e);
-    SCAN(e, exclusive_scan<uint32_t, uint32_t>(e->d_due_cnt, e->d_due_off, P, e->d_scan_scratch, s, pb.off + S));
-    due_total_kernel<<<1, 1, 0, s>>>(pb.off + S, P, e->d_due_off, e->lim.max_due, e->d_ctr);
-    KCHECK(e);
-    fanout_kernel<true><<<grid, 128, 0, s>>>(pb.off + S, P, pb, e->d_conn, ring, t_ns, e->g.id_start, e->d_due_cnt, e->d_due_off, e->d_due,
-                                             e->lim.max_due);
-    KCHECK(e);
-    return CHD_OK;
+    const uint64_t key = mix_key(mix_key(mix_key(0x66616eull, S), (uint64_t)e->cur), e->have_ch_msg_index);
+    return run_stage(e, e->g_fanout[e->cur], key, [&]() -> chd_status {
+        fanout_kernel<false><<<grid, 128, 0, s>>>(pb.off + S, P, pb, e->d_conn, ring, e->d_time + 1, e->g.id_start, e->d_due_cnt, nullptr, nullptr,
+                                                  0, e->d_ctr);
+        KCHECK(e);
+        SCAN(e, exclusive_scan<uint32_t, uint32_t>(e->d_due_cnt, e->d_due_off, P, e->d_scan_scratch, s, pb.off + S));
+        fanout_kernel<true><<<grid, 128, 0, s>>>(pb.off + S, P, pb, e->d_conn, ring, e->d_time + 1, e->g.id_start, e->d_due_cnt, e->d_due_off,
+                                                 e->d_due, e->lim.max_due, e->d_ctr);
+        KCHECK(e);
+        return CHD_OK;
+    });
 }
 
 chd_status chd_summary(chd_engine* e, chd_tick_summary* out) {
@@ -1086,6 +1226,14 @@ chd_status chd_import_halo(chd_engine* e, const uint32_t* d_records, uint32_t n_
 /* ------------------------------------------------------------------ instrumentation ---- */
 
 uint64_t chd_launch_count(const chd_engine* e) { return e ? e->n_launch : 0; }
+
+chd_status chd_enable_graphs(chd_engine* e, int on) {
+    if (!e) return CHD_ERR_INVALID;
+    e->use_graphs = on != 0;
+    return CHD_OK;
+}
+
+uint64_t chd_graph_launch_count(const chd_engine* e) { return e ? e->graph_launches : 0; }
 
 chd_status chd_profile_enable(chd_engine* e, int on) {
     if (!e) return CHD_ERR_INVALID;

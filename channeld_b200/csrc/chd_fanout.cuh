@@ -18,6 +18,7 @@ struct RingDev {
     const uint32_t* sender;
     const uint64_t* index;
     const uint64_t* channel_msg_index;  // [C] or nullptr
+    const uint32_t* total;              // entries uploaded (device scalar): offsets are clamped to it
 };
 
 constexpr uint32_t FANOUT_MAX_STEPS = 1u << 16;
@@ -25,9 +26,17 @@ constexpr uint32_t FANOUT_MAX_STEPS = 1u << 16;
 template <bool WRITE>
 __global__ void __launch_bounds__(128)
     fanout_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, PairBuf pb, const uint32_t* __restrict__ conn_id,
-                  RingDev ring, int64_t t, uint32_t id_start, uint32_t* __restrict__ due_cnt, const uint32_t* __restrict__ due_off,
-                  chd_due* __restrict__ due, uint32_t due_cap) {
+                  RingDev ring, const int64_t* __restrict__ t_ptr, uint32_t id_start, uint32_t* __restrict__ due_cnt, const uint32_t* __restrict__ due_off,
+                  chd_due* __restrict__ due, uint32_t due_cap, Counters* __restrict__ ctr) {
     const uint64_t n = min((uint64_t)*n_pairs_ptr, pair_cap);
+    const int64_t t = *t_ptr;  // device-resident so the launch can be replayed from a CUDA graph
+    const uint32_t ring_total = *ring.total;
+    if (WRITE && blockIdx.x == 0 && threadIdx.x == 0) {
+        const uint32_t total = due_off[n];
+        ctr->n_due = total;
+        ctr->required_due = total;
+        if (total > due_cap) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_DUE);
+    }
     for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < n; p += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t interval = pb.interval[p];
         const int64_t step_ns = (int64_t)interval * 1000000ll;  // ChannelTime.AddMs (channel.go:30-32)
@@ -43,7 +52,7 @@ __global__ void __launch_bounds__(128)
         const uint32_t s = pb.sub[p];
         const uint32_t me = conn_id[s];
         const bool skip_self = flags & PF_SKIP_SELF;
-        const uint32_t r0 = ring.off[c], r1 = ring.off[c + 1];
+        const uint32_t r0 = min(ring.off[c], ring_total), r1 = min(ring.off[c + 1], ring_total);
         uint32_t o = WRITE ? due_off[p] : 0u;
         const bool can_write = WRITE && due_off[n] <= due_cap;
         const uint32_t max_steps = interval ? FANOUT_MAX_STEPS : 1u;  // interval 0: the reference never terminates
@@ -103,15 +112,6 @@ __global__ void __launch_bounds__(128)
             due_cnt[p] = n_out;
         }
     }
-}
-
-__global__ void due_total_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, const uint32_t* __restrict__ due_off,
-                                 uint32_t due_cap, Counters* __restrict__ ctr) {
-    const uint64_t n = min((uint64_t)*n_pairs_ptr, pair_cap);
-    const uint32_t total = due_off[n];
-    ctr->n_due = total;
-    ctr->required_due = total;
-    if (total > due_cap) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_DUE);
 }
 
 }  // namespace chd

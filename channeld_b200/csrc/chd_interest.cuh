@@ -62,13 +62,20 @@ __global__ void __launch_bounds__(128)
                          const Bbox* __restrict__ bbox, const uint64_t* __restrict__ win_off, const uint32_t* __restrict__ window,
                          const uint32_t* __restrict__ side_cell, const uint32_t* __restrict__ side_dist,
                          const uint32_t* __restrict__ side_cnt, const uint32_t* __restrict__ spot_off, PairBuf prev, PairBuf cur,
-                         uint64_t pair_cap, int64_t now_ns, uint32_t* __restrict__ new_flag, uint32_t* __restrict__ gone_flag,
+                         uint64_t pair_cap, const int64_t* __restrict__ now_ptr, uint32_t* __restrict__ new_flag, uint32_t* __restrict__ gone_flag,
                          Counters* __restrict__ ctr) {
     __shared__ uint32_t s_new, s_gone, s_kept;
     if (threadIdx.x == 0) s_new = s_gone = s_kept = 0;
     __syncthreads();
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t now_ns = *now_ptr;  // device-resident so the launch can be replayed from a CUDA graph
     uint32_t n_new = 0, n_gone = 0, n_kept = 0;
+    if (s == 0) {
+        const unsigned long long p = cur.off[n_slots];
+        ctr->n_pairs = p;
+        ctr->required_pairs = p;
+        if (p > pair_cap) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_PAIRS);
+    }
     if (s < n_slots && cur.off[n_slots] <= pair_cap) {
         const int32_t q = slot_query[s];
         uint32_t pp = prev.off[s];
@@ -140,17 +147,37 @@ __global__ void __launch_bounds__(128)
     }
 }
 
+// Both diff lists share ONE prefix sum: element p of the scan input packs new_flag[p] (cur pair p) in the low
+// 32 bits and gone_flag[p] (prev pair p) in the high 32 bits.
+__global__ void __launch_bounds__(256)
+    diff_pack_kernel(const uint32_t* __restrict__ new_flag, const uint32_t* __restrict__ n_cur_ptr, const uint32_t* __restrict__ gone_flag,
+                     const uint32_t* __restrict__ n_prev_ptr, uint64_t cap, uint64_t* __restrict__ packed, uint32_t* __restrict__ len_out) {
+    const uint64_t nc = min((uint64_t)*n_cur_ptr, cap), np = min((uint64_t)*n_prev_ptr, cap);
+    const uint64_t n = max(nc, np);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *len_out = (uint32_t)n;  // live length of the packed scan
+    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < n; p += (uint64_t)gridDim.x * blockDim.x)
+        packed[p] = (uint64_t)(p < nc ? new_flag[p] : 0u) | ((uint64_t)(p < np ? gone_flag[p] : 0u) << 32);
+}
+
 // (sub, channel id) of flagged pairs, compacted in pair order
 __global__ void __launch_bounds__(256)
-    diff_compact_kernel(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ flag_off, const uint32_t* __restrict__ n_ptr,
-                        uint64_t n_cap, const uint32_t* __restrict__ pair_sub, const uint32_t* __restrict__ pair_cell,
-                        uint32_t id_start, uint32_t* __restrict__ out_sub, uint32_t* __restrict__ out_channel) {
-    const uint64_t n = min((uint64_t)*n_ptr, n_cap);
+    diff_compact_kernel(const uint64_t* __restrict__ packed_off, const uint32_t* __restrict__ new_flag, const uint32_t* __restrict__ n_cur_ptr,
+                        const uint32_t* __restrict__ gone_flag, const uint32_t* __restrict__ n_prev_ptr, uint64_t cap, PairBuf cur,
+                        PairBuf prev, uint32_t id_start, uint32_t* __restrict__ new_sub, uint32_t* __restrict__ new_ch,
+                        uint32_t* __restrict__ gone_sub, uint32_t* __restrict__ gone_ch) {
+    const uint64_t nc = min((uint64_t)*n_cur_ptr, cap), np = min((uint64_t)*n_prev_ptr, cap);
+    const uint64_t n = max(nc, np);
     for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < n; p += (uint64_t)gridDim.x * blockDim.x) {
-        if (flag[p]) {
-            const uint32_t o = flag_off[p];
-            out_sub[o] = pair_sub[p];
-            out_channel[o] = pair_cell[p] + id_start;
+        const uint64_t off = packed_off[p];
+        if (p < nc && new_flag[p]) {
+            const uint32_t o = (uint32_t)off;
+            new_sub[o] = cur.sub[p];
+            new_ch[o] = cur.cell[p] + id_start;
+        }
+        if (p < np && gone_flag[p]) {
+            const uint32_t o = (uint32_t)(off >> 32);
+            gone_sub[o] = prev.sub[p];
+            gone_ch[o] = prev.cell[p] + id_start;
         }
     }
 }

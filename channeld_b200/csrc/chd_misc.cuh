@@ -9,23 +9,6 @@ __global__ void cell_key_to_id_kernel(uint32_t* __restrict__ k, uint32_t n, uint
     if (i < n) k[i] = k[i] >= cells ? 0u : k[i] + id_start;
 }
 
-__global__ void set_in_world_kernel(const uint32_t* __restrict__ cell_start, uint32_t cells, Counters* __restrict__ ctr) {
-    ctr->n_entities_in_world = cell_start[cells];
-}
-
-__global__ void window_overflow_kernel(const uint64_t* __restrict__ win_off, uint32_t n, uint64_t cap, Counters* __restrict__ ctr) {
-    const uint64_t need = win_off[n];
-    ctr->required_window_cells = need;
-    if (need > cap) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_WINDOW);
-}
-
-__global__ void pairs_total_kernel(const uint32_t* __restrict__ off, uint32_t n_slots, uint64_t cap, Counters* __restrict__ ctr) {
-    const uint64_t p = off[n_slots];
-    ctr->n_pairs = p;
-    ctr->required_pairs = p;
-    if (p > cap) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_PAIRS);
-}
-
 __global__ void narrow_offsets_kernel(const uint64_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (uint32_t)in[i];
@@ -34,11 +17,6 @@ __global__ void narrow_offsets_kernel(const uint64_t* __restrict__ in, uint32_t 
 __global__ void add_const_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t c, uint32_t* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i] + c;
-}
-
-__global__ void clamp_ring_off_kernel(uint32_t* __restrict__ off, uint32_t n, uint32_t total) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && off[i] > total) off[i] = total;
 }
 
 // ---- X-slab sharding.  A record is (global entity id, cell index).

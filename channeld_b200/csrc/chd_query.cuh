@@ -113,9 +113,14 @@ struct WinRef {
 __global__ void __launch_bounds__(128)
     query_sample_kernel(GridDev g, QueryDev q, const Bbox* __restrict__ bbox, const uint64_t* __restrict__ win_off, uint64_t win_cap,
                         uint32_t* __restrict__ window, uint32_t* __restrict__ side_cell, uint32_t* __restrict__ side_dist,
-                        uint32_t* __restrict__ side_cnt, uint32_t* __restrict__ status, uint32_t* __restrict__ count) {
+                        uint32_t* __restrict__ side_cnt, uint32_t* __restrict__ status, uint32_t* __restrict__ count,
+                        unsigned long long* __restrict__ required_window_cells, uint32_t* __restrict__ overflow) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= q.n) return;
+    if (i == 0) {
+        *required_window_cells = win_off[q.n];
+        if (win_off[q.n] > win_cap) atomicOr(overflow, (uint32_t)CHD_OVF_WINDOW);
+    }
     if (win_off[q.n] > win_cap) {
         status[i] = CHD_Q_OK;
         count[i] = 0;

@@ -256,6 +256,12 @@ class Engine:
     def launch_count(self):
         return int(self.L.chd_launch_count(self.h))
 
+    def enable_graphs(self, on=True):
+        self._ck(self.L.chd_enable_graphs(self.h, int(bool(on))))
+
+    def graph_launch_count(self):
+        return int(self.L.chd_graph_launch_count(self.h))
+
     def profile_enable(self, on=True):
         self._ck(self.L.chd_profile_enable(self.h, int(bool(on))))
 

@@ -262,6 +262,11 @@ uint32_t chd_damping_interval_ms(uint32_t dist, uint32_t default_ms);
  * exactly the emit_visible kernel (the dominant HBM term; bench.py's roofline uses it). */
 enum { CHD_STAGE_BUILD = 0, CHD_STAGE_INTEREST, CHD_STAGE_EMIT, CHD_STAGE_EMIT_KERNEL, CHD_STAGE_FANOUT, CHD_STAGE_COUNT };
 uint64_t chd_launch_count(const chd_engine* e);
+/* The launch-bound stages (build, interest update, emit preparation, fan-out) are replayed as CUDA graphs once
+ * their shape (entity / query / subscriber counts) has been stable for two ticks.  chd_enable_graphs(e, 0) forces
+ * direct launches; chd_graph_launch_count reports how many stage executions were graph replays. */
+chd_status chd_enable_graphs(chd_engine* e, int on);
+uint64_t chd_graph_launch_count(const chd_engine* e);
 chd_status chd_profile_enable(chd_engine* e, int on);
 chd_status chd_profile_get(chd_engine* e, int stage, double* total_ms, uint64_t* samples);
 

@@ -457,3 +457,54 @@ def test_handover_detection(chd, oracle):
     np.testing.assert_array_equal(src[order], old[moved])
     np.testing.assert_array_equal(dst[order], new[moved])
     assert len(moved) > 1000
+
+
+def test_graph_replay_matches_direct_and_oracle(chd, oracle):
+    """Six full ticks with moving entities: the CUDA-graph replay path (stable shapes) must give the same pairs,
+    visible lists, diff counts, handover lists and fan-out decisions as direct launches, and match the oracle."""
+    wc = chd.synth.scaled(chd.synth.CONFIGS["benchmark"], 30_000, 3_000)
+    og = _oracle_grid(wc)
+    results = {}
+    for use_graphs in (True, False):
+        e = chd.engine.Engine(wc.cfg(), wc.n_entities, wc.n_subscribers, max_visible=1 << 22)
+        e.enable_graphs(use_graphs)
+        ex, ez = chd.synth.entities(wc)
+        conn, _, _, _ = chd.synth.subscribers(wc, ex, ez)
+        e.set_subscribers(conn)
+        ring_state, out = None, []
+        for tick in range(6):
+            t = (tick + 1) * 33_000_000
+            ex, ez = chd.synth.move_entities(wc, ex, ez, tick, 400.0)
+            _, cx, cz, r = chd.synth.subscribers(wc, ex, ez)
+            e.set_entities(ex, ez)
+            batch, keep = chd.engine.make_batch(len(cx), sub=np.arange(len(cx), dtype=np.uint32), sphere=(cx, cz, r))
+            ring_state, off, arr, snd, idx, cmi = chd.synth.update_rings(wc, tick, t, 33_000_000, 4, len(conn), ring_len=16, state=ring_state)
+            e.set_rings(off, arr, snd, idx, cmi)
+            s = e.tick(batch, t, chd.capi.TICK_ALL)
+            pairs = e.get_pairs(s.n_pairs)
+            voff, vis = e.get_visible()
+            due = e.get_due(s.n_due)
+            ho = e.get_handover(s.n_handover)
+            order = np.argsort(ho[0])
+            out.append((s.as_dict(), pairs, voff, vis, due, tuple(a[order] for a in ho)))
+            if use_graphs:
+                want = oracle.sphere_tick(og, ex, ez, cx, cz, r)
+                np.testing.assert_array_equal(pairs["channel"], want["pair_cell"])
+                np.testing.assert_array_equal(pairs["dist"], want["pair_dist"])
+                np.testing.assert_array_equal(voff, want["vis_off"])
+                np.testing.assert_array_equal(vis, want["vis_entity"])
+        results[use_graphs] = out
+        if use_graphs:
+            assert e.graph_launch_count() >= 8, e.graph_launch_count()
+        else:
+            assert e.graph_launch_count() == 0
+    for a, b in zip(results[True], results[False]):
+        assert a[0] == b[0]
+        for k in a[1]:
+            np.testing.assert_array_equal(a[1][k], b[1][k])
+        np.testing.assert_array_equal(a[2], b[2])
+        np.testing.assert_array_equal(a[3], b[3])
+        np.testing.assert_array_equal(a[4], b[4])
+        for x, y in zip(a[5], b[5]):
+            np.testing.assert_array_equal(x, y)
+    assert sum(r[0]["n_due"] for r in results[True]) > 1000 and sum(r[0]["n_handover"] for r in results[True]) > 100
