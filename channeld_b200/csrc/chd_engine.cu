@@ -41,6 +41,9 @@ struct chd_engine {
         uint64_t nodes = 0;
     };
     bool use_graphs = true;
+    bool overlap_fanout = true;        // chd_tick runs the fan-out stage on aux_stream concurrently with emit
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     GraphSlot g_build[2], g_interest[2], g_emit_prep[2], g_fanout[2];
     uint64_t graph_launches = 0, graph_captures = 0;
     uint32_t* d_key_a = nullptr;  // identity of the first key buffer (graph slot selection)
@@ -107,6 +110,7 @@ struct chd_engine {
     uint64_t *d_ring_index = nullptr, *d_ch_msg_index = nullptr;
     bool have_ch_msg_index = false;
     uint32_t *d_due_cnt = nullptr, *d_due_off = nullptr;
+    uint32_t *d_cell_pairs = nullptr, *d_cell_pair_off = nullptr, *d_cell_cursor = nullptr, *d_by_cell = nullptr;
     chd_due* d_due = nullptr;
     // counters
     Counters* d_ctr = nullptr;
@@ -292,6 +296,9 @@ void chd_destroy(chd_engine* e) {
     }
     if (e->h_ctr) cudaFreeHost(e->h_ctr);
     if (e->h_u32) cudaFreeHost(e->h_u32);
+    if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -370,6 +377,9 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
     CCU(cudaSetDevice(device));
     CCU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     e->own_stream = true;
+    CCU(cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking));
+    CCU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    CCU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
     CCU(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device));
 
     GridDev& g = e->g;
@@ -421,7 +431,8 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
          dalloc(e, &e->d_vis_off, S + 1) && dalloc(e, &e->d_vis, L.max_visible);
     ok = ok && dalloc(e, &e->d_ring_off, C + 1) && dalloc(e, &e->d_ring_arrival, (uint64_t)L.max_ring_entries) &&
          dalloc(e, &e->d_ring_sender, (uint64_t)L.max_ring_entries) && dalloc(e, &e->d_ring_index, (uint64_t)L.max_ring_entries) &&
-         dalloc(e, &e->d_ch_msg_index, C) && dalloc(e, &e->d_due_cnt, P) && dalloc(e, &e->d_due_off, P + 1) &&
+         dalloc(e, &e->d_ch_msg_index, C) && dalloc(e, &e->d_due_cnt, P) && dalloc(e, &e->d_cell_pairs, C + 1) &&
+         dalloc(e, &e->d_cell_pair_off, C + 2) && dalloc(e, &e->d_cell_cursor, C + 1) && dalloc(e, &e->d_by_cell, P) && dalloc(e, &e->d_due_off, P + 1) &&
          dalloc(e, &e->d_due, (uint64_t)L.max_due) && dalloc(e, &e->d_ctr, 1) && dalloc(e, &e->d_time, 2) &&
          dalloc(e, &e->d_ring_total, 1);
     if (!ok) {
@@ -817,6 +828,8 @@ static chd_status interest_enqueue(chd_engine* e, const QueryDev& d) {
     const uint64_t P = e->lim.max_pairs;
     CU(e, cudaMemsetAsync(e->d_slot_query, 0xFF, sizeof(int32_t) * (uint64_t)(S ? S : 1), s));
     CU(e, cudaMemsetAsync(&e->d_ctr->n_query_errors, 0, 4 * 4, s));  // n_query_errors, n_sub_new, n_unsub, n_kept
+    CU(e, cudaMemsetAsync(e->d_cell_pairs, 0, sizeof(uint32_t) * ((uint64_t)e->g.cells + 1), s));
+    CU(e, cudaMemsetAsync(e->d_cell_cursor, 0, sizeof(uint32_t) * ((uint64_t)e->g.cells + 1), s));
     if (n) {
         slot_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(d.sub, n, S, e->d_slot_query);
         KCHECK(e);
@@ -829,9 +842,13 @@ static chd_status interest_enqueue(chd_engine* e, const QueryDev& d) {
     if (S) {
         interest_fill_kernel<<<blocks_for(S, 128), 128, 0, s>>>(e->g, S, e->d_slot_query, e->d_status, e->d_bbox, e->d_win_off, e->d_window,
                                                                 e->d_side_cell, e->d_side_dist, e->d_side_cnt, d.spot_off, prev, cur, P,
-                                                                e->d_time, e->d_new_flag, e->d_gone_flag, e->d_ctr);
+                                                                e->d_time, e->d_new_flag, e->d_gone_flag, e->d_cell_pairs, e->d_ctr);
         KCHECK(e);
     }
+    // pairs grouped by cell for the fan-out pass
+    SCAN(e, exclusive_scan<uint32_t, uint32_t>(e->d_cell_pairs, e->d_cell_pair_off, e->g.cells, e->d_scan_scratch, s));
+    pairs_by_cell_kernel<<<(unsigned)e->sm_count * 4, 256, 0, s>>>(cur.off + S, P, cur.cell, e->d_cell_pair_off, e->d_cell_cursor, e->d_by_cell);
+    KCHECK(e);
     // diff lists: compact flagged pairs (deterministic order); one packed prefix sum serves both lists
     const unsigned grid = (unsigned)e->sm_count * 4;
     diff_pack_kernel<<<grid, 256, 0, s>>>(e->d_new_flag, cur.off + S, e->d_gone_flag, prev.off + S, P, e->d_diff_packed, e->d_diff_len);
@@ -942,11 +959,11 @@ chd_status chd_fanout_tick(chd_engine* e, int64_t t_ns) {
     const uint64_t key = mix_key(mix_key(mix_key(0x66616eull, S), (uint64_t)e->cur), e->have_ch_msg_index);
     return run_stage(e, e->g_fanout[e->cur], key, [&]() -> chd_status {
         fanout_kernel<false><<<grid, 128, 0, s>>>(pb.off + S, P, pb, e->d_conn, ring, e->d_time + 1, e->g.id_start, e->d_due_cnt, nullptr, nullptr,
-                                                  0, e->d_ctr);
+                                                  0, e->d_by_cell, e->d_ctr);
         KCHECK(e);
         SCAN(e, exclusive_scan<uint32_t, uint32_t>(e->d_due_cnt, e->d_due_off, P, e->d_scan_scratch, s, pb.off + S));
         fanout_kernel<true><<<grid, 128, 0, s>>>(pb.off + S, P, pb, e->d_conn, ring, e->d_time + 1, e->g.id_start, e->d_due_cnt, e->d_due_off,
-                                                 e->d_due, e->lim.max_due, e->d_ctr);
+                                                 e->d_due, e->lim.max_due, e->d_by_cell, e->d_ctr);
         KCHECK(e);
         return CHD_OK;
     });
@@ -985,13 +1002,29 @@ chd_status chd_tick(chd_engine* e, const chd_query_batch* q, int64_t t_ns, uint3
         st = chd_update_interest(e, q, t_ns);
         if (st != CHD_OK) return st;
     }
-    if (flags & CHD_TICK_EMIT) {
+    const bool both = (flags & CHD_TICK_EMIT) && (flags & CHD_TICK_FANOUT);
+    if (both && e->overlap_fanout && e->aux_stream) {
+        // emit is HBM-bound, fan-out is latency-bound and they touch disjoint state: run them concurrently
+        cudaStream_t main_stream = e->stream;
+        CU(e, cudaEventRecord(e->ev_fork, main_stream));
+        CU(e, cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0));
+        e->stream = e->aux_stream;
+        st = chd_fanout_tick(e, t_ns);
+        e->stream = main_stream;
+        if (st != CHD_OK) return st;
+        CU(e, cudaEventRecord(e->ev_join, e->aux_stream));
         st = chd_emit_visible(e);
         if (st != CHD_OK) return st;
-    }
-    if (flags & CHD_TICK_FANOUT) {
-        st = chd_fanout_tick(e, t_ns);
-        if (st != CHD_OK) return st;
+        CU(e, cudaStreamWaitEvent(main_stream, e->ev_join, 0));
+    } else {
+        if (flags & CHD_TICK_EMIT) {
+            st = chd_emit_visible(e);
+            if (st != CHD_OK) return st;
+        }
+        if (flags & CHD_TICK_FANOUT) {
+            st = chd_fanout_tick(e, t_ns);
+            if (st != CHD_OK) return st;
+        }
     }
     if (out) return chd_summary(e, out);
     return CHD_OK;

@@ -27,7 +27,7 @@ template <bool WRITE>
 __global__ void __launch_bounds__(128)
     fanout_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, PairBuf pb, const uint32_t* __restrict__ conn_id,
                   RingDev ring, const int64_t* __restrict__ t_ptr, uint32_t id_start, uint32_t* __restrict__ due_cnt, const uint32_t* __restrict__ due_off,
-                  chd_due* __restrict__ due, uint32_t due_cap, Counters* __restrict__ ctr) {
+                  chd_due* __restrict__ due, uint32_t due_cap, const uint32_t* __restrict__ by_cell, Counters* __restrict__ ctr) {
     const uint64_t n = min((uint64_t)*n_pairs_ptr, pair_cap);
     const int64_t t = *t_ptr;  // device-resident so the launch can be replayed from a CUDA graph
     const uint32_t ring_total = *ring.total;
@@ -37,7 +37,11 @@ __global__ void __launch_bounds__(128)
         ctr->required_due = total;
         if (total > due_cap) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_DUE);
     }
-    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < n; p += (uint64_t)gridDim.x * blockDim.x) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        // pairs are visited grouped by cell: neighbouring lanes walk the same ring (uniform-address loads);
+        // results are written at positions derived from the canonical pair index p, so the output order
+        // (slot, channel, step) does not depend on the grouping order.
+        const uint64_t p = by_cell[i];
         const uint32_t interval = pb.interval[p];
         const int64_t step_ns = (int64_t)interval * 1000000ll;  // ChannelTime.AddMs (channel.go:30-32)
         int64_t last = pb.last[p];
