@@ -41,9 +41,9 @@ struct chd_engine {
         uint64_t nodes = 0;
     };
     bool use_graphs = true;
-    bool overlap_fanout = true;        // chd_tick runs the fan-out stage on aux_stream concurrently with emit
+    bool overlap_fanout = true;        // chd_tick runs interest + fan-out on aux_stream concurrently with build + emit
     cudaStream_t aux_stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_interest = nullptr;
     GraphSlot g_build[2], g_interest[2], g_emit_prep[2], g_fanout[2];
     uint64_t graph_launches = 0, graph_captures = 0;
     uint32_t* d_key_a = nullptr;  // identity of the first key buffer (graph slot selection)
@@ -299,6 +299,7 @@ void chd_destroy(chd_engine* e) {
     if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->ev_interest) cudaEventDestroy(e->ev_interest);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -359,7 +360,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
     if (!L.max_visible) L.max_visible = 1u << 20;
     if (!L.max_ring_entries) L.max_ring_entries = 1u << 16;
     if (!L.max_due) L.max_due = 1u << 16;
-    if (L.max_pairs >= 0xFFFFFFF0ull || L.max_window_cells >= (1ull << 40)) {
+    if (L.max_pairs >= 0xFFFFFFF0ull || L.max_window_cells >= (1ull << 40) || L.max_entities >= (1u << 30)) {
         g_create_error = "limits too large (pairs are indexed with 32 bits)";
         delete e;
         return CHD_ERR_INVALID;
@@ -380,6 +381,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
     CCU(cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking));
     CCU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     CCU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    CCU(cudaEventCreateWithFlags(&e->ev_interest, cudaEventDisableTiming));
     CCU(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device));
 
     GridDev& g = e->g;
@@ -908,7 +910,7 @@ chd_status chd_emit_visible(chd_engine* e) {
     if (st != CHD_OK) return st;
     {
         StageTimer kt(e, CHD_STAGE_EMIT_KERNEL);
-        emit_visible_kernel<<<grid, EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4, e->phase_stride,
+        emit_visible_kernel<<<(unsigned)e->sm_count * 4, EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4, e->phase_stride,
                                                           e->d_first_pair, e->d_vis, e->lim.max_visible);
         KCHECK(e);
     }
@@ -994,34 +996,50 @@ chd_status chd_summary(chd_engine* e, chd_tick_summary* out) {
 chd_status chd_tick(chd_engine* e, const chd_query_batch* q, int64_t t_ns, uint32_t flags, chd_tick_summary* out) {
     if (!e) return CHD_ERR_INVALID;
     chd_status st;
-    if ((flags & CHD_TICK_BUILD) && (e->entities_dirty || !e->built)) {
-        st = chd_build(e);
-        if (st != CHD_OK) return st;
-    }
-    if (q) {
-        st = chd_update_interest(e, q, t_ns);
-        if (st != CHD_OK) return st;
-    }
-    const bool both = (flags & CHD_TICK_EMIT) && (flags & CHD_TICK_FANOUT);
-    if (both && e->overlap_fanout && e->aux_stream) {
-        // emit is HBM-bound, fan-out is latency-bound and they touch disjoint state: run them concurrently
+    const bool need_build = (flags & CHD_TICK_BUILD) && (e->entities_dirty || !e->built);
+    const bool do_emit = flags & CHD_TICK_EMIT, do_fanout = flags & CHD_TICK_FANOUT;
+    if (e->overlap_fanout && e->aux_stream && (q || do_fanout) && (need_build || do_emit)) {
+        // Dependency graph of a tick:   build ----------------+--> emit
+        //                               interest --> fan-out  |      (emit needs the cell CSR and the new pairs)
+        // The build / emit chain (HBM-bound) runs on the main stream, the interest / fan-out chain
+        // (latency-bound, disjoint state) on aux_stream; they are joined before the summary.
         cudaStream_t main_stream = e->stream;
         CU(e, cudaEventRecord(e->ev_fork, main_stream));
         CU(e, cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0));
         e->stream = e->aux_stream;
-        st = chd_fanout_tick(e, t_ns);
+        st = q ? chd_update_interest(e, q, t_ns) : CHD_OK;
+        if (st == CHD_OK) {
+            cudaError_t r = cudaEventRecord(e->ev_interest, e->aux_stream);
+            if (r != cudaSuccess) st = CHD_ERR_CUDA;
+        }
+        if (st == CHD_OK && do_fanout) st = chd_fanout_tick(e, t_ns);
         e->stream = main_stream;
         if (st != CHD_OK) return st;
         CU(e, cudaEventRecord(e->ev_join, e->aux_stream));
-        st = chd_emit_visible(e);
-        if (st != CHD_OK) return st;
-        CU(e, cudaStreamWaitEvent(main_stream, e->ev_join, 0));
-    } else {
-        if (flags & CHD_TICK_EMIT) {
+        if (need_build) {
+            st = chd_build(e);
+            if (st != CHD_OK) return st;
+        }
+        if (do_emit) {
+            CU(e, cudaStreamWaitEvent(main_stream, e->ev_interest, 0));
             st = chd_emit_visible(e);
             if (st != CHD_OK) return st;
         }
-        if (flags & CHD_TICK_FANOUT) {
+        CU(e, cudaStreamWaitEvent(main_stream, e->ev_join, 0));
+    } else {
+        if (need_build) {
+            st = chd_build(e);
+            if (st != CHD_OK) return st;
+        }
+        if (q) {
+            st = chd_update_interest(e, q, t_ns);
+            if (st != CHD_OK) return st;
+        }
+        if (do_emit) {
+            st = chd_emit_visible(e);
+            if (st != CHD_OK) return st;
+        }
+        if (do_fanout) {
             st = chd_fanout_tick(e, t_ns);
             if (st != CHD_OK) return st;
         }

@@ -1,0 +1,250 @@
+// Package channeld (drop this file into pkg/channeld of channeldorg/channeld @ 61fa8add).
+//
+// GpuStaticGrid2DSpatialController implements the SpatialController interface (spatial.go:17-35) on top of
+// libchd_b200.so through cgo.  It embeds the reference StaticGrid2DSpatialController for the control-plane
+// methods that stay in Go (CreateChannels, Tick's server-slot bookkeeping, the handover orchestration inside
+// Notify) and forwards the data-parallel methods to the GPU engine.
+//
+// UN-RUN: this image has no Go toolchain; the file is written against include/chd_gpu.h and has not been
+// compiled.  INTEGRATION.md lists the three-line change to InitSpatialController that selects it.
+package channeld
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../channeld_b200 -lchd_b200 -Wl,-rpath,${SRCDIR}/../../channeld_b200
+#include <stdlib.h>
+#include "chd_gpu.h"
+*/
+import "C"
+
+import (
+	"encoding/json"
+	"errors"
+	"fmt"
+	"sync"
+	"unsafe"
+
+	"github.com/channeldorg/channeld/pkg/channeldpb"
+	"github.com/channeldorg/channeld/pkg/common"
+)
+
+type GpuStaticGrid2DSpatialController struct {
+	StaticGrid2DSpatialController // LoadConfig fields, GetRegions, CreateChannels, Tick, Notify orchestration
+
+	engine *C.chd_engine
+	mu     sync.Mutex // chd_cell_of / chd_query_channel_ids are internally locked; this guards engine lifetime
+}
+
+// LoadConfig (spatial.go:141-159) + engine creation.  ServerInterestBorderSize == 0 is tolerated like
+// InitSpatialController does (it drops LoadConfig's error, spatial.go:68).
+func (ctl *GpuStaticGrid2DSpatialController) LoadConfig(config []byte) error {
+	if err := json.Unmarshal(config, &ctl.StaticGrid2DSpatialController); err != nil {
+		return err
+	}
+	cfg := C.chd_grid_cfg{
+		world_offset_x: C.double(ctl.WorldOffsetX), world_offset_z: C.double(ctl.WorldOffsetZ),
+		grid_width: C.double(ctl.GridWidth), grid_height: C.double(ctl.GridHeight),
+		grid_cols: C.uint32_t(ctl.GridCols), grid_rows: C.uint32_t(ctl.GridRows),
+		server_cols: C.uint32_t(ctl.ServerCols), server_rows: C.uint32_t(ctl.ServerRows),
+		server_interest_border_size: C.uint32_t(ctl.ServerInterestBorderSize),
+		channel_id_start:            C.uint32_t(GlobalSettings.SpatialChannelIdStart),
+	}
+	var lim C.chd_limits
+	C.chd_default_limits(&cfg, 1<<20, 1<<17, &lim)
+	lim.default_fanout_interval_ms = C.uint32_t(GlobalSettings.GetChannelSettings(channeldpb.ChannelType_SPATIAL).DefaultFanOutIntervalMs)
+	lim.default_fanout_delay_ms = C.int32_t(GlobalSettings.GetChannelSettings(channeldpb.ChannelType_SPATIAL).DefaultFanOutDelayMs)
+	if st := C.chd_create(&cfg, &lim, 0, &ctl.engine); st != C.CHD_OK {
+		return fmt.Errorf("chd_create: %s", C.GoString(C.chd_last_error(nil)))
+	}
+	return nil
+}
+
+// GetChannelId (spatial.go:161-163).  One position per cgo call is only for interface compatibility; the
+// batched form below (handleQuerySpatialChannel, message_spatial.go:335-370) is the one to use on hot paths.
+func (ctl *GpuStaticGrid2DSpatialController) GetChannelId(info common.SpatialInfo) (common.ChannelId, error) {
+	ids, err := ctl.GetChannelIds([]float64{info.X}, []float64{info.Z})
+	if err != nil {
+		return 0, err
+	}
+	if ids[0] == 0 {
+		return 0, fmt.Errorf("position (%f, %f) is outside the grid", info.X, info.Z)
+	}
+	return common.ChannelId(ids[0]), nil
+}
+
+func (ctl *GpuStaticGrid2DSpatialController) GetChannelIds(x, z []float64) ([]uint32, error) {
+	n := len(x)
+	out := make([]uint32, n)
+	if n == 0 {
+		return out, nil
+	}
+	st := C.chd_cell_of(ctl.engine, (*C.double)(unsafe.Pointer(&x[0])), (*C.double)(unsafe.Pointer(&z[0])), C.uint32_t(n),
+		(*C.uint32_t)(unsafe.Pointer(&out[0])))
+	if st != C.CHD_OK {
+		return nil, errors.New(C.GoString(C.chd_last_error(ctl.engine)))
+	}
+	return out, nil
+}
+
+// QueryChannelIds (spatial.go:182-317) for one query: a batch of one through chd_query_channel_ids.
+func (ctl *GpuStaticGrid2DSpatialController) QueryChannelIds(query *channeldpb.SpatialInterestQuery) (map[common.ChannelId]uint, error) {
+	if query == nil {
+		return nil, fmt.Errorf("query is nil")
+	}
+	var b C.chd_query_batch
+	b.n = 1
+	kind := C.uint8_t(0)
+	var sph [3]C.double
+	var box [4]C.double
+	var cone [6]C.double
+	var spotOff [2]C.uint32_t
+	var spotN C.uint32_t
+	var sx, sz []C.double
+	var sd []C.uint32_t
+	if q := query.SpotsAOI; q != nil {
+		kind |= C.CHD_AOI_SPOTS
+		for i, s := range q.Spots {
+			sx, sz = append(sx, C.double(s.X)), append(sz, C.double(s.Z))
+			if i < len(q.Dists) {
+				sd = append(sd, C.uint32_t(q.Dists[i]))
+			} else {
+				sd = append(sd, 0)
+			}
+		}
+		spotOff[1] = C.uint32_t(len(sx))
+		if len(q.Dists) < len(q.Spots) {
+			spotN = C.uint32_t(len(q.Dists))
+		} else {
+			spotN = C.uint32_t(len(q.Spots))
+		}
+	}
+	if q := query.BoxAOI; q != nil {
+		if q.Center == nil || q.Extent == nil {
+			return nil, errors.New("BoxAOI with nil Center/Extent") // the reference would panic (spatial.go:205)
+		}
+		kind |= C.CHD_AOI_BOX
+		box = [4]C.double{C.double(q.Center.X), C.double(q.Center.Z), C.double(q.Extent.X), C.double(q.Extent.Z)}
+	}
+	if q := query.SphereAOI; q != nil {
+		if q.Center == nil {
+			return nil, errors.New("SphereAOI with nil Center")
+		}
+		kind |= C.CHD_AOI_SPHERE
+		sph = [3]C.double{C.double(q.Center.X), C.double(q.Center.Z), C.double(q.Radius)}
+	}
+	if q := query.ConeAOI; q != nil {
+		if q.Center == nil || q.Direction == nil {
+			return nil, errors.New("ConeAOI with nil Center/Direction")
+		}
+		kind |= C.CHD_AOI_CONE
+		cone = [6]C.double{C.double(q.Center.X), C.double(q.Center.Z), C.double(q.Direction.X), C.double(q.Direction.Z),
+			C.double(q.Angle), C.double(q.Radius)}
+	}
+	// cgo rule: no Go pointers to Go pointers — the batch struct lives in C memory-free stack and only holds
+	// pointers to pinned-for-the-call Go arrays (runtime.Pinner in Go >= 1.21) or C.malloc'ed staging.
+	b.kind = &kind
+	b.sph_cx, b.sph_cz, b.sph_r = &sph[0], &sph[1], &sph[2]
+	b.box_cx, b.box_cz, b.box_ex, b.box_ez = &box[0], &box[1], &box[2], &box[3]
+	b.cone_cx, b.cone_cz, b.cone_dx, b.cone_dz, b.cone_angle, b.cone_r = &cone[0], &cone[1], &cone[2], &cone[3], &cone[4], &cone[5]
+	if len(sx) > 0 {
+		b.spot_off, b.spot_ndist = &spotOff[0], &spotN
+		b.spot_x, b.spot_z, b.spot_dist = &sx[0], &sz[0], &sd[0]
+	}
+	const capEntries = 1 << 16
+	ids := make([]C.uint32_t, capEntries)
+	dists := make([]C.uint32_t, capEntries)
+	var status C.uint32_t
+	var off [2]C.uint32_t
+	st := C.chd_query_channel_ids(ctl.engine, &b, &status, &off[0], &ids[0], &dists[0], capEntries)
+	if st != C.CHD_OK {
+		return nil, errors.New(C.GoString(C.chd_last_error(ctl.engine)))
+	}
+	if status != C.CHD_Q_OK {
+		return nil, fmt.Errorf("spatial query failed with status %d", uint32(status)) // (nil, err) like the reference
+	}
+	result := make(map[common.ChannelId]uint, int(off[1]))
+	for i := 0; i < int(off[1]); i++ {
+		result[common.ChannelId(ids[i])] = uint(dists[i])
+	}
+	return result, nil
+}
+
+// GetAdjacentChannels (spatial.go:358-381).
+func (ctl *GpuStaticGrid2DSpatialController) GetAdjacentChannels(spatialChannelId common.ChannelId) ([]common.ChannelId, error) {
+	var out [8]C.uint32_t
+	cfg := ctl.cCfg()
+	n := C.chd_get_adjacent_channels(&cfg, C.uint32_t(spatialChannelId), &out[0])
+	res := make([]common.ChannelId, int(n))
+	for i := range res {
+		res[i] = common.ChannelId(out[i])
+	}
+	return res, nil
+}
+
+func (ctl *GpuStaticGrid2DSpatialController) cCfg() C.chd_grid_cfg {
+	return C.chd_grid_cfg{
+		world_offset_x: C.double(ctl.WorldOffsetX), world_offset_z: C.double(ctl.WorldOffsetZ),
+		grid_width: C.double(ctl.GridWidth), grid_height: C.double(ctl.GridHeight),
+		grid_cols: C.uint32_t(ctl.GridCols), grid_rows: C.uint32_t(ctl.GridRows),
+		server_cols: C.uint32_t(ctl.ServerCols), server_rows: C.uint32_t(ctl.ServerRows),
+		server_interest_border_size: C.uint32_t(ctl.ServerInterestBorderSize),
+		channel_id_start:            C.uint32_t(GlobalSettings.SpatialChannelIdStart),
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Batched tick: replaces the per-channel goroutine loop (channel.go:358-387) for SPATIAL channels.
+// The tick driver (one goroutine) gathers, once per tick:
+//   - entity positions (SoA, pinned staging from chd_alloc_pinned) from the ENTITY channels' Merge hook
+//     (tpspb/data.go:227-256) instead of calling Notify per update,
+//   - the UPDATE_SPATIAL_INTEREST messages received since the last tick (message_spatial.go:41) as a
+//     chd_query_batch (coalesced to one per connection),
+//   - each spatial channel's updateMsgBuffer metadata (data.go:46-51) as the ring CSR,
+// then calls chd_tick once and consumes: chd_get_diff -> handleSubToChannel/handleUnsubFromChannel per entry,
+// chd_get_due -> fanOutDataUpdate per entry (payload = whole data for kind 0, merge of ring entries selected by
+// the returned window for kind 1), chd_get_handover -> the orchestration half of Notify (spatial.go:628-858).
+type GpuTickInput struct {
+	EntityX, EntityZ []float64 // index = entity slot
+	ConnSlot         []uint32  // per query: subscriber slot
+	SphX, SphZ, SphR []float64
+	RingOff          []uint32 // [cells+1]
+	RingArrival      []int64
+	RingSender       []uint32
+	RingIndex        []uint64
+	ChannelMsgIndex  []uint64
+}
+
+func (ctl *GpuStaticGrid2DSpatialController) TickBatch(in *GpuTickInput, now ChannelTime) (C.chd_tick_summary, error) {
+	var sum C.chd_tick_summary
+	e := ctl.engine
+	if n := len(in.EntityX); n > 0 {
+		if st := C.chd_set_entities(e, (*C.double)(unsafe.Pointer(&in.EntityX[0])), (*C.double)(unsafe.Pointer(&in.EntityZ[0])), C.uint32_t(n)); st != C.CHD_OK {
+			return sum, errors.New(C.GoString(C.chd_last_error(e)))
+		}
+	}
+	if len(in.RingOff) > 0 {
+		total := in.RingOff[len(in.RingOff)-1]
+		var a *C.int64_t
+		var s *C.uint32_t
+		var i *C.uint64_t
+		if total > 0 {
+			a, s, i = (*C.int64_t)(unsafe.Pointer(&in.RingArrival[0])), (*C.uint32_t)(unsafe.Pointer(&in.RingSender[0])), (*C.uint64_t)(unsafe.Pointer(&in.RingIndex[0]))
+		}
+		if st := C.chd_set_rings(e, (*C.uint32_t)(unsafe.Pointer(&in.RingOff[0])), C.uint32_t(total), a, s, i,
+			(*C.uint64_t)(unsafe.Pointer(&in.ChannelMsgIndex[0]))); st != C.CHD_OK {
+			return sum, errors.New(C.GoString(C.chd_last_error(e)))
+		}
+	}
+	var b C.chd_query_batch
+	var bp *C.chd_query_batch
+	if nq := len(in.ConnSlot); nq > 0 {
+		b.n = C.uint32_t(nq)
+		b.sub = (*C.uint32_t)(unsafe.Pointer(&in.ConnSlot[0]))
+		b.sph_cx, b.sph_cz, b.sph_r = (*C.double)(unsafe.Pointer(&in.SphX[0])), (*C.double)(unsafe.Pointer(&in.SphZ[0])), (*C.double)(unsafe.Pointer(&in.SphR[0]))
+		bp = &b
+	}
+	if st := C.chd_tick(e, bp, C.int64_t(now), C.CHD_TICK_ALL, &sum); st != C.CHD_OK {
+		return sum, errors.New(C.GoString(C.chd_last_error(e)))
+	}
+	return sum, nil
+}
