@@ -67,8 +67,8 @@ struct chd_engine {
     uint32_t *d_sorted4 = nullptr;        // 4 phase-shifted copies of d_sorted_ent (chd_emit.cuh), stride = phase_stride
     uint32_t phase_stride = 0;
     uint32_t *d_hist = nullptr;           // [BUILD_MAX_BINS * nblocks + 1]
-    uint32_t *d_scan_scratch = nullptr;   // u32 scan scratch
-    uint64_t *d_scan_scratch64 = nullptr;
+    // one look-back scan site per call site: stages run concurrently on two streams and must not share scan state
+    ScanSite site_hist{}, site_win{}, site_qoff{}, site_slot{}, site_cellpairs{}, site_diff{}, site_diff2{}, site_voff{}, site_due{}, site_border{};
     uint32_t build_blocks = 0;
     bool assigned = false, built = false, have_prev_key = false, entities_dirty = false;
     uint32_t n_sorted = 0;
@@ -97,8 +97,7 @@ struct chd_engine {
     uint32_t* d_slot_cnt = nullptr;
     uint32_t last_nq = 0;
     // diff
-    uint32_t *d_new_flag = nullptr, *d_gone_flag = nullptr, *d_new_off = nullptr, *d_diff_len = nullptr;
-    uint64_t *d_diff_packed = nullptr, *d_diff_off = nullptr;
+    uint32_t *d_new_flag = nullptr, *d_gone_flag = nullptr, *d_new_off = nullptr, *d_gone_off = nullptr;
     uint32_t *d_new_sub = nullptr, *d_new_ch = nullptr, *d_gone_sub = nullptr, *d_gone_ch = nullptr;
     // emit
     uint32_t *d_vcnt = nullptr, *d_first_pair = nullptr, *d_vis = nullptr;
@@ -177,6 +176,12 @@ static bool dalloc(chd_engine* e, T** p, uint64_t count) {
     e->allocs.push_back(q);
     *p = (T*)q;
     return true;
+}
+
+static bool make_site(chd_engine* e, ScanSite& site, uint64_t n_max) {
+    site.tiles = n_max == 0 ? 1 : (n_max + SCAN_TILE - 1) / SCAN_TILE;
+    if (!dalloc(e, &site.desc, site.tiles) || !dalloc(e, &site.state, 4)) return false;
+    return cudaMemset(site.desc, 0, site.tiles * 8) == cudaSuccess && cudaMemset(site.state, 0, 32) == cudaSuccess;
 }
 
 static inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
@@ -409,7 +414,10 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
          dalloc(e, &e->d_prev_key, N) && dalloc(e, &e->d_tmp_key, N) && dalloc(e, &e->d_tmp_val, N) &&
          dalloc(e, &e->d_sorted_key, N) && dalloc(e, &e->d_sorted4, 4 * (((N + 3) / 4) * 4 + 8)) && dalloc(e, &e->d_cell_start, C + 2) &&
          dalloc(e, &e->d_hist, (uint64_t)BUILD_MAX_BINS * e->build_blocks + 2) &&
-         dalloc(e, &e->d_scan_scratch, scan_scratch_elems(scan_n) + 8) && dalloc(e, &e->d_scan_scratch64, scan_scratch_elems(scan_n) + 8) &&
+         make_site(e, e->site_hist, (uint64_t)BUILD_MAX_BINS * e->build_blocks + 1) && make_site(e, e->site_win, Q + 1) &&
+         make_site(e, e->site_qoff, Q + 1) && make_site(e, e->site_slot, S + 1) && make_site(e, e->site_cellpairs, C + 2) &&
+         make_site(e, e->site_diff, P + 1) && make_site(e, e->site_diff2, P + 1) && make_site(e, e->site_voff, P + 1) && make_site(e, e->site_due, P + 1) &&
+         make_site(e, e->site_border, N + 1) &&
          dalloc(e, &e->d_ho_entity, N) && dalloc(e, &e->d_ho_src, N) && dalloc(e, &e->d_ho_dst, N) &&
          dalloc(e, &e->d_bflag, N + 1) && dalloc(e, &e->d_boff, N + 2);
     e->d_sorted_ent = e->d_sorted4;  // phase copy 0 IS the plain sorted entity array
@@ -427,7 +435,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
          dalloc(e, &e->d_qcount, Q) && dalloc(e, &e->d_qoff, Q + 1) && dalloc(e, &e->d_qout_id, P) && dalloc(e, &e->d_qout_dist, P) &&
          dalloc(e, &e->d_slot_query, S) && dalloc(e, &e->d_slot_cnt, S);
     ok = ok && dalloc(e, &e->d_new_flag, P) && dalloc(e, &e->d_gone_flag, P) && dalloc(e, &e->d_new_off, P + 1) &&
-         dalloc(e, &e->d_diff_packed, P + 1) && dalloc(e, &e->d_diff_off, P + 2) && dalloc(e, &e->d_diff_len, 4) && dalloc(e, &e->d_new_sub, P) && dalloc(e, &e->d_new_ch, P) && dalloc(e, &e->d_gone_sub, P) &&
+         dalloc(e, &e->d_gone_off, P + 1) && dalloc(e, &e->d_new_sub, P) && dalloc(e, &e->d_new_ch, P) && dalloc(e, &e->d_gone_sub, P) &&
          dalloc(e, &e->d_gone_ch, P);
     ok = ok && dalloc(e, &e->d_vcnt, P) && dalloc(e, &e->d_voff, P + 1) && dalloc(e, &e->d_first_pair, e->max_tiles + 1) &&
          dalloc(e, &e->d_vis_off, S + 1) && dalloc(e, &e->d_vis, L.max_visible);
@@ -590,7 +598,7 @@ static chd_status sort_pass(chd_engine* e, const uint32_t* key_in, const uint32_
     const uint32_t mask = (1u << bits) - 1u;
     radix_hist_kernel<BINS><<<nblocks, BUILD_THREADS, 0, e->stream>>>(key_in, n, per_block, shift, mask, e->d_hist, nblocks);
     KCHECK(e);
-    SCAN(e, exclusive_scan<uint32_t, uint32_t>(e->d_hist, e->d_hist, (uint64_t)BINS * nblocks, e->d_scan_scratch, e->stream));
+    SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_hist, e->d_hist, (uint64_t)BINS * nblocks, e->site_hist, e->stream));
     radix_scatter_kernel<BINS><<<nblocks, BUILD_THREADS, 0, e->stream>>>(key_in, val_in, n, per_block, shift, mask, e->d_hist, nblocks,
                                                                         key_out, val_out);
     KCHECK(e);
@@ -758,7 +766,7 @@ static chd_status run_query_kernels(chd_engine* e, const QueryDev& d) {
     if (n == 0) return CHD_OK;
     query_bbox_kernel<<<blocks_for(n, 256), 256, 0, e->stream>>>(e->g, d, e->d_bbox, e->d_win_size);
     KCHECK(e);
-    SCAN(e, exclusive_scan<uint32_t, uint64_t>(e->d_win_size, e->d_win_off, n, e->d_scan_scratch64, e->stream));
+    SCAN(e, exclusive_scan_1p<uint32_t, uint64_t>(e->d_win_size, e->d_win_off, n, e->site_win, e->stream));
     query_sample_kernel<<<blocks_for(n, 128), 128, 0, e->stream>>>(e->g, d, e->d_bbox, e->d_win_off, e->lim.max_window_cells, e->d_window,
                                                                    e->d_side_cell, e->d_side_dist, e->d_side_cnt, e->d_status, e->d_qcount,
                                                                    &e->d_ctr->required_window_cells, &e->d_ctr->overflow);
@@ -785,7 +793,7 @@ chd_status chd_query_channel_ids(chd_engine* e, const chd_query_batch* q, uint32
     }
     st = run_query_kernels(e, d);
     if (st != CHD_OK) return st;
-    SCAN(e, exclusive_scan<uint32_t, uint64_t>(e->d_qcount, e->d_qoff, n, e->d_scan_scratch64, e->stream));
+    SCAN(e, exclusive_scan_1p<uint32_t, uint64_t>(e->d_qcount, e->d_qoff, n, e->site_qoff, e->stream));
     const uint64_t dev_cap = e->lim.max_pairs;
     query_write_kernel<<<blocks_for(n, 128), 128, 0, e->stream>>>(e->g, n, e->d_status, e->d_bbox, e->d_win_off, e->d_window, e->d_side_cell,
                                                                   e->d_side_dist, e->d_side_cnt, d.spot_off, e->d_qoff, dev_cap,
@@ -840,7 +848,7 @@ static chd_status interest_enqueue(chd_engine* e, const QueryDev& d) {
         slot_count_kernel<<<blocks_for(S, 256), 256, 0, s>>>(S, e->d_slot_query, e->d_status, e->d_qcount, prev.off, e->d_slot_cnt, e->d_ctr);
         KCHECK(e);
     }
-    SCAN(e, exclusive_scan<uint32_t, uint32_t>(e->d_slot_cnt, cur.off, S, e->d_scan_scratch, s));
+    SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_slot_cnt, cur.off, S, e->site_slot, s));
     if (S) {
         interest_fill_kernel<<<blocks_for(S, 128), 128, 0, s>>>(e->g, S, e->d_slot_query, e->d_status, e->d_bbox, e->d_win_off, e->d_window,
                                                                 e->d_side_cell, e->d_side_dist, e->d_side_cnt, d.spot_off, prev, cur, P,
@@ -848,16 +856,15 @@ static chd_status interest_enqueue(chd_engine* e, const QueryDev& d) {
         KCHECK(e);
     }
     // pairs grouped by cell for the fan-out pass
-    SCAN(e, exclusive_scan<uint32_t, uint32_t>(e->d_cell_pairs, e->d_cell_pair_off, e->g.cells, e->d_scan_scratch, s));
+    SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_cell_pairs, e->d_cell_pair_off, e->g.cells, e->site_cellpairs, s));
     pairs_by_cell_kernel<<<(unsigned)e->sm_count * 4, 256, 0, s>>>(cur.off + S, P, cur.cell, e->d_cell_pair_off, e->d_cell_cursor, e->d_by_cell);
     KCHECK(e);
-    // diff lists: compact flagged pairs (deterministic order); one packed prefix sum serves both lists
+    // diff lists: compact flagged pairs (deterministic order)
     const unsigned grid = (unsigned)e->sm_count * 4;
-    diff_pack_kernel<<<grid, 256, 0, s>>>(e->d_new_flag, cur.off + S, e->d_gone_flag, prev.off + S, P, e->d_diff_packed, e->d_diff_len);
-    KCHECK(e);
-    SCAN(e, exclusive_scan<uint64_t, uint64_t>(e->d_diff_packed, e->d_diff_off, P, e->d_scan_scratch64, s, e->d_diff_len));
-    diff_compact_kernel<<<grid, 256, 0, s>>>(e->d_diff_off, e->d_new_flag, cur.off + S, e->d_gone_flag, prev.off + S, P, cur, prev, e->g.id_start,
-                                             e->d_new_sub, e->d_new_ch, e->d_gone_sub, e->d_gone_ch);
+    SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_new_flag, e->d_new_off, P, e->site_diff, s, cur.off + S));
+    SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_gone_flag, e->d_gone_off, P, e->site_diff2, s, prev.off + S));
+    diff_compact_kernel<<<grid, 256, 0, s>>>(e->d_new_flag, e->d_new_off, cur.off + S, e->d_gone_flag, e->d_gone_off, prev.off + S, P, cur, prev,
+                                             e->g.id_start, e->d_new_sub, e->d_new_ch, e->d_gone_sub, e->d_gone_ch);
     KCHECK(e);
     return CHD_OK;
 }
@@ -900,7 +907,7 @@ chd_status chd_emit_visible(chd_engine* e) {
     chd_status st = run_stage(e, e->g_emit_prep[e->cur], key, [&]() -> chd_status {
         pair_vcount_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, pb.cell, e->d_cell_start, e->d_vcnt);
         KCHECK(e);
-        SCAN(e, exclusive_scan<uint32_t, uint64_t>(e->d_vcnt, e->d_voff, P, e->d_scan_scratch64, s, pb.off + S));
+        SCAN(e, exclusive_scan_1p<uint32_t, uint64_t>(e->d_vcnt, e->d_voff, P, e->site_voff, s, pb.off + S));
         vis_off_kernel<<<blocks_for((uint64_t)S + 1, 256), 256, 0, s>>>(S, pb.off, P, e->d_voff, e->d_vis_off, e->lim.max_visible, e->d_ctr);
         KCHECK(e);
         emit_partition_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, e->d_voff, e->d_first_pair, e->max_tiles);
@@ -963,7 +970,7 @@ chd_status chd_fanout_tick(chd_engine* e, int64_t t_ns) {
         fanout_kernel<false><<<grid, 128, 0, s>>>(pb.off + S, P, pb, e->d_conn, ring, e->d_time + 1, e->g.id_start, e->d_due_cnt, nullptr, nullptr,
                                                   0, e->d_by_cell, e->d_ctr);
         KCHECK(e);
-        SCAN(e, exclusive_scan<uint32_t, uint32_t>(e->d_due_cnt, e->d_due_off, P, e->d_scan_scratch, s, pb.off + S));
+        SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_due_cnt, e->d_due_off, P, e->site_due, s, pb.off + S));
         fanout_kernel<true><<<grid, 128, 0, s>>>(pb.off + S, P, pb, e->d_conn, ring, e->d_time + 1, e->g.id_start, e->d_due_cnt, e->d_due_off,
                                                  e->d_due, e->lim.max_due, e->d_by_cell, e->d_ctr);
         KCHECK(e);
@@ -1227,7 +1234,7 @@ chd_status chd_export_border(chd_engine* e, uint32_t* d_records, uint32_t cap_re
     const uint32_t n = e->n_own;
     border_flag_kernel<<<blocks_for(n ? n : 1, 256), 256, 0, s>>>(e->g, e->d_key, n, e->d_bflag);
     KCHECK(e);
-    SCAN(e, exclusive_scan<uint32_t, uint32_t>(e->d_bflag, e->d_boff, n, e->d_scan_scratch, s));
+    SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_bflag, e->d_boff, n, e->site_border, s));
     border_write_kernel<<<blocks_for(n ? n : 1, 256), 256, 0, s>>>(e->d_key, e->have_gid ? e->d_gid : nullptr, n, e->d_bflag, e->d_boff,
                                                                     d_records, cap_records);
     KCHECK(e);
@@ -1254,7 +1261,7 @@ chd_status chd_import_halo(chd_engine* e, const uint32_t* d_records, uint32_t n_
     }
     halo_flag_kernel<<<blocks_for(n_records ? n_records : 1, 256), 256, 0, s>>>(e->g, d_records, n_records, skip_first, skip_count, e->d_bflag);
     KCHECK(e);
-    SCAN(e, exclusive_scan<uint32_t, uint32_t>(e->d_bflag, e->d_boff, n_records, e->d_scan_scratch, s));
+    SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_bflag, e->d_boff, n_records, e->site_border, s));
     uint32_t n_keep = 0;
     chd_status st = read_u32(e, e->d_boff + n_records, &n_keep);
     if (st != CHD_OK) return st;

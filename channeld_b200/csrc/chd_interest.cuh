@@ -161,35 +161,23 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// Both diff lists share ONE prefix sum: element p of the scan input packs new_flag[p] (cur pair p) in the low
-// 32 bits and gone_flag[p] (prev pair p) in the high 32 bits.
+// (sub, channel id) of flagged pairs, compacted in pair order: new subscriptions index the cur buffer,
+// unsubscriptions the prev buffer.
 __global__ void __launch_bounds__(256)
-    diff_pack_kernel(const uint32_t* __restrict__ new_flag, const uint32_t* __restrict__ n_cur_ptr, const uint32_t* __restrict__ gone_flag,
-                     const uint32_t* __restrict__ n_prev_ptr, uint64_t cap, uint64_t* __restrict__ packed, uint32_t* __restrict__ len_out) {
-    const uint64_t nc = min((uint64_t)*n_cur_ptr, cap), np = min((uint64_t)*n_prev_ptr, cap);
-    const uint64_t n = max(nc, np);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *len_out = (uint32_t)n;  // live length of the packed scan
-    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < n; p += (uint64_t)gridDim.x * blockDim.x)
-        packed[p] = (uint64_t)(p < nc ? new_flag[p] : 0u) | ((uint64_t)(p < np ? gone_flag[p] : 0u) << 32);
-}
-
-// (sub, channel id) of flagged pairs, compacted in pair order
-__global__ void __launch_bounds__(256)
-    diff_compact_kernel(const uint64_t* __restrict__ packed_off, const uint32_t* __restrict__ new_flag, const uint32_t* __restrict__ n_cur_ptr,
-                        const uint32_t* __restrict__ gone_flag, const uint32_t* __restrict__ n_prev_ptr, uint64_t cap, PairBuf cur,
-                        PairBuf prev, uint32_t id_start, uint32_t* __restrict__ new_sub, uint32_t* __restrict__ new_ch,
-                        uint32_t* __restrict__ gone_sub, uint32_t* __restrict__ gone_ch) {
+    diff_compact_kernel(const uint32_t* __restrict__ new_flag, const uint32_t* __restrict__ new_off, const uint32_t* __restrict__ n_cur_ptr,
+                        const uint32_t* __restrict__ gone_flag, const uint32_t* __restrict__ gone_off, const uint32_t* __restrict__ n_prev_ptr,
+                        uint64_t cap, PairBuf cur, PairBuf prev, uint32_t id_start, uint32_t* __restrict__ new_sub,
+                        uint32_t* __restrict__ new_ch, uint32_t* __restrict__ gone_sub, uint32_t* __restrict__ gone_ch) {
     const uint64_t nc = min((uint64_t)*n_cur_ptr, cap), np = min((uint64_t)*n_prev_ptr, cap);
     const uint64_t n = max(nc, np);
     for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < n; p += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t off = packed_off[p];
         if (p < nc && new_flag[p]) {
-            const uint32_t o = (uint32_t)off;
+            const uint32_t o = new_off[p];
             new_sub[o] = cur.sub[p];
             new_ch[o] = cur.cell[p] + id_start;
         }
         if (p < np && gone_flag[p]) {
-            const uint32_t o = (uint32_t)(off >> 32);
+            const uint32_t o = gone_off[p];
             gone_sub[o] = prev.sub[p];
             gone_ch[o] = prev.cell[p] + id_start;
         }

@@ -118,4 +118,96 @@ inline int exclusive_scan(const TIn* in, TOut* out, uint64_t n, TOut* scratch, c
     return inner + 2;  // kernels launched
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Single-pass scan (decoupled look-back): ONE kernel per prefix sum instead of three.  Each scan call site owns
+// a ScanSite: tile descriptors + a ticket counter + a completion counter + an epoch, all in device memory, so a
+// launch carries no per-call host state and can be replayed from a CUDA graph.  A descriptor is one 64-bit
+// word [epoch:22 | flag:2 | value:40]; descriptors written by an earlier scan carry an older epoch and read as
+// "not ready".  Blocks take tile ids from the ticket counter (a predecessor tile is always owned by a block that
+// is already running: forward progress).  The last block to finish resets the counters and bumps the epoch.
+// Sums must stay below 2^40.
+struct ScanSite {
+    unsigned long long* desc;   // [tiles]
+    unsigned long long* state;  // [0] ticket counter, [1] finished blocks, [2] epoch
+    uint64_t tiles;             // fixed launch width of this site (from its capacity)
+};
+
+constexpr unsigned long long SCAN_FLAG_AGG = 1ull, SCAN_FLAG_PREFIX = 2ull;
+__device__ __forceinline__ unsigned long long scan_pack(unsigned long long epoch, unsigned long long flag, unsigned long long v) {
+    return (epoch << 42) | (flag << 40) | (v & ((1ull << 40) - 1));
+}
+
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(SCAN_THREADS)
+    scan_lookback_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, uint64_t n, const uint32_t* __restrict__ n_ptr, ScanSite site) {
+    __shared__ unsigned long long s_tile, s_prefix;
+    volatile unsigned long long* desc = site.desc;
+    const unsigned long long epoch = (*(volatile unsigned long long*)(site.state + 2) + 1) & ((1ull << 22) - 1);
+    if (threadIdx.x == 0) s_tile = atomicAdd(site.state, 1ull);
+    if (n_ptr) n = min(n, (uint64_t)*n_ptr);
+    __syncthreads();
+    const uint64_t tile = s_tile;
+    const bool live = tile * SCAN_TILE < n || (n == 0 && tile == 0);
+    if (live) {
+        const uint64_t base = tile * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+        TOut v[SCAN_ITEMS];
+        TOut acc = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            const uint64_t i = base + k;
+            v[k] = i < n ? (TOut)in[i] : TOut(0);
+            acc += v[k];
+        }
+        TOut total;
+        TOut pre = block_excl_scan<TOut>(acc, total);
+        if (threadIdx.x == 0) {
+            if (tile == 0) {
+                s_prefix = 0;
+                desc[0] = scan_pack(epoch, SCAN_FLAG_PREFIX, (unsigned long long)total);
+            } else {
+                desc[tile] = scan_pack(epoch, SCAN_FLAG_AGG, (unsigned long long)total);
+                unsigned long long run = 0;
+                for (int64_t j = (int64_t)tile - 1;; ) {
+                    const unsigned long long d = desc[j];
+                    if ((d >> 42) != epoch) continue;  // predecessor has not published yet
+                    run += d & ((1ull << 40) - 1);
+                    if (((d >> 40) & 3ull) == SCAN_FLAG_PREFIX) break;
+                    j--;
+                }
+                s_prefix = run;
+                desc[tile] = scan_pack(epoch, SCAN_FLAG_PREFIX, run + (unsigned long long)total);
+            }
+        }
+        __syncthreads();
+        pre += (TOut)s_prefix;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            const uint64_t i = base + k;
+            if (i < n) out[i] = pre;
+            pre += v[k];
+            if (i + 1 == n) out[n] = pre;
+        }
+        if (n == 0 && threadIdx.x == 0) out[0] = 0;
+    }
+    // completion: the last block resets the site for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(site.state + 1, 1ull) + 1 == gridDim.x) {
+            site.state[0] = 0;
+            site.state[1] = 0;
+            site.state[2] = epoch;
+            __threadfence();
+        }
+    }
+}
+
+template <typename TIn, typename TOut>
+inline int exclusive_scan_1p(const TIn* in, TOut* out, uint64_t n, const ScanSite& site, cudaStream_t st, const uint32_t* n_ptr = nullptr) {
+    const uint64_t tiles = n == 0 ? 1 : (n + SCAN_TILE - 1) / SCAN_TILE;
+    // the launch width is the site's fixed width so that every launch rewrites the same descriptor range
+    scan_lookback_kernel<TIn, TOut><<<(unsigned)(tiles > site.tiles ? tiles : site.tiles), SCAN_THREADS, 0, st>>>(in, out, n, n_ptr, site);
+    return 1;
+}
+
 }  // namespace chd

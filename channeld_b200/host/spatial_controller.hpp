@@ -1,0 +1,157 @@
+// spatial_controller.hpp — header-only C++17 host mirror of channeld's SpatialController plugin surface
+// (pkg/channeld/spatial.go:17-35) on top of the C ABI (include/chd_gpu.h).  Method names, argument meaning and
+// error behaviour follow the Go interface: Go's `(value, error)` becomes `value` + SpatialError thrown.
+// No hot-path arithmetic lives here: every position -> cell, query and fan-out decision is a libchd_b200.so call.
+#pragma once
+#include <cstdint>
+#include <map>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/chd_gpu.h"
+
+namespace channeld {
+
+struct SpatialError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+struct SpatialInfo {  // pkg/common/common.go:20-24
+    double X = 0, Y = 0, Z = 0;
+};
+
+struct SpatialInterestQuery {  // channeld.proto:436-469
+    struct Spots { std::vector<SpatialInfo> spots; std::vector<uint32_t> dists; };
+    struct Box { SpatialInfo center, extent; };
+    struct Sphere { SpatialInfo center; double radius = 0; };
+    struct Cone { SpatialInfo center, direction; double angle = 0, radius = 0; };
+    std::optional<Spots> spotsAOI;
+    std::optional<Box> boxAOI;
+    std::optional<Sphere> sphereAOI;
+    std::optional<Cone> coneAOI;
+};
+
+struct SpatialRegion {  // channeld.proto:419-424
+    SpatialInfo min, max;
+    uint32_t channelId = 0, serverIndex = 0;
+};
+
+class GpuStaticGrid2DSpatialController {
+   public:
+    GpuStaticGrid2DSpatialController() = default;
+    GpuStaticGrid2DSpatialController(const GpuStaticGrid2DSpatialController&) = delete;
+    GpuStaticGrid2DSpatialController& operator=(const GpuStaticGrid2DSpatialController&) = delete;
+    ~GpuStaticGrid2DSpatialController() { chd_destroy(engine_); }
+
+    // LoadConfig (spatial.go:141-159) with the fields already parsed from the -scc JSON.
+    void LoadConfig(const chd_grid_cfg& cfg, uint32_t max_entities, uint32_t max_subscribers, int device = 0) {
+        cfg_ = cfg;
+        chd_limits lim;
+        chd_default_limits(&cfg_, max_entities, max_subscribers, &lim);
+        chd_destroy(engine_);
+        engine_ = nullptr;
+        if (chd_create(&cfg_, &lim, device, &engine_) != CHD_OK) throw SpatialError(chd_last_error(nullptr));
+    }
+
+    // GetChannelId (spatial.go:161-163)
+    uint32_t GetChannelId(const SpatialInfo& info) {
+        uint32_t id = 0;
+        check(chd_cell_of(engine_, &info.X, &info.Z, 1, &id));
+        if (id == 0) throw SpatialError("position is outside the grid");
+        return id;
+    }
+    // batched form (handleQuerySpatialChannel, message_spatial.go:335-370); 0 marks an error
+    std::vector<uint32_t> GetChannelIds(const std::vector<double>& x, const std::vector<double>& z) {
+        std::vector<uint32_t> out(x.size());
+        check(chd_cell_of(engine_, x.data(), z.data(), (uint32_t)x.size(), out.data()));
+        return out;
+    }
+
+    // QueryChannelIds (spatial.go:182-317)
+    std::map<uint32_t, uint32_t> QueryChannelIds(const SpatialInterestQuery& q) {
+        chd_query_batch b{};
+        b.n = 1;
+        uint8_t kind = 0;
+        double sph[3] = {}, box[4] = {}, cone[6] = {};
+        uint32_t spot_off[2] = {0, 0}, spot_nd = 0;
+        std::vector<double> sx, sz;
+        std::vector<uint32_t> sd;
+        if (q.spotsAOI) {
+            kind |= CHD_AOI_SPOTS;
+            for (size_t i = 0; i < q.spotsAOI->spots.size(); i++) {
+                sx.push_back(q.spotsAOI->spots[i].X);
+                sz.push_back(q.spotsAOI->spots[i].Z);
+                sd.push_back(i < q.spotsAOI->dists.size() ? q.spotsAOI->dists[i] : 0u);
+            }
+            spot_off[1] = (uint32_t)sx.size();
+            spot_nd = (uint32_t)std::min(q.spotsAOI->dists.size(), q.spotsAOI->spots.size());
+        }
+        if (q.boxAOI) {
+            kind |= CHD_AOI_BOX;
+            box[0] = q.boxAOI->center.X; box[1] = q.boxAOI->center.Z; box[2] = q.boxAOI->extent.X; box[3] = q.boxAOI->extent.Z;
+        }
+        if (q.sphereAOI) {
+            kind |= CHD_AOI_SPHERE;
+            sph[0] = q.sphereAOI->center.X; sph[1] = q.sphereAOI->center.Z; sph[2] = q.sphereAOI->radius;
+        }
+        if (q.coneAOI) {
+            kind |= CHD_AOI_CONE;
+            cone[0] = q.coneAOI->center.X; cone[1] = q.coneAOI->center.Z; cone[2] = q.coneAOI->direction.X;
+            cone[3] = q.coneAOI->direction.Z; cone[4] = q.coneAOI->angle; cone[5] = q.coneAOI->radius;
+        }
+        b.kind = &kind;
+        b.sph_cx = &sph[0]; b.sph_cz = &sph[1]; b.sph_r = &sph[2];
+        b.box_cx = &box[0]; b.box_cz = &box[1]; b.box_ex = &box[2]; b.box_ez = &box[3];
+        b.cone_cx = &cone[0]; b.cone_cz = &cone[1]; b.cone_dx = &cone[2]; b.cone_dz = &cone[3]; b.cone_angle = &cone[4]; b.cone_r = &cone[5];
+        if (!sx.empty()) {
+            b.spot_off = spot_off; b.spot_ndist = &spot_nd; b.spot_x = sx.data(); b.spot_z = sz.data(); b.spot_dist = sd.data();
+        }
+        std::vector<uint32_t> ids(1 << 16), dists(1 << 16);
+        uint32_t status = 0, off[2] = {0, 0};
+        check(chd_query_channel_ids(engine_, &b, &status, off, ids.data(), dists.data(), ids.size()));
+        if (status != CHD_Q_OK) throw SpatialError("spatial query failed with status " + std::to_string(status));
+        std::map<uint32_t, uint32_t> res;
+        for (uint32_t i = 0; i < off[1]; i++) res[ids[i]] = dists[i];
+        return res;
+    }
+
+    // GetRegions (spatial.go:319-356); Y bounds are the reference's MinY/MaxY constants (spatial.go:80-83)
+    std::vector<SpatialRegion> GetRegions() const {
+        const size_t n = (size_t)cfg_.grid_cols * cfg_.grid_rows;
+        std::vector<double> a(n), b(n), c(n), d(n);
+        std::vector<uint32_t> id(n), srv(n);
+        if (chd_get_regions(&cfg_, a.data(), b.data(), c.data(), d.data(), id.data(), srv.data()) != CHD_OK)
+            throw SpatialError("GetRegions failed");
+        std::vector<SpatialRegion> out(n);
+        for (size_t i = 0; i < n; i++)
+            out[i] = SpatialRegion{{a[i], -3.40282347e+38 / 2, b[i]}, {c[i], 3.40282347e+38 / 2, d[i]}, id[i], srv[i]};
+        return out;
+    }
+
+    // GetAdjacentChannels (spatial.go:358-381)
+    std::vector<uint32_t> GetAdjacentChannels(uint32_t spatialChannelId) const {
+        uint32_t out8[8];
+        const uint32_t n = chd_get_adjacent_channels(&cfg_, spatialChannelId, out8);
+        return std::vector<uint32_t>(out8, out8 + n);
+    }
+
+    // Tick (channel.go:358-387 for every spatial channel): see include/chd_gpu.h for the result getters.
+    chd_tick_summary Tick(const chd_query_batch* batch, int64_t t_ns, uint32_t flags = CHD_TICK_ALL) {
+        chd_tick_summary s{};
+        check(chd_tick(engine_, batch, t_ns, flags, &s));
+        return s;
+    }
+
+    chd_engine* engine() { return engine_; }
+
+   private:
+    void check(chd_status st) const {
+        if (st != CHD_OK) throw SpatialError(chd_last_error(engine_));
+    }
+    chd_grid_cfg cfg_{};
+    chd_engine* engine_ = nullptr;
+};
+
+}  // namespace channeld

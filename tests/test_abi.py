@@ -87,3 +87,19 @@ def test_create_validates_like_load_config():
     for bad in [grid_cfg(0, 0, 0, 10, 1, 1), grid_cfg(0, 0, 10, -1, 1, 1), grid_cfg(0, 0, 10, 10, 0, 1), grid_cfg(0, 0, 10, 10, 1, 1, 0, 1)]:
         assert L.chd_create(C.byref(bad), None, 0, C.byref(h)) == capi.ERR_INVALID
         assert b"should be positive" in L.chd_last_error(None)
+
+
+def test_cpp_host_mirror_compiles(tmp_path):
+    """channeld_b200/host/spatial_controller.hpp (the C++ mirror of the SpatialController interface) compiles
+    against include/chd_gpu.h and links with the library."""
+    import subprocess
+
+    from channeld_b200 import capi
+
+    src = tmp_path / "host_check.cpp"
+    src.write_text('#include "channeld_b200/host/spatial_controller.hpp"\n'
+                   'int main() { channeld::GpuStaticGrid2DSpatialController c; return c.GetAdjacentChannels(65536).size() == 0 ? 0 : 1; }\n')
+    lib_dir = os.path.dirname(capi.lib_path())
+    exe = tmp_path / "host_check"
+    subprocess.check_call(["g++", "-std=c++17", "-I", ROOT, str(src), "-L", lib_dir, "-lchd_b200", "-Wl,-rpath," + lib_dir,
+                           "-Wl,-rpath,/usr/local/cuda/lib64", "-L/usr/local/cuda/lib64", "-o", str(exe)])
