@@ -295,7 +295,7 @@ def run_ours(args):
         ck(L.chd_set_entities(e.h, capi.ptr(d["x"]), capi.ptr(d["z"]), n_own))
         if world > 1:
             rec_local.fill_(-1)
-            e.export_border(rec_local, border_cap)
+            e.export_border(rec_local, border_cap, want_count=False)
             dist.all_gather_into_tensor(rec_all, rec_local)
             e.import_halo(rec_all, border_cap * world, rank * border_cap, border_cap)
         ck(L.chd_set_rings(e.h, capi.ptr(rg["off"]), rg["n"], capi.ptr(rg["arr"]), capi.ptr(rg["snd"]), capi.ptr(rg["idx"]), capi.ptr(rg["cmi"])))
@@ -399,7 +399,7 @@ def run_ours(args):
             ck(L.chd_set_entities(e.h, capi.ptr(d["x"]), capi.ptr(d["z"]), n_own))
             if world > 1:
                 rec_local.fill_(-1)
-                e.export_border(rec_local, border_cap)
+                e.export_border(rec_local, border_cap, want_count=False)
                 dist.all_gather_into_tensor(rec_all, rec_local)
                 e.import_halo(rec_all, border_cap * world, rank * border_cap, border_cap)
             ck(L.chd_set_rings(e.h, capi.ptr(rg["off"]), rg["n"], capi.ptr(rg["arr"]), capi.ptr(rg["snd"]), capi.ptr(rg["idx"]), capi.ptr(rg["cmi"])))

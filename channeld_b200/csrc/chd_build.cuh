@@ -53,12 +53,13 @@ __global__ void __launch_bounds__(256) assign_cells_kernel(GridDev g, const doub
 // per-block digit histogram; hist layout [digit][block]
 template <int BINS>
 __global__ void __launch_bounds__(BUILD_THREADS)
-    radix_hist_kernel(const uint32_t* __restrict__ key, uint32_t n, uint32_t per_block, uint32_t shift, uint32_t mask,
-                      uint32_t* __restrict__ hist, uint32_t nblocks) {
+    radix_hist_kernel(const uint32_t* __restrict__ key, uint32_t n, const uint32_t* __restrict__ n_ptr, uint32_t per_block,
+                      uint32_t shift, uint32_t mask, uint32_t* __restrict__ hist, uint32_t nblocks) {
     __shared__ uint32_t s_hist[BINS];
+    if (n_ptr) n = min(n, *n_ptr);  // live length on the device (multi-GPU: own + halo entities)
     for (int d = threadIdx.x; d < BINS; d += BUILD_THREADS) s_hist[d] = 0;
     __syncthreads();
-    const uint32_t lo = blockIdx.x * per_block;
+    const uint32_t lo = min(n, blockIdx.x * per_block);
     const uint32_t hi = min(n, lo + per_block);
     for (uint32_t i = lo + threadIdx.x; i < hi; i += BUILD_THREADS) atomicAdd(&s_hist[(key[i] >> shift) & mask], 1u);
     __syncthreads();
@@ -69,15 +70,16 @@ __global__ void __launch_bounds__(BUILD_THREADS)
 template <int BINS>
 __global__ void __launch_bounds__(BUILD_THREADS)
     radix_scatter_kernel(const uint32_t* __restrict__ key_in, const uint32_t* __restrict__ val_in, uint32_t n,
-                         uint32_t per_block, uint32_t shift, uint32_t mask, const uint32_t* __restrict__ hist_scanned,
+                         const uint32_t* __restrict__ n_ptr, uint32_t per_block, uint32_t shift, uint32_t mask, const uint32_t* __restrict__ hist_scanned,
                          uint32_t nblocks, uint32_t* __restrict__ key_out, uint32_t* __restrict__ val_out) {
     __shared__ uint32_t s_base[BINS];
     __shared__ uint32_t s_tot[BINS];
     __shared__ uint32_t s_wcnt[BUILD_WARPS][BINS];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
+    if (n_ptr) n = min(n, *n_ptr);
     for (int d = threadIdx.x; d < BINS; d += BUILD_THREADS) s_base[d] = hist_scanned[(uint32_t)d * nblocks + blockIdx.x];
-    const uint32_t lo = blockIdx.x * per_block;
+    const uint32_t lo = min(n, blockIdx.x * per_block);
     const uint32_t hi = min(n, lo + per_block);
     for (uint32_t tile = lo; tile < hi; tile += BUILD_TILE) {
         for (int d = threadIdx.x; d < BINS * BUILD_WARPS; d += BUILD_THREADS) (&s_wcnt[0][0])[d] = 0;
@@ -129,9 +131,10 @@ __global__ void __launch_bounds__(BUILD_THREADS)
 
 // cell_start[c] = first sorted position whose key >= c, for c in [0, C+1]; cell_start[C+1] = n.
 __global__ void __launch_bounds__(256)
-    cell_bounds_kernel(const uint32_t* __restrict__ sorted_key, uint32_t n, uint32_t cells, uint32_t* __restrict__ cell_start,
-                       uint32_t* __restrict__ n_in_world) {
+    cell_bounds_kernel(const uint32_t* __restrict__ sorted_key, uint32_t n, const uint32_t* __restrict__ n_ptr, uint32_t cells,
+                       uint32_t* __restrict__ cell_start, uint32_t* __restrict__ n_in_world) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_ptr) n = min(n, *n_ptr);
     if (i > n) return;
     // position i: keys (prev, cur]; prev = -1 at i == 0; cur = C+1 at i == n
     const int64_t prev = i == 0 ? -1 : (int64_t)sorted_key[i - 1];

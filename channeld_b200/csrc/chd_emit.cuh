@@ -26,8 +26,9 @@ constexpr int EMIT_SMEM_PAIRS = 64;              // pairs per warp tile staged i
 // the whole run moves as LDG.128 -> STG.128 with no realignment shuffles.  Cost: 12 extra bytes per entity
 // written once per build (L2-resident), against 8 bytes per VISIBLE entry saved from 4-byte accesses.
 __global__ void __launch_bounds__(256)
-    replicate_phases_kernel(const uint32_t* src, uint32_t n, uint32_t stride, uint32_t* dst4) {
+    replicate_phases_kernel(const uint32_t* src, uint32_t n, const uint32_t* __restrict__ n_ptr, uint32_t stride, uint32_t* dst4) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_ptr) n = min(n, *n_ptr);
     if (i >= n) return;
     const uint32_t v = src[i];
 #pragma unroll

@@ -58,6 +58,8 @@ struct chd_engine {
 
     // ---- entities
     uint32_t n_own = 0, n_halo = 0;  // entities with positions / appended halo records
+    bool halo_on_device = false;     // multi-GPU: the build length (own + halo) lives in d_n_build
+    uint32_t* d_n_build = nullptr;
     bool have_gid = false;
     double *d_x = nullptr, *d_z = nullptr;
     uint32_t *d_gid = nullptr;            // [max_entities] global ids (multi-GPU) of own + halo
@@ -68,7 +70,7 @@ struct chd_engine {
     uint32_t phase_stride = 0;
     uint32_t *d_hist = nullptr;           // [BUILD_MAX_BINS * nblocks + 1]
     // one look-back scan site per call site: stages run concurrently on two streams and must not share scan state
-    ScanSite site_hist{}, site_win{}, site_qoff{}, site_slot{}, site_cellpairs{}, site_diff{}, site_diff2{}, site_voff{}, site_due{}, site_border{};
+    ScanSite site_hist{}, site_win{}, site_qoff{}, site_slot{}, site_pchist{}, site_diff{}, site_diff2{}, site_voff{}, site_due{}, site_border{};
     uint32_t build_blocks = 0;
     bool assigned = false, built = false, have_prev_key = false, entities_dirty = false;
     uint32_t n_sorted = 0;
@@ -109,7 +111,8 @@ struct chd_engine {
     uint64_t *d_ring_index = nullptr, *d_ch_msg_index = nullptr;
     bool have_ch_msg_index = false;
     uint32_t *d_due_cnt = nullptr, *d_due_off = nullptr;
-    uint32_t *d_cell_pairs = nullptr, *d_cell_pair_off = nullptr, *d_cell_cursor = nullptr, *d_by_cell = nullptr;
+    uint32_t *d_by_cell = nullptr, *d_pc_hist = nullptr, *d_pc_tmp_key = nullptr, *d_pc_tmp_val = nullptr;  // pairs grouped by cell
+    uint32_t pc_blocks = 0;
     chd_due* d_due = nullptr;
     // counters
     Counters* d_ctr = nullptr;
@@ -402,6 +405,8 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
     const uint64_t N = L.max_entities, S = L.max_subscribers, Q = L.max_queries, P = L.max_pairs, C = g.cells;
     e->build_blocks = (uint32_t)e->sm_count * 4;
     e->phase_stride = (uint32_t)(((N + 3) / 4) * 4 + 8);
+    e->pc_blocks = (uint32_t)std::min<uint64_t>(4096, (P + BUILD_TILE - 1) / BUILD_TILE);
+    if (e->pc_blocks == 0) e->pc_blocks = 1;
     e->ho_cap = L.max_entities;
     e->max_tiles = (L.max_visible + EMIT_TILE - 1) / EMIT_TILE + 1;
     uint64_t scan_n = (uint64_t)BUILD_MAX_BINS * e->build_blocks + 1;
@@ -415,7 +420,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
          dalloc(e, &e->d_sorted_key, N) && dalloc(e, &e->d_sorted4, 4 * (((N + 3) / 4) * 4 + 8)) && dalloc(e, &e->d_cell_start, C + 2) &&
          dalloc(e, &e->d_hist, (uint64_t)BUILD_MAX_BINS * e->build_blocks + 2) &&
          make_site(e, e->site_hist, (uint64_t)BUILD_MAX_BINS * e->build_blocks + 1) && make_site(e, e->site_win, Q + 1) &&
-         make_site(e, e->site_qoff, Q + 1) && make_site(e, e->site_slot, S + 1) && make_site(e, e->site_cellpairs, C + 2) &&
+         make_site(e, e->site_qoff, Q + 1) && make_site(e, e->site_slot, S + 1) &&
          make_site(e, e->site_diff, P + 1) && make_site(e, e->site_diff2, P + 1) && make_site(e, e->site_voff, P + 1) && make_site(e, e->site_due, P + 1) &&
          make_site(e, e->site_border, N + 1) &&
          dalloc(e, &e->d_ho_entity, N) && dalloc(e, &e->d_ho_src, N) && dalloc(e, &e->d_ho_dst, N) &&
@@ -441,10 +446,11 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
          dalloc(e, &e->d_vis_off, S + 1) && dalloc(e, &e->d_vis, L.max_visible);
     ok = ok && dalloc(e, &e->d_ring_off, C + 1) && dalloc(e, &e->d_ring_arrival, (uint64_t)L.max_ring_entries) &&
          dalloc(e, &e->d_ring_sender, (uint64_t)L.max_ring_entries) && dalloc(e, &e->d_ring_index, (uint64_t)L.max_ring_entries) &&
-         dalloc(e, &e->d_ch_msg_index, C) && dalloc(e, &e->d_due_cnt, P) && dalloc(e, &e->d_cell_pairs, C + 1) &&
-         dalloc(e, &e->d_cell_pair_off, C + 2) && dalloc(e, &e->d_cell_cursor, C + 1) && dalloc(e, &e->d_by_cell, P) && dalloc(e, &e->d_due_off, P + 1) &&
+         dalloc(e, &e->d_ch_msg_index, C) && dalloc(e, &e->d_due_cnt, P) && dalloc(e, &e->d_by_cell, P) &&
+         dalloc(e, &e->d_pc_hist, (uint64_t)BUILD_MAX_BINS * e->pc_blocks + 2) && dalloc(e, &e->d_pc_tmp_key, P) && dalloc(e, &e->d_pc_tmp_val, P) &&
+         make_site(e, e->site_pchist, (uint64_t)BUILD_MAX_BINS * e->pc_blocks + 1) && dalloc(e, &e->d_due_off, P + 1) &&
          dalloc(e, &e->d_due, (uint64_t)L.max_due) && dalloc(e, &e->d_ctr, 1) && dalloc(e, &e->d_time, 2) &&
-         dalloc(e, &e->d_ring_total, 1);
+         dalloc(e, &e->d_ring_total, 1) && dalloc(e, &e->d_n_build, 1);
     if (!ok) {
         g_create_error = e->err;
         chd_destroy(e);
@@ -528,6 +534,7 @@ chd_status chd_set_entities(chd_engine* e, const double* x, const double* z, uin
     CU(e, cudaMemcpyAsync(e->d_z, z, sizeof(double) * n, cudaMemcpyDefault, e->stream));
     e->n_own = n;
     e->n_halo = 0;
+    e->halo_on_device = false;
     e->assigned = false;
     e->entities_dirty = true;
     return CHD_OK;
@@ -548,6 +555,7 @@ chd_status chd_set_entity_count(chd_engine* e, uint32_t n) {
     if (n != e->n_own) e->have_prev_key = false;
     e->n_own = n;
     e->n_halo = 0;
+    e->halo_on_device = false;
     e->assigned = false;
     e->entities_dirty = true;
     return CHD_OK;
@@ -593,23 +601,25 @@ chd_status chd_assign_cells(chd_engine* e) {
 
 extern "C++" {
 template <int BINS>
-static chd_status sort_pass(chd_engine* e, const uint32_t* key_in, const uint32_t* val_in, uint32_t n, uint32_t per_block,
-                            uint32_t nblocks, uint32_t shift, uint32_t bits, uint32_t* key_out, uint32_t* val_out) {
+static chd_status sort_pass(chd_engine* e, uint32_t* hist, const ScanSite& site, const uint32_t* key_in, const uint32_t* val_in, uint32_t n,
+                            const uint32_t* n_ptr, uint32_t per_block, uint32_t nblocks, uint32_t shift, uint32_t bits, uint32_t* key_out,
+                            uint32_t* val_out) {
     const uint32_t mask = (1u << bits) - 1u;
-    radix_hist_kernel<BINS><<<nblocks, BUILD_THREADS, 0, e->stream>>>(key_in, n, per_block, shift, mask, e->d_hist, nblocks);
+    radix_hist_kernel<BINS><<<nblocks, BUILD_THREADS, 0, e->stream>>>(key_in, n, n_ptr, per_block, shift, mask, hist, nblocks);
     KCHECK(e);
-    SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_hist, e->d_hist, (uint64_t)BINS * nblocks, e->site_hist, e->stream));
-    radix_scatter_kernel<BINS><<<nblocks, BUILD_THREADS, 0, e->stream>>>(key_in, val_in, n, per_block, shift, mask, e->d_hist, nblocks,
+    SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(hist, hist, (uint64_t)BINS * nblocks, site, e->stream));
+    radix_scatter_kernel<BINS><<<nblocks, BUILD_THREADS, 0, e->stream>>>(key_in, val_in, n, n_ptr, per_block, shift, mask, hist, nblocks,
                                                                         key_out, val_out);
     KCHECK(e);
     return CHD_OK;
 }
 }  // extern "C++"
 
-static chd_status sort_pass_any(chd_engine* e, const uint32_t* key_in, const uint32_t* val_in, uint32_t n, uint32_t per_block,
-                                uint32_t nblocks, uint32_t shift, uint32_t bits, uint32_t* key_out, uint32_t* val_out) {
-    if (bits <= 8) return sort_pass<256>(e, key_in, val_in, n, per_block, nblocks, shift, bits, key_out, val_out);
-    return sort_pass<1024>(e, key_in, val_in, n, per_block, nblocks, shift, bits, key_out, val_out);
+static chd_status sort_pass_any(chd_engine* e, uint32_t* hist, const ScanSite& site, const uint32_t* key_in, const uint32_t* val_in,
+                                uint32_t n, const uint32_t* n_ptr, uint32_t per_block, uint32_t nblocks, uint32_t shift, uint32_t bits,
+                                uint32_t* key_out, uint32_t* val_out) {
+    if (bits <= 8) return sort_pass<256>(e, hist, site, key_in, val_in, n, n_ptr, per_block, nblocks, shift, bits, key_out, val_out);
+    return sort_pass<1024>(e, hist, site, key_in, val_in, n, n_ptr, per_block, nblocks, shift, bits, key_out, val_out);
 }
 
 static chd_status build_enqueue(chd_engine* e, bool with_assign) {
@@ -618,7 +628,10 @@ static chd_status build_enqueue(chd_engine* e, bool with_assign) {
         st = chd_assign_cells(e);
         if (st != CHD_OK) return st;
     }
-    const uint32_t n = e->n_own + e->n_halo;
+    // multi-GPU: the halo count stays on the device (d_n_build = own + kept halo records); launches are sized for
+    // the entity capacity and blocks beyond the live length idle.
+    const uint32_t* n_ptr = e->halo_on_device ? e->d_n_build : nullptr;
+    const uint32_t n = e->halo_on_device ? e->lim.max_entities : e->n_own + e->n_halo;
     const uint32_t C = e->g.cells;
     uint32_t bits = 1;
     while ((1u << bits) < C + 1) bits++;  // keys are in [0, C]
@@ -632,19 +645,19 @@ static chd_status build_enqueue(chd_engine* e, bool with_assign) {
     if (nblocks == 0) nblocks = 1;
     const uint32_t* vals = e->have_gid ? e->d_gid : nullptr;
     if (passes == 1) {
-        st = sort_pass_any(e, e->d_key, vals, n, per_block, nblocks, 0, bits0, e->d_sorted_key, e->d_sorted_ent);
+        st = sort_pass_any(e, e->d_hist, e->site_hist, e->d_key, vals, n, n_ptr, per_block, nblocks, 0, bits0, e->d_sorted_key, e->d_sorted_ent);
         if (st != CHD_OK) return st;
     } else {
-        st = sort_pass_any(e, e->d_key, vals, n, per_block, nblocks, 0, bits0, e->d_tmp_key, e->d_tmp_val);
+        st = sort_pass_any(e, e->d_hist, e->site_hist, e->d_key, vals, n, n_ptr, per_block, nblocks, 0, bits0, e->d_tmp_key, e->d_tmp_val);
         if (st != CHD_OK) return st;
-        st = sort_pass_any(e, e->d_tmp_key, e->d_tmp_val, n, per_block, nblocks, bits0, bits1, e->d_sorted_key, e->d_sorted_ent);
+        st = sort_pass_any(e, e->d_hist, e->site_hist, e->d_tmp_key, e->d_tmp_val, n, n_ptr, per_block, nblocks, bits0, bits1, e->d_sorted_key, e->d_sorted_ent);
         if (st != CHD_OK) return st;
     }
     if (n) {
-        replicate_phases_kernel<<<blocks_for(n, 256), 256, 0, e->stream>>>(e->d_sorted_ent, n, e->phase_stride, e->d_sorted4);
+        replicate_phases_kernel<<<blocks_for(n, 256), 256, 0, e->stream>>>(e->d_sorted_ent, n, n_ptr, e->phase_stride, e->d_sorted4);
         KCHECK(e);
     }
-    cell_bounds_kernel<<<blocks_for((uint64_t)n + 1, 256), 256, 0, e->stream>>>(e->d_sorted_key, n, C, e->d_cell_start,
+    cell_bounds_kernel<<<blocks_for((uint64_t)n + 1, 256), 256, 0, e->stream>>>(e->d_sorted_key, n, n_ptr, C, e->d_cell_start,
                                                                                   &e->d_ctr->n_entities_in_world);
     KCHECK(e);
     return CHD_OK;
@@ -655,7 +668,7 @@ chd_status chd_build(chd_engine* e) {
     CU(e, cudaSetDevice(e->device));
     StageTimer timer(e, CHD_STAGE_BUILD);
     chd_status st;
-    if (!e->assigned && e->n_halo == 0) {
+    if (!e->assigned && !e->halo_on_device) {
         // single-GPU flow: assign + sort as one replayable graph.  The key buffers swap every assignment
         // (handover detection compares against the previous keys), so there are two graph variants.
         uint32_t* target = e->have_prev_key ? e->d_prev_key : e->d_key;  // buffer the new keys will be written to
@@ -673,6 +686,12 @@ chd_status chd_build(chd_engine* e) {
             e->n_halo = 0;
             e->assigned = true;
         }
+    } else if (e->assigned && e->halo_on_device) {
+        // multi-GPU flow: cells were assigned by chd_export_border and the halo appended on the device; the sort over
+        // own + halo entities is sized by capacity (device-side length) and therefore replayable as well.
+        const int slot = e->d_key == e->d_key_a ? 0 : 1;
+        uint64_t key = mix_key(mix_key(mix_key(0x736f7274ull, e->lim.max_entities), e->have_gid), (uint64_t)(uintptr_t)e->d_key);
+        st = run_stage(e, e->g_build[slot], key, [&]() { return build_enqueue(e, false); });
     } else {
         st = build_enqueue(e, !e->assigned);
     }
@@ -838,8 +857,7 @@ static chd_status interest_enqueue(chd_engine* e, const QueryDev& d) {
     const uint64_t P = e->lim.max_pairs;
     CU(e, cudaMemsetAsync(e->d_slot_query, 0xFF, sizeof(int32_t) * (uint64_t)(S ? S : 1), s));
     CU(e, cudaMemsetAsync(&e->d_ctr->n_query_errors, 0, 4 * 4, s));  // n_query_errors, n_sub_new, n_unsub, n_kept
-    CU(e, cudaMemsetAsync(e->d_cell_pairs, 0, sizeof(uint32_t) * ((uint64_t)e->g.cells + 1), s));
-    CU(e, cudaMemsetAsync(e->d_cell_cursor, 0, sizeof(uint32_t) * ((uint64_t)e->g.cells + 1), s));
+
     if (n) {
         slot_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(d.sub, n, S, e->d_slot_query);
         KCHECK(e);
@@ -852,13 +870,35 @@ static chd_status interest_enqueue(chd_engine* e, const QueryDev& d) {
     if (S) {
         interest_fill_kernel<<<blocks_for(S, 128), 128, 0, s>>>(e->g, S, e->d_slot_query, e->d_status, e->d_bbox, e->d_win_off, e->d_window,
                                                                 e->d_side_cell, e->d_side_dist, e->d_side_cnt, d.spot_off, prev, cur, P,
-                                                                e->d_time, e->d_new_flag, e->d_gone_flag, e->d_cell_pairs, e->d_ctr);
+                                                                e->d_time, e->d_new_flag, e->d_gone_flag, e->d_ctr);
         KCHECK(e);
     }
-    // pairs grouped by cell for the fan-out pass
-    SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_cell_pairs, e->d_cell_pair_off, e->g.cells, e->site_cellpairs, s));
-    pairs_by_cell_kernel<<<(unsigned)e->sm_count * 4, 256, 0, s>>>(cur.off + S, P, cur.cell, e->d_cell_pair_off, e->d_cell_cursor, e->d_by_cell);
-    KCHECK(e);
+    // pairs grouped by cell for the fan-out pass (= every channel's subscriber list): a stable radix sort of pair
+    // indices by cell with the same kernels as the entity build (no global atomics), device-side length
+    {
+        const uint32_t C = e->g.cells;
+        uint32_t bits = 1;
+        while ((1u << bits) < C) bits++;
+        const uint32_t passes = bits <= 10 ? 1 : 2;
+        const uint32_t bits0 = passes == 1 ? bits : (bits + 1) / 2, bits1 = bits - bits0;
+        const uint32_t nb = e->pc_blocks;
+        uint32_t per_block = (uint32_t)((P + nb - 1) / nb);
+        per_block = ((per_block + BUILD_TILE - 1) / BUILD_TILE) * BUILD_TILE;
+        cudaStream_t keep = e->stream;  // sort_pass launches on e->stream, which already is `s`
+        (void)keep;
+        if (passes == 1) {
+            st = sort_pass_any(e, e->d_pc_hist, e->site_pchist, cur.cell, nullptr, (uint32_t)P, cur.off + S, per_block, nb, 0, bits0, nullptr,
+                               e->d_by_cell);
+            if (st != CHD_OK) return st;
+        } else {
+            st = sort_pass_any(e, e->d_pc_hist, e->site_pchist, cur.cell, nullptr, (uint32_t)P, cur.off + S, per_block, nb, 0, bits0,
+                               e->d_pc_tmp_key, e->d_pc_tmp_val);
+            if (st != CHD_OK) return st;
+            st = sort_pass_any(e, e->d_pc_hist, e->site_pchist, e->d_pc_tmp_key, e->d_pc_tmp_val, (uint32_t)P, cur.off + S, per_block, nb, bits0,
+                               bits1, nullptr, e->d_by_cell);
+            if (st != CHD_OK) return st;
+        }
+    }
     // diff lists: compact flagged pairs (deterministic order)
     const unsigned grid = (unsigned)e->sm_count * 4;
     SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_new_flag, e->d_new_off, P, e->site_diff, s, cur.off + S));
@@ -1222,11 +1262,12 @@ chd_status chd_set_slab(chd_engine* e, uint32_t col_lo, uint32_t col_hi, uint32_
     e->g.col_lo = col_lo;
     e->g.col_hi = col_hi;
     e->g.halo = halo;
+    e->halo_on_device = false;  // set again by chd_import_halo
     return CHD_OK;
 }
 
 chd_status chd_export_border(chd_engine* e, uint32_t* d_records, uint32_t cap_records, uint32_t* out_count) {
-    if (!e || !d_records || !out_count) return CHD_ERR_INVALID;
+    if (!e || !d_records) return CHD_ERR_INVALID;
     CU(e, cudaSetDevice(e->device));
     chd_status st = chd_assign_cells(e);
     if (st != CHD_OK) return st;
@@ -1236,13 +1277,15 @@ chd_status chd_export_border(chd_engine* e, uint32_t* d_records, uint32_t cap_re
     KCHECK(e);
     SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_bflag, e->d_boff, n, e->site_border, s));
     border_write_kernel<<<blocks_for(n ? n : 1, 256), 256, 0, s>>>(e->d_key, e->have_gid ? e->d_gid : nullptr, n, e->d_bflag, e->d_boff,
-                                                                    d_records, cap_records);
+                                                                    d_records, cap_records, e->d_ctr);
     KCHECK(e);
-    st = read_u32(e, e->d_boff + n, out_count);
-    if (st != CHD_OK) return st;
-    if (*out_count > cap_records) {
-        e->fail("border export needs %u records > capacity %u", *out_count, cap_records);
-        return CHD_ERR_CAPACITY;
+    if (out_count) {
+        st = read_u32(e, e->d_boff + n, out_count);
+        if (st != CHD_OK) return st;
+        if (*out_count > cap_records) {
+            e->fail("border export needs %u records > capacity %u", *out_count, cap_records);
+            return CHD_ERR_CAPACITY;
+        }
     }
     return CHD_OK;
 }
@@ -1254,6 +1297,10 @@ chd_status chd_import_halo(chd_engine* e, const uint32_t* d_records, uint32_t n_
         e->fail("chd_import_halo before chd_export_border / chd_assign_cells");
         return CHD_ERR_STATE;
     }
+    if (!e->have_gid) {
+        e->fail("chd_import_halo requires global entity ids (chd_set_entity_ids)");
+        return CHD_ERR_STATE;
+    }
     cudaStream_t s = e->stream;
     if (n_records > e->lim.max_entities) {
         e->fail("halo import of %u records > max_entities scratch %u", n_records, e->lim.max_entities);
@@ -1262,21 +1309,12 @@ chd_status chd_import_halo(chd_engine* e, const uint32_t* d_records, uint32_t n_
     halo_flag_kernel<<<blocks_for(n_records ? n_records : 1, 256), 256, 0, s>>>(e->g, d_records, n_records, skip_first, skip_count, e->d_bflag);
     KCHECK(e);
     SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_bflag, e->d_boff, n_records, e->site_border, s));
-    uint32_t n_keep = 0;
-    chd_status st = read_u32(e, e->d_boff + n_records, &n_keep);
-    if (st != CHD_OK) return st;
-    if ((uint64_t)e->n_own + n_keep > e->lim.max_entities) {
-        e->fail("own %u + halo %u entities > max_entities %u", e->n_own, n_keep, e->lim.max_entities);
-        return CHD_ERR_CAPACITY;
-    }
-    if (!e->have_gid) {
-        e->fail("chd_import_halo requires global entity ids (chd_set_entity_ids)");
-        return CHD_ERR_STATE;
-    }
-    halo_append_kernel<<<blocks_for(n_records ? n_records : 1, 256), 256, 0, s>>>(d_records, n_records, e->d_bflag, e->d_boff, e->n_own, e->d_key,
-                                                                                  e->d_gid);
+    // no host round trip: the kept count and the build length stay on the device (overflow -> CHD_OVF_BORDER)
+    halo_append_kernel<<<blocks_for(n_records ? n_records : 1, 256), 256, 0, s>>>(d_records, n_records, e->d_bflag, e->d_boff, e->n_own,
+                                                                                  e->lim.max_entities, e->d_key, e->d_gid, e->d_n_build, e->d_ctr);
     KCHECK(e);
-    e->n_halo = n_keep;
+    e->halo_on_device = true;
+    e->n_halo = 0;
     e->entities_dirty = true;
     return CHD_OK;
 }

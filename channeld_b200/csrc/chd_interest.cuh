@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(128)
                          const uint32_t* __restrict__ side_cell, const uint32_t* __restrict__ side_dist,
                          const uint32_t* __restrict__ side_cnt, const uint32_t* __restrict__ spot_off, PairBuf prev, PairBuf cur,
                          uint64_t pair_cap, const int64_t* __restrict__ now_ptr, uint32_t* __restrict__ new_flag, uint32_t* __restrict__ gone_flag,
-                         uint32_t* __restrict__ cell_pairs, Counters* __restrict__ ctr) {
+                         Counters* __restrict__ ctr) {
     __shared__ uint32_t s_new, s_gone, s_kept;
     if (threadIdx.x == 0) s_new = s_gone = s_kept = 0;
     __syncthreads();
@@ -96,7 +96,6 @@ __global__ void __launch_bounds__(128)
                 cur.cell[o] = c;
                 cur.dist[o] = d;
                 cur.interval[o] = interval;
-                atomicAdd(&cell_pairs[c], 1u);  // per-cell subscriber count (the channel's subscribedConnections)
                 if (pp < pe && prev.cell[pp] == c) {
                     // already subscribed: options merged, fan-out state untouched (subscription.go:43-58)
                     cur.flags[o] = prev.flags[pp] & ~PF_NEW;
@@ -127,7 +126,6 @@ __global__ void __launch_bounds__(128)
             for (; pp < pe; pp++, o++) {
                 cur.sub[o] = s;
                 cur.cell[o] = prev.cell[pp];
-                atomicAdd(&cell_pairs[prev.cell[pp]], 1u);
                 cur.dist[o] = prev.dist[pp];
                 cur.interval[o] = prev.interval[pp];
                 cur.flags[o] = prev.flags[pp] & ~PF_NEW;
@@ -146,18 +144,6 @@ __global__ void __launch_bounds__(128)
         if (s_new) atomicAdd(&ctr->n_sub_new, s_new);
         if (s_gone) atomicAdd(&ctr->n_unsub, s_gone);
         if (s_kept) atomicAdd(&ctr->n_kept, s_kept);
-    }
-}
-
-// by_cell[cell_pair_off[c] + k] = k-th subscription pair of cell c (the channel's subscriber list, any order):
-// the fan-out pass walks pairs in this order so that a warp scans ONE update ring in lockstep (broadcast loads).
-__global__ void __launch_bounds__(256)
-    pairs_by_cell_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, const uint32_t* __restrict__ pair_cell,
-                         const uint32_t* __restrict__ cell_pair_off, uint32_t* __restrict__ cursor, uint32_t* __restrict__ by_cell) {
-    const uint64_t n = min((uint64_t)*n_pairs_ptr, pair_cap);
-    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < n; p += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t c = pair_cell[p];
-        by_cell[cell_pair_off[c] + atomicAdd(&cursor[c], 1u)] = (uint32_t)p;
     }
 }
 

@@ -41,8 +41,9 @@ __global__ void border_flag_kernel(GridDev g, const uint32_t* __restrict__ key, 
 
 __global__ void border_write_kernel(const uint32_t* __restrict__ key, const uint32_t* __restrict__ gid, uint32_t n,
                                     const uint32_t* __restrict__ flag, const uint32_t* __restrict__ off, uint32_t* __restrict__ out,
-                                    uint32_t cap) {
+                                    uint32_t cap, Counters* __restrict__ ctr) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && off[n] > cap) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_BORDER);
     if (i >= n || !flag[i]) return;
     const uint32_t o = off[i];
     if (o < cap) {
@@ -65,11 +66,20 @@ __global__ void halo_flag_kernel(GridDev g, const uint32_t* __restrict__ rec, ui
     flag[i] = f;
 }
 
+// appends the kept records after the `base` own entities and publishes the build length (own + halo) on the device:
+// the host never needs the halo count, so the whole multi-GPU tick is free of host round trips.
 __global__ void halo_append_kernel(const uint32_t* __restrict__ rec, uint32_t n, const uint32_t* __restrict__ flag,
-                                   const uint32_t* __restrict__ off, uint32_t base, uint32_t* __restrict__ key, uint32_t* __restrict__ gid) {
+                                   const uint32_t* __restrict__ off, uint32_t base, uint32_t cap_total, uint32_t* __restrict__ key,
+                                   uint32_t* __restrict__ gid, uint32_t* __restrict__ n_build, Counters* __restrict__ ctr) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        const uint64_t total = (uint64_t)base + off[n];
+        if (total > cap_total) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_BORDER);
+        *n_build = (uint32_t)min(total, (uint64_t)cap_total);
+    }
     if (i >= n || !flag[i]) return;
     const uint32_t o = base + off[i];
+    if (o >= cap_total) return;
     gid[o] = rec[2 * i];
     key[o] = rec[2 * i + 1];
 }

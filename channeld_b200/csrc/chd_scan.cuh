@@ -160,22 +160,41 @@ __global__ void __launch_bounds__(SCAN_THREADS)
         }
         TOut total;
         TOut pre = block_excl_scan<TOut>(acc, total);
-        if (threadIdx.x == 0) {
+        if (threadIdx.x < 32) {
+            // warp-parallel look-back: 32 predecessor descriptors per hop
+            const int lane = threadIdx.x;
             if (tile == 0) {
-                s_prefix = 0;
-                desc[0] = scan_pack(epoch, SCAN_FLAG_PREFIX, (unsigned long long)total);
-            } else {
-                desc[tile] = scan_pack(epoch, SCAN_FLAG_AGG, (unsigned long long)total);
-                unsigned long long run = 0;
-                for (int64_t j = (int64_t)tile - 1;; ) {
-                    const unsigned long long d = desc[j];
-                    if ((d >> 42) != epoch) continue;  // predecessor has not published yet
-                    run += d & ((1ull << 40) - 1);
-                    if (((d >> 40) & 3ull) == SCAN_FLAG_PREFIX) break;
-                    j--;
+                if (lane == 0) {
+                    s_prefix = 0;
+                    desc[0] = scan_pack(epoch, SCAN_FLAG_PREFIX, (unsigned long long)total);
                 }
-                s_prefix = run;
-                desc[tile] = scan_pack(epoch, SCAN_FLAG_PREFIX, run + (unsigned long long)total);
+            } else {
+                if (lane == 0) desc[tile] = scan_pack(epoch, SCAN_FLAG_AGG, (unsigned long long)total);
+                unsigned long long run = 0;
+                int64_t start = (int64_t)tile - 1;
+                for (;;) {
+                    const int64_t j = start - lane;
+                    // tiles before 0 act as an (always valid) zero prefix
+                    const unsigned long long d = j >= 0 ? desc[j] : scan_pack(epoch, SCAN_FLAG_PREFIX, 0ull);
+                    const bool valid = (d >> 42) == epoch;
+                    const bool is_prefix = valid && ((d >> 40) & 3ull) == SCAN_FLAG_PREFIX;
+                    const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+                    const uint32_t pmask = __ballot_sync(0xffffffffu, is_prefix);
+                    // lanes 0..fp are needed (fp = nearest published prefix), or all 32 when none is visible yet
+                    const int fp = pmask ? __ffs(pmask) - 1 : 31;
+                    const uint32_t need = fp == 31 ? 0xffffffffu : ((2u << fp) - 1u);
+                    if ((vmask & need) != need) continue;  // a needed predecessor has not published yet: re-read
+                    unsigned long long v = (lane <= fp) ? (d & ((1ull << 40) - 1)) : 0ull;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    run += v;
+                    if (pmask) break;
+                    start -= 32;
+                }
+                if (lane == 0) {
+                    s_prefix = run;
+                    desc[tile] = scan_pack(epoch, SCAN_FLAG_PREFIX, run + (unsigned long long)total);
+                }
             }
         }
         __syncthreads();

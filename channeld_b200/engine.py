@@ -274,7 +274,11 @@ class Engine:
     def set_slab(self, col_lo, col_hi, halo):
         self._ck(self.L.chd_set_slab(self.h, int(col_lo), int(col_hi), int(halo)))
 
-    def export_border(self, d_records, cap_records):
+    def export_border(self, d_records, cap_records, want_count=True):
+        """want_count=False keeps the call free of host synchronisation (overflow shows up in the next summary)."""
+        if not want_count:
+            self._ck(self.L.chd_export_border(self.h, ptr(d_records), int(cap_records), None))
+            return None
         n = C.c_uint32()
         self._ck(self.L.chd_export_border(self.h, ptr(d_records), int(cap_records), C.byref(n)))
         return n.value

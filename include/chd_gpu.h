@@ -195,7 +195,7 @@ typedef struct chd_tick_summary {
     uint32_t required_due;
     uint32_t reserved;
 } chd_tick_summary;
-enum { CHD_OVF_PAIRS = 1, CHD_OVF_WINDOW = 2, CHD_OVF_VISIBLE = 4, CHD_OVF_DUE = 8 };
+enum { CHD_OVF_PAIRS = 1, CHD_OVF_WINDOW = 2, CHD_OVF_VISIBLE = 4, CHD_OVF_DUE = 8, CHD_OVF_BORDER = 16 };
 
 /* Synchronises the stream and returns the counters.  CHD_ERR_CAPACITY if any overflow bit is set. */
 chd_status chd_summary(chd_engine* e, chd_tick_summary* out);
@@ -245,6 +245,8 @@ chd_status chd_device_view(chd_engine* e, int which, void** d_ptr, uint64_t* cou
  * chd_import_halo -> chd_build.  Entity ids are global: set with chd_set_entity_ids. */
 chd_status chd_set_slab(chd_engine* e, uint32_t col_lo, uint32_t col_hi, uint32_t halo);
 chd_status chd_set_entity_ids(chd_engine* e, const uint32_t* global_id, uint32_t n);
+/* out_count may be NULL: then nothing synchronises with the host (an overflow of cap_records or of the entity capacity
+ * surfaces as CHD_OVF_BORDER in the next chd_summary). */
 chd_status chd_export_border(chd_engine* e, uint32_t* d_records, uint32_t cap_records, uint32_t* out_count);
 chd_status chd_import_halo(chd_engine* e, const uint32_t* d_records, uint32_t n_records, uint32_t skip_first, uint32_t skip_count);
 
