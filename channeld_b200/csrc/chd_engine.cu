@@ -70,7 +70,8 @@ struct chd_engine {
     uint32_t phase_stride = 0;
     uint32_t *d_hist = nullptr;           // [BUILD_MAX_BINS * nblocks + 1]
     // one look-back scan site per call site: stages run concurrently on two streams and must not share scan state
-    ScanSite site_hist{}, site_win{}, site_qoff{}, site_slot{}, site_pchist{}, site_diff{}, site_diff2{}, site_voff{}, site_due{}, site_border{};
+    unsigned long long* d_epoch = nullptr;  // [EP_COUNT] stage epochs for the look-back scans
+    ScanSite site_hist_b{}, site_pchist_b{}, site_hist{}, site_win{}, site_qoff{}, site_slot{}, site_pchist{}, site_diff{}, site_diff2{}, site_voff{}, site_due{}, site_border{};
     uint32_t build_blocks = 0;
     bool assigned = false, built = false, have_prev_key = false, entities_dirty = false;
     uint32_t n_sorted = 0;
@@ -181,15 +182,23 @@ static bool dalloc(chd_engine* e, T** p, uint64_t count) {
     return true;
 }
 
-static bool make_site(chd_engine* e, ScanSite& site, uint64_t n_max) {
+enum { EP_BUILD = 0, EP_QUERY, EP_EMIT, EP_FANOUT, EP_BORDER, EP_COUNT };
+
+static bool make_site(chd_engine* e, ScanSite& site, uint64_t n_max, int stage) {
     site.tiles = n_max == 0 ? 1 : (n_max + SCAN_TILE - 1) / SCAN_TILE;
-    if (!dalloc(e, &site.desc, site.tiles) || !dalloc(e, &site.state, 4)) return false;
-    return cudaMemset(site.desc, 0, site.tiles * 8) == cudaSuccess && cudaMemset(site.state, 0, 32) == cudaSuccess;
+    site.epoch = e->d_epoch + stage;
+    if (!dalloc(e, &site.desc, site.tiles)) return false;
+    return cudaMemset(site.desc, 0, site.tiles * 8) == cudaSuccess;
 }
 
 static inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 
 __global__ void set_i64_kernel(int64_t* dst, int64_t v) { *dst = v; }
+// first kernel of the interest / fan-out stages: publishes the tick time and opens a new scan epoch
+__global__ void stage_begin_kernel(int64_t* dst, int64_t v, unsigned long long* epoch) {
+    *dst = v;
+    *epoch = (*epoch + 1) & ((1ull << 22) - 1);
+}
 __global__ void set_u32_kernel(uint32_t* dst, uint32_t v) { *dst = v; }
 
 static inline uint64_t mix_key(uint64_t h, uint64_t v) {
@@ -419,10 +428,12 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
          dalloc(e, &e->d_prev_key, N) && dalloc(e, &e->d_tmp_key, N) && dalloc(e, &e->d_tmp_val, N) &&
          dalloc(e, &e->d_sorted_key, N) && dalloc(e, &e->d_sorted4, 4 * (((N + 3) / 4) * 4 + 8)) && dalloc(e, &e->d_cell_start, C + 2) &&
          dalloc(e, &e->d_hist, (uint64_t)BUILD_MAX_BINS * e->build_blocks + 2) &&
-         make_site(e, e->site_hist, (uint64_t)BUILD_MAX_BINS * e->build_blocks + 1) && make_site(e, e->site_win, Q + 1) &&
-         make_site(e, e->site_qoff, Q + 1) && make_site(e, e->site_slot, S + 1) &&
-         make_site(e, e->site_diff, P + 1) && make_site(e, e->site_diff2, P + 1) && make_site(e, e->site_voff, P + 1) && make_site(e, e->site_due, P + 1) &&
-         make_site(e, e->site_border, N + 1) &&
+         dalloc(e, &e->d_epoch, 8) && cudaMemset(e->d_epoch, 0, 64) == cudaSuccess &&
+         make_site(e, e->site_hist, (uint64_t)BUILD_MAX_BINS * e->build_blocks + 1, EP_BUILD) &&
+         make_site(e, e->site_hist_b, (uint64_t)BUILD_MAX_BINS * e->build_blocks + 1, EP_BUILD) && make_site(e, e->site_win, Q + 1, EP_QUERY) &&
+         make_site(e, e->site_qoff, Q + 1, EP_QUERY) && make_site(e, e->site_slot, S + 1, EP_QUERY) &&
+         make_site(e, e->site_diff, P + 1, EP_QUERY) && make_site(e, e->site_diff2, P + 1, EP_QUERY) && make_site(e, e->site_voff, P + 1, EP_EMIT) &&
+         make_site(e, e->site_due, P + 1, EP_FANOUT) && make_site(e, e->site_border, N + 1, EP_BORDER) &&
          dalloc(e, &e->d_ho_entity, N) && dalloc(e, &e->d_ho_src, N) && dalloc(e, &e->d_ho_dst, N) &&
          dalloc(e, &e->d_bflag, N + 1) && dalloc(e, &e->d_boff, N + 2);
     e->d_sorted_ent = e->d_sorted4;  // phase copy 0 IS the plain sorted entity array
@@ -448,7 +459,8 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
          dalloc(e, &e->d_ring_sender, (uint64_t)L.max_ring_entries) && dalloc(e, &e->d_ring_index, (uint64_t)L.max_ring_entries) &&
          dalloc(e, &e->d_ch_msg_index, C) && dalloc(e, &e->d_due_cnt, P) && dalloc(e, &e->d_by_cell, P) &&
          dalloc(e, &e->d_pc_hist, (uint64_t)BUILD_MAX_BINS * e->pc_blocks + 2) && dalloc(e, &e->d_pc_tmp_key, P) && dalloc(e, &e->d_pc_tmp_val, P) &&
-         make_site(e, e->site_pchist, (uint64_t)BUILD_MAX_BINS * e->pc_blocks + 1) && dalloc(e, &e->d_due_off, P + 1) &&
+         make_site(e, e->site_pchist, (uint64_t)BUILD_MAX_BINS * e->pc_blocks + 1, EP_QUERY) &&
+         make_site(e, e->site_pchist_b, (uint64_t)BUILD_MAX_BINS * e->pc_blocks + 1, EP_QUERY) && dalloc(e, &e->d_due_off, P + 1) &&
          dalloc(e, &e->d_due, (uint64_t)L.max_due) && dalloc(e, &e->d_ctr, 1) && dalloc(e, &e->d_time, 2) &&
          dalloc(e, &e->d_ring_total, 1) && dalloc(e, &e->d_n_build, 1);
     if (!ok) {
@@ -624,6 +636,8 @@ static chd_status sort_pass_any(chd_engine* e, uint32_t* hist, const ScanSite& s
 
 static chd_status build_enqueue(chd_engine* e, bool with_assign) {
     chd_status st;
+    bump_epoch_kernel<<<1, 1, 0, e->stream>>>(e->d_epoch + EP_BUILD);
+    KCHECK(e);
     if (with_assign) {
         st = chd_assign_cells(e);
         if (st != CHD_OK) return st;
@@ -650,7 +664,7 @@ static chd_status build_enqueue(chd_engine* e, bool with_assign) {
     } else {
         st = sort_pass_any(e, e->d_hist, e->site_hist, e->d_key, vals, n, n_ptr, per_block, nblocks, 0, bits0, e->d_tmp_key, e->d_tmp_val);
         if (st != CHD_OK) return st;
-        st = sort_pass_any(e, e->d_hist, e->site_hist, e->d_tmp_key, e->d_tmp_val, n, n_ptr, per_block, nblocks, bits0, bits1, e->d_sorted_key, e->d_sorted_ent);
+        st = sort_pass_any(e, e->d_hist, e->site_hist_b, e->d_tmp_key, e->d_tmp_val, n, n_ptr, per_block, nblocks, bits0, bits1, e->d_sorted_key, e->d_sorted_ent);
         if (st != CHD_OK) return st;
     }
     if (n) {
@@ -810,6 +824,8 @@ chd_status chd_query_channel_ids(chd_engine* e, const chd_query_batch* q, uint32
         }
         return CHD_OK;
     }
+    bump_epoch_kernel<<<1, 1, 0, e->stream>>>(e->d_epoch + EP_QUERY);
+    KCHECK(e);
     st = run_query_kernels(e, d);
     if (st != CHD_OK) return st;
     SCAN(e, exclusive_scan_1p<uint32_t, uint64_t>(e->d_qcount, e->d_qoff, n, e->site_qoff, e->stream));
@@ -894,7 +910,7 @@ static chd_status interest_enqueue(chd_engine* e, const QueryDev& d) {
             st = sort_pass_any(e, e->d_pc_hist, e->site_pchist, cur.cell, nullptr, (uint32_t)P, cur.off + S, per_block, nb, 0, bits0,
                                e->d_pc_tmp_key, e->d_pc_tmp_val);
             if (st != CHD_OK) return st;
-            st = sort_pass_any(e, e->d_pc_hist, e->site_pchist, e->d_pc_tmp_key, e->d_pc_tmp_val, (uint32_t)P, cur.off + S, per_block, nb, bits0,
+            st = sort_pass_any(e, e->d_pc_hist, e->site_pchist_b, e->d_pc_tmp_key, e->d_pc_tmp_val, (uint32_t)P, cur.off + S, per_block, nb, bits0,
                                bits1, nullptr, e->d_by_cell);
             if (st != CHD_OK) return st;
         }
@@ -917,7 +933,7 @@ chd_status chd_update_interest(chd_engine* e, const chd_query_batch* q, int64_t 
     QueryDev d;
     chd_status st = upload_queries(e, q, &d, true);  // H2D / D2D copies into the engine's SoA: outside the graph
     if (st != CHD_OK) return st;
-    set_i64_kernel<<<1, 1, 0, e->stream>>>(e->d_time, now_ns);
+    stage_begin_kernel<<<1, 1, 0, e->stream>>>(e->d_time, now_ns, e->d_epoch + EP_QUERY);
     KCHECK(e);
     // the graph bakes in which staging arrays are live, the batch size and the pair-buffer parity
     uint64_t key = mix_key(mix_key(mix_key(0x696e74ull, d.n), e->n_slots), (uint64_t)e->cur);
@@ -945,6 +961,8 @@ chd_status chd_emit_visible(chd_engine* e) {
     const unsigned grid = (unsigned)e->sm_count * 8;
     const uint64_t key = mix_key(mix_key(0x656d6974ull, S), (uint64_t)e->cur);
     chd_status st = run_stage(e, e->g_emit_prep[e->cur], key, [&]() -> chd_status {
+        bump_epoch_kernel<<<1, 1, 0, s>>>(e->d_epoch + EP_EMIT);
+        KCHECK(e);
         pair_vcount_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, pb.cell, e->d_cell_start, e->d_vcnt);
         KCHECK(e);
         SCAN(e, exclusive_scan_1p<uint32_t, uint64_t>(e->d_vcnt, e->d_voff, P, e->site_voff, s, pb.off + S));
@@ -1000,7 +1018,7 @@ chd_status chd_fanout_tick(chd_engine* e, int64_t t_ns) {
     const uint32_t S = e->n_slots;
     const uint64_t P = e->lim.max_pairs;
     StageTimer timer(e, CHD_STAGE_FANOUT);
-    set_i64_kernel<<<1, 1, 0, s>>>(e->d_time + 1, t_ns);
+    stage_begin_kernel<<<1, 1, 0, s>>>(e->d_time + 1, t_ns, e->d_epoch + EP_FANOUT);
     KCHECK(e);
     RingDev ring{e->d_ring_off, e->d_ring_arrival, e->d_ring_sender, e->d_ring_index, e->have_ch_msg_index ? e->d_ch_msg_index : nullptr,
                  e->d_ring_total};
@@ -1273,6 +1291,8 @@ chd_status chd_export_border(chd_engine* e, uint32_t* d_records, uint32_t cap_re
     if (st != CHD_OK) return st;
     cudaStream_t s = e->stream;
     const uint32_t n = e->n_own;
+    bump_epoch_kernel<<<1, 1, 0, s>>>(e->d_epoch + EP_BORDER);
+    KCHECK(e);
     border_flag_kernel<<<blocks_for(n ? n : 1, 256), 256, 0, s>>>(e->g, e->d_key, n, e->d_bflag);
     KCHECK(e);
     SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_bflag, e->d_boff, n, e->site_border, s));
@@ -1306,6 +1326,8 @@ chd_status chd_import_halo(chd_engine* e, const uint32_t* d_records, uint32_t n_
         e->fail("halo import of %u records > max_entities scratch %u", n_records, e->lim.max_entities);
         return CHD_ERR_CAPACITY;
     }
+    bump_epoch_kernel<<<1, 1, 0, s>>>(e->d_epoch + EP_BORDER);
+    KCHECK(e);
     halo_flag_kernel<<<blocks_for(n_records ? n_records : 1, 256), 256, 0, s>>>(e->g, d_records, n_records, skip_first, skip_count, e->d_bflag);
     KCHECK(e);
     SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_bflag, e->d_boff, n_records, e->site_border, s));

@@ -120,17 +120,20 @@ inline int exclusive_scan(const TIn* in, TOut* out, uint64_t n, TOut* scratch, c
 
 // ---------------------------------------------------------------------------------------------------------
 // Single-pass scan (decoupled look-back): ONE kernel per prefix sum instead of three.  Each scan call site owns
-// a ScanSite: tile descriptors + a ticket counter + a completion counter + an epoch, all in device memory, so a
-// launch carries no per-call host state and can be replayed from a CUDA graph.  A descriptor is one 64-bit
-// word [epoch:22 | flag:2 | value:40]; descriptors written by an earlier scan carry an older epoch and read as
-// "not ready".  Blocks take tile ids from the ticket counter (a predecessor tile is always owned by a block that
-// is already running: forward progress).  The last block to finish resets the counters and bumps the epoch.
-// Sums must stay below 2^40.
+// a ScanSite: tile descriptors in device memory plus a pointer to its stage's epoch counter, which an earlier
+// kernel of the same stage increments once per stage execution (bump_epoch_kernel / stage_begin_kernel).  A launch
+// therefore carries no per-call host state and can be replayed from a CUDA graph.  A descriptor is one 64-bit
+// word [epoch:22 | flag:2 | value:40]; descriptors written by an earlier stage execution carry an older epoch
+// and read as "not ready".  Tile id = blockIdx.x (lower-indexed blocks of a 1-D grid are dispatched first, the
+// usual forward-progress assumption of decoupled look-back).  No atomics.  Sums must stay below 2^40; a site may
+// be used once per stage execution.
 struct ScanSite {
-    unsigned long long* desc;   // [tiles]
-    unsigned long long* state;  // [0] ticket counter, [1] finished blocks, [2] epoch
-    uint64_t tiles;             // fixed launch width of this site (from its capacity)
+    unsigned long long* desc;         // [tiles]
+    const unsigned long long* epoch;  // the owning stage's epoch counter
+    uint64_t tiles;                   // descriptor capacity
 };
+
+__global__ void bump_epoch_kernel(unsigned long long* epoch) { *epoch = (*epoch + 1) & ((1ull << 22) - 1); }
 
 constexpr unsigned long long SCAN_FLAG_AGG = 1ull, SCAN_FLAG_PREFIX = 2ull;
 __device__ __forceinline__ unsigned long long scan_pack(unsigned long long epoch, unsigned long long flag, unsigned long long v) {
@@ -140,92 +143,76 @@ __device__ __forceinline__ unsigned long long scan_pack(unsigned long long epoch
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(SCAN_THREADS)
     scan_lookback_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, uint64_t n, const uint32_t* __restrict__ n_ptr, ScanSite site) {
-    __shared__ unsigned long long s_tile, s_prefix;
+    __shared__ unsigned long long s_prefix;
     volatile unsigned long long* desc = site.desc;
-    const unsigned long long epoch = (*(volatile unsigned long long*)(site.state + 2) + 1) & ((1ull << 22) - 1);
-    if (threadIdx.x == 0) s_tile = atomicAdd(site.state, 1ull);
     if (n_ptr) n = min(n, (uint64_t)*n_ptr);
-    __syncthreads();
-    const uint64_t tile = s_tile;
-    const bool live = tile * SCAN_TILE < n || (n == 0 && tile == 0);
-    if (live) {
-        const uint64_t base = tile * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
-        TOut v[SCAN_ITEMS];
-        TOut acc = 0;
+    const uint64_t tile = blockIdx.x;
+    if (!(tile * SCAN_TILE < n || (n == 0 && tile == 0))) return;  // beyond the live length: nothing to publish
+    const unsigned long long epoch = *site.epoch;
+    const uint64_t base = tile * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    TOut v[SCAN_ITEMS];
+    TOut acc = 0;
 #pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; k++) {
-            const uint64_t i = base + k;
-            v[k] = i < n ? (TOut)in[i] : TOut(0);
-            acc += v[k];
-        }
-        TOut total;
-        TOut pre = block_excl_scan<TOut>(acc, total);
-        if (threadIdx.x < 32) {
-            // warp-parallel look-back: 32 predecessor descriptors per hop
-            const int lane = threadIdx.x;
-            if (tile == 0) {
-                if (lane == 0) {
-                    s_prefix = 0;
-                    desc[0] = scan_pack(epoch, SCAN_FLAG_PREFIX, (unsigned long long)total);
-                }
-            } else {
-                if (lane == 0) desc[tile] = scan_pack(epoch, SCAN_FLAG_AGG, (unsigned long long)total);
-                unsigned long long run = 0;
-                int64_t start = (int64_t)tile - 1;
-                for (;;) {
-                    const int64_t j = start - lane;
-                    // tiles before 0 act as an (always valid) zero prefix
-                    const unsigned long long d = j >= 0 ? desc[j] : scan_pack(epoch, SCAN_FLAG_PREFIX, 0ull);
-                    const bool valid = (d >> 42) == epoch;
-                    const bool is_prefix = valid && ((d >> 40) & 3ull) == SCAN_FLAG_PREFIX;
-                    const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-                    const uint32_t pmask = __ballot_sync(0xffffffffu, is_prefix);
-                    // lanes 0..fp are needed (fp = nearest published prefix), or all 32 when none is visible yet
-                    const int fp = pmask ? __ffs(pmask) - 1 : 31;
-                    const uint32_t need = fp == 31 ? 0xffffffffu : ((2u << fp) - 1u);
-                    if ((vmask & need) != need) continue;  // a needed predecessor has not published yet: re-read
-                    unsigned long long v = (lane <= fp) ? (d & ((1ull << 40) - 1)) : 0ull;
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        const uint64_t i = base + k;
+        v[k] = i < n ? (TOut)in[i] : TOut(0);
+        acc += v[k];
+    }
+    TOut total;
+    TOut pre = block_excl_scan<TOut>(acc, total);
+    if (threadIdx.x < 32) {
+        // warp-parallel look-back: 32 predecessor descriptors per hop
+        const int lane = threadIdx.x;
+        if (tile == 0) {
+            if (lane == 0) {
+                s_prefix = 0;
+                desc[0] = scan_pack(epoch, SCAN_FLAG_PREFIX, (unsigned long long)total);
+            }
+        } else {
+            if (lane == 0) desc[tile] = scan_pack(epoch, SCAN_FLAG_AGG, (unsigned long long)total);
+            unsigned long long run = 0;
+            int64_t start = (int64_t)tile - 1;
+            for (;;) {
+                const int64_t j = start - lane;
+                // tiles before 0 act as an (always valid) zero prefix
+                const unsigned long long d = j >= 0 ? desc[j] : scan_pack(epoch, SCAN_FLAG_PREFIX, 0ull);
+                const bool valid = (d >> 42) == epoch;
+                const bool is_prefix = valid && ((d >> 40) & 3ull) == SCAN_FLAG_PREFIX;
+                const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+                const uint32_t pmask = __ballot_sync(0xffffffffu, is_prefix);
+                // lanes 0..fp are needed (fp = nearest published prefix), or all 32 when none is visible yet
+                const int fp = pmask ? __ffs(pmask) - 1 : 31;
+                const uint32_t need = fp == 31 ? 0xffffffffu : ((2u << fp) - 1u);
+                if ((vmask & need) != need) continue;  // a needed predecessor has not published yet: re-read
+                unsigned long long x = (lane <= fp) ? (d & ((1ull << 40) - 1)) : 0ull;
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                    run += v;
-                    if (pmask) break;
-                    start -= 32;
-                }
-                if (lane == 0) {
-                    s_prefix = run;
-                    desc[tile] = scan_pack(epoch, SCAN_FLAG_PREFIX, run + (unsigned long long)total);
-                }
+                for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                run += x;
+                if (pmask) break;
+                start -= 32;
+            }
+            if (lane == 0) {
+                s_prefix = run;
+                desc[tile] = scan_pack(epoch, SCAN_FLAG_PREFIX, run + (unsigned long long)total);
             }
         }
-        __syncthreads();
-        pre += (TOut)s_prefix;
-#pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; k++) {
-            const uint64_t i = base + k;
-            if (i < n) out[i] = pre;
-            pre += v[k];
-            if (i + 1 == n) out[n] = pre;
-        }
-        if (n == 0 && threadIdx.x == 0) out[0] = 0;
     }
-    // completion: the last block resets the site for the next launch
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(site.state + 1, 1ull) + 1 == gridDim.x) {
-            site.state[0] = 0;
-            site.state[1] = 0;
-            site.state[2] = epoch;
-            __threadfence();
-        }
+    pre += (TOut)s_prefix;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        const uint64_t i = base + k;
+        if (i < n) out[i] = pre;
+        pre += v[k];
+        if (i + 1 == n) out[n] = pre;
     }
+    if (n == 0 && threadIdx.x == 0) out[0] = 0;
 }
 
 template <typename TIn, typename TOut>
 inline int exclusive_scan_1p(const TIn* in, TOut* out, uint64_t n, const ScanSite& site, cudaStream_t st, const uint32_t* n_ptr = nullptr) {
-    const uint64_t tiles = n == 0 ? 1 : (n + SCAN_TILE - 1) / SCAN_TILE;
-    // the launch width is the site's fixed width so that every launch rewrites the same descriptor range
-    scan_lookback_kernel<TIn, TOut><<<(unsigned)(tiles > site.tiles ? tiles : site.tiles), SCAN_THREADS, 0, st>>>(in, out, n, n_ptr, site);
+    const uint64_t tiles = n == 0 ? 1 : (n + SCAN_TILE - 1) / SCAN_TILE;  // <= site.tiles by construction of the site
+    scan_lookback_kernel<TIn, TOut><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, out, n, n_ptr, site);
     return 1;
 }
 
