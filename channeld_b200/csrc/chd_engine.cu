@@ -187,6 +187,7 @@ enum { EP_BUILD = 0, EP_QUERY, EP_EMIT, EP_FANOUT, EP_BORDER, EP_COUNT };
 static bool make_site(chd_engine* e, ScanSite& site, uint64_t n_max, int stage) {
     site.tiles = n_max == 0 ? 1 : (n_max + SCAN_TILE - 1) / SCAN_TILE;
     site.epoch = e->d_epoch + stage;
+    site.error = nullptr;  // set once d_ctr exists
     if (!dalloc(e, &site.desc, site.tiles)) return false;
     return cudaMemset(site.desc, 0, site.tiles * 8) == cudaSuccess;
 }
@@ -468,6 +469,9 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
         chd_destroy(e);
         return CHD_ERR_CUDA;
     }
+    for (ScanSite* site : {&e->site_hist, &e->site_hist_b, &e->site_pchist, &e->site_pchist_b, &e->site_win, &e->site_qoff, &e->site_slot,
+                           &e->site_diff, &e->site_diff2, &e->site_voff, &e->site_due, &e->site_border})
+        site->error = &e->d_ctr->overflow;
     CCU(cudaHostAlloc((void**)&e->h_ctr, sizeof(Counters), cudaHostAllocDefault));
     CCU(cudaHostAlloc((void**)&e->h_u32, 64, cudaHostAllocDefault));
     CCU(cudaMemsetAsync(e->d_ctr, 0, sizeof(Counters), e->stream));

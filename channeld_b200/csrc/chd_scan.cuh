@@ -130,6 +130,7 @@ inline int exclusive_scan(const TIn* in, TOut* out, uint64_t n, TOut* scratch, c
 struct ScanSite {
     unsigned long long* desc;         // [tiles]
     const unsigned long long* epoch;  // the owning stage's epoch counter
+    uint32_t* error;                  // bit 31 is set if a look-back ever times out (reported as an overflow bit)
     uint64_t tiles;                   // descriptor capacity
 };
 
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(SCAN_THREADS)
             if (lane == 0) desc[tile] = scan_pack(epoch, SCAN_FLAG_AGG, (unsigned long long)total);
             unsigned long long run = 0;
             int64_t start = (int64_t)tile - 1;
+            uint32_t spins = 0;
             for (;;) {
                 const int64_t j = start - lane;
                 // tiles before 0 act as an (always valid) zero prefix
@@ -183,7 +185,14 @@ __global__ void __launch_bounds__(SCAN_THREADS)
                 // lanes 0..fp are needed (fp = nearest published prefix), or all 32 when none is visible yet
                 const int fp = pmask ? __ffs(pmask) - 1 : 31;
                 const uint32_t need = fp == 31 ? 0xffffffffu : ((2u << fp) - 1u);
-                if ((vmask & need) != need) continue;  // a needed predecessor has not published yet: re-read
+                if ((vmask & need) != need) {  // a needed predecessor has not published yet: re-read
+                    // bounded: a scheduling pathology must surface as an error, never as a hung GPU
+                    if (++spins > (1u << 24)) {
+                        if (lane == 0 && site.error) atomicOr(site.error, 0x80000000u);
+                        break;
+                    }
+                    continue;
+                }
                 unsigned long long x = (lane <= fp) ? (d & ((1ull << 40) - 1)) : 0ull;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
