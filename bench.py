@@ -386,13 +386,22 @@ def run_ours(args):
         r_iv, _ = pinned((P_cap,), torch.int32)
         r_new = [pinned((P_cap,), torch.int32)[0] for _ in range(4)]
         r_due, _ = pinned((2 * P_cap, 12), torch.int32)
-        r_cs, _ = pinned((wc.cells + 1,), torch.int32)
-        r_se, _ = pinned((max_ent,), torch.int32)
+        r_ho = [pinned((max_ent,), torch.int32)[0] for _ in range(3)]
+        r_status, _ = pinned((max(S, 1),), torch.int32)
         r_voff, _ = pinned((S + 1,), torch.int64)
-        r_vis = None
         summ = capi.TickSummary()
+        rb = capi.ResultBuffers()
+        rb.pair_off, rb.pair_channel, rb.pair_dist, rb.pair_interval_ms, rb.pair_cap = (capi.ptr(r_off), capi.ptr(r_ch), capi.ptr(r_dist),
+                                                                                       capi.ptr(r_iv), P_cap)
+        rb.new_sub, rb.new_channel, rb.unsub_sub, rb.unsub_channel, rb.diff_cap = (*[capi.ptr(t) for t in r_new], P_cap)
+        rb.due, rb.due_cap = capi.ptr(r_due), 2 * P_cap
+        rb.handover_entity, rb.handover_src, rb.handover_dst, rb.handover_cap = (*[capi.ptr(t) for t in r_ho], max_ent)
+        rb.query_status, rb.status_cap = capi.ptr(r_status), S
+        rb.vis_off = capi.ptr(r_voff)
+        r_vis_keep = []
 
         def e2e_step(i, expanded=False):
+            """Host inputs -> H2D -> one batched tick -> D2H of everything a channeld host consumes (chd_fetch_results)."""
             d = host_in[i % 2]
             rg = rings_host[i]
             t_ns = (i + 1) * TICK_NS
@@ -403,19 +412,15 @@ def run_ours(args):
                 dist.all_gather_into_tensor(rec_all, rec_local)
                 e.import_halo(rec_all, border_cap * world, rank * border_cap, border_cap)
             ck(L.chd_set_rings(e.h, capi.ptr(rg["off"]), rg["n"], capi.ptr(rg["arr"]), capi.ptr(rg["snd"]), capi.ptr(rg["idx"]), capi.ptr(rg["cmi"])))
-            ck(L.chd_tick(e.h, C.byref(batches_host[i % 2]), t_ns, capi.TICK_ALL, C.byref(summ)))
-            if summ.n_pairs > P_cap:
-                raise SystemExit("e2e result buffers too small")
-            ck(L.chd_get_pairs(e.h, capi.ptr(r_off), capi.ptr(r_ch), capi.ptr(r_dist), capi.ptr(r_iv), None, None, None))
-            ck(L.chd_get_diff(e.h, capi.ptr(r_new[0]), capi.ptr(r_new[1]), capi.ptr(r_new[2]), capi.ptr(r_new[3])))
-            nd = min(int(summ.n_due), r_due.shape[0])
-            if nd:
-                ck(L.chd_get_due(e.h, capi.ptr(r_due), nd))
-            ck(L.chd_get_cells(e.h, capi.ptr(r_cs), capi.ptr(r_se)))
-            ck(L.chd_get_visible(e.h, capi.ptr(r_voff), capi.ptr(r_vis) if expanded else None))
+            ck(L.chd_tick(e.h, C.byref(batches_host[i % 2]), t_ns, capi.TICK_ALL, None))
+            if expanded:
+                rb.vis_entity, rb.vis_cap = capi.ptr(r_vis_keep[0]), r_vis_keep[0].numel()
+            else:
+                rb.vis_entity, rb.vis_cap = None, 0
+            ck(L.chd_fetch_results(e.h, C.byref(rb), C.byref(summ)))
             h2d = 16 * n_own + 28 * S + (wc.cells + 1) * 4 + rg["n"] * 20 + wc.cells * 8
-            d2h = (C.sizeof(capi.TickSummary) + (S + 1) * 4 + 12 * int(summ.n_pairs) + 8 * (int(summ.n_sub_new) + int(summ.n_unsub)) + 48 * nd
-                   + (wc.cells + 1) * 4 + 4 * int(summ.n_entities_in_world) + (S + 1) * 8 + (4 * int(summ.n_visible) if expanded else 0))
+            d2h = (C.sizeof(capi.TickSummary) + (S + 1) * 4 + 12 * int(summ.n_pairs) + 8 * (int(summ.n_sub_new) + int(summ.n_unsub))
+                   + 48 * int(summ.n_due) + 12 * int(summ.n_handover) + 4 * S + (S + 1) * 8 + (4 * int(summ.n_visible) if expanded else 0))
             return h2d, d2h
 
         base = args.warmup + 1 + args.steps
@@ -431,7 +436,7 @@ def run_ours(args):
         e2e_dt = time.perf_counter() - t0
         e2e_exp = None
         if args.expanded_steps > 0 and world == 1:
-            r_vis, _ = pinned((int(summ.n_visible) + 1024,), torch.int32)
+            r_vis_keep.append(pinned((int(sm.n_visible) + (1 << 20),), torch.int32)[0])
             e2e_step(base + 2 + n_e2e, True)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -484,8 +489,8 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": S_total * n_e2e / e2e_dt, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_dt / n_e2e * 1e3,
-                    "result": "summary + (cell,dist,interval) pairs + sub/unsub lists + fan-out due list + cell CSR + visible offsets; "
-                              "the expanded list stays in HBM for GPU-side consumers (see e2e_expanded)"},
+                    "result": "chd_fetch_results: summary + (cell,dist,interval) pairs + sub/unsub lists + fan-out due list + handover "
+                              "list + query statuses + visible offsets; the expanded list stays in HBM for GPU-side consumers (see e2e_expanded)"},
             "e2e_expanded": e2e_exp,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "emit_visible_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -70,6 +70,20 @@ DUE_DTYPE = np.dtype([("sub", "<u4"), ("channel_id", "<u4"), ("kind", "<u4"), ("
 assert DUE_DTYPE.itemsize == C.sizeof(Due) == 48
 
 
+class ResultBuffers(C.Structure):
+    _fields_ = [
+        ("pair_off", C.c_void_p), ("pair_channel", C.c_void_p), ("pair_dist", C.c_void_p), ("pair_interval_ms", C.c_void_p),
+        ("pair_cap", C.c_uint64),
+        ("new_sub", C.c_void_p), ("new_channel", C.c_void_p), ("unsub_sub", C.c_void_p), ("unsub_channel", C.c_void_p),
+        ("diff_cap", C.c_uint64),
+        ("due", C.c_void_p), ("due_cap", C.c_uint32),
+        ("handover_entity", C.c_void_p), ("handover_src", C.c_void_p), ("handover_dst", C.c_void_p), ("handover_cap", C.c_uint32),
+        ("query_status", C.c_void_p), ("status_cap", C.c_uint32),
+        ("vis_off", C.c_void_p), ("vis_entity", C.c_void_p), ("vis_cap", C.c_uint64),
+        ("cell_start", C.c_void_p), ("sorted_entity", C.c_void_p), ("entity_cap", C.c_uint32),
+    ]
+
+
 class TickSummary(C.Structure):
     _fields_ = [
         ("n_pairs", C.c_uint64), ("n_visible", C.c_uint64), ("n_entities_in_world", C.c_uint32),
@@ -89,7 +103,7 @@ SYMBOLS = [
     "chd_alloc_pinned", "chd_free_pinned", "chd_cell_of", "chd_set_entities", "chd_entity_buffers", "chd_set_entity_count",
     "chd_assign_cells", "chd_build", "chd_set_subscribers", "chd_query_channel_ids", "chd_update_interest",
     "chd_emit_visible", "chd_set_rings", "chd_fanout_tick", "chd_summary", "chd_tick", "chd_get_cells", "chd_get_pairs",
-    "chd_get_query_status", "chd_get_diff", "chd_get_visible", "chd_get_visible_slot", "chd_get_due", "chd_get_handover", "chd_device_view",
+    "chd_get_query_status", "chd_get_diff", "chd_get_visible", "chd_get_visible_slot", "chd_get_due", "chd_fetch_results", "chd_get_handover", "chd_device_view",
     "chd_set_slab", "chd_set_entity_ids", "chd_export_border", "chd_import_halo", "chd_get_adjacent_channels",
     "chd_get_regions", "chd_damping_interval_ms", "chd_launch_count", "chd_profile_enable", "chd_profile_get", "chd_enable_graphs",
     "chd_graph_launch_count",
@@ -162,6 +176,8 @@ def lib():
     L.chd_get_diff.argtypes = [vp, vp, vp, vp, vp]
     L.chd_get_visible.restype = C.c_int
     L.chd_get_visible.argtypes = [vp, vp, vp]
+    L.chd_fetch_results.restype = C.c_int
+    L.chd_fetch_results.argtypes = [vp, C.POINTER(ResultBuffers), C.POINTER(TickSummary)]
     L.chd_get_visible_slot.restype = C.c_int
     L.chd_get_visible_slot.argtypes = [vp, C.c_uint32, vp, C.c_uint64, u64p]
     L.chd_get_due.restype = C.c_int

@@ -1255,6 +1255,63 @@ chd_status chd_get_handover(chd_engine* e, uint32_t* entity, uint32_t* src_chann
     return CHD_OK;
 }
 
+chd_status chd_fetch_results(chd_engine* e, const chd_result_buffers* b, chd_tick_summary* summary) {
+    if (!e || !b || !summary) return CHD_ERR_INVALID;
+    chd_status st = chd_summary(e, summary);  // sync #1 (also surfaces capacity overflows)
+    if (st != CHD_OK) return st;
+    cudaStream_t s = e->stream;
+    PairBuf& pb = e->pairs[e->cur];
+    const uint32_t S = e->n_slots;
+    const uint64_t P = summary->n_pairs;
+    if ((b->pair_channel || b->pair_dist || b->pair_interval_ms) && P > b->pair_cap) {
+        e->fail("chd_fetch_results: %llu pairs > pair_cap %llu", (unsigned long long)P, (unsigned long long)b->pair_cap);
+        return CHD_ERR_CAPACITY;
+    }
+    if (b->pair_off) CU(e, cudaMemcpyAsync(b->pair_off, pb.off, sizeof(uint32_t) * ((uint64_t)S + 1), cudaMemcpyDefault, s));
+    if (b->pair_channel) {
+        add_const_kernel<<<blocks_for(P ? P : 1, 256), 256, 0, s>>>(pb.cell, (uint32_t)P, e->g.id_start, e->d_vcnt);
+        KCHECK(e);
+        CU(e, cudaMemcpyAsync(b->pair_channel, e->d_vcnt, sizeof(uint32_t) * P, cudaMemcpyDefault, s));
+    }
+    if (b->pair_dist) CU(e, cudaMemcpyAsync(b->pair_dist, pb.dist, sizeof(uint32_t) * P, cudaMemcpyDefault, s));
+    if (b->pair_interval_ms) CU(e, cudaMemcpyAsync(b->pair_interval_ms, pb.interval, sizeof(uint32_t) * P, cudaMemcpyDefault, s));
+    const uint64_t nn = summary->n_sub_new, nu = summary->n_unsub;
+    if ((b->new_sub || b->new_channel) && nn > b->diff_cap) return CHD_ERR_CAPACITY;
+    if ((b->unsub_sub || b->unsub_channel) && nu > b->diff_cap) return CHD_ERR_CAPACITY;
+    if (b->new_sub) CU(e, cudaMemcpyAsync(b->new_sub, e->d_new_sub, sizeof(uint32_t) * nn, cudaMemcpyDefault, s));
+    if (b->new_channel) CU(e, cudaMemcpyAsync(b->new_channel, e->d_new_ch, sizeof(uint32_t) * nn, cudaMemcpyDefault, s));
+    if (b->unsub_sub) CU(e, cudaMemcpyAsync(b->unsub_sub, e->d_gone_sub, sizeof(uint32_t) * nu, cudaMemcpyDefault, s));
+    if (b->unsub_channel) CU(e, cudaMemcpyAsync(b->unsub_channel, e->d_gone_ch, sizeof(uint32_t) * nu, cudaMemcpyDefault, s));
+    if (b->due) {
+        if (summary->n_due > b->due_cap) return CHD_ERR_CAPACITY;
+        CU(e, cudaMemcpyAsync(b->due, e->d_due, sizeof(chd_due) * (uint64_t)summary->n_due, cudaMemcpyDefault, s));
+    }
+    if (b->handover_entity || b->handover_src || b->handover_dst) {
+        uint32_t nh = summary->n_handover;
+        if (nh > e->ho_cap) nh = e->ho_cap;
+        if (nh > b->handover_cap) return CHD_ERR_CAPACITY;
+        if (b->handover_entity) CU(e, cudaMemcpyAsync(b->handover_entity, e->d_ho_entity, sizeof(uint32_t) * nh, cudaMemcpyDefault, s));
+        if (b->handover_src) CU(e, cudaMemcpyAsync(b->handover_src, e->d_ho_src, sizeof(uint32_t) * nh, cudaMemcpyDefault, s));
+        if (b->handover_dst) CU(e, cudaMemcpyAsync(b->handover_dst, e->d_ho_dst, sizeof(uint32_t) * nh, cudaMemcpyDefault, s));
+    }
+    if (b->query_status) {
+        const uint32_t n = e->last_nq < b->status_cap ? e->last_nq : b->status_cap;
+        CU(e, cudaMemcpyAsync(b->query_status, e->d_status, sizeof(uint32_t) * n, cudaMemcpyDefault, s));
+    }
+    if (b->vis_off) CU(e, cudaMemcpyAsync(b->vis_off, e->d_vis_off, sizeof(uint64_t) * ((uint64_t)S + 1), cudaMemcpyDefault, s));
+    if (b->vis_entity) {
+        if (summary->n_visible > b->vis_cap) return CHD_ERR_CAPACITY;
+        CU(e, cudaMemcpyAsync(b->vis_entity, e->d_vis, sizeof(uint32_t) * summary->n_visible, cudaMemcpyDefault, s));
+    }
+    if (b->cell_start) CU(e, cudaMemcpyAsync(b->cell_start, e->d_cell_start, sizeof(uint32_t) * ((uint64_t)e->g.cells + 1), cudaMemcpyDefault, s));
+    if (b->sorted_entity) {
+        if (summary->n_entities_in_world > b->entity_cap) return CHD_ERR_CAPACITY;
+        CU(e, cudaMemcpyAsync(b->sorted_entity, e->d_sorted_ent, sizeof(uint32_t) * (uint64_t)summary->n_entities_in_world, cudaMemcpyDefault, s));
+    }
+    CU(e, cudaStreamSynchronize(s));  // sync #2
+    return CHD_OK;
+}
+
 chd_status chd_device_view(chd_engine* e, int which, void** d_ptr, uint64_t* count) {
     if (!e || !d_ptr) return CHD_ERR_INVALID;
     PairBuf& pb = e->pairs[e->cur];

@@ -228,6 +228,29 @@ chd_status chd_get_due(chd_engine* e, chd_due* out, uint32_t cap);
 /* handover candidates of the last build: entity, src channel id, dst channel id (0 = left/entered the world) */
 chd_status chd_get_handover(chd_engine* e, uint32_t* entity, uint32_t* src_channel, uint32_t* dst_channel, uint32_t cap);
 
+/* ---- all host-facing results of a tick with TWO synchronisations instead of one or two per getter: waits for
+ * the tick, reads the summary, then enqueues every requested copy (exact sizes from the summary) and waits once.
+ * Any pointer may be NULL (skipped).  Capacities are in elements; CHD_ERR_CAPACITY if a requested list does not
+ * fit (nothing is truncated silently).  This is what a channeld host calls once per tick. */
+typedef struct chd_result_buffers {
+    uint32_t *pair_off, *pair_channel, *pair_dist, *pair_interval_ms; /* pair_off[n_subscribers+1]; others [pair_cap] */
+    uint64_t pair_cap;
+    uint32_t *new_sub, *new_channel, *unsub_sub, *unsub_channel;      /* [diff_cap] each */
+    uint64_t diff_cap;
+    chd_due* due;                                                     /* [due_cap] */
+    uint32_t due_cap;
+    uint32_t *handover_entity, *handover_src, *handover_dst;          /* [handover_cap] */
+    uint32_t handover_cap;
+    uint32_t* query_status;                                           /* [status_cap] */
+    uint32_t status_cap;
+    uint64_t* vis_off;                                                /* [n_subscribers+1] */
+    uint32_t* vis_entity;                                             /* [vis_cap] (the big one: usually NULL) */
+    uint64_t vis_cap;
+    uint32_t *cell_start, *sorted_entity;                             /* [cells+1], [entity_cap] */
+    uint32_t entity_cap;
+} chd_result_buffers;
+chd_status chd_fetch_results(chd_engine* e, const chd_result_buffers* bufs, chd_tick_summary* summary);
+
 /* Device-resident views (valid until the next call that rewrites them) for consumers that stay on the GPU. */
 enum {
     CHD_VIEW_CELL_START = 0, CHD_VIEW_SORTED_ENTITY, CHD_VIEW_ENT_CELL, CHD_VIEW_PAIR_OFF, CHD_VIEW_PAIR_CHANNEL,

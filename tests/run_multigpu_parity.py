@@ -28,8 +28,10 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     orc = _oracle.load()
     failures = 0
+    # the 2x2 grid gives every rank of a 2-GPU run a ONE-column slab (empty interior, as at 8 GPUs on 15 columns)
     for name, n_ent, n_sub, radius, max_move in (("benchmark", 120_000, 6_000, 50.0, 60.0), ("benchmark", 60_000, 3_000, 2500.0, 900.0),
-                                                 ("handover", 200_000, 4_000, 50.0, 120.0)):
+                                                 ("handover", 200_000, 4_000, 50.0, 120.0), ("2x2", 50_000, 2_000, 50.0, 60.0),
+                                                 ("2x2", 50_000, 2_000, 500.0, 300.0)):
         wc = synth.scaled(synth.CONFIGS[name], n_ent, n_sub)
         if world > wc.cols:
             continue

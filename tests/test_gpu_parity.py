@@ -508,3 +508,61 @@ def test_graph_replay_matches_direct_and_oracle(chd, oracle):
         for x, y in zip(a[5], b[5]):
             np.testing.assert_array_equal(x, y)
     assert sum(r[0]["n_due"] for r in results[True]) > 1000 and sum(r[0]["n_handover"] for r in results[True]) > 100
+
+
+def test_fetch_results_matches_getters(chd):
+    """chd_fetch_results (one call, two syncs) returns exactly what the individual getters return."""
+    import ctypes as C
+
+    wc = chd.synth.scaled(chd.synth.CONFIGS["benchmark"], 20_000, 2_000)
+    e = chd.engine.Engine(wc.cfg(), wc.n_entities, wc.n_subscribers, max_visible=1 << 22)
+    ex, ez = chd.synth.entities(wc)
+    conn, cx, cz, r = chd.synth.subscribers(wc, ex, ez)
+    cx[:3] = wc.offx - 5.0  # a few failing queries
+    e.set_subscribers(conn)
+    ring_state = None
+    for tick in range(3):
+        t = (tick + 1) * 33_000_000
+        ex, ez = chd.synth.move_entities(wc, ex, ez, tick, 500.0)
+        e.set_entities(ex, ez)
+        batch, keep = chd.engine.make_batch(len(cx), sub=np.arange(len(cx), dtype=np.uint32), sphere=(cx + 300.0 * tick, cz, r))
+        ring_state, off, arr, snd, idx, cmi = chd.synth.update_rings(wc, tick, t, 33_000_000, 4, len(conn), ring_len=16, state=ring_state)
+        e.set_rings(off, arr, snd, idx, cmi)
+        e.tick(batch, t, chd.capi.TICK_ALL, want_summary=False)
+        S, cap = len(conn), 1 << 16
+        bufs = {k: np.zeros(cap, np.uint32) for k in ("ch", "dist", "iv", "ns", "nc", "us", "uc", "he", "hs", "hd", "st", "se")}
+        poff, voff = np.zeros(S + 1, np.uint32), np.zeros(S + 1, np.uint64)
+        due = np.zeros(cap, chd.capi.DUE_DTYPE)
+        vis = np.zeros(1 << 22, np.uint32)
+        cs = np.zeros(wc.cells + 1, np.uint32)
+        rb = chd.capi.ResultBuffers()
+        P = chd.capi.ptr
+        rb.pair_off, rb.pair_channel, rb.pair_dist, rb.pair_interval_ms, rb.pair_cap = P(poff), P(bufs["ch"]), P(bufs["dist"]), P(bufs["iv"]), cap
+        rb.new_sub, rb.new_channel, rb.unsub_sub, rb.unsub_channel, rb.diff_cap = P(bufs["ns"]), P(bufs["nc"]), P(bufs["us"]), P(bufs["uc"]), cap
+        rb.due, rb.due_cap = P(due), cap
+        rb.handover_entity, rb.handover_src, rb.handover_dst, rb.handover_cap = P(bufs["he"]), P(bufs["hs"]), P(bufs["hd"]), cap
+        rb.query_status, rb.status_cap = P(bufs["st"]), cap
+        rb.vis_off, rb.vis_entity, rb.vis_cap = P(voff), P(vis), len(vis)
+        rb.cell_start, rb.sorted_entity, rb.entity_cap = P(cs), P(bufs["se"]), cap
+        s = chd.capi.TickSummary()
+        assert e.L.chd_fetch_results(e.h, C.byref(rb), C.byref(s)) == 0
+        pairs = e.get_pairs(s.n_pairs)
+        np.testing.assert_array_equal(poff, pairs["off"])
+        for k, name in (("ch", "channel"), ("dist", "dist"), ("iv", "interval")):
+            np.testing.assert_array_equal(bufs[k][:s.n_pairs], pairs[name])
+        (a, b), (c, d) = e.get_diff(s.n_sub_new, s.n_unsub)
+        np.testing.assert_array_equal(bufs["ns"][:s.n_sub_new], a); np.testing.assert_array_equal(bufs["nc"][:s.n_sub_new], b)
+        np.testing.assert_array_equal(bufs["us"][:s.n_unsub], c); np.testing.assert_array_equal(bufs["uc"][:s.n_unsub], d)
+        np.testing.assert_array_equal(due[:s.n_due], e.get_due(s.n_due))
+        h = e.get_handover(s.n_handover)
+        for k, arr_ in zip(("he", "hs", "hd"), h):
+            np.testing.assert_array_equal(bufs[k][:s.n_handover], arr_)
+        np.testing.assert_array_equal(bufs["st"][:len(cx)], e.get_query_status(len(cx)))
+        v0, v1 = e.get_visible()
+        np.testing.assert_array_equal(voff, v0); np.testing.assert_array_equal(vis[:s.n_visible], v1)
+        c0, c1 = e.get_cells()
+        np.testing.assert_array_equal(cs, c0); np.testing.assert_array_equal(bufs["se"][:s.n_entities_in_world], c1)
+        assert s.n_query_errors == 3 and (bufs["st"][:3] == chd.capi.Q_ERR_OUT_OF_WORLD).all()
+    # too small a capacity is an error, never a silent truncation
+    rb.pair_cap = 1
+    assert e.L.chd_fetch_results(e.h, C.byref(rb), C.byref(s)) == chd.capi.ERR_CAPACITY
