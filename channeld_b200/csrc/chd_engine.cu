@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -71,7 +72,7 @@ struct chd_engine {
     uint32_t *d_hist = nullptr;           // [BUILD_MAX_BINS * nblocks + 1]
     // one look-back scan site per call site: stages run concurrently on two streams and must not share scan state
     unsigned long long* d_epoch = nullptr;  // [EP_COUNT] stage epochs for the look-back scans
-    ScanSite site_hist_b{}, site_pchist_b{}, site_hist{}, site_win{}, site_qoff{}, site_slot{}, site_pchist{}, site_diff{}, site_diff2{}, site_voff{}, site_due{}, site_border{};
+    ScanSite site_hist_b{}, site_pchist_b{}, site_hist{}, site_win{}, site_qoff{}, site_slot{}, site_pchist{}, site_diff{}, site_diff2{}, site_voff{}, site_uoff{}, site_due{}, site_border{};
     uint32_t build_blocks = 0;
     bool assigned = false, built = false, have_prev_key = false, entities_dirty = false;
     uint32_t n_sorted = 0;
@@ -103,7 +104,8 @@ struct chd_engine {
     uint32_t *d_new_flag = nullptr, *d_gone_flag = nullptr, *d_new_off = nullptr, *d_gone_off = nullptr;
     uint32_t *d_new_sub = nullptr, *d_new_ch = nullptr, *d_gone_sub = nullptr, *d_gone_ch = nullptr;
     // emit
-    uint32_t *d_vcnt = nullptr, *d_first_pair = nullptr, *d_vis = nullptr;
+    uint32_t *d_vcnt = nullptr, *d_first_pair = nullptr, *d_vis = nullptr, *d_ucnt = nullptr, *d_uoff = nullptr;
+    int emit_variant = 4;  // 4 = cell-grouped units (L1-resident sources), 3 = output-ordered warp tiles
     uint64_t *d_voff = nullptr, *d_vis_off = nullptr;
     uint64_t max_tiles = 0;
     // fanout
@@ -384,6 +386,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
         return CHD_ERR_INVALID;
     }
     e->device = device;
+    if (const char* v = getenv("CHD_EMIT_VARIANT")) e->emit_variant = atoi(v) == 3 ? 3 : 4;
 #define CCU(call)                                                                       \
     do {                                                                                \
         cudaError_t _r = (call);                                                        \
@@ -433,7 +436,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
          make_site(e, e->site_hist, (uint64_t)BUILD_MAX_BINS * e->build_blocks + 1, EP_BUILD) &&
          make_site(e, e->site_hist_b, (uint64_t)BUILD_MAX_BINS * e->build_blocks + 1, EP_BUILD) && make_site(e, e->site_win, Q + 1, EP_QUERY) &&
          make_site(e, e->site_qoff, Q + 1, EP_QUERY) && make_site(e, e->site_slot, S + 1, EP_QUERY) &&
-         make_site(e, e->site_diff, P + 1, EP_QUERY) && make_site(e, e->site_diff2, P + 1, EP_QUERY) && make_site(e, e->site_voff, P + 1, EP_EMIT) &&
+         make_site(e, e->site_diff, P + 1, EP_QUERY) && make_site(e, e->site_diff2, P + 1, EP_QUERY) && make_site(e, e->site_voff, P + 1, EP_EMIT) && make_site(e, e->site_uoff, P + 1, EP_EMIT) &&
          make_site(e, e->site_due, P + 1, EP_FANOUT) && make_site(e, e->site_border, N + 1, EP_BORDER) &&
          dalloc(e, &e->d_ho_entity, N) && dalloc(e, &e->d_ho_src, N) && dalloc(e, &e->d_ho_dst, N) &&
          dalloc(e, &e->d_bflag, N + 1) && dalloc(e, &e->d_boff, N + 2);
@@ -454,7 +457,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
     ok = ok && dalloc(e, &e->d_new_flag, P) && dalloc(e, &e->d_gone_flag, P) && dalloc(e, &e->d_new_off, P + 1) &&
          dalloc(e, &e->d_gone_off, P + 1) && dalloc(e, &e->d_new_sub, P) && dalloc(e, &e->d_new_ch, P) && dalloc(e, &e->d_gone_sub, P) &&
          dalloc(e, &e->d_gone_ch, P);
-    ok = ok && dalloc(e, &e->d_vcnt, P) && dalloc(e, &e->d_voff, P + 1) && dalloc(e, &e->d_first_pair, e->max_tiles + 1) &&
+    ok = ok && dalloc(e, &e->d_vcnt, P) && dalloc(e, &e->d_ucnt, P) && dalloc(e, &e->d_uoff, P + 2) && dalloc(e, &e->d_voff, P + 1) && dalloc(e, &e->d_first_pair, e->max_tiles + 1) &&
          dalloc(e, &e->d_vis_off, S + 1) && dalloc(e, &e->d_vis, L.max_visible);
     ok = ok && dalloc(e, &e->d_ring_off, C + 1) && dalloc(e, &e->d_ring_arrival, (uint64_t)L.max_ring_entries) &&
          dalloc(e, &e->d_ring_sender, (uint64_t)L.max_ring_entries) && dalloc(e, &e->d_ring_index, (uint64_t)L.max_ring_entries) &&
@@ -470,7 +473,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
         return CHD_ERR_CUDA;
     }
     for (ScanSite* site : {&e->site_hist, &e->site_hist_b, &e->site_pchist, &e->site_pchist_b, &e->site_win, &e->site_qoff, &e->site_slot,
-                           &e->site_diff, &e->site_diff2, &e->site_voff, &e->site_due, &e->site_border})
+                           &e->site_diff, &e->site_diff2, &e->site_voff, &e->site_uoff, &e->site_due, &e->site_border})
         site->error = &e->d_ctr->overflow;
     CCU(cudaHostAlloc((void**)&e->h_ctr, sizeof(Counters), cudaHostAllocDefault));
     CCU(cudaHostAlloc((void**)&e->h_u32, 64, cudaHostAllocDefault));
@@ -963,24 +966,39 @@ chd_status chd_emit_visible(chd_engine* e) {
     const uint64_t P = e->lim.max_pairs;
     StageTimer timer(e, CHD_STAGE_EMIT);
     const unsigned grid = (unsigned)e->sm_count * 8;
-    const uint64_t key = mix_key(mix_key(0x656d6974ull, S), (uint64_t)e->cur);
+    const int variant = e->emit_variant;
+    const uint64_t key = mix_key(mix_key(mix_key(0x656d6974ull, S), (uint64_t)e->cur), (uint64_t)variant);
     chd_status st = run_stage(e, e->g_emit_prep[e->cur], key, [&]() -> chd_status {
         bump_epoch_kernel<<<1, 1, 0, s>>>(e->d_epoch + EP_EMIT);
         KCHECK(e);
-        pair_vcount_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, pb.cell, e->d_cell_start, e->d_vcnt);
-        KCHECK(e);
-        SCAN(e, exclusive_scan_1p<uint32_t, uint64_t>(e->d_vcnt, e->d_voff, P, e->site_voff, s, pb.off + S));
-        vis_off_kernel<<<blocks_for((uint64_t)S + 1, 256), 256, 0, s>>>(S, pb.off, P, e->d_voff, e->d_vis_off, e->lim.max_visible, e->d_ctr);
-        KCHECK(e);
-        emit_partition_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, e->d_voff, e->d_first_pair, e->max_tiles);
-        KCHECK(e);
+        if (variant == 4) {
+            pair_vcount_units_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, pb.cell, e->d_by_cell, e->d_cell_start, e->d_vcnt, e->d_ucnt);
+            KCHECK(e);
+            SCAN(e, exclusive_scan_1p<uint32_t, uint64_t>(e->d_vcnt, e->d_voff, P, e->site_voff, s, pb.off + S));
+            SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_ucnt, e->d_uoff, P, e->site_uoff, s, pb.off + S));
+            vis_off_kernel<<<blocks_for((uint64_t)S + 1, 256), 256, 0, s>>>(S, pb.off, P, e->d_voff, e->d_vis_off, e->lim.max_visible, e->d_ctr);
+            KCHECK(e);
+        } else {
+            pair_vcount_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, pb.cell, e->d_cell_start, e->d_vcnt);
+            KCHECK(e);
+            SCAN(e, exclusive_scan_1p<uint32_t, uint64_t>(e->d_vcnt, e->d_voff, P, e->site_voff, s, pb.off + S));
+            vis_off_kernel<<<blocks_for((uint64_t)S + 1, 256), 256, 0, s>>>(S, pb.off, P, e->d_voff, e->d_vis_off, e->lim.max_visible, e->d_ctr);
+            KCHECK(e);
+            emit_partition_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, e->d_voff, e->d_first_pair, e->max_tiles);
+            KCHECK(e);
+        }
         return CHD_OK;
     });
     if (st != CHD_OK) return st;
     {
         StageTimer kt(e, CHD_STAGE_EMIT_KERNEL);
-        emit_visible_kernel<<<(unsigned)e->sm_count * 4, EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4, e->phase_stride,
-                                                          e->d_first_pair, e->d_vis, e->lim.max_visible);
+        if (variant == 4)
+            emit_visible_v4_kernel<<<(unsigned)e->sm_count * 4, EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, e->d_uoff, e->d_by_cell, pb.cell,
+                                                                                      e->d_cell_start, e->d_sorted4, e->phase_stride, e->d_vis,
+                                                                                      e->lim.max_visible, (uint32_t)e->sm_count);
+        else
+            emit_visible_kernel<<<(unsigned)e->sm_count * 4, EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4,
+                                                                                   e->phase_stride, e->d_first_pair, e->d_vis, e->lim.max_visible);
         KCHECK(e);
     }
     return CHD_OK;

@@ -525,7 +525,9 @@ def test_fetch_results_matches_getters(chd):
         t = (tick + 1) * 33_000_000
         ex, ez = chd.synth.move_entities(wc, ex, ez, tick, 500.0)
         e.set_entities(ex, ez)
-        batch, keep = chd.engine.make_batch(len(cx), sub=np.arange(len(cx), dtype=np.uint32), sphere=(cx + 300.0 * tick, cz, r))
+        cq = cx.copy()
+        cq[3:] += 300.0 * tick  # the first three stay outside the world
+        batch, keep = chd.engine.make_batch(len(cx), sub=np.arange(len(cx), dtype=np.uint32), sphere=(cq, cz, r))
         ring_state, off, arr, snd, idx, cmi = chd.synth.update_rings(wc, tick, t, 33_000_000, 4, len(conn), ring_len=16, state=ring_state)
         e.set_rings(off, arr, snd, idx, cmi)
         e.tick(batch, t, chd.capi.TICK_ALL, want_summary=False)
