@@ -105,7 +105,9 @@ struct chd_engine {
     uint32_t *d_new_sub = nullptr, *d_new_ch = nullptr, *d_gone_sub = nullptr, *d_gone_ch = nullptr;
     // emit
     uint32_t *d_vcnt = nullptr, *d_first_pair = nullptr, *d_vis = nullptr, *d_ucnt = nullptr, *d_uoff = nullptr;
-    int emit_variant = 4;  // 4 = cell-grouped units (L1-resident sources), 3 = output-ordered warp tiles
+    // 3 = output-ordered warp tiles (default: 0.37 ms on config #2); 4 = cell-grouped units with L1-resident sources
+    // (experimental: fewer instructions and less L2 traffic, but latency-bound at 0.42-0.44 ms: profiles/README.md)
+    int emit_variant = 3;
     uint64_t *d_voff = nullptr, *d_vis_off = nullptr;
     uint64_t max_tiles = 0;
     // fanout
@@ -386,7 +388,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
         return CHD_ERR_INVALID;
     }
     e->device = device;
-    if (const char* v = getenv("CHD_EMIT_VARIANT")) e->emit_variant = atoi(v) == 3 ? 3 : 4;
+    if (const char* v = getenv("CHD_EMIT_VARIANT")) e->emit_variant = atoi(v) == 4 ? 4 : 3;
 #define CCU(call)                                                                       \
     do {                                                                                \
         cudaError_t _r = (call);                                                        \

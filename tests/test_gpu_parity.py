@@ -564,7 +564,7 @@ def test_fetch_results_matches_getters(chd):
         np.testing.assert_array_equal(voff, v0); np.testing.assert_array_equal(vis[:s.n_visible], v1)
         c0, c1 = e.get_cells()
         np.testing.assert_array_equal(cs, c0); np.testing.assert_array_equal(bufs["se"][:s.n_entities_in_world], c1)
-        assert s.n_query_errors == 3 and (bufs["st"][:3] == chd.capi.Q_ERR_OUT_OF_WORLD).all()
+        assert s.n_query_errors == int((bufs["st"][:len(cx)] != 0).sum()) >= 3 and (bufs["st"][:3] == chd.capi.Q_ERR_OUT_OF_WORLD).all()
     # too small a capacity is an error, never a silent truncation
     rb.pair_cap = 1
     assert e.L.chd_fetch_results(e.h, C.byref(rb), C.byref(s)) == chd.capi.ERR_CAPACITY
