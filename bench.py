@@ -192,6 +192,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
     wc = world_config(args)
     conn_all, snaps = make_snapshots(wc)
@@ -292,14 +293,19 @@ def run_ours(args):
         d = inputs[i % 2]
         rg = rings[i]
         t_ns = (i + 1) * TICK_NS
-        ck(L.chd_set_entities(e.h, capi.ptr(d["x"]), capi.ptr(d["z"]), n_own))
+        ck(L.chd_set_rings(e.h, capi.ptr(rg["off"]), rg["n"], capi.ptr(rg["arr"]), capi.ptr(rg["snd"]), capi.ptr(rg["idx"]), capi.ptr(rg["cmi"])))
         if world > 1:
+            # interest + fan-out do not need positions: start them on the engine's second stream, then exchange borders
+            ck(L.chd_begin_interest(e.h, C.byref(batches[i % 2]), t_ns, 1))
+            ck(L.chd_set_entities(e.h, capi.ptr(d["x"]), capi.ptr(d["z"]), n_own))
             rec_local.fill_(-1)
             e.export_border(rec_local, border_cap, want_count=False)
             dist.all_gather_into_tensor(rec_all, rec_local)
             e.import_halo(rec_all, border_cap * world, rank * border_cap, border_cap)
-        ck(L.chd_set_rings(e.h, capi.ptr(rg["off"]), rg["n"], capi.ptr(rg["arr"]), capi.ptr(rg["snd"]), capi.ptr(rg["idx"]), capi.ptr(rg["cmi"])))
-        ck(L.chd_tick(e.h, C.byref(batches[i % 2]), t_ns, capi.TICK_ALL, None))
+            ck(L.chd_tick(e.h, None, t_ns, capi.TICK_ALL, None))
+        else:
+            ck(L.chd_set_entities(e.h, capi.ptr(d["x"]), capi.ptr(d["z"]), n_own))
+            ck(L.chd_tick(e.h, C.byref(batches[i % 2]), t_ns, capi.TICK_ALL, None))
 
     def barrier():
         if world > 1:
@@ -405,14 +411,17 @@ def run_ours(args):
             d = host_in[i % 2]
             rg = rings_host[i]
             t_ns = (i + 1) * TICK_NS
+            ck(L.chd_set_rings(e.h, capi.ptr(rg["off"]), rg["n"], capi.ptr(rg["arr"]), capi.ptr(rg["snd"]), capi.ptr(rg["idx"]), capi.ptr(rg["cmi"])))
+            # queries + rings go up first and the interest / fan-out stages start on the second stream while the
+            # (much larger) position upload is still in flight
+            ck(L.chd_begin_interest(e.h, C.byref(batches_host[i % 2]), t_ns, 1))
             ck(L.chd_set_entities(e.h, capi.ptr(d["x"]), capi.ptr(d["z"]), n_own))
             if world > 1:
                 rec_local.fill_(-1)
                 e.export_border(rec_local, border_cap, want_count=False)
                 dist.all_gather_into_tensor(rec_all, rec_local)
                 e.import_halo(rec_all, border_cap * world, rank * border_cap, border_cap)
-            ck(L.chd_set_rings(e.h, capi.ptr(rg["off"]), rg["n"], capi.ptr(rg["arr"]), capi.ptr(rg["snd"]), capi.ptr(rg["idx"]), capi.ptr(rg["cmi"])))
-            ck(L.chd_tick(e.h, C.byref(batches_host[i % 2]), t_ns, capi.TICK_ALL, None))
+            ck(L.chd_tick(e.h, None, t_ns, capi.TICK_ALL, None))
             if expanded:
                 rb.vis_entity, rb.vis_cap = capi.ptr(r_vis_keep[0]), r_vis_keep[0].numel()
             else:

@@ -102,7 +102,7 @@ SYMBOLS = [
     "chd_abi_version", "chd_default_limits", "chd_create", "chd_destroy", "chd_last_error", "chd_set_stream", "chd_sync",
     "chd_alloc_pinned", "chd_free_pinned", "chd_cell_of", "chd_set_entities", "chd_entity_buffers", "chd_set_entity_count",
     "chd_assign_cells", "chd_build", "chd_set_subscribers", "chd_query_channel_ids", "chd_update_interest",
-    "chd_emit_visible", "chd_set_rings", "chd_fanout_tick", "chd_summary", "chd_tick", "chd_get_cells", "chd_get_pairs",
+    "chd_emit_visible", "chd_set_rings", "chd_fanout_tick", "chd_summary", "chd_tick", "chd_begin_interest", "chd_get_cells", "chd_get_pairs",
     "chd_get_query_status", "chd_get_diff", "chd_get_visible", "chd_get_visible_slot", "chd_get_due", "chd_fetch_results", "chd_get_handover", "chd_device_view",
     "chd_set_slab", "chd_set_entity_ids", "chd_export_border", "chd_import_halo", "chd_get_adjacent_channels",
     "chd_get_regions", "chd_damping_interval_ms", "chd_launch_count", "chd_profile_enable", "chd_profile_get", "chd_enable_graphs",
@@ -164,6 +164,8 @@ def lib():
     L.chd_fanout_tick.argtypes = [vp, C.c_int64]
     L.chd_summary.restype = C.c_int
     L.chd_summary.argtypes = [vp, C.POINTER(TickSummary)]
+    L.chd_begin_interest.restype = C.c_int
+    L.chd_begin_interest.argtypes = [vp, C.POINTER(QueryBatch), C.c_int64, C.c_int]
     L.chd_tick.restype = C.c_int
     L.chd_tick.argtypes = [vp, C.POINTER(QueryBatch), C.c_int64, C.c_uint32, C.POINTER(TickSummary)]
     L.chd_get_cells.restype = C.c_int

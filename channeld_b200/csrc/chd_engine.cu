@@ -45,6 +45,7 @@ struct chd_engine {
     bool overlap_fanout = true;        // chd_tick runs interest + fan-out on aux_stream concurrently with build + emit
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_interest = nullptr;
+    bool interest_pending = false, pending_fanout = false;  // chd_begin_interest issued, not yet joined by chd_tick
     GraphSlot g_build[2], g_interest[2], g_emit_prep[2], g_fanout[2];
     uint64_t graph_launches = 0, graph_captures = 0;
     uint32_t* d_key_a = nullptr;  // identity of the first key buffer (graph slot selection)
@@ -1082,11 +1083,64 @@ chd_status chd_summary(chd_engine* e, chd_tick_summary* out) {
     return CHD_OK;
 }
 
+chd_status chd_begin_interest(chd_engine* e, const chd_query_batch* q, int64_t t_ns, int with_fanout) {
+    if (!e || !q) return CHD_ERR_INVALID;
+    if (e->interest_pending) {
+        e->fail("chd_begin_interest: the previous one has not been joined by chd_tick yet");
+        return CHD_ERR_STATE;
+    }
+    CU(e, cudaSetDevice(e->device));
+    if (!e->aux_stream) {  // no second stream: run in place
+        chd_status st = chd_update_interest(e, q, t_ns);
+        if (st == CHD_OK && with_fanout) st = chd_fanout_tick(e, t_ns);
+        return st;
+    }
+    cudaStream_t main_stream = e->stream;
+    CU(e, cudaEventRecord(e->ev_fork, main_stream));
+    CU(e, cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0));
+    e->stream = e->aux_stream;
+    chd_status st = chd_update_interest(e, q, t_ns);
+    if (st == CHD_OK && cudaEventRecord(e->ev_interest, e->aux_stream) != cudaSuccess) st = CHD_ERR_CUDA;
+    if (st == CHD_OK && with_fanout) st = chd_fanout_tick(e, t_ns);
+    if (st == CHD_OK && cudaEventRecord(e->ev_join, e->aux_stream) != cudaSuccess) st = CHD_ERR_CUDA;
+    e->stream = main_stream;
+    if (st != CHD_OK) return st;
+    e->interest_pending = true;
+    e->pending_fanout = with_fanout != 0;
+    return CHD_OK;
+}
+
 chd_status chd_tick(chd_engine* e, const chd_query_batch* q, int64_t t_ns, uint32_t flags, chd_tick_summary* out) {
     if (!e) return CHD_ERR_INVALID;
     chd_status st;
     const bool need_build = (flags & CHD_TICK_BUILD) && (e->entities_dirty || !e->built);
-    const bool do_emit = flags & CHD_TICK_EMIT, do_fanout = flags & CHD_TICK_FANOUT;
+    const bool do_emit = flags & CHD_TICK_EMIT;
+    bool do_fanout = flags & CHD_TICK_FANOUT;
+    if (e->interest_pending) {
+        // interest (+ fan-out) of this tick were started early with chd_begin_interest and are running on aux_stream
+        if (q) {
+            e->fail("chd_tick: a query batch was given while chd_begin_interest is pending");
+            return CHD_ERR_STATE;
+        }
+        cudaStream_t main_stream = e->stream;
+        e->interest_pending = false;
+        if (need_build) {
+            st = chd_build(e);
+            if (st != CHD_OK) return st;
+        }
+        CU(e, cudaStreamWaitEvent(main_stream, e->ev_interest, 0));
+        if (do_emit) {
+            st = chd_emit_visible(e);
+            if (st != CHD_OK) return st;
+        }
+        CU(e, cudaStreamWaitEvent(main_stream, e->ev_join, 0));
+        if (do_fanout && !e->pending_fanout) {
+            st = chd_fanout_tick(e, t_ns);
+            if (st != CHD_OK) return st;
+        }
+        if (out) return chd_summary(e, out);
+        return CHD_OK;
+    }
     if (e->overlap_fanout && e->aux_stream && (q || do_fanout) && (need_build || do_emit)) {
         // Dependency graph of a tick:   build ----------------+--> emit
         //                               interest --> fan-out  |      (emit needs the cell CSR and the new pairs)

@@ -183,6 +183,9 @@ class Engine:
         self._ck(self.L.chd_summary(self.h, C.byref(s)))
         return s
 
+    def begin_interest(self, batch, t_ns, with_fanout=True):
+        self._ck(self.L.chd_begin_interest(self.h, C.byref(batch), int(t_ns), int(bool(with_fanout))))
+
     def tick(self, batch, t_ns, flags=capi.TICK_ALL, want_summary=True):
         s = TickSummary() if want_summary else None
         self._ck(self.L.chd_tick(self.h, C.byref(batch) if batch is not None else None, int(t_ns), int(flags),

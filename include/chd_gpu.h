@@ -205,6 +205,11 @@ chd_status chd_summary(chd_engine* e, chd_tick_summary* out);
  * update_interest(q) (if q != NULL) -> emit_visible (flags & CHD_TICK_EMIT) -> fanout_tick(t_ns)
  * (flags & CHD_TICK_FANOUT) -> summary.  One stream, no intermediate host sync. */
 enum { CHD_TICK_BUILD = 1, CHD_TICK_EMIT = 2, CHD_TICK_FANOUT = 4, CHD_TICK_ALL = 7 };
+/* Optional early start: the interest update (and the fan-out pass when with_fanout != 0) do not depend on the entity
+ * positions, so a host can start them as soon as the tick's queries and rings are known — on the engine's second
+ * stream — and then upload / exchange positions; the following chd_tick(e, NULL, t_ns, flags, ..) runs build + emit
+ * and joins.  Used by the multi-GPU driver to overlap the border exchange with the interest stage. */
+chd_status chd_begin_interest(chd_engine* e, const chd_query_batch* q, int64_t t_ns, int with_fanout);
 chd_status chd_tick(chd_engine* e, const chd_query_batch* q, int64_t t_ns, uint32_t flags, chd_tick_summary* out);
 
 /* ---- results.  Each copies to caller memory (host or device) on the engine stream and synchronises.

@@ -480,7 +480,13 @@ def test_graph_replay_matches_direct_and_oracle(chd, oracle):
             batch, keep = chd.engine.make_batch(len(cx), sub=np.arange(len(cx), dtype=np.uint32), sphere=(cx, cz, r))
             ring_state, off, arr, snd, idx, cmi = chd.synth.update_rings(wc, tick, t, 33_000_000, 4, len(conn), ring_len=16, state=ring_state)
             e.set_rings(off, arr, snd, idx, cmi)
-            s = e.tick(batch, t, chd.capi.TICK_ALL)
+            if use_graphs and tick % 2:
+                # early-start path: interest + fan-out begin on the second stream before the positions are uploaded
+                e.begin_interest(batch, t, with_fanout=True)
+                e.set_entities(ex, ez)
+                s = e.tick(None, t, chd.capi.TICK_ALL)
+            else:
+                s = e.tick(batch, t, chd.capi.TICK_ALL)
             pairs = e.get_pairs(s.n_pairs)
             voff, vis = e.get_visible()
             due = e.get_due(s.n_due)
