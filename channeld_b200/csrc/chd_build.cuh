@@ -66,19 +66,38 @@ __global__ void __launch_bounds__(BUILD_THREADS)
     for (int d = threadIdx.x; d < BINS; d += BUILD_THREADS) hist[(uint32_t)d * nblocks + blockIdx.x] = s_hist[d];
 }
 
+// Extras of the FINAL pass of the entity build, fused into the scatter:
+//   phase_stride != 0 : also write the three phase-shifted copies of the payload (chd_emit.cuh)
+//   cell_start != null: single-pass sorts only (digit == key): block 0 publishes the cell CSR offsets straight from
+//                       the scanned histogram (cell_start[c] = #keys < c), replacing a separate boundaries kernel
+struct ScatterExtras {
+    uint32_t phase_stride;
+    uint32_t* cell_start;
+    uint32_t cells;
+    uint32_t* n_in_world;
+};
+
 // stable scatter of one pass.  val_in == nullptr means "value = index" (first pass).
 template <int BINS>
 __global__ void __launch_bounds__(BUILD_THREADS)
     radix_scatter_kernel(const uint32_t* __restrict__ key_in, const uint32_t* __restrict__ val_in, uint32_t n,
                          const uint32_t* __restrict__ n_ptr, uint32_t per_block, uint32_t shift, uint32_t mask, const uint32_t* __restrict__ hist_scanned,
-                         uint32_t nblocks, uint32_t* __restrict__ key_out, uint32_t* __restrict__ val_out) {
+                         uint32_t nblocks, uint32_t* __restrict__ key_out, uint32_t* val_out, ScatterExtras ex) {
     __shared__ uint32_t s_base[BINS];
     __shared__ uint32_t s_tot[BINS];
     __shared__ uint32_t s_wcnt[BUILD_WARPS][BINS];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
     if (n_ptr) n = min(n, *n_ptr);
-    for (int d = threadIdx.x; d < BINS; d += BUILD_THREADS) s_base[d] = hist_scanned[(uint32_t)d * nblocks + blockIdx.x];
+    for (int d = threadIdx.x; d < BINS; d += BUILD_THREADS) {
+        const uint32_t b = hist_scanned[(uint32_t)d * nblocks + blockIdx.x];
+        s_base[d] = b;
+        if (ex.cell_start && blockIdx.x == 0) {  // block 0's bases are the global exclusive counts per key
+            if ((uint32_t)d <= ex.cells) ex.cell_start[d] = b;
+            if ((uint32_t)d == ex.cells) *ex.n_in_world = b;  // keys == cells mark out-of-world entities
+            if (d == 0) ex.cell_start[ex.cells + 1] = n;
+        }
+    }
     const uint32_t lo = min(n, blockIdx.x * per_block);
     const uint32_t hi = min(n, lo + per_block);
     for (uint32_t tile = lo; tile < hi; tile += BUILD_TILE) {
@@ -121,6 +140,10 @@ __global__ void __launch_bounds__(BUILD_THREADS)
                 const uint32_t dst = s_base[d] + s_wcnt[w][d] + rk[r];
                 val_out[dst] = v[r];
                 if (key_out) key_out[dst] = k[r];
+                if (ex.phase_stride) {
+#pragma unroll
+                    for (uint32_t ph = 1; ph < 4; ph++) val_out[(size_t)ph * ex.phase_stride + ph + dst] = v[r];
+                }
             }
         }
         __syncthreads();

@@ -44,9 +44,9 @@ struct chd_engine {
     bool use_graphs = true;
     bool overlap_fanout = true;        // chd_tick runs interest + fan-out on aux_stream concurrently with build + emit
     cudaStream_t aux_stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_interest = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_interest = nullptr, ev_pairs = nullptr;
     bool interest_pending = false, pending_fanout = false;  // chd_begin_interest issued, not yet joined by chd_tick
-    GraphSlot g_build[2], g_interest[2], g_emit_prep[2], g_fanout[2];
+    GraphSlot g_build[2], g_interest[2], g_interest_b[2], g_emit_prep[2], g_fanout[2];
     uint64_t graph_launches = 0, graph_captures = 0;
     uint32_t* d_key_a = nullptr;  // identity of the first key buffer (graph slot selection)
     int64_t* d_time = nullptr;      // [0] = now_ns of the last update_interest, [1] = t_ns of the last fanout_tick
@@ -309,7 +309,7 @@ void chd_destroy(chd_engine* e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (void* p : e->allocs) cudaFree(p);
-    for (auto* arr : {e->g_build, e->g_interest, e->g_emit_prep, e->g_fanout})
+    for (auto* arr : {e->g_build, e->g_interest, e->g_interest_b, e->g_emit_prep, e->g_fanout})
         for (int i = 0; i < 2; i++)
             if (arr[i].exec) cudaGraphExecDestroy(arr[i].exec);
     if (e->ev) {
@@ -323,6 +323,7 @@ void chd_destroy(chd_engine* e) {
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
     if (e->ev_interest) cudaEventDestroy(e->ev_interest);
+    if (e->ev_pairs) cudaEventDestroy(e->ev_pairs);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -406,6 +407,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
     CCU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     CCU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
     CCU(cudaEventCreateWithFlags(&e->ev_interest, cudaEventDisableTiming));
+    CCU(cudaEventCreateWithFlags(&e->ev_pairs, cudaEventDisableTiming));
     CCU(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device));
 
     GridDev& g = e->g;
@@ -625,13 +627,13 @@ extern "C++" {
 template <int BINS>
 static chd_status sort_pass(chd_engine* e, uint32_t* hist, const ScanSite& site, const uint32_t* key_in, const uint32_t* val_in, uint32_t n,
                             const uint32_t* n_ptr, uint32_t per_block, uint32_t nblocks, uint32_t shift, uint32_t bits, uint32_t* key_out,
-                            uint32_t* val_out) {
+                            uint32_t* val_out, ScatterExtras ex) {
     const uint32_t mask = (1u << bits) - 1u;
     radix_hist_kernel<BINS><<<nblocks, BUILD_THREADS, 0, e->stream>>>(key_in, n, n_ptr, per_block, shift, mask, hist, nblocks);
     KCHECK(e);
     SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(hist, hist, (uint64_t)BINS * nblocks, site, e->stream));
     radix_scatter_kernel<BINS><<<nblocks, BUILD_THREADS, 0, e->stream>>>(key_in, val_in, n, n_ptr, per_block, shift, mask, hist, nblocks,
-                                                                        key_out, val_out);
+                                                                        key_out, val_out, ex);
     KCHECK(e);
     return CHD_OK;
 }
@@ -639,9 +641,9 @@ static chd_status sort_pass(chd_engine* e, uint32_t* hist, const ScanSite& site,
 
 static chd_status sort_pass_any(chd_engine* e, uint32_t* hist, const ScanSite& site, const uint32_t* key_in, const uint32_t* val_in,
                                 uint32_t n, const uint32_t* n_ptr, uint32_t per_block, uint32_t nblocks, uint32_t shift, uint32_t bits,
-                                uint32_t* key_out, uint32_t* val_out) {
-    if (bits <= 8) return sort_pass<256>(e, hist, site, key_in, val_in, n, n_ptr, per_block, nblocks, shift, bits, key_out, val_out);
-    return sort_pass<1024>(e, hist, site, key_in, val_in, n, n_ptr, per_block, nblocks, shift, bits, key_out, val_out);
+                                uint32_t* key_out, uint32_t* val_out, ScatterExtras ex = ScatterExtras{0, nullptr, 0, nullptr}) {
+    if (bits <= 8) return sort_pass<256>(e, hist, site, key_in, val_in, n, n_ptr, per_block, nblocks, shift, bits, key_out, val_out, ex);
+    return sort_pass<1024>(e, hist, site, key_in, val_in, n, n_ptr, per_block, nblocks, shift, bits, key_out, val_out, ex);
 }
 
 static chd_status build_enqueue(chd_engine* e, bool with_assign) {
@@ -669,21 +671,21 @@ static chd_status build_enqueue(chd_engine* e, bool with_assign) {
     if (nblocks == 0) nblocks = 1;
     const uint32_t* vals = e->have_gid ? e->d_gid : nullptr;
     if (passes == 1) {
-        st = sort_pass_any(e, e->d_hist, e->site_hist, e->d_key, vals, n, n_ptr, per_block, nblocks, 0, bits0, e->d_sorted_key, e->d_sorted_ent);
+        // single pass: digit == key, so the scatter also publishes the CSR offsets and the phase copies
+        ScatterExtras ex{e->phase_stride, e->d_cell_start, C, &e->d_ctr->n_entities_in_world};
+        st = sort_pass_any(e, e->d_hist, e->site_hist, e->d_key, vals, n, n_ptr, per_block, nblocks, 0, bits0, nullptr, e->d_sorted_ent, ex);
         if (st != CHD_OK) return st;
     } else {
         st = sort_pass_any(e, e->d_hist, e->site_hist, e->d_key, vals, n, n_ptr, per_block, nblocks, 0, bits0, e->d_tmp_key, e->d_tmp_val);
         if (st != CHD_OK) return st;
-        st = sort_pass_any(e, e->d_hist, e->site_hist_b, e->d_tmp_key, e->d_tmp_val, n, n_ptr, per_block, nblocks, bits0, bits1, e->d_sorted_key, e->d_sorted_ent);
+        ScatterExtras ex{e->phase_stride, nullptr, C, nullptr};
+        st = sort_pass_any(e, e->d_hist, e->site_hist_b, e->d_tmp_key, e->d_tmp_val, n, n_ptr, per_block, nblocks, bits0, bits1, e->d_sorted_key,
+                           e->d_sorted_ent, ex);
         if (st != CHD_OK) return st;
-    }
-    if (n) {
-        replicate_phases_kernel<<<blocks_for(n, 256), 256, 0, e->stream>>>(e->d_sorted_ent, n, n_ptr, e->phase_stride, e->d_sorted4);
+        cell_bounds_kernel<<<blocks_for((uint64_t)n + 1, 256), 256, 0, e->stream>>>(e->d_sorted_key, n, n_ptr, C, e->d_cell_start,
+                                                                                      &e->d_ctr->n_entities_in_world);
         KCHECK(e);
     }
-    cell_bounds_kernel<<<blocks_for((uint64_t)n + 1, 256), 256, 0, e->stream>>>(e->d_sorted_key, n, n_ptr, C, e->d_cell_start,
-                                                                                  &e->d_ctr->n_entities_in_world);
-    KCHECK(e);
     return CHD_OK;
 }
 
@@ -873,14 +875,18 @@ chd_status chd_query_channel_ids(chd_engine* e, const chd_query_batch* q, uint32
     return CHD_OK;
 }
 
-static chd_status interest_enqueue(chd_engine* e, const QueryDev& d) {
+// part 0: query -> new subscription pairs (everything emit needs); part 1: pairs grouped by cell + diff lists
+// (needed by the fan-out pass and the host only).  An event between the two lets emit start early.
+static chd_status interest_enqueue(chd_engine* e, const QueryDev& d, int part) {
     const uint32_t n = d.n, S = e->n_slots;
     cudaStream_t s = e->stream;
-    chd_status st = run_query_kernels(e, d);
-    if (st != CHD_OK) return st;
+    chd_status st = CHD_OK;
     PairBuf& prev = e->pairs[e->cur];
     PairBuf& cur = e->pairs[e->cur ^ 1];
     const uint64_t P = e->lim.max_pairs;
+    if (part == 0) {
+    st = run_query_kernels(e, d);
+    if (st != CHD_OK) return st;
     CU(e, cudaMemsetAsync(e->d_slot_query, 0xFF, sizeof(int32_t) * (uint64_t)(S ? S : 1), s));
     CU(e, cudaMemsetAsync(&e->d_ctr->n_query_errors, 0, 4 * 4, s));  // n_query_errors, n_sub_new, n_unsub, n_kept
 
@@ -899,6 +905,8 @@ static chd_status interest_enqueue(chd_engine* e, const QueryDev& d) {
                                                                 e->d_time, e->d_new_flag, e->d_gone_flag, e->d_ctr);
         KCHECK(e);
     }
+    return CHD_OK;
+    }  // part 0
     // pairs grouped by cell for the fan-out pass (= every channel's subscriber list): a stable radix sort of pair
     // indices by cell with the same kernels as the entity build (no global atomics), device-side length
     {
@@ -949,7 +957,10 @@ chd_status chd_update_interest(chd_engine* e, const chd_query_batch* q, int64_t 
     uint64_t key = mix_key(mix_key(mix_key(0x696e74ull, d.n), e->n_slots), (uint64_t)e->cur);
     const void* present[] = {d.sub, d.kind, d.sph_cx, d.box_cx, d.cone_cx, d.spot_off, d.spot_ndist};
     for (const void* p : present) key = mix_key(key, p != nullptr);
-    st = run_stage(e, e->g_interest[e->cur], key, [&]() { return interest_enqueue(e, d); });
+    st = run_stage(e, e->g_interest[e->cur], key, [&]() { return interest_enqueue(e, d, 0); });
+    if (st != CHD_OK) return st;
+    CU(e, cudaEventRecord(e->ev_pairs, e->stream));  // the new pairs exist: emit may start (chd_tick waits on this)
+    st = run_stage(e, e->g_interest_b[e->cur], mix_key(key, 0xb), [&]() { return interest_enqueue(e, d, 1); });
     if (st != CHD_OK) return st;
     e->cur ^= 1;
     e->last_nq = d.n;
@@ -1128,7 +1139,7 @@ chd_status chd_tick(chd_engine* e, const chd_query_batch* q, int64_t t_ns, uint3
             st = chd_build(e);
             if (st != CHD_OK) return st;
         }
-        CU(e, cudaStreamWaitEvent(main_stream, e->ev_interest, 0));
+        CU(e, cudaStreamWaitEvent(main_stream, e->emit_variant == 4 ? e->ev_interest : e->ev_pairs, 0));
         if (do_emit) {
             st = chd_emit_visible(e);
             if (st != CHD_OK) return st;
@@ -1164,7 +1175,7 @@ chd_status chd_tick(chd_engine* e, const chd_query_batch* q, int64_t t_ns, uint3
             if (st != CHD_OK) return st;
         }
         if (do_emit) {
-            CU(e, cudaStreamWaitEvent(main_stream, e->ev_interest, 0));
+            CU(e, cudaStreamWaitEvent(main_stream, (e->emit_variant == 4 || !q) ? e->ev_interest : e->ev_pairs, 0));
             st = chd_emit_visible(e);
             if (st != CHD_OK) return st;
         }
