@@ -109,6 +109,7 @@ struct chd_engine {
     // 3 = output-ordered warp tiles (default: 0.37 ms on config #2); 4 = cell-grouped units with L1-resident sources
     // (experimental: fewer instructions and less L2 traffic, but latency-bound at 0.42-0.44 ms: profiles/README.md)
     int emit_variant = 3;
+    int emit_blocks_per_sm = 4;  // 4 x 256 threads x 64 registers fill an SM; 3 leaves room for the aux-stream kernels
     uint64_t *d_voff = nullptr, *d_vis_off = nullptr;
     uint64_t max_tiles = 0;
     // fanout
@@ -390,6 +391,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
         return CHD_ERR_INVALID;
     }
     e->device = device;
+    if (const char* v = getenv("CHD_EMIT_BPS")) e->emit_blocks_per_sm = atoi(v) >= 1 && atoi(v) <= 4 ? atoi(v) : 4;
     if (const char* v = getenv("CHD_EMIT_VARIANT")) e->emit_variant = atoi(v) == 4 ? 4 : 3;
 #define CCU(call)                                                                       \
     do {                                                                                \
@@ -403,7 +405,12 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
     CCU(cudaSetDevice(device));
     CCU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     e->own_stream = true;
-    CCU(cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking));
+    {
+        // the aux stream carries short latency-bound kernels that should slot in ahead of the long emit kernel
+        int lo_prio = 0, hi_prio = 0;
+        CCU(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+        CCU(cudaStreamCreateWithPriority(&e->aux_stream, cudaStreamNonBlocking, hi_prio));
+    }
     CCU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     CCU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
     CCU(cudaEventCreateWithFlags(&e->ev_interest, cudaEventDisableTiming));
@@ -1011,7 +1018,7 @@ chd_status chd_emit_visible(chd_engine* e) {
                                                                                       e->d_cell_start, e->d_sorted4, e->phase_stride, e->d_vis,
                                                                                       e->lim.max_visible, (uint32_t)e->sm_count);
         else
-            emit_visible_kernel<<<(unsigned)e->sm_count * 4, EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4,
+            emit_visible_kernel<<<(unsigned)(e->sm_count * e->emit_blocks_per_sm), EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4,
                                                                                    e->phase_stride, e->d_first_pair, e->d_vis, e->lim.max_visible);
         KCHECK(e);
     }
