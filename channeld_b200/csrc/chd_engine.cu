@@ -73,7 +73,7 @@ struct chd_engine {
     uint32_t *d_hist = nullptr;           // [BUILD_MAX_BINS * nblocks + 1]
     // one look-back scan site per call site: stages run concurrently on two streams and must not share scan state
     unsigned long long* d_epoch = nullptr;  // [EP_COUNT] stage epochs for the look-back scans
-    ScanSite site_hist_b{}, site_pchist_b{}, site_hist{}, site_win{}, site_qoff{}, site_slot{}, site_pchist{}, site_diff{}, site_diff2{}, site_voff{}, site_uoff{}, site_due{}, site_border{};
+    ScanSite site_hist_b{}, site_pchist_b{}, site_hist{}, site_win{}, site_qoff{}, site_slot{}, site_pchist{}, site_voff{}, site_uoff{}, site_due{}, site_border{};
     uint32_t build_blocks = 0;
     bool assigned = false, built = false, have_prev_key = false, entities_dirty = false;
     uint32_t n_sorted = 0;
@@ -102,14 +102,18 @@ struct chd_engine {
     uint32_t* d_slot_cnt = nullptr;
     uint32_t last_nq = 0;
     // diff
-    uint32_t *d_new_flag = nullptr, *d_gone_flag = nullptr, *d_new_off = nullptr, *d_gone_off = nullptr;
+    uint32_t *d_new_off = nullptr;  // scratch for u64 -> u32 offset narrowing (stateless query path)
     uint32_t *d_new_sub = nullptr, *d_new_ch = nullptr, *d_gone_sub = nullptr, *d_gone_ch = nullptr;
     // emit
     uint32_t *d_vcnt = nullptr, *d_first_pair = nullptr, *d_vis = nullptr, *d_ucnt = nullptr, *d_uoff = nullptr;
     // 3 = output-ordered warp tiles (default: 0.37 ms on config #2); 4 = cell-grouped units with L1-resident sources
     // (experimental: fewer instructions and less L2 traffic, but latency-bound at 0.42-0.44 ms: profiles/README.md)
     int emit_variant = 3;
-    int emit_blocks_per_sm = 4;  // 4 x 256 threads x 64 registers fill an SM; 3 leaves room for the aux-stream kernels
+    int emit_blocks_per_sm = 4;
+    // Where the aux chain (interest part 1 + fan-out) is joined: before the emit kernel (it then never competes with the
+    // saturating emit kernel for SM slots) or after it (overlap).  Measured: profiles/README.md.
+    bool join_before_emit = true;
+    cudaEvent_t wait_before_emit_kernel = nullptr;  // 4 x 256 threads x 64 registers fill an SM; 3 leaves room for the aux-stream kernels
     uint64_t *d_voff = nullptr, *d_vis_off = nullptr;
     uint64_t max_tiles = 0;
     // fanout
@@ -118,6 +122,7 @@ struct chd_engine {
     uint64_t *d_ring_index = nullptr, *d_ch_msg_index = nullptr;
     bool have_ch_msg_index = false;
     uint32_t *d_due_cnt = nullptr, *d_due_off = nullptr;
+    chd_due* d_due_slots = nullptr;  // [FANOUT_SLOTS * max_pairs] decisions kept by the evaluation pass
     uint32_t *d_by_cell = nullptr, *d_pc_hist = nullptr, *d_pc_tmp_key = nullptr, *d_pc_tmp_val = nullptr;  // pairs grouped by cell
     uint32_t pc_blocks = 0;
     chd_due* d_due = nullptr;
@@ -391,6 +396,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
         return CHD_ERR_INVALID;
     }
     e->device = device;
+    if (const char* v = getenv("CHD_JOIN_BEFORE_EMIT")) e->join_before_emit = atoi(v) != 0;
     if (const char* v = getenv("CHD_EMIT_BPS")) e->emit_blocks_per_sm = atoi(v) >= 1 && atoi(v) <= 4 ? atoi(v) : 4;
     if (const char* v = getenv("CHD_EMIT_VARIANT")) e->emit_variant = atoi(v) == 4 ? 4 : 3;
 #define CCU(call)                                                                       \
@@ -448,7 +454,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
          make_site(e, e->site_hist, (uint64_t)BUILD_MAX_BINS * e->build_blocks + 1, EP_BUILD) &&
          make_site(e, e->site_hist_b, (uint64_t)BUILD_MAX_BINS * e->build_blocks + 1, EP_BUILD) && make_site(e, e->site_win, Q + 1, EP_QUERY) &&
          make_site(e, e->site_qoff, Q + 1, EP_QUERY) && make_site(e, e->site_slot, S + 1, EP_QUERY) &&
-         make_site(e, e->site_diff, P + 1, EP_QUERY) && make_site(e, e->site_diff2, P + 1, EP_QUERY) && make_site(e, e->site_voff, P + 1, EP_EMIT) && make_site(e, e->site_uoff, P + 1, EP_EMIT) &&
+         make_site(e, e->site_voff, P + 1, EP_EMIT) && make_site(e, e->site_uoff, P + 1, EP_EMIT) &&
          make_site(e, e->site_due, P + 1, EP_FANOUT) && make_site(e, e->site_border, N + 1, EP_BORDER) &&
          dalloc(e, &e->d_ho_entity, N) && dalloc(e, &e->d_ho_src, N) && dalloc(e, &e->d_ho_dst, N) &&
          dalloc(e, &e->d_bflag, N + 1) && dalloc(e, &e->d_boff, N + 2);
@@ -466,14 +472,14 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
          dalloc(e, &e->d_side_dist, (uint64_t)L.max_spots) && dalloc(e, &e->d_side_cnt, Q) && dalloc(e, &e->d_status, Q) &&
          dalloc(e, &e->d_qcount, Q) && dalloc(e, &e->d_qoff, Q + 1) && dalloc(e, &e->d_qout_id, P) && dalloc(e, &e->d_qout_dist, P) &&
          dalloc(e, &e->d_slot_query, S) && dalloc(e, &e->d_slot_cnt, S);
-    ok = ok && dalloc(e, &e->d_new_flag, P) && dalloc(e, &e->d_gone_flag, P) && dalloc(e, &e->d_new_off, P + 1) &&
-         dalloc(e, &e->d_gone_off, P + 1) && dalloc(e, &e->d_new_sub, P) && dalloc(e, &e->d_new_ch, P) && dalloc(e, &e->d_gone_sub, P) &&
+    ok = ok && dalloc(e, &e->d_new_off, (Q > P ? Q : P) + 2) && dalloc(e, &e->d_new_sub, P) && dalloc(e, &e->d_new_ch, P) && dalloc(e, &e->d_gone_sub, P) &&
          dalloc(e, &e->d_gone_ch, P);
     ok = ok && dalloc(e, &e->d_vcnt, P) && dalloc(e, &e->d_ucnt, P) && dalloc(e, &e->d_uoff, P + 2) && dalloc(e, &e->d_voff, P + 1) && dalloc(e, &e->d_first_pair, e->max_tiles + 1) &&
          dalloc(e, &e->d_vis_off, S + 1) && dalloc(e, &e->d_vis, L.max_visible);
     ok = ok && dalloc(e, &e->d_ring_off, C + 1) && dalloc(e, &e->d_ring_arrival, (uint64_t)L.max_ring_entries) &&
          dalloc(e, &e->d_ring_sender, (uint64_t)L.max_ring_entries) && dalloc(e, &e->d_ring_index, (uint64_t)L.max_ring_entries) &&
-         dalloc(e, &e->d_ch_msg_index, C) && dalloc(e, &e->d_due_cnt, P) && dalloc(e, &e->d_by_cell, P) &&
+         dalloc(e, &e->d_ch_msg_index, C) && dalloc(e, &e->d_due_cnt, P) &&
+         dalloc(e, &e->d_due_slots, (uint64_t)FANOUT_SLOTS * P) && dalloc(e, &e->d_by_cell, P) &&
          dalloc(e, &e->d_pc_hist, (uint64_t)BUILD_MAX_BINS * e->pc_blocks + 2) && dalloc(e, &e->d_pc_tmp_key, P) && dalloc(e, &e->d_pc_tmp_val, P) &&
          make_site(e, e->site_pchist, (uint64_t)BUILD_MAX_BINS * e->pc_blocks + 1, EP_QUERY) &&
          make_site(e, e->site_pchist_b, (uint64_t)BUILD_MAX_BINS * e->pc_blocks + 1, EP_QUERY) && dalloc(e, &e->d_due_off, P + 1) &&
@@ -485,7 +491,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
         return CHD_ERR_CUDA;
     }
     for (ScanSite* site : {&e->site_hist, &e->site_hist_b, &e->site_pchist, &e->site_pchist_b, &e->site_win, &e->site_qoff, &e->site_slot,
-                           &e->site_diff, &e->site_diff2, &e->site_voff, &e->site_uoff, &e->site_due, &e->site_border})
+                           &e->site_voff, &e->site_uoff, &e->site_due, &e->site_border})
         site->error = &e->d_ctr->overflow;
     CCU(cudaHostAlloc((void**)&e->h_ctr, sizeof(Counters), cudaHostAllocDefault));
     CCU(cudaHostAlloc((void**)&e->h_u32, 64, cudaHostAllocDefault));
@@ -909,7 +915,7 @@ static chd_status interest_enqueue(chd_engine* e, const QueryDev& d, int part) {
     if (S) {
         interest_fill_kernel<<<blocks_for(S, 128), 128, 0, s>>>(e->g, S, e->d_slot_query, e->d_status, e->d_bbox, e->d_win_off, e->d_window,
                                                                 e->d_side_cell, e->d_side_dist, e->d_side_cnt, d.spot_off, prev, cur, P,
-                                                                e->d_time, e->d_new_flag, e->d_gone_flag, e->d_ctr);
+                                                                e->d_time, DiffOut{e->d_new_sub, e->d_new_ch, e->d_gone_sub, e->d_gone_ch}, e->d_ctr);
         KCHECK(e);
     }
     return CHD_OK;
@@ -940,13 +946,6 @@ static chd_status interest_enqueue(chd_engine* e, const QueryDev& d, int part) {
             if (st != CHD_OK) return st;
         }
     }
-    // diff lists: compact flagged pairs (deterministic order)
-    const unsigned grid = (unsigned)e->sm_count * 4;
-    SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_new_flag, e->d_new_off, P, e->site_diff, s, cur.off + S));
-    SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_gone_flag, e->d_gone_off, P, e->site_diff2, s, prev.off + S));
-    diff_compact_kernel<<<grid, 256, 0, s>>>(e->d_new_flag, e->d_new_off, cur.off + S, e->d_gone_flag, e->d_gone_off, prev.off + S, P, cur, prev,
-                                             e->g.id_start, e->d_new_sub, e->d_new_ch, e->d_gone_sub, e->d_gone_ch);
-    KCHECK(e);
     return CHD_OK;
 }
 
@@ -1011,6 +1010,10 @@ chd_status chd_emit_visible(chd_engine* e) {
         return CHD_OK;
     });
     if (st != CHD_OK) return st;
+    if (e->wait_before_emit_kernel) {
+        CU(e, cudaStreamWaitEvent(s, e->wait_before_emit_kernel, 0));
+        e->wait_before_emit_kernel = nullptr;
+    }
     {
         StageTimer kt(e, CHD_STAGE_EMIT_KERNEL);
         if (variant == 4)
@@ -1068,12 +1071,12 @@ chd_status chd_fanout_tick(chd_engine* e, int64_t t_ns) {
     const unsigned grid = (unsigned)e->sm_count * 16;
     const uint64_t key = mix_key(mix_key(mix_key(0x66616eull, S), (uint64_t)e->cur), e->have_ch_msg_index);
     return run_stage(e, e->g_fanout[e->cur], key, [&]() -> chd_status {
-        fanout_kernel<false><<<grid, 128, 0, s>>>(pb.off + S, P, pb, e->d_conn, ring, e->d_time + 1, e->g.id_start, e->d_due_cnt, nullptr, nullptr,
-                                                  0, e->d_by_cell, e->d_ctr);
+        fanout_eval_kernel<<<grid, 128, 0, s>>>(pb.off + S, P, pb, e->d_conn, ring, e->d_time + 1, e->g.id_start, e->d_due_cnt, e->d_due_slots,
+                                                e->d_by_cell);
         KCHECK(e);
         SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_due_cnt, e->d_due_off, P, e->site_due, s, pb.off + S));
-        fanout_kernel<true><<<grid, 128, 0, s>>>(pb.off + S, P, pb, e->d_conn, ring, e->d_time + 1, e->g.id_start, e->d_due_cnt, e->d_due_off,
-                                                 e->d_due, e->lim.max_due, e->d_by_cell, e->d_ctr);
+        fanout_gather_kernel<<<grid, 128, 0, s>>>(pb.off + S, P, pb, e->d_conn, ring, e->d_time + 1, e->g.id_start, e->d_due_cnt, e->d_due_off,
+                                                  e->d_due_slots, e->d_due, e->lim.max_due, e->d_ctr);
         KCHECK(e);
         return CHD_OK;
     });
@@ -1148,6 +1151,7 @@ chd_status chd_tick(chd_engine* e, const chd_query_batch* q, int64_t t_ns, uint3
         }
         CU(e, cudaStreamWaitEvent(main_stream, e->emit_variant == 4 ? e->ev_interest : e->ev_pairs, 0));
         if (do_emit) {
+            if (e->join_before_emit) e->wait_before_emit_kernel = e->ev_join;
             st = chd_emit_visible(e);
             if (st != CHD_OK) return st;
         }
@@ -1183,6 +1187,7 @@ chd_status chd_tick(chd_engine* e, const chd_query_batch* q, int64_t t_ns, uint3
         }
         if (do_emit) {
             CU(e, cudaStreamWaitEvent(main_stream, (e->emit_variant == 4 || !q) ? e->ev_interest : e->ev_pairs, 0));
+            if (e->join_before_emit) e->wait_before_emit_kernel = e->ev_join;
             st = chd_emit_visible(e);
             if (st != CHD_OK) return st;
         }

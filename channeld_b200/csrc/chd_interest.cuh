@@ -54,118 +54,128 @@ __global__ void __launch_bounds__(256)
     if (threadIdx.x == 0 && nerr) atomicAdd(&ctr->n_query_errors, nerr);
 }
 
-// Builds the new subscription set of each slot + diff flags.
-//   new_flag[p]  (cur index)  = 1 if pair p was subscribed by this update
-//   gone_flag[p] (prev index) = 1 if prev pair p was unsubscribed by this update
+struct DiffOut {  // the two interest-diff lists of a tick: (subscriber slot, channel id)
+    uint32_t *new_sub, *new_ch, *gone_sub, *gone_ch;
+};
+
+// Builds the new subscription set of each slot and appends the interest diff:
+//   new list  = wanted \ existing  -> handleSubToChannel   (message_spatial.go:110-128)
+//   gone list = existing \ wanted  -> handleUnsubFromChannel (message_spatial.go:88-108, util.go:105-113)
+// Two sweeps of the same sorted merge per subscriber: sweep 1 counts, a block-wide scan turns the counts into
+// offsets, ONE atomicAdd per block and list reserves the block's output range (the running totals double as the
+// n_sub_new / n_unsub counters of the summary), sweep 2 writes pairs + list entries.  The lists are therefore grouped
+// by block, ordered within a block, and unordered across blocks: they are SETS (the reference issues these messages
+// in Go map order, i.e. in no order at all).
 __global__ void __launch_bounds__(128)
     interest_fill_kernel(GridDev g, uint32_t n_slots, const int32_t* __restrict__ slot_query, const uint32_t* __restrict__ status,
                          const Bbox* __restrict__ bbox, const uint64_t* __restrict__ win_off, const uint32_t* __restrict__ window,
                          const uint32_t* __restrict__ side_cell, const uint32_t* __restrict__ side_dist,
                          const uint32_t* __restrict__ side_cnt, const uint32_t* __restrict__ spot_off, PairBuf prev, PairBuf cur,
-                         uint64_t pair_cap, const int64_t* __restrict__ now_ptr, uint32_t* __restrict__ new_flag, uint32_t* __restrict__ gone_flag,
-                         Counters* __restrict__ ctr) {
-    __shared__ uint32_t s_new, s_gone, s_kept;
-    if (threadIdx.x == 0) s_new = s_gone = s_kept = 0;
-    __syncthreads();
+                         uint64_t pair_cap, const int64_t* __restrict__ now_ptr, DiffOut diff, Counters* __restrict__ ctr) {
+    __shared__ uint32_t s_warp_new[4], s_warp_gone[4], s_base_new, s_base_gone, s_kept;
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t now_ns = *now_ptr;  // device-resident so the launch can be replayed from a CUDA graph
-    uint32_t n_new = 0, n_gone = 0, n_kept = 0;
+    if (threadIdx.x == 0) s_kept = 0;
     if (s == 0) {
         const unsigned long long p = cur.off[n_slots];
         ctr->n_pairs = p;
         ctr->required_pairs = p;
         if (p > pair_cap) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_PAIRS);
     }
-    if (s < n_slots && cur.off[n_slots] <= pair_cap) {
-        const int32_t q = slot_query[s];
-        uint32_t pp = prev.off[s];
-        const uint32_t pe = prev.off[s + 1];
-        uint32_t o = cur.off[s];
-        if (q >= 0 && status[q] == CHD_Q_OK) {
-            ResultIter it;
-            it.init(window, win_off, bbox, side_cell, side_dist, side_cnt, spot_off, (uint32_t)q, g.cols);
-            uint32_t c, d;
-            while (it.next(c, d)) {
-                while (pp < pe && prev.cell[pp] < c) {  // existing \ wanted -> unsubscribe (message_spatial.go:88-108)
-                    gone_flag[pp] = 1;
-                    n_gone++;
-                    pp++;
-                }
-                const uint32_t interval = damping_interval_ms(d, g.default_interval_ms);  // message_spatial.go:65-80
-                cur.sub[o] = s;
-                cur.cell[o] = c;
-                cur.dist[o] = d;
-                cur.interval[o] = interval;
-                if (pp < pe && prev.cell[pp] == c) {
-                    // already subscribed: options merged, fan-out state untouched (subscription.go:43-58)
-                    cur.flags[o] = prev.flags[pp] & ~PF_NEW;
-                    cur.last[o] = prev.last[pp];
-                    cur.last_index[o] = prev.last_index[pp];
-                    gone_flag[pp] = 0;
-                    new_flag[o] = 0;
-                    n_kept++;
-                    pp++;
-                } else {
-                    // new subscription (subscription.go:60-87): hadFirstFanOut = SkipFirstFanOut(false),
-                    // lastFanOutTime = now + FanOutDelayMs, SkipSelfUpdateFanOut = true
-                    cur.flags[o] = PF_NEW | PF_SKIP_SELF;
-                    cur.last[o] = now_ns + (int64_t)g.default_delay_ms * 1000000ll;
-                    cur.last_index[o] = 0;
-                    new_flag[o] = 1;
-                    n_new++;
-                }
-                o++;
-            }
-            while (pp < pe) {
-                gone_flag[pp] = 1;
-                n_gone++;
+    const bool active = s < n_slots && cur.off[n_slots] <= pair_cap;
+    int32_t q = -1;
+    uint32_t pb = 0, pe = 0;
+    bool queried = false;
+    if (active) {
+        q = slot_query[s];
+        pb = prev.off[s];
+        pe = prev.off[s + 1];
+        queried = q >= 0 && status[q] == CHD_Q_OK;
+    }
+    // ---- sweep 1: count
+    uint32_t n_new = 0, n_gone = 0, n_kept = 0;
+    if (queried) {
+        ResultIter it;
+        it.init(window, win_off, bbox, side_cell, side_dist, side_cnt, spot_off, (uint32_t)q, g.cols);
+        uint32_t pp = pb, c, d;
+        while (it.next(c, d)) {
+            while (pp < pe && prev.cell[pp] < c) { n_gone++; pp++; }
+            if (pp < pe && prev.cell[pp] == c) { n_kept++; pp++; } else n_new++;
+        }
+        n_gone += pe - pp;
+    }
+    // ---- block-wide exclusive offsets (128 threads = 4 warps)
+    uint32_t in_new = n_new, in_gone = n_gone;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, in_new, o), b2 = __shfl_up_sync(0xffffffffu, in_gone, o);
+        if (lane >= o) { in_new += a; in_gone += b2; }
+    }
+    if (lane == 31) { s_warp_new[w] = in_new; s_warp_gone[w] = in_gone; }
+    __syncthreads();
+    uint32_t off_new = in_new - n_new, off_gone = in_gone - n_gone;
+    for (int k = 0; k < w; k++) { off_new += s_warp_new[k]; off_gone += s_warp_gone[k]; }
+    if (threadIdx.x == 0) {
+        const uint32_t tn = s_warp_new[0] + s_warp_new[1] + s_warp_new[2] + s_warp_new[3];
+        const uint32_t tg = s_warp_gone[0] + s_warp_gone[1] + s_warp_gone[2] + s_warp_gone[3];
+        s_base_new = tn ? atomicAdd(&ctr->n_sub_new, tn) : 0u;
+        s_base_gone = tg ? atomicAdd(&ctr->n_unsub, tg) : 0u;
+    }
+    if (n_kept) atomicAdd(&s_kept, n_kept);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_kept) atomicAdd(&ctr->n_kept, s_kept);
+    if (!active) return;
+    uint32_t on = s_base_new + off_new, og = s_base_gone + off_gone;
+    // ---- sweep 2: write the subscriber's new pair run (+ diff entries)
+    uint32_t pp = pb;
+    uint32_t o = cur.off[s];
+    if (queried) {
+        ResultIter it;
+        it.init(window, win_off, bbox, side_cell, side_dist, side_cnt, spot_off, (uint32_t)q, g.cols);
+        uint32_t c, d;
+        while (it.next(c, d)) {
+            while (pp < pe && prev.cell[pp] < c) {  // existing \ wanted -> unsubscribe
+                if (og < pair_cap) { diff.gone_sub[og] = s; diff.gone_ch[og] = prev.cell[pp] + g.id_start; }
+                og++;
                 pp++;
             }
-        } else {
-            // no query this batch, or the query errored: subscriptions stay (message_spatial.go:60-63)
-            for (; pp < pe; pp++, o++) {
-                cur.sub[o] = s;
-                cur.cell[o] = prev.cell[pp];
-                cur.dist[o] = prev.dist[pp];
-                cur.interval[o] = prev.interval[pp];
+            const uint32_t interval = damping_interval_ms(d, g.default_interval_ms);  // message_spatial.go:65-80
+            cur.sub[o] = s;
+            cur.cell[o] = c;
+            cur.dist[o] = d;
+            cur.interval[o] = interval;
+            if (pp < pe && prev.cell[pp] == c) {
+                // already subscribed: options merged, fan-out state untouched (subscription.go:43-58)
                 cur.flags[o] = prev.flags[pp] & ~PF_NEW;
                 cur.last[o] = prev.last[pp];
                 cur.last_index[o] = prev.last_index[pp];
-                gone_flag[pp] = 0;
-                new_flag[o] = 0;
+                pp++;
+            } else {
+                // new subscription (subscription.go:60-87): hadFirstFanOut = SkipFirstFanOut(false),
+                // lastFanOutTime = now + FanOutDelayMs, SkipSelfUpdateFanOut = true
+                cur.flags[o] = PF_NEW | PF_SKIP_SELF;
+                cur.last[o] = now_ns + (int64_t)g.default_delay_ms * 1000000ll;
+                cur.last_index[o] = 0;
+                if (on < pair_cap) { diff.new_sub[on] = s; diff.new_ch[on] = c + g.id_start; }
+                on++;
             }
+            o++;
         }
-    }
-    if (n_new) atomicAdd(&s_new, n_new);
-    if (n_gone) atomicAdd(&s_gone, n_gone);
-    if (n_kept) atomicAdd(&s_kept, n_kept);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (s_new) atomicAdd(&ctr->n_sub_new, s_new);
-        if (s_gone) atomicAdd(&ctr->n_unsub, s_gone);
-        if (s_kept) atomicAdd(&ctr->n_kept, s_kept);
-    }
-}
-
-// (sub, channel id) of flagged pairs, compacted in pair order: new subscriptions index the cur buffer,
-// unsubscriptions the prev buffer.
-__global__ void __launch_bounds__(256)
-    diff_compact_kernel(const uint32_t* __restrict__ new_flag, const uint32_t* __restrict__ new_off, const uint32_t* __restrict__ n_cur_ptr,
-                        const uint32_t* __restrict__ gone_flag, const uint32_t* __restrict__ gone_off, const uint32_t* __restrict__ n_prev_ptr,
-                        uint64_t cap, PairBuf cur, PairBuf prev, uint32_t id_start, uint32_t* __restrict__ new_sub,
-                        uint32_t* __restrict__ new_ch, uint32_t* __restrict__ gone_sub, uint32_t* __restrict__ gone_ch) {
-    const uint64_t nc = min((uint64_t)*n_cur_ptr, cap), np = min((uint64_t)*n_prev_ptr, cap);
-    const uint64_t n = max(nc, np);
-    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < n; p += (uint64_t)gridDim.x * blockDim.x) {
-        if (p < nc && new_flag[p]) {
-            const uint32_t o = new_off[p];
-            new_sub[o] = cur.sub[p];
-            new_ch[o] = cur.cell[p] + id_start;
+        for (; pp < pe; pp++) {
+            if (og < pair_cap) { diff.gone_sub[og] = s; diff.gone_ch[og] = prev.cell[pp] + g.id_start; }
+            og++;
         }
-        if (p < np && gone_flag[p]) {
-            const uint32_t o = gone_off[p];
-            gone_sub[o] = prev.sub[p];
-            gone_ch[o] = prev.cell[p] + id_start;
+    } else {
+        // no query this batch, or the query errored: subscriptions stay (message_spatial.go:60-63)
+        for (; pp < pe; pp++, o++) {
+            cur.sub[o] = s;
+            cur.cell[o] = prev.cell[pp];
+            cur.dist[o] = prev.dist[pp];
+            cur.interval[o] = prev.interval[pp];
+            cur.flags[o] = prev.flags[pp] & ~PF_NEW;
+            cur.last[o] = prev.last[pp];
+            cur.last_index[o] = prev.last_index[pp];
         }
     }
 }

@@ -222,7 +222,8 @@ chd_status chd_get_pairs(chd_engine* e, uint32_t* pair_off, uint32_t* channel_id
                          uint8_t* flags, int64_t* last_fanout_ns, uint64_t* last_message_index);
 /* status per query of the last chd_update_interest batch */
 chd_status chd_get_query_status(chd_engine* e, uint32_t* status, uint32_t n);
-/* interest diff of the last update: (subscriber slot, channel id) lists, (slot asc, channel asc) */
+/* interest diff of the last update: (subscriber slot, channel id) lists.  They are SETS: the order is unspecified
+ * (the reference issues these messages in Go map order); sort on the host if a canonical order is needed. */
 chd_status chd_get_diff(chd_engine* e, uint32_t* new_sub, uint32_t* new_channel, uint32_t* unsub_sub, uint32_t* unsub_channel);
 /* visible lists: vis_off[n_subscribers+1] (u64), vis_entity[n_visible] */
 chd_status chd_get_visible(chd_engine* e, uint64_t* vis_off, uint32_t* vis_entity);
