@@ -112,7 +112,7 @@ struct chd_engine {
     int emit_blocks_per_sm = 4;
     // Where the aux chain (interest part 1 + fan-out) is joined: before the emit kernel (it then never competes with the
     // saturating emit kernel for SM slots) or after it (overlap).  Measured: profiles/README.md.
-    bool join_before_emit = true;
+    bool join_before_emit = false;
     cudaEvent_t wait_before_emit_kernel = nullptr;  // 4 x 256 threads x 64 registers fill an SM; 3 leaves room for the aux-stream kernels
     uint64_t *d_voff = nullptr, *d_vis_off = nullptr;
     uint64_t max_tiles = 0;
