@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--no-gate", action="store_true")
     ap.add_argument("--updates-per-cell", type=int, default=8)
     ap.add_argument("--ring-len", type=int, default=64)
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N>1: strong = the named config sharded over N GPUs (BASELINE config #4); weak = the world, the entities and "
+                         "the subscribers grow N-fold in X (per-GPU work fixed)")
     return ap.parse_args()
 
 
@@ -56,6 +59,15 @@ def world_config(args):
     wc = synth.CONFIGS[args.config]
     if args.entities or args.subscribers:
         wc = synth.scaled(wc, args.entities or wc.n_entities, args.subscribers or wc.n_subscribers)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.scaling == "weak" and world > 1 and args.impl == "ours":
+        import copy
+
+        wc = copy.copy(wc)
+        wc.name += " x%d in X (weak scaling)" % world
+        wc.cols *= world
+        wc.n_entities *= world
+        wc.n_subscribers *= world
     return wc
 
 
@@ -489,7 +501,8 @@ def run_ours(args):
             pass
         out = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64+u32",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling if world > 1 else "strong", "vs_baseline": None,
+            "dtype": "f64+u32",
             "data": "synthetic",
             "config": {"workload": wc.name, "entities": N_total, "subscribers": S_total, "radius": wc.radius,
                        "grid": "%dx%d" % (wc.cols, wc.rows), "parallelism": "xslab%d" % world if world > 1 else "single",
