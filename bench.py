@@ -287,7 +287,8 @@ def run_ours(args):
     def make_batches(inputs, sub_t):
         out = []
         for d in inputs:
-            b, k = engine.make_batch(S, sub=sub_t, sphere=(d["cx"], d["cz"], d["r"]))
+            # every subscriber queries every tick, query i <-> slot i: the identity batch (sub = NULL)
+            b, k = engine.make_batch(S, sub=None, sphere=(d["cx"], d["cz"], d["r"]))
             keep.append(k)
             out.append(b)
         return out
@@ -439,7 +440,7 @@ def run_ours(args):
             else:
                 rb.vis_entity, rb.vis_cap = None, 0
             ck(L.chd_fetch_results(e.h, C.byref(rb), C.byref(summ)))
-            h2d = 16 * n_own + 28 * S + (wc.cells + 1) * 4 + rg["n"] * 20 + wc.cells * 8
+            h2d = 16 * n_own + 24 * S + (wc.cells + 1) * 4 + rg["n"] * 20 + wc.cells * 8
             d2h = (C.sizeof(capi.TickSummary) + (S + 1) * 4 + 12 * int(summ.n_pairs) + 8 * (int(summ.n_sub_new) + int(summ.n_unsub))
                    + 48 * int(summ.n_due) + 12 * int(summ.n_handover) + 4 * S + (S + 1) * 8 + (4 * int(summ.n_visible) if expanded else 0))
             return h2d, d2h

@@ -54,8 +54,10 @@ __global__ void __launch_bounds__(256) assign_cells_kernel(GridDev g, const doub
 template <int BINS>
 __global__ void __launch_bounds__(BUILD_THREADS)
     radix_hist_kernel(const uint32_t* __restrict__ key, uint32_t n, const uint32_t* __restrict__ n_ptr, uint32_t per_block,
-                      uint32_t shift, uint32_t mask, uint32_t* __restrict__ hist, uint32_t nblocks) {
+                      uint32_t shift, uint32_t mask, uint32_t* __restrict__ hist, uint32_t nblocks, unsigned long long* bump_epoch) {
     __shared__ uint32_t s_hist[BINS];
+    // first kernel of the build stage: opens a new epoch for the stage's look-back scans (chd_scan.cuh)
+    if (bump_epoch && blockIdx.x == 0 && threadIdx.x == 0) *bump_epoch = (*bump_epoch + 1) & ((1ull << 22) - 1);
     if (n_ptr) n = min(n, *n_ptr);  // live length on the device (multi-GPU: own + halo entities)
     for (int d = threadIdx.x; d < BINS; d += BUILD_THREADS) s_hist[d] = 0;
     __syncthreads();

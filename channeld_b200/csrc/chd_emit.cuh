@@ -38,8 +38,9 @@ __global__ void __launch_bounds__(256)
 // per pair: number of visible entities = size of the cell's list
 __global__ void __launch_bounds__(256)
     pair_vcount_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, const uint32_t* __restrict__ pair_cell,
-                       const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ vcnt) {
+                       const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ vcnt, unsigned long long* bump_epoch) {
     const uint64_t n = min((uint64_t)*n_pairs_ptr, pair_cap);
+    if (bump_epoch && blockIdx.x == 0 && threadIdx.x == 0) *bump_epoch = (*bump_epoch + 1) & ((1ull << 22) - 1);  // emit stage epoch
     for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < n; p += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t c = pair_cell[p];
         vcnt[p] = cell_start[c + 1] - cell_start[c];
@@ -63,11 +64,22 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// first_pair[t] = the pair whose output interval [voff[p], voff[p+1]) contains entry t*EMIT_TILE
+// first_pair[t] = the pair whose output interval [voff[p], voff[p+1]) contains entry t*EMIT_TILE;
+// also vis_off[s] = voff[pair_off[s]] and the V / overflow bookkeeping (one launch instead of two)
 __global__ void __launch_bounds__(256)
     emit_partition_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, const uint64_t* __restrict__ voff,
-                          uint32_t* __restrict__ first_pair, uint64_t max_tiles) {
+                          uint32_t* __restrict__ first_pair, uint64_t max_tiles, uint32_t n_slots, const uint32_t* __restrict__ pair_off,
+                          uint64_t* __restrict__ vis_off, uint64_t vis_cap, Counters* __restrict__ ctr) {
     const uint64_t n = min((uint64_t)*n_pairs_ptr, pair_cap);
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s <= n_slots; s += (uint64_t)gridDim.x * blockDim.x) {
+        vis_off[s] = voff[min((uint64_t)pair_off[s], n)];
+        if (s == n_slots) {
+            const uint64_t V = voff[n];
+            ctr->n_visible = V;
+            ctr->required_visible = V;
+            if (V > vis_cap) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_VISIBLE);
+        }
+    }
     for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < n; p += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t b = voff[p], e = voff[p + 1];
         if (e == b) continue;

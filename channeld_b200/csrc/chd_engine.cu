@@ -640,9 +640,9 @@ extern "C++" {
 template <int BINS>
 static chd_status sort_pass(chd_engine* e, uint32_t* hist, const ScanSite& site, const uint32_t* key_in, const uint32_t* val_in, uint32_t n,
                             const uint32_t* n_ptr, uint32_t per_block, uint32_t nblocks, uint32_t shift, uint32_t bits, uint32_t* key_out,
-                            uint32_t* val_out, ScatterExtras ex) {
+                            uint32_t* val_out, ScatterExtras ex, unsigned long long* bump) {
     const uint32_t mask = (1u << bits) - 1u;
-    radix_hist_kernel<BINS><<<nblocks, BUILD_THREADS, 0, e->stream>>>(key_in, n, n_ptr, per_block, shift, mask, hist, nblocks);
+    radix_hist_kernel<BINS><<<nblocks, BUILD_THREADS, 0, e->stream>>>(key_in, n, n_ptr, per_block, shift, mask, hist, nblocks, bump);
     KCHECK(e);
     SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(hist, hist, (uint64_t)BINS * nblocks, site, e->stream));
     radix_scatter_kernel<BINS><<<nblocks, BUILD_THREADS, 0, e->stream>>>(key_in, val_in, n, n_ptr, per_block, shift, mask, hist, nblocks,
@@ -654,15 +654,14 @@ static chd_status sort_pass(chd_engine* e, uint32_t* hist, const ScanSite& site,
 
 static chd_status sort_pass_any(chd_engine* e, uint32_t* hist, const ScanSite& site, const uint32_t* key_in, const uint32_t* val_in,
                                 uint32_t n, const uint32_t* n_ptr, uint32_t per_block, uint32_t nblocks, uint32_t shift, uint32_t bits,
-                                uint32_t* key_out, uint32_t* val_out, ScatterExtras ex = ScatterExtras{0, nullptr, 0, nullptr}) {
-    if (bits <= 8) return sort_pass<256>(e, hist, site, key_in, val_in, n, n_ptr, per_block, nblocks, shift, bits, key_out, val_out, ex);
-    return sort_pass<1024>(e, hist, site, key_in, val_in, n, n_ptr, per_block, nblocks, shift, bits, key_out, val_out, ex);
+                                uint32_t* key_out, uint32_t* val_out, ScatterExtras ex = ScatterExtras{0, nullptr, 0, nullptr},
+                                unsigned long long* bump = nullptr) {
+    if (bits <= 8) return sort_pass<256>(e, hist, site, key_in, val_in, n, n_ptr, per_block, nblocks, shift, bits, key_out, val_out, ex, bump);
+    return sort_pass<1024>(e, hist, site, key_in, val_in, n, n_ptr, per_block, nblocks, shift, bits, key_out, val_out, ex, bump);
 }
 
 static chd_status build_enqueue(chd_engine* e, bool with_assign) {
     chd_status st;
-    bump_epoch_kernel<<<1, 1, 0, e->stream>>>(e->d_epoch + EP_BUILD);
-    KCHECK(e);
     if (with_assign) {
         st = chd_assign_cells(e);
         if (st != CHD_OK) return st;
@@ -686,10 +685,12 @@ static chd_status build_enqueue(chd_engine* e, bool with_assign) {
     if (passes == 1) {
         // single pass: digit == key, so the scatter also publishes the CSR offsets and the phase copies
         ScatterExtras ex{e->phase_stride, e->d_cell_start, C, &e->d_ctr->n_entities_in_world};
-        st = sort_pass_any(e, e->d_hist, e->site_hist, e->d_key, vals, n, n_ptr, per_block, nblocks, 0, bits0, nullptr, e->d_sorted_ent, ex);
+        st = sort_pass_any(e, e->d_hist, e->site_hist, e->d_key, vals, n, n_ptr, per_block, nblocks, 0, bits0, nullptr, e->d_sorted_ent, ex,
+                           e->d_epoch + EP_BUILD);
         if (st != CHD_OK) return st;
     } else {
-        st = sort_pass_any(e, e->d_hist, e->site_hist, e->d_key, vals, n, n_ptr, per_block, nblocks, 0, bits0, e->d_tmp_key, e->d_tmp_val);
+        st = sort_pass_any(e, e->d_hist, e->site_hist, e->d_key, vals, n, n_ptr, per_block, nblocks, 0, bits0, e->d_tmp_key, e->d_tmp_val,
+                           ScatterExtras{0, nullptr, 0, nullptr}, e->d_epoch + EP_BUILD);
         if (st != CHD_OK) return st;
         ScatterExtras ex{e->phase_stride, nullptr, C, nullptr};
         st = sort_pass_any(e, e->d_hist, e->site_hist_b, e->d_tmp_key, e->d_tmp_val, n, n_ptr, per_block, nblocks, bits0, bits1, e->d_sorted_key,
@@ -776,8 +777,8 @@ static chd_status upload_queries(chd_engine* e, const chd_query_batch* q, QueryD
         d.field = e->dq.field;                                                                            \
     }
     if (need_sub) {
-        if (!q->sub && n) {
-            e->fail("query batch without subscriber slots");
+        if (!q->sub && n > e->n_slots) {
+            e->fail("identity query batch (sub == NULL) of %u queries > %u subscribers", n, e->n_slots);
             return CHD_ERR_INVALID;
         }
         UP(sub, uint32_t);
@@ -900,20 +901,22 @@ static chd_status interest_enqueue(chd_engine* e, const QueryDev& d, int part) {
     if (part == 0) {
     st = run_query_kernels(e, d);
     if (st != CHD_OK) return st;
-    CU(e, cudaMemsetAsync(e->d_slot_query, 0xFF, sizeof(int32_t) * (uint64_t)(S ? S : 1), s));
+    // sub == NULL is the identity batch (query i <-> subscriber slot i): no slot table needed
+    const int32_t* slot_query = d.sub ? e->d_slot_query : nullptr;
+    if (d.sub) CU(e, cudaMemsetAsync(e->d_slot_query, 0xFF, sizeof(int32_t) * (uint64_t)(S ? S : 1), s));
     CU(e, cudaMemsetAsync(&e->d_ctr->n_query_errors, 0, 4 * 4, s));  // n_query_errors, n_sub_new, n_unsub, n_kept
 
-    if (n) {
+    if (n && d.sub) {
         slot_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(d.sub, n, S, e->d_slot_query);
         KCHECK(e);
     }
     if (S) {
-        slot_count_kernel<<<blocks_for(S, 256), 256, 0, s>>>(S, e->d_slot_query, e->d_status, e->d_qcount, prev.off, e->d_slot_cnt, e->d_ctr);
+        slot_count_kernel<<<blocks_for(S, 256), 256, 0, s>>>(S, slot_query, n, e->d_status, e->d_qcount, prev.off, e->d_slot_cnt, e->d_ctr);
         KCHECK(e);
     }
     SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_slot_cnt, cur.off, S, e->site_slot, s));
     if (S) {
-        interest_fill_kernel<<<blocks_for(S, 128), 128, 0, s>>>(e->g, S, e->d_slot_query, e->d_status, e->d_bbox, e->d_win_off, e->d_window,
+        interest_fill_kernel<<<blocks_for(S, 128), 128, 0, s>>>(e->g, S, slot_query, n, e->d_status, e->d_bbox, e->d_win_off, e->d_window,
                                                                 e->d_side_cell, e->d_side_dist, e->d_side_cnt, d.spot_off, prev, cur, P,
                                                                 e->d_time, DiffOut{e->d_new_sub, e->d_new_ch, e->d_gone_sub, e->d_gone_ch}, e->d_ctr);
         KCHECK(e);
@@ -989,9 +992,9 @@ chd_status chd_emit_visible(chd_engine* e) {
     const int variant = e->emit_variant;
     const uint64_t key = mix_key(mix_key(mix_key(0x656d6974ull, S), (uint64_t)e->cur), (uint64_t)variant);
     chd_status st = run_stage(e, e->g_emit_prep[e->cur], key, [&]() -> chd_status {
-        bump_epoch_kernel<<<1, 1, 0, s>>>(e->d_epoch + EP_EMIT);
-        KCHECK(e);
         if (variant == 4) {
+            bump_epoch_kernel<<<1, 1, 0, s>>>(e->d_epoch + EP_EMIT);
+            KCHECK(e);
             pair_vcount_units_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, pb.cell, e->d_by_cell, e->d_cell_start, e->d_vcnt, e->d_ucnt);
             KCHECK(e);
             SCAN(e, exclusive_scan_1p<uint32_t, uint64_t>(e->d_vcnt, e->d_voff, P, e->site_voff, s, pb.off + S));
@@ -999,12 +1002,11 @@ chd_status chd_emit_visible(chd_engine* e) {
             vis_off_kernel<<<blocks_for((uint64_t)S + 1, 256), 256, 0, s>>>(S, pb.off, P, e->d_voff, e->d_vis_off, e->lim.max_visible, e->d_ctr);
             KCHECK(e);
         } else {
-            pair_vcount_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, pb.cell, e->d_cell_start, e->d_vcnt);
+            pair_vcount_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, pb.cell, e->d_cell_start, e->d_vcnt, e->d_epoch + EP_EMIT);
             KCHECK(e);
             SCAN(e, exclusive_scan_1p<uint32_t, uint64_t>(e->d_vcnt, e->d_voff, P, e->site_voff, s, pb.off + S));
-            vis_off_kernel<<<blocks_for((uint64_t)S + 1, 256), 256, 0, s>>>(S, pb.off, P, e->d_voff, e->d_vis_off, e->lim.max_visible, e->d_ctr);
-            KCHECK(e);
-            emit_partition_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, e->d_voff, e->d_first_pair, e->max_tiles);
+            emit_partition_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, e->d_voff, e->d_first_pair, e->max_tiles, S, pb.off, e->d_vis_off,
+                                                       e->lim.max_visible, e->d_ctr);
             KCHECK(e);
         }
         return CHD_OK;
@@ -1449,9 +1451,7 @@ chd_status chd_export_border(chd_engine* e, uint32_t* d_records, uint32_t cap_re
     if (st != CHD_OK) return st;
     cudaStream_t s = e->stream;
     const uint32_t n = e->n_own;
-    bump_epoch_kernel<<<1, 1, 0, s>>>(e->d_epoch + EP_BORDER);
-    KCHECK(e);
-    border_flag_kernel<<<blocks_for(n ? n : 1, 256), 256, 0, s>>>(e->g, e->d_key, n, e->d_bflag);
+    border_flag_kernel<<<blocks_for(n ? n : 1, 256), 256, 0, s>>>(e->g, e->d_key, n, e->d_bflag, e->d_epoch + EP_BORDER);
     KCHECK(e);
     SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_bflag, e->d_boff, n, e->site_border, s));
     border_write_kernel<<<blocks_for(n ? n : 1, 256), 256, 0, s>>>(e->d_key, e->have_gid ? e->d_gid : nullptr, n, e->d_bflag, e->d_boff,
@@ -1484,9 +1484,8 @@ chd_status chd_import_halo(chd_engine* e, const uint32_t* d_records, uint32_t n_
         e->fail("halo import of %u records > max_entities scratch %u", n_records, e->lim.max_entities);
         return CHD_ERR_CAPACITY;
     }
-    bump_epoch_kernel<<<1, 1, 0, s>>>(e->d_epoch + EP_BORDER);
-    KCHECK(e);
-    halo_flag_kernel<<<blocks_for(n_records ? n_records : 1, 256), 256, 0, s>>>(e->g, d_records, n_records, skip_first, skip_count, e->d_bflag);
+    halo_flag_kernel<<<blocks_for(n_records ? n_records : 1, 256), 256, 0, s>>>(e->g, d_records, n_records, skip_first, skip_count, e->d_bflag,
+                                                                                e->d_epoch + EP_BORDER);
     KCHECK(e);
     SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_bflag, e->d_boff, n_records, e->site_border, s));
     // no host round trip: the kept count and the build length stay on the device (overflow -> CHD_OVF_BORDER)

@@ -36,13 +36,14 @@ __global__ void __launch_bounds__(256) slot_scatter_kernel(const uint32_t* __res
 
 // new pair count per slot
 __global__ void __launch_bounds__(256)
-    slot_count_kernel(uint32_t n_slots, const int32_t* __restrict__ slot_query, const uint32_t* __restrict__ status,
+    slot_count_kernel(uint32_t n_slots, const int32_t* __restrict__ slot_query, uint32_t n_queries, const uint32_t* __restrict__ status,
                       const uint32_t* __restrict__ qcount, const uint32_t* __restrict__ prev_off, uint32_t* __restrict__ cnt,
                       Counters* __restrict__ ctr) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t err = 0;
     if (s < n_slots) {
-        const int32_t q = slot_query[s];
+        // slot_query == nullptr: identity batch (query i belongs to subscriber slot i)
+        const int32_t q = slot_query ? slot_query[s] : (s < n_queries ? (int32_t)s : -1);
         if (q >= 0 && status[q] == CHD_Q_OK)
             cnt[s] = qcount[q];
         else {
@@ -67,7 +68,7 @@ struct DiffOut {  // the two interest-diff lists of a tick: (subscriber slot, ch
 // by block, ordered within a block, and unordered across blocks: they are SETS (the reference issues these messages
 // in Go map order, i.e. in no order at all).
 __global__ void __launch_bounds__(128)
-    interest_fill_kernel(GridDev g, uint32_t n_slots, const int32_t* __restrict__ slot_query, const uint32_t* __restrict__ status,
+    interest_fill_kernel(GridDev g, uint32_t n_slots, const int32_t* __restrict__ slot_query, uint32_t n_queries, const uint32_t* __restrict__ status,
                          const Bbox* __restrict__ bbox, const uint64_t* __restrict__ win_off, const uint32_t* __restrict__ window,
                          const uint32_t* __restrict__ side_cell, const uint32_t* __restrict__ side_dist,
                          const uint32_t* __restrict__ side_cnt, const uint32_t* __restrict__ spot_off, PairBuf prev, PairBuf cur,
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(128)
     uint32_t pb = 0, pe = 0;
     bool queried = false;
     if (active) {
-        q = slot_query[s];
+        q = slot_query ? slot_query[s] : (s < n_queries ? (int32_t)s : -1);
         pb = prev.off[s];
         pe = prev.off[s + 1];
         queried = q >= 0 && status[q] == CHD_Q_OK;

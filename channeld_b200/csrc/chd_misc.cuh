@@ -21,8 +21,10 @@ __global__ void add_const_kernel(const uint32_t* __restrict__ in, uint32_t n, ui
 
 // ---- X-slab sharding.  A record is (global entity id, cell index).
 // An own entity is exported when another rank may need it: its column is not strictly interior to this slab.
-__global__ void border_flag_kernel(GridDev g, const uint32_t* __restrict__ key, uint32_t n, uint32_t* __restrict__ flag) {
+__global__ void border_flag_kernel(GridDev g, const uint32_t* __restrict__ key, uint32_t n, uint32_t* __restrict__ flag,
+                                   unsigned long long* bump_epoch) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *bump_epoch = (*bump_epoch + 1) & ((1ull << 22) - 1);  // border stage epoch
     if (i >= n) return;
     const uint32_t k = key[i];
     uint32_t f = 0;
@@ -54,8 +56,9 @@ __global__ void border_write_kernel(const uint32_t* __restrict__ key, const uint
 
 // keep gathered records whose column lies in this rank's extended range and which another rank exported
 __global__ void halo_flag_kernel(GridDev g, const uint32_t* __restrict__ rec, uint32_t n, uint32_t skip_first, uint32_t skip_count,
-                                 uint32_t* __restrict__ flag) {
+                                 uint32_t* __restrict__ flag, unsigned long long* bump_epoch) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *bump_epoch = (*bump_epoch + 1) & ((1ull << 22) - 1);  // border stage epoch
     if (i >= n) return;
     const uint32_t cell = rec[2 * i + 1];
     uint32_t f = 0;

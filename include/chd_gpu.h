@@ -117,7 +117,8 @@ enum { CHD_AOI_SPOTS = 1, CHD_AOI_BOX = 2, CHD_AOI_SPHERE = 4, CHD_AOI_CONE = 8 
  * in arrival order and only the last one's subscriptions survive). */
 typedef struct chd_query_batch {
     uint32_t        n;
-    const uint32_t* sub;   /* [n] subscriber slot (UpdateSpatialInterestMessage.connId -> slot); ignored by chd_query_channel_ids */
+    const uint32_t* sub;   /* [n] subscriber slot (UpdateSpatialInterestMessage.connId -> slot), or NULL = identity (query i is
+                              subscriber slot i, n <= subscribers); ignored by chd_query_channel_ids */
     const uint8_t*  kind;  /* [n] CHD_AOI_* mask, or NULL = all CHD_AOI_SPHERE */
     const double *sph_cx, *sph_cz, *sph_r;
     const double *box_cx, *box_cz, *box_ex, *box_ez;
