@@ -73,7 +73,7 @@ struct chd_engine {
     uint32_t *d_hist = nullptr;           // [BUILD_MAX_BINS * nblocks + 1]
     // one look-back scan site per call site: stages run concurrently on two streams and must not share scan state
     unsigned long long* d_epoch = nullptr;  // [EP_COUNT] stage epochs for the look-back scans
-    ScanSite site_hist_b{}, site_pchist_b{}, site_hist{}, site_win{}, site_qoff{}, site_slot{}, site_pchist{}, site_voff{}, site_uoff{}, site_due{}, site_border{};
+    ScanSite site_hist_b{}, site_pchist_b{}, site_hist{}, site_win{}, site_qoff{}, site_slot{}, site_pchist{}, site_voff{}, site_uoff{}, site_border{};
     uint32_t build_blocks = 0;
     bool assigned = false, built = false, have_prev_key = false, entities_dirty = false;
     uint32_t n_sorted = 0;
@@ -121,8 +121,7 @@ struct chd_engine {
     int64_t* d_ring_arrival = nullptr;
     uint64_t *d_ring_index = nullptr, *d_ch_msg_index = nullptr;
     bool have_ch_msg_index = false;
-    uint32_t *d_due_cnt = nullptr, *d_due_off = nullptr;
-    chd_due* d_due_slots = nullptr;  // [FANOUT_SLOTS * max_pairs] decisions kept by the evaluation pass
+
     uint32_t *d_by_cell = nullptr, *d_pc_hist = nullptr, *d_pc_tmp_key = nullptr, *d_pc_tmp_val = nullptr;  // pairs grouped by cell
     uint32_t pc_blocks = 0;
     chd_due* d_due = nullptr;
@@ -207,9 +206,10 @@ static inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsign
 
 __global__ void set_i64_kernel(int64_t* dst, int64_t v) { *dst = v; }
 // first kernel of the interest / fan-out stages: publishes the tick time and opens a new scan epoch
-__global__ void stage_begin_kernel(int64_t* dst, int64_t v, unsigned long long* epoch) {
+__global__ void stage_begin_kernel(int64_t* dst, int64_t v, unsigned long long* epoch, uint32_t* zero_me) {
     *dst = v;
     *epoch = (*epoch + 1) & ((1ull << 22) - 1);
+    if (zero_me) *zero_me = 0;  // fan-out: the due-list cursor (n_due)
 }
 __global__ void set_u32_kernel(uint32_t* dst, uint32_t v) { *dst = v; }
 
@@ -455,7 +455,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
          make_site(e, e->site_hist_b, (uint64_t)BUILD_MAX_BINS * e->build_blocks + 1, EP_BUILD) && make_site(e, e->site_win, Q + 1, EP_QUERY) &&
          make_site(e, e->site_qoff, Q + 1, EP_QUERY) && make_site(e, e->site_slot, S + 1, EP_QUERY) &&
          make_site(e, e->site_voff, P + 1, EP_EMIT) && make_site(e, e->site_uoff, P + 1, EP_EMIT) &&
-         make_site(e, e->site_due, P + 1, EP_FANOUT) && make_site(e, e->site_border, N + 1, EP_BORDER) &&
+         make_site(e, e->site_border, N + 1, EP_BORDER) &&
          dalloc(e, &e->d_ho_entity, N) && dalloc(e, &e->d_ho_src, N) && dalloc(e, &e->d_ho_dst, N) &&
          dalloc(e, &e->d_bflag, N + 1) && dalloc(e, &e->d_boff, N + 2);
     e->d_sorted_ent = e->d_sorted4;  // phase copy 0 IS the plain sorted entity array
@@ -478,11 +478,10 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
          dalloc(e, &e->d_vis_off, S + 1) && dalloc(e, &e->d_vis, L.max_visible);
     ok = ok && dalloc(e, &e->d_ring_off, C + 1) && dalloc(e, &e->d_ring_arrival, (uint64_t)L.max_ring_entries) &&
          dalloc(e, &e->d_ring_sender, (uint64_t)L.max_ring_entries) && dalloc(e, &e->d_ring_index, (uint64_t)L.max_ring_entries) &&
-         dalloc(e, &e->d_ch_msg_index, C) && dalloc(e, &e->d_due_cnt, P) &&
-         dalloc(e, &e->d_due_slots, (uint64_t)FANOUT_SLOTS * P) && dalloc(e, &e->d_by_cell, P) &&
+         dalloc(e, &e->d_ch_msg_index, C) && dalloc(e, &e->d_by_cell, P) &&
          dalloc(e, &e->d_pc_hist, (uint64_t)BUILD_MAX_BINS * e->pc_blocks + 2) && dalloc(e, &e->d_pc_tmp_key, P) && dalloc(e, &e->d_pc_tmp_val, P) &&
          make_site(e, e->site_pchist, (uint64_t)BUILD_MAX_BINS * e->pc_blocks + 1, EP_QUERY) &&
-         make_site(e, e->site_pchist_b, (uint64_t)BUILD_MAX_BINS * e->pc_blocks + 1, EP_QUERY) && dalloc(e, &e->d_due_off, P + 1) &&
+         make_site(e, e->site_pchist_b, (uint64_t)BUILD_MAX_BINS * e->pc_blocks + 1, EP_QUERY) &&
          dalloc(e, &e->d_due, (uint64_t)L.max_due) && dalloc(e, &e->d_ctr, 1) && dalloc(e, &e->d_time, 2) &&
          dalloc(e, &e->d_ring_total, 1) && dalloc(e, &e->d_n_build, 1);
     if (!ok) {
@@ -491,7 +490,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
         return CHD_ERR_CUDA;
     }
     for (ScanSite* site : {&e->site_hist, &e->site_hist_b, &e->site_pchist, &e->site_pchist_b, &e->site_win, &e->site_qoff, &e->site_slot,
-                           &e->site_voff, &e->site_uoff, &e->site_due, &e->site_border})
+                           &e->site_voff, &e->site_uoff, &e->site_border})
         site->error = &e->d_ctr->overflow;
     CCU(cudaHostAlloc((void**)&e->h_ctr, sizeof(Counters), cudaHostAllocDefault));
     CCU(cudaHostAlloc((void**)&e->h_u32, 64, cudaHostAllocDefault));
@@ -960,7 +959,7 @@ chd_status chd_update_interest(chd_engine* e, const chd_query_batch* q, int64_t 
     QueryDev d;
     chd_status st = upload_queries(e, q, &d, true);  // H2D / D2D copies into the engine's SoA: outside the graph
     if (st != CHD_OK) return st;
-    stage_begin_kernel<<<1, 1, 0, e->stream>>>(e->d_time, now_ns, e->d_epoch + EP_QUERY);
+    stage_begin_kernel<<<1, 1, 0, e->stream>>>(e->d_time, now_ns, e->d_epoch + EP_QUERY, nullptr);
     KCHECK(e);
     // the graph bakes in which staging arrays are live, the batch size and the pair-buffer parity
     uint64_t key = mix_key(mix_key(mix_key(0x696e74ull, d.n), e->n_slots), (uint64_t)e->cur);
@@ -1066,19 +1065,16 @@ chd_status chd_fanout_tick(chd_engine* e, int64_t t_ns) {
     const uint32_t S = e->n_slots;
     const uint64_t P = e->lim.max_pairs;
     StageTimer timer(e, CHD_STAGE_FANOUT);
-    stage_begin_kernel<<<1, 1, 0, s>>>(e->d_time + 1, t_ns, e->d_epoch + EP_FANOUT);
+    stage_begin_kernel<<<1, 1, 0, s>>>(e->d_time + 1, t_ns, e->d_epoch + EP_FANOUT, &e->d_ctr->n_due);
     KCHECK(e);
     RingDev ring{e->d_ring_off, e->d_ring_arrival, e->d_ring_sender, e->d_ring_index, e->have_ch_msg_index ? e->d_ch_msg_index : nullptr,
                  e->d_ring_total};
     const unsigned grid = (unsigned)e->sm_count * 16;
     const uint64_t key = mix_key(mix_key(mix_key(0x66616eull, S), (uint64_t)e->cur), e->have_ch_msg_index);
     return run_stage(e, e->g_fanout[e->cur], key, [&]() -> chd_status {
-        fanout_eval_kernel<<<grid, 128, 0, s>>>(pb.off + S, P, pb, e->d_conn, ring, e->d_time + 1, e->g.id_start, e->d_due_cnt, e->d_due_slots,
-                                                e->d_by_cell);
-        KCHECK(e);
-        SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_due_cnt, e->d_due_off, P, e->site_due, s, pb.off + S));
-        fanout_gather_kernel<<<grid, 128, 0, s>>>(pb.off + S, P, pb, e->d_conn, ring, e->d_time + 1, e->g.id_start, e->d_due_cnt, e->d_due_off,
-                                                  e->d_due_slots, e->d_due, e->lim.max_due, e->d_ctr);
+        const unsigned blocks = (unsigned)std::min<uint64_t>((P + 127) / 128, (uint64_t)e->sm_count * 16);
+        fanout_kernel<<<blocks ? blocks : 1, 128, 0, s>>>(pb.off + S, P, pb, e->d_conn, ring, e->d_time + 1, e->g.id_start, e->d_by_cell, e->d_due,
+                                                          e->lim.max_due, e->d_ctr);
         KCHECK(e);
         return CHD_OK;
     });
@@ -1093,12 +1089,12 @@ chd_status chd_summary(chd_engine* e, chd_tick_summary* out) {
     out->n_pairs = c.n_pairs; out->n_visible = c.n_visible; out->n_entities_in_world = c.n_entities_in_world;
     out->n_query_errors = c.n_query_errors; out->n_sub_new = c.n_sub_new; out->n_unsub = c.n_unsub; out->n_kept = c.n_kept;
     out->n_due = c.n_due; out->n_handover = c.n_handover; out->overflow = c.overflow; out->required_pairs = c.required_pairs;
-    out->required_window_cells = c.required_window_cells; out->required_visible = c.required_visible; out->required_due = c.required_due;
+    out->required_window_cells = c.required_window_cells; out->required_visible = c.required_visible; out->required_due = c.n_due;
     out->reserved = 0;
     if (c.overflow) {
         e->fail("capacity overflow mask 0x%x (pairs %llu, window cells %llu, visible %llu, due %u required)", c.overflow,
                 (unsigned long long)c.required_pairs, (unsigned long long)c.required_window_cells,
-                (unsigned long long)c.required_visible, c.required_due);
+                (unsigned long long)c.required_visible, c.n_due);
         // sticky bits are cleared so the caller can retry after raising limits
         CU(e, cudaMemsetAsync(&e->d_ctr->overflow, 0, 4, e->stream));
         return CHD_ERR_CAPACITY;

@@ -5,9 +5,7 @@
 //       otherwise   -> scan the cell's update ring in insertion order, select entries with
 //                      lastUpdateTime <= arrival <= nextFanOutTime (skipping own updates), lastUpdateTime
 //                      advancing to every picked arrival; last += interval
-// Evaluate pass (state machine once per pair, up to two decisions kept in per-pair slots, state committed) ->
-// exclusive scan of the decision counts -> gather pass (moves the kept decisions to (slot, cell, step) order;
-// pairs that are more than two intervals behind are re-evaluated there).
+// One launch: see fanout_kernel below.
 #pragma once
 #include "chd_interest.cuh"
 
@@ -79,69 +77,75 @@ __device__ __forceinline__ uint32_t fanout_eval(const RingDev& ring, uint32_t ri
     return n_out;
 }
 
-// Pass 1 (evaluate): runs the state machine ONCE per pair, keeps up to FANOUT_SLOTS decisions in slots[] and commits
-// the state.  Pairs with more decisions (far behind) are left uncommitted.
+// ONE kernel per tick.  Every thread evaluates one pair (state machine once, up to FANOUT_SLOTS decisions kept in
+// registers), a block-wide scan turns the decision counts into offsets, one atomicAdd per block reserves the block's
+// range of the due list (the running total doubles as n_due), then the decisions are written and the state committed.
+// Pairs with more decisions (several intervals behind) re-evaluate from their saved state while writing.
+// The due list is therefore grouped by block and unordered across blocks: it is a SET of send decisions (the
+// reference issues them from independent per-channel goroutines, i.e. in no global order either).
 __global__ void __launch_bounds__(128)
-    fanout_eval_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, PairBuf pb, const uint32_t* __restrict__ conn_id,
-                       RingDev ring, const int64_t* __restrict__ t_ptr, uint32_t id_start, uint32_t* __restrict__ due_cnt,
-                       chd_due* __restrict__ slots, const uint32_t* __restrict__ by_cell) {
+    fanout_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, PairBuf pb, const uint32_t* __restrict__ conn_id, RingDev ring,
+                  const int64_t* __restrict__ t_ptr, uint32_t id_start, const uint32_t* __restrict__ by_cell, chd_due* __restrict__ due,
+                  uint32_t due_cap, Counters* __restrict__ ctr) {
+    __shared__ uint32_t s_warp[4], s_base;
     const uint64_t n = min((uint64_t)*n_pairs_ptr, pair_cap);
     const int64_t t = *t_ptr;  // device-resident so the launch can be replayed from a CUDA graph
     const uint32_t ring_total = *ring.total;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        // pairs are visited grouped by cell: neighbouring lanes walk the same ring (uniform-address loads); results are
-        // stored by the canonical pair index p, so the output order (slot, channel, step) does not depend on the grouping
-        const uint64_t p = by_cell[i];
-        const uint32_t interval = pb.interval[p];
-        int64_t last = pb.last[p];
-        if (t < last + (int64_t)interval * 1000000ll) {  // not due: the common case, no further state is read
-            due_cnt[p] = 0;
-            continue;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        // pairs are visited grouped by cell: neighbouring lanes walk the same ring (uniform-address loads)
+        uint32_t n_out = 0, interval = 0, c = 0, s = 0, me = 0;
+        uint64_t p = 0, last_index0 = 0, last_index = 0;
+        int64_t last0 = 0, last = 0;
+        uint8_t flags0 = 0, flags = 0;
+        chd_due d0, d1;
+        if (i < n) {
+            p = by_cell[i];
+            interval = pb.interval[p];
+            last0 = last = pb.last[p];
+            if (t >= last + (int64_t)interval * 1000000ll) {  // due (else: the common cheap exit, no further state is read)
+                flags0 = flags = pb.flags[p];
+                last_index0 = last_index = pb.last_index[p];
+                c = pb.cell[p];
+                s = pb.sub[p];
+                me = conn_id[s];
+                n_out = fanout_eval(ring, ring_total, t, interval, c, s, me, id_start, last, flags, last_index, [&](uint32_t j, const chd_due& d) {
+                    if (j == 0) d0 = d;
+                    else if (j == 1) d1 = d;
+                });
+            }
         }
-        uint8_t flags = pb.flags[p];
-        uint64_t last_index = pb.last_index[p];
-        const uint32_t c = pb.cell[p], s = pb.sub[p];
-        chd_due* my = slots + p * FANOUT_SLOTS;
-        const uint32_t n_out = fanout_eval(ring, ring_total, t, interval, c, s, conn_id[s], id_start, last, flags, last_index,
-                                           [&](uint32_t j, const chd_due& d) { if (j < FANOUT_SLOTS) my[j] = d; });
-        if (n_out <= FANOUT_SLOTS) {  // otherwise: left uncommitted, the gather pass re-evaluates and commits
-            pb.last[p] = last;
-            pb.flags[p] = flags;
-            pb.last_index[p] = last_index;
+        // block-wide exclusive offsets of n_out (128 threads = 4 warps)
+        uint32_t incl = n_out;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += a;
         }
-        due_cnt[p] = n_out;
-    }
-}
-
-// Pass 2 (gather): copies the kept decisions to their final positions (slot, channel, step order); re-evaluates the
-// rare pairs with more than FANOUT_SLOTS decisions from their untouched state, writing directly.
-__global__ void __launch_bounds__(128)
-    fanout_gather_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, PairBuf pb, const uint32_t* __restrict__ conn_id,
-                         RingDev ring, const int64_t* __restrict__ t_ptr, uint32_t id_start, const uint32_t* __restrict__ due_cnt,
-                         const uint32_t* __restrict__ due_off, const chd_due* __restrict__ slots, chd_due* __restrict__ due, uint32_t due_cap,
-                         Counters* __restrict__ ctr) {
-    const uint64_t n = min((uint64_t)*n_pairs_ptr, pair_cap);
-    const uint32_t total = due_off[n];
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        ctr->n_due = total;
-        ctr->required_due = total;
-        if (total > due_cap) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_DUE);
-    }
-    const bool can_write = total <= due_cap;
-    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < n; p += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t cnt = due_cnt[p];
-        if (cnt == 0) continue;
-        const uint32_t o = due_off[p];
-        if (cnt <= FANOUT_SLOTS) {
-            if (can_write)
-                for (uint32_t j = 0; j < cnt; j++) due[o + j] = slots[p * FANOUT_SLOTS + j];
-        } else {
-            int64_t last = pb.last[p];
-            uint8_t flags = pb.flags[p];
-            uint64_t last_index = pb.last_index[p];
-            const uint32_t c = pb.cell[p], s = pb.sub[p];
-            fanout_eval(ring, *ring.total, *t_ptr, pb.interval[p], c, s, conn_id[s], id_start, last, flags, last_index,
-                        [&](uint32_t j, const chd_due& d) { if (can_write) due[o + j] = d; });
+        __syncthreads();  // previous iteration's readers of s_warp / s_base are done
+        if (lane == 31) s_warp[w] = incl;
+        __syncthreads();
+        uint32_t off = incl - n_out;
+        for (int k = 0; k < w; k++) off += s_warp[k];
+        if (threadIdx.x == 0) {
+            const uint32_t total = s_warp[0] + s_warp[1] + s_warp[2] + s_warp[3];
+            s_base = total ? atomicAdd(&ctr->n_due, total) : 0u;
+        }
+        __syncthreads();
+        if (n_out) {
+            const uint32_t o = s_base + off;
+            if ((uint64_t)o + n_out > due_cap) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_DUE);
+            if (n_out <= FANOUT_SLOTS) {
+                if (o < due_cap) due[o] = d0;
+                if (n_out > 1 && o + 1 < due_cap) due[o + 1] = d1;
+            } else {  // several intervals behind: re-evaluate from the saved state, writing directly
+                last = last0; flags = flags0; last_index = last_index0;
+                fanout_eval(ring, ring_total, t, interval, c, s, me, id_start, last, flags, last_index,
+                            [&](uint32_t j, const chd_due& d) { if (o + j < due_cap) due[o + j] = d; });
+            }
+        }
+        if (i < n && (n_out || last != last0)) {  // commit (steps without a decision still advance lastFanOutTime)
             pb.last[p] = last;
             pb.flags[p] = flags;
             pb.last_index[p] = last_index;

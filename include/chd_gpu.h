@@ -230,7 +230,8 @@ chd_status chd_get_diff(chd_engine* e, uint32_t* new_sub, uint32_t* new_channel,
 chd_status chd_get_visible(chd_engine* e, uint64_t* vis_off, uint32_t* vis_entity);
 /* one subscriber's visible list: copies min(count, cap) entries, *count = its full length */
 chd_status chd_get_visible_slot(chd_engine* e, uint32_t slot, uint32_t* out, uint64_t cap, uint64_t* count);
-/* fan-out decisions of the last chd_fanout_tick, ordered by (slot asc, channel asc, step asc) */
+/* fan-out decisions of the last chd_fanout_tick.  A SET: the decisions of one (subscriber, channel) pair are contiguous
+ * and in step order, the order across pairs is unspecified (the reference sends from independent channel goroutines). */
 chd_status chd_get_due(chd_engine* e, chd_due* out, uint32_t cap);
 /* handover candidates of the last build: entity, src channel id, dst channel id (0 = left/entered the world) */
 chd_status chd_get_handover(chd_engine* e, uint32_t* entity, uint32_t* src_channel, uint32_t* dst_channel, uint32_t cap);

@@ -491,6 +491,7 @@ def test_graph_replay_matches_direct_and_oracle(chd, oracle):
             pairs = e.get_pairs(s.n_pairs)
             voff, vis = e.get_visible()
             due = e.get_due(s.n_due)
+            due = due[np.lexsort((due["window_hi"], due["channel_id"], due["sub"]))]  # the due list is a set: canonical order
             ho = e.get_handover(s.n_handover)
             order = np.argsort(ho[0])
             out.append((s.as_dict(), pairs, voff, vis, due, tuple(a[order] for a in ho)))
