@@ -110,6 +110,9 @@ struct chd_engine {
     // (experimental: fewer instructions and less L2 traffic, but latency-bound at 0.42-0.44 ms: profiles/README.md)
     int emit_variant = 3;
     int emit_blocks_per_sm = 4;
+    // CTAs withheld from the emit grid so that the concurrent aux-stream kernels (fan-out, pair grouping) find free SM
+    // slots instead of queueing behind the saturating emit kernel (measured: profiles/README.md)
+    int emit_grid_reduce = 0;
     // Where the aux chain (interest part 1 + fan-out) is joined: before the emit kernel (it then never competes with the
     // saturating emit kernel for SM slots) or after it (overlap).  Measured: profiles/README.md.
     bool join_before_emit = false;
@@ -397,6 +400,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
     }
     e->device = device;
     if (const char* v = getenv("CHD_JOIN_BEFORE_EMIT")) e->join_before_emit = atoi(v) != 0;
+    if (const char* v = getenv("CHD_EMIT_GRID_REDUCE")) e->emit_grid_reduce = atoi(v) >= 0 && atoi(v) < 400 ? atoi(v) : 0;
     if (const char* v = getenv("CHD_EMIT_BPS")) e->emit_blocks_per_sm = atoi(v) >= 1 && atoi(v) <= 4 ? atoi(v) : 4;
     if (const char* v = getenv("CHD_EMIT_VARIANT")) e->emit_variant = atoi(v) == 4 ? 4 : 3;
 #define CCU(call)                                                                       \
@@ -1022,7 +1026,7 @@ chd_status chd_emit_visible(chd_engine* e) {
                                                                                       e->d_cell_start, e->d_sorted4, e->phase_stride, e->d_vis,
                                                                                       e->lim.max_visible, (uint32_t)e->sm_count);
         else
-            emit_visible_kernel<<<(unsigned)(e->sm_count * e->emit_blocks_per_sm), EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4,
+            emit_visible_kernel<<<(unsigned)std::max(1, e->sm_count * e->emit_blocks_per_sm - e->emit_grid_reduce), EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4,
                                                                                    e->phase_stride, e->d_first_pair, e->d_vis, e->lim.max_visible);
         KCHECK(e);
     }
