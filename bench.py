@@ -395,6 +395,14 @@ def run_ours(args):
                           ("emit_kernel", capi.STAGE_EMIT_KERNEL), ("fanout", capi.STAGE_FANOUT)):
             tot, n = e.profile_get(sid)
             stage[name] = tot / max(n, 1)
+        timeline = {}
+        for name, sid in (("tick", capi.STAGE_TICK), ("build", capi.STAGE_BUILD), ("interest", capi.STAGE_INTEREST), ("emit", capi.STAGE_EMIT),
+                          ("emit_kernel", capi.STAGE_EMIT_KERNEL), ("fanout", capi.STAGE_FANOUT)):
+            try:
+                a, b = e.profile_timeline(sid)
+                timeline[name] = [round(a, 4), round(b, 4)]
+            except Exception:
+                pass
         e.profile_enable(False)
 
         # ---- e2e: host inputs, H2D + tick + D2H of the host-facing results, wall clock
@@ -523,6 +531,7 @@ def run_ours(args):
                          "note": "reads hit the L2-resident cell CSR, so DRAM traffic is the 4 B/entry write stream: compare dram_write_gbs "
                                  "with write_only_peak_gbs_this_run (torch fill_ of the same size, best of 6)"},
             "stage_ms": stage,
+            "last_tick_timeline_ms": timeline,
             "per_tick": {"pairs": tot_pairs, "visible": tot_vis, "fanout_decisions": tot_due, "handover": int(sm.n_handover),
                          "fanout_msgs_per_s": tot_due / (ms_step * 1e-3)},
             "parity_gate": gate,

@@ -105,10 +105,10 @@ SYMBOLS = [
     "chd_emit_visible", "chd_set_rings", "chd_fanout_tick", "chd_summary", "chd_tick", "chd_begin_interest", "chd_get_cells", "chd_get_pairs",
     "chd_get_query_status", "chd_get_diff", "chd_get_visible", "chd_get_visible_slot", "chd_get_due", "chd_fetch_results", "chd_get_handover", "chd_device_view",
     "chd_set_slab", "chd_set_entity_ids", "chd_export_border", "chd_import_halo", "chd_get_adjacent_channels",
-    "chd_get_regions", "chd_damping_interval_ms", "chd_launch_count", "chd_profile_enable", "chd_profile_get", "chd_enable_graphs",
+    "chd_get_regions", "chd_damping_interval_ms", "chd_launch_count", "chd_profile_enable", "chd_profile_get", "chd_profile_timeline", "chd_enable_graphs",
     "chd_graph_launch_count",
 ]
-STAGE_BUILD, STAGE_INTEREST, STAGE_EMIT, STAGE_EMIT_KERNEL, STAGE_FANOUT = range(5)
+STAGE_BUILD, STAGE_INTEREST, STAGE_EMIT, STAGE_EMIT_KERNEL, STAGE_FANOUT, STAGE_TICK = range(6)
 
 _lib = None
 
@@ -210,6 +210,8 @@ def lib():
     L.chd_graph_launch_count.argtypes = [vp]
     L.chd_profile_enable.restype = C.c_int
     L.chd_profile_enable.argtypes = [vp, C.c_int]
+    L.chd_profile_timeline.restype = C.c_int
+    L.chd_profile_timeline.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.chd_profile_get.restype = C.c_int
     L.chd_profile_get.argtypes = [vp, C.c_int, C.POINTER(C.c_double), u64p]
     _lib = L

@@ -1133,8 +1133,21 @@ chd_status chd_begin_interest(chd_engine* e, const chd_query_batch* q, int64_t t
     return CHD_OK;
 }
 
+static chd_status chd_tick_impl(chd_engine* e, const chd_query_batch* q, int64_t t_ns, uint32_t flags, chd_tick_summary* out);
+
 chd_status chd_tick(chd_engine* e, const chd_query_batch* q, int64_t t_ns, uint32_t flags, chd_tick_summary* out) {
     if (!e) return CHD_ERR_INVALID;
+    chd_status st;
+    {
+        StageTimer whole(e, CHD_STAGE_TICK);  // main-stream span of the tick (without the summary read-back)
+        st = chd_tick_impl(e, q, t_ns, flags, nullptr);
+    }
+    if (st != CHD_OK) return st;
+    if (out) return chd_summary(e, out);
+    return CHD_OK;
+}
+
+static chd_status chd_tick_impl(chd_engine* e, const chd_query_batch* q, int64_t t_ns, uint32_t flags, chd_tick_summary* out) {
     chd_status st;
     const bool need_build = (flags & CHD_TICK_BUILD) && (e->entities_dirty || !e->built);
     const bool do_emit = flags & CHD_TICK_EMIT;
@@ -1521,6 +1534,21 @@ chd_status chd_profile_enable(chd_engine* e, int on) {
     CU(e, cudaStreamSynchronize(e->stream));
     for (int s = 0; s < CHD_STAGE_COUNT; s++) e->stage_n[s] = 0;
     e->profiling = on != 0;
+    return CHD_OK;
+}
+
+chd_status chd_profile_timeline(chd_engine* e, int stage, double* start_ms, double* stop_ms) {
+    if (!e || stage < 0 || stage >= CHD_STAGE_COUNT || !start_ms || !stop_ms || !e->ev) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    CU(e, cudaStreamSynchronize(e->stream));
+    if (e->aux_stream) CU(e, cudaStreamSynchronize(e->aux_stream));
+    if (!e->stage_n[CHD_STAGE_TICK] || !e->stage_n[stage]) return CHD_ERR_STATE;
+    cudaEvent_t t0 = e->evt(CHD_STAGE_TICK, e->stage_n[CHD_STAGE_TICK] - 1, 0);
+    float a = 0, b = 0;
+    CU(e, cudaEventElapsedTime(&a, t0, e->evt(stage, e->stage_n[stage] - 1, 0)));
+    CU(e, cudaEventElapsedTime(&b, t0, e->evt(stage, e->stage_n[stage] - 1, 1)));
+    *start_ms = a;
+    *stop_ms = b;
     return CHD_OK;
 }
 

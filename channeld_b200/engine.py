@@ -273,6 +273,11 @@ class Engine:
         self._ck(self.L.chd_profile_get(self.h, int(stage), C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def profile_timeline(self, stage):
+        a, b = C.c_double(), C.c_double()
+        self._ck(self.L.chd_profile_timeline(self.h, int(stage), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     # ---- multi-GPU slab
     def set_slab(self, col_lo, col_hi, halo):
         self._ck(self.L.chd_set_slab(self.h, int(col_lo), int(col_hi), int(halo)))

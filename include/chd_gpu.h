@@ -294,7 +294,7 @@ uint32_t chd_damping_interval_ms(uint32_t dist, uint32_t default_ms);
  * makes every stage record a CUDA-event pair on the engine stream (the last 1024 samples are kept);
  * chd_profile_get synchronises and returns the summed device time of a stage.  CHD_STAGE_EMIT_KERNEL brackets
  * exactly the emit_visible kernel (the dominant HBM term; bench.py's roofline uses it). */
-enum { CHD_STAGE_BUILD = 0, CHD_STAGE_INTEREST, CHD_STAGE_EMIT, CHD_STAGE_EMIT_KERNEL, CHD_STAGE_FANOUT, CHD_STAGE_COUNT };
+enum { CHD_STAGE_BUILD = 0, CHD_STAGE_INTEREST, CHD_STAGE_EMIT, CHD_STAGE_EMIT_KERNEL, CHD_STAGE_FANOUT, CHD_STAGE_TICK, CHD_STAGE_COUNT };
 uint64_t chd_launch_count(const chd_engine* e);
 /* The launch-bound stages (build, interest update, emit preparation, fan-out) are replayed as CUDA graphs once
  * their shape (entity / query / subscriber counts) has been stable for two ticks.  chd_enable_graphs(e, 0) forces
@@ -303,6 +303,8 @@ chd_status chd_enable_graphs(chd_engine* e, int on);
 uint64_t chd_graph_launch_count(const chd_engine* e);
 chd_status chd_profile_enable(chd_engine* e, int on);
 chd_status chd_profile_get(chd_engine* e, int stage, double* total_ms, uint64_t* samples);
+/* Timeline of the most recent chd_tick: start / stop of a stage in ms after the tick started (CHD_STAGE_TICK start). */
+chd_status chd_profile_timeline(chd_engine* e, int stage, double* start_ms, double* stop_ms);
 
 uint32_t chd_abi_version(void);
 
