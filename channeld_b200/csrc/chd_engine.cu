@@ -63,7 +63,8 @@ struct chd_engine {
     bool halo_on_device = false;     // multi-GPU: the build length (own + halo) lives in d_n_build
     uint32_t* d_n_build = nullptr;
     bool have_gid = false;
-    double *d_x = nullptr, *d_z = nullptr;
+    double *d_x = nullptr, *d_z = nullptr;        // engine-owned staging for host inputs
+    const double *pos_x = nullptr, *pos_z = nullptr;  // what the kernels read: the staging buffers, or the caller's device arrays
     uint32_t *d_gid = nullptr;            // [max_entities] global ids (multi-GPU) of own + halo
     uint32_t *d_key = nullptr, *d_prev_key = nullptr;  // [max_entities] cell key per entity
     uint32_t *d_tmp_key = nullptr, *d_tmp_val = nullptr, *d_sorted_key = nullptr, *d_sorted_ent = nullptr;
@@ -124,6 +125,10 @@ struct chd_engine {
     int64_t* d_ring_arrival = nullptr;
     uint64_t *d_ring_index = nullptr, *d_ch_msg_index = nullptr;
     bool have_ch_msg_index = false;
+    // what the fan-out kernel reads: the staging copies above or the caller's device arrays (zero-copy)
+    const uint32_t *ring_off_p = nullptr, *ring_sender_p = nullptr;
+    const int64_t* ring_arrival_p = nullptr;
+    const uint64_t *ring_index_p = nullptr, *ch_msg_index_p = nullptr;
 
     uint32_t *d_by_cell = nullptr, *d_pc_hist = nullptr, *d_pc_tmp_key = nullptr, *d_pc_tmp_val = nullptr;  // pairs grouped by cell
     uint32_t pc_blocks = 0;
@@ -203,6 +208,18 @@ static bool make_site(chd_engine* e, ScanSite& site, uint64_t n_max, int stage) 
     site.error = nullptr;  // set once d_ctr exists
     if (!dalloc(e, &site.desc, site.tiles)) return false;
     return cudaMemset(site.desc, 0, site.tiles * 8) == cudaSuccess;
+}
+
+// Zero-copy inputs: a pointer into this device's memory is consumed in place (no staging copy); the caller keeps it valid
+// and unmodified until the work that reads it has finished (chd_summary / chd_sync / any chd_get_*).
+static bool is_device_ptr(const chd_engine* e, const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice && a.device == e->device;
 }
 
 static inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
@@ -570,8 +587,15 @@ chd_status chd_set_entities(chd_engine* e, const double* x, const double* z, uin
     }
     CU(e, cudaSetDevice(e->device));
     if (n != e->n_own) e->have_prev_key = false;
-    CU(e, cudaMemcpyAsync(e->d_x, x, sizeof(double) * n, cudaMemcpyDefault, e->stream));
-    CU(e, cudaMemcpyAsync(e->d_z, z, sizeof(double) * n, cudaMemcpyDefault, e->stream));
+    if (n && is_device_ptr(e, x) && is_device_ptr(e, z)) {
+        e->pos_x = x;  // device-resident producer: read in place
+        e->pos_z = z;
+    } else {
+        CU(e, cudaMemcpyAsync(e->d_x, x, sizeof(double) * n, cudaMemcpyDefault, e->stream));
+        CU(e, cudaMemcpyAsync(e->d_z, z, sizeof(double) * n, cudaMemcpyDefault, e->stream));
+        e->pos_x = e->d_x;
+        e->pos_z = e->d_z;
+    }
     e->n_own = n;
     e->n_halo = 0;
     e->halo_on_device = false;
@@ -585,6 +609,8 @@ chd_status chd_entity_buffers(chd_engine* e, double** d_x, double** d_z, uint32_
     if (d_x) *d_x = e->d_x;
     if (d_z) *d_z = e->d_z;
     if (n) *n = e->n_own;
+    e->pos_x = e->d_x;
+    e->pos_z = e->d_z;
     e->assigned = false;  // the caller may write positions
     e->entities_dirty = true;
     return CHD_OK;
@@ -630,7 +656,8 @@ chd_status chd_assign_cells(chd_engine* e) {
     HandoverOut ho{e->d_ho_entity, e->d_ho_src, e->d_ho_dst, &e->d_ctr->n_handover, e->ho_cap};
     CU(e, cudaMemsetAsync(&e->d_ctr->n_handover, 0, 4, e->stream));
     if (e->n_own) {
-        assign_cells_kernel<<<blocks_for(e->n_own, 256), 256, 0, e->stream>>>(e->g, e->d_x, e->d_z, e->n_own, e->d_key, prev, ho);
+        assign_cells_kernel<<<blocks_for(e->n_own, 256), 256, 0, e->stream>>>(e->g, e->pos_x ? e->pos_x : e->d_x, e->pos_z ? e->pos_z : e->d_z,
+                                                                              e->n_own, e->d_key, prev, ho);
         KCHECK(e);
         e->have_prev_key = true;
     }
@@ -717,7 +744,7 @@ chd_status chd_build(chd_engine* e) {
         uint32_t* target = e->have_prev_key ? e->d_prev_key : e->d_key;  // buffer the new keys will be written to
         const int slot = target == e->d_key_a ? 0 : 1;
         uint64_t key = mix_key(mix_key(mix_key(0x6275696c64ull, e->n_own), e->have_gid), e->have_prev_key);
-        key = mix_key(key, (uint64_t)(uintptr_t)target);
+        key = mix_key(mix_key(key, (uint64_t)(uintptr_t)target), (uint64_t)(uintptr_t)e->pos_x ^ ((uint64_t)(uintptr_t)e->pos_z << 1));
         st = run_stage(e, e->g_build[slot], key, [&]() { return build_enqueue(e, true); });
         if (st == CHD_OK && !e->assigned) {  // replayed graph: mirror the host-side bookkeeping of chd_assign_cells
             if (e->have_prev_key) {
@@ -776,8 +803,12 @@ static chd_status upload_queries(chd_engine* e, const chd_query_batch* q, QueryD
     cudaStream_t st = e->stream;
 #define UP(field, T)                                                                                      \
     if (q->field) {                                                                                       \
-        CU(e, cudaMemcpyAsync(e->dq.field, q->field, sizeof(T) * n, cudaMemcpyDefault, st));              \
-        d.field = e->dq.field;                                                                            \
+        if (is_device_ptr(e, q->field)) {                                                                 \
+            d.field = q->field; /* device-resident batch: consumed in place */                            \
+        } else {                                                                                          \
+            CU(e, cudaMemcpyAsync(e->dq.field, q->field, sizeof(T) * n, cudaMemcpyDefault, st));          \
+            d.field = e->dq.field;                                                                        \
+        }                                                                                                 \
     }
     if (need_sub) {
         if (!q->sub && n > e->n_slots) {
@@ -967,8 +998,9 @@ chd_status chd_update_interest(chd_engine* e, const chd_query_batch* q, int64_t 
     KCHECK(e);
     // the graph bakes in which staging arrays are live, the batch size and the pair-buffer parity
     uint64_t key = mix_key(mix_key(mix_key(0x696e74ull, d.n), e->n_slots), (uint64_t)e->cur);
-    const void* present[] = {d.sub, d.kind, d.sph_cx, d.box_cx, d.cone_cx, d.spot_off, d.spot_ndist};
-    for (const void* p : present) key = mix_key(key, p != nullptr);
+    const void* baked[] = {d.sub, d.kind, d.sph_cx, d.sph_cz, d.sph_r, d.box_cx, d.box_cz, d.box_ex, d.box_ez, d.cone_cx, d.cone_cz,
+                           d.cone_dx, d.cone_dz, d.cone_angle, d.cone_r, d.spot_off, d.spot_ndist, d.spot_x, d.spot_z, d.spot_dist};
+    for (const void* p : baked) key = mix_key(key, (uint64_t)(uintptr_t)p);  // pointers are baked into the captured launches
     st = run_stage(e, e->g_interest[e->cur], key, [&]() { return interest_enqueue(e, d, 0); });
     if (st != CHD_OK) return st;
     CU(e, cudaEventRecord(e->ev_pairs, e->stream));  // the new pairs exist: emit may start (chd_tick waits on this)
@@ -1044,20 +1076,26 @@ chd_status chd_set_rings(chd_engine* e, const uint32_t* ring_off, uint32_t n_ent
         return CHD_ERR_CAPACITY;
     }
     if (total && (!arrival || !sender || !index)) return CHD_ERR_INVALID;
-    CU(e, cudaMemcpyAsync(e->d_ring_off, ring_off, sizeof(uint32_t) * ((uint64_t)C + 1), cudaMemcpyDefault, e->stream));
-    if (total) {
-        CU(e, cudaMemcpyAsync(e->d_ring_arrival, arrival, sizeof(int64_t) * total, cudaMemcpyDefault, e->stream));
-        CU(e, cudaMemcpyAsync(e->d_ring_sender, sender, sizeof(uint32_t) * total, cudaMemcpyDefault, e->stream));
-        CU(e, cudaMemcpyAsync(e->d_ring_index, index, sizeof(uint64_t) * total, cudaMemcpyDefault, e->stream));
+    const bool in_place = is_device_ptr(e, ring_off) && (!total || (is_device_ptr(e, arrival) && is_device_ptr(e, sender) && is_device_ptr(e, index))) &&
+                          (!ch_msg_index || is_device_ptr(e, ch_msg_index));
+    if (in_place) {  // device-resident rings: consumed in place
+        e->ring_off_p = ring_off; e->ring_arrival_p = arrival; e->ring_sender_p = sender; e->ring_index_p = index;
+        e->ch_msg_index_p = ch_msg_index;
+    } else {
+        CU(e, cudaMemcpyAsync(e->d_ring_off, ring_off, sizeof(uint32_t) * ((uint64_t)C + 1), cudaMemcpyDefault, e->stream));
+        if (total) {
+            CU(e, cudaMemcpyAsync(e->d_ring_arrival, arrival, sizeof(int64_t) * total, cudaMemcpyDefault, e->stream));
+            CU(e, cudaMemcpyAsync(e->d_ring_sender, sender, sizeof(uint32_t) * total, cudaMemcpyDefault, e->stream));
+            CU(e, cudaMemcpyAsync(e->d_ring_index, index, sizeof(uint64_t) * total, cudaMemcpyDefault, e->stream));
+        }
+        if (ch_msg_index) CU(e, cudaMemcpyAsync(e->d_ch_msg_index, ch_msg_index, sizeof(uint64_t) * C, cudaMemcpyDefault, e->stream));
+        e->ring_off_p = e->d_ring_off; e->ring_arrival_p = e->d_ring_arrival; e->ring_sender_p = e->d_ring_sender;
+        e->ring_index_p = e->d_ring_index; e->ch_msg_index_p = ch_msg_index ? e->d_ch_msg_index : nullptr;
     }
+    e->have_ch_msg_index = ch_msg_index != nullptr;
     // the fan-out kernel clamps ring_off to this: a lying caller cannot cause out-of-bounds reads
     set_u32_kernel<<<1, 1, 0, e->stream>>>(e->d_ring_total, total);
     KCHECK(e);
-    if (ch_msg_index) {
-        CU(e, cudaMemcpyAsync(e->d_ch_msg_index, ch_msg_index, sizeof(uint64_t) * C, cudaMemcpyDefault, e->stream));
-        e->have_ch_msg_index = true;
-    } else
-        e->have_ch_msg_index = false;
     return CHD_OK;
 }
 
@@ -1071,10 +1109,14 @@ chd_status chd_fanout_tick(chd_engine* e, int64_t t_ns) {
     StageTimer timer(e, CHD_STAGE_FANOUT);
     stage_begin_kernel<<<1, 1, 0, s>>>(e->d_time + 1, t_ns, e->d_epoch + EP_FANOUT, &e->d_ctr->n_due);
     KCHECK(e);
-    RingDev ring{e->d_ring_off, e->d_ring_arrival, e->d_ring_sender, e->d_ring_index, e->have_ch_msg_index ? e->d_ch_msg_index : nullptr,
-                 e->d_ring_total};
+    RingDev ring{e->ring_off_p ? e->ring_off_p : e->d_ring_off, e->ring_arrival_p ? e->ring_arrival_p : e->d_ring_arrival,
+                 e->ring_sender_p ? e->ring_sender_p : e->d_ring_sender, e->ring_index_p ? e->ring_index_p : e->d_ring_index,
+                 e->have_ch_msg_index ? e->ch_msg_index_p : nullptr, e->d_ring_total};
     const unsigned grid = (unsigned)e->sm_count * 16;
-    const uint64_t key = mix_key(mix_key(mix_key(0x66616eull, S), (uint64_t)e->cur), e->have_ch_msg_index);
+    uint64_t key = mix_key(mix_key(mix_key(0x66616eull, S), (uint64_t)e->cur), e->have_ch_msg_index);
+    for (const void* p : {(const void*)ring.off, (const void*)ring.arrival, (const void*)ring.sender, (const void*)ring.index,
+                          (const void*)ring.channel_msg_index})
+        key = mix_key(key, (uint64_t)(uintptr_t)p);  // pointers are baked into the captured launch
     return run_stage(e, e->g_fanout[e->cur], key, [&]() -> chd_status {
         const unsigned blocks = (unsigned)std::min<uint64_t>((P + 127) / 128, (uint64_t)e->sm_count * 16);
         fanout_kernel<<<blocks ? blocks : 1, 128, 0, s>>>(pb.off + S, P, pb, e->d_conn, ring, e->d_time + 1, e->g.id_start, e->d_by_cell, e->d_due,

@@ -6,7 +6,11 @@
  * these entry points (go/gpucontroller.go).  Plain pointers and sizes only; no C++/torch
  * types; integer status codes; no exceptions cross the ABI; the engine never retains caller pointers after
  * a call returns (cgo rule).  Pointer arguments may be host (pageable or pinned) or device pointers unless
- * stated otherwise: copies use cudaMemcpyDefault (UVA) on the engine's stream.
+ * stated otherwise.  HOST inputs are copied (cudaMemcpyAsync on the engine's stream; pinned memory makes that
+ * asynchronous) and may be reused once the call that consumes them has been followed by chd_summary / chd_sync /
+ * a chd_get_* call.  DEVICE inputs of the tick path (chd_set_entities, chd_set_rings, the arrays of a
+ * chd_query_batch) that live on the engine's GPU are consumed IN PLACE (zero copy): the producer keeps them valid
+ * and unmodified until the tick that reads them has finished.
  *
  * Threading: one tick driver per engine handle (thread-compatible).  chd_cell_of / chd_query_channel_ids
  * take an internal mutex and may be called from any thread (the reference calls GetChannelId /

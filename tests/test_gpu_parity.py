@@ -576,3 +576,50 @@ def test_fetch_results_matches_getters(chd):
     # too small a capacity is an error, never a silent truncation
     rb.pair_cap = 1
     assert e.L.chd_fetch_results(e.h, C.byref(rb), C.byref(s)) == chd.capi.ERR_CAPACITY
+
+
+def test_zero_copy_device_inputs_match_host_inputs(chd):
+    """Device-resident positions / queries / rings are consumed in place; results equal the host-input path."""
+    import torch
+
+    wc = chd.synth.scaled(chd.synth.CONFIGS["benchmark"], 40_000, 4_000)
+    out = {}
+    for mode in ("host", "device"):
+        e = chd.engine.Engine(wc.cfg(), wc.n_entities, wc.n_subscribers, max_visible=1 << 23)
+        ex, ez = chd.synth.entities(wc)
+        conn, _, _, _ = chd.synth.subscribers(wc, ex, ez)
+        e.set_subscribers(conn)
+        ring_state, res = None, []
+        keep = []
+        for tick in range(5):
+            t = (tick + 1) * 33_000_000
+            ex, ez = chd.synth.move_entities(wc, ex, ez, tick, 300.0)
+            _, cx, cz, r = chd.synth.subscribers(wc, ex, ez)
+            ring_state, off, arr, snd, idx, cmi = chd.synth.update_rings(wc, tick, t, 33_000_000, 4, len(conn), ring_len=16, state=ring_state)
+            if mode == "device":
+                dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64 if a.dtype.itemsize == 8 and a.dtype.kind != "f" else
+                                                                               (np.int32 if a.dtype.kind != "f" else a.dtype))).cuda()
+                tx, tz, tcx, tcz, tr = (torch.from_numpy(a).cuda() for a in (ex, ez, cx, cz, r))
+                toff, tarr, tsnd, tidx, tcmi = dev(off), dev(arr), dev(snd), dev(idx), dev(cmi)
+                keep.append((tx, tz, tcx, tcz, tr, toff, tarr, tsnd, tidx, tcmi))  # stay alive until consumed
+                torch.cuda.synchronize()
+                e._ck(e.L.chd_set_entities(e.h, tx.data_ptr(), tz.data_ptr(), len(ex)))
+                e._ck(e.L.chd_set_rings(e.h, toff.data_ptr(), int(off[-1]), tarr.data_ptr(), tsnd.data_ptr(), tidx.data_ptr(), tcmi.data_ptr()))
+                batch, k2 = chd.engine.make_batch(len(cx), sub=None, sphere=(tcx, tcz, tr))
+            else:
+                e.set_entities(ex, ez)
+                e.set_rings(off, arr, snd, idx, cmi)
+                batch, k2 = chd.engine.make_batch(len(cx), sub=None, sphere=(cx, cz, r))
+            s = e.tick(batch, t, chd.capi.TICK_ALL)
+            pairs = e.get_pairs(s.n_pairs)
+            voff, vis = e.get_visible()
+            due = e.get_due(s.n_due)
+            due = due[np.lexsort((due["window_hi"], due["channel_id"], due["sub"]))]
+            res.append((s.as_dict(), pairs, voff, vis, due))
+        out[mode] = res
+    for a, b in zip(out["host"], out["device"]):
+        assert a[0] == b[0]
+        for k in a[1]:
+            np.testing.assert_array_equal(a[1][k], b[1][k])
+        np.testing.assert_array_equal(a[2], b[2]); np.testing.assert_array_equal(a[3], b[3]); np.testing.assert_array_equal(a[4], b[4])
+    assert sum(r[0]["n_due"] for r in out["host"]) > 1000
