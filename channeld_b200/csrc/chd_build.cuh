@@ -32,14 +32,31 @@ struct HandoverOut {
 __global__ void __launch_bounds__(256) assign_cells_kernel(GridDev g, const double* __restrict__ x, const double* __restrict__ z,
                                                            uint32_t n, uint32_t* __restrict__ key,
                                                            const uint32_t* __restrict__ prev_key, HandoverOut ho) {
+    __shared__ uint32_t s_cnt, s_base;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t c = cell_index(g, x[i], z[i]);
-    if (c == CHD_INVALID_CELL) c = g.cells;
     if (prev_key) {
-        const uint32_t p = prev_key[i];
-        if (p != c) {
-            const uint32_t slot = atomicAdd(ho.count, 1u);
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+    }
+    uint32_t c = g.cells, p = g.cells, my = 0;
+    bool moved = false;
+    if (i < n) {
+        c = cell_index(g, x[i], z[i]);
+        if (c == CHD_INVALID_CELL) c = g.cells;
+        key[i] = c;
+        if (prev_key) {
+            p = prev_key[i];
+            moved = p != c;
+        }
+    }
+    if (prev_key) {
+        // block-aggregated append: one global atomic per block instead of one per crossing entity
+        if (moved) my = atomicAdd(&s_cnt, 1u);
+        __syncthreads();
+        if (threadIdx.x == 0 && s_cnt) s_base = atomicAdd(ho.count, s_cnt);
+        __syncthreads();
+        if (moved) {
+            const uint32_t slot = s_base + my;
             if (slot < ho.cap) {  // channel ids; 0 = outside the world (GetChannelId error, spatial.go:613-622)
                 ho.entity[slot] = i;
                 ho.src_cell[slot] = p >= g.cells ? 0u : p + g.id_start;
@@ -47,7 +64,6 @@ __global__ void __launch_bounds__(256) assign_cells_kernel(GridDev g, const doub
             }
         }
     }
-    key[i] = c;
 }
 
 // per-block digit histogram; hist layout [digit][block]

@@ -35,6 +35,16 @@ __global__ void __launch_bounds__(256)
     for (uint32_t k = 1; k < 4; k++) dst4[(size_t)k * stride + k + i] = v;  // copy 0 is src itself (dst4 == src)
 }
 
+// scan input functor: visible entries of pair p = size of its cell's list (computed on the fly by the offset scan)
+struct PairVcountIn {
+    const uint32_t* pair_cell;
+    const uint32_t* cell_start;
+    __device__ __forceinline__ uint64_t operator()(uint64_t p) const {
+        const uint32_t c = pair_cell[p];
+        return (uint64_t)(cell_start[c + 1] - cell_start[c]);
+    }
+};
+
 // per pair: number of visible entities = size of the cell's list
 __global__ void __launch_bounds__(256)
     pair_vcount_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, const uint32_t* __restrict__ pair_cell,
@@ -69,8 +79,10 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     emit_partition_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, const uint64_t* __restrict__ voff,
                           uint32_t* __restrict__ first_pair, uint64_t max_tiles, uint32_t n_slots, const uint32_t* __restrict__ pair_off,
-                          uint64_t* __restrict__ vis_off, uint64_t vis_cap, Counters* __restrict__ ctr) {
+                          uint64_t* __restrict__ vis_off, uint64_t vis_cap, Counters* __restrict__ ctr, unsigned long long* bump_epoch) {
     const uint64_t n = min((uint64_t)*n_pairs_ptr, pair_cap);
+    // last kernel of the emit preparation: open the NEXT execution's scan epoch (the scan of this one has completed)
+    if (bump_epoch && blockIdx.x == 0 && threadIdx.x == 0) *bump_epoch = (*bump_epoch + 1) & ((1ull << 22) - 1);
     for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s <= n_slots; s += (uint64_t)gridDim.x * blockDim.x) {
         vis_off[s] = voff[min((uint64_t)pair_off[s], n)];
         if (s == n_slots) {

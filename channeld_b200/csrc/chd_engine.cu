@@ -202,6 +202,12 @@ static bool dalloc(chd_engine* e, T** p, uint64_t count) {
 
 enum { EP_BUILD = 0, EP_QUERY, EP_EMIT, EP_FANOUT, EP_BORDER, EP_COUNT };
 
+// epochs start at 1 so that the zero-initialised descriptors (epoch 0) read as stale on first use
+static bool init_epochs(chd_engine* e) {
+    const unsigned long long ones[8] = {1, 1, 1, 1, 1, 1, 1, 1};
+    return cudaMemcpy(e->d_epoch, ones, sizeof ones, cudaMemcpyHostToDevice) == cudaSuccess;
+}
+
 static bool make_site(chd_engine* e, ScanSite& site, uint64_t n_max, int stage) {
     site.tiles = n_max == 0 ? 1 : (n_max + SCAN_TILE - 1) / SCAN_TILE;
     site.epoch = e->d_epoch + stage;
@@ -471,7 +477,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
          dalloc(e, &e->d_prev_key, N) && dalloc(e, &e->d_tmp_key, N) && dalloc(e, &e->d_tmp_val, N) &&
          dalloc(e, &e->d_sorted_key, N) && dalloc(e, &e->d_sorted4, 4 * (((N + 3) / 4) * 4 + 8)) && dalloc(e, &e->d_cell_start, C + 2) &&
          dalloc(e, &e->d_hist, (uint64_t)BUILD_MAX_BINS * e->build_blocks + 2) &&
-         dalloc(e, &e->d_epoch, 8) && cudaMemset(e->d_epoch, 0, 64) == cudaSuccess &&
+         dalloc(e, &e->d_epoch, 8) && init_epochs(e) &&
          make_site(e, e->site_hist, (uint64_t)BUILD_MAX_BINS * e->build_blocks + 1, EP_BUILD) &&
          make_site(e, e->site_hist_b, (uint64_t)BUILD_MAX_BINS * e->build_blocks + 1, EP_BUILD) && make_site(e, e->site_win, Q + 1, EP_QUERY) &&
          make_site(e, e->site_qoff, Q + 1, EP_QUERY) && make_site(e, e->site_slot, S + 1, EP_QUERY) &&
@@ -944,11 +950,7 @@ static chd_status interest_enqueue(chd_engine* e, const QueryDev& d, int part) {
         slot_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(d.sub, n, S, e->d_slot_query);
         KCHECK(e);
     }
-    if (S) {
-        slot_count_kernel<<<blocks_for(S, 256), 256, 0, s>>>(S, slot_query, n, e->d_status, e->d_qcount, prev.off, e->d_slot_cnt, e->d_ctr);
-        KCHECK(e);
-    }
-    SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_slot_cnt, cur.off, S, e->site_slot, s));
+    SCAN(e, exclusive_scan_fn<SlotCountIn, uint32_t>(SlotCountIn{slot_query, n, e->d_status, e->d_qcount, prev.off}, cur.off, S, e->site_slot, s));
     if (S) {
         interest_fill_kernel<<<blocks_for(S, 128), 128, 0, s>>>(e->g, S, slot_query, n, e->d_status, e->d_bbox, e->d_win_off, e->d_window,
                                                                 e->d_side_cell, e->d_side_dist, e->d_side_cnt, d.spot_off, prev, cur, P,
@@ -1037,11 +1039,10 @@ chd_status chd_emit_visible(chd_engine* e) {
             vis_off_kernel<<<blocks_for((uint64_t)S + 1, 256), 256, 0, s>>>(S, pb.off, P, e->d_voff, e->d_vis_off, e->lim.max_visible, e->d_ctr);
             KCHECK(e);
         } else {
-            pair_vcount_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, pb.cell, e->d_cell_start, e->d_vcnt, e->d_epoch + EP_EMIT);
-            KCHECK(e);
-            SCAN(e, exclusive_scan_1p<uint32_t, uint64_t>(e->d_vcnt, e->d_voff, P, e->site_voff, s, pb.off + S));
+            // per-pair visible counts are computed by the scan itself; the partition pass opens the next epoch
+            SCAN(e, exclusive_scan_fn<PairVcountIn, uint64_t>(PairVcountIn{pb.cell, e->d_cell_start}, e->d_voff, P, e->site_voff, s, pb.off + S));
             emit_partition_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, e->d_voff, e->d_first_pair, e->max_tiles, S, pb.off, e->d_vis_off,
-                                                       e->lim.max_visible, e->d_ctr);
+                                                       e->lim.max_visible, e->d_ctr, e->d_epoch + EP_EMIT);
             KCHECK(e);
         }
         return CHD_OK;

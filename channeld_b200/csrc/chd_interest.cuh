@@ -34,6 +34,20 @@ __global__ void __launch_bounds__(256) slot_scatter_kernel(const uint32_t* __res
     if (i < nq && sub[i] < n_slots) slot_query[sub[i]] = (int32_t)i;
 }
 
+// scan input functor: new pair count of subscriber slot s (computed on the fly by the offset scan)
+struct SlotCountIn {
+    const int32_t* slot_query;  // nullptr = identity batch
+    uint32_t n_queries;
+    const uint32_t* status;
+    const uint32_t* qcount;
+    const uint32_t* prev_off;
+    __device__ __forceinline__ uint64_t operator()(uint64_t s) const {
+        const int32_t q = slot_query ? slot_query[s] : (s < n_queries ? (int32_t)s : -1);
+        if (q >= 0 && status[q] == CHD_Q_OK) return qcount[q];
+        return prev_off[s + 1] - prev_off[s];
+    }
+};
+
 // new pair count per slot
 __global__ void __launch_bounds__(256)
     slot_count_kernel(uint32_t n_slots, const int32_t* __restrict__ slot_query, uint32_t n_queries, const uint32_t* __restrict__ status,
@@ -88,11 +102,19 @@ __global__ void __launch_bounds__(128)
     int32_t q = -1;
     uint32_t pb = 0, pe = 0;
     bool queried = false;
-    if (active) {
+    if (s < n_slots) {
         q = slot_query ? slot_query[s] : (s < n_queries ? (int32_t)s : -1);
+        queried = q >= 0 && status[q] == CHD_Q_OK;
+    }
+    {   // queries that failed (message_spatial.go:60-63): counted for the summary
+        const uint32_t nerr = __syncthreads_count(s < n_slots && q >= 0 && !queried);
+        if (threadIdx.x == 0 && nerr) atomicAdd(&ctr->n_query_errors, nerr);
+    }
+    if (active) {
         pb = prev.off[s];
         pe = prev.off[s + 1];
-        queried = q >= 0 && status[q] == CHD_Q_OK;
+    } else {
+        queried = false;
     }
     // ---- sweep 1: count
     uint32_t n_new = 0, n_gone = 0, n_kept = 0;

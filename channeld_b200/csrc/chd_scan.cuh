@@ -141,9 +141,17 @@ __device__ __forceinline__ unsigned long long scan_pack(unsigned long long epoch
     return (epoch << 42) | (flag << 40) | (v & ((1ull << 40) - 1));
 }
 
-template <typename TIn, typename TOut>
+// scan input: either a plain array or a functor computing element i on the fly (saves the kernel that would have
+// materialised the counts)
+template <typename T>
+struct ScanPtrIn {
+    const T* p;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return (uint64_t)p[i]; }
+};
+
+template <typename InFn, typename TOut>
 __global__ void __launch_bounds__(SCAN_THREADS)
-    scan_lookback_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, uint64_t n, const uint32_t* __restrict__ n_ptr, ScanSite site) {
+    scan_lookback_kernel(InFn in, TOut* __restrict__ out, uint64_t n, const uint32_t* __restrict__ n_ptr, ScanSite site) {
     __shared__ unsigned long long s_prefix;
     volatile unsigned long long* desc = site.desc;
     if (n_ptr) n = min(n, (uint64_t)*n_ptr);
@@ -156,7 +164,7 @@ __global__ void __launch_bounds__(SCAN_THREADS)
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
         const uint64_t i = base + k;
-        v[k] = i < n ? (TOut)in[i] : TOut(0);
+        v[k] = i < n ? (TOut)in(i) : TOut(0);
         acc += v[k];
     }
     TOut total;
@@ -221,7 +229,14 @@ __global__ void __launch_bounds__(SCAN_THREADS)
 template <typename TIn, typename TOut>
 inline int exclusive_scan_1p(const TIn* in, TOut* out, uint64_t n, const ScanSite& site, cudaStream_t st, const uint32_t* n_ptr = nullptr) {
     const uint64_t tiles = n == 0 ? 1 : (n + SCAN_TILE - 1) / SCAN_TILE;  // <= site.tiles by construction of the site
-    scan_lookback_kernel<TIn, TOut><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, out, n, n_ptr, site);
+    scan_lookback_kernel<ScanPtrIn<TIn>, TOut><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(ScanPtrIn<TIn>{in}, out, n, n_ptr, site);
+    return 1;
+}
+
+template <typename InFn, typename TOut>
+inline int exclusive_scan_fn(InFn in, TOut* out, uint64_t n, const ScanSite& site, cudaStream_t st, const uint32_t* n_ptr = nullptr) {
+    const uint64_t tiles = n == 0 ? 1 : (n + SCAN_TILE - 1) / SCAN_TILE;
+    scan_lookback_kernel<InFn, TOut><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, out, n, n_ptr, site);
     return 1;
 }
 
