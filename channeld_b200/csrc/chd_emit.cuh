@@ -266,4 +266,103 @@ __global__ void __launch_bounds__(EMIT_THREADS, 4)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// v5 = v4 with per-unit descriptors: the preparation pass writes one 16-byte descriptor {src, len, dst} per unit,
+// so the copy kernel has a single (prefetched, warp-uniform) metadata load per 4 KB instead of v4's 4-deep
+// dependent chain by_cell -> pair_cell -> cell_start -> voff.
+struct EmitUnit {
+    uint32_t src;  // first source entry (index into phase copy 0)
+    uint32_t len;  // entries (1..EMIT_UNIT)
+    uint64_t dst;  // first destination entry
+};
+
+// scan input functor: units of the pair at by-cell position i
+struct UnitCountIn {
+    const uint32_t* pair_cell;
+    const uint32_t* by_cell;
+    const uint32_t* cell_start;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const {
+        const uint32_t c = pair_cell[by_cell[i]];
+        return (uint64_t)((cell_start[c + 1] - cell_start[c] + EMIT_UNIT - 1) / EMIT_UNIT);
+    }
+};
+
+// descriptors + vis_off + V bookkeeping (last kernel of the v5 emit preparation: also opens the next scan epoch)
+__global__ void __launch_bounds__(256)
+    emit_units_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, const uint64_t* __restrict__ voff,
+                      const uint32_t* __restrict__ uoff, const uint32_t* __restrict__ by_cell, const uint32_t* __restrict__ pair_cell,
+                      const uint32_t* __restrict__ cell_start, EmitUnit* __restrict__ units, uint64_t unit_cap, uint32_t n_slots,
+                      const uint32_t* __restrict__ pair_off, uint64_t* __restrict__ vis_off, uint64_t vis_cap, Counters* __restrict__ ctr,
+                      unsigned long long* bump_epoch) {
+    const uint64_t n = min((uint64_t)*n_pairs_ptr, pair_cap);
+    if (bump_epoch && blockIdx.x == 0 && threadIdx.x == 0) *bump_epoch = (*bump_epoch + 1) & ((1ull << 22) - 1);
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s <= n_slots; s += (uint64_t)gridDim.x * blockDim.x) {
+        vis_off[s] = voff[min((uint64_t)pair_off[s], n)];
+        if (s == n_slots) {
+            const uint64_t V = voff[n];
+            ctr->n_visible = V;
+            ctr->required_visible = V;
+            if (V > vis_cap || uoff[n] > unit_cap) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_VISIBLE);
+        }
+    }
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t p = by_cell[i];
+        const uint32_t c = pair_cell[p];
+        const uint32_t cs = cell_start[c], len = cell_start[c + 1] - cs;
+        const uint64_t d0 = voff[p];
+        const uint32_t u0 = uoff[i], nu = uoff[i + 1] - u0;
+        for (uint32_t k = 0; k < nu; k++) {
+            if ((uint64_t)u0 + k >= unit_cap) break;
+            EmitUnit u;
+            u.src = cs + k * EMIT_UNIT;
+            u.len = min((uint32_t)EMIT_UNIT, len - k * EMIT_UNIT);
+            u.dst = d0 + (uint64_t)k * EMIT_UNIT;
+            units[u0 + k] = u;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(EMIT_THREADS, 4)
+    emit_visible_v5_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, const uint64_t* __restrict__ voff,
+                           const uint32_t* __restrict__ uoff, const EmitUnit* __restrict__ units, uint64_t unit_cap,
+                           const uint32_t* __restrict__ sorted4, uint32_t stride, uint32_t* __restrict__ vis_entity, uint64_t vis_cap,
+                           uint32_t sm_count) {
+    const uint64_t np = min((uint64_t)*n_pairs_ptr, pair_cap);
+    if (np == 0) return;
+    if (voff[np] > vis_cap) return;
+    const uint32_t U = uoff[np];
+    if (U > unit_cap) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    // blocks b, b+sm_count, b+2*sm_count, ... are typically co-resident on one SM: give them adjacent slices
+    const uint32_t per_sm = gridDim.x / sm_count ? gridDim.x / sm_count : 1;
+    const uint32_t lb = (blockIdx.x % sm_count) * per_sm + (blockIdx.x / sm_count);
+    const uint64_t n_warps = (uint64_t)gridDim.x * EMIT_WARPS, wid = (uint64_t)(lb < gridDim.x ? lb : blockIdx.x) * EMIT_WARPS + w;
+    const uint32_t u0 = (uint32_t)((uint64_t)U * wid / n_warps), u1 = (uint32_t)((uint64_t)U * (wid + 1) / n_warps);
+    if (u0 >= u1) return;
+    const uint4* __restrict__ desc = reinterpret_cast<const uint4*>(units);
+    uint4 nd = __ldg(desc + u0);  // software pipeline: the next descriptor is always in flight
+    for (uint32_t u = u0; u < u1; u++) {
+        const uint4 cd = nd;
+        if (u + 1 < u1) nd = __ldg(desc + u + 1);
+        uint32_t s = cd.x, m = cd.y;
+        uint64_t d = (uint64_t)cd.z | ((uint64_t)cd.w << 32);
+        const uint32_t head = min(m, (uint32_t)((4 - (d & 3)) & 3));  // entries up to the next 16-byte boundary
+        if (lane < head) vis_entity[d + lane] = __ldg(sorted4 + s + lane);
+        s += head; d += head; m -= head;
+        const uint32_t ph = (0u - s) & 3u;  // d is 16-byte aligned now: pick the co-aligned phase copy
+        const uint4* __restrict__ src = reinterpret_cast<const uint4*>(sorted4 + (size_t)ph * stride + ph + s);
+        uint4* __restrict__ dst = reinterpret_cast<uint4*>(vis_entity + d);
+        const uint32_t nv = m >> 2;
+        uint4 v[EMIT_UNIT / 128];
+#pragma unroll
+        for (int it = 0; it < EMIT_UNIT / 128; it++)
+            if (it * 32 + lane < nv) v[it] = __ldg(src + it * 32 + lane);
+#pragma unroll
+        for (int it = 0; it < EMIT_UNIT / 128; it++)
+            if (it * 32 + lane < nv) __stcs(dst + it * 32 + lane, v[it]);
+        const uint32_t tail = m & 3u;
+        if (lane < tail) vis_entity[d + 4 * nv + lane] = __ldg(sorted4 + s + 4 * nv + lane);
+    }
+}
+
 }  // namespace chd

@@ -107,6 +107,8 @@ struct chd_engine {
     uint32_t *d_new_sub = nullptr, *d_new_ch = nullptr, *d_gone_sub = nullptr, *d_gone_ch = nullptr;
     // emit
     uint32_t *d_vcnt = nullptr, *d_first_pair = nullptr, *d_vis = nullptr, *d_ucnt = nullptr, *d_uoff = nullptr;
+    EmitUnit* d_units = nullptr;  // v5 copy-unit descriptors
+    uint64_t unit_cap = 0;
     // 3 = output-ordered warp tiles (default: 0.37 ms on config #2); 4 = cell-grouped units with L1-resident sources
     // (experimental: fewer instructions and less L2 traffic, but latency-bound at 0.42-0.44 ms: profiles/README.md)
     int emit_variant = 3;
@@ -425,7 +427,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
     if (const char* v = getenv("CHD_JOIN_BEFORE_EMIT")) e->join_before_emit = atoi(v) != 0;
     if (const char* v = getenv("CHD_EMIT_GRID_REDUCE")) e->emit_grid_reduce = atoi(v) >= 0 && atoi(v) < 400 ? atoi(v) : 0;
     if (const char* v = getenv("CHD_EMIT_BPS")) e->emit_blocks_per_sm = atoi(v) >= 1 && atoi(v) <= 4 ? atoi(v) : 4;
-    if (const char* v = getenv("CHD_EMIT_VARIANT")) e->emit_variant = atoi(v) == 4 ? 4 : 3;
+    if (const char* v = getenv("CHD_EMIT_VARIANT")) e->emit_variant = (atoi(v) == 4 || atoi(v) == 5) ? atoi(v) : 3;
 #define CCU(call)                                                                       \
     do {                                                                                \
         cudaError_t _r = (call);                                                        \
@@ -467,6 +469,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
     if (e->pc_blocks == 0) e->pc_blocks = 1;
     e->ho_cap = L.max_entities;
     e->max_tiles = (L.max_visible + EMIT_TILE - 1) / EMIT_TILE + 1;
+    e->unit_cap = L.max_visible / EMIT_UNIT + L.max_pairs + 1;
     uint64_t scan_n = (uint64_t)BUILD_MAX_BINS * e->build_blocks + 1;
     if (P + 1 > scan_n) scan_n = P + 1;
     if (Q + 1 > scan_n) scan_n = Q + 1;
@@ -501,7 +504,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
          dalloc(e, &e->d_slot_query, S) && dalloc(e, &e->d_slot_cnt, S);
     ok = ok && dalloc(e, &e->d_new_off, (Q > P ? Q : P) + 2) && dalloc(e, &e->d_new_sub, P) && dalloc(e, &e->d_new_ch, P) && dalloc(e, &e->d_gone_sub, P) &&
          dalloc(e, &e->d_gone_ch, P);
-    ok = ok && dalloc(e, &e->d_vcnt, P) && dalloc(e, &e->d_ucnt, P) && dalloc(e, &e->d_uoff, P + 2) && dalloc(e, &e->d_voff, P + 1) && dalloc(e, &e->d_first_pair, e->max_tiles + 1) &&
+    ok = ok && dalloc(e, &e->d_vcnt, P) && dalloc(e, &e->d_ucnt, P) && dalloc(e, &e->d_uoff, P + 2) && dalloc(e, &e->d_units, e->unit_cap) && dalloc(e, &e->d_voff, P + 1) && dalloc(e, &e->d_first_pair, e->max_tiles + 1) &&
          dalloc(e, &e->d_vis_off, S + 1) && dalloc(e, &e->d_vis, L.max_visible);
     ok = ok && dalloc(e, &e->d_ring_off, C + 1) && dalloc(e, &e->d_ring_arrival, (uint64_t)L.max_ring_entries) &&
          dalloc(e, &e->d_ring_sender, (uint64_t)L.max_ring_entries) && dalloc(e, &e->d_ring_index, (uint64_t)L.max_ring_entries) &&
@@ -1029,7 +1032,14 @@ chd_status chd_emit_visible(chd_engine* e) {
     const int variant = e->emit_variant;
     const uint64_t key = mix_key(mix_key(mix_key(0x656d6974ull, S), (uint64_t)e->cur), (uint64_t)variant);
     chd_status st = run_stage(e, e->g_emit_prep[e->cur], key, [&]() -> chd_status {
-        if (variant == 4) {
+        if (variant == 5) {
+            SCAN(e, exclusive_scan_fn<PairVcountIn, uint64_t>(PairVcountIn{pb.cell, e->d_cell_start}, e->d_voff, P, e->site_voff, s, pb.off + S));
+            SCAN(e, exclusive_scan_fn<UnitCountIn, uint32_t>(UnitCountIn{pb.cell, e->d_by_cell, e->d_cell_start}, e->d_uoff, P, e->site_uoff, s,
+                                                             pb.off + S));
+            emit_units_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, e->d_voff, e->d_uoff, e->d_by_cell, pb.cell, e->d_cell_start, e->d_units,
+                                                   e->unit_cap, S, pb.off, e->d_vis_off, e->lim.max_visible, e->d_ctr, e->d_epoch + EP_EMIT);
+            KCHECK(e);
+        } else if (variant == 4) {
             bump_epoch_kernel<<<1, 1, 0, s>>>(e->d_epoch + EP_EMIT);
             KCHECK(e);
             pair_vcount_units_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, pb.cell, e->d_by_cell, e->d_cell_start, e->d_vcnt, e->d_ucnt);
@@ -1054,7 +1064,11 @@ chd_status chd_emit_visible(chd_engine* e) {
     }
     {
         StageTimer kt(e, CHD_STAGE_EMIT_KERNEL);
-        if (variant == 4)
+        if (variant == 5)
+            emit_visible_v5_kernel<<<(unsigned)e->sm_count * 4, EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, e->d_uoff, e->d_units, e->unit_cap,
+                                                                                      e->d_sorted4, e->phase_stride, e->d_vis, e->lim.max_visible,
+                                                                                      (uint32_t)e->sm_count);
+        else if (variant == 4)
             emit_visible_v4_kernel<<<(unsigned)e->sm_count * 4, EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, e->d_uoff, e->d_by_cell, pb.cell,
                                                                                       e->d_cell_start, e->d_sorted4, e->phase_stride, e->d_vis,
                                                                                       e->lim.max_visible, (uint32_t)e->sm_count);
@@ -1207,7 +1221,7 @@ static chd_status chd_tick_impl(chd_engine* e, const chd_query_batch* q, int64_t
             st = chd_build(e);
             if (st != CHD_OK) return st;
         }
-        CU(e, cudaStreamWaitEvent(main_stream, e->emit_variant == 4 ? e->ev_interest : e->ev_pairs, 0));
+        CU(e, cudaStreamWaitEvent(main_stream, e->emit_variant >= 4 ? e->ev_interest : e->ev_pairs, 0));
         if (do_emit) {
             if (e->join_before_emit) e->wait_before_emit_kernel = e->ev_join;
             st = chd_emit_visible(e);
@@ -1244,7 +1258,7 @@ static chd_status chd_tick_impl(chd_engine* e, const chd_query_batch* q, int64_t
             if (st != CHD_OK) return st;
         }
         if (do_emit) {
-            CU(e, cudaStreamWaitEvent(main_stream, (e->emit_variant == 4 || !q) ? e->ev_interest : e->ev_pairs, 0));
+            CU(e, cudaStreamWaitEvent(main_stream, (e->emit_variant >= 4 || !q) ? e->ev_interest : e->ev_pairs, 0));
             if (e->join_before_emit) e->wait_before_emit_kernel = e->ev_join;
             st = chd_emit_visible(e);
             if (st != CHD_OK) return st;
