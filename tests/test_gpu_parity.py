@@ -623,3 +623,43 @@ def test_zero_copy_device_inputs_match_host_inputs(chd):
             np.testing.assert_array_equal(a[1][k], b[1][k])
         np.testing.assert_array_equal(a[2], b[2]); np.testing.assert_array_equal(a[3], b[3]); np.testing.assert_array_equal(a[4], b[4])
     assert sum(r[0]["n_due"] for r in out["host"]) > 1000
+
+
+def test_update_interest_all_aoi_kinds(chd, oracle):
+    """The stateful path (chd_update_interest) with spots / box / sphere / cone queries and their combinations:
+    every subscriber's subscription set (channel, dist, damping interval) equals the oracle's QueryChannelIds; failed
+    queries leave the previous subscriptions untouched (message_spatial.go:60-63)."""
+    from tests._oracle import make_grid
+
+    g = GRIDS[5]  # 9 x 8 grid, 100 x 50 cells
+    og = make_grid(*g)
+    rng = np.random.default_rng(4242)
+    S = 600
+    e = chd.engine.Engine(chd.engine.grid_cfg(*g), 16, S, max_spots=1 << 14, max_window_cells=1 << 20, max_visible=1 << 16)
+    e.set_entities(np.array([0.0]), np.array([0.0]))
+    e.build()
+    e.set_subscribers(np.arange(1, S + 1, dtype=np.uint32))
+    state = [dict() for _ in range(S)]
+    for tick in range(3):
+        qs = _random_queries(rng, g, S)
+        order = rng.permutation(S)  # query i belongs to subscriber order[i]
+        batch, keep = chd.controller.pack_queries(qs, subs=order.astype(np.uint32))
+        e.update_interest(batch, (tick + 1) * 33_000_000)
+        s = e.summary()
+        status = e.get_query_status(S)
+        n_err = 0
+        for i, q in enumerate(qs):
+            want, st = _oracle_query(oracle, og, q)
+            if st != 0:
+                n_err += 1
+                assert status[i] != 0
+            else:
+                assert status[i] == 0
+                state[order[i]] = want
+        assert s.n_query_errors == n_err and 0 < n_err < S
+        pairs = e.get_pairs(s.n_pairs)
+        for j in range(S):
+            sl = slice(pairs["off"][j], pairs["off"][j + 1])
+            got = dict(zip(pairs["channel"][sl].tolist(), pairs["dist"][sl].tolist()))
+            assert got == state[j], (tick, j)
+            assert pairs["interval"][sl].tolist() == [oracle.damping(d, 20) for d in pairs["dist"][sl].tolist()]
