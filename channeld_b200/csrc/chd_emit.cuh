@@ -45,35 +45,6 @@ struct PairVcountIn {
     }
 };
 
-// per pair: number of visible entities = size of the cell's list
-__global__ void __launch_bounds__(256)
-    pair_vcount_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, const uint32_t* __restrict__ pair_cell,
-                       const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ vcnt, unsigned long long* bump_epoch) {
-    const uint64_t n = min((uint64_t)*n_pairs_ptr, pair_cap);
-    if (bump_epoch && blockIdx.x == 0 && threadIdx.x == 0) *bump_epoch = (*bump_epoch + 1) & ((1ull << 22) - 1);  // emit stage epoch
-    for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < n; p += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t c = pair_cell[p];
-        vcnt[p] = cell_start[c + 1] - cell_start[c];
-    }
-}
-
-// vis_off[s] = voff[pair_off[s]]; also records V and the overflow flag
-__global__ void __launch_bounds__(256)
-    vis_off_kernel(uint32_t n_slots, const uint32_t* __restrict__ pair_off, uint64_t pair_cap, const uint64_t* __restrict__ voff,
-                   uint64_t* __restrict__ vis_off, uint64_t vis_cap, Counters* __restrict__ ctr) {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s > n_slots) return;
-    const uint64_t np = min((uint64_t)pair_off[n_slots], pair_cap);
-    const uint64_t p = min((uint64_t)pair_off[s], np);
-    vis_off[s] = voff[p];
-    if (s == n_slots) {
-        const uint64_t V = voff[np];
-        ctr->n_visible = V;
-        ctr->required_visible = V;
-        if (V > vis_cap) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_VISIBLE);
-    }
-}
-
 // first_pair[t] = the pair whose output interval [voff[p], voff[p+1]) contains entry t*EMIT_TILE;
 // also vis_off[s] = voff[pair_off[s]] and the V / overflow bookkeeping (one launch instead of two)
 __global__ void __launch_bounds__(256)
@@ -185,91 +156,15 @@ __global__ void __launch_bounds__(EMIT_THREADS, 4)
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// v4: cell-grouped work order.  v3 is bound by L2 bandwidth, not HBM: every visible entry is read from L2 and
-// written through L2 (2 x 1.95 GB per tick ~ 88 % of the ~12 TB/s L2 ceiling).  Here the work list is ordered
-// by CELL (the by_cell permutation of the pairs): the warps of an SM copy the same cell's entity list over and
-// over, so after the first touch the reads are L1 hits and L2 carries (almost) only the write stream.
-// Work unit = up to EMIT_UNIT consecutive entries of one pair; ucnt[i] = ceil(len(by_cell[i]) / EMIT_UNIT),
-// uoff = exclusive scan.  A warp owns a contiguous slice of units; neighbouring warps / co-resident blocks own
-// neighbouring slices (same or adjacent cells).
+// v5 (experimental, CHD_EMIT_VARIANT=5): cell-grouped work order.  v3 is bound by the L2 -> HBM write stream with every
+// visible entry also READ from L2; here the copy units are ordered by CELL (the by_cell permutation of the pairs) so the
+// warps of an SM copy the same cell's entity list over and over and the reads become L1 hits.  Work unit = up to
+// EMIT_UNIT consecutive entries of one pair, described by a 16-byte descriptor written by the preparation pass.
+// Measured (profiles/README.md): L1 hit rate 11 % -> 46 %, L2 traffic and instruction count down — and the kernel
+// SLOWER (0.42-0.46 ms vs 0.355 ms), because each warp now sweeps its own distant region of the output: thousands of
+// scattered write streams instead of v3's single contiguous sweep, and the write stream is the scarce resource.
 constexpr int EMIT_UNIT = 1024;
 
-// per pair p: vcnt[p] (visible entries); per by-cell position i: ucnt[i] (units of pair by_cell[i])
-__global__ void __launch_bounds__(256)
-    pair_vcount_units_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, const uint32_t* __restrict__ pair_cell,
-                             const uint32_t* __restrict__ by_cell, const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ vcnt,
-                             uint32_t* __restrict__ ucnt) {
-    const uint64_t n = min((uint64_t)*n_pairs_ptr, pair_cap);
-    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t c = pair_cell[t];
-        vcnt[t] = cell_start[c + 1] - cell_start[c];
-        const uint32_t c2 = pair_cell[by_cell[t]];
-        ucnt[t] = (cell_start[c2 + 1] - cell_start[c2] + EMIT_UNIT - 1) / EMIT_UNIT;
-    }
-}
-
-__global__ void __launch_bounds__(EMIT_THREADS, 4)
-    emit_visible_v4_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, const uint64_t* __restrict__ voff,
-                           const uint32_t* __restrict__ uoff, const uint32_t* __restrict__ by_cell, const uint32_t* __restrict__ pair_cell,
-                           const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ sorted4, uint32_t stride,
-                           uint32_t* __restrict__ vis_entity, uint64_t vis_cap, uint32_t sm_count) {
-    const uint64_t np = min((uint64_t)*n_pairs_ptr, pair_cap);
-    if (np == 0) return;
-    if (voff[np] > vis_cap) return;
-    const uint32_t U = uoff[np];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    // blocks b, b+sm_count, b+2*sm_count, ... are typically co-resident on one SM: give them adjacent slices
-    const uint32_t per_sm = gridDim.x / sm_count ? gridDim.x / sm_count : 1;
-    const uint32_t lb = (blockIdx.x % sm_count) * per_sm + (blockIdx.x / sm_count);
-    const uint64_t n_warps = (uint64_t)gridDim.x * EMIT_WARPS, wid = (uint64_t)(lb < gridDim.x ? lb : blockIdx.x) * EMIT_WARPS + w;
-    const uint32_t u0 = (uint32_t)((uint64_t)U * wid / n_warps), u1 = (uint32_t)((uint64_t)U * (wid + 1) / n_warps);
-    if (u0 >= u1) return;
-    // largest i with uoff[i] <= u0
-    uint32_t lo = 0, hi = (uint32_t)np - 1;
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi + 1) >> 1;
-        if (uoff[mid] <= u0) lo = mid; else hi = mid - 1;
-    }
-    uint32_t i = lo, u = u0;
-    while (u < u1) {
-        const uint32_t ub = uoff[i], ue = uoff[i + 1];
-        if (ue <= u) {  // empty pair (or already past it)
-            i++;
-            continue;
-        }
-        const uint32_t p = by_cell[i];
-        const uint32_t c = pair_cell[p];
-        const uint32_t cs = cell_start[c], len = cell_start[c + 1] - cs;
-        const uint64_t dst0 = voff[p];
-        for (uint32_t k = u - ub; ub + k < ue && u < u1; k++, u++) {
-            uint32_t s = cs + k * EMIT_UNIT;                      // source entry (index into phase copy 0)
-            uint64_t d = dst0 + (uint64_t)k * EMIT_UNIT;          // destination entry
-            uint32_t m = min((uint32_t)EMIT_UNIT, len - k * EMIT_UNIT);
-            const uint32_t head = min(m, (uint32_t)((4 - (d & 3)) & 3));  // entries up to the next 16-byte boundary
-            if (lane < head) vis_entity[d + lane] = __ldg(sorted4 + s + lane);
-            s += head; d += head; m -= head;
-            const uint32_t ph = (0u - s) & 3u;  // d is 16-byte aligned now: pick the co-aligned phase copy
-            const uint4* __restrict__ src = reinterpret_cast<const uint4*>(sorted4 + (size_t)ph * stride + ph + s);
-            uint4* __restrict__ dst = reinterpret_cast<uint4*>(vis_entity + d);
-            const uint32_t nv = m >> 2;
-            uint4 v[EMIT_UNIT / 128];
-#pragma unroll
-            for (int it = 0; it < EMIT_UNIT / 128; it++)
-                if (it * 32 + lane < nv) v[it] = __ldg(src + it * 32 + lane);
-#pragma unroll
-            for (int it = 0; it < EMIT_UNIT / 128; it++)
-                if (it * 32 + lane < nv) __stcs(dst + it * 32 + lane, v[it]);
-            const uint32_t tail = m & 3u;
-            if (lane < tail) vis_entity[d + 4 * nv + lane] = __ldg(sorted4 + s + 4 * nv + lane);
-        }
-        i++;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// v5 = v4 with per-unit descriptors: the preparation pass writes one 16-byte descriptor {src, len, dst} per unit,
-// so the copy kernel has a single (prefetched, warp-uniform) metadata load per 4 KB instead of v4's 4-deep
-// dependent chain by_cell -> pair_cell -> cell_start -> voff.
 struct EmitUnit {
     uint32_t src;  // first source entry (index into phase copy 0)
     uint32_t len;  // entries (1..EMIT_UNIT)

@@ -100,17 +100,16 @@ struct chd_engine {
     uint64_t* d_qoff = nullptr;  // stateless query CSR offsets
     uint32_t *d_qout_id = nullptr, *d_qout_dist = nullptr;
     int32_t* d_slot_query = nullptr;
-    uint32_t* d_slot_cnt = nullptr;
     uint32_t last_nq = 0;
     // diff
     uint32_t *d_new_off = nullptr;  // scratch for u64 -> u32 offset narrowing (stateless query path)
     uint32_t *d_new_sub = nullptr, *d_new_ch = nullptr, *d_gone_sub = nullptr, *d_gone_ch = nullptr;
     // emit
-    uint32_t *d_vcnt = nullptr, *d_first_pair = nullptr, *d_vis = nullptr, *d_ucnt = nullptr, *d_uoff = nullptr;
+    uint32_t *d_vcnt = nullptr, *d_first_pair = nullptr, *d_vis = nullptr, *d_uoff = nullptr;
     EmitUnit* d_units = nullptr;  // v5 copy-unit descriptors
     uint64_t unit_cap = 0;
-    // 3 = output-ordered warp tiles (default: 0.37 ms on config #2); 4 = cell-grouped units with L1-resident sources
-    // (experimental: fewer instructions and less L2 traffic, but latency-bound at 0.42-0.44 ms: profiles/README.md)
+    // 3 = output-ordered warp tiles (default: 0.355 ms on config #2); 5 = cell-grouped copy units with L1-resident sources
+    // (experimental: fewer instructions and less L2 traffic, but it scatters the write stream: 0.42-0.46 ms, profiles/README.md)
     int emit_variant = 3;
     int emit_blocks_per_sm = 4;
     // CTAs withheld from the emit grid so that the concurrent aux-stream kernels (fan-out, pair grouping) find free SM
@@ -427,7 +426,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
     if (const char* v = getenv("CHD_JOIN_BEFORE_EMIT")) e->join_before_emit = atoi(v) != 0;
     if (const char* v = getenv("CHD_EMIT_GRID_REDUCE")) e->emit_grid_reduce = atoi(v) >= 0 && atoi(v) < 400 ? atoi(v) : 0;
     if (const char* v = getenv("CHD_EMIT_BPS")) e->emit_blocks_per_sm = atoi(v) >= 1 && atoi(v) <= 4 ? atoi(v) : 4;
-    if (const char* v = getenv("CHD_EMIT_VARIANT")) e->emit_variant = (atoi(v) == 4 || atoi(v) == 5) ? atoi(v) : 3;
+    if (const char* v = getenv("CHD_EMIT_VARIANT")) e->emit_variant = atoi(v) == 5 ? 5 : 3;
 #define CCU(call)                                                                       \
     do {                                                                                \
         cudaError_t _r = (call);                                                        \
@@ -501,10 +500,10 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
          dalloc(e, &e->d_window, L.max_window_cells) && dalloc(e, &e->d_side_cell, (uint64_t)L.max_spots) &&
          dalloc(e, &e->d_side_dist, (uint64_t)L.max_spots) && dalloc(e, &e->d_side_cnt, Q) && dalloc(e, &e->d_status, Q) &&
          dalloc(e, &e->d_qcount, Q) && dalloc(e, &e->d_qoff, Q + 1) && dalloc(e, &e->d_qout_id, P) && dalloc(e, &e->d_qout_dist, P) &&
-         dalloc(e, &e->d_slot_query, S) && dalloc(e, &e->d_slot_cnt, S);
+         dalloc(e, &e->d_slot_query, S);
     ok = ok && dalloc(e, &e->d_new_off, (Q > P ? Q : P) + 2) && dalloc(e, &e->d_new_sub, P) && dalloc(e, &e->d_new_ch, P) && dalloc(e, &e->d_gone_sub, P) &&
          dalloc(e, &e->d_gone_ch, P);
-    ok = ok && dalloc(e, &e->d_vcnt, P) && dalloc(e, &e->d_ucnt, P) && dalloc(e, &e->d_uoff, P + 2) && dalloc(e, &e->d_units, e->unit_cap) && dalloc(e, &e->d_voff, P + 1) && dalloc(e, &e->d_first_pair, e->max_tiles + 1) &&
+    ok = ok && dalloc(e, &e->d_vcnt, P) && dalloc(e, &e->d_uoff, P + 2) && dalloc(e, &e->d_units, e->unit_cap) && dalloc(e, &e->d_voff, P + 1) && dalloc(e, &e->d_first_pair, e->max_tiles + 1) &&
          dalloc(e, &e->d_vis_off, S + 1) && dalloc(e, &e->d_vis, L.max_visible);
     ok = ok && dalloc(e, &e->d_ring_off, C + 1) && dalloc(e, &e->d_ring_arrival, (uint64_t)L.max_ring_entries) &&
          dalloc(e, &e->d_ring_sender, (uint64_t)L.max_ring_entries) && dalloc(e, &e->d_ring_index, (uint64_t)L.max_ring_entries) &&
@@ -1048,15 +1047,6 @@ chd_status chd_emit_visible(chd_engine* e) {
             emit_units_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, e->d_voff, e->d_uoff, e->d_by_cell, pb.cell, e->d_cell_start, e->d_units,
                                                    e->unit_cap, S, pb.off, e->d_vis_off, e->lim.max_visible, e->d_ctr, e->d_epoch + EP_EMIT);
             KCHECK(e);
-        } else if (variant == 4) {
-            bump_epoch_kernel<<<1, 1, 0, s>>>(e->d_epoch + EP_EMIT);
-            KCHECK(e);
-            pair_vcount_units_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, pb.cell, e->d_by_cell, e->d_cell_start, e->d_vcnt, e->d_ucnt);
-            KCHECK(e);
-            SCAN(e, exclusive_scan_1p<uint32_t, uint64_t>(e->d_vcnt, e->d_voff, P, e->site_voff, s, pb.off + S));
-            SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_ucnt, e->d_uoff, P, e->site_uoff, s, pb.off + S));
-            vis_off_kernel<<<blocks_for((uint64_t)S + 1, 256), 256, 0, s>>>(S, pb.off, P, e->d_voff, e->d_vis_off, e->lim.max_visible, e->d_ctr);
-            KCHECK(e);
         } else {
             // per-pair visible counts are computed by the scan itself; the partition pass opens the next epoch
             SCAN(e, exclusive_scan_fn<PairVcountIn, uint64_t>(PairVcountIn{pb.cell, e->d_cell_start}, e->d_voff, P, e->site_voff, s, pb.off + S));
@@ -1077,10 +1067,6 @@ chd_status chd_emit_visible(chd_engine* e) {
             emit_visible_v5_kernel<<<(unsigned)e->sm_count * 4, EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, e->d_uoff, e->d_units, e->unit_cap,
                                                                                       e->d_sorted4, e->phase_stride, e->d_vis, e->lim.max_visible,
                                                                                       (uint32_t)e->sm_count);
-        else if (variant == 4)
-            emit_visible_v4_kernel<<<(unsigned)e->sm_count * 4, EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, e->d_uoff, e->d_by_cell, pb.cell,
-                                                                                      e->d_cell_start, e->d_sorted4, e->phase_stride, e->d_vis,
-                                                                                      e->lim.max_visible, (uint32_t)e->sm_count);
         else
             emit_visible_kernel<<<(unsigned)std::max(1, e->sm_count * e->emit_blocks_per_sm - e->emit_grid_reduce), EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4,
                                                                                    e->phase_stride, e->d_first_pair, e->d_vis, e->lim.max_visible);

@@ -48,27 +48,6 @@ struct SlotCountIn {
     }
 };
 
-// new pair count per slot
-__global__ void __launch_bounds__(256)
-    slot_count_kernel(uint32_t n_slots, const int32_t* __restrict__ slot_query, uint32_t n_queries, const uint32_t* __restrict__ status,
-                      const uint32_t* __restrict__ qcount, const uint32_t* __restrict__ prev_off, uint32_t* __restrict__ cnt,
-                      Counters* __restrict__ ctr) {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t err = 0;
-    if (s < n_slots) {
-        // slot_query == nullptr: identity batch (query i belongs to subscriber slot i)
-        const int32_t q = slot_query ? slot_query[s] : (s < n_queries ? (int32_t)s : -1);
-        if (q >= 0 && status[q] == CHD_Q_OK)
-            cnt[s] = qcount[q];
-        else {
-            cnt[s] = prev_off[s + 1] - prev_off[s];
-            err = q >= 0;
-        }
-    }
-    const uint32_t nerr = __syncthreads_count(err);
-    if (threadIdx.x == 0 && nerr) atomicAdd(&ctr->n_query_errors, nerr);
-}
-
 struct DiffOut {  // the two interest-diff lists of a tick: (subscriber slot, channel id)
     uint32_t *new_sub, *new_ch, *gone_sub, *gone_ch;
 };
