@@ -30,7 +30,9 @@ struct chd_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    std::mutex mu;
+    // Guards (a) the shared query scratch between the stateless query entry points and the tick driver and (b) the
+    // temporary redirection of `stream` to aux_stream while the interest / fan-out chain is being enqueued.
+    std::recursive_mutex mu;
     mutable std::string err;
     std::vector<void*> allocs;
     int sm_count = 148;
@@ -560,7 +562,7 @@ chd_status chd_sync(chd_engine* e) {
 
 chd_status chd_cell_of(chd_engine* e, const double* x, const double* z, uint32_t n, uint32_t* out) {
     if (!e || (n && (!x || !z || !out))) return CHD_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(e->mu);
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
     CU(e, cudaSetDevice(e->device));
     // chunked through the tmp buffers (they are free outside chd_build)
     double *dx = nullptr, *dz = nullptr;
@@ -887,8 +889,9 @@ static chd_status run_query_kernels(chd_engine* e, const QueryDev& d) {
 chd_status chd_query_channel_ids(chd_engine* e, const chd_query_batch* q, uint32_t* out_status, uint32_t* out_off,
                                  uint32_t* out_channel_id, uint32_t* out_dist, uint64_t cap) {
     if (!e || !q) return CHD_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(e->mu);
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
     CU(e, cudaSetDevice(e->device));
+    if (e->aux_stream) CU(e, cudaStreamSynchronize(e->aux_stream));  // an in-flight interest update shares the query scratch
     QueryDev d;
     chd_status st = upload_queries(e, q, &d, false);
     if (st != CHD_OK) return st;
@@ -1001,7 +1004,7 @@ static chd_status interest_enqueue(chd_engine* e, const QueryDev& d, int part) {
 
 chd_status chd_update_interest(chd_engine* e, const chd_query_batch* q, int64_t now_ns) {
     if (!e || !q) return CHD_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(e->mu);
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
     CU(e, cudaSetDevice(e->device));
     StageTimer timer(e, CHD_STAGE_INTEREST);
     QueryDev d;
@@ -1170,6 +1173,7 @@ chd_status chd_begin_interest(chd_engine* e, const chd_query_batch* q, int64_t t
         if (st == CHD_OK && with_fanout) st = chd_fanout_tick(e, t_ns);
         return st;
     }
+    std::lock_guard<std::recursive_mutex> lk(e->mu);  // `stream` is redirected below
     cudaStream_t main_stream = e->stream;
     CU(e, cudaEventRecord(e->ev_fork, main_stream));
     CU(e, cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0));
@@ -1238,6 +1242,7 @@ static chd_status chd_tick_impl(chd_engine* e, const chd_query_batch* q, int64_t
         cudaStream_t main_stream = e->stream;
         CU(e, cudaEventRecord(e->ev_fork, main_stream));
         CU(e, cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0));
+        std::unique_lock<std::recursive_mutex> redirect(e->mu);  // `stream` is redirected until it is restored below
         e->stream = e->aux_stream;
         st = q ? chd_update_interest(e, q, t_ns) : CHD_OK;
         if (st == CHD_OK) {
@@ -1246,6 +1251,7 @@ static chd_status chd_tick_impl(chd_engine* e, const chd_query_batch* q, int64_t
         }
         if (st == CHD_OK && do_fanout) st = chd_fanout_tick(e, t_ns);
         e->stream = main_stream;
+        redirect.unlock();
         if (st != CHD_OK) return st;
         CU(e, cudaEventRecord(e->ev_join, e->aux_stream));
         if (need_build) {

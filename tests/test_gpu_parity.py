@@ -663,3 +663,58 @@ def test_update_interest_all_aoi_kinds(chd, oracle):
             got = dict(zip(pairs["channel"][sl].tolist(), pairs["dist"][sl].tolist()))
             assert got == state[j], (tick, j)
             assert pairs["interval"][sl].tolist() == [oracle.damping(d, 20) for d in pairs["dist"][sl].tolist()]
+
+
+def test_concurrent_stateless_queries_during_ticks(chd, oracle):
+    """GetChannelId / QueryChannelIds are called from arbitrary channel goroutines while the tick driver runs
+    (spatial.go:20-29): a second thread hammers the stateless entry points during batched ticks; both stay exact."""
+    import threading
+
+    wc = chd.synth.scaled(chd.synth.CONFIGS["benchmark"], 50_000, 5_000)
+    og = _oracle_grid(wc)
+    e = chd.engine.Engine(wc.cfg(), wc.n_entities, wc.n_subscribers, max_visible=1 << 23)
+    ex, ez = chd.synth.entities(wc)
+    conn, cx, cz, r = chd.synth.subscribers(wc, ex, ez)
+    e.set_subscribers(conn)
+    stop, errors = threading.Event(), []
+
+    def worker():
+        rng = np.random.default_rng(7)
+        while not stop.is_set():
+            try:
+                x, z = rng.uniform(-16000, 16000, 257), rng.uniform(-16000, 16000, 257)
+                if not np.array_equal(e.cell_of(x, z), oracle.cell_of(og, x, z)):
+                    errors.append("cell_of mismatch")
+                n = 64
+                qx, qz, qr = rng.uniform(-15000, 15000, n), rng.uniform(-15000, 15000, n), rng.choice([50.0, 900.0, 2500.0], n)
+                b, keep = chd.engine.make_batch(n, sphere=(qx, qz, qr))
+                st, off, ids, dist = e.query_channel_ids(b)
+                for i in range(n):
+                    want, wst = oracle.query(og, sphere=(qx[i], qz[i], qr[i]))
+                    got = dict(zip(ids[off[i]:off[i + 1]].tolist(), dist[off[i]:off[i + 1]].tolist()))
+                    if (wst != 0) != (st[i] != 0) or (wst == 0 and got != want):
+                        errors.append("query mismatch")
+            except Exception as ex_:  # noqa: BLE001
+                errors.append(repr(ex_))
+                return
+
+    th = threading.Thread(target=worker)
+    th.start()
+    try:
+        for tick in range(30):
+            ex, ez = chd.synth.move_entities(wc, ex, ez, tick, 200.0)
+            _, cx, cz, r = chd.synth.subscribers(wc, ex, ez)
+            e.set_entities(ex, ez)
+            batch, keep = chd.engine.make_batch(len(cx), sub=None, sphere=(cx, cz, r))
+            s = e.tick(batch, (tick + 1) * 33_000_000, chd.capi.TICK_BUILD | chd.capi.TICK_EMIT)
+            if tick % 10 == 9:
+                want = oracle.sphere_tick(og, ex, ez, cx, cz, r)
+                pairs = e.get_pairs(s.n_pairs)
+                voff, vis = e.get_visible()
+                np.testing.assert_array_equal(pairs["channel"], want["pair_cell"])
+                np.testing.assert_array_equal(voff, want["vis_off"])
+                np.testing.assert_array_equal(vis, want["vis_entity"])
+    finally:
+        stop.set()
+        th.join(60)
+    assert not errors, errors[:3]
