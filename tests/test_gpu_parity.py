@@ -718,3 +718,48 @@ def test_concurrent_stateless_queries_during_ticks(chd, oracle):
         stop.set()
         th.join(60)
     assert not errors, errors[:3]
+
+
+def test_full_size_config2_properties(chd, oracle):
+    """BASELINE config #2 at FULL size (1 M entities / 100 K subscribers, r = 50): size-independent properties of the
+    whole result + bit-exact oracle comparison on a 2 % subscriber sample."""
+    wc = chd.synth.CONFIGS["benchmark"]
+    ex, ez = chd.synth.entities(wc)
+    conn, cx, cz, r = chd.synth.subscribers(wc, ex, ez)
+    S, N = wc.n_subscribers, wc.n_entities
+    e = chd.engine.Engine(wc.cfg(), N, S, max_visible=int(6.0e8))
+    e.set_entities(ex, ez)
+    e.set_subscribers(conn)
+    batch, keep = chd.engine.make_batch(S, sub=None, sphere=(cx, cz, r))
+    s = e.tick(batch, 33_000_000, chd.capi.TICK_BUILD | chd.capi.TICK_EMIT)
+    # cell CSR: a permutation of the in-world entities, sorted by (cell, entity id)
+    cs, se = e.get_cells()
+    ids = oracle.cell_of(_oracle_grid(wc), ex, ez)
+    in_world = ids != 0
+    assert s.n_entities_in_world == int(in_world.sum()) == len(se) == int(cs[-1])
+    assert int(se.astype(np.uint64).sum()) == int(np.nonzero(in_world)[0].astype(np.uint64).sum())  # checksum: every id once
+    cell_of_sorted = ids[se] - S0
+    assert (np.diff(cell_of_sorted.astype(np.int64)) >= 0).all()  # sorted by cell
+    same = np.diff(cell_of_sorted.astype(np.int64)) == 0
+    assert (np.diff(se.astype(np.int64))[same] > 0).all()  # entity ids ascending inside a cell
+    np.testing.assert_array_equal(cs, np.concatenate([[0], np.cumsum(np.bincount(cell_of_sorted, minlength=wc.cells))]))
+    # pairs / visible lists: totals are consistent with the CSR
+    pairs = e.get_pairs(s.n_pairs)
+    voff = np.zeros(S + 1, np.uint64)
+    e._ck(e.L.chd_get_visible(e.h, chd.capi.ptr(voff), None))
+    counts = np.diff(cs.astype(np.int64))
+    per_pair = counts[pairs["channel"] - S0]
+    per_sub = np.add.reduceat(per_pair, pairs["off"][:-1].astype(np.int64)) if s.n_pairs else np.zeros(S)
+    per_sub[np.diff(pairs["off"].astype(np.int64)) == 0] = 0
+    np.testing.assert_array_equal(np.diff(voff.astype(np.int64)), per_sub)
+    assert s.n_visible == int(voff[-1]) == int(per_pair.sum()) > 4.0e8
+    assert (pairs["dist"] <= 1).all() and s.n_query_errors == int((e.get_query_status(S) != 0).sum())
+    # 2 % sample against the oracle, bit-exact (pairs, dists, visible lists)
+    sel = np.linspace(0, S - 1, S // 50).astype(np.int64)
+    want = oracle.sphere_tick(_oracle_grid(wc), ex, ez, cx[sel], cz[sel], r[sel])
+    for k, j in enumerate(sel):
+        a = slice(pairs["off"][j], pairs["off"][j + 1])
+        b = slice(int(want["pair_off"][k]), int(want["pair_off"][k + 1]))
+        np.testing.assert_array_equal(pairs["channel"][a], want["pair_cell"][b])
+        np.testing.assert_array_equal(pairs["dist"][a], want["pair_dist"][b])
+        np.testing.assert_array_equal(e.get_visible_slot(int(j)), want["vis_entity"][int(want["vis_off"][k]):int(want["vis_off"][k + 1])])
