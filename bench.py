@@ -311,8 +311,7 @@ def run_ours(args):
             # interest + fan-out do not need positions: start them on the engine's second stream, then exchange borders
             ck(L.chd_begin_interest(e.h, C.byref(batches[i % 2]), t_ns, 1))
             ck(L.chd_set_entities(e.h, capi.ptr(d["x"]), capi.ptr(d["z"]), n_own))
-            rec_local.fill_(-1)
-            e.export_border(rec_local, border_cap, want_count=False)
+            e.export_border(rec_local, border_cap, want_count=False)  # also pads the buffer
             dist.all_gather_into_tensor(rec_all, rec_local)
             e.import_halo(rec_all, border_cap * world, rank * border_cap, border_cap)
             ck(L.chd_tick(e.h, None, t_ns, capi.TICK_ALL, None))
@@ -438,8 +437,7 @@ def run_ours(args):
             ck(L.chd_begin_interest(e.h, C.byref(batches_host[i % 2]), t_ns, 1))
             ck(L.chd_set_entities(e.h, capi.ptr(d["x"]), capi.ptr(d["z"]), n_own))
             if world > 1:
-                rec_local.fill_(-1)
-                e.export_border(rec_local, border_cap, want_count=False)
+                e.export_border(rec_local, border_cap, want_count=False)  # also pads the buffer
                 dist.all_gather_into_tensor(rec_all, rec_local)
                 e.import_halo(rec_all, border_cap * world, rank * border_cap, border_cap)
             ck(L.chd_tick(e.h, None, t_ns, capi.TICK_ALL, None))

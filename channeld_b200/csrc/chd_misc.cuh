@@ -41,11 +41,17 @@ __global__ void border_flag_kernel(GridDev g, const uint32_t* __restrict__ key, 
     flag[i] = f;
 }
 
+// writes the flagged records and pads the rest of the caller's buffer with 0xFFFFFFFF (no separate fill needed)
 __global__ void border_write_kernel(const uint32_t* __restrict__ key, const uint32_t* __restrict__ gid, uint32_t n,
                                     const uint32_t* __restrict__ flag, const uint32_t* __restrict__ off, uint32_t* __restrict__ out,
                                     uint32_t cap, Counters* __restrict__ ctr) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0 && off[n] > cap) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_BORDER);
+    const uint32_t count = off[n];
+    if (i == 0 && count > cap) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_BORDER);
+    if (i < cap && i >= count) {  // padding slot
+        out[2 * i] = 0xFFFFFFFFu;
+        out[2 * i + 1] = 0xFFFFFFFFu;
+    }
     if (i >= n || !flag[i]) return;
     const uint32_t o = off[i];
     if (o < cap) {

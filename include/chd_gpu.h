@@ -273,7 +273,7 @@ chd_status chd_device_view(chd_engine* e, int which, void** d_ptr, uint64_t* cou
 /* ---- multi-GPU X-slab sharding.  The engine owns grid columns [col_lo, col_hi) and serves
  * queries whose cells lie in [col_lo-halo, col_hi+halo).  After chd_build, chd_export_border writes the
  * (entity id, cell index) records of the entities in this rank's outermost `halo` columns on each side into a
- * caller-provided DEVICE buffer (2 x u32 per record; pre-fill with 0xFFFFFFFF as padding) for the all-gather;
+ * caller-provided DEVICE buffer (2 x u32 per record; the unused tail is padded with 0xFFFFFFFF) for the all-gather;
  * chd_import_halo takes the gathered records of all ranks (records [skip_first, skip_first+skip_count) are this
  * rank's own and ignored), keeps those whose column lies in [col_lo-halo, col_hi+halo) and appends them as
  * position-less halo entities; the following chd_build sorts own + halo entities into the cell CSR.

@@ -54,7 +54,6 @@ def main():
             for tick in range(3):
                 x, z = synth.move_entities(wc, x, z, tick, max_move)  # entities drift across slab borders
                 e.set_entities(x[mine], z[mine])
-                rec_local.fill_(-1)
                 n_exp = e.export_border(rec_local, cap)
                 dist.all_gather_into_tensor(rec_all, rec_local)
                 e.import_halo(rec_all, cap * world, rank * cap, cap)
