@@ -136,7 +136,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    _emit_line(_OUT_FD, json.dumps(out))
 
 
 # ----------------------------------------------------------------------------------------- clocks
@@ -554,13 +554,27 @@ def run_ours(args):
             out["cpu_baseline"] = {"value": qn * reps / dtc, "unit": "queries/s", "cores": cores, "kind": "port",
                                    "sample": "%d ticks x %d of %d subscribers (build of %d entities included each tick); C++ restatement of "
                                              "channeld's Go path, all host threads" % (reps, qn, S_total, N_total)}
-        print(json.dumps(out), flush=True)
+        _emit_line(_OUT_FD, json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
+def _protect_stdout():
+    """rank 0 must print exactly ONE JSON line: route everything libraries write to fd 1 (e.g. NCCL's version banner)
+    to stderr and keep the real stdout for the result line."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def _emit_line(saved_fd, text):
+    os.write(saved_fd, (text + "\n").encode())
+
+
 if __name__ == "__main__":
     a = parse()
+    _OUT_FD = _protect_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:
