@@ -48,7 +48,7 @@ struct chd_engine {
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_interest = nullptr, ev_pairs = nullptr;
     bool interest_pending = false, pending_fanout = false;  // chd_begin_interest issued, not yet joined by chd_tick
-    GraphSlot g_build[2], g_interest[2], g_interest_b[2], g_emit_prep[2], g_fanout[2], g_export[2], g_import[2];
+    GraphSlot g_build[4], g_interest[2], g_interest_b[2], g_emit_prep[2], g_fanout[2], g_export[4], g_import[2];  // build / export: [key buffer][position buffer]
     uint64_t graph_launches = 0, graph_captures = 0;
     uint32_t* d_key_a = nullptr;  // identity of the first key buffer (graph slot selection)
     int64_t* d_time = nullptr;      // [0] = now_ns of the last update_interest, [1] = t_ns of the last fanout_tick
@@ -65,7 +65,16 @@ struct chd_engine {
     bool halo_on_device = false;     // multi-GPU: the build length (own + halo) lives in d_n_build
     uint32_t* d_n_build = nullptr;
     bool have_gid = false;
-    double *d_x = nullptr, *d_z = nullptr;        // engine-owned staging for host inputs
+    double *d_x = nullptr, *d_z = nullptr;        // engine-owned staging for host inputs (the FRONT buffers)
+    // chd_prefetch_entities: the BACK buffers receive the next tick's positions on `up_stream` while the current tick runs;
+    // chd_adopt_prefetched swaps front and back.  ev_pos_read[b] = last assign_cells that read buffer pair b.
+    double *d_xb[2] = {nullptr, nullptr}, *d_zb[2] = {nullptr, nullptr};
+    int pos_buf = 0;
+    cudaStream_t up_stream = nullptr;
+    cudaEvent_t ev_upload = nullptr, ev_pos_read[2] = {nullptr, nullptr};
+    bool pos_read_recorded[2] = {false, false};
+    bool staged = false;
+    uint32_t staged_n = 0;
     const double *pos_x = nullptr, *pos_z = nullptr;  // what the kernels read: the staging buffers, or the caller's device arrays
     uint32_t *d_gid = nullptr;            // [max_entities] global ids (multi-GPU) of own + halo
     uint32_t *d_key = nullptr, *d_prev_key = nullptr;  // [max_entities] cell key per entity
@@ -117,6 +126,9 @@ struct chd_engine {
     // CTAs withheld from the emit grid so that the concurrent aux-stream kernels (fan-out, pair grouping) find free SM
     // slots instead of queueing behind the saturating emit kernel (measured: profiles/README.md)
     int emit_grid_reduce = 0;
+    // grid = waves x the resident capacity: with more than one wave the emit CTAs retire as they go, so the high-priority
+    // aux-stream kernels get SM slots at the first wave boundary instead of after the whole kernel
+    int emit_waves = 1;
     // Where the aux chain (interest part 1 + fan-out) is joined: before the emit kernel (it then never competes with the
     // saturating emit kernel for SM slots) or after it (overlap).  Measured: profiles/README.md.
     bool join_before_emit = false;
@@ -343,10 +355,21 @@ void chd_destroy(chd_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->up_stream) cudaStreamSynchronize(e->up_stream);
     for (void* p : e->allocs) cudaFree(p);
-    for (auto* arr : {e->g_build, e->g_interest, e->g_interest_b, e->g_emit_prep, e->g_fanout, e->g_export, e->g_import})
+    for (auto* arr : {e->g_interest, e->g_interest_b, e->g_emit_prep, e->g_fanout, e->g_import})
         for (int i = 0; i < 2; i++)
             if (arr[i].exec) cudaGraphExecDestroy(arr[i].exec);
+    for (auto* arr : {e->g_build, e->g_export})
+        for (int i = 0; i < 4; i++)
+            if (arr[i].exec) cudaGraphExecDestroy(arr[i].exec);
+    if (e->up_stream) {
+        cudaStreamSynchronize(e->up_stream);
+        cudaStreamDestroy(e->up_stream);
+    }
+    if (e->ev_upload) cudaEventDestroy(e->ev_upload);
+    for (int i = 0; i < 2; i++)
+        if (e->ev_pos_read[i]) cudaEventDestroy(e->ev_pos_read[i]);
     if (e->ev) {
         for (size_t i = 0; i < (size_t)CHD_STAGE_COUNT * chd_engine::EV_RING * 2; i++)
             if (e->ev[i]) cudaEventDestroy(e->ev[i]);
@@ -428,6 +451,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
     if (const char* v = getenv("CHD_JOIN_BEFORE_EMIT")) e->join_before_emit = atoi(v) != 0;
     if (const char* v = getenv("CHD_EMIT_GRID_REDUCE")) e->emit_grid_reduce = atoi(v) >= 0 && atoi(v) < 400 ? atoi(v) : 0;
     if (const char* v = getenv("CHD_EMIT_BPS")) e->emit_blocks_per_sm = atoi(v) >= 1 && atoi(v) <= 4 ? atoi(v) : 4;
+    if (const char* v = getenv("CHD_EMIT_WAVES")) e->emit_waves = atoi(v) >= 1 && atoi(v) <= 64 ? atoi(v) : 1;
     if (const char* v = getenv("CHD_EMIT_VARIANT")) e->emit_variant = atoi(v) == 5 ? 5 : 3;
 #define CCU(call)                                                                       \
     do {                                                                                \
@@ -477,7 +501,9 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
     if (S + 1 > scan_n) scan_n = S + 1;
     if (N + 1 > scan_n) scan_n = N + 1;
     bool ok = true;
-    ok = ok && dalloc(e, &e->d_x, N) && dalloc(e, &e->d_z, N) && dalloc(e, &e->d_gid, N) && dalloc(e, &e->d_key, N) &&
+    ok = ok && dalloc(e, &e->d_x, N) && dalloc(e, &e->d_z, N) && (e->d_xb[0] = e->d_x, e->d_zb[0] = e->d_z, true) &&
+         cudaEventCreateWithFlags(&e->ev_pos_read[0], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&e->ev_pos_read[1], cudaEventDisableTiming) == cudaSuccess && dalloc(e, &e->d_gid, N) && dalloc(e, &e->d_key, N) &&
          dalloc(e, &e->d_prev_key, N) && dalloc(e, &e->d_tmp_key, N) && dalloc(e, &e->d_tmp_val, N) &&
          dalloc(e, &e->d_sorted_key, N) && dalloc(e, &e->d_sorted4, 4 * (((N + 3) / 4) * 4 + 8)) && dalloc(e, &e->d_cell_start, C + 2) &&
          dalloc(e, &e->d_hist, (uint64_t)BUILD_MAX_BINS * e->build_blocks + 2) &&
@@ -614,6 +640,56 @@ chd_status chd_set_entities(chd_engine* e, const double* x, const double* z, uin
     return CHD_OK;
 }
 
+chd_status chd_prefetch_entities(chd_engine* e, const double* x, const double* z, uint32_t n) {
+    if (!e || (n && (!x || !z))) return CHD_ERR_INVALID;
+    if (n > e->lim.max_entities) {
+        e->fail("chd_prefetch_entities: %u > max_entities %u", n, e->lim.max_entities);
+        return CHD_ERR_CAPACITY;
+    }
+    CU(e, cudaSetDevice(e->device));
+    const int back = e->pos_buf ^ 1;
+    if (!e->up_stream) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        CU(e, cudaStreamCreateWithPriority(&e->up_stream, cudaStreamNonBlocking, hi));
+        CU(e, cudaEventCreateWithFlags(&e->ev_upload, cudaEventDisableTiming));
+    }
+    if (!e->d_xb[back]) {  // the second pair of position buffers exists only for hosts that prefetch
+        if (!dalloc(e, &e->d_xb[back], e->lim.max_entities) || !dalloc(e, &e->d_zb[back], e->lim.max_entities)) return CHD_ERR_CUDA;
+    }
+    // the back pair was last read by the cell assignment of an earlier tick
+    if (e->pos_read_recorded[back]) CU(e, cudaStreamWaitEvent(e->up_stream, e->ev_pos_read[back], 0));
+    CU(e, cudaMemcpyAsync(e->d_xb[back], x, sizeof(double) * n, cudaMemcpyDefault, e->up_stream));
+    CU(e, cudaMemcpyAsync(e->d_zb[back], z, sizeof(double) * n, cudaMemcpyDefault, e->up_stream));
+    CU(e, cudaEventRecord(e->ev_upload, e->up_stream));
+    e->staged = true;
+    e->staged_n = n;
+    return CHD_OK;
+}
+
+chd_status chd_adopt_prefetched(chd_engine* e) {
+    if (!e) return CHD_ERR_INVALID;
+    if (!e->staged) {
+        e->fail("chd_adopt_prefetched without a preceding chd_prefetch_entities");
+        return CHD_ERR_STATE;
+    }
+    CU(e, cudaSetDevice(e->device));
+    CU(e, cudaStreamWaitEvent(e->stream, e->ev_upload, 0));
+    e->pos_buf ^= 1;
+    e->d_x = e->d_xb[e->pos_buf];
+    e->d_z = e->d_zb[e->pos_buf];
+    e->pos_x = e->d_x;
+    e->pos_z = e->d_z;
+    if (e->staged_n != e->n_own) e->have_prev_key = false;
+    e->n_own = e->staged_n;
+    e->n_halo = 0;
+    e->halo_on_device = false;
+    e->assigned = false;
+    e->entities_dirty = true;
+    e->staged = false;
+    return CHD_OK;
+}
+
 chd_status chd_entity_buffers(chd_engine* e, double** d_x, double** d_z, uint32_t* n) {
     if (!e) return CHD_ERR_INVALID;
     if (d_x) *d_x = e->d_x;
@@ -650,8 +726,26 @@ chd_status chd_set_entity_ids(chd_engine* e, const uint32_t* gid, uint32_t n) {
     return CHD_OK;
 }
 
+// The engine's position buffers are double-buffered for chd_prefetch_entities: remember (outside any graph capture)
+// the last kernel that read the front pair, so an upload into it can be ordered after that read.
+static chd_status note_pos_read(chd_engine* e) {
+    if (e->pos_x != e->d_x || !e->ev_pos_read[e->pos_buf]) return CHD_OK;
+    CU(e, cudaEventRecord(e->ev_pos_read[e->pos_buf], e->stream));
+    e->pos_read_recorded[e->pos_buf] = true;
+    return CHD_OK;
+}
+
+static chd_status assign_cells_impl(chd_engine* e);
+
 chd_status chd_assign_cells(chd_engine* e) {
     if (!e) return CHD_ERR_INVALID;
+    const bool was_assigned = e->assigned;
+    chd_status st = assign_cells_impl(e);
+    if (st == CHD_OK && !was_assigned) st = note_pos_read(e);
+    return st;
+}
+
+static chd_status assign_cells_impl(chd_engine* e) {
     CU(e, cudaSetDevice(e->device));
     if (e->assigned) return CHD_OK;
     // handover detection compares against the keys of the previous assignment (same entity count):
@@ -703,7 +797,7 @@ static chd_status sort_pass_any(chd_engine* e, uint32_t* hist, const ScanSite& s
 static chd_status build_enqueue(chd_engine* e, bool with_assign) {
     chd_status st;
     if (with_assign) {
-        st = chd_assign_cells(e);
+        st = assign_cells_impl(e);
         if (st != CHD_OK) return st;
     }
     // multi-GPU: the halo count stays on the device (d_n_build = own + kept halo records); launches are sized for
@@ -761,7 +855,7 @@ chd_status chd_build(chd_engine* e) {
         // single-GPU flow: assign + sort as one replayable graph.  The key buffers swap every assignment
         // (handover detection compares against the previous keys), so there are two graph variants.
         uint32_t* target = e->have_prev_key ? e->d_prev_key : e->d_key;  // buffer the new keys will be written to
-        const int slot = target == e->d_key_a ? 0 : 1;
+        const int slot = (target == e->d_key_a ? 0 : 1) + 2 * e->pos_buf;
         uint64_t key = mix_key(mix_key(mix_key(0x6275696c64ull, e->n_own), e->have_gid), e->have_prev_key);
         key = mix_key(mix_key(key, (uint64_t)(uintptr_t)target), (uint64_t)(uintptr_t)e->pos_x ^ ((uint64_t)(uintptr_t)e->pos_z << 1));
         st = run_stage(e, e->g_build[slot], key, [&]() { return build_enqueue(e, true); });
@@ -775,6 +869,7 @@ chd_status chd_build(chd_engine* e) {
             e->n_halo = 0;
             e->assigned = true;
         }
+        if (st == CHD_OK) st = note_pos_read(e);
     } else if (e->assigned && e->halo_on_device) {
         // multi-GPU flow: cells were assigned by chd_export_border and the halo appended on the device; the sort over
         // own + halo entities is sized by capacity (device-side length) and therefore replayable as well.
@@ -782,7 +877,9 @@ chd_status chd_build(chd_engine* e) {
         uint64_t key = mix_key(mix_key(mix_key(0x736f7274ull, e->lim.max_entities), e->have_gid), (uint64_t)(uintptr_t)e->d_key);
         st = run_stage(e, e->g_build[slot], key, [&]() { return build_enqueue(e, false); });
     } else {
-        st = build_enqueue(e, !e->assigned);
+        const bool with_assign = !e->assigned;
+        st = build_enqueue(e, with_assign);
+        if (st == CHD_OK && with_assign) st = note_pos_read(e);
     }
     if (st != CHD_OK) return st;
     e->n_sorted = e->n_own + e->n_halo;
@@ -1071,7 +1168,7 @@ chd_status chd_emit_visible(chd_engine* e) {
                                                                                       e->d_sorted4, e->phase_stride, e->d_vis, e->lim.max_visible,
                                                                                       (uint32_t)e->sm_count);
         else
-            emit_visible_kernel<<<(unsigned)std::max(1, e->sm_count * e->emit_blocks_per_sm - e->emit_grid_reduce), EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4,
+            emit_visible_kernel<<<(unsigned)std::max(1, e->sm_count * e->emit_blocks_per_sm * e->emit_waves - e->emit_grid_reduce), EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4,
                                                                                    e->phase_stride, e->d_first_pair, e->d_vis, e->lim.max_visible);
         KCHECK(e);
     }
@@ -1522,7 +1619,7 @@ chd_status chd_export_border(chd_engine* e, uint32_t* d_records, uint32_t cap_re
     const uint32_t n = e->n_own;
     const uint32_t n_launch = n > cap_records ? n : cap_records;  // the write pass also pads the caller's buffer
     auto enqueue = [&]() -> chd_status {
-        chd_status st = chd_assign_cells(e);
+        chd_status st = assign_cells_impl(e);
         if (st != CHD_OK) return st;
         border_flag_kernel<<<blocks_for(n ? n : 1, 256), 256, 0, s>>>(e->g, e->d_key, n, e->d_bflag, e->d_epoch + EP_BORDER);
         KCHECK(e);
@@ -1536,7 +1633,7 @@ chd_status chd_export_border(chd_engine* e, uint32_t* d_records, uint32_t cap_re
     if (!e->assigned) {
         // replayable: cell assignment + border selection of one tick (two variants: the key buffers ping-pong)
         uint32_t* target = e->have_prev_key ? e->d_prev_key : e->d_key;
-        const int slot = target == e->d_key_a ? 0 : 1;
+        const int slot = (target == e->d_key_a ? 0 : 1) + 2 * e->pos_buf;
         uint64_t key = mix_key(mix_key(mix_key(0x6578706full, n), e->have_gid), e->have_prev_key);
         key = mix_key(mix_key(key, (uint64_t)(uintptr_t)target), (uint64_t)(uintptr_t)e->pos_x ^ ((uint64_t)(uintptr_t)e->pos_z << 1));
         key = mix_key(mix_key(key, (uint64_t)(uintptr_t)d_records), cap_records);
@@ -1552,6 +1649,7 @@ chd_status chd_export_border(chd_engine* e, uint32_t* d_records, uint32_t cap_re
             e->n_halo = 0;
             e->assigned = true;
         }
+        if (st == CHD_OK) st = note_pos_read(e);
     } else {
         st = enqueue();
     }

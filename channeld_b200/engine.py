@@ -118,6 +118,19 @@ class Engine:
         self._keep = [x, z]  # async H2D: keep alive until the next call
         self._ck(self.L.chd_set_entities(self.h, ptr(x), ptr(z), int(n)))
 
+    def prefetch_entities(self, x, z, n=None):
+        """Start the H2D upload of the NEXT tick's positions (overlaps the tick in flight); see chd_prefetch_entities."""
+        if isinstance(x, np.ndarray):
+            x = np.ascontiguousarray(x, np.float64)
+            z = np.ascontiguousarray(z, np.float64)
+        n = len(x) if n is None else n
+        self._keep_prefetch = [x, z]
+        self._ck(self.L.chd_prefetch_entities(self.h, ptr(x), ptr(z), int(n)))
+
+    def adopt_prefetched(self):
+        self._ck(self.L.chd_adopt_prefetched(self.h))
+        self._keep = getattr(self, "_keep_prefetch", None)
+
     def set_entity_ids(self, gid):
         if gid is None:
             self._ck(self.L.chd_set_entity_ids(self.h, None, 0))

@@ -94,6 +94,14 @@ chd_status chd_cell_of(chd_engine* e, const double* x, const double* z, uint32_t
  * SpatialChannelData.Entities (pkg/unrealpb/extension.go:38-62) fed by AddEntity/RemoveEntity
  * (spatial.go:606-609,702-736).  Entity i has id i (the host maps it to EntityChannelIdStart + i). */
 chd_status chd_set_entities(chd_engine* e, const double* x, const double* z, uint32_t n);
+/* Double-buffered upload for pipelined hosts: chd_prefetch_entities starts copying the NEXT tick's host positions
+ * into the engine's second pair of position buffers on a dedicated upload stream and returns immediately; it may be
+ * called while a tick is in flight (the H2D transfer then overlaps that tick's kernels).  x / z must stay valid until
+ * chd_adopt_prefetched has been followed by chd_summary / chd_sync / chd_fetch_results.  chd_adopt_prefetched makes the
+ * prefetched positions the current ones (replaces chd_set_entities for that tick; CHD_ERR_STATE if nothing was
+ * prefetched).  The second buffer pair is allocated on the first prefetch. */
+chd_status chd_prefetch_entities(chd_engine* e, const double* x, const double* z, uint32_t n);
+chd_status chd_adopt_prefetched(chd_engine* e);
 /* Device pointers of the resident position arrays, for producers that write positions on the GPU. */
 chd_status chd_entity_buffers(chd_engine* e, double** d_x, double** d_z, uint32_t* n);
 
