@@ -41,10 +41,11 @@ def parse():
     ap.add_argument("--config", default="benchmark", choices=["2x2", "benchmark", "10m", "handover"])
     ap.add_argument("--entities", type=int, default=0)
     ap.add_argument("--subscribers", type=int, default=0)
-    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 30)")
     ap.add_argument("--expanded-steps", type=int, default=2, help="extra e2e steps that also copy the expanded list to the host")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gate", action="store_true")
+    ap.add_argument("--no-early", action="store_true", help="e2e ticks without CHD_TICK_EARLY_RESULTS")
     ap.add_argument("--updates-per-cell", type=int, default=8)
     ap.add_argument("--ring-len", type=int, default=64)
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
@@ -252,7 +253,7 @@ def run_ours(args):
     a_sub[:] = sub_idx.view(np.int32)
     d_sub = t_sub.to(dev)
 
-    n_e2e = args.e2e_steps or min(args.steps, 10)
+    n_e2e = args.e2e_steps or min(args.steps, 30)
     n_steps_total = 1 + args.warmup + args.steps + 2 * (2 + n_e2e) + 2 + args.expanded_steps + 2
     # one ring snapshot per step (arrival times follow the tick clock); bound the staging memory for huge grids
     ring_len, upc = args.ring_len, args.updates_per_cell
@@ -426,7 +427,7 @@ def run_ours(args):
         rb.vis_off = capi.ptr(r_voff)
         r_vis_keep = []
 
-        def e2e_step(i, expanded=False, pipelined=False):
+        def e2e_step(i, expanded=False, pipelined=False, early=not args.no_early):
             """Host inputs -> H2D -> one batched tick -> D2H of everything a channeld host consumes (chd_fetch_results).
             pipelined: the positions of step i were uploaded with chd_prefetch_entities while step i-1 ran, and this step
             uploads those of step i+1 behind its own kernels (double-buffered staging: one 16 B/entity upload per step,
@@ -446,7 +447,7 @@ def run_ours(args):
                 e.export_border(rec_local, border_cap, want_count=False)  # also pads the buffer
                 dist.all_gather_into_tensor(rec_all, rec_local)
                 e.import_halo(rec_all, border_cap * world, rank * border_cap, border_cap)
-            ck(L.chd_tick(e.h, None, t_ns, capi.TICK_ALL, None))
+            ck(L.chd_tick(e.h, None, t_ns, capi.TICK_ALL | (capi.TICK_EARLY_RESULTS if early else 0), None))
             if pipelined:  # next step's positions go up while this tick's kernels run
                 dn = host_in[(i + 1) % 2]
                 ck(L.chd_prefetch_entities(e.h, capi.ptr(dn["x"]), capi.ptr(dn["z"]), n_own))

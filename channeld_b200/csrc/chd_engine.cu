@@ -117,6 +117,14 @@ struct chd_engine {
     uint32_t *d_new_sub = nullptr, *d_new_ch = nullptr, *d_gone_sub = nullptr, *d_gone_ch = nullptr;
     // emit
     uint32_t *d_vcnt = nullptr, *d_first_pair = nullptr, *d_vis = nullptr, *d_uoff = nullptr;
+    uint32_t* d_pair_ch = nullptr;  // channel id of every current pair (written by interest_fill_kernel)
+    bool pair_ch_valid = false;
+    // chd_fetch_results reads back on its own stream as soon as the aux chain (pairs, diff, due list) and the emit
+    // preparation (visible offsets) are done, i.e. while the emit kernel is still streaming
+    cudaStream_t dl_stream = nullptr;
+    cudaEvent_t ev_prep_done = nullptr;
+    bool early_ready = false;  // ev_join + ev_prep_done of the last tick are recorded
+    bool early_results_tick = false;  // CHD_TICK_EARLY_RESULTS of the tick being enqueued
     EmitUnit* d_units = nullptr;  // v5 copy-unit descriptors
     uint64_t unit_cap = 0;
     // 3 = output-ordered warp tiles (default: 0.355 ms on config #2); 5 = cell-grouped copy units with L1-resident sources
@@ -378,6 +386,8 @@ void chd_destroy(chd_engine* e) {
     if (e->h_ctr) cudaFreeHost(e->h_ctr);
     if (e->h_u32) cudaFreeHost(e->h_u32);
     if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
+    if (e->dl_stream) cudaStreamDestroy(e->dl_stream);
+    if (e->ev_prep_done) cudaEventDestroy(e->ev_prep_done);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
     if (e->ev_interest) cudaEventDestroy(e->ev_interest);
@@ -475,6 +485,12 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
     CCU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
     CCU(cudaEventCreateWithFlags(&e->ev_interest, cudaEventDisableTiming));
     CCU(cudaEventCreateWithFlags(&e->ev_pairs, cudaEventDisableTiming));
+    CCU(cudaEventCreateWithFlags(&e->ev_prep_done, cudaEventDisableTiming));
+    {
+        int lo_prio = 0, hi_prio2 = 0;
+        CCU(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio2));
+        CCU(cudaStreamCreateWithPriority(&e->dl_stream, cudaStreamNonBlocking, hi_prio2));
+    }
     CCU(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device));
 
     GridDev& g = e->g;
@@ -531,7 +547,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
          dalloc(e, &e->d_slot_query, S);
     ok = ok && dalloc(e, &e->d_new_off, (Q > P ? Q : P) + 2) && dalloc(e, &e->d_new_sub, P) && dalloc(e, &e->d_new_ch, P) && dalloc(e, &e->d_gone_sub, P) &&
          dalloc(e, &e->d_gone_ch, P);
-    ok = ok && dalloc(e, &e->d_vcnt, P) && dalloc(e, &e->d_uoff, P + 2) && dalloc(e, &e->d_units, e->unit_cap) && dalloc(e, &e->d_voff, P + 1) && dalloc(e, &e->d_first_pair, e->max_tiles + 1) &&
+    ok = ok && dalloc(e, &e->d_pair_ch, P) && dalloc(e, &e->d_vcnt, P) && dalloc(e, &e->d_uoff, P + 2) && dalloc(e, &e->d_units, e->unit_cap) && dalloc(e, &e->d_voff, P + 1) && dalloc(e, &e->d_first_pair, e->max_tiles + 1) &&
          dalloc(e, &e->d_vis_off, S + 1) && dalloc(e, &e->d_vis, L.max_visible);
     ok = ok && dalloc(e, &e->d_ring_off, C + 1) && dalloc(e, &e->d_ring_arrival, (uint64_t)L.max_ring_entries) &&
          dalloc(e, &e->d_ring_sender, (uint64_t)L.max_ring_entries) && dalloc(e, &e->d_ring_index, (uint64_t)L.max_ring_entries) &&
@@ -1065,7 +1081,8 @@ static chd_status interest_enqueue(chd_engine* e, const QueryDev& d, int part) {
     if (S) {
         interest_fill_kernel<<<blocks_for(S, 128), 128, 0, s>>>(e->g, S, slot_query, n, e->d_status, e->d_bbox, e->d_win_off, e->d_window,
                                                                 e->d_side_cell, e->d_side_dist, e->d_side_cnt, d.spot_off, prev, cur, P,
-                                                                e->d_time, DiffOut{e->d_new_sub, e->d_new_ch, e->d_gone_sub, e->d_gone_ch}, e->d_ctr);
+                                                                e->d_time, DiffOut{e->d_new_sub, e->d_new_ch, e->d_gone_sub, e->d_gone_ch}, e->d_pair_ch, e->d_ctr);
+        e->pair_ch_valid = true;
         KCHECK(e);
     }
     return CHD_OK;
@@ -1161,6 +1178,7 @@ chd_status chd_emit_visible(chd_engine* e) {
         CU(e, cudaStreamWaitEvent(s, e->wait_before_emit_kernel, 0));
         e->wait_before_emit_kernel = nullptr;
     }
+    CU(e, cudaEventRecord(e->ev_prep_done, s));  // visible offsets + counters are final; only the expanded list is still to come
     {
         StageTimer kt(e, CHD_STAGE_EMIT_KERNEL);
         if (variant == 5)
@@ -1168,7 +1186,7 @@ chd_status chd_emit_visible(chd_engine* e) {
                                                                                       e->d_sorted4, e->phase_stride, e->d_vis, e->lim.max_visible,
                                                                                       (uint32_t)e->sm_count);
         else
-            emit_visible_kernel<<<(unsigned)std::max(1, e->sm_count * e->emit_blocks_per_sm * e->emit_waves - e->emit_grid_reduce), EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4,
+            emit_visible_kernel<<<(unsigned)std::max(1, e->sm_count * e->emit_blocks_per_sm * (e->early_results_tick ? std::max(e->emit_waves, 8) : e->emit_waves) - e->emit_grid_reduce), EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4,
                                                                                    e->phase_stride, e->d_first_pair, e->d_vis, e->lim.max_visible);
         KCHECK(e);
     }
@@ -1236,11 +1254,17 @@ chd_status chd_fanout_tick(chd_engine* e, int64_t t_ns) {
     });
 }
 
+static chd_status decode_summary(chd_engine* e, chd_tick_summary* out);
+
 chd_status chd_summary(chd_engine* e, chd_tick_summary* out) {
     if (!e || !out) return CHD_ERR_INVALID;
     CU(e, cudaSetDevice(e->device));
     CU(e, cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaStreamSynchronize(e->stream));
+    return decode_summary(e, out);
+}
+
+static chd_status decode_summary(chd_engine* e, chd_tick_summary* out) {
     const Counters& c = *e->h_ctr;
     out->n_pairs = c.n_pairs; out->n_visible = c.n_visible; out->n_entities_in_world = c.n_entities_in_world;
     out->n_query_errors = c.n_query_errors; out->n_sub_new = c.n_sub_new; out->n_unsub = c.n_unsub; out->n_kept = c.n_kept;
@@ -1305,6 +1329,8 @@ static chd_status chd_tick_impl(chd_engine* e, const chd_query_batch* q, int64_t
     const bool need_build = (flags & CHD_TICK_BUILD) && (e->entities_dirty || !e->built);
     const bool do_emit = flags & CHD_TICK_EMIT;
     bool do_fanout = flags & CHD_TICK_FANOUT;
+    e->early_ready = false;
+    e->early_results_tick = (flags & CHD_TICK_EARLY_RESULTS) != 0;
     if (e->interest_pending) {
         // interest (+ fan-out) of this tick were started early with chd_begin_interest and are running on aux_stream
         if (q) {
@@ -1327,6 +1353,8 @@ static chd_status chd_tick_impl(chd_engine* e, const chd_query_batch* q, int64_t
         if (do_fanout && !e->pending_fanout) {
             st = chd_fanout_tick(e, t_ns);
             if (st != CHD_OK) return st;
+        } else {
+            e->early_ready = do_emit;  // everything but the expanded list is final at ev_join + ev_prep_done
         }
         if (out) return chd_summary(e, out);
         return CHD_OK;
@@ -1362,6 +1390,7 @@ static chd_status chd_tick_impl(chd_engine* e, const chd_query_batch* q, int64_t
             if (st != CHD_OK) return st;
         }
         CU(e, cudaStreamWaitEvent(main_stream, e->ev_join, 0));
+        e->early_ready = do_emit;
     } else {
         if (need_build) {
             st = chd_build(e);
@@ -1524,9 +1553,23 @@ chd_status chd_get_handover(chd_engine* e, uint32_t* entity, uint32_t* src_chann
 
 chd_status chd_fetch_results(chd_engine* e, const chd_result_buffers* b, chd_tick_summary* summary) {
     if (!e || !b || !summary) return CHD_ERR_INVALID;
-    chd_status st = chd_summary(e, summary);  // sync #1 (also surfaces capacity overflows)
-    if (st != CHD_OK) return st;
+    chd_status st;
     cudaStream_t s = e->stream;
+    cudaStream_t main_stream = e->stream;
+    if (e->early_ready && e->dl_stream) {
+        // The lists below are final once the aux chain (ev_join) and the emit preparation (ev_prep_done) have finished: read
+        // them back on a separate stream while the emit kernel is still writing the expanded list.
+        CU(e, cudaSetDevice(e->device));
+        s = e->dl_stream;
+        CU(e, cudaStreamWaitEvent(s, e->ev_join, 0));
+        CU(e, cudaStreamWaitEvent(s, e->ev_prep_done, 0));
+        CU(e, cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        CU(e, cudaStreamSynchronize(s));  // sync #1
+        st = decode_summary(e, summary);
+    } else {
+        st = chd_summary(e, summary);  // sync #1 (also surfaces capacity overflows)
+    }
+    if (st != CHD_OK) return st;
     PairBuf& pb = e->pairs[e->cur];
     const uint32_t S = e->n_slots;
     const uint64_t P = summary->n_pairs;
@@ -1535,10 +1578,12 @@ chd_status chd_fetch_results(chd_engine* e, const chd_result_buffers* b, chd_tic
         return CHD_ERR_CAPACITY;
     }
     if (b->pair_off) CU(e, cudaMemcpyAsync(b->pair_off, pb.off, sizeof(uint32_t) * ((uint64_t)S + 1), cudaMemcpyDefault, s));
-    if (b->pair_channel) {
-        add_const_kernel<<<blocks_for(P ? P : 1, 256), 256, 0, s>>>(pb.cell, (uint32_t)P, e->g.id_start, e->d_vcnt);
+    if (b->pair_channel && e->pair_ch_valid) {
+        CU(e, cudaMemcpyAsync(b->pair_channel, e->d_pair_ch, sizeof(uint32_t) * P, cudaMemcpyDefault, s));
+    } else if (b->pair_channel) {
+        add_const_kernel<<<blocks_for(P ? P : 1, 256), 256, 0, main_stream>>>(pb.cell, (uint32_t)P, e->g.id_start, e->d_vcnt);
         KCHECK(e);
-        CU(e, cudaMemcpyAsync(b->pair_channel, e->d_vcnt, sizeof(uint32_t) * P, cudaMemcpyDefault, s));
+        CU(e, cudaMemcpyAsync(b->pair_channel, e->d_vcnt, sizeof(uint32_t) * P, cudaMemcpyDefault, main_stream));
     }
     if (b->pair_dist) CU(e, cudaMemcpyAsync(b->pair_dist, pb.dist, sizeof(uint32_t) * P, cudaMemcpyDefault, s));
     if (b->pair_interval_ms) CU(e, cudaMemcpyAsync(b->pair_interval_ms, pb.interval, sizeof(uint32_t) * P, cudaMemcpyDefault, s));
@@ -1568,7 +1613,7 @@ chd_status chd_fetch_results(chd_engine* e, const chd_result_buffers* b, chd_tic
     if (b->vis_off) CU(e, cudaMemcpyAsync(b->vis_off, e->d_vis_off, sizeof(uint64_t) * ((uint64_t)S + 1), cudaMemcpyDefault, s));
     if (b->vis_entity) {
         if (summary->n_visible > b->vis_cap) return CHD_ERR_CAPACITY;
-        CU(e, cudaMemcpyAsync(b->vis_entity, e->d_vis, sizeof(uint32_t) * summary->n_visible, cudaMemcpyDefault, s));
+        CU(e, cudaMemcpyAsync(b->vis_entity, e->d_vis, sizeof(uint32_t) * summary->n_visible, cudaMemcpyDefault, main_stream));
     }
     if (b->cell_start) CU(e, cudaMemcpyAsync(b->cell_start, e->d_cell_start, sizeof(uint32_t) * ((uint64_t)e->g.cells + 1), cudaMemcpyDefault, s));
     if (b->sorted_entity) {
@@ -1576,6 +1621,7 @@ chd_status chd_fetch_results(chd_engine* e, const chd_result_buffers* b, chd_tic
         CU(e, cudaMemcpyAsync(b->sorted_entity, e->d_sorted_ent, sizeof(uint32_t) * (uint64_t)summary->n_entities_in_world, cudaMemcpyDefault, s));
     }
     CU(e, cudaStreamSynchronize(s));  // sync #2
+    if (s != main_stream) CU(e, cudaStreamSynchronize(main_stream));  // the tick itself (expanded list) has finished
     return CHD_OK;
 }
 

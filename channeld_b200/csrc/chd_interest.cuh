@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(128)
                          const Bbox* __restrict__ bbox, const uint64_t* __restrict__ win_off, const uint32_t* __restrict__ window,
                          const uint32_t* __restrict__ side_cell, const uint32_t* __restrict__ side_dist,
                          const uint32_t* __restrict__ side_cnt, const uint32_t* __restrict__ spot_off, PairBuf prev, PairBuf cur,
-                         uint64_t pair_cap, const int64_t* __restrict__ now_ptr, DiffOut diff, Counters* __restrict__ ctr) {
+                         uint64_t pair_cap, const int64_t* __restrict__ now_ptr, DiffOut diff, uint32_t* __restrict__ pair_channel,
+                         Counters* __restrict__ ctr) {
     __shared__ uint32_t s_warp_new[4], s_warp_gone[4], s_base_new, s_base_gone, s_kept;
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(128)
             const uint32_t interval = damping_interval_ms(d, g.default_interval_ms);  // message_spatial.go:65-80
             cur.sub[o] = s;
             cur.cell[o] = c;
+            pair_channel[o] = c + g.id_start;  // host-facing copy (chd_fetch_results reads it back without a conversion pass)
             cur.dist[o] = d;
             cur.interval[o] = interval;
             if (pp < pe && prev.cell[pp] == c) {
@@ -173,6 +175,7 @@ __global__ void __launch_bounds__(128)
         for (; pp < pe; pp++, o++) {
             cur.sub[o] = s;
             cur.cell[o] = prev.cell[pp];
+            pair_channel[o] = prev.cell[pp] + g.id_start;
             cur.dist[o] = prev.dist[pp];
             cur.interval[o] = prev.interval[pp];
             cur.flags[o] = prev.flags[pp] & ~PF_NEW;

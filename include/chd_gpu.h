@@ -217,7 +217,13 @@ chd_status chd_summary(chd_engine* e, chd_tick_summary* out);
 /* ---- Channel.Tick for all spatial channels (channel.go:358-387), batched: build (if entities changed) ->
  * update_interest(q) (if q != NULL) -> emit_visible (flags & CHD_TICK_EMIT) -> fanout_tick(t_ns)
  * (flags & CHD_TICK_FANOUT) -> summary.  One stream, no intermediate host sync. */
-enum { CHD_TICK_BUILD = 1, CHD_TICK_EMIT = 2, CHD_TICK_FANOUT = 4, CHD_TICK_ALL = 7 };
+enum {
+    CHD_TICK_BUILD = 1, CHD_TICK_EMIT = 2, CHD_TICK_FANOUT = 4, CHD_TICK_ALL = 7,
+    /* The host will read this tick's results back (chd_fetch_results): schedule the expanded-list kernel in waves so the
+     * fan-out / interest results complete, and can be copied to the host, while it is still running.  Costs ~2 % of
+     * device time per tick; results are identical. */
+    CHD_TICK_EARLY_RESULTS = 8
+};
 /* Optional early start: the interest update (and the fan-out pass when with_fanout != 0) do not depend on the entity
  * positions, so a host can start them as soon as the tick's queries and rings are known — on the engine's second
  * stream — and then upload / exchange positions; the following chd_tick(e, NULL, t_ns, flags, ..) runs build + emit

@@ -519,8 +519,10 @@ def test_graph_replay_matches_direct_and_oracle(chd, oracle):
     assert sum(r[0]["n_due"] for r in results[True]) > 1000 and sum(r[0]["n_handover"] for r in results[True]) > 100
 
 
-def test_fetch_results_matches_getters(chd):
-    """chd_fetch_results (one call, two syncs) returns exactly what the individual getters return."""
+@pytest.mark.parametrize("early", [False, True])
+def test_fetch_results_matches_getters(chd, early):
+    """chd_fetch_results (one call) returns exactly what the individual getters return, also when the read-back runs
+    on its own stream while the expanded-list kernel is still in flight (CHD_TICK_EARLY_RESULTS)."""
     import ctypes as C
 
     wc = chd.synth.scaled(chd.synth.CONFIGS["benchmark"], 20_000, 2_000)
@@ -539,7 +541,7 @@ def test_fetch_results_matches_getters(chd):
         batch, keep = chd.engine.make_batch(len(cx), sub=np.arange(len(cx), dtype=np.uint32), sphere=(cq, cz, r))
         ring_state, off, arr, snd, idx, cmi = chd.synth.update_rings(wc, tick, t, 33_000_000, 4, len(conn), ring_len=16, state=ring_state)
         e.set_rings(off, arr, snd, idx, cmi)
-        e.tick(batch, t, chd.capi.TICK_ALL, want_summary=False)
+        e.tick(batch, t, chd.capi.TICK_ALL | (chd.capi.TICK_EARLY_RESULTS if early else 0), want_summary=False)
         S, cap = len(conn), 1 << 16
         bufs = {k: np.zeros(cap, np.uint32) for k in ("ch", "dist", "iv", "ns", "nc", "us", "uc", "he", "hs", "hd", "st", "se")}
         poff, voff = np.zeros(S + 1, np.uint32), np.zeros(S + 1, np.uint64)
