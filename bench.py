@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--expanded-steps", type=int, default=2, help="extra e2e steps that also copy the expanded list to the host")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gate", action="store_true")
+    ap.add_argument("--trace-e2e", action="store_true", help="diagnostics: host-side phase times of the pipelined e2e step on stderr")
     ap.add_argument("--no-early", action="store_true", help="e2e ticks without CHD_TICK_EARLY_RESULTS")
     ap.add_argument("--updates-per-cell", type=int, default=8)
     ap.add_argument("--ring-len", type=int, default=64)
@@ -427,6 +428,14 @@ def run_ours(args):
         rb.vis_off = capi.ptr(r_voff)
         r_vis_keep = []
 
+        phase_acc = {}
+
+        def prefetch_inputs(i):
+            dn, rn = host_in[i % 2], rings_host[i]
+            ck(L.chd_prefetch_rings(e.h, capi.ptr(rn["off"]), rn["n"], capi.ptr(rn["arr"]), capi.ptr(rn["snd"]), capi.ptr(rn["idx"]), capi.ptr(rn["cmi"])))
+            ck(L.chd_prefetch_queries(e.h, C.byref(batches_host[i % 2])))
+            ck(L.chd_prefetch_entities(e.h, capi.ptr(dn["x"]), capi.ptr(dn["z"]), n_own))
+
         def e2e_step(i, expanded=False, pipelined=False, early=not args.no_early):
             """Host inputs -> H2D -> one batched tick -> D2H of everything a channeld host consumes (chd_fetch_results).
             pipelined: the positions of step i were uploaded with chd_prefetch_entities while step i-1 ran, and this step
@@ -435,27 +444,34 @@ def run_ours(args):
             d = host_in[i % 2]
             rg = rings_host[i]
             t_ns = (i + 1) * TICK_NS
-            ck(L.chd_set_rings(e.h, capi.ptr(rg["off"]), rg["n"], capi.ptr(rg["arr"]), capi.ptr(rg["snd"]), capi.ptr(rg["idx"]), capi.ptr(rg["cmi"])))
-            # queries + rings go up first and the interest / fan-out stages start on the second stream while the
-            # (much larger) position upload is still in flight
-            ck(L.chd_begin_interest(e.h, C.byref(batches_host[i % 2]), t_ns, 1))
+            tp0 = time.perf_counter()
             if pipelined:
-                ck(L.chd_adopt_prefetched(e.h))
+                ck(L.chd_adopt_prefetched(e.h))  # rings + queries + positions of this step went up during the previous one
+                ck(L.chd_begin_interest(e.h, None, t_ns, 1))
             else:
+                ck(L.chd_set_rings(e.h, capi.ptr(rg["off"]), rg["n"], capi.ptr(rg["arr"]), capi.ptr(rg["snd"]), capi.ptr(rg["idx"]), capi.ptr(rg["cmi"])))
+                # queries + rings go up first and the interest / fan-out stages start on the second stream while the
+                # (much larger) position upload is still in flight
+                ck(L.chd_begin_interest(e.h, C.byref(batches_host[i % 2]), t_ns, 1))
                 ck(L.chd_set_entities(e.h, capi.ptr(d["x"]), capi.ptr(d["z"]), n_own))
             if world > 1:
                 e.export_border(rec_local, border_cap, want_count=False)  # also pads the buffer
                 dist.all_gather_into_tensor(rec_all, rec_local)
                 e.import_halo(rec_all, border_cap * world, rank * border_cap, border_cap)
             ck(L.chd_tick(e.h, None, t_ns, capi.TICK_ALL | (capi.TICK_EARLY_RESULTS if early else 0), None))
-            if pipelined:  # next step's positions go up while this tick's kernels run
-                dn = host_in[(i + 1) % 2]
-                ck(L.chd_prefetch_entities(e.h, capi.ptr(dn["x"]), capi.ptr(dn["z"]), n_own))
+            tp1 = time.perf_counter()
+            if pipelined:  # the next step's inputs go up while this tick's kernels run
+                prefetch_inputs(i + 1)
+            tp2 = time.perf_counter()
             if expanded:
                 rb.vis_entity, rb.vis_cap = capi.ptr(r_vis_keep[0]), r_vis_keep[0].numel()
             else:
                 rb.vis_entity, rb.vis_cap = None, 0
             ck(L.chd_fetch_results(e.h, C.byref(rb), C.byref(summ)))
+            tp3 = time.perf_counter()
+            for k_, v_ in (("launch", tp1 - tp0), ("prefetch", tp2 - tp1), ("fetch", tp3 - tp2)):
+                phase_acc[k_] = phase_acc.get(k_, 0.0) + v_
+            phase_acc["n"] = phase_acc.get("n", 0) + 1
             h2d = 16 * n_own + 24 * S + (wc.cells + 1) * 4 + rg["n"] * 20 + wc.cells * 8
             d2h = (C.sizeof(capi.TickSummary) + (S + 1) * 4 + 12 * int(summ.n_pairs) + 8 * (int(summ.n_sub_new) + int(summ.n_unsub))
                    + 48 * int(summ.n_due) + 12 * int(summ.n_handover) + 4 * S + (S + 1) * 8 + (4 * int(summ.n_visible) if expanded else 0))
@@ -474,18 +490,25 @@ def run_ours(args):
         e2e_serial_dt = time.perf_counter() - t0
         # pipelined form: same work per step, the position upload of step i+1 overlaps the kernels of step i
         base += 2 + n_e2e
-        d0 = host_in[base % 2]
-        ck(L.chd_prefetch_entities(e.h, capi.ptr(d0["x"]), capi.ptr(d0["z"]), n_own))
+        prefetch_inputs(base)
         for i in range(2):
             e2e_step(base + i, pipelined=True)
         barrier()
         torch.cuda.synchronize()
+        phase_acc.clear()
+        if args.trace_e2e:
+            e.profile_enable(False)  # also resets the CHD_TRACE_FETCH accumulators
         t0 = time.perf_counter()
         for i in range(n_e2e):
             h2d, d2h = e2e_step(base + 2 + i, pipelined=True)
         torch.cuda.synchronize()
         barrier()
         e2e_dt = time.perf_counter() - t0
+        if args.trace_e2e and rank == 0:
+            n_ = max(phase_acc.get("n", 1), 1)
+            e.close()
+            print("[bench] pipelined e2e step, host view (us): " + ", ".join("%s %.1f" % (k_, phase_acc[k_] / n_ * 1e6)
+                                                                              for k_ in ("launch", "prefetch", "fetch")), file=sys.stderr)
         e2e_exp = None
         if args.expanded_steps > 0 and world == 1:
             r_vis_keep.append(pinned((int(sm.n_visible) + (1 << 20),), torch.int32)[0])
@@ -542,9 +565,10 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": S_total * n_e2e / e2e_dt, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_dt / n_e2e * 1e3,
-                    "pipeline": "double-buffered inputs: chd_prefetch_entities uploads the positions of step i+1 (pinned host memory) while the "
-                                "kernels of step i run; every step still uploads one full position snapshot + its queries + rings and reads "
-                                "back its results inside the timed region",
+                    "pipeline": "double-buffered inputs: chd_prefetch_{rings,queries,entities} upload the inputs of step i+1 (pinned host memory) "
+                                "while the kernels of step i run; every step still uploads one full position snapshot + its queries + rings and "
+                                "reads back its results inside the timed region; chd_fetch_results copies on its own stream while the "
+                                "expanded-list kernel is still running (CHD_TICK_EARLY_RESULTS)",
                     "serial": {"value": S_total * n_e2e / e2e_serial_dt, "ms_per_step": e2e_serial_dt / n_e2e * 1e3,
                                "note": "no overlap between steps: upload -> tick -> read-back, one after the other (per-tick latency)"},
                     "result": "chd_fetch_results: summary + (cell,dist,interval) pairs + sub/unsub lists + fan-out due list + handover "

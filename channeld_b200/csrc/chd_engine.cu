@@ -3,6 +3,7 @@
 // chd_summary / the chd_get_* copies — never synchronises with the host.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -48,7 +49,7 @@ struct chd_engine {
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_interest = nullptr, ev_pairs = nullptr;
     bool interest_pending = false, pending_fanout = false;  // chd_begin_interest issued, not yet joined by chd_tick
-    GraphSlot g_build[4], g_interest[2], g_interest_b[2], g_emit_prep[2], g_fanout[2], g_export[4], g_import[2];  // build / export: [key buffer][position buffer]
+    GraphSlot g_build[4], g_interest[4], g_interest_b[4], g_emit_prep[2], g_fanout[4], g_export[4], g_import[2];  // build / export: [key buffer][position buffer]
     uint64_t graph_launches = 0, graph_captures = 0;
     uint32_t* d_key_a = nullptr;  // identity of the first key buffer (graph slot selection)
     int64_t* d_time = nullptr;      // [0] = now_ns of the last update_interest, [1] = t_ns of the last fanout_tick
@@ -99,11 +100,30 @@ struct chd_engine {
     PairBuf pairs[2];
     int cur = 0;
     // ---- query scratch
-    struct {
+    struct QStage {
         uint32_t *sub; uint8_t* kind;
         double *sph_cx, *sph_cz, *sph_r, *box_cx, *box_cz, *box_ex, *box_ez, *cone_cx, *cone_cz, *cone_dx, *cone_dz, *cone_angle, *cone_r;
         uint32_t *spot_off, *spot_ndist; double *spot_x, *spot_z; uint32_t* spot_dist;
     } dq{};
+    // chd_prefetch_queries / chd_prefetch_rings: two dedicated staging sets each (allocated on first use), filled on
+    // up_stream while a tick is in flight and handed to the next tick by chd_adopt_prefetched
+    QStage dq_pf[2] = {};
+    bool dq_pf_alloc[2] = {false, false};
+    int q_next = 0;                       // set the next chd_prefetch_queries fills
+    bool staged_q = false, have_adopted_q = false, wait_q = false;
+    int staged_q_set = 0, adopted_q_set = 0;
+    QueryDev staged_qd{}, adopted_qd{};
+    cudaEvent_t ev_upload_q = nullptr, ev_q_read[2] = {nullptr, nullptr};
+    bool q_read_recorded[2] = {false, false};
+    struct RStage {
+        uint32_t *off, *sender; int64_t* arrival; uint64_t *index, *cmi;
+    } ring_pf[2] = {};
+    bool ring_pf_alloc[2] = {false, false};
+    int ring_next = 0, staged_ring_set = 0, ring_set = -1;  // ring_set: prefetch set the current ring pointers refer to (-1: none)
+    bool staged_rings = false, staged_ring_cmi = false, wait_rings = false;
+    uint32_t staged_ring_total = 0;
+    cudaEvent_t ev_upload_rings = nullptr, ev_ring_read[2] = {nullptr, nullptr};
+    bool ring_read_recorded[2] = {false, false};
     Bbox* d_bbox = nullptr;
     uint32_t *d_win_size = nullptr, *d_window = nullptr, *d_side_cell = nullptr, *d_side_dist = nullptr, *d_side_cnt = nullptr;
     uint64_t* d_win_off = nullptr;
@@ -121,9 +141,13 @@ struct chd_engine {
     bool pair_ch_valid = false;
     // chd_fetch_results reads back on its own stream as soon as the aux chain (pairs, diff, due list) and the emit
     // preparation (visible offsets) are done, i.e. while the emit kernel is still streaming
-    cudaStream_t dl_stream = nullptr;
-    cudaEvent_t ev_prep_done = nullptr;
+    cudaStream_t dl_stream = nullptr, dl_stream_b = nullptr;  // phase A / phase B of the early read-back
+    cudaEvent_t ev_prep_done = nullptr, ev_build_done = nullptr;
+    bool build_done_recorded = false;  // this tick ran a build (its end is ev_build_done)
     bool early_ready = false;  // ev_join + ev_prep_done of the last tick are recorded
+    bool trace_fetch = false;  // CHD_TRACE_FETCH=1: host-side phase times of chd_fetch_results, printed by chd_destroy
+    double fetch_t[4] = {0, 0, 0, 0};
+    uint64_t fetch_n = 0;
     bool early_results_tick = false;  // CHD_TICK_EARLY_RESULTS of the tick being enqueued
     EmitUnit* d_units = nullptr;  // v5 copy-unit descriptors
     uint64_t unit_cap = 0;
@@ -140,6 +164,10 @@ struct chd_engine {
     // Where the aux chain (interest part 1 + fan-out) is joined: before the emit kernel (it then never competes with the
     // saturating emit kernel for SM slots) or after it (overlap).  Measured: profiles/README.md.
     bool join_before_emit = false;
+    // CHD_TICK_EARLY_RESULTS strategy (CHD_EARLY_MODE): 1 = emit kernel after the aux chain, 0 = emit in waves,
+    // 2 = emit grid short of `early_reduce` CTAs so the aux chain finds free SM slots next to it (CHD_EARLY_REDUCE)
+    int early_mode = 1;
+    int early_reduce = 32;
     cudaEvent_t wait_before_emit_kernel = nullptr;  // 4 x 256 threads x 64 registers fill an SM; 3 leaves room for the aux-stream kernels
     uint64_t *d_voff = nullptr, *d_vis_off = nullptr;
     uint64_t max_tiles = 0;
@@ -162,6 +190,9 @@ struct chd_engine {
     // border export scratch
     uint32_t *d_bflag = nullptr, *d_boff = nullptr;
     uint32_t* h_u32 = nullptr;  // pinned scalar
+    // scratch of the tick driver's getters (chd_get_visible*, export counts): separate from h_u32, which the stateless entry
+    // points use under the engine mutex from other threads
+    uint32_t* h_get = nullptr;
 
     bool fail(const char* fmt, ...) const {
         char buf[512];
@@ -289,6 +320,9 @@ static chd_status run_stage(chd_engine* e, chd_engine::GraphSlot& slot, uint64_t
         slot.exec = nullptr;
     }
     const uint64_t l0 = e->n_launch;
+    // Stateless entry points (chd_cell_of, chd_query_channel_ids) may be called from other threads and launch into the same
+    // stream: they hold the engine mutex for their whole call, so taking it here keeps their work out of the capture.
+    std::lock_guard<std::recursive_mutex> capture_lock(e->mu);
     CU(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
     chd_status st = enqueue();
     cudaGraph_t g = nullptr;
@@ -361,16 +395,22 @@ void chd_free_pinned(void* p) {
 
 void chd_destroy(chd_engine* e) {
     if (!e) return;
+    if (e->trace_fetch && e->fetch_n)
+        fprintf(stderr, "[chd] fetch_results x%llu: phase-A ready %.1f us, phase A+B enqueue (incl. wait for B) %.1f us, copies done %.1f us, tick done %.1f us\n",
+                (unsigned long long)e->fetch_n, e->fetch_t[0] / e->fetch_n, e->fetch_t[1] / e->fetch_n, e->fetch_t[2] / e->fetch_n,
+                e->fetch_t[3] / e->fetch_n);
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->up_stream) cudaStreamSynchronize(e->up_stream);
     for (void* p : e->allocs) cudaFree(p);
-    for (auto* arr : {e->g_interest, e->g_interest_b, e->g_emit_prep, e->g_fanout, e->g_import})
+    for (auto* arr : {e->g_emit_prep, e->g_import})
         for (int i = 0; i < 2; i++)
             if (arr[i].exec) cudaGraphExecDestroy(arr[i].exec);
-    for (auto* arr : {e->g_build, e->g_export})
+    for (auto* arr : {e->g_build, e->g_export, e->g_interest, e->g_interest_b, e->g_fanout})
         for (int i = 0; i < 4; i++)
             if (arr[i].exec) cudaGraphExecDestroy(arr[i].exec);
+    for (cudaEvent_t ev : {e->ev_upload_q, e->ev_q_read[0], e->ev_q_read[1], e->ev_upload_rings, e->ev_ring_read[0], e->ev_ring_read[1]})
+        if (ev) cudaEventDestroy(ev);
     if (e->up_stream) {
         cudaStreamSynchronize(e->up_stream);
         cudaStreamDestroy(e->up_stream);
@@ -385,9 +425,12 @@ void chd_destroy(chd_engine* e) {
     }
     if (e->h_ctr) cudaFreeHost(e->h_ctr);
     if (e->h_u32) cudaFreeHost(e->h_u32);
+    if (e->h_get) cudaFreeHost(e->h_get);
     if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
     if (e->dl_stream) cudaStreamDestroy(e->dl_stream);
+    if (e->dl_stream_b) cudaStreamDestroy(e->dl_stream_b);
     if (e->ev_prep_done) cudaEventDestroy(e->ev_prep_done);
+    if (e->ev_build_done) cudaEventDestroy(e->ev_build_done);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
     if (e->ev_interest) cudaEventDestroy(e->ev_interest);
@@ -459,8 +502,11 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
     }
     e->device = device;
     if (const char* v = getenv("CHD_JOIN_BEFORE_EMIT")) e->join_before_emit = atoi(v) != 0;
+    if (const char* v = getenv("CHD_EARLY_MODE")) e->early_mode = atoi(v) >= 0 && atoi(v) <= 2 ? atoi(v) : 1;
+    if (const char* v = getenv("CHD_EARLY_REDUCE")) e->early_reduce = atoi(v) >= 0 && atoi(v) < 400 ? atoi(v) : 32;
     if (const char* v = getenv("CHD_EMIT_GRID_REDUCE")) e->emit_grid_reduce = atoi(v) >= 0 && atoi(v) < 400 ? atoi(v) : 0;
     if (const char* v = getenv("CHD_EMIT_BPS")) e->emit_blocks_per_sm = atoi(v) >= 1 && atoi(v) <= 4 ? atoi(v) : 4;
+    if (const char* v = getenv("CHD_TRACE_FETCH")) e->trace_fetch = atoi(v) != 0;
     if (const char* v = getenv("CHD_EMIT_WAVES")) e->emit_waves = atoi(v) >= 1 && atoi(v) <= 64 ? atoi(v) : 1;
     if (const char* v = getenv("CHD_EMIT_VARIANT")) e->emit_variant = atoi(v) == 5 ? 5 : 3;
 #define CCU(call)                                                                       \
@@ -486,10 +532,12 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
     CCU(cudaEventCreateWithFlags(&e->ev_interest, cudaEventDisableTiming));
     CCU(cudaEventCreateWithFlags(&e->ev_pairs, cudaEventDisableTiming));
     CCU(cudaEventCreateWithFlags(&e->ev_prep_done, cudaEventDisableTiming));
+    CCU(cudaEventCreateWithFlags(&e->ev_build_done, cudaEventDisableTiming));
     {
         int lo_prio = 0, hi_prio2 = 0;
         CCU(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio2));
         CCU(cudaStreamCreateWithPriority(&e->dl_stream, cudaStreamNonBlocking, hi_prio2));
+        CCU(cudaStreamCreateWithPriority(&e->dl_stream_b, cudaStreamNonBlocking, hi_prio2));
     }
     CCU(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device));
 
@@ -567,6 +615,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
         site->error = &e->d_ctr->overflow;
     CCU(cudaHostAlloc((void**)&e->h_ctr, sizeof(Counters), cudaHostAllocDefault));
     CCU(cudaHostAlloc((void**)&e->h_u32, 64, cudaHostAllocDefault));
+    CCU(cudaHostAlloc((void**)&e->h_get, 64, cudaHostAllocDefault));
     CCU(cudaMemsetAsync(e->d_ctr, 0, sizeof(Counters), e->stream));
     CCU(cudaMemsetAsync(e->d_time, 0, 16, e->stream));
     CCU(cudaMemsetAsync(e->d_ring_total, 0, 4, e->stream));
@@ -656,6 +705,10 @@ chd_status chd_set_entities(chd_engine* e, const double* x, const double* z, uin
     return CHD_OK;
 }
 
+static chd_status ensure_upload_stream(chd_engine* e);
+static chd_status upload_queries(chd_engine* e, const chd_query_batch* q, QueryDev* out, bool need_sub, chd_engine::QStage* stage = nullptr,
+                                 cudaStream_t on_stream = nullptr);
+
 chd_status chd_prefetch_entities(chd_engine* e, const double* x, const double* z, uint32_t n) {
     if (!e || (n && (!x || !z))) return CHD_ERR_INVALID;
     if (n > e->lim.max_entities) {
@@ -664,11 +717,9 @@ chd_status chd_prefetch_entities(chd_engine* e, const double* x, const double* z
     }
     CU(e, cudaSetDevice(e->device));
     const int back = e->pos_buf ^ 1;
-    if (!e->up_stream) {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        CU(e, cudaStreamCreateWithPriority(&e->up_stream, cudaStreamNonBlocking, hi));
-        CU(e, cudaEventCreateWithFlags(&e->ev_upload, cudaEventDisableTiming));
+    {
+        chd_status st = ensure_upload_stream(e);
+        if (st != CHD_OK) return st;
     }
     if (!e->d_xb[back]) {  // the second pair of position buffers exists only for hosts that prefetch
         if (!dalloc(e, &e->d_xb[back], e->lim.max_entities) || !dalloc(e, &e->d_zb[back], e->lim.max_entities)) return CHD_ERR_CUDA;
@@ -683,13 +734,116 @@ chd_status chd_prefetch_entities(chd_engine* e, const double* x, const double* z
     return CHD_OK;
 }
 
+static chd_status ensure_upload_stream(chd_engine* e) {
+    if (e->up_stream) return CHD_OK;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    CU(e, cudaStreamCreateWithPriority(&e->up_stream, cudaStreamNonBlocking, hi));
+    CU(e, cudaEventCreateWithFlags(&e->ev_upload, cudaEventDisableTiming));
+    CU(e, cudaEventCreateWithFlags(&e->ev_upload_q, cudaEventDisableTiming));
+    CU(e, cudaEventCreateWithFlags(&e->ev_upload_rings, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) {
+        CU(e, cudaEventCreateWithFlags(&e->ev_q_read[i], cudaEventDisableTiming));
+        CU(e, cudaEventCreateWithFlags(&e->ev_ring_read[i], cudaEventDisableTiming));
+    }
+    return CHD_OK;
+}
+
+chd_status chd_prefetch_queries(chd_engine* e, const chd_query_batch* q) {
+    if (!e || !q) return CHD_ERR_INVALID;
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
+    CU(e, cudaSetDevice(e->device));
+    chd_status st = ensure_upload_stream(e);
+    if (st != CHD_OK) return st;
+    const int set = e->q_next;
+    chd_engine::QStage& qs = e->dq_pf[set];
+    if (!e->dq_pf_alloc[set]) {
+        const uint64_t Q = e->lim.max_queries;
+        const bool ok = dalloc(e, &qs.sub, Q) && dalloc(e, &qs.kind, Q) && dalloc(e, &qs.sph_cx, Q) && dalloc(e, &qs.sph_cz, Q) && dalloc(e, &qs.sph_r, Q) &&
+                        dalloc(e, &qs.box_cx, Q) && dalloc(e, &qs.box_cz, Q) && dalloc(e, &qs.box_ex, Q) && dalloc(e, &qs.box_ez, Q) &&
+                        dalloc(e, &qs.cone_cx, Q) && dalloc(e, &qs.cone_cz, Q) && dalloc(e, &qs.cone_dx, Q) && dalloc(e, &qs.cone_dz, Q) &&
+                        dalloc(e, &qs.cone_angle, Q) && dalloc(e, &qs.cone_r, Q) && dalloc(e, &qs.spot_off, Q + 1) && dalloc(e, &qs.spot_ndist, Q) &&
+                        dalloc(e, &qs.spot_x, (uint64_t)e->lim.max_spots) && dalloc(e, &qs.spot_z, (uint64_t)e->lim.max_spots) &&
+                        dalloc(e, &qs.spot_dist, (uint64_t)e->lim.max_spots);
+        if (!ok) return CHD_ERR_CUDA;
+        e->dq_pf_alloc[set] = true;
+    }
+    if (e->q_read_recorded[set]) CU(e, cudaStreamWaitEvent(e->up_stream, e->ev_q_read[set], 0));  // its previous batch has been consumed
+    QueryDev d;
+    st = upload_queries(e, q, &d, true, &qs, e->up_stream);
+    if (st != CHD_OK) return st;
+    CU(e, cudaEventRecord(e->ev_upload_q, e->up_stream));
+    e->staged_qd = d;
+    e->staged_q_set = set;
+    e->staged_q = true;
+    e->q_next = set ^ 1;
+    return CHD_OK;
+}
+
+chd_status chd_prefetch_rings(chd_engine* e, const uint32_t* ring_off, uint32_t n_entries, const int64_t* arrival, const uint32_t* sender,
+                              const uint64_t* index, const uint64_t* ch_msg_index) {
+    if (!e || !ring_off) return CHD_ERR_INVALID;
+    if (n_entries > e->lim.max_ring_entries) {
+        e->fail("%u ring entries > max_ring_entries %u", n_entries, e->lim.max_ring_entries);
+        return CHD_ERR_CAPACITY;
+    }
+    if (n_entries && (!arrival || !sender || !index)) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    chd_status st = ensure_upload_stream(e);
+    if (st != CHD_OK) return st;
+    const int set = e->ring_next;
+    chd_engine::RStage& r = e->ring_pf[set];
+    const uint64_t C = e->g.cells;
+    if (!e->ring_pf_alloc[set]) {
+        const uint64_t R = e->lim.max_ring_entries;
+        if (!(dalloc(e, &r.off, C + 1) && dalloc(e, &r.arrival, R) && dalloc(e, &r.sender, R) && dalloc(e, &r.index, R) && dalloc(e, &r.cmi, C)))
+            return CHD_ERR_CUDA;
+        e->ring_pf_alloc[set] = true;
+    }
+    if (e->ring_read_recorded[set]) CU(e, cudaStreamWaitEvent(e->up_stream, e->ev_ring_read[set], 0));
+    cudaStream_t us = e->up_stream;
+    CU(e, cudaMemcpyAsync(r.off, ring_off, sizeof(uint32_t) * (C + 1), cudaMemcpyDefault, us));
+    if (n_entries) {
+        CU(e, cudaMemcpyAsync(r.arrival, arrival, sizeof(int64_t) * n_entries, cudaMemcpyDefault, us));
+        CU(e, cudaMemcpyAsync(r.sender, sender, sizeof(uint32_t) * n_entries, cudaMemcpyDefault, us));
+        CU(e, cudaMemcpyAsync(r.index, index, sizeof(uint64_t) * n_entries, cudaMemcpyDefault, us));
+    }
+    if (ch_msg_index) CU(e, cudaMemcpyAsync(r.cmi, ch_msg_index, sizeof(uint64_t) * C, cudaMemcpyDefault, us));
+    CU(e, cudaEventRecord(e->ev_upload_rings, us));
+    e->staged_rings = true;
+    e->staged_ring_set = set;
+    e->staged_ring_total = n_entries;
+    e->staged_ring_cmi = ch_msg_index != nullptr;
+    e->ring_next = set ^ 1;
+    return CHD_OK;
+}
+
 chd_status chd_adopt_prefetched(chd_engine* e) {
     if (!e) return CHD_ERR_INVALID;
-    if (!e->staged) {
-        e->fail("chd_adopt_prefetched without a preceding chd_prefetch_entities");
+    if (!e->staged && !e->staged_q && !e->staged_rings) {
+        e->fail("chd_adopt_prefetched without a preceding chd_prefetch_entities / chd_prefetch_queries / chd_prefetch_rings");
         return CHD_ERR_STATE;
     }
     CU(e, cudaSetDevice(e->device));
+    if (e->staged_q) {  // consumed by the next chd_begin_interest / chd_update_interest called with q == NULL
+        e->adopted_qd = e->staged_qd;
+        e->adopted_q_set = e->staged_q_set;
+        e->have_adopted_q = true;
+        e->wait_q = true;
+        e->staged_q = false;
+    }
+    if (e->staged_rings) {
+        const chd_engine::RStage& r = e->ring_pf[e->staged_ring_set];
+        e->ring_off_p = r.off; e->ring_arrival_p = r.arrival; e->ring_sender_p = r.sender; e->ring_index_p = r.index;
+        e->ch_msg_index_p = e->staged_ring_cmi ? r.cmi : nullptr;
+        e->have_ch_msg_index = e->staged_ring_cmi;
+        e->ring_set = e->staged_ring_set;
+        e->wait_rings = true;
+        e->staged_rings = false;
+        set_u32_kernel<<<1, 1, 0, e->stream>>>(e->d_ring_total, e->staged_ring_total);
+        KCHECK(e);
+    }
+    if (!e->staged) return CHD_OK;
     CU(e, cudaStreamWaitEvent(e->stream, e->ev_upload, 0));
     e->pos_buf ^= 1;
     e->d_x = e->d_xb[e->pos_buf];
@@ -923,8 +1077,10 @@ chd_status chd_set_subscribers(chd_engine* e, const uint32_t* conn_id, uint32_t 
 }
 
 // copies the batch into the engine's device SoA and returns the device view
-static chd_status upload_queries(chd_engine* e, const chd_query_batch* q, QueryDev* out, bool need_sub) {
+static chd_status upload_queries(chd_engine* e, const chd_query_batch* q, QueryDev* out, bool need_sub, chd_engine::QStage* stage,
+                                 cudaStream_t on_stream) {
     if (!q) return CHD_ERR_INVALID;
+    chd_engine::QStage& dq = stage ? *stage : e->dq;
     const uint32_t n = q->n;
     if (n > e->lim.max_queries) {
         e->fail("query batch of %u > max_queries %u", n, e->lim.max_queries);
@@ -932,14 +1088,14 @@ static chd_status upload_queries(chd_engine* e, const chd_query_batch* q, QueryD
     }
     QueryDev d{};
     d.n = n;
-    cudaStream_t st = e->stream;
+    cudaStream_t st = stage ? on_stream : e->stream;
 #define UP(field, T)                                                                                      \
     if (q->field) {                                                                                       \
         if (is_device_ptr(e, q->field)) {                                                                 \
             d.field = q->field; /* device-resident batch: consumed in place */                            \
         } else {                                                                                          \
-            CU(e, cudaMemcpyAsync(e->dq.field, q->field, sizeof(T) * n, cudaMemcpyDefault, st));          \
-            d.field = e->dq.field;                                                                        \
+            CU(e, cudaMemcpyAsync(dq.field, q->field, sizeof(T) * n, cudaMemcpyDefault, st));          \
+            d.field = dq.field;                                                                        \
         }                                                                                                 \
     }
     if (need_sub) {
@@ -962,8 +1118,8 @@ static chd_status upload_queries(chd_engine* e, const chd_query_batch* q, QueryD
     if (q->spot_off) {
         // spot_off may live on the host or on the device; its last element sizes the spot arrays
         uint32_t total = 0;
-        CU(e, cudaMemcpyAsync(e->dq.spot_off, q->spot_off, sizeof(uint32_t) * ((uint64_t)n + 1), cudaMemcpyDefault, st));
-        CU(e, cudaMemcpyAsync(e->h_u32, e->dq.spot_off + n, 4, cudaMemcpyDeviceToHost, st));
+        CU(e, cudaMemcpyAsync(dq.spot_off, q->spot_off, sizeof(uint32_t) * ((uint64_t)n + 1), cudaMemcpyDefault, st));
+        CU(e, cudaMemcpyAsync(e->h_u32, dq.spot_off + n, 4, cudaMemcpyDeviceToHost, st));
         CU(e, cudaStreamSynchronize(st));
         total = *e->h_u32;
         if (total > e->lim.max_spots) {
@@ -971,14 +1127,14 @@ static chd_status upload_queries(chd_engine* e, const chd_query_batch* q, QueryD
             return CHD_ERR_CAPACITY;
         }
         if (total && (!q->spot_x || !q->spot_z)) return CHD_ERR_INVALID;
-        CU(e, cudaMemcpyAsync(e->dq.spot_x, q->spot_x, sizeof(double) * total, cudaMemcpyDefault, st));
-        CU(e, cudaMemcpyAsync(e->dq.spot_z, q->spot_z, sizeof(double) * total, cudaMemcpyDefault, st));
-        if (q->spot_dist) CU(e, cudaMemcpyAsync(e->dq.spot_dist, q->spot_dist, sizeof(uint32_t) * total, cudaMemcpyDefault, st));
-        else CU(e, cudaMemsetAsync(e->dq.spot_dist, 0, sizeof(uint32_t) * total, st));
-        d.spot_off = e->dq.spot_off; d.spot_x = e->dq.spot_x; d.spot_z = e->dq.spot_z; d.spot_dist = e->dq.spot_dist;
+        CU(e, cudaMemcpyAsync(dq.spot_x, q->spot_x, sizeof(double) * total, cudaMemcpyDefault, st));
+        CU(e, cudaMemcpyAsync(dq.spot_z, q->spot_z, sizeof(double) * total, cudaMemcpyDefault, st));
+        if (q->spot_dist) CU(e, cudaMemcpyAsync(dq.spot_dist, q->spot_dist, sizeof(uint32_t) * total, cudaMemcpyDefault, st));
+        else CU(e, cudaMemsetAsync(dq.spot_dist, 0, sizeof(uint32_t) * total, st));
+        d.spot_off = dq.spot_off; d.spot_x = dq.spot_x; d.spot_z = dq.spot_z; d.spot_dist = dq.spot_dist;
         if (!q->spot_ndist) {
-            CU(e, cudaMemsetAsync(e->dq.spot_ndist, 0, sizeof(uint32_t) * n, st));
-            d.spot_ndist = e->dq.spot_ndist;
+            CU(e, cudaMemsetAsync(dq.spot_ndist, 0, sizeof(uint32_t) * n, st));
+            d.spot_ndist = dq.spot_ndist;
         }
     }
     *out = d;
@@ -1117,13 +1273,34 @@ static chd_status interest_enqueue(chd_engine* e, const QueryDev& d, int part) {
 }
 
 chd_status chd_update_interest(chd_engine* e, const chd_query_batch* q, int64_t now_ns) {
-    if (!e || !q) return CHD_ERR_INVALID;
+    if (!e) return CHD_ERR_INVALID;
     std::lock_guard<std::recursive_mutex> lk(e->mu);
     CU(e, cudaSetDevice(e->device));
     StageTimer timer(e, CHD_STAGE_INTEREST);
     QueryDev d;
-    chd_status st = upload_queries(e, q, &d, true);  // H2D / D2D copies into the engine's SoA: outside the graph
-    if (st != CHD_OK) return st;
+    chd_status st;
+    int pf_set = -1;  // prefetch staging set this batch lives in
+    if (!q) {  // the batch uploaded by chd_prefetch_queries and handed over by chd_adopt_prefetched
+        if (!e->have_adopted_q) {
+            e->fail("interest update without a batch: q == NULL needs chd_prefetch_queries + chd_adopt_prefetched first");
+            return CHD_ERR_STATE;
+        }
+        d = e->adopted_qd;
+        pf_set = e->adopted_q_set;
+        e->have_adopted_q = false;
+        if (d.n > e->n_slots && !d.sub) {
+            e->fail("identity query batch (sub == NULL) of %u queries > %u subscribers", d.n, e->n_slots);
+            return CHD_ERR_INVALID;
+        }
+        if (e->wait_q) {
+            CU(e, cudaStreamWaitEvent(e->stream, e->ev_upload_q, 0));
+            e->wait_q = false;
+        }
+    } else {
+        st = upload_queries(e, q, &d, true);  // H2D / D2D copies into the engine's SoA: outside the graph
+        if (st != CHD_OK) return st;
+    }
+    const int gslot = e->cur + (pf_set == 1 ? 2 : 0);
     stage_begin_kernel<<<1, 1, 0, e->stream>>>(e->d_time, now_ns, e->d_epoch + EP_QUERY, nullptr);
     KCHECK(e);
     // the graph bakes in which staging arrays are live, the batch size and the pair-buffer parity
@@ -1131,11 +1308,15 @@ chd_status chd_update_interest(chd_engine* e, const chd_query_batch* q, int64_t 
     const void* baked[] = {d.sub, d.kind, d.sph_cx, d.sph_cz, d.sph_r, d.box_cx, d.box_cz, d.box_ex, d.box_ez, d.cone_cx, d.cone_cz,
                            d.cone_dx, d.cone_dz, d.cone_angle, d.cone_r, d.spot_off, d.spot_ndist, d.spot_x, d.spot_z, d.spot_dist};
     for (const void* p : baked) key = mix_key(key, (uint64_t)(uintptr_t)p);  // pointers are baked into the captured launches
-    st = run_stage(e, e->g_interest[e->cur], key, [&]() { return interest_enqueue(e, d, 0); });
+    st = run_stage(e, e->g_interest[gslot], key, [&]() { return interest_enqueue(e, d, 0); });
     if (st != CHD_OK) return st;
     CU(e, cudaEventRecord(e->ev_pairs, e->stream));  // the new pairs exist: emit may start (chd_tick waits on this)
-    st = run_stage(e, e->g_interest_b[e->cur], mix_key(key, 0xb), [&]() { return interest_enqueue(e, d, 1); });
+    st = run_stage(e, e->g_interest_b[gslot], mix_key(key, 0xb), [&]() { return interest_enqueue(e, d, 1); });
     if (st != CHD_OK) return st;
+    if (pf_set >= 0) {  // the staging set may be refilled once these kernels have run
+        CU(e, cudaEventRecord(e->ev_q_read[pf_set], e->stream));
+        e->q_read_recorded[pf_set] = true;
+    }
     e->cur ^= 1;
     e->last_nq = d.n;
     return CHD_OK;
@@ -1186,7 +1367,8 @@ chd_status chd_emit_visible(chd_engine* e) {
                                                                                       e->d_sorted4, e->phase_stride, e->d_vis, e->lim.max_visible,
                                                                                       (uint32_t)e->sm_count);
         else
-            emit_visible_kernel<<<(unsigned)std::max(1, e->sm_count * e->emit_blocks_per_sm * (e->early_results_tick ? std::max(e->emit_waves, 8) : e->emit_waves) - e->emit_grid_reduce), EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4,
+            emit_visible_kernel<<<(unsigned)std::max(1, e->sm_count * e->emit_blocks_per_sm * (e->early_results_tick && e->early_mode == 0 ? std::max(e->emit_waves, 8) : e->emit_waves) - e->emit_grid_reduce -
+                                                   (e->early_results_tick && e->early_mode == 2 ? e->early_reduce : 0)), EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4,
                                                                                    e->phase_stride, e->d_first_pair, e->d_vis, e->lim.max_visible);
         KCHECK(e);
     }
@@ -1221,6 +1403,8 @@ chd_status chd_set_rings(chd_engine* e, const uint32_t* ring_off, uint32_t n_ent
         e->ring_index_p = e->d_ring_index; e->ch_msg_index_p = ch_msg_index ? e->d_ch_msg_index : nullptr;
     }
     e->have_ch_msg_index = ch_msg_index != nullptr;
+    e->ring_set = -1;
+    e->wait_rings = false;
     // the fan-out kernel clamps ring_off to this: a lying caller cannot cause out-of-bounds reads
     set_u32_kernel<<<1, 1, 0, e->stream>>>(e->d_ring_total, total);
     KCHECK(e);
@@ -1235,6 +1419,10 @@ chd_status chd_fanout_tick(chd_engine* e, int64_t t_ns) {
     const uint32_t S = e->n_slots;
     const uint64_t P = e->lim.max_pairs;
     StageTimer timer(e, CHD_STAGE_FANOUT);
+    if (e->wait_rings) {  // rings handed over by chd_adopt_prefetched: ordered after their upload
+        CU(e, cudaStreamWaitEvent(s, e->ev_upload_rings, 0));
+        e->wait_rings = false;
+    }
     stage_begin_kernel<<<1, 1, 0, s>>>(e->d_time + 1, t_ns, e->d_epoch + EP_FANOUT, &e->d_ctr->n_due);
     KCHECK(e);
     RingDev ring{e->ring_off_p ? e->ring_off_p : e->d_ring_off, e->ring_arrival_p ? e->ring_arrival_p : e->d_ring_arrival,
@@ -1245,13 +1433,18 @@ chd_status chd_fanout_tick(chd_engine* e, int64_t t_ns) {
     for (const void* p : {(const void*)ring.off, (const void*)ring.arrival, (const void*)ring.sender, (const void*)ring.index,
                           (const void*)ring.channel_msg_index})
         key = mix_key(key, (uint64_t)(uintptr_t)p);  // pointers are baked into the captured launch
-    return run_stage(e, e->g_fanout[e->cur], key, [&]() -> chd_status {
+    chd_status st = run_stage(e, e->g_fanout[e->cur + (e->ring_set == 1 ? 2 : 0)], key, [&]() -> chd_status {
         const unsigned blocks = (unsigned)std::min<uint64_t>((P + 127) / 128, (uint64_t)e->sm_count * 16);
         fanout_kernel<<<blocks ? blocks : 1, 128, 0, s>>>(pb.off + S, P, pb, e->d_conn, ring, e->d_time + 1, e->g.id_start, e->d_by_cell, e->d_due,
                                                           e->lim.max_due, e->d_ctr);
         KCHECK(e);
         return CHD_OK;
     });
+    if (st == CHD_OK && e->ring_set >= 0) {
+        CU(e, cudaEventRecord(e->ev_ring_read[e->ring_set], s));
+        e->ring_read_recorded[e->ring_set] = true;
+    }
+    return st;
 }
 
 static chd_status decode_summary(chd_engine* e, chd_tick_summary* out);
@@ -1283,7 +1476,11 @@ static chd_status decode_summary(chd_engine* e, chd_tick_summary* out) {
 }
 
 chd_status chd_begin_interest(chd_engine* e, const chd_query_batch* q, int64_t t_ns, int with_fanout) {
-    if (!e || !q) return CHD_ERR_INVALID;
+    if (!e) return CHD_ERR_INVALID;
+    if (!q && !e->have_adopted_q) {
+        e->fail("chd_begin_interest: q == NULL needs chd_prefetch_queries + chd_adopt_prefetched first");
+        return CHD_ERR_STATE;
+    }
     if (e->interest_pending) {
         e->fail("chd_begin_interest: the previous one has not been joined by chd_tick yet");
         return CHD_ERR_STATE;
@@ -1330,6 +1527,7 @@ static chd_status chd_tick_impl(chd_engine* e, const chd_query_batch* q, int64_t
     const bool do_emit = flags & CHD_TICK_EMIT;
     bool do_fanout = flags & CHD_TICK_FANOUT;
     e->early_ready = false;
+    e->build_done_recorded = false;
     e->early_results_tick = (flags & CHD_TICK_EARLY_RESULTS) != 0;
     if (e->interest_pending) {
         // interest (+ fan-out) of this tick were started early with chd_begin_interest and are running on aux_stream
@@ -1342,10 +1540,12 @@ static chd_status chd_tick_impl(chd_engine* e, const chd_query_batch* q, int64_t
         if (need_build) {
             st = chd_build(e);
             if (st != CHD_OK) return st;
+            CU(e, cudaEventRecord(e->ev_build_done, main_stream));
+            e->build_done_recorded = true;
         }
         CU(e, cudaStreamWaitEvent(main_stream, e->emit_variant >= 4 ? e->ev_interest : e->ev_pairs, 0));
         if (do_emit) {
-            if (e->join_before_emit) e->wait_before_emit_kernel = e->ev_join;
+            if (e->join_before_emit || (e->early_results_tick && e->early_mode == 1)) e->wait_before_emit_kernel = e->ev_join;
             st = chd_emit_visible(e);
             if (st != CHD_OK) return st;
         }
@@ -1382,10 +1582,12 @@ static chd_status chd_tick_impl(chd_engine* e, const chd_query_batch* q, int64_t
         if (need_build) {
             st = chd_build(e);
             if (st != CHD_OK) return st;
+            CU(e, cudaEventRecord(e->ev_build_done, main_stream));
+            e->build_done_recorded = true;
         }
         if (do_emit) {
             CU(e, cudaStreamWaitEvent(main_stream, (e->emit_variant >= 4 || !q) ? e->ev_interest : e->ev_pairs, 0));
-            if (e->join_before_emit) e->wait_before_emit_kernel = e->ev_join;
+            if (e->join_before_emit || (e->early_results_tick && e->early_mode == 1)) e->wait_before_emit_kernel = e->ev_join;
             st = chd_emit_visible(e);
             if (st != CHD_OK) return st;
         }
@@ -1416,9 +1618,9 @@ static chd_status chd_tick_impl(chd_engine* e, const chd_query_batch* q, int64_t
 /* ------------------------------------------------------------------ results ---- */
 
 static chd_status read_u32(chd_engine* e, const uint32_t* d, uint32_t* v) {
-    CU(e, cudaMemcpyAsync(e->h_u32, d, 4, cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(e->h_get, d, 4, cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaStreamSynchronize(e->stream));
-    *v = *e->h_u32;
+    *v = *e->h_get;
     return CHD_OK;
 }
 
@@ -1494,7 +1696,7 @@ chd_status chd_get_visible(chd_engine* e, uint64_t* vis_off, uint32_t* vis_entit
     cudaStream_t s = e->stream;
     if (vis_off) CU(e, cudaMemcpyAsync(vis_off, e->d_vis_off, sizeof(uint64_t) * ((uint64_t)S + 1), cudaMemcpyDefault, s));
     if (vis_entity) {
-        uint64_t* h64 = (uint64_t*)e->h_u32;
+        uint64_t* h64 = (uint64_t*)e->h_get;
         CU(e, cudaMemcpyAsync(h64, e->d_vis_off + S, 8, cudaMemcpyDeviceToHost, s));
         CU(e, cudaStreamSynchronize(s));
         const uint64_t V = *h64;
@@ -1508,7 +1710,7 @@ chd_status chd_get_visible(chd_engine* e, uint64_t* vis_off, uint32_t* vis_entit
 chd_status chd_get_visible_slot(chd_engine* e, uint32_t slot, uint32_t* out, uint64_t cap, uint64_t* count) {
     if (!e || !count || slot >= e->n_slots) return CHD_ERR_INVALID;
     CU(e, cudaSetDevice(e->device));
-    uint64_t* h64 = (uint64_t*)e->h_u32;
+    uint64_t* h64 = (uint64_t*)e->h_get;
     CU(e, cudaMemcpyAsync(h64, e->d_vis_off + slot, 16, cudaMemcpyDeviceToHost, e->stream));
     CU(e, cudaStreamSynchronize(e->stream));
     const uint64_t b = h64[0], n = h64[1] - h64[0];
@@ -1556,26 +1758,46 @@ chd_status chd_fetch_results(chd_engine* e, const chd_result_buffers* b, chd_tic
     chd_status st;
     cudaStream_t s = e->stream;
     cudaStream_t main_stream = e->stream;
-    if (e->early_ready && e->dl_stream) {
-        // The lists below are final once the aux chain (ev_join) and the emit preparation (ev_prep_done) have finished: read
-        // them back on a separate stream while the emit kernel is still writing the expanded list.
+    const auto now_us = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = e->trace_fetch ? now_us() : 0.0;
+    const bool early = e->early_ready && e->dl_stream;
+    // error exits: no copy into the caller's buffers may still be in flight when this returns
+    auto drain = [&](chd_status r) {
+        if (e->dl_stream) cudaStreamSynchronize(e->dl_stream);
+        if (e->dl_stream_b) cudaStreamSynchronize(e->dl_stream_b);
+        cudaStreamSynchronize(main_stream);
+        return r;
+    };
+    Counters ca{};  // counters as of phase A
+    if (early) {
+        // The tick is probably still running.  Read back on a separate stream, in the order in which results become final:
+        //   phase A  after the interest fill (ev_pairs) and the build: pairs, interest diff, query statuses, handover list, cell CSR
+        //   phase B  after the aux chain (ev_join: fan-out) and the emit preparation (ev_prep_done): due list, visible offsets
+        // while the emit kernel is still writing the expanded list.
         CU(e, cudaSetDevice(e->device));
         s = e->dl_stream;
-        CU(e, cudaStreamWaitEvent(s, e->ev_join, 0));
-        CU(e, cudaStreamWaitEvent(s, e->ev_prep_done, 0));
+        CU(e, cudaStreamWaitEvent(s, e->ev_pairs, 0));
+        if (e->build_done_recorded) CU(e, cudaStreamWaitEvent(s, e->ev_build_done, 0));
         CU(e, cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
-        CU(e, cudaStreamSynchronize(s));  // sync #1
-        st = decode_summary(e, summary);
+        CU(e, cudaStreamSynchronize(s));  // sync A
+        ca = *e->h_ctr;
+        if (ca.overflow & CHD_OVF_PAIRS) {  // the pair arrays are incomplete: report through the full summary
+            CU(e, cudaStreamSynchronize(main_stream));
+            return chd_summary(e, summary);
+        }
     } else {
         st = chd_summary(e, summary);  // sync #1 (also surfaces capacity overflows)
+        if (st != CHD_OK) return st;
+        ca.n_pairs = summary->n_pairs; ca.n_sub_new = summary->n_sub_new; ca.n_unsub = summary->n_unsub;
+        ca.n_handover = summary->n_handover; ca.n_entities_in_world = summary->n_entities_in_world;
     }
-    if (st != CHD_OK) return st;
+    const double t1 = e->trace_fetch ? now_us() : 0.0;
     PairBuf& pb = e->pairs[e->cur];
     const uint32_t S = e->n_slots;
-    const uint64_t P = summary->n_pairs;
+    const uint64_t P = ca.n_pairs;
     if ((b->pair_channel || b->pair_dist || b->pair_interval_ms) && P > b->pair_cap) {
         e->fail("chd_fetch_results: %llu pairs > pair_cap %llu", (unsigned long long)P, (unsigned long long)b->pair_cap);
-        return CHD_ERR_CAPACITY;
+        return drain(CHD_ERR_CAPACITY);
     }
     if (b->pair_off) CU(e, cudaMemcpyAsync(b->pair_off, pb.off, sizeof(uint32_t) * ((uint64_t)S + 1), cudaMemcpyDefault, s));
     if (b->pair_channel && e->pair_ch_valid) {
@@ -1587,21 +1809,17 @@ chd_status chd_fetch_results(chd_engine* e, const chd_result_buffers* b, chd_tic
     }
     if (b->pair_dist) CU(e, cudaMemcpyAsync(b->pair_dist, pb.dist, sizeof(uint32_t) * P, cudaMemcpyDefault, s));
     if (b->pair_interval_ms) CU(e, cudaMemcpyAsync(b->pair_interval_ms, pb.interval, sizeof(uint32_t) * P, cudaMemcpyDefault, s));
-    const uint64_t nn = summary->n_sub_new, nu = summary->n_unsub;
-    if ((b->new_sub || b->new_channel) && nn > b->diff_cap) return CHD_ERR_CAPACITY;
-    if ((b->unsub_sub || b->unsub_channel) && nu > b->diff_cap) return CHD_ERR_CAPACITY;
+    const uint64_t nn = ca.n_sub_new, nu = ca.n_unsub;
+    if ((b->new_sub || b->new_channel) && nn > b->diff_cap) return drain(CHD_ERR_CAPACITY);
+    if ((b->unsub_sub || b->unsub_channel) && nu > b->diff_cap) return drain(CHD_ERR_CAPACITY);
     if (b->new_sub) CU(e, cudaMemcpyAsync(b->new_sub, e->d_new_sub, sizeof(uint32_t) * nn, cudaMemcpyDefault, s));
     if (b->new_channel) CU(e, cudaMemcpyAsync(b->new_channel, e->d_new_ch, sizeof(uint32_t) * nn, cudaMemcpyDefault, s));
     if (b->unsub_sub) CU(e, cudaMemcpyAsync(b->unsub_sub, e->d_gone_sub, sizeof(uint32_t) * nu, cudaMemcpyDefault, s));
     if (b->unsub_channel) CU(e, cudaMemcpyAsync(b->unsub_channel, e->d_gone_ch, sizeof(uint32_t) * nu, cudaMemcpyDefault, s));
-    if (b->due) {
-        if (summary->n_due > b->due_cap) return CHD_ERR_CAPACITY;
-        CU(e, cudaMemcpyAsync(b->due, e->d_due, sizeof(chd_due) * (uint64_t)summary->n_due, cudaMemcpyDefault, s));
-    }
     if (b->handover_entity || b->handover_src || b->handover_dst) {
-        uint32_t nh = summary->n_handover;
+        uint32_t nh = ca.n_handover;
         if (nh > e->ho_cap) nh = e->ho_cap;
-        if (nh > b->handover_cap) return CHD_ERR_CAPACITY;
+        if (nh > b->handover_cap) return drain(CHD_ERR_CAPACITY);
         if (b->handover_entity) CU(e, cudaMemcpyAsync(b->handover_entity, e->d_ho_entity, sizeof(uint32_t) * nh, cudaMemcpyDefault, s));
         if (b->handover_src) CU(e, cudaMemcpyAsync(b->handover_src, e->d_ho_src, sizeof(uint32_t) * nh, cudaMemcpyDefault, s));
         if (b->handover_dst) CU(e, cudaMemcpyAsync(b->handover_dst, e->d_ho_dst, sizeof(uint32_t) * nh, cudaMemcpyDefault, s));
@@ -1610,18 +1828,40 @@ chd_status chd_fetch_results(chd_engine* e, const chd_result_buffers* b, chd_tic
         const uint32_t n = e->last_nq < b->status_cap ? e->last_nq : b->status_cap;
         CU(e, cudaMemcpyAsync(b->query_status, e->d_status, sizeof(uint32_t) * n, cudaMemcpyDefault, s));
     }
-    if (b->vis_off) CU(e, cudaMemcpyAsync(b->vis_off, e->d_vis_off, sizeof(uint64_t) * ((uint64_t)S + 1), cudaMemcpyDefault, s));
-    if (b->vis_entity) {
-        if (summary->n_visible > b->vis_cap) return CHD_ERR_CAPACITY;
-        CU(e, cudaMemcpyAsync(b->vis_entity, e->d_vis, sizeof(uint32_t) * summary->n_visible, cudaMemcpyDefault, main_stream));
-    }
     if (b->cell_start) CU(e, cudaMemcpyAsync(b->cell_start, e->d_cell_start, sizeof(uint32_t) * ((uint64_t)e->g.cells + 1), cudaMemcpyDefault, s));
     if (b->sorted_entity) {
-        if (summary->n_entities_in_world > b->entity_cap) return CHD_ERR_CAPACITY;
-        CU(e, cudaMemcpyAsync(b->sorted_entity, e->d_sorted_ent, sizeof(uint32_t) * (uint64_t)summary->n_entities_in_world, cudaMemcpyDefault, s));
+        if (ca.n_entities_in_world > b->entity_cap) return drain(CHD_ERR_CAPACITY);
+        CU(e, cudaMemcpyAsync(b->sorted_entity, e->d_sorted_ent, sizeof(uint32_t) * (uint64_t)ca.n_entities_in_world, cudaMemcpyDefault, s));
     }
-    CU(e, cudaStreamSynchronize(s));  // sync #2
+    cudaStream_t sa = s;  // stream carrying the phase-A copies
+    if (early) {  // phase B, on its own stream: its counter read-back must not queue behind the phase-A copies
+        s = e->dl_stream_b;
+        CU(e, cudaStreamWaitEvent(s, e->ev_join, 0));
+        CU(e, cudaStreamWaitEvent(s, e->ev_prep_done, 0));
+        CU(e, cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+        CU(e, cudaStreamSynchronize(s));  // sync B
+        st = decode_summary(e, summary);
+        if (st != CHD_OK) return drain(st);
+    }
+    if (b->due) {
+        if (summary->n_due > b->due_cap) return drain(CHD_ERR_CAPACITY);
+        CU(e, cudaMemcpyAsync(b->due, e->d_due, sizeof(chd_due) * (uint64_t)summary->n_due, cudaMemcpyDefault, s));
+    }
+    if (b->vis_off) CU(e, cudaMemcpyAsync(b->vis_off, e->d_vis_off, sizeof(uint64_t) * ((uint64_t)S + 1), cudaMemcpyDefault, s));
+    if (b->vis_entity) {
+        if (summary->n_visible > b->vis_cap) return drain(CHD_ERR_CAPACITY);
+        CU(e, cudaMemcpyAsync(b->vis_entity, e->d_vis, sizeof(uint32_t) * summary->n_visible, cudaMemcpyDefault, main_stream));
+    }
+    const double t2 = e->trace_fetch ? now_us() : 0.0;
+    CU(e, cudaStreamSynchronize(s));  // last sync of the read-back stream(s)
+    if (sa != s) CU(e, cudaStreamSynchronize(sa));
+    const double t3 = e->trace_fetch ? now_us() : 0.0;
     if (s != main_stream) CU(e, cudaStreamSynchronize(main_stream));  // the tick itself (expanded list) has finished
+    if (e->trace_fetch) {
+        const double t4 = now_us();
+        e->fetch_t[0] += t1 - t0; e->fetch_t[1] += t2 - t1; e->fetch_t[2] += t3 - t2; e->fetch_t[3] += t4 - t3;
+        e->fetch_n++;
+    }
     return CHD_OK;
 }
 
@@ -1765,6 +2005,7 @@ chd_status chd_enable_graphs(chd_engine* e, int on) {
 uint64_t chd_graph_launch_count(const chd_engine* e) { return e ? e->graph_launches : 0; }
 
 chd_status chd_profile_enable(chd_engine* e, int on) {
+    if (e) { e->fetch_n = 0; e->fetch_t[0] = e->fetch_t[1] = e->fetch_t[2] = e->fetch_t[3] = 0; }
     if (!e) return CHD_ERR_INVALID;
     CU(e, cudaSetDevice(e->device));
     if (on && !e->ev) {

@@ -174,7 +174,7 @@ class Engine:
         return status, off, ids[:t].copy(), dist[:t].copy()
 
     def update_interest(self, batch, now_ns):
-        self._ck(self.L.chd_update_interest(self.h, C.byref(batch), int(now_ns)))
+        self._ck(self.L.chd_update_interest(self.h, C.byref(batch) if batch is not None else None, int(now_ns)))
 
     def emit_visible(self):
         self._ck(self.L.chd_emit_visible(self.h))
@@ -197,7 +197,21 @@ class Engine:
         return s
 
     def begin_interest(self, batch, t_ns, with_fanout=True):
-        self._ck(self.L.chd_begin_interest(self.h, C.byref(batch), int(t_ns), int(bool(with_fanout))))
+        """batch None = the batch handed over by prefetch_queries + adopt_prefetched."""
+        self._ck(self.L.chd_begin_interest(self.h, C.byref(batch) if batch is not None else None, int(t_ns), int(bool(with_fanout))))
+
+    def prefetch_queries(self, batch, keep=None):
+        self._keep_pf_q = (batch, keep)
+        self._ck(self.L.chd_prefetch_queries(self.h, C.byref(batch)))
+
+    def prefetch_rings(self, ring_off, arrival, sender, index, channel_msg_index=None):
+        ring_off = np.ascontiguousarray(ring_off, np.uint32)
+        arrival = np.ascontiguousarray(arrival, np.int64)
+        sender = np.ascontiguousarray(sender, np.uint32)
+        index = np.ascontiguousarray(index, np.uint64)
+        cmi = None if channel_msg_index is None else np.ascontiguousarray(channel_msg_index, np.uint64)
+        self._keep_pf_ring = [ring_off, arrival, sender, index, cmi]
+        self._ck(self.L.chd_prefetch_rings(self.h, ptr(ring_off), int(ring_off[-1]), ptr(arrival), ptr(sender), ptr(index), ptr(cmi)))
 
     def tick(self, batch, t_ns, flags=capi.TICK_ALL, want_summary=True):
         s = TickSummary() if want_summary else None

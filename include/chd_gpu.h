@@ -101,6 +101,7 @@ chd_status chd_set_entities(chd_engine* e, const double* x, const double* z, uin
  * prefetched positions the current ones (replaces chd_set_entities for that tick; CHD_ERR_STATE if nothing was
  * prefetched).  The second buffer pair is allocated on the first prefetch. */
 chd_status chd_prefetch_entities(chd_engine* e, const double* x, const double* z, uint32_t n);
+/* (chd_prefetch_queries / chd_prefetch_rings, declared after chd_set_rings, do the same for the other per-tick inputs.) */
 chd_status chd_adopt_prefetched(chd_engine* e);
 /* Device pointers of the resident position arrays, for producers that write positions on the GPU. */
 chd_status chd_entity_buffers(chd_engine* e, double** d_x, double** d_z, uint32_t* n);
@@ -174,6 +175,14 @@ chd_status chd_emit_visible(chd_engine* e);
  * opaque protobuf work. */
 chd_status chd_set_rings(chd_engine* e, const uint32_t* ring_off, uint32_t n_entries, const int64_t* arrival_ns,
                          const uint32_t* sender_conn_id, const uint64_t* message_index, const uint64_t* channel_msg_index);
+/* The same for the other per-tick inputs: the query batch (consumed by the next chd_begin_interest / chd_update_interest
+ * called with q == NULL) and the update rings (arguments as chd_set_rings).  Each kind has two staging sets; a set is
+ * refilled only after the tick that read it.  chd_adopt_prefetched hands over everything prefetched since the last
+ * adoption (any subset of positions / queries / rings). */
+chd_status chd_prefetch_queries(chd_engine* e, const chd_query_batch* q);
+chd_status chd_prefetch_rings(chd_engine* e, const uint32_t* ring_off, uint32_t n_entries, const int64_t* arrival, const uint32_t* sender,
+                              const uint64_t* index, const uint64_t* ch_msg_index);
+
 
 /* One fan-out decision = one fanOutDataUpdate call of the reference (data.go:221,263). */
 typedef struct chd_due {
@@ -219,15 +228,17 @@ chd_status chd_summary(chd_engine* e, chd_tick_summary* out);
  * (flags & CHD_TICK_FANOUT) -> summary.  One stream, no intermediate host sync. */
 enum {
     CHD_TICK_BUILD = 1, CHD_TICK_EMIT = 2, CHD_TICK_FANOUT = 4, CHD_TICK_ALL = 7,
-    /* The host will read this tick's results back (chd_fetch_results): schedule the expanded-list kernel in waves so the
-     * fan-out / interest results complete, and can be copied to the host, while it is still running.  Costs ~2 % of
-     * device time per tick; results are identical. */
+    /* The host will read this tick's results back (chd_fetch_results): start the expanded-list kernel only after the
+     * fan-out pass (it would otherwise starve it of SM slots), so that every host-facing result is final, and is copied
+     * to the host, while that kernel is still running.  Costs ~0.06 ms of device time per tick; results are identical. */
     CHD_TICK_EARLY_RESULTS = 8
 };
 /* Optional early start: the interest update (and the fan-out pass when with_fanout != 0) do not depend on the entity
  * positions, so a host can start them as soon as the tick's queries and rings are known — on the engine's second
  * stream — and then upload / exchange positions; the following chd_tick(e, NULL, t_ns, flags, ..) runs build + emit
- * and joins.  Used by the multi-GPU driver to overlap the border exchange with the interest stage. */
+ * and joins.  Used by the multi-GPU driver to overlap the border exchange with the interest stage.
+ * q == NULL (here and in chd_update_interest) = the batch uploaded by chd_prefetch_queries and handed over by
+ * chd_adopt_prefetched; CHD_ERR_STATE if there is none. */
 chd_status chd_begin_interest(chd_engine* e, const chd_query_batch* q, int64_t t_ns, int with_fanout);
 chd_status chd_tick(chd_engine* e, const chd_query_batch* q, int64_t t_ns, uint32_t flags, chd_tick_summary* out);
 

@@ -628,47 +628,58 @@ def test_zero_copy_device_inputs_match_host_inputs(chd):
     assert sum(r[0]["n_due"] for r in out["host"]) > 1000
 
 
-def test_prefetched_positions_match_direct_upload(chd):
-    """chd_prefetch_entities / chd_adopt_prefetched (double-buffered upload that overlaps the tick in flight) gives the
-    same pairs, visible lists, fan-out decisions and handover lists as chd_set_entities, tick after tick."""
+def test_prefetched_inputs_match_direct_upload(chd):
+    """chd_prefetch_{entities,queries,rings} + chd_adopt_prefetched (double-buffered uploads that overlap the tick in
+    flight) give the same pairs, visible lists, fan-out decisions and handover lists as chd_set_entities / chd_set_rings /
+    an explicit query batch, tick after tick."""
     wc = chd.synth.scaled(chd.synth.CONFIGS["benchmark"], 60_000, 5_000)
-    frames, ex, ez = [], *chd.synth.entities(wc)
+    ex, ez = chd.synth.entities(wc)
     conn, _, _, _ = chd.synth.subscribers(wc, ex, ez)
+    frames, ring_state = [], None
     for tick in range(7):
+        t = (tick + 1) * 33_000_000
         ex, ez = chd.synth.move_entities(wc, ex, ez, tick, 400.0)
-        frames.append((ex.copy(), ez.copy()))
+        _, cx, cz, r = chd.synth.subscribers(wc, ex, ez)
+        ring_state, off, arr, snd, idx, cmi = chd.synth.update_rings(wc, tick, t, 33_000_000, 4, len(conn), ring_len=16, state=ring_state)
+        frames.append(dict(t=t, x=ex.copy(), z=ez.copy(), q=(cx, cz, r), rings=(off, arr, snd, idx, cmi)))
     out = {}
     for mode in ("direct", "prefetch"):
         e = chd.engine.Engine(wc.cfg(), wc.n_entities, wc.n_subscribers, max_visible=1 << 24)
         e.set_subscribers(conn)
-        ring_state, res = None, []
+        res = []
+
+        def prefetch(f):
+            batch, keep = chd.engine.make_batch(len(f["q"][0]), sub=None, sphere=f["q"])
+            e.prefetch_rings(*f["rings"])
+            e.prefetch_queries(batch, keep)
+            e.prefetch_entities(f["x"], f["z"])
+
         if mode == "prefetch":
-            e.prefetch_entities(*frames[0])
-        for tick, (fx, fz) in enumerate(frames):
-            t = (tick + 1) * 33_000_000
-            _, cx, cz, r = chd.synth.subscribers(wc, fx, fz)
-            ring_state, off, arr, snd, idx, cmi = chd.synth.update_rings(wc, tick, t, 33_000_000, 4, len(conn), ring_len=16, state=ring_state)
-            e.set_rings(off, arr, snd, idx, cmi)
-            batch, keep = chd.engine.make_batch(len(cx), sub=None, sphere=(cx, cz, r))
+            prefetch(frames[0])
+        for tick, f in enumerate(frames):
             if mode == "prefetch":
                 e.adopt_prefetched()
-                e._ck(e.L.chd_tick(e.h, C.byref(batch), t, chd.capi.TICK_ALL, None))  # asynchronous
+                e.begin_interest(None, f["t"])
+                e._ck(e.L.chd_tick(e.h, None, f["t"], chd.capi.TICK_ALL | chd.capi.TICK_EARLY_RESULTS, None))  # asynchronous
                 if tick + 1 < len(frames):
-                    e.prefetch_entities(*frames[tick + 1])  # goes up while the tick runs
+                    prefetch(frames[tick + 1])  # goes up while the tick runs
                 s = e.summary()
             else:
-                e.set_entities(fx, fz)
-                s = e.tick(batch, t, chd.capi.TICK_ALL)
+                e.set_rings(*f["rings"])
+                e.set_entities(f["x"], f["z"])
+                batch, keep = chd.engine.make_batch(len(f["q"][0]), sub=None, sphere=f["q"])
+                s = e.tick(batch, f["t"], chd.capi.TICK_ALL)
             pairs = e.get_pairs(s.n_pairs)
             voff, vis = e.get_visible()
             due = e.get_due(s.n_due)
             due = due[np.lexsort((due["window_hi"], due["channel_id"], due["sub"]))]
-            ho = e.get_handover(s.n_handover)
-            ho = np.stack(ho, 1)
+            ho = np.stack(e.get_handover(s.n_handover), 1)
             ho = ho[np.lexsort((ho[:, 2], ho[:, 1], ho[:, 0]))]
             res.append((s.as_dict(), pairs, voff, vis, due, ho))
         with pytest.raises(Exception):
             e.adopt_prefetched()  # nothing staged any more
+        with pytest.raises(Exception):
+            e.begin_interest(None, 1)  # no adopted batch
         out[mode] = res
     for a, b in zip(out["direct"], out["prefetch"]):
         assert a[0] == b[0]
@@ -676,7 +687,7 @@ def test_prefetched_positions_match_direct_upload(chd):
             np.testing.assert_array_equal(a[1][k], b[1][k])
         for i in (2, 3, 4, 5):
             np.testing.assert_array_equal(a[i], b[i])
-    assert sum(r[0]["n_handover"] for r in out["direct"]) > 100
+    assert sum(r[0]["n_handover"] for r in out["direct"]) > 100 and sum(r[0]["n_due"] for r in out["direct"]) > 1000
 
 
 def test_update_interest_all_aoi_kinds(chd, oracle):
