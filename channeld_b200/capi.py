@@ -57,6 +57,15 @@ class QueryBatch(C.Structure):
     ]
 
 
+class BroadcastBatch(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("channel_id", C.c_void_p), ("broadcast", C.c_void_p), ("sender_conn_id", C.c_void_p),
+                ("client_conn_id", C.c_void_p)]
+
+
+BC_ALL_BUT_SENDER, BC_ALL_BUT_OWNER, BC_ALL_BUT_CLIENT, BC_ALL_BUT_SERVER, BC_ADJACENT_CHANNELS = 4, 8, 16, 32, 64
+CONN_SERVER, CONN_CLIENT = 1, 2
+
+
 class Due(C.Structure):
     _fields_ = [
         ("sub", C.c_uint32), ("channel_id", C.c_uint32), ("kind", C.c_uint32), ("n_selected", C.c_uint32),
@@ -105,7 +114,7 @@ SYMBOLS = [
     "chd_assign_cells", "chd_build", "chd_set_subscribers", "chd_query_channel_ids", "chd_update_interest",
     "chd_emit_visible", "chd_set_rings", "chd_fanout_tick", "chd_summary", "chd_tick", "chd_begin_interest", "chd_get_cells", "chd_get_pairs",
     "chd_get_query_status", "chd_get_diff", "chd_get_visible", "chd_get_visible_slot", "chd_get_due", "chd_fetch_results", "chd_get_handover", "chd_device_view",
-    "chd_set_slab", "chd_set_entity_ids", "chd_export_border", "chd_import_halo", "chd_get_adjacent_channels",
+    "chd_set_slab", "chd_set_entity_ids", "chd_export_border", "chd_import_halo", "chd_due_classes", "chd_set_subscriber_types", "chd_adjacent_broadcast", "chd_get_adjacent_channels",
     "chd_get_regions", "chd_damping_interval_ms", "chd_launch_count", "chd_profile_enable", "chd_profile_get", "chd_profile_timeline", "chd_enable_graphs",
     "chd_graph_launch_count",
 ]
@@ -205,6 +214,12 @@ def lib():
     L.chd_export_border.argtypes = [vp, vp, C.c_uint32, u32p]
     L.chd_import_halo.restype = C.c_int
     L.chd_import_halo.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.chd_due_classes.restype = C.c_int
+    L.chd_due_classes.argtypes = [vp, vp, vp, vp, C.c_uint32, u32p]
+    L.chd_set_subscriber_types.restype = C.c_int
+    L.chd_set_subscriber_types.argtypes = [vp, vp, C.c_uint32]
+    L.chd_adjacent_broadcast.restype = C.c_int
+    L.chd_adjacent_broadcast.argtypes = [vp, C.POINTER(BroadcastBatch), vp, vp, vp, C.c_uint64]
     L.chd_get_adjacent_channels.restype = C.c_uint32
     L.chd_get_adjacent_channels.argtypes = [C.POINTER(GridCfg), C.c_uint32, vp]
     L.chd_get_regions.restype = C.c_int

@@ -20,6 +20,18 @@ struct RingDev {
     const uint32_t* total;              // entries uploaded (device scalar): offsets are clamped to it
 };
 
+// Payload identity of a decision (window classes, chd_classes.cuh): two decisions of one channel carry the same merged
+// payload if they are both FULL, or if they start from the same lastFanOutTime (`lo`), end at the same nextFanOutTime
+// (the record's window_hi) and neither subscriber had an own update left out of that window; a decision with
+// self-skipped updates is its own class.  word = cell << 34 | kind << 33 | skipped << 32 | (skipped ? subscriber slot : 0).
+struct DueKey {
+    int64_t lo;
+    uint64_t word;
+};
+__device__ __forceinline__ DueKey make_due_key(uint32_t cell, uint32_t kind, bool skipped, uint32_t sub, int64_t lo) {
+    return DueKey{kind ? lo : 0ll, ((uint64_t)cell << 34) | ((uint64_t)kind << 33) | ((uint64_t)(skipped ? 1u : 0u) << 32) | (skipped ? sub : 0u)};
+}
+
 constexpr uint32_t FANOUT_MAX_STEPS = 1u << 16;
 constexpr uint32_t FANOUT_SLOTS = 2;            // decisions per pair kept by the evaluation pass
 
@@ -44,16 +56,20 @@ __device__ __forceinline__ uint32_t fanout_eval(const RingDev& ring, uint32_t ri
             chd_due d;
             d.sub = s; d.channel_id = c + id_start; d.kind = 0; d.n_selected = 0; d.first_sel = 0; d.last_sel = 0;
             d.sel_hash = 0; d.last_message_index = last_index; d.window_hi = next;
-            emit(n_out, d);
+            emit(n_out, d, make_due_key(c, 0u, false, s, 0));
             n_out++;
         } else if (r1 > r0) {  // data.go:225-265
             int64_t last_update = 0;
             if (last >= last_update) last_update = last;
             uint32_t nsel = 0, first = 0, lastsel = 0;
             uint64_t hash = 0;
+            bool skipped = false;  // an own update fell into the window and was left out (data.go:239-242)
             for (uint32_t k = r0; k < r1; k++) {
-                if (skip_self && ring.sender[k] == me) continue;
                 const int64_t a = ring.arrival[k];
+                if (skip_self && ring.sender[k] == me) {
+                    skipped |= a >= last_update && a <= next;
+                    continue;
+                }
                 if (a >= last_update && a <= next) {
                     if (!nsel) first = k - r0;
                     lastsel = k - r0;
@@ -68,7 +84,7 @@ __device__ __forceinline__ uint32_t fanout_eval(const RingDev& ring, uint32_t ri
                 chd_due d;
                 d.sub = s; d.channel_id = c + id_start; d.kind = 1; d.n_selected = nsel; d.first_sel = first; d.last_sel = lastsel;
                 d.sel_hash = hash; d.last_message_index = last_index; d.window_hi = next;
-                emit(n_out, d);
+                emit(n_out, d, make_due_key(c, 1u, skipped, s, last));
                 n_out++;
             }
         }
@@ -86,7 +102,7 @@ __device__ __forceinline__ uint32_t fanout_eval(const RingDev& ring, uint32_t ri
 __global__ void __launch_bounds__(128)
     fanout_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, PairBuf pb, const uint32_t* __restrict__ conn_id, RingDev ring,
                   const int64_t* __restrict__ t_ptr, uint32_t id_start, const uint32_t* __restrict__ by_cell, chd_due* __restrict__ due,
-                  uint32_t due_cap, Counters* __restrict__ ctr) {
+                  DueKey* __restrict__ due_key, uint32_t due_cap, Counters* __restrict__ ctr) {
     __shared__ uint32_t s_warp[4], s_base;
     const uint64_t n = min((uint64_t)*n_pairs_ptr, pair_cap);
     const int64_t t = *t_ptr;  // device-resident so the launch can be replayed from a CUDA graph
@@ -100,6 +116,7 @@ __global__ void __launch_bounds__(128)
         int64_t last0 = 0, last = 0;
         uint8_t flags0 = 0, flags = 0;
         chd_due d0, d1;
+        DueKey k0{}, k1{};
         if (i < n) {
             p = by_cell[i];
             interval = pb.interval[p];
@@ -110,10 +127,11 @@ __global__ void __launch_bounds__(128)
                 c = pb.cell[p];
                 s = pb.sub[p];
                 me = conn_id[s];
-                n_out = fanout_eval(ring, ring_total, t, interval, c, s, me, id_start, last, flags, last_index, [&](uint32_t j, const chd_due& d) {
-                    if (j == 0) d0 = d;
-                    else if (j == 1) d1 = d;
-                });
+                n_out = fanout_eval(ring, ring_total, t, interval, c, s, me, id_start, last, flags, last_index,
+                                    [&](uint32_t j, const chd_due& d, const DueKey& k) {
+                                        if (j == 0) { d0 = d; k0 = k; }
+                                        else if (j == 1) { d1 = d; k1 = k; }
+                                    });
             }
         }
         // block-wide exclusive offsets of n_out (128 threads = 4 warps)
@@ -137,12 +155,14 @@ __global__ void __launch_bounds__(128)
             const uint32_t o = s_base + off;
             if ((uint64_t)o + n_out > due_cap) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_DUE);
             if (n_out <= FANOUT_SLOTS) {
-                if (o < due_cap) due[o] = d0;
-                if (n_out > 1 && o + 1 < due_cap) due[o + 1] = d1;
+                if (o < due_cap) { due[o] = d0; due_key[o] = k0; }
+                if (n_out > 1 && o + 1 < due_cap) { due[o + 1] = d1; due_key[o + 1] = k1; }
             } else {  // several intervals behind: re-evaluate from the saved state, writing directly
                 last = last0; flags = flags0; last_index = last_index0;
                 fanout_eval(ring, ring_total, t, interval, c, s, me, id_start, last, flags, last_index,
-                            [&](uint32_t j, const chd_due& d) { if (o + j < due_cap) due[o + j] = d; });
+                            [&](uint32_t j, const chd_due& d, const DueKey& k) {
+                                if (o + j < due_cap) { due[o + j] = d; due_key[o + j] = k; }
+                            });
             }
         }
         if (i < n && (n_out || last != last0)) {  // commit (steps without a decision still advance lastFanOutTime)

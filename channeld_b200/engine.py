@@ -277,6 +277,37 @@ class Engine:
         self._ck(self.L.chd_get_handover(self.h, ptr(a), ptr(b), ptr(c), n))
         return a, b, c
 
+    def due_classes(self, n_due):
+        """Window classes of the last fan-out pass -> (class_of[n_due], class_rep[n_classes], class_count[n_classes])."""
+        of = np.zeros(n_due, np.uint32)
+        rep = np.zeros(max(n_due, 1), np.uint32)
+        cnt = np.zeros(max(n_due, 1), np.uint32)
+        n = C.c_uint32(0)
+        self._ck(self.L.chd_due_classes(self.h, ptr(of), ptr(rep), ptr(cnt), len(rep), C.byref(n)))
+        return of, rep[:n.value], cnt[:n.value]
+
+    def set_subscriber_types(self, conn_type):
+        if conn_type is None:
+            self._ck(self.L.chd_set_subscriber_types(self.h, None, 0))
+            return
+        t = np.ascontiguousarray(conn_type, np.uint8)
+        self._ck(self.L.chd_set_subscriber_types(self.h, ptr(t), len(t)))
+
+    def adjacent_broadcast(self, channel_id, broadcast, sender_conn_id=None, client_conn_id=None, cap=None):
+        """BroadcastType_ADJACENT_CHANNELS recipient sets (message.go:188-239) -> (status[n], off[n+1], slot[])."""
+        ch = np.ascontiguousarray(channel_id, np.uint32)
+        bc = np.ascontiguousarray(broadcast, np.uint32)
+        n = len(ch)
+        snd = None if sender_conn_id is None else np.ascontiguousarray(sender_conn_id, np.uint32)
+        cli = None if client_conn_id is None else np.ascontiguousarray(client_conn_id, np.uint32)
+        b = capi.BroadcastBatch()
+        b.n, b.channel_id, b.broadcast, b.sender_conn_id, b.client_conn_id = n, ptr(ch), ptr(bc), ptr(snd), ptr(cli)
+        cap = int(cap if cap is not None else max(1, 9 * n * max(self.n_slots, 1)))
+        cap = min(cap, 1 << 26)
+        status, off, slot = np.zeros(n, np.uint32), np.zeros(n + 1, np.uint32), np.zeros(cap, np.uint32)
+        self._ck(self.L.chd_adjacent_broadcast(self.h, C.byref(b), ptr(status), ptr(off), ptr(slot), cap))
+        return status, off, slot[:off[-1]]
+
     def device_view(self, which):
         p, n = C.c_void_p(), C.c_uint64()
         self._ck(self.L.chd_device_view(self.h, which, C.byref(p), C.byref(n)))

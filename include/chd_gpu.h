@@ -311,6 +311,46 @@ chd_status chd_set_entity_ids(chd_engine* e, const uint32_t* global_id, uint32_t
 chd_status chd_export_border(chd_engine* e, uint32_t* d_records, uint32_t cap_records, uint32_t* out_count);
 chd_status chd_import_halo(chd_engine* e, const uint32_t* d_records, uint32_t n_records, uint32_t skip_first, uint32_t skip_count);
 
+/* ---- window classes of the last fan-out pass (payload assembly).  The reference merges the selected
+ * update window afresh for every subscriber (data.go:248-252); decisions of one channel whose merged payload is
+ * necessarily identical are grouped so the host merges / frames each distinct payload once:
+ *   - all FULL decisions (kind 0) of a channel form one class (they all send ch.data.msg, data.go:219-224);
+ *   - UPDATE decisions (kind 1) of a channel with the same lastFanOutTime at the start of the step, the same window_hi and
+ *     no own update left out by SkipSelfUpdateFanOut form one class (the selection loop data.go:226-256 is then a
+ *     function of the channel's buffer and these two times only);
+ *   - an UPDATE decision whose subscriber had own updates inside the window is a class of its own.
+ * out_class_of[i] = class of due record i (index into the list chd_get_due / chd_fetch_results return, same order),
+ * out_class_rep[k] = lowest due index of class k (classes are numbered by it), out_class_count[k] = its size.
+ * Any output may be NULL.  CHD_ERR_CAPACITY if there are more than cap_classes classes.  Synchronous. */
+chd_status chd_due_classes(chd_engine* e, uint32_t* out_class_of, uint32_t* out_class_rep, uint32_t* out_class_count,
+                           uint32_t cap_classes, uint32_t* out_n_classes);
+
+/* ---- BroadcastType_ADJACENT_CHANNELS recipient sets, batched (message.go:188-239).
+ * For message m sent to spatial channel channel_id[m] with BroadcastType mask broadcast[m] (channeld.proto: ALL_BUT_SENDER 4,
+ * ALL_BUT_OWNER 8, ALL_BUT_CLIENT 16, ALL_BUT_SERVER 32; the ADJACENT_CHANNELS bit itself is implied): the recipients are
+ * the subscribers (slots of chd_set_subscribers, per the CURRENT spatial subscriptions = last chd_update_interest) of the
+ * channel's 3x3 neighbours (spatial.go:358-381) and — unless ALL_BUT_OWNER — of the channel itself, each slot once
+ * (the reference's adjacentConns map), minus the slot whose connection id equals sender_conn_id[m] when ALL_BUT_SENDER
+ * is set, the clients / servers when ALL_BUT_CLIENT / ALL_BUT_SERVER are set (chd_set_subscriber_types), and the slot
+ * whose connection id equals client_conn_id[m] (ServerForwardMessage.ClientConnId; 0 = none).
+ * Output: CSR out_off[n + 1] / out_slot[] (a SET per message: the reference iterates a Go map), out_status[m] =
+ * CHD_BC_OK or CHD_BC_ERR_NOT_A_CELL (channel id outside this grid: the reference cannot reach this, the channel must
+ * exist; such a message gets no recipients).  Synchronous; CHD_ERR_CAPACITY if the lists need more than cap entries.
+ * sender_conn_id / client_conn_id may be NULL (= all 0). */
+typedef struct chd_broadcast_batch {
+    uint32_t n;
+    const uint32_t* channel_id;
+    const uint32_t* broadcast;
+    const uint32_t* sender_conn_id;
+    const uint32_t* client_conn_id;
+} chd_broadcast_batch;
+enum { CHD_BC_OK = 0, CHD_BC_ERR_NOT_A_CELL = 1 };
+enum { CHD_CONN_SERVER = 1, CHD_CONN_CLIENT = 2 }; /* channeldpb.ConnectionType */
+/* ConnectionType per subscriber slot (NULL = unknown: the ALL_BUT_CLIENT / ALL_BUT_SERVER filters then remove nobody). */
+chd_status chd_set_subscriber_types(chd_engine* e, const uint8_t* conn_type, uint32_t n);
+chd_status chd_adjacent_broadcast(chd_engine* e, const chd_broadcast_batch* b, uint32_t* out_status, uint32_t* out_off,
+                                  uint32_t* out_slot, uint64_t cap);
+
 /* ---- control-plane helpers kept for interface completeness (pure integer/config math on the host; not part
  * of the data-parallel path): GetAdjacentChannels (spatial.go:358-381) and GetRegions (spatial.go:319-356). */
 uint32_t chd_get_adjacent_channels(const chd_grid_cfg* cfg, uint32_t channel_id, uint32_t* out8);

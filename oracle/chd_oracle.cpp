@@ -239,6 +239,33 @@ uint32_t orc_get_adjacent_channels(const orc_grid* g, uint32_t channel_id, uint3
     return n;
 }
 
+uint32_t orc_adjacent_broadcast(const orc_grid* g, uint32_t channel_id, uint32_t broadcast, uint32_t sender_conn_id,
+                                uint32_t client_conn_id, const uint32_t* cell_off, const uint32_t* conn_id,
+                                const uint8_t* conn_type, uint32_t* out_conn, uint32_t cap) {  // message.go:188-239
+    enum : uint32_t { ALL_BUT_SENDER = 4, ALL_BUT_OWNER = 8, ALL_BUT_CLIENT = 16, ALL_BUT_SERVER = 32 };  // channeld.proto BroadcastType
+    const auto check = [&](uint32_t bit) { return (broadcast & bit) > 0; };  // channeldpb/extension.go:5-7
+    uint32_t ids[9];
+    uint32_t n = orc_get_adjacent_channels(g, channel_id, ids);  // message.go:197
+    if (!check(ALL_BUT_OWNER)) ids[n++] = channel_id;            // :203-205
+    std::map<uint32_t, uint8_t> adjacent_conns;                  // :208-219 (connection -> its type)
+    const uint32_t cells = g->grid_cols * g->grid_rows;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t cell = ids[i] - g->channel_id_start;
+        if (cell >= cells) continue;  // GetChannel(id) == nil
+        for (uint32_t k = cell_off[cell]; k < cell_off[cell + 1]; k++) adjacent_conns[conn_id[k]] = conn_type ? conn_type[k] : uint8_t(0);
+    }
+    uint32_t out = 0;
+    for (const auto& kv : adjacent_conns) {  // :220-238
+        if (check(ALL_BUT_SENDER) && kv.first == sender_conn_id) continue;
+        if (check(ALL_BUT_CLIENT) && kv.second == 2) continue;
+        if (check(ALL_BUT_SERVER) && kv.second == 1) continue;
+        if (kv.first == client_conn_id) continue;
+        if (out < cap) out_conn[out] = kv.first;
+        out++;
+    }
+    return out;
+}
+
 void orc_get_regions(const orc_grid* g, double* min_x, double* min_z, double* max_x, double* max_z, uint32_t* channel_id,
                      uint32_t* server_index) {  // spatial.go:319-356
     uint32_t sgc = g->grid_cols / g->server_cols;
@@ -351,8 +378,15 @@ void orc_channel_on_update(orc_channel* ch, int64_t arrival_ns, uint32_t sender)
 
 uint32_t orc_channel_ring_len(const orc_channel* ch) { return uint32_t(ch->ring.size()); }
 
-uint32_t orc_channel_tick_data(orc_channel* ch, int64_t t, orc_send* out, uint32_t cap) {  // data.go:175-291
+uint32_t orc_channel_tick_data(orc_channel* ch, int64_t t, orc_send* out, uint32_t cap) {
+    return orc_channel_tick_data_ex(ch, t, out, cap, nullptr, nullptr, nullptr, nullptr, 0);
+}
+
+uint32_t orc_channel_tick_data_ex(orc_channel* ch, int64_t t, orc_send* out, uint32_t cap, int64_t* window_lo, uint32_t* self_skipped,
+                                  uint32_t* sel_off, uint32_t* sel_pos, uint32_t sel_cap) {  // data.go:175-291
     uint32_t n_out = 0;
+    uint32_t n_sel = 0;
+    if (sel_off) sel_off[0] = 0;
     uint64_t guard = 0;
     auto focp = ch->queue.begin();
     while (focp != ch->queue.end()) {
@@ -368,15 +402,27 @@ uint32_t orc_channel_tick_data(orc_channel* ch, int64_t t, orc_send* out, uint32
                 foc.had_first = true;
                 foc.last_index = ch->msg_index;
                 latest = t;
+                if (window_lo) window_lo[n_out] = foc.last;
+                if (self_skipped) self_skipped[n_out] = 0;
                 out[n_out++] = orc_send{foc.conn, 0u, 0u, 0u, 0u, 0ull, foc.last_index, next};
+                if (sel_off) sel_off[n_out] = n_sel;
             } else if (!ch->ring.empty()) {  // data.go:225-265
                 if (foc.last >= last_update_time) last_update_time = foc.last;
                 orc_send s{foc.conn, 1u, 0u, 0u, 0u, 0ull, 0ull, next};
-                uint32_t pos = 0;
+                uint32_t pos = 0, skipped = 0;
+                const uint32_t sel_begin = n_sel;
                 for (auto& be : ch->ring) {
                     const uint32_t p = pos++;
-                    if (be.sender == foc.conn && foc.skip_self) continue;
+                    if (be.sender == foc.conn && foc.skip_self) {
+                        if (be.arrival >= last_update_time && be.arrival <= next) skipped++;  // would have been merged
+                        continue;
+                    }
                     if (be.arrival >= last_update_time && be.arrival <= next) {
+                        if (sel_pos) {
+                            if (n_sel >= sel_cap) return uint32_t(-1);
+                            sel_pos[n_sel] = p;
+                        }
+                        n_sel++;
                         if (!merged) s.first_sel = p;
                         merged = true;
                         s.last_sel = p;
@@ -389,7 +435,12 @@ uint32_t orc_channel_tick_data(orc_channel* ch, int64_t t, orc_send* out, uint32
                 if (merged) {
                     if (n_out >= cap) return uint32_t(-1);
                     s.last_message_index = foc.last_index;
+                    if (window_lo) window_lo[n_out] = foc.last;
+                    if (self_skipped) self_skipped[n_out] = skipped;
                     out[n_out++] = s;
+                    if (sel_off) sel_off[n_out] = n_sel;
+                } else {
+                    n_sel = sel_begin;  // nothing merged: nothing sent
                 }
             }
             foc.last = latest;  // data.go:268

@@ -84,6 +84,16 @@ int orc_query_channel_ids(const orc_grid* g, const orc_query* q, uint32_t* out_i
 /* spatial.go:358-381; order as the reference emits (row-major y,x).  Returns count (<=8). */
 uint32_t orc_get_adjacent_channels(const orc_grid* g, uint32_t channel_id, uint32_t* out8);
 
+/* message.go:188-239 — recipients of a BroadcastType_ADJACENT_CHANNELS message sent to spatial channel `channel_id`.
+ * Every spatial channel's subscribedConnections is given as a CSR by cell index: cell_off[cells+1], conn_id[], conn_type[]
+ * (channeldpb.ConnectionType: 1 server, 2 client).  `broadcast` is the BroadcastType mask of the message.
+ * Literal restatement: GetAdjacentChannels, append the centre unless ALL_BUT_OWNER, merge all connections of those
+ * channels into one map, then the four filters in the reference's order.  out_conn = recipients' connection ids,
+ * sorted ascending (the reference iterates a Go map: only the SET is defined).  Returns the count. */
+uint32_t orc_adjacent_broadcast(const orc_grid* g, uint32_t channel_id, uint32_t broadcast, uint32_t sender_conn_id,
+                                uint32_t client_conn_id, const uint32_t* cell_off, const uint32_t* conn_id,
+                                const uint8_t* conn_type, uint32_t* out_conn, uint32_t cap);
+
 /* spatial.go:319-356.  Arrays sized cols*rows. min/max hold x,z (Y is the constant MinY/MaxY). */
 void orc_get_regions(const orc_grid* g, double* min_x, double* min_z, double* max_x, double* max_z,
                      uint32_t* channel_id, uint32_t* server_index);
@@ -125,6 +135,13 @@ uint32_t orc_channel_ring_len(const orc_channel*);
 /* data.go:175-291.  Appends sends in the order the reference would issue them. Returns count, or
  * (uint32_t)-1 when `cap` is too small or the iteration bound trips (FanOutIntervalMs == 0). */
 uint32_t orc_channel_tick_data(orc_channel*, int64_t t_ns, orc_send* out, uint32_t cap);
+/* The same tick, additionally reporting for send i: window_lo[i] = the connection's lastFanOutTime when the step began
+ * (data.go:205,226), self_skipped[i] = how many of the connection's own buffered updates fell into the window and were
+ * left out by SkipSelfUpdateFanOut (data.go:239-242), and the ring positions merged into its payload as a CSR
+ * (sel_off[n+1], sel_pos[]) — the exact payload identity used to check the window classes.
+ * Returns (uint32_t)-1 when cap / sel_cap are too small. */
+uint32_t orc_channel_tick_data_ex(orc_channel*, int64_t t_ns, orc_send* out, uint32_t cap, int64_t* window_lo, uint32_t* self_skipped,
+                                  uint32_t* sel_off, uint32_t* sel_pos, uint32_t sel_cap);
 /* read back per-connection state: returns 0 if found */
 int orc_channel_get_state(const orc_channel*, uint32_t conn_id, int64_t* last_fanout, int* had_first,
                           uint64_t* last_msg_index);

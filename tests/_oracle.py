@@ -70,6 +70,8 @@ class Oracle:
         L.orc_query_channel_ids.argtypes = [C.POINTER(Grid), C.POINTER(Query), u32p, u32p, C.c_uint32, u32p]
         L.orc_get_adjacent_channels.restype = C.c_uint32
         L.orc_get_adjacent_channels.argtypes = [C.POINTER(Grid), C.c_uint32, u32p]
+        L.orc_adjacent_broadcast.restype = C.c_uint32
+        L.orc_adjacent_broadcast.argtypes = [C.POINTER(Grid), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p, u32p, C.c_void_p, u32p, C.c_uint32]
         L.orc_get_regions.restype = None
         L.orc_get_regions.argtypes = [C.POINTER(Grid), f64p, f64p, f64p, f64p, u32p, u32p]
         L.orc_damping_interval_ms.restype = C.c_uint32
@@ -86,6 +88,8 @@ class Oracle:
         L.orc_channel_on_update.argtypes = [C.c_void_p, C.c_int64, C.c_uint32]
         L.orc_channel_ring_len.restype = C.c_uint32
         L.orc_channel_ring_len.argtypes = [C.c_void_p]
+        L.orc_channel_tick_data_ex.restype = C.c_uint32
+        L.orc_channel_tick_data_ex.argtypes = [C.c_void_p, C.c_int64, C.POINTER(Send), C.c_uint32, C.POINTER(C.c_int64), u32p, u32p, u32p, C.c_uint32]
         L.orc_channel_tick_data.restype = C.c_uint32
         L.orc_channel_tick_data.argtypes = [C.c_void_p, C.c_int64, C.POINTER(Send), C.c_uint32]
         L.orc_channel_get_state.restype = C.c_int
@@ -151,6 +155,17 @@ class Oracle:
         out = np.zeros(8, np.uint32)
         n = self.lib.orc_get_adjacent_channels(C.byref(g), channel_id, _p(out, u32p))
         return [int(v) for v in out[:n]]
+
+    def adjacent_broadcast(self, g, channel_id, broadcast, sender, client, cell_off, conn_id, conn_type):
+        """message.go:188-239 on per-cell subscriber lists (CSR) -> sorted recipient connection ids."""
+        cell_off = np.ascontiguousarray(cell_off, np.uint32)
+        conn_id = np.ascontiguousarray(conn_id, np.uint32)
+        ct = None if conn_type is None else np.ascontiguousarray(conn_type, np.uint8)
+        cap = len(conn_id) + 1
+        out = np.zeros(cap, np.uint32)
+        n = self.lib.orc_adjacent_broadcast(C.byref(g), int(channel_id), int(broadcast), int(sender), int(client), _p(cell_off, u32p),
+                                            _p(conn_id, u32p), None if ct is None else ct.ctypes.data_as(C.c_void_p), _p(out, u32p), cap)
+        return out[:n].copy()
 
     def regions(self, g):
         n = g.grid_cols * g.grid_rows
@@ -233,6 +248,20 @@ class OracleChannel:
         assert n != 0xFFFFFFFF, "oracle tick_data: capacity/iteration bound"
         return [dict(conn=b.conn_id, kind=b.kind, n=b.n_selected, first=b.first_sel, last=b.last_sel,
                      hash=b.sel_hash, last_index=b.last_message_index, window_hi=b.window_hi) for b in buf[:n]]
+
+    def tick_data_ex(self, t_ns, cap=4096, sel_cap=1 << 18):
+        """tick_data + per send: window_lo, self_skipped, and the exact ring positions merged (tuple)."""
+        buf = (Send * cap)()
+        lo = np.zeros(cap, np.int64)
+        sk = np.zeros(cap, np.uint32)
+        so = np.zeros(cap + 1, np.uint32)
+        sp = np.zeros(sel_cap, np.uint32)
+        n = self.L.orc_channel_tick_data_ex(self.h, int(t_ns), buf, cap, lo.ctypes.data_as(C.POINTER(C.c_int64)), _p(sk, u32p), _p(so, u32p),
+                                            _p(sp, u32p), sel_cap)
+        assert n != 0xFFFFFFFF, "oracle tick_data_ex: capacity/iteration bound"
+        return [dict(conn=b.conn_id, kind=b.kind, n=b.n_selected, first=b.first_sel, last=b.last_sel, hash=b.sel_hash,
+                     last_index=b.last_message_index, window_hi=b.window_hi, window_lo=int(lo[i]), self_skipped=int(sk[i]),
+                     selected=tuple(sp[so[i]:so[i + 1]].tolist())) for i, b in enumerate(buf[:n])]
 
     def state(self, conn):
         a, b, c = C.c_int64(0), C.c_int(0), C.c_uint64(0)

@@ -333,7 +333,7 @@ def test_interest_diff_and_fanout_parity(chd, oracle):
     subs_now = [dict() for _ in range(S)]  # channel id -> dist, the oracle-side spatialSubscriptions
     t = 0
     tick_ns = 33 * MS
-    total_due = 0
+    total_due = total_classes = total_shared = 0
     for tick in range(12):
         t += tick_ns if tick % 4 else 70 * MS  # irregular ticks exercise multi-step catch-up
         cx += rng.uniform(-45, 45, S)
@@ -382,21 +382,45 @@ def test_interest_diff_and_fanout_parity(chd, oracle):
         e.fanout_tick(t)
         s = e.summary()
         due = e.get_due(s.n_due)
-        want = []
+        want, want_ex = [], {}
         for c in range(cells):
-            for d in chans[c].tick_data(t):
+            for d in chans[c].tick_data_ex(t):
                 want.append((d["conn"], S0 + c, d["kind"], d["n"], d["first"], d["last"], d["hash"], d["last_index"], d["window_hi"]))
+                want_ex[(d["conn"], S0 + c, d["kind"], d["window_hi"])] = d
         got = [(int(conn[d["sub"]]), int(d["channel_id"]), int(d["kind"]), int(d["n_selected"]), int(d["first_sel"]), int(d["last_sel"]),
                 int(d["sel_hash"]), int(d["last_message_index"]), int(d["window_hi"])) for d in due]
         assert sorted(got) == sorted(want)
         total_due += len(got)
+        # window classes (chd_due_classes): decisions grouped by payload identity
+        cls_of, cls_rep, cls_cnt = e.due_classes(s.n_due)
+        assert len(want_ex) == len(want)
+        exact, doc = [], []
+        for g_ in got:
+            w = want_ex[(g_[0], g_[1], g_[2], g_[8])]
+            if g_[2] == 0:
+                exact.append((g_[1], 0)); doc.append((g_[1], 0))
+            else:
+                exact.append((g_[1], 1, w["selected"]))  # the ring entries actually merged (oracle emulation)
+                doc.append((g_[1], 1, w["window_lo"], w["window_hi"], g_[0] if w["self_skipped"] else 0))
+        members = {}
+        for i, k in enumerate(cls_of.tolist()):
+            members.setdefault(k, []).append(i)
+        assert sorted(members) == list(range(len(cls_rep)))
+        for k, idx in members.items():
+            assert len({exact[i] for i in idx}) == 1, "a class mixes different payloads"
+            assert len({doc[i] for i in idx}) == 1
+            assert cls_rep[k] == min(idx) and cls_cnt[k] == len(idx)
+        assert len({doc[i] for i in range(len(got))}) == len(cls_rep)  # no identity is split over two classes
+        assert cls_rep.tolist() == sorted(cls_rep.tolist())
+        total_classes += len(cls_rep)
+        total_shared += len(got) - len(cls_rep)
         # committed state matches the oracle's fanOutConnection
         pairs = e.get_pairs()
         for j in range(S):
             for p in range(pairs["off"][j], pairs["off"][j + 1]):
                 last, had, idx = chans[int(pairs["channel"][p]) - S0].state(int(conn[j]))
                 assert (int(pairs["last"][p]), bool(pairs["flags"][p] & 1), int(pairs["last_index"][p])) == (last, had, idx)
-    assert total_due > 200
+    assert total_due > 200 and 0 < total_classes < total_due and total_shared > 50
 
 
 def test_fanout_kat_through_engine(chd):
@@ -688,6 +712,75 @@ def test_prefetched_inputs_match_direct_upload(chd):
         for i in (2, 3, 4, 5):
             np.testing.assert_array_equal(a[i], b[i])
     assert sum(r[0]["n_handover"] for r in out["direct"]) > 100 and sum(r[0]["n_due"] for r in out["direct"]) > 1000
+
+
+def test_adjacent_broadcast_sets_parity(chd, oracle):
+    """BroadcastType_ADJACENT_CHANNELS recipient sets (message.go:188-239) for a batch of messages against the oracle
+    restatement: every cell x every filter combination + random senders / forwarded clients, on subscriptions built
+    by chd_update_interest from random sphere queries (many subscribers span several cells, so the de-duplication is
+    exercised); also the empty / invalid-channel / capacity edges."""
+    from tests._oracle import make_grid
+
+    g = GRIDS[5]  # 9 x 8 grid, 100 x 50 cells
+    og = make_grid(*g)
+    cells = 72
+    rng = np.random.default_rng(99)
+    S = 3000
+    e = chd.engine.Engine(chd.engine.grid_cfg(*g), 16, S, max_visible=1 << 16)
+    e.set_entities(np.array([0.0]), np.array([0.0]))
+    e.build()
+    conn = (rng.permutation(S) + 1).astype(np.uint32)
+    types = rng.integers(1, 3, S).astype(np.uint8)
+    e.set_subscribers(conn)
+    # nothing subscribed yet: every list is empty
+    st, off, slot = e.adjacent_broadcast([S0 + 3, S0 + 40], [64, 64])
+    assert st.tolist() == [0, 0] and off.tolist() == [0, 0, 0] and len(slot) == 0
+    e.set_subscriber_types(types)
+    cx, cz = rng.uniform(-450, 450, S), rng.uniform(-200, 200, S)
+    r = rng.choice([10.0, 40.0, 90.0, 160.0], S)
+    batch, keep = chd.engine.make_batch(S, sub=None, sphere=(cx, cz, r))
+    for tick in range(2):  # second update: pairs live in the other buffer, by-cell order rebuilt
+        if tick == 1:
+            cx = cx + rng.uniform(-30, 30, S)
+            batch, keep = chd.engine.make_batch(S, sub=None, sphere=(cx, cz, r))
+        e.update_interest(batch, (tick + 1) * 1000 * MS)
+        s = e.summary()
+        pairs = e.get_pairs(s.n_pairs)
+        # every channel's subscriber list from the engine's (already parity-checked) pairs
+        sub_of_pair = np.repeat(np.arange(S), np.diff(pairs["off"].astype(np.int64)))
+        cell_of_pair = pairs["channel"].astype(np.int64) - S0
+        order = np.lexsort((sub_of_pair, cell_of_pair))
+        cell_off = np.searchsorted(cell_of_pair[order], np.arange(cells + 1)).astype(np.uint32)
+        list_conn, list_type = conn[sub_of_pair[order]], types[sub_of_pair[order]]
+        assert (np.diff(pairs["off"].astype(np.int64)) > 1).sum() > S // 10  # plenty of multi-cell subscribers
+        combos = [0, 4, 8, 16, 32, 4 | 8, 8 | 16, 8 | 32, 4 | 16 | 32, 2]
+        ch, fl, snd, cli = [], [], [], []
+        for c in range(cells):
+            for f in combos:
+                ch.append(S0 + c); fl.append(64 | f)
+                snd.append(int(conn[rng.integers(0, S)]) if rng.random() < 0.8 else 0)
+                cli.append(int(conn[rng.integers(0, S)]) if rng.random() < 0.5 else 0)
+        ch += [S0 + cells, S0 - 1, 5]  # not cells of this grid
+        fl += [64, 64, 64]; snd += [0, 0, 0]; cli += [0, 0, 0]
+        st, off, slot = e.adjacent_broadcast(ch, fl, snd, cli)
+        assert st[-3:].tolist() == [1, 1, 1] and (st[:-3] == 0).all()
+        assert off[-4] == off[-1]  # invalid channels get no recipients
+        n_multi = 0
+        for m in range(len(ch) - 3):
+            got = conn[slot[off[m]:off[m + 1]]]
+            assert len(np.unique(got)) == len(got), "a connection was reported twice"
+            want = oracle.adjacent_broadcast(og, ch[m], fl[m], snd[m], cli[m], cell_off, list_conn, list_type)
+            np.testing.assert_array_equal(np.sort(got), want)
+            n_multi += len(got)
+        assert n_multi > 50_000
+        # without types the client / server filters remove nobody
+        e.set_subscriber_types(None)
+        st2, off2, slot2 = e.adjacent_broadcast([S0 + 40, S0 + 40], [64 | 16, 64])
+        np.testing.assert_array_equal(np.sort(slot2[off2[0]:off2[1]]), np.sort(slot2[off2[1]:off2[2]]))
+        e.set_subscriber_types(types)
+        # capacity is an error, never a truncation
+        with pytest.raises(Exception):
+            e.adjacent_broadcast(ch[:50], fl[:50], cap=3)
 
 
 def test_update_interest_all_aoi_kinds(chd, oracle):
