@@ -374,6 +374,15 @@ def run_ours(args):
         launches = e.launch_count() - launches0
         clocks = sampler.stop(tb, te) if rank == 0 else None
         sm = e.summary()  # raises on any capacity overflow during the timed steps
+        # window classes of the last tick's due list (outside the timed region): distinct payloads a host has to merge
+        n_classes, classes_ms = None, None
+        try:
+            tc0 = time.perf_counter()
+            _, cls_rep, _ = e.due_classes(int(sm.n_due))
+            classes_ms = (time.perf_counter() - tc0) * 1e3
+            n_classes = int(len(cls_rep))
+        except Exception as ex_:  # noqa: BLE001
+            print("due_classes failed: %r" % (ex_,), file=sys.stderr)
         # write-only stream of the same size as the visible list (torch fill): the DRAM-side ceiling of the emit kernel
         wp = None
         try:
@@ -584,7 +593,8 @@ def run_ours(args):
             "stage_ms": stage,
             "last_tick_timeline_ms": timeline,
             "per_tick": {"pairs": tot_pairs, "visible": tot_vis, "fanout_decisions": tot_due, "handover": int(sm.n_handover),
-                         "fanout_msgs_per_s": tot_due / (ms_step * 1e-3)},
+                         "fanout_msgs_per_s": tot_due / (ms_step * 1e-3),
+                         "window_classes_rank0": n_classes, "window_classes_call_ms": classes_ms},
             "parity_gate": gate,
         }
         if world == 1 and not args.no_cpu_baseline:

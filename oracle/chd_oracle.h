@@ -6,6 +6,7 @@
  *   pkg/channeld/message_spatial.go (damping table + interest diff)
  *   pkg/channeld/data.go           (OnUpdate ring + tickData fan-out windows)
  *   pkg/channeld/subscription.go   (fan-out state initialisation)
+ *   pkg/channeld/message.go:188-239 (ADJACENT_CHANNELS broadcast recipients)
  *   pkg/common/common.go           (Dist2D / Dot2D / Normalize2D)
  * of channeldorg/channeld @ 61fa8add.  Every function cites the file:line it follows.
  *
@@ -20,8 +21,9 @@
  *     data_test.go:168-197 does not follow from the code as written and is not used.
  *   - math.Cos (Go stdlib, go 1.25 per go.mod:3; source NOT under /root/reference): restated
  *     from the published Cephes-derived algorithm; cone AOI is "parity unpinned" beyond TestConeAOI.
- *   - SpotsAOI, dist values, damping, interest diff, visible-entity sets: no reference test
- *     exists ("parity unpinned" by the reference); the restatement itself is the ground truth.
+ *   - SpotsAOI, dist values, damping, interest diff, visible-entity sets, the ADJACENT_CHANNELS broadcast
+ *     branch (message.go:188-239): no reference test exists ("parity unpinned" by the reference); the
+ *     restatement itself is the ground truth.
  *
  * Numerics: IEEE binary64, round-to-nearest, compiled with -ffp-contract=off (Go/amd64 does not fuse).
  */
