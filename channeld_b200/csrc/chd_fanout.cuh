@@ -35,7 +35,8 @@ __device__ __forceinline__ DueKey make_due_key(uint32_t cell, uint32_t kind, boo
 constexpr uint32_t FANOUT_MAX_STEPS = 1u << 16;
 constexpr uint32_t FANOUT_SLOTS = 2;            // decisions per pair kept by the evaluation pass
 
-// The per-pair state machine of tickData.  Decisions j < n_keep are handed to `emit(j, decision)`.
+// The per-pair state machine of tickData.  Decisions are handed to `emit(j, decision, skipped)`; skipped = an own update
+// fell into the decision's window and was left out.  (The window's lower end is window_hi - interval: not passed.)
 // Returns the number of decisions; the final state is left in (last, flags, last_index).
 template <typename Emit>
 __device__ __forceinline__ uint32_t fanout_eval(const RingDev& ring, uint32_t ring_total, int64_t t, uint32_t interval, uint32_t c, uint32_t s,
@@ -56,7 +57,7 @@ __device__ __forceinline__ uint32_t fanout_eval(const RingDev& ring, uint32_t ri
             chd_due d;
             d.sub = s; d.channel_id = c + id_start; d.kind = 0; d.n_selected = 0; d.first_sel = 0; d.last_sel = 0;
             d.sel_hash = 0; d.last_message_index = last_index; d.window_hi = next;
-            emit(n_out, d, make_due_key(c, 0u, false, s, 0));
+            emit(n_out, d, false);
             n_out++;
         } else if (r1 > r0) {  // data.go:225-265
             int64_t last_update = 0;
@@ -84,7 +85,7 @@ __device__ __forceinline__ uint32_t fanout_eval(const RingDev& ring, uint32_t ri
                 chd_due d;
                 d.sub = s; d.channel_id = c + id_start; d.kind = 1; d.n_selected = nsel; d.first_sel = first; d.last_sel = lastsel;
                 d.sel_hash = hash; d.last_message_index = last_index; d.window_hi = next;
-                emit(n_out, d, make_due_key(c, 1u, skipped, s, last));
+                emit(n_out, d, skipped);
                 n_out++;
             }
         }
@@ -99,7 +100,7 @@ __device__ __forceinline__ uint32_t fanout_eval(const RingDev& ring, uint32_t ri
 // Pairs with more decisions (several intervals behind) re-evaluate from their saved state while writing.
 // The due list is therefore grouped by block and unordered across blocks: it is a SET of send decisions (the
 // reference issues them from independent per-channel goroutines, i.e. in no global order either).
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)  // <= 85 registers: the whole pair list of config #2 (855 CTAs) stays one wave on 148 SMs
     fanout_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, PairBuf pb, const uint32_t* __restrict__ conn_id, RingDev ring,
                   const int64_t* __restrict__ t_ptr, uint32_t id_start, const uint32_t* __restrict__ by_cell, chd_due* __restrict__ due,
                   DueKey* __restrict__ due_key, uint32_t due_cap, Counters* __restrict__ ctr) {
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(128)
         int64_t last0 = 0, last = 0;
         uint8_t flags0 = 0, flags = 0;
         chd_due d0, d1;
-        DueKey k0{}, k1{};
+        bool sk0 = false, sk1 = false;
         if (i < n) {
             p = by_cell[i];
             interval = pb.interval[p];
@@ -128,9 +129,9 @@ __global__ void __launch_bounds__(128)
                 s = pb.sub[p];
                 me = conn_id[s];
                 n_out = fanout_eval(ring, ring_total, t, interval, c, s, me, id_start, last, flags, last_index,
-                                    [&](uint32_t j, const chd_due& d, const DueKey& k) {
-                                        if (j == 0) { d0 = d; k0 = k; }
-                                        else if (j == 1) { d1 = d; k1 = k; }
+                                    [&](uint32_t j, const chd_due& d, bool skipped) {
+                                        if (j == 0) { d0 = d; sk0 = skipped; }
+                                        else if (j == 1) { d1 = d; sk1 = skipped; }
                                     });
             }
         }
@@ -153,15 +154,16 @@ __global__ void __launch_bounds__(128)
         __syncthreads();
         if (n_out) {
             const uint32_t o = s_base + off;
+            const int64_t step_ns = (int64_t)interval * 1000000ll;  // an UPDATE decision's window starts at window_hi - interval
             if ((uint64_t)o + n_out > due_cap) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_DUE);
             if (n_out <= FANOUT_SLOTS) {
-                if (o < due_cap) { due[o] = d0; due_key[o] = k0; }
-                if (n_out > 1 && o + 1 < due_cap) { due[o + 1] = d1; due_key[o + 1] = k1; }
+                if (o < due_cap) { due[o] = d0; due_key[o] = make_due_key(c, d0.kind, sk0, s, d0.window_hi - step_ns); }
+                if (n_out > 1 && o + 1 < due_cap) { due[o + 1] = d1; due_key[o + 1] = make_due_key(c, d1.kind, sk1, s, d1.window_hi - step_ns); }
             } else {  // several intervals behind: re-evaluate from the saved state, writing directly
                 last = last0; flags = flags0; last_index = last_index0;
                 fanout_eval(ring, ring_total, t, interval, c, s, me, id_start, last, flags, last_index,
-                            [&](uint32_t j, const chd_due& d, const DueKey& k) {
-                                if (o + j < due_cap) { due[o + j] = d; due_key[o + j] = k; }
+                            [&](uint32_t j, const chd_due& d, bool skipped) {
+                                if (o + j < due_cap) { due[o + j] = d; due_key[o + j] = make_due_key(c, d.kind, skipped, s, d.window_hi - step_ns); }
                             });
             }
         }
