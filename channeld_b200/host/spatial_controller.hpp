@@ -144,6 +144,57 @@ class GpuStaticGrid2DSpatialController {
         return s;
     }
 
+    // Pipelined host loop (include/chd_gpu.h): the inputs of tick k+1 go up while tick k runs, tick k+1 starts with
+    // AdoptPrefetched() + BeginInterest(nullptr, ...) and Tick(nullptr, t, CHD_TICK_ALL | CHD_TICK_EARLY_RESULTS).
+    void PrefetchEntities(const double* x, const double* z, uint32_t n) { check(chd_prefetch_entities(engine_, x, z, n)); }
+    void PrefetchQueries(const chd_query_batch& batch) { check(chd_prefetch_queries(engine_, &batch)); }
+    void PrefetchRings(const uint32_t* ring_off, uint32_t n_entries, const int64_t* arrival, const uint32_t* sender, const uint64_t* index,
+                       const uint64_t* ch_msg_index) {
+        check(chd_prefetch_rings(engine_, ring_off, n_entries, arrival, sender, index, ch_msg_index));
+    }
+    void AdoptPrefetched() { check(chd_adopt_prefetched(engine_)); }
+    void BeginInterest(const chd_query_batch* batch, int64_t t_ns, bool with_fanout = true) {
+        check(chd_begin_interest(engine_, batch, t_ns, with_fanout ? 1 : 0));
+    }
+    void FetchResults(const chd_result_buffers& buffers, chd_tick_summary* summary) { check(chd_fetch_results(engine_, &buffers, summary)); }
+
+    // Recipients of BroadcastType_ADJACENT_CHANNELS messages (message.go:188-239), batched: CSR of subscriber slots.
+    struct BroadcastSets {
+        std::vector<uint32_t> status, off, slot;
+    };
+    BroadcastSets AdjacentBroadcast(const std::vector<uint32_t>& channel_id, const std::vector<uint32_t>& broadcast,
+                                    const std::vector<uint32_t>& sender_conn_id, const std::vector<uint32_t>& client_conn_id, uint64_t cap) {
+        const uint32_t n = (uint32_t)channel_id.size();
+        if (broadcast.size() != n || (!sender_conn_id.empty() && sender_conn_id.size() != n) ||
+            (!client_conn_id.empty() && client_conn_id.size() != n))
+            throw SpatialError("AdjacentBroadcast: array sizes differ");
+        chd_broadcast_batch b{n, channel_id.data(), broadcast.data(), sender_conn_id.empty() ? nullptr : sender_conn_id.data(),
+                              client_conn_id.empty() ? nullptr : client_conn_id.data()};
+        BroadcastSets r;
+        r.status.resize(n);
+        r.off.resize((size_t)n + 1);
+        r.slot.resize(cap);
+        check(chd_adjacent_broadcast(engine_, &b, r.status.data(), r.off.data(), r.slot.data(), cap));
+        r.slot.resize(r.off[n]);
+        return r;
+    }
+
+    // Window classes of the last fan-out pass (data.go:248-252: which decisions share one merged payload).
+    struct DueClasses {
+        std::vector<uint32_t> class_of, rep, count;
+    };
+    DueClasses GetDueClasses(uint32_t n_due) {
+        DueClasses r;
+        r.class_of.resize(n_due);
+        r.rep.resize(n_due ? n_due : 1);
+        r.count.resize(n_due ? n_due : 1);
+        uint32_t n = 0;
+        check(chd_due_classes(engine_, r.class_of.data(), r.rep.data(), r.count.data(), (uint32_t)r.rep.size(), &n));
+        r.rep.resize(n);
+        r.count.resize(n);
+        return r;
+    }
+
     chd_engine* engine() { return engine_; }
 
    private:

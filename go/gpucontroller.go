@@ -248,3 +248,110 @@ func (ctl *GpuStaticGrid2DSpatialController) TickBatch(in *GpuTickInput, now Cha
 	}
 	return sum, nil
 }
+
+// PrefetchTick / TickPrefetched are the pipelined form of TickBatch (INTEGRATION.md §2): while tick k is in flight the
+// driver hands the inputs of tick k+1 — collected into a SECOND set of pinned staging slices — to PrefetchTick, which
+// only starts asynchronous uploads on the engine's upload stream; tick k+1 is then started with TickPrefetched, which
+// adopts them, starts the interest / fan-out chain, runs build + emit with CHD_TICK_EARLY_RESULTS and leaves the read-back
+// to FetchResults (chd_fetch_results copies each list as soon as it is final, while the expanded-list kernel still runs).
+// The slices passed to PrefetchTick must stay untouched until the tick that consumes them has been fetched.
+func (ctl *GpuStaticGrid2DSpatialController) PrefetchTick(in *GpuTickInput) error {
+	e := ctl.engine
+	fail := func() error { return errors.New(C.GoString(C.chd_last_error(e))) }
+	if len(in.RingOff) > 0 {
+		total := in.RingOff[len(in.RingOff)-1]
+		var a *C.int64_t
+		var s *C.uint32_t
+		var i *C.uint64_t
+		if total > 0 {
+			a, s, i = (*C.int64_t)(unsafe.Pointer(&in.RingArrival[0])), (*C.uint32_t)(unsafe.Pointer(&in.RingSender[0])), (*C.uint64_t)(unsafe.Pointer(&in.RingIndex[0]))
+		}
+		if st := C.chd_prefetch_rings(e, (*C.uint32_t)(unsafe.Pointer(&in.RingOff[0])), C.uint32_t(total), a, s, i,
+			(*C.uint64_t)(unsafe.Pointer(&in.ChannelMsgIndex[0]))); st != C.CHD_OK {
+			return fail()
+		}
+	}
+	if nq := len(in.ConnSlot); nq > 0 {
+		var b C.chd_query_batch
+		b.n = C.uint32_t(nq)
+		b.sub = (*C.uint32_t)(unsafe.Pointer(&in.ConnSlot[0]))
+		b.sph_cx, b.sph_cz, b.sph_r = (*C.double)(unsafe.Pointer(&in.SphX[0])), (*C.double)(unsafe.Pointer(&in.SphZ[0])), (*C.double)(unsafe.Pointer(&in.SphR[0]))
+		if st := C.chd_prefetch_queries(e, &b); st != C.CHD_OK {
+			return fail()
+		}
+	}
+	if n := len(in.EntityX); n > 0 {
+		if st := C.chd_prefetch_entities(e, (*C.double)(unsafe.Pointer(&in.EntityX[0])), (*C.double)(unsafe.Pointer(&in.EntityZ[0])), C.uint32_t(n)); st != C.CHD_OK {
+			return fail()
+		}
+	}
+	return nil
+}
+
+// TickPrefetched starts the tick whose inputs PrefetchTick uploaded.  hadQueries = that input carried a query batch.
+func (ctl *GpuStaticGrid2DSpatialController) TickPrefetched(now ChannelTime, hadQueries bool) error {
+	e := ctl.engine
+	fail := func() error { return errors.New(C.GoString(C.chd_last_error(e))) }
+	if st := C.chd_adopt_prefetched(e); st != C.CHD_OK {
+		return fail()
+	}
+	if hadQueries {
+		if st := C.chd_begin_interest(e, nil, C.int64_t(now), 1); st != C.CHD_OK {
+			return fail()
+		}
+	}
+	if st := C.chd_tick(e, nil, C.int64_t(now), C.CHD_TICK_ALL|C.CHD_TICK_EARLY_RESULTS, nil); st != C.CHD_OK {
+		return fail()
+	}
+	return nil
+}
+
+// FetchResults copies every host-facing result of the tick into caller-owned (pinned) buffers.
+func (ctl *GpuStaticGrid2DSpatialController) FetchResults(buffers *C.chd_result_buffers) (C.chd_tick_summary, error) {
+	var sum C.chd_tick_summary
+	if st := C.chd_fetch_results(ctl.engine, buffers, &sum); st != C.CHD_OK {
+		return sum, errors.New(C.GoString(C.chd_last_error(ctl.engine)))
+	}
+	return sum, nil
+}
+
+// AdjacentBroadcast replaces the per-message map merge of message.go:188-239 for a batch of
+// BroadcastType_ADJACENT_CHANNELS messages: recipients of message m are slots[off[m]:off[m+1]] (subscriber slots).
+// Connection types for the ALL_BUT_CLIENT / ALL_BUT_SERVER filters are registered once with chd_set_subscriber_types.
+func (ctl *GpuStaticGrid2DSpatialController) AdjacentBroadcast(channelIds []common.ChannelId, broadcast, senderConnId, clientConnId []uint32, capSlots int) (status, off, slots []uint32, err error) {
+	n := len(channelIds)
+	status, off, slots = make([]uint32, n), make([]uint32, n+1), make([]uint32, capSlots)
+	if n == 0 {
+		return status, off, slots[:0], nil
+	}
+	b := C.chd_broadcast_batch{n: C.uint32_t(n), channel_id: (*C.uint32_t)(unsafe.Pointer(&channelIds[0])), broadcast: (*C.uint32_t)(unsafe.Pointer(&broadcast[0]))}
+	if len(senderConnId) == n {
+		b.sender_conn_id = (*C.uint32_t)(unsafe.Pointer(&senderConnId[0]))
+	}
+	if len(clientConnId) == n {
+		b.client_conn_id = (*C.uint32_t)(unsafe.Pointer(&clientConnId[0]))
+	}
+	var slotPtr *C.uint32_t
+	if capSlots > 0 {
+		slotPtr = (*C.uint32_t)(unsafe.Pointer(&slots[0]))
+	}
+	if st := C.chd_adjacent_broadcast(ctl.engine, &b, (*C.uint32_t)(unsafe.Pointer(&status[0])), (*C.uint32_t)(unsafe.Pointer(&off[0])), slotPtr, C.uint64_t(capSlots)); st != C.CHD_OK {
+		return nil, nil, nil, errors.New(C.GoString(C.chd_last_error(ctl.engine)))
+	}
+	return status, off, slots[:off[n]], nil
+}
+
+// DueClasses groups the due list of the last tick by payload identity (data.go:248-252 merges afresh per subscriber):
+// the host merges / marshals the window of due record rep[k] once and sends it to every record i with classOf[i] == k.
+func (ctl *GpuStaticGrid2DSpatialController) DueClasses(nDue int) (classOf, rep, count []uint32, err error) {
+	if nDue == 0 {
+		return nil, nil, nil, nil
+	}
+	classOf, rep, count = make([]uint32, nDue), make([]uint32, nDue), make([]uint32, nDue)
+	var n C.uint32_t
+	if st := C.chd_due_classes(ctl.engine, (*C.uint32_t)(unsafe.Pointer(&classOf[0])), (*C.uint32_t)(unsafe.Pointer(&rep[0])),
+		(*C.uint32_t)(unsafe.Pointer(&count[0])), C.uint32_t(nDue), &n); st != C.CHD_OK {
+		return nil, nil, nil, errors.New(C.GoString(C.chd_last_error(ctl.engine)))
+	}
+	return classOf, rep[:n], count[:n], nil
+}

@@ -98,6 +98,12 @@ def test_cpp_host_mirror_compiles(tmp_path):
 
     src = tmp_path / "host_check.cpp"
     src.write_text('#include "channeld_b200/host/spatial_controller.hpp"\n'
+                   '// instantiate the whole method set (never called: there is no GPU on the build host)\n'
+                   'void use_all(channeld::GpuStaticGrid2DSpatialController& c, const chd_query_batch& b, const chd_result_buffers& rb) {\n'
+                   '  chd_tick_summary s{}; c.PrefetchEntities(nullptr, nullptr, 0); c.PrefetchQueries(b);\n'
+                   '  c.PrefetchRings(nullptr, 0, nullptr, nullptr, nullptr, nullptr); c.AdoptPrefetched(); c.BeginInterest(nullptr, 0);\n'
+                   '  c.Tick(nullptr, 0, CHD_TICK_ALL | CHD_TICK_EARLY_RESULTS); c.FetchResults(rb, &s);\n'
+                   '  c.AdjacentBroadcast({65536}, {64}, {}, {}, 16); c.GetDueClasses(s.n_due); }\n'
                    'int main() { channeld::GpuStaticGrid2DSpatialController c; return c.GetAdjacentChannels(65536).size() == 0 ? 0 : 1; }\n')
     lib_dir = os.path.dirname(capi.lib_path())
     exe = tmp_path / "host_check"
