@@ -217,8 +217,10 @@ typedef struct chd_tick_summary {
     uint32_t required_due;
     uint32_t reserved;
 } chd_tick_summary;
-enum { CHD_OVF_PAIRS = 1, CHD_OVF_WINDOW = 2, CHD_OVF_VISIBLE = 4, CHD_OVF_DUE = 8, CHD_OVF_BORDER = 16,
-       CHD_OVF_INTERNAL = 0x80000000u /* a device-side wait timed out: results invalid, please report */ };
+enum { CHD_OVF_PAIRS = 1, CHD_OVF_WINDOW = 2, CHD_OVF_VISIBLE = 4, CHD_OVF_DUE = 8, CHD_OVF_BORDER = 16 };
+/* bit 31: a device-side wait timed out (results invalid, please report).  A macro, not an enumerator: ISO C enumerators
+ * must fit an int. */
+#define CHD_OVF_INTERNAL 0x80000000u
 
 /* Synchronises the stream and returns the counters.  CHD_ERR_CAPACITY if any overflow bit is set. */
 chd_status chd_summary(chd_engine* e, chd_tick_summary* out);

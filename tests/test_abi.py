@@ -37,6 +37,32 @@ def test_struct_layouts_match_header():
     assert C.sizeof(capi.QueryBatch) == 8 + 20 * 8
 
 
+def test_header_is_plain_c_and_ctypes_mirrors_it(tmp_path):
+    """include/chd_gpu.h compiles as C99 (it is what cgo / JNI / ctypes bind) and every struct the Python binding
+    mirrors has the size and field offsets the C compiler gives it."""
+    import subprocess
+
+    from channeld_b200 import capi
+
+    pairs = [("chd_grid_cfg", capi.GridCfg), ("chd_limits", capi.Limits), ("chd_query_batch", capi.QueryBatch), ("chd_due", capi.Due),
+             ("chd_tick_summary", capi.TickSummary), ("chd_result_buffers", capi.ResultBuffers), ("chd_broadcast_batch", capi.BroadcastBatch)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "chd_gpu.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        lines.append('  printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in pairs:
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
+
+
 def test_host_helpers_match_oracle(oracle):
     """GetAdjacentChannels / GetRegions / damping are plain host integer math in the library: checked here."""
     from channeld_b200 import capi
