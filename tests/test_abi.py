@@ -63,6 +63,37 @@ def test_header_is_plain_c_and_ctypes_mirrors_it(tmp_path):
             assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
 
 
+def test_null_engine_is_an_error_everywhere():
+    """Error behaviour of the boundary: every entry point that takes an engine handle returns CHD_ERR_INVALID for a NULL
+    handle (no crash, no CUDA call).  Runs in a subprocess so that a missing check cannot take pytest down with it."""
+    import subprocess
+    import sys
+
+    code = '''
+import ctypes as C, sys
+sys.path.insert(0, %r)
+from channeld_b200 import capi
+L = capi.lib()
+no_handle = {"chd_abi_version", "chd_default_limits", "chd_create", "chd_destroy", "chd_last_error", "chd_alloc_pinned", "chd_free_pinned",
+             "chd_get_adjacent_channels", "chd_get_regions", "chd_damping_interval_ms", "chd_launch_count", "chd_graph_launch_count"}
+bad = []
+for name in capi.SYMBOLS:
+    if name in no_handle:
+        continue
+    f = getattr(L, name)
+    assert f.argtypes is not None, name
+    args = [0.0 if t is C.c_double else (None if (t is C.c_void_p or hasattr(t, "contents")) else 0) for t in f.argtypes]
+    if f(*args) != capi.ERR_INVALID:
+        bad.append(name)
+L.chd_destroy(None)
+assert L.chd_launch_count(None) == 0 and L.chd_graph_launch_count(None) == 0
+print("BAD", bad)
+''' % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "BAD []" in out.stdout, out.stdout
+
+
 def test_host_helpers_match_oracle(oracle):
     """GetAdjacentChannels / GetRegions / damping are plain host integer math in the library: checked here."""
     from channeld_b200 import capi
