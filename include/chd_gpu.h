@@ -267,9 +267,13 @@ chd_status chd_get_due(chd_engine* e, chd_due* out, uint32_t cap);
 /* handover candidates of the last build: entity, src channel id, dst channel id (0 = left/entered the world) */
 chd_status chd_get_handover(chd_engine* e, uint32_t* entity, uint32_t* src_channel, uint32_t* dst_channel, uint32_t cap);
 
-/* ---- all host-facing results of a tick with TWO synchronisations instead of one or two per getter: waits for
- * the tick, reads the summary, then enqueues every requested copy (exact sizes from the summary) and waits once.
- * Any pointer may be NULL (skipped).  Capacities are in elements; CHD_ERR_CAPACITY if a requested list does not
+/* ---- all host-facing results of a tick in ONE call instead of one or two synchronisations per getter.  After a
+ * two-stream tick (chd_tick with emit, or chd_begin_interest + chd_tick) the lists are copied in the order they become
+ * final, on the engine's read-back streams, while the expanded-list kernel may still be running: first the pairs /
+ * sub-unsub lists / query statuses / handover list / cell CSR (after the interest fill and the build), then the due list
+ * and the visible offsets (after the fan-out pass and the emit preparation; see CHD_TICK_EARLY_RESULTS); the call returns
+ * when the tick has finished.  Otherwise: waits for the tick, reads the summary, enqueues every copy, waits once.
+ * Exact sizes come from the device counters.  Any pointer may be NULL (skipped).  Capacities are in elements; CHD_ERR_CAPACITY if a requested list does not
  * fit (nothing is truncated silently).  This is what a channeld host calls once per tick. */
 typedef struct chd_result_buffers {
     uint32_t *pair_off, *pair_channel, *pair_dist, *pair_interval_ms; /* pair_off[n_subscribers+1]; others [pair_cap] */
