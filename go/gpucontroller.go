@@ -21,6 +21,7 @@ import (
 	"encoding/json"
 	"errors"
 	"fmt"
+	"runtime"
 	"sync"
 	"unsafe"
 
@@ -140,8 +141,21 @@ func (ctl *GpuStaticGrid2DSpatialController) QueryChannelIds(query *channeldpb.S
 		cone = [6]C.double{C.double(q.Center.X), C.double(q.Center.Z), C.double(q.Direction.X), C.double(q.Direction.Z),
 			C.double(q.Angle), C.double(q.Radius)}
 	}
-	// cgo rule: no Go pointers to Go pointers — the batch struct lives in C memory-free stack and only holds
-	// pointers to pinned-for-the-call Go arrays (runtime.Pinner in Go >= 1.21) or C.malloc'ed staging.
+	// cgo pointer-passing rule: &b is Go memory that holds Go pointers, which is only legal while those pointers are
+	// pinned (runtime.Pinner, Go >= 1.21; go.mod of the reference says 1.25).  The call is synchronous.
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	pin.Pin(&kind)
+	pin.Pin(&sph)
+	pin.Pin(&box)
+	pin.Pin(&cone)
+	pin.Pin(&spotOff)
+	pin.Pin(&spotN)
+	if len(sx) > 0 {
+		pin.Pin(&sx[0])
+		pin.Pin(&sz[0])
+		pin.Pin(&sd[0])
+	}
 	b.kind = &kind
 	b.sph_cx, b.sph_cz, b.sph_r = &sph[0], &sph[1], &sph[2]
 	b.box_cx, b.box_cz, b.box_ex, b.box_ez = &box[0], &box[1], &box[2], &box[3]
@@ -217,6 +231,17 @@ type GpuTickInput struct {
 func (ctl *GpuStaticGrid2DSpatialController) TickBatch(in *GpuTickInput, now ChannelTime) (C.chd_tick_summary, error) {
 	var sum C.chd_tick_summary
 	e := ctl.engine
+	// The query batch struct below holds pointers into in.*: legal for Go-heap slices only while pinned (see
+	// QueryChannelIds); slices carved out of chd_alloc_pinned memory (PinnedFloat64s & co.) are C memory and need no pin.
+	// chd_tick is called with a summary, i.e. synchronously: every async copy has completed when it returns.
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	if len(in.ConnSlot) > 0 {
+		pin.Pin(&in.ConnSlot[0])
+		pin.Pin(&in.SphX[0])
+		pin.Pin(&in.SphZ[0])
+		pin.Pin(&in.SphR[0])
+	}
 	if n := len(in.EntityX); n > 0 {
 		if st := C.chd_set_entities(e, (*C.double)(unsafe.Pointer(&in.EntityX[0])), (*C.double)(unsafe.Pointer(&in.EntityZ[0])), C.uint32_t(n)); st != C.CHD_OK {
 			return sum, errors.New(C.GoString(C.chd_last_error(e)))
@@ -254,7 +279,9 @@ func (ctl *GpuStaticGrid2DSpatialController) TickBatch(in *GpuTickInput, now Cha
 // only starts asynchronous uploads on the engine's upload stream; tick k+1 is then started with TickPrefetched, which
 // adopts them, starts the interest / fan-out chain, runs build + emit with CHD_TICK_EARLY_RESULTS and leaves the read-back
 // to FetchResults (chd_fetch_results copies each list as soon as it is final, while the expanded-list kernel still runs).
-// The slices passed to PrefetchTick must stay untouched until the tick that consumes them has been fetched.
+// The uploads are ASYNCHRONOUS: the slices passed to PrefetchTick must be carved out of chd_alloc_pinned memory
+// (PinnedFloat64s / PinnedUint32s / ...: C memory, so no Go pointer is retained by C after the call returns — the cgo
+// rule) and must stay untouched until the tick that consumes them has been fetched.
 func (ctl *GpuStaticGrid2DSpatialController) PrefetchTick(in *GpuTickInput) error {
 	e := ctl.engine
 	fail := func() error { return errors.New(C.GoString(C.chd_last_error(e))) }
@@ -324,11 +351,17 @@ func (ctl *GpuStaticGrid2DSpatialController) AdjacentBroadcast(channelIds []comm
 	if n == 0 {
 		return status, off, slots[:0], nil
 	}
+	var pin runtime.Pinner // the batch struct holds pointers to Go slices: pinned for this synchronous call
+	defer pin.Unpin()
+	pin.Pin(&channelIds[0])
+	pin.Pin(&broadcast[0])
 	b := C.chd_broadcast_batch{n: C.uint32_t(n), channel_id: (*C.uint32_t)(unsafe.Pointer(&channelIds[0])), broadcast: (*C.uint32_t)(unsafe.Pointer(&broadcast[0]))}
 	if len(senderConnId) == n {
+		pin.Pin(&senderConnId[0])
 		b.sender_conn_id = (*C.uint32_t)(unsafe.Pointer(&senderConnId[0]))
 	}
 	if len(clientConnId) == n {
+		pin.Pin(&clientConnId[0])
 		b.client_conn_id = (*C.uint32_t)(unsafe.Pointer(&clientConnId[0]))
 	}
 	var slotPtr *C.uint32_t
@@ -355,3 +388,20 @@ func (ctl *GpuStaticGrid2DSpatialController) DueClasses(nDue int) (classOf, rep,
 	}
 	return classOf, rep[:n], count[:n], nil
 }
+
+// PinnedFloat64s / PinnedUint32s / PinnedInt64s / PinnedUint64s carve staging slices out of page-locked C memory
+// (chd_alloc_pinned): uploads from them are truly asynchronous and, being C memory, they may be referenced by the
+// engine after a cgo call has returned (PrefetchTick).  Release with FreePinned(unsafe.Pointer(&s[0])).
+func PinnedFloat64s(n int) []float64 {
+	return unsafe.Slice((*float64)(C.chd_alloc_pinned(C.uint64_t(8*n))), n)
+}
+func PinnedUint32s(n int) []uint32 {
+	return unsafe.Slice((*uint32)(C.chd_alloc_pinned(C.uint64_t(4*n))), n)
+}
+func PinnedInt64s(n int) []int64 {
+	return unsafe.Slice((*int64)(C.chd_alloc_pinned(C.uint64_t(8*n))), n)
+}
+func PinnedUint64s(n int) []uint64 {
+	return unsafe.Slice((*uint64)(C.chd_alloc_pinned(C.uint64_t(8*n))), n)
+}
+func FreePinned(p unsafe.Pointer) { C.chd_free_pinned(p) }
