@@ -7,7 +7,8 @@ from channeld_b200 import synth
 def test_splitmix64_known_answers():
     # splitmix64 reference sequence for seed 0 (public test vector of the algorithm): first outputs of
     # state += golden; mix(state)
-    got = [int(synth.splitmix64(np.uint64(0) + np.uint64(k) * synth._GOLDEN)) for k in range(3)]
+    states = np.arange(3, dtype=np.uint64) * synth._GOLDEN  # wraps mod 2^64 (array arithmetic: no overflow warning)
+    got = [int(v) for v in synth.splitmix64(states)]
     assert got == [0xE220A8397B1DCDAF, 0x6E789E6AA1B965F4, 0x06C45D188009454F]
 
 
