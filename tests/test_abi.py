@@ -63,6 +63,25 @@ def test_header_is_plain_c_and_ctypes_mirrors_it(tmp_path):
             assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
 
 
+def test_c_example_compiles_links_and_fails_loudly_without_gpu(tmp_path):
+    """examples/tick_loop.c (the pipelined host loop in plain C99) builds against the header and the library; on a box
+    without a GPU it stops at chd_create with the 'no CPU fallback' error instead of computing anything."""
+    import subprocess
+
+    from channeld_b200 import capi
+
+    lib_dir = os.path.dirname(capi.lib_path())
+    exe = tmp_path / "tick_loop"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "tick_loop.c"), "-L", lib_dir, "-lchd_b200", "-Wl,-rpath," + lib_dir,
+                           "-Wl,-rpath,/usr/local/cuda/lib64", "-L/usr/local/cuda/lib64", "-o", str(exe)])
+    import torch
+
+    if not torch.cuda.is_available():
+        out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 2 and "no CPU fallback" in out.stderr
+
+
 def test_null_engine_is_an_error_everywhere():
     """Error behaviour of the boundary: every entry point that takes an engine handle returns CHD_ERR_INVALID for a NULL
     handle (no crash, no CUDA call).  Runs in a subprocess so that a missing check cannot take pytest down with it."""
