@@ -19,7 +19,8 @@ f64p = C.POINTER(C.c_double)
 
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_STATE = 0, 1, 2, 3, 4
 AOI_SPOTS, AOI_BOX, AOI_SPHERE, AOI_CONE = 1, 2, 4, 8
-Q_OK, Q_ERR_OUT_OF_WORLD, Q_ERR_BAD_STEP, Q_ERR_ITER_BOUND, Q_ERR_ANGLE_RANGE = 0, 1, 2, 5, 6
+Q_OK, Q_ERR_OUT_OF_WORLD, Q_ERR_BAD_STEP, Q_ERR_ITER_BOUND, Q_ERR_ANGLE_RANGE, Q_ERR_CAPACITY, Q_ERR_MISSING_ARRAY = 0, 1, 2, 5, 6, 7, 8
+DUE_VOID = 0xFFFFFFFF
 TICK_BUILD, TICK_EMIT, TICK_FANOUT, TICK_ALL = 1, 2, 4, 7
 TICK_EARLY_RESULTS = 8
 OVF_PAIRS, OVF_WINDOW, OVF_VISIBLE, OVF_DUE, OVF_BORDER = 1, 2, 4, 8, 16
@@ -110,7 +111,7 @@ class TickSummary(C.Structure):
 # every symbol include/chd_gpu.h declares (checked by tests/test_abi.py against the header text)
 SYMBOLS = [
     "chd_abi_version", "chd_default_limits", "chd_create", "chd_destroy", "chd_last_error", "chd_set_stream", "chd_sync",
-    "chd_alloc_pinned", "chd_free_pinned", "chd_cell_of", "chd_set_entities", "chd_prefetch_entities", "chd_prefetch_queries", "chd_prefetch_rings", "chd_adopt_prefetched", "chd_entity_buffers", "chd_set_entity_count",
+    "chd_alloc_pinned", "chd_free_pinned", "chd_cell_of", "chd_cell_of_valid", "chd_set_entities", "chd_prefetch_entities", "chd_prefetch_queries", "chd_prefetch_rings", "chd_adopt_prefetched", "chd_entity_buffers", "chd_set_entity_count",
     "chd_assign_cells", "chd_build", "chd_set_subscribers", "chd_query_channel_ids", "chd_update_interest",
     "chd_emit_visible", "chd_set_rings", "chd_fanout_tick", "chd_summary", "chd_tick", "chd_begin_interest", "chd_get_cells", "chd_get_pairs",
     "chd_get_query_status", "chd_get_diff", "chd_get_visible", "chd_get_visible_slot", "chd_get_due", "chd_fetch_results", "chd_get_handover", "chd_device_view",
@@ -150,6 +151,8 @@ def lib():
     L.chd_free_pinned.argtypes = [vp]
     L.chd_cell_of.restype = C.c_int
     L.chd_cell_of.argtypes = [vp, vp, vp, C.c_uint32, vp]
+    L.chd_cell_of_valid.restype = C.c_int
+    L.chd_cell_of_valid.argtypes = [vp, vp, vp, C.c_uint32, vp, vp]
     L.chd_set_entities.restype = C.c_int
     L.chd_set_entities.argtypes = [vp, vp, vp, C.c_uint32]
     L.chd_prefetch_entities.restype = C.c_int

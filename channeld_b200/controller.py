@@ -156,8 +156,9 @@ class GpuStaticGrid2DSpatialController:
 
     # -- GetChannelId(info SpatialInfo) (ChannelId, error)   (spatial.go:161-163)
     def GetChannelId(self, info: SpatialInfo) -> int:
-        cid = int(self.engine.cell_of(np.array([info.X]), np.array([info.Z]))[0])
-        if cid == 0:
+        ids, ok = self.engine.cell_of(np.array([info.X]), np.array([info.Z]), with_valid=True)
+        cid = int(ids[0])
+        if not ok[0]:  # (an explicit flag: with SpatialChannelIdStart == 0 the id 0 is a real cell)
             raise SpatialError("position (%f, %f) is outside the grid" % (info.X, info.Z))
         return cid
 

@@ -10,14 +10,9 @@
 // (its own pair run is sorted by cell, so "first" = no smaller member cell in the run): that is the de-duplication the
 // reference does with a Go map.  The result is a SET per message (the reference iterates a map: no order).
 #pragma once
-#include "chd_interest.cuh"
+#include "chd_types.cuh"
 
 namespace chd {
-
-struct BcastDev {
-    uint32_t n;
-    const uint32_t *channel, *flags, *sender, *client;
-};
 
 enum : uint32_t {  // channeldpb.BroadcastType (channeld.proto), Check() = any bit in common (channeldpb/extension.go:5-7)
     BC_ALL_BUT_SENDER = 4, BC_ALL_BUT_OWNER = 8, BC_ALL_BUT_CLIENT = 16, BC_ALL_BUT_SERVER = 32
@@ -63,7 +58,7 @@ __global__ void __launch_bounds__(256)
                  unsigned long long* bump_epoch) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (!WRITE && bump_epoch && blockIdx.x == 0 && threadIdx.x == 0) *bump_epoch = (*bump_epoch + 1) & ((1ull << 22) - 1);
+    if (!WRITE && bump_epoch && blockIdx.x == 0 && threadIdx.x == 0) *bump_epoch = chd_next_epoch(*bump_epoch);
     if (warp >= b.n * 9u) return;
     const uint32_t m = warp / 9u;
     const int k = (int)(warp % 9u);

@@ -9,23 +9,10 @@
 // HBM traffic per pass: read key(+val) / write key+val, coalesced reads; per entity 16 B of positions are
 // read once in the assign kernel.
 #pragma once
-#include "chd_device.cuh"
+#include "chd_types.cuh"
 
 namespace chd {
 
-constexpr int BUILD_THREADS = 256;
-constexpr int BUILD_WARPS = BUILD_THREADS / 32;
-constexpr int BUILD_ROUNDS = 8;
-constexpr int BUILD_TILE = BUILD_THREADS * BUILD_ROUNDS;  // 2048 entities per tile
-constexpr int BUILD_MAX_BINS = 1024;
-
-struct HandoverOut {
-    uint32_t* entity;
-    uint32_t* src_cell;
-    uint32_t* dst_cell;
-    uint32_t* count;  // device counter (may exceed cap: required size)
-    uint32_t cap;
-};
 
 // cell key per entity (+ optional handover detection against the previous build's keys:
 // the prefix of Notify, spatial.go:612-626: GetChannelId(old) != GetChannelId(new)).
@@ -73,7 +60,7 @@ __global__ void __launch_bounds__(BUILD_THREADS)
                       uint32_t shift, uint32_t mask, uint32_t* __restrict__ hist, uint32_t nblocks, unsigned long long* bump_epoch) {
     __shared__ uint32_t s_hist[BINS];
     // first kernel of the build stage: opens a new epoch for the stage's look-back scans (chd_scan.cuh)
-    if (bump_epoch && blockIdx.x == 0 && threadIdx.x == 0) *bump_epoch = (*bump_epoch + 1) & ((1ull << 22) - 1);
+    if (bump_epoch && blockIdx.x == 0 && threadIdx.x == 0) *bump_epoch = chd_next_epoch(*bump_epoch);
     if (n_ptr) n = min(n, *n_ptr);  // live length on the device (multi-GPU: own + halo entities)
     for (int d = threadIdx.x; d < BINS; d += BUILD_THREADS) s_hist[d] = 0;
     __syncthreads();
@@ -83,17 +70,6 @@ __global__ void __launch_bounds__(BUILD_THREADS)
     __syncthreads();
     for (int d = threadIdx.x; d < BINS; d += BUILD_THREADS) hist[(uint32_t)d * nblocks + blockIdx.x] = s_hist[d];
 }
-
-// Extras of the FINAL pass of the entity build, fused into the scatter:
-//   phase_stride != 0 : also write the three phase-shifted copies of the payload (chd_emit.cuh)
-//   cell_start != null: single-pass sorts only (digit == key): block 0 publishes the cell CSR offsets straight from
-//                       the scanned histogram (cell_start[c] = #keys < c), replacing a separate boundaries kernel
-struct ScatterExtras {
-    uint32_t phase_stride;
-    uint32_t* cell_start;
-    uint32_t cells;
-    uint32_t* n_in_world;
-};
 
 // stable scatter of one pass.  val_in == nullptr means "value = index" (first pass).
 template <int BINS>
@@ -184,6 +160,21 @@ __global__ void __launch_bounds__(256)
         cell_start[c] = i;
         if (c == (int64_t)cells) *n_in_world = i;  // entities with a valid cell precede the key == cells tail
     }
+}
+
+// The cell CSR's entity array is kept in FOUR phase-shifted copies: copy k stores element i at index
+// k*stride + k + i (stride % 4 == 0), i.e. at 16-byte phase (k + i) % 4.  Output chunks are 16-byte aligned, so
+// for a run that starts at source index s the copy k = (-s) & 3 makes source and destination co-aligned and
+// the whole run moves as LDG.128 -> STG.128 with no realignment shuffles.  Cost: 12 extra bytes per entity
+// written once per build (L2-resident), against 8 bytes per VISIBLE entry saved from 4-byte accesses.
+__global__ void __launch_bounds__(256)
+    replicate_phases_kernel(const uint32_t* src, uint32_t n, const uint32_t* __restrict__ n_ptr, uint32_t stride, uint32_t* dst4) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_ptr) n = min(n, *n_ptr);
+    if (i >= n) return;
+    const uint32_t v = src[i];
+#pragma unroll
+    for (uint32_t k = 1; k < 4; k++) dst4[(size_t)k * stride + k + i] = v;  // copy 0 is src itself (dst4 == src)
 }
 
 }  // namespace chd

@@ -9,7 +9,7 @@
 // one atomicCAS by the first record that reaches it and identified by THAT record's key from then on, so equal keys
 // always meet in the same slot and unequal keys never share one — exact, no reliance on hash quality.
 #pragma once
-#include "chd_fanout.cuh"
+#include "chd_types.cuh"
 
 namespace chd {
 
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256)
                       const uint32_t* __restrict__ rep_min, uint32_t* __restrict__ flag, unsigned long long* bump_epoch) {
     const uint32_t n = min(*n_due_ptr, due_cap);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) *bump_epoch = (*bump_epoch + 1) & ((1ull << 22) - 1);
+    if (i == 0) *bump_epoch = chd_next_epoch(*bump_epoch);
     if (i < n) flag[i] = rep_min[slot_of[i]] == i ? 1u : 0u;
 }
 

@@ -10,6 +10,12 @@
 
 #include "../../include/chd_gpu.h"
 
+// look-back scan epochs (chd_scan.cuh) are 22 bits and skip 0, the value of a never-written descriptor
+__host__ __device__ __forceinline__ unsigned long long chd_next_epoch(unsigned long long e) {
+    e = (e + 1) & ((1ull << 22) - 1);
+    return e ? e : 1ull;
+}
+
 #define CHD_INVALID_CELL 0xFFFFFFFFu
 #define CHD_ABSENT 0xFFFFFFFFu
 

@@ -7,27 +7,10 @@
 //                      advancing to every picked arrival; last += interval
 // One launch: see fanout_kernel below.
 #pragma once
-#include "chd_interest.cuh"
+#include "chd_types.cuh"
 
 namespace chd {
 
-struct RingDev {
-    const uint32_t* off;        // [C+1]
-    const int64_t* arrival;     // insertion order per cell
-    const uint32_t* sender;
-    const uint64_t* index;
-    const uint64_t* channel_msg_index;  // [C] or nullptr
-    const uint32_t* total;              // entries uploaded (device scalar): offsets are clamped to it
-};
-
-// Payload identity of a decision (window classes, chd_classes.cuh): two decisions of one channel carry the same merged
-// payload if they are both FULL, or if they start from the same lastFanOutTime (`lo`), end at the same nextFanOutTime
-// (the record's window_hi) and neither subscriber had an own update left out of that window; a decision with
-// self-skipped updates is its own class.  word = cell << 34 | kind << 33 | skipped << 32 | (skipped ? subscriber slot : 0).
-struct DueKey {
-    int64_t lo;
-    uint64_t word;
-};
 __device__ __forceinline__ DueKey make_due_key(uint32_t cell, uint32_t kind, bool skipped, uint32_t sub, int64_t lo) {
     return DueKey{kind ? lo : 0ll, ((uint64_t)cell << 34) | ((uint64_t)kind << 33) | ((uint64_t)(skipped ? 1u : 0u) << 32) | (skipped ? sub : 0u)};
 }
@@ -152,22 +135,29 @@ __global__ void __launch_bounds__(128, 6)  // <= 85 registers: the whole pair li
             s_base = total ? atomicAdd(&ctr->n_due, total) : 0u;
         }
         __syncthreads();
+        // Transactional capacity rule: a pair whose decisions do not fit the due list is left exactly as it was (nothing
+        // written, no state committed): it is still due at the next tick and catches up then (CHD_OVF_DUE is raised,
+        // n_due = the capacity that would have been needed).
+        bool fits = true;
         if (n_out) {
             const uint32_t o = s_base + off;
             const int64_t step_ns = (int64_t)interval * 1000000ll;  // an UPDATE decision's window starts at window_hi - interval
-            if ((uint64_t)o + n_out > due_cap) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_DUE);
-            if (n_out <= FANOUT_SLOTS) {
-                if (o < due_cap) { due[o] = d0; due_key[o] = make_due_key(c, d0.kind, sk0, s, d0.window_hi - step_ns); }
-                if (n_out > 1 && o + 1 < due_cap) { due[o + 1] = d1; due_key[o + 1] = make_due_key(c, d1.kind, sk1, s, d1.window_hi - step_ns); }
+            fits = (uint64_t)o + n_out <= due_cap;
+            if (!fits) {
+                atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_DUE);
+                for (uint32_t j = 0; j < n_out && (uint64_t)o + j < due_cap; j++) due[o + j].kind = CHD_DUE_VOID;  // a hole, not a decision
+            } else if (n_out <= FANOUT_SLOTS) {
+                due[o] = d0; due_key[o] = make_due_key(c, d0.kind, sk0, s, d0.window_hi - step_ns);
+                if (n_out > 1) { due[o + 1] = d1; due_key[o + 1] = make_due_key(c, d1.kind, sk1, s, d1.window_hi - step_ns); }
             } else {  // several intervals behind: re-evaluate from the saved state, writing directly
                 last = last0; flags = flags0; last_index = last_index0;
                 fanout_eval(ring, ring_total, t, interval, c, s, me, id_start, last, flags, last_index,
                             [&](uint32_t j, const chd_due& d, bool skipped) {
-                                if (o + j < due_cap) { due[o + j] = d; due_key[o + j] = make_due_key(c, d.kind, skipped, s, d.window_hi - step_ns); }
+                                due[o + j] = d; due_key[o + j] = make_due_key(c, d.kind, skipped, s, d.window_hi - step_ns);
                             });
             }
         }
-        if (i < n && (n_out || last != last0)) {  // commit (steps without a decision still advance lastFanOutTime)
+        if (i < n && fits && (n_out || last != last0)) {  // commit (steps without a decision still advance lastFanOutTime)
             pb.last[p] = last;
             pb.flags[p] = flags;
             pb.last_index[p] = last_index;

@@ -10,25 +10,6 @@
 
 namespace chd {
 
-struct PairBuf {
-    uint32_t* off;         // [S+1]
-    uint32_t* sub;         // [P] owning subscriber slot
-    uint32_t* cell;        // [P] cell index
-    uint32_t* dist;        // [P]
-    uint32_t* interval;    // [P] FanOutIntervalMs
-    uint8_t* flags;        // [P]
-    int64_t* last;         // [P] lastFanOutTime (ns)
-    uint64_t* last_index;  // [P] lastMessageIndex
-};
-enum : uint8_t { PF_HAD_FIRST = 1, PF_NEW = 2, PF_SKIP_SELF = 4 };
-
-struct Counters {  // device mirror of chd_tick_summary's counters
-    unsigned long long n_pairs, n_visible;
-    uint32_t n_entities_in_world, n_query_errors, n_sub_new, n_unsub, n_kept, n_due, n_handover, overflow;
-    unsigned long long required_pairs, required_window_cells, required_visible;
-    uint32_t required_due, reserved;
-};
-
 __global__ void __launch_bounds__(256) slot_scatter_kernel(const uint32_t* __restrict__ sub, uint32_t nq, uint32_t n_slots, int32_t* __restrict__ slot_query) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nq && sub[i] < n_slots) slot_query[sub[i]] = (int32_t)i;
@@ -48,10 +29,6 @@ struct SlotCountIn {
     }
 };
 
-struct DiffOut {  // the two interest-diff lists of a tick: (subscriber slot, channel id)
-    uint32_t *new_sub, *new_ch, *gone_sub, *gone_ch;
-};
-
 // Builds the new subscription set of each slot and appends the interest diff:
 //   new list  = wanted \ existing  -> handleSubToChannel   (message_spatial.go:110-128)
 //   gone list = existing \ wanted  -> handleUnsubFromChannel (message_spatial.go:88-108, util.go:105-113)
@@ -65,26 +42,31 @@ __global__ void __launch_bounds__(128)
                          const Bbox* __restrict__ bbox, const uint64_t* __restrict__ win_off, const uint32_t* __restrict__ window,
                          const uint32_t* __restrict__ side_cell, const uint32_t* __restrict__ side_dist,
                          const uint32_t* __restrict__ side_cnt, const uint32_t* __restrict__ spot_off, PairBuf prev, PairBuf cur,
-                         uint64_t pair_cap, const int64_t* __restrict__ now_ptr, DiffOut diff, uint32_t* __restrict__ pair_channel,
-                         Counters* __restrict__ ctr) {
+                         const uint32_t* __restrict__ new_off, uint64_t pair_cap, const int64_t* __restrict__ now_ptr, DiffOut diff,
+                         uint32_t* __restrict__ pair_channel, const unsigned long long* __restrict__ win_cursor, Counters* __restrict__ ctr) {
     __shared__ uint32_t s_warp_new[4], s_warp_gone[4], s_base_new, s_base_gone, s_kept;
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t now_ns = *now_ptr;  // device-resident so the launch can be replayed from a CUDA graph
     if (threadIdx.x == 0) s_kept = 0;
+    // Transactional capacity rule: the new offsets were scanned into scratch (new_off).  If the new pair total does not fit,
+    // NOTHING changes: every subscriber keeps its current subscriptions (cur := prev, diff lists empty) and CHD_OVF_PAIRS is
+    // raised with required_pairs = the total that would have been needed.
+    const unsigned long long total_new = new_off[n_slots];
+    const bool ovf = total_new > pair_cap;
     if (s == 0) {
-        const unsigned long long p = cur.off[n_slots];
-        ctr->n_pairs = p;
-        ctr->required_pairs = p;
-        if (p > pair_cap) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_PAIRS);
+        ctr->n_pairs = ovf ? (unsigned long long)prev.off[n_slots] : total_new;
+        ctr->required_pairs = total_new;
+        ctr->required_window_cells = *win_cursor;
+        if (ovf) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_PAIRS);
     }
-    const bool active = s < n_slots && cur.off[n_slots] <= pair_cap;
+    const bool active = s < n_slots;
     int32_t q = -1;
     uint32_t pb = 0, pe = 0;
     bool queried = false;
     if (s < n_slots) {
         q = slot_query ? slot_query[s] : (s < n_queries ? (int32_t)s : -1);
-        queried = q >= 0 && status[q] == CHD_Q_OK;
+        queried = q >= 0 && status[q] == CHD_Q_OK && !ovf;
     }
     {   // queries that failed (message_spatial.go:60-63): counted for the summary
         const uint32_t nerr = __syncthreads_count(s < n_slots && q >= 0 && !queried);
@@ -132,12 +114,15 @@ __global__ void __launch_bounds__(128)
     uint32_t on = s_base_new + off_new, og = s_base_gone + off_gone;
     // ---- sweep 2: write the subscriber's new pair run (+ diff entries)
     uint32_t pp = pb;
-    uint32_t o = cur.off[s];
+    uint32_t o = ovf ? pb : new_off[s];
+    const uint32_t o_end = ovf ? pe : new_off[s + 1];  // (defensive bound: a run never grows past its reserved range)
+    cur.off[s] = o;
+    if (s + 1 == n_slots) cur.off[n_slots] = o_end;
     if (queried) {
         ResultIter it;
         it.init(window, win_off, bbox, side_cell, side_dist, side_cnt, spot_off, (uint32_t)q, g.cols);
         uint32_t c, d;
-        while (it.next(c, d)) {
+        while (o < o_end && it.next(c, d)) {
             while (pp < pe && prev.cell[pp] < c) {  // existing \ wanted -> unsubscribe
                 if (og < pair_cap) { diff.gone_sub[og] = s; diff.gone_ch[og] = prev.cell[pp] + g.id_start; }
                 og++;
@@ -172,7 +157,7 @@ __global__ void __launch_bounds__(128)
         }
     } else {
         // no query this batch, or the query errored: subscriptions stay (message_spatial.go:60-63)
-        for (; pp < pe; pp++, o++) {
+        for (; pp < pe && o < o_end; pp++, o++) {
             cur.sub[o] = s;
             cur.cell[o] = prev.cell[pp];
             pair_channel[o] = prev.cell[pp] + g.id_start;

@@ -1,96 +1,37 @@
-// chd_misc.cuh — small bookkeeping kernels (counters, id conversion, multi-GPU border records).
+// chd_misc.cuh — small bookkeeping kernels (counters, id conversion).  Internal linkage: several translation units use them.
 #pragma once
-#include "chd_interest.cuh"
+#include "chd_types.cuh"
 
 namespace chd {
 
-__global__ void cell_key_to_id_kernel(uint32_t* __restrict__ k, uint32_t n, uint32_t cells, uint32_t id_start) {
+static __global__ void cell_key_to_id_kernel(uint32_t* __restrict__ k, uint32_t n, uint32_t cells, uint32_t id_start, uint8_t* __restrict__ valid) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) k[i] = k[i] >= cells ? 0u : k[i] + id_start;
+    if (i >= n) return;
+    const bool ok = k[i] < cells;
+    k[i] = ok ? k[i] + id_start : 0u;
+    if (valid) valid[i] = ok ? 1 : 0;
 }
 
-__global__ void narrow_offsets_kernel(const uint64_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out) {
+static __global__ void narrow_offsets_kernel(const uint64_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (uint32_t)in[i];
 }
 
-__global__ void add_const_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t c, uint32_t* __restrict__ out) {
+static __global__ void add_const_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t c, uint32_t* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i] + c;
 }
 
-// ---- X-slab sharding.  A record is (global entity id, cell index).
-// An own entity is exported when another rank may need it: its column is not strictly interior to this slab.
-__global__ void border_flag_kernel(GridDev g, const uint32_t* __restrict__ key, uint32_t n, uint32_t* __restrict__ flag,
-                                   unsigned long long* bump_epoch) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) *bump_epoch = (*bump_epoch + 1) & ((1ull << 22) - 1);  // border stage epoch
-    if (i >= n) return;
-    const uint32_t k = key[i];
-    uint32_t f = 0;
-    if (k < g.cells) {
-        const uint32_t col = k % g.cols;
-        const bool interior = col >= g.col_lo + g.halo && col + g.halo < g.col_hi;
-        const bool left_edge_open = g.col_lo > 0, right_edge_open = g.col_hi < g.cols;
-        if (!interior) {
-            // columns near a world edge with no neighbour beyond need no export
-            const bool near_left = col < g.col_lo + g.halo, near_right = col + g.halo >= g.col_hi;
-            f = (near_left && left_edge_open) || (near_right && right_edge_open) || col < g.col_lo || col >= g.col_hi;
-        }
-    }
-    flag[i] = f;
+static __global__ void set_i64_kernel(int64_t* dst, int64_t v) { *dst = v; }
+// first kernel of the interest / fan-out stages: publishes the tick time, opens a new scan epoch (never 0: zero-initialised
+// descriptors must read as stale) and zeroes the stage's counters / cursors
+static __global__ void stage_begin_kernel(int64_t* dst, int64_t v, unsigned long long* epoch, uint32_t* zero_u32, uint32_t n_zero,
+                                          unsigned long long* zero_u64) {
+    *dst = v;
+    *epoch = chd_next_epoch(*epoch);
+    for (uint32_t k = 0; k < n_zero; k++) zero_u32[k] = 0;
+    if (zero_u64) *zero_u64 = 0;
 }
-
-// writes the flagged records and pads the rest of the caller's buffer with 0xFFFFFFFF (no separate fill needed)
-__global__ void border_write_kernel(const uint32_t* __restrict__ key, const uint32_t* __restrict__ gid, uint32_t n,
-                                    const uint32_t* __restrict__ flag, const uint32_t* __restrict__ off, uint32_t* __restrict__ out,
-                                    uint32_t cap, Counters* __restrict__ ctr) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t count = off[n];
-    if (i == 0 && count > cap) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_BORDER);
-    if (i < cap && i >= count) {  // padding slot
-        out[2 * i] = 0xFFFFFFFFu;
-        out[2 * i + 1] = 0xFFFFFFFFu;
-    }
-    if (i >= n || !flag[i]) return;
-    const uint32_t o = off[i];
-    if (o < cap) {
-        out[2 * o] = gid ? gid[i] : i;
-        out[2 * o + 1] = key[i];
-    }
-}
-
-// keep gathered records whose column lies in this rank's extended range and which another rank exported
-__global__ void halo_flag_kernel(GridDev g, const uint32_t* __restrict__ rec, uint32_t n, uint32_t skip_first, uint32_t skip_count,
-                                 uint32_t* __restrict__ flag, unsigned long long* bump_epoch) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) *bump_epoch = (*bump_epoch + 1) & ((1ull << 22) - 1);  // border stage epoch
-    if (i >= n) return;
-    const uint32_t cell = rec[2 * i + 1];
-    uint32_t f = 0;
-    if (cell < g.cells && !(i >= skip_first && i - skip_first < skip_count)) {
-        const uint32_t col = cell % g.cols;
-        f = (col + g.halo >= g.col_lo) && (col < g.col_hi + g.halo);
-    }
-    flag[i] = f;
-}
-
-// appends the kept records after the `base` own entities and publishes the build length (own + halo) on the device:
-// the host never needs the halo count, so the whole multi-GPU tick is free of host round trips.
-__global__ void halo_append_kernel(const uint32_t* __restrict__ rec, uint32_t n, const uint32_t* __restrict__ flag,
-                                   const uint32_t* __restrict__ off, uint32_t base, uint32_t cap_total, uint32_t* __restrict__ key,
-                                   uint32_t* __restrict__ gid, uint32_t* __restrict__ n_build, Counters* __restrict__ ctr) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) {
-        const uint64_t total = (uint64_t)base + off[n];
-        if (total > cap_total) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_BORDER);
-        *n_build = (uint32_t)min(total, (uint64_t)cap_total);
-    }
-    if (i >= n || !flag[i]) return;
-    const uint32_t o = base + off[i];
-    if (o >= cap_total) return;
-    gid[o] = rec[2 * i];
-    key[o] = rec[2 * i + 1];
-}
+static __global__ void set_u32_kernel(uint32_t* dst, uint32_t v) { *dst = v; }
 
 }  // namespace chd

@@ -8,27 +8,14 @@
 // Row-major windows enumerate cells in ascending channel id: the canonical output order.  SpotsAOI cells
 // outside the window go to a small per-query side list (last-write-wins, then sorted).
 #pragma once
-#include "chd_device.cuh"
+#include "chd_types.cuh"
 
 namespace chd {
 
-struct QueryDev {
-    uint32_t n;
-    const uint32_t* sub;
-    const uint8_t* kind;
-    const double *sph_cx, *sph_cz, *sph_r;
-    const double *box_cx, *box_cz, *box_ex, *box_ez;
-    const double *cone_cx, *cone_cz, *cone_dx, *cone_dz, *cone_angle, *cone_r;
-    const uint32_t *spot_off, *spot_ndist;
-    const double *spot_x, *spot_z;
-    const uint32_t* spot_dist;
-};
-
-struct Bbox {
-    uint32_t gx0, gy0, bw, bh;  // bw == 0 => empty
-};
-
-constexpr uint32_t QUERY_ITER_BOUND = 1u << 24;  // guard against the reference's absorbed-step infinite loop
+// Guards against the reference's non-terminating lattice walks (SURVEY.md §8c'): an absorbed step (v + step == v) is
+// detected directly; a walk of more than 2^24 samples is cut off as well (a documented deviation: the reference would
+// answer such a query after minutes of CPU time; the oracle applies the same bound).
+constexpr uint32_t QUERY_ITER_BOUND = 1u << 24;
 
 struct BboxAcc {
     uint32_t gx0, gx1, gy0, gy1;
@@ -64,11 +51,8 @@ struct BboxAcc {
 
 __device__ __forceinline__ uint32_t query_kind(const QueryDev& q, uint32_t i) { return q.kind ? q.kind[i] : (uint32_t)CHD_AOI_SPHERE; }
 
-// Q1: bounding box of reachable cells per query and its size.
-__global__ void __launch_bounds__(256) query_bbox_kernel(GridDev g, QueryDev q, Bbox* __restrict__ bbox, uint32_t* __restrict__ win_size) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= q.n) return;
-    const uint32_t kind = query_kind(q, i);
+// Q1: bounding box of the cells a query's lattice samples can reach.
+__device__ __forceinline__ Bbox query_bbox(const GridDev& g, const QueryDev& q, uint32_t i, uint32_t kind) {
     BboxAcc acc;
     acc.init();
     if (kind & CHD_AOI_BOX) {
@@ -93,8 +77,7 @@ __global__ void __launch_bounds__(256) query_bbox_kernel(GridDev g, QueryDev q, 
     } else {
         b.gx0 = b.gy0 = 0; b.bw = b.bh = 0;
     }
-    bbox[i] = b;
-    win_size[i] = b.bw * b.bh;
+    return b;
 }
 
 struct WinRef {
@@ -108,30 +91,60 @@ struct WinRef {
     }
 };
 
-// Q2: the lattice walk.  Writes the window, the side list, status and the number of result entries.
-// If the window scratch overflowed (win_off[n] > win_cap) nothing is touched: the host reports CHD_OVF_WINDOW.
+// The whole query in ONE launch: bounding box -> window scratch -> lattice walk.  A query's window is private scratch, so
+// its location does not matter: the block's windows are carved out of `window` with one atomicAdd per block on a bump
+// cursor (zeroed by the stage's first kernel) instead of a device-wide prefix sum (two launches less per tick).
+// A query whose window does not fit the scratch gets CHD_Q_ERR_CAPACITY: like any failed query it leaves the subscriber's
+// subscriptions untouched; CHD_OVF_WINDOW is raised and the cursor's final value is the required capacity.
+// A query that sets a kind bit without supplying that kind's arrays gets CHD_Q_ERR_MISSING_ARRAY.
 __global__ void __launch_bounds__(128)
-    query_sample_kernel(GridDev g, QueryDev q, const Bbox* __restrict__ bbox, const uint64_t* __restrict__ win_off, uint64_t win_cap,
-                        uint32_t* __restrict__ window, uint32_t* __restrict__ side_cell, uint32_t* __restrict__ side_dist,
-                        uint32_t* __restrict__ side_cnt, uint32_t* __restrict__ status, uint32_t* __restrict__ count,
-                        unsigned long long* __restrict__ required_window_cells, uint32_t* __restrict__ overflow) {
+    query_kernel(GridDev g, QueryDev q, Bbox* __restrict__ bbox, uint64_t* __restrict__ win_off, uint64_t win_cap,
+                 unsigned long long* __restrict__ win_cursor, uint32_t* __restrict__ window, uint32_t* __restrict__ side_cell,
+                 uint32_t* __restrict__ side_dist, uint32_t* __restrict__ side_cnt, uint32_t* __restrict__ status, uint32_t* __restrict__ count,
+                 uint32_t* __restrict__ overflow) {
+    __shared__ unsigned long long s_warp[4], s_base;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= q.n) return;
-    if (i == 0) {
-        *required_window_cells = win_off[q.n];
-        if (win_off[q.n] > win_cap) atomicOr(overflow, (uint32_t)CHD_OVF_WINDOW);
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    uint32_t kind = 0;
+    bool missing = false;
+    WinRef win;
+    win.b.gx0 = win.b.gy0 = win.b.bw = win.b.bh = 0;
+    if (i < q.n) {
+        kind = query_kind(q, i);
+        missing = ((kind & CHD_AOI_BOX) && (!q.box_cx || !q.box_cz || !q.box_ex || !q.box_ez)) ||
+                  ((kind & CHD_AOI_SPHERE) && (!q.sph_cx || !q.sph_cz || !q.sph_r)) ||
+                  ((kind & CHD_AOI_CONE) && (!q.cone_cx || !q.cone_cz || !q.cone_dx || !q.cone_dz || !q.cone_angle || !q.cone_r)) ||
+                  ((kind & CHD_AOI_SPOTS) && q.spot_off && (!q.spot_x || !q.spot_z || !q.spot_dist));
+        if (!missing) win.b = query_bbox(g, q, i, kind);
     }
-    if (win_off[q.n] > win_cap) {
-        status[i] = CHD_Q_OK;
+    const uint32_t wn = win.b.bw * win.b.bh;
+    // block-aggregated reservation of the window scratch
+    unsigned long long incl = wn;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long a = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += a;
+    }
+    if (lane == 31) s_warp[wp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long tot = s_warp[0] + s_warp[1] + s_warp[2] + s_warp[3];
+        s_base = tot ? atomicAdd(win_cursor, tot) : 0ull;
+    }
+    __syncthreads();
+    unsigned long long off = s_base + incl - wn;
+    for (int k = 0; k < wp; k++) off += s_warp[k];
+    if (i >= q.n) return;
+    bbox[i] = win.b;
+    win_off[i] = off;
+    if (missing || off + wn > win_cap) {
+        if (!missing) atomicOr(overflow, (uint32_t)CHD_OVF_WINDOW);
+        status[i] = missing ? CHD_Q_ERR_MISSING_ARRAY : CHD_Q_ERR_CAPACITY;
         count[i] = 0;
         if (side_cnt) side_cnt[i] = 0;
         return;
     }
-    const uint32_t kind = query_kind(q, i);
-    WinRef win;
-    win.b = bbox[i];
-    win.w = window + win_off[i];
-    const uint32_t wn = win.b.bw * win.b.bh;
+    win.w = window + off;
     for (uint32_t k = 0; k < wn; k++) win.w[k] = CHD_ABSENT;
     uint32_t st = CHD_Q_OK;
     uint32_t n_side = 0;
@@ -162,9 +175,12 @@ __global__ void __launch_bounds__(128)
         if (stepX <= 0) { st = CHD_Q_ERR_BAD_STEP; goto done; }
         const double zhi = f64add(cz, ez), xhi = f64add(cx, ex), xlo = f64sub(cx, ex);
         uint32_t iters = 0;
-        for (double z = f64sub(cz, ez); z <= zhi; z = f64add(z, stepZ)) {
-            for (double x = xlo; x <= xhi; x = f64add(x, stepX)) {
-                if (++iters > QUERY_ITER_BOUND) { st = CHD_Q_ERR_ITER_BOUND; goto done; }
+        for (double z = f64sub(cz, ez), zn; z <= zhi; z = zn) {
+            zn = f64add(z, stepZ);
+            if (zn == z) { st = CHD_Q_ERR_ITER_BOUND; goto done; }
+            for (double x = xlo, xn; x <= xhi; x = xn) {
+                xn = f64add(x, stepX);
+                if (xn == x || ++iters > QUERY_ITER_BOUND) { st = CHD_Q_ERR_ITER_BOUND; goto done; }  // absorbed step: the reference never terminates
                 if (!grid_coord(g, x, z, gx, gy)) continue;
                 win.put(gx, gy, cell_dist(g, cx, cz, x, z));
             }
@@ -182,11 +198,14 @@ __global__ void __launch_bounds__(128)
         if (stepX <= 0) { st = CHD_Q_ERR_BAD_STEP; goto done; }
         const double zhi = f64add(cz, r), xhi = f64add(cx, r), xlo = f64sub(cx, r), rr = f64mul(r, r);
         uint32_t iters = 0;
-        for (double z = f64sub(cz, r); z <= zhi; z = f64add(z, stepZ)) {
+        for (double z = f64sub(cz, r), zn; z <= zhi; z = zn) {
+            zn = f64add(z, stepZ);
+            if (zn == z) { st = CHD_Q_ERR_ITER_BOUND; goto done; }
             const double dz = f64sub(z, cz);
             const double dz2 = f64mul(dz, dz);
-            for (double x = xlo; x <= xhi; x = f64add(x, stepX)) {
-                if (++iters > QUERY_ITER_BOUND) { st = CHD_Q_ERR_ITER_BOUND; goto done; }
+            for (double x = xlo, xn; x <= xhi; x = xn) {
+                xn = f64add(x, stepX);
+                if (xn == x || ++iters > QUERY_ITER_BOUND) { st = CHD_Q_ERR_ITER_BOUND; goto done; }  // absorbed step: the reference never terminates
                 const double dx = f64sub(x, cx);
                 if (f64add(f64mul(dx, dx), dz2) > rr) continue;
                 if (!grid_coord(g, x, z, gx, gy)) continue;
@@ -216,11 +235,14 @@ __global__ void __launch_bounds__(128)
         const double cosv = go_cos(q.cone_angle[i], cos_ok);  // spatial.go:295 (loop invariant)
         if (!cos_ok) { st = CHD_Q_ERR_ANGLE_RANGE; goto done; }
         uint32_t iters = 0;
-        for (double z = go_max(g.off_z, f64sub(cz, r)); z <= zhi; z = f64add(z, stepZ)) {
+        for (double z = go_max(g.off_z, f64sub(cz, r)), zn; z <= zhi; z = zn) {
+            zn = f64add(z, stepZ);
+            if (zn == z) { st = CHD_Q_ERR_ITER_BOUND; goto done; }
             const double dz = f64sub(z, cz);
             const double dz2 = f64mul(dz, dz);
-            for (double x = xlo; x <= xhi; x = f64add(x, stepX)) {
-                if (++iters > QUERY_ITER_BOUND) { st = CHD_Q_ERR_ITER_BOUND; goto done; }
+            for (double x = xlo, xn; x <= xhi; x = xn) {
+                xn = f64add(x, stepX);
+                if (xn == x || ++iters > QUERY_ITER_BOUND) { st = CHD_Q_ERR_ITER_BOUND; goto done; }  // absorbed step: the reference never terminates
                 const double dx = f64sub(x, cx);
                 if (f64add(f64mul(dx, dx), dz2) > rr) continue;
                 const double mag = f64sqrt(f64add(f64mul(dx, dx), dz2));

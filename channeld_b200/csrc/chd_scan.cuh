@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "chd_device.cuh"
+
 namespace chd {
 
 constexpr int SCAN_THREADS = 256;
@@ -124,7 +126,8 @@ inline int exclusive_scan(const TIn* in, TOut* out, uint64_t n, TOut* scratch, c
 // kernel of the same stage increments once per stage execution (bump_epoch_kernel / stage_begin_kernel).  A launch
 // therefore carries no per-call host state and can be replayed from a CUDA graph.  A descriptor is one 64-bit
 // word [epoch:22 | flag:2 | value:40]; descriptors written by an earlier stage execution carry an older epoch
-// and read as "not ready".  Tile id = blockIdx.x (lower-indexed blocks of a 1-D grid are dispatched first, the
+// and read as "not ready"; a valid descriptor also needs a non-zero flag, and the engine clears every site's descriptors
+// long before the 22-bit epoch can wrap around to a value a stale descriptor still carries (chd_epoch_tick, chd_engine.cu).  Tile id = blockIdx.x (lower-indexed blocks of a 1-D grid are dispatched first, the
 // usual forward-progress assumption of decoupled look-back).  No atomics.  Sums must stay below 2^40; a site may
 // be used once per stage execution.
 struct ScanSite {
@@ -132,9 +135,10 @@ struct ScanSite {
     const unsigned long long* epoch;  // the owning stage's epoch counter
     uint32_t* error;                  // bit 31 is set if a look-back ever times out (reported as an overflow bit)
     uint64_t tiles;                   // descriptor capacity
+    int stage;                        // index of the owning stage epoch (host bookkeeping)
 };
 
-__global__ void bump_epoch_kernel(unsigned long long* epoch) { *epoch = (*epoch + 1) & ((1ull << 22) - 1); }
+static __global__ void bump_epoch_kernel(unsigned long long* epoch) { *epoch = chd_next_epoch(*epoch); }
 
 constexpr unsigned long long SCAN_FLAG_AGG = 1ull, SCAN_FLAG_PREFIX = 2ull;
 __device__ __forceinline__ unsigned long long scan_pack(unsigned long long epoch, unsigned long long flag, unsigned long long v) {
@@ -186,7 +190,7 @@ __global__ void __launch_bounds__(SCAN_THREADS)
                 const int64_t j = start - lane;
                 // tiles before 0 act as an (always valid) zero prefix
                 const unsigned long long d = j >= 0 ? desc[j] : scan_pack(epoch, SCAN_FLAG_PREFIX, 0ull);
-                const bool valid = (d >> 42) == epoch;
+                const bool valid = (d >> 42) == epoch && ((d >> 40) & 3ull) != 0;
                 const bool is_prefix = valid && ((d >> 40) & 3ull) == SCAN_FLAG_PREFIX;
                 const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
                 const uint32_t pmask = __ballot_sync(0xffffffffu, is_prefix);

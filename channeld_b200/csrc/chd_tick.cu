@@ -1,0 +1,368 @@
+// chd_tick.cu — expanded visible lists, update rings, fan-out, and Channel.Tick for every spatial channel as one batched,
+// two-stream tick.
+#include "chd_engine.h"
+
+#include "chd_emit.cuh"
+#include "chd_fanout.cuh"
+#include "chd_misc.cuh"
+
+extern "C" {
+
+chd_status chd_emit_visible(chd_engine* e) {
+    if (!e) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    if (!e->built) {
+        e->fail("chd_emit_visible before chd_build");
+        return CHD_ERR_STATE;
+    }
+    cudaStream_t s = e->stream;
+    PairBuf& pb = e->pairs[e->cur];
+    const uint32_t S = e->n_slots;
+    const uint64_t P = e->lim.max_pairs;
+    StageTimer timer(e, CHD_STAGE_EMIT);
+    const unsigned grid = (unsigned)e->sm_count * 8;
+    const uint64_t key = mix_key(mix_key(0x656d6974ull, S), (uint64_t)e->cur);
+    chd_status st = chd_epoch_tick(e, EP_EMIT);
+    if (st != CHD_OK) return st;
+    st = run_stage(e, e->g_emit_prep[e->cur], key, [&]() -> chd_status {
+        // per-pair visible counts are computed by the scan itself; the partition pass opens the next epoch
+        SCAN(e, exclusive_scan_fn<PairVcountIn, uint64_t>(PairVcountIn{pb.cell, e->d_cell_start}, e->d_voff, P, e->site_voff, s, pb.off + S));
+        emit_partition_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, e->d_voff, e->d_first_pair, e->max_tiles, S, pb.off, e->d_vis_off,
+                                                   e->lim.max_visible, e->d_ctr, e->d_epoch + EP_EMIT);
+        KCHECK(e);
+        return CHD_OK;
+    });
+    if (st != CHD_OK) return st;
+    if (e->wait_before_emit_kernel) {
+        CU(e, cudaStreamWaitEvent(s, e->wait_before_emit_kernel, 0));
+        e->wait_before_emit_kernel = nullptr;
+    }
+    CU(e, cudaEventRecord(e->ev_prep_done, s));  // visible offsets + counters are final; only the expanded list is still to come
+    {
+        StageTimer kt(e, CHD_STAGE_EMIT_KERNEL);
+        emit_visible_kernel<<<(unsigned)e->sm_count * 4, EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4, e->phase_stride,
+                                                                                e->d_first_pair, e->d_vis, e->lim.max_visible);
+        KCHECK(e);
+    }
+    return CHD_OK;
+}
+
+chd_status chd_set_rings(chd_engine* e, const uint32_t* ring_off, uint32_t n_entries, const int64_t* arrival, const uint32_t* sender,
+                         const uint64_t* index, const uint64_t* ch_msg_index) {
+    if (!e || !ring_off) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    const uint32_t C = e->g.cells;
+    const uint32_t total = n_entries;
+    if (total > e->lim.max_ring_entries) {
+        e->fail("%u ring entries > max_ring_entries %u", total, e->lim.max_ring_entries);
+        return CHD_ERR_CAPACITY;
+    }
+    if (total && (!arrival || !sender || !index)) return CHD_ERR_INVALID;
+    const bool in_place = chd_is_device_ptr(e, ring_off) && (!total || (chd_is_device_ptr(e, arrival) && chd_is_device_ptr(e, sender) && chd_is_device_ptr(e, index))) &&
+                          (!ch_msg_index || chd_is_device_ptr(e, ch_msg_index));
+    if (in_place) {  // device-resident rings: consumed in place
+        e->ring_off_p = ring_off; e->ring_arrival_p = arrival; e->ring_sender_p = sender; e->ring_index_p = index;
+        e->ch_msg_index_p = ch_msg_index;
+    } else {
+        CU(e, cudaMemcpyAsync(e->d_ring_off, ring_off, sizeof(uint32_t) * ((uint64_t)C + 1), cudaMemcpyDefault, e->stream));
+        if (total) {
+            CU(e, cudaMemcpyAsync(e->d_ring_arrival, arrival, sizeof(int64_t) * total, cudaMemcpyDefault, e->stream));
+            CU(e, cudaMemcpyAsync(e->d_ring_sender, sender, sizeof(uint32_t) * total, cudaMemcpyDefault, e->stream));
+            CU(e, cudaMemcpyAsync(e->d_ring_index, index, sizeof(uint64_t) * total, cudaMemcpyDefault, e->stream));
+        }
+        if (ch_msg_index) CU(e, cudaMemcpyAsync(e->d_ch_msg_index, ch_msg_index, sizeof(uint64_t) * C, cudaMemcpyDefault, e->stream));
+        e->ring_off_p = e->d_ring_off; e->ring_arrival_p = e->d_ring_arrival; e->ring_sender_p = e->d_ring_sender;
+        e->ring_index_p = e->d_ring_index; e->ch_msg_index_p = ch_msg_index ? e->d_ch_msg_index : nullptr;
+    }
+    e->have_ch_msg_index = ch_msg_index != nullptr;
+    e->ring_set = -1;
+    e->wait_rings = false;
+    // the fan-out kernel clamps ring_off to this: a lying caller cannot cause out-of-bounds reads
+    set_u32_kernel<<<1, 1, 0, e->stream>>>(e->d_ring_total, total);
+    KCHECK(e);
+    return CHD_OK;
+}
+
+chd_status chd_fanout_tick(chd_engine* e, int64_t t_ns) {
+    if (!e) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    cudaStream_t s = e->stream;
+    PairBuf& pb = e->pairs[e->cur];
+    const uint32_t S = e->n_slots;
+    const uint64_t P = e->lim.max_pairs;
+    StageTimer timer(e, CHD_STAGE_FANOUT);
+    if (e->wait_rings) {  // rings handed over by chd_adopt_prefetched: ordered after their upload
+        CU(e, cudaStreamWaitEvent(s, e->ev_upload_rings, 0));
+        e->wait_rings = false;
+    }
+    chd_epoch_tick(e, EP_FANOUT);
+    stage_begin_kernel<<<1, 1, 0, s>>>(e->d_time + 1, t_ns, e->d_epoch + EP_FANOUT, &e->d_ctr->n_due, 1, nullptr);
+    KCHECK(e);
+    RingDev ring{e->ring_off_p ? e->ring_off_p : e->d_ring_off, e->ring_arrival_p ? e->ring_arrival_p : e->d_ring_arrival,
+                 e->ring_sender_p ? e->ring_sender_p : e->d_ring_sender, e->ring_index_p ? e->ring_index_p : e->d_ring_index,
+                 e->have_ch_msg_index ? e->ch_msg_index_p : nullptr, e->d_ring_total};
+    const unsigned grid = (unsigned)e->sm_count * 16;
+    uint64_t key = mix_key(mix_key(mix_key(0x66616eull, S), (uint64_t)e->cur), e->have_ch_msg_index);
+    for (const void* p : {(const void*)ring.off, (const void*)ring.arrival, (const void*)ring.sender, (const void*)ring.index,
+                          (const void*)ring.channel_msg_index})
+        key = mix_key(key, (uint64_t)(uintptr_t)p);  // pointers are baked into the captured launch
+    chd_status st = run_stage(e, e->g_fanout[e->cur + (e->ring_set == 1 ? 2 : 0)], key, [&]() -> chd_status {
+        const unsigned blocks = (unsigned)std::min<uint64_t>((P + 127) / 128, (uint64_t)e->sm_count * 16);
+        fanout_kernel<<<blocks ? blocks : 1, 128, 0, s>>>(pb.off + S, P, pb, e->d_conn, ring, e->d_time + 1, e->g.id_start, e->d_by_cell, e->d_due,
+                                                          e->d_due_key, e->lim.max_due, e->d_ctr);
+        KCHECK(e);
+        return CHD_OK;
+    });
+    if (st == CHD_OK && e->ring_set >= 0) {
+        CU(e, cudaEventRecord(e->ev_ring_read[e->ring_set], s));
+        e->ring_read_recorded[e->ring_set] = true;
+    }
+    return st;
+}
+
+chd_status chd_prefetch_rings(chd_engine* e, const uint32_t* ring_off, uint32_t n_entries, const int64_t* arrival, const uint32_t* sender,
+                              const uint64_t* index, const uint64_t* ch_msg_index) {
+    if (!e || !ring_off) return CHD_ERR_INVALID;
+    if (n_entries > e->lim.max_ring_entries) {
+        e->fail("%u ring entries > max_ring_entries %u", n_entries, e->lim.max_ring_entries);
+        return CHD_ERR_CAPACITY;
+    }
+    if (n_entries && (!arrival || !sender || !index)) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    chd_status st = chd_ensure_upload_stream(e);
+    if (st != CHD_OK) return st;
+    const int set = e->ring_next;
+    chd_engine::RStage& r = e->ring_pf[set];
+    const uint64_t C = e->g.cells;
+    if (!e->ring_pf_alloc[set]) {
+        const uint64_t R = e->lim.max_ring_entries;
+        if (!(dalloc(e, &r.off, C + 1) && dalloc(e, &r.arrival, R) && dalloc(e, &r.sender, R) && dalloc(e, &r.index, R) && dalloc(e, &r.cmi, C)))
+            return CHD_ERR_CUDA;
+        e->ring_pf_alloc[set] = true;
+    }
+    if (e->ring_read_recorded[set]) CU(e, cudaStreamWaitEvent(e->up_stream, e->ev_ring_read[set], 0));
+    cudaStream_t us = e->up_stream;
+    CU(e, cudaMemcpyAsync(r.off, ring_off, sizeof(uint32_t) * (C + 1), cudaMemcpyDefault, us));
+    if (n_entries) {
+        CU(e, cudaMemcpyAsync(r.arrival, arrival, sizeof(int64_t) * n_entries, cudaMemcpyDefault, us));
+        CU(e, cudaMemcpyAsync(r.sender, sender, sizeof(uint32_t) * n_entries, cudaMemcpyDefault, us));
+        CU(e, cudaMemcpyAsync(r.index, index, sizeof(uint64_t) * n_entries, cudaMemcpyDefault, us));
+    }
+    if (ch_msg_index) CU(e, cudaMemcpyAsync(r.cmi, ch_msg_index, sizeof(uint64_t) * C, cudaMemcpyDefault, us));
+    CU(e, cudaEventRecord(e->ev_upload_rings, us));
+    e->staged_rings = true;
+    e->staged_ring_set = set;
+    e->staged_ring_total = n_entries;
+    e->staged_ring_cmi = ch_msg_index != nullptr;
+    e->ring_next = set ^ 1;
+    return CHD_OK;
+}
+
+chd_status chd_adopt_prefetched(chd_engine* e) {
+    if (!e) return CHD_ERR_INVALID;
+    if (!e->staged && !e->staged_q && !e->staged_rings) {
+        e->fail("chd_adopt_prefetched without a preceding chd_prefetch_entities / chd_prefetch_queries / chd_prefetch_rings");
+        return CHD_ERR_STATE;
+    }
+    CU(e, cudaSetDevice(e->device));
+    if (e->staged_q) {  // consumed by the next chd_begin_interest / chd_update_interest called with q == NULL
+        e->adopted_qd = e->staged_qd;
+        e->adopted_q_set = e->staged_q_set;
+        e->have_adopted_q = true;
+        e->wait_q = true;
+        e->staged_q = false;
+    }
+    if (e->staged_rings) {
+        const chd_engine::RStage& r = e->ring_pf[e->staged_ring_set];
+        e->ring_off_p = r.off; e->ring_arrival_p = r.arrival; e->ring_sender_p = r.sender; e->ring_index_p = r.index;
+        e->ch_msg_index_p = e->staged_ring_cmi ? r.cmi : nullptr;
+        e->have_ch_msg_index = e->staged_ring_cmi;
+        e->ring_set = e->staged_ring_set;
+        e->wait_rings = true;
+        e->staged_rings = false;
+        set_u32_kernel<<<1, 1, 0, e->stream>>>(e->d_ring_total, e->staged_ring_total);
+        KCHECK(e);
+    }
+    if (!e->staged) return CHD_OK;
+    CU(e, cudaStreamWaitEvent(e->stream, e->ev_upload, 0));
+    e->pos_buf ^= 1;
+    e->d_x = e->d_xb[e->pos_buf];
+    e->d_z = e->d_zb[e->pos_buf];
+    e->pos_x = e->d_x;
+    e->pos_z = e->d_z;
+    if (e->staged_n != e->n_own) e->have_prev_key = false;
+    e->n_own = e->staged_n;
+    e->n_halo = 0;
+    e->halo_on_device = false;
+    e->assigned = false;
+    e->entities_dirty = true;
+    e->staged = false;
+    return CHD_OK;
+}
+
+chd_status chd_summary(chd_engine* e, chd_tick_summary* out) {
+    if (!e || !out) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    CU(e, cudaMemcpyAsync(e->h_ctr, e->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    return chd_decode_summary(e, out);
+}
+
+chd_status chd_decode_summary(chd_engine* e, chd_tick_summary* out) {
+    const Counters& c = *e->h_ctr;
+    out->n_pairs = c.n_pairs; out->n_visible = c.n_visible; out->n_entities_in_world = c.n_entities_in_world;
+    out->n_query_errors = c.n_query_errors; out->n_sub_new = c.n_sub_new; out->n_unsub = c.n_unsub; out->n_kept = c.n_kept;
+    out->n_due = c.n_due; out->n_handover = c.n_handover; out->overflow = c.overflow; out->required_pairs = c.required_pairs;
+    out->required_window_cells = c.required_window_cells; out->required_visible = c.required_visible; out->required_due = c.n_due;
+    out->reserved = 0;
+    if (c.overflow) {
+        e->fail("capacity overflow mask 0x%x (pairs %llu, window cells %llu, visible %llu, due %u required)", c.overflow,
+                (unsigned long long)c.required_pairs, (unsigned long long)c.required_window_cells,
+                (unsigned long long)c.required_visible, c.n_due);
+        // sticky bits are cleared for the next tick; what each overflow leaves behind is specified in chd_gpu.h (CHD_OVF_*)
+        CU(e, cudaMemsetAsync(&e->d_ctr->overflow, 0, 4, e->stream));
+        return CHD_ERR_CAPACITY;
+    }
+    return CHD_OK;
+}
+
+chd_status chd_begin_interest(chd_engine* e, const chd_query_batch* q, int64_t t_ns, int with_fanout) {
+    if (!e) return CHD_ERR_INVALID;
+    if (!q && !e->have_adopted_q) {
+        e->fail("chd_begin_interest: q == NULL needs chd_prefetch_queries + chd_adopt_prefetched first");
+        return CHD_ERR_STATE;
+    }
+    if (e->interest_pending) {
+        e->fail("chd_begin_interest: the previous one has not been joined by chd_tick yet");
+        return CHD_ERR_STATE;
+    }
+    CU(e, cudaSetDevice(e->device));
+    if (!e->aux_stream) {  // no second stream: run in place
+        chd_status st = chd_update_interest(e, q, t_ns);
+        if (st == CHD_OK && with_fanout) st = chd_fanout_tick(e, t_ns);
+        return st;
+    }
+    std::lock_guard<std::recursive_mutex> lk(e->mu);  // `stream` is redirected below
+    cudaStream_t main_stream = e->stream;
+    CU(e, cudaEventRecord(e->ev_fork, main_stream));
+    CU(e, cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0));
+    e->stream = e->aux_stream;
+    chd_status st = chd_update_interest(e, q, t_ns);
+    if (st == CHD_OK && cudaEventRecord(e->ev_interest, e->aux_stream) != cudaSuccess) st = CHD_ERR_CUDA;
+    if (st == CHD_OK && with_fanout) st = chd_fanout_tick(e, t_ns);
+    if (st == CHD_OK && cudaEventRecord(e->ev_join, e->aux_stream) != cudaSuccess) st = CHD_ERR_CUDA;
+    e->stream = main_stream;
+    if (st != CHD_OK) return st;
+    e->interest_pending = true;
+    e->pending_fanout = with_fanout != 0;
+    return CHD_OK;
+}
+
+static chd_status chd_tick_impl(chd_engine* e, const chd_query_batch* q, int64_t t_ns, uint32_t flags, chd_tick_summary* out);
+
+chd_status chd_tick(chd_engine* e, const chd_query_batch* q, int64_t t_ns, uint32_t flags, chd_tick_summary* out) {
+    if (!e) return CHD_ERR_INVALID;
+    chd_status st;
+    {
+        StageTimer whole(e, CHD_STAGE_TICK);  // main-stream span of the tick (without the summary read-back)
+        st = chd_tick_impl(e, q, t_ns, flags, nullptr);
+    }
+    if (st != CHD_OK) return st;
+    if (out) return chd_summary(e, out);
+    return CHD_OK;
+}
+
+static chd_status chd_tick_impl(chd_engine* e, const chd_query_batch* q, int64_t t_ns, uint32_t flags, chd_tick_summary* out) {
+    chd_status st;
+    const bool need_build = (flags & CHD_TICK_BUILD) && (e->entities_dirty || !e->built);
+    const bool do_emit = flags & CHD_TICK_EMIT;
+    bool do_fanout = flags & CHD_TICK_FANOUT;
+    e->early_ready = false;
+    e->build_done_recorded = false;
+    e->early_results_tick = (flags & CHD_TICK_EARLY_RESULTS) != 0;
+    if (e->interest_pending) {
+        // interest (+ fan-out) of this tick were started early with chd_begin_interest and are running on aux_stream
+        if (q) {
+            e->fail("chd_tick: a query batch was given while chd_begin_interest is pending");
+            return CHD_ERR_STATE;
+        }
+        cudaStream_t main_stream = e->stream;
+        e->interest_pending = false;
+        if (need_build) {
+            st = chd_build(e);
+            if (st != CHD_OK) return st;
+            CU(e, cudaEventRecord(e->ev_build_done, main_stream));
+            e->build_done_recorded = true;
+        }
+        CU(e, cudaStreamWaitEvent(main_stream, e->ev_pairs, 0));
+        if (do_emit) {
+            if (e->early_results_tick) e->wait_before_emit_kernel = e->ev_join;
+            st = chd_emit_visible(e);
+            if (st != CHD_OK) return st;
+        }
+        CU(e, cudaStreamWaitEvent(main_stream, e->ev_join, 0));
+        if (do_fanout && !e->pending_fanout) {
+            st = chd_fanout_tick(e, t_ns);
+            if (st != CHD_OK) return st;
+        } else {
+            e->early_ready = do_emit;  // everything but the expanded list is final at ev_join + ev_prep_done
+        }
+        if (out) return chd_summary(e, out);
+        return CHD_OK;
+    }
+    if (e->overlap_fanout && e->aux_stream && (q || do_fanout) && (need_build || do_emit)) {
+        // Dependency graph of a tick:   build ----------------+--> emit
+        //                               interest --> fan-out  |      (emit needs the cell CSR and the new pairs)
+        // The build / emit chain (HBM-bound) runs on the main stream, the interest / fan-out chain
+        // (latency-bound, disjoint state) on aux_stream; they are joined before the summary.
+        cudaStream_t main_stream = e->stream;
+        CU(e, cudaEventRecord(e->ev_fork, main_stream));
+        CU(e, cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0));
+        std::unique_lock<std::recursive_mutex> redirect(e->mu);  // `stream` is redirected until it is restored below
+        e->stream = e->aux_stream;
+        st = q ? chd_update_interest(e, q, t_ns) : CHD_OK;
+        if (st == CHD_OK) {
+            cudaError_t r = cudaEventRecord(e->ev_interest, e->aux_stream);
+            if (r != cudaSuccess) st = CHD_ERR_CUDA;
+        }
+        if (st == CHD_OK && do_fanout) st = chd_fanout_tick(e, t_ns);
+        e->stream = main_stream;
+        redirect.unlock();
+        if (st != CHD_OK) return st;
+        CU(e, cudaEventRecord(e->ev_join, e->aux_stream));
+        if (need_build) {
+            st = chd_build(e);
+            if (st != CHD_OK) return st;
+            CU(e, cudaEventRecord(e->ev_build_done, main_stream));
+            e->build_done_recorded = true;
+        }
+        if (do_emit) {
+            CU(e, cudaStreamWaitEvent(main_stream, !q ? e->ev_interest : e->ev_pairs, 0));
+            if (e->early_results_tick) e->wait_before_emit_kernel = e->ev_join;
+            st = chd_emit_visible(e);
+            if (st != CHD_OK) return st;
+        }
+        CU(e, cudaStreamWaitEvent(main_stream, e->ev_join, 0));
+        e->early_ready = do_emit;
+    } else {
+        if (need_build) {
+            st = chd_build(e);
+            if (st != CHD_OK) return st;
+        }
+        if (q) {
+            st = chd_update_interest(e, q, t_ns);
+            if (st != CHD_OK) return st;
+        }
+        if (do_emit) {
+            st = chd_emit_visible(e);
+            if (st != CHD_OK) return st;
+        }
+        if (do_fanout) {
+            st = chd_fanout_tick(e, t_ns);
+            if (st != CHD_OK) return st;
+        }
+    }
+    if (out) return chd_summary(e, out);
+    return CHD_OK;
+}
+}  // extern "C"

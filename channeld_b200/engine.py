@@ -102,10 +102,14 @@ class Engine:
         self._ck(self.L.chd_sync(self.h))
 
     # ---- GetChannelId (batched)
-    def cell_of(self, x, z):
+    def cell_of(self, x, z, with_valid=False):
         x = np.ascontiguousarray(x, np.float64)
         z = np.ascontiguousarray(z, np.float64)
         out = np.zeros(len(x), np.uint32)
+        if with_valid:
+            ok = np.zeros(len(x), np.uint8)
+            self._ck(self.L.chd_cell_of_valid(self.h, ptr(x), ptr(z), len(x), ptr(out), ptr(ok)))
+            return out, ok.astype(bool)
         self._ck(self.L.chd_cell_of(self.h, ptr(x), ptr(z), len(x), ptr(out)))
         return out
 

@@ -58,8 +58,9 @@ class GpuStaticGrid2DSpatialController {
     // GetChannelId (spatial.go:161-163)
     uint32_t GetChannelId(const SpatialInfo& info) {
         uint32_t id = 0;
-        check(chd_cell_of(engine_, &info.X, &info.Z, 1, &id));
-        if (id == 0) throw SpatialError("position is outside the grid");
+        uint8_t ok = 0;  // explicit validity: with SpatialChannelIdStart == 0 the id 0 is a real cell
+        check(chd_cell_of_valid(engine_, &info.X, &info.Z, 1, &id, &ok));
+        if (!ok) throw SpatialError("position is outside the grid");
         return id;
     }
     // batched form (handleQuerySpatialChannel, message_spatial.go:335-370); 0 marks an error

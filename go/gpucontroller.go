@@ -63,14 +63,16 @@ func (ctl *GpuStaticGrid2DSpatialController) LoadConfig(config []byte) error {
 // GetChannelId (spatial.go:161-163).  One position per cgo call is only for interface compatibility; the
 // batched form below (handleQuerySpatialChannel, message_spatial.go:335-370) is the one to use on hot paths.
 func (ctl *GpuStaticGrid2DSpatialController) GetChannelId(info common.SpatialInfo) (common.ChannelId, error) {
-	ids, err := ctl.GetChannelIds([]float64{info.X}, []float64{info.Z})
-	if err != nil {
-		return 0, err
+	x, z := C.double(info.X), C.double(info.Z)
+	var id C.uint32_t
+	var ok C.uint8_t // explicit validity: with SpatialChannelIdStart == 0 the id 0 is a real cell
+	if st := C.chd_cell_of_valid(ctl.engine, &x, &z, 1, &id, &ok); st != C.CHD_OK {
+		return 0, errors.New(C.GoString(C.chd_last_error(ctl.engine)))
 	}
-	if ids[0] == 0 {
+	if ok == 0 {
 		return 0, fmt.Errorf("position (%f, %f) is outside the grid", info.X, info.Z)
 	}
-	return common.ChannelId(ids[0]), nil
+	return common.ChannelId(id), nil
 }
 
 func (ctl *GpuStaticGrid2DSpatialController) GetChannelIds(x, z []float64) ([]uint32, error) {

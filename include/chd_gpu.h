@@ -4,8 +4,11 @@
  * This is the drop-in boundary behind channeld's SpatialController plugin surface
  * (reference: channeldorg/channeld @ 61fa8add, pkg/channeld/spatial.go:17-35).  A cgo shim binds exactly
  * these entry points (go/gpucontroller.go).  Plain pointers and sizes only; no C++/torch
- * types; integer status codes; no exceptions cross the ABI; the engine never retains caller pointers after
- * a call returns (cgo rule).  Pointer arguments may be host (pageable or pinned) or device pointers unless
+ * types; integer status codes; no exceptions cross the ABI.  Pointer retention: the synchronous entry points (chd_cell_of,
+ * chd_query_channel_ids, chd_adjacent_broadcast, chd_get_*, chd_fetch_results, chd_summary) are done with every caller pointer
+ * when they return; the stream-ordered ones (chd_set_*, chd_prefetch_*, chd_tick, chd_update_interest with HOST arrays) read
+ * caller memory asynchronously until the next synchronising call — such buffers must be C memory (chd_alloc_pinned), never
+ * Go-managed memory (cgo pointer rules).  Pointer arguments may be host (pageable or pinned) or device pointers unless
  * stated otherwise.  HOST inputs are copied (cudaMemcpyAsync on the engine's stream; pinned memory makes that
  * asynchronous) and may be reused once the call that consumes them has been followed by chd_summary / chd_sync /
  * a chd_get_* call.  DEVICE inputs of the tick path (chd_set_entities, chd_set_rings, the arrays of a
@@ -89,6 +92,9 @@ void chd_free_pinned(void* p);
  * message_spatial.go:335-370).  out_channel_id[i] = channel id, or 0 where the reference returns an error
  * (outside [0,cols) x [0,rows), NaN, +-Inf, huge).  Synchronous. */
 chd_status chd_cell_of(chd_engine* e, const double* x, const double* z, uint32_t n, uint32_t* out_channel_id);
+/* The same with an explicit validity flag per position (out_valid[i] = 1 / 0; may be NULL): needed when
+ * channel_id_start == 0, where channel id 0 is a real cell and cannot double as the error value. */
+chd_status chd_cell_of_valid(chd_engine* e, const double* x, const double* z, uint32_t n, uint32_t* out_channel_id, uint8_t* out_valid);
 
 /* ---- entity positions (SoA).  Replaces the per-cell entity maps the reference keeps in
  * SpatialChannelData.Entities (pkg/unrealpb/extension.go:38-62) fed by AddEntity/RemoveEntity
@@ -147,8 +153,12 @@ enum {
     CHD_Q_OK = 0,
     CHD_Q_ERR_OUT_OF_WORLD = 1, /* centre of a box/sphere/cone outside the world: (nil, err) */
     CHD_Q_ERR_BAD_STEP = 2,     /* radius / extent <= 0 */
-    CHD_Q_ERR_ITER_BOUND = 5,   /* step absorbed by a huge coordinate: the reference would loop forever */
-    CHD_Q_ERR_ANGLE_RANGE = 6   /* |cone angle| >= 2^29: Go switches to Payne-Hanek reduction, not reproduced */
+    CHD_Q_ERR_ITER_BOUND = 5,   /* step absorbed by a huge coordinate (v + step == v: the reference would loop forever), or a
+                                   lattice walk of more than 2^24 samples (cut off: a documented deviation) */
+    CHD_Q_ERR_ANGLE_RANGE = 6,  /* |cone angle| >= 2^29: Go switches to Payne-Hanek reduction, not reproduced */
+    CHD_Q_ERR_CAPACITY = 7,     /* the query's cell window did not fit chd_limits.max_window_cells (CHD_OVF_WINDOW is raised):
+                                   like every failed query it leaves the subscriber's subscriptions untouched */
+    CHD_Q_ERR_MISSING_ARRAY = 8 /* a kind bit is set but that kind's arrays were not supplied in the batch */
 };
 
 /* ---- QueryChannelIds, batched and stateless (spatial.go:182-317).  CSR output, entries of one query sorted
@@ -185,10 +195,12 @@ chd_status chd_prefetch_rings(chd_engine* e, const uint32_t* ring_off, uint32_t 
 
 
 /* One fan-out decision = one fanOutDataUpdate call of the reference (data.go:221,263). */
+#define CHD_DUE_VOID 0xFFFFFFFFu
 typedef struct chd_due {
     uint32_t sub;          /* subscriber slot */
     uint32_t channel_id;   /* spatial channel */
-    uint32_t kind;         /* 0 = FULL channel data (first fan-out, data.go:218-224), 1 = accumulated UPDATE */
+    uint32_t kind;         /* 0 = FULL channel data (first fan-out, data.go:218-224), 1 = accumulated UPDATE,
+                              CHD_DUE_VOID = not a decision (only in a list that overflowed, see CHD_OVF_DUE) */
     uint32_t n_selected;   /* UPDATE: ring entries merged (data.go:246-256) */
     uint32_t first_sel, last_sel; /* ring positions (0-based within the cell's ring) of the first/last merged entry */
     uint64_t sel_hash;     /* sum of merged entries' messageIndex mod 2^64 (lets the host verify its own selection) */
@@ -212,11 +224,21 @@ typedef struct chd_tick_summary {
     uint32_t n_sub_new, n_unsub, n_kept;
     uint32_t n_due;
     uint32_t n_handover;
-    uint32_t overflow;         /* bitmask of CHD_OVF_*; outputs of an overflowed stage are truncated/invalid */
+    uint32_t overflow;         /* bitmask of CHD_OVF_* (see below for what each one leaves behind) */
     uint64_t required_pairs, required_window_cells, required_visible;
     uint32_t required_due;
     uint32_t reserved;
 } chd_tick_summary;
+/* Capacities are fixed at chd_create, so an overflow cannot be retried with the same engine; what matters is that it never
+ * corrupts state:
+ *   CHD_OVF_PAIRS   the interest update was NOT applied: every subscriber keeps its previous subscriptions and fan-out state,
+ *                   the diff lists are empty; required_pairs = the total the update would have needed
+ *   CHD_OVF_WINDOW  the queries whose cell windows did not fit got CHD_Q_ERR_CAPACITY and, like any failed query, left their
+ *                   subscribers untouched; the rest of the batch was applied; required_window_cells = scratch needed
+ *   CHD_OVF_VISIBLE the expanded visible list was not written (offsets are valid); required_visible = entries needed
+ *   CHD_OVF_DUE     the pairs whose decisions did not fit were left untouched (still due: they catch up at the next
+ *                   chd_fanout_tick); the list holds the decisions that did fit plus CHD_DUE_VOID holes; required_due
+ *   CHD_OVF_BORDER  multi-GPU border / halo capacity exceeded: this tick's halo is incomplete */
 enum { CHD_OVF_PAIRS = 1, CHD_OVF_WINDOW = 2, CHD_OVF_VISIBLE = 4, CHD_OVF_DUE = 8, CHD_OVF_BORDER = 16 };
 /* bit 31: a device-side wait timed out (results invalid, please report).  A macro, not an enumerator: ISO C enumerators
  * must fit an int. */

@@ -5,7 +5,10 @@
 
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <list>
 #include <map>
 #include <thread>
@@ -52,7 +55,9 @@ inline bool cell_index(const orc_grid* g, double x, double z, uint32_t* idx) {
     return true;
 }
 
-const uint64_t kIterBound = 1ull << 26;  // oracle-only guard (absorbed step, SURVEY §8c')
+// Guard against the reference's non-terminating walks (SURVEY §8c'): an absorbed step (v + step == v) loops forever in Go;
+// walks of more than 2^24 samples are cut off too.  The CUDA path applies the same two rules (chd_query.cuh).
+const uint64_t kIterBound = 1ull << 24;
 
 // spatial.go:182-317 into any map-like container M (operator[] overwrite = Go map assignment).
 template <class M>
@@ -78,11 +83,11 @@ int query_into(const orc_grid* g, const orc_query* q, M& result) {
         uint64_t iters = 0;
         for (double z = cz - q->box_ez; z <= cz + q->box_ez; z += stepZ) {
             for (double x = cx - q->box_ex; x <= cx + q->box_ex; x += stepX) {
-                if (++iters > kIterBound) return ORC_ERR_ITER_BOUND;
+                if (x + stepX == x || ++iters > kIterBound) return ORC_ERR_ITER_BOUND;
                 if (!cell_index(g, x, z, &idx)) continue;
                 result[idx + base] = uint32_t(std::ceil(dist2d(cx, cz, x, z) / grid_size));
             }
-            if (++iters > kIterBound) return ORC_ERR_ITER_BOUND;
+            if (z + stepZ == z || ++iters > kIterBound) return ORC_ERR_ITER_BOUND;
         }
         if (!cell_index(g, cx, cz, &idx)) return ORC_ERR_OUT_OF_WORLD;
         result[idx + base] = 0;
@@ -97,12 +102,12 @@ int query_into(const orc_grid* g, const orc_query* q, M& result) {
         uint64_t iters = 0;
         for (double z = cz - r; z <= cz + r; z += stepZ) {
             for (double x = cx - r; x <= cx + r; x += stepX) {
-                if (++iters > kIterBound) return ORC_ERR_ITER_BOUND;
+                if (x + stepX == x || ++iters > kIterBound) return ORC_ERR_ITER_BOUND;
                 if ((x - cx) * (x - cx) + (z - cz) * (z - cz) > r * r) continue;
                 if (!cell_index(g, x, z, &idx)) continue;
                 result[idx + base] = uint32_t(std::ceil(dist2d(cx, cz, x, z) / grid_size));
             }
-            if (++iters > kIterBound) return ORC_ERR_ITER_BOUND;
+            if (z + stepZ == z || ++iters > kIterBound) return ORC_ERR_ITER_BOUND;
         }
         if (!cell_index(g, cx, cz, &idx)) return ORC_ERR_OUT_OF_WORLD;
         result[idx + base] = 0;
@@ -122,11 +127,14 @@ int query_into(const orc_grid* g, const orc_query* q, M& result) {
         if (stepX <= 0) return ORC_ERR_BAD_STEP;
         const double z_hi = go_min(g->world_offset_z + world_height(g), cz + r);
         const double x_hi = go_min(g->world_offset_x + world_width(g), cx + r);
+        // |angle| >= 2^29: Go's math.Cos switches to Payne-Hanek reduction, which is not restated; both this oracle and the CUDA
+        // path reject such a query (documented deviation) instead of answering with a different cosine
+        if (std::fabs(q->cone_angle) >= double(1 << 29)) return ORC_ERR_ANGLE_RANGE;
         const double cosv = orc_go_cos(q->cone_angle);  // spatial.go:295 (loop-invariant)
         uint64_t iters = 0;
         for (double z = go_max(g->world_offset_z, cz - r); z <= z_hi; z += stepZ) {
             for (double x = go_max(g->world_offset_x, cx - r); x <= x_hi; x += stepX) {
-                if (++iters > kIterBound) return ORC_ERR_ITER_BOUND;
+                if (x + stepX == x || ++iters > kIterBound) return ORC_ERR_ITER_BOUND;
                 if ((x - cx) * (x - cx) + (z - cz) * (z - cz) > r * r) continue;
                 double vx = x - cx, vz = z - cz;
                 const double mag = std::sqrt(vx * vx + vz * vz);
@@ -137,7 +145,7 @@ int query_into(const orc_grid* g, const orc_query* q, M& result) {
                 if (!cell_index(g, x, z, &idx)) continue;
                 result[idx + base] = uint32_t(std::ceil(dist2d(cx, cz, x, z) / grid_size));
             }
-            if (++iters > kIterBound) return ORC_ERR_ITER_BOUND;
+            if (z + stepZ == z || ++iters > kIterBound) return ORC_ERR_ITER_BOUND;
         }
         if (!cell_index(g, cx, cz, &idx)) return ORC_ERR_OUT_OF_WORLD;
         result[idx + base] = 0;
@@ -157,7 +165,7 @@ double orc_grid_size(const orc_grid* g) {  // spatial.go:134-139
 
 // Go math.Cos (src/math/sin.go; Cephes cosf/sinf polynomials, 3-part pi/4 reduction).  The Go source is not
 // in /root/reference; this restates the published algorithm.  |x| >= 2^29 uses Payne-Hanek in Go; that branch
-// is outside every parity input, so libm cos is substituted there (documented deviation).
+// is not restated: QueryChannelIds rejects such cone angles (ORC_ERR_ANGLE_RANGE); this function alone falls back to libm.
 double orc_go_cos(double x) {
     static const double kSin[6] = {1.58962301576546568060e-10, -2.50507477628578072866e-8, 2.75573136213857245213e-6,
                                    -1.98412698295895385996e-4, 8.33333333332211858878e-3,  -1.66666666666666307295e-1};
@@ -546,16 +554,129 @@ int orc_sphere_tick(const orc_grid* g, const double* ex, const double* ez, uint3
     return rc;
 }
 
+// ---- CPU baseline (bench.py cpu_baseline / --impl reference): the reference's per-query algorithm over all host threads.
+// A persistent pool (workers park on a condition variable between calls) replaces the thread-per-call spawning of round 1,
+// and the per-cell entity lists are built in parallel (per-thread histograms over contiguous slices + prefix + stable scatter:
+// same (cell asc, entity asc) order as the serial build).  Round 1's serial build made the 128-thread figure Amdahl-bound.
+namespace {
+class Pool {
+public:
+    static Pool& get() {
+        static Pool* p = new Pool();  // leaked on purpose: parked workers must never see the pool destroyed at exit
+        return *p;
+    }
+    // runs fn(tid) for tid in [0, n) on n threads (the caller is tid 0) and waits
+    void run(int n, const std::function<void(int)>& fn) {
+        std::unique_lock<std::mutex> call_lock(call_mu_);  // one parallel region at a time
+        grow(n - 1);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &fn;
+            active_ = n - 1;
+            pending_ = n - 1;
+            gen_++;
+        }
+        cv_.notify_all();
+        fn(0);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+private:
+    void grow(int workers) {
+        while ((int)th_.size() < workers) {
+            const int id = (int)th_.size() + 1;
+            th_.emplace_back([this, id] { loop(id); });
+            th_.back().detach();
+        }
+    }
+    void loop(int id) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int)>* fn = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (id <= active_) fn = fn_;
+            }
+            if (!fn) continue;
+            (*fn)(id);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--pending_ == 0) done_cv_.notify_one();
+            }
+        }
+    }
+    std::mutex mu_, call_mu_;
+    std::condition_variable cv_, done_cv_;
+    std::vector<std::thread> th_;
+    const std::function<void(int)>* fn_ = nullptr;
+    int active_ = 0, pending_ = 0;
+    uint64_t gen_ = 0;
+};
+
+void build_cell_lists_mt(const orc_grid* g, const double* ex, const double* ez, uint32_t n, CellLists& cl, int n_threads) {
+    if (n_threads <= 1 || n < 65536) {
+        build_cell_lists(g, ex, ez, n, cl);
+        return;
+    }
+    const uint32_t C = g->grid_cols * g->grid_rows;
+    static std::vector<uint32_t> cell;       // reused between ticks
+    static std::vector<uint32_t> hist;       // [thread][C]
+    cell.resize(n);
+    hist.assign(size_t(n_threads) * C, 0);
+    auto slice = [&](int t, uint32_t& lo, uint32_t& hi) {
+        lo = uint32_t(uint64_t(n) * uint64_t(t) / uint64_t(n_threads));
+        hi = uint32_t(uint64_t(n) * uint64_t(t + 1) / uint64_t(n_threads));
+    };
+    Pool::get().run(n_threads, [&](int t) {
+        uint32_t lo, hi;
+        slice(t, lo, hi);
+        uint32_t* h = hist.data() + size_t(t) * C;
+        for (uint32_t i = lo; i < hi; i++) {
+            uint32_t idx;
+            if (cell_index(g, ex[i], ez[i], &idx)) {
+                cell[i] = idx;
+                h[idx]++;
+            } else
+                cell[i] = 0xFFFFFFFFu;
+        }
+    });
+    cl.start.assign(C + 1, 0);
+    uint32_t run = 0;
+    for (uint32_t c = 0; c < C; c++) {  // exclusive offsets in (cell, thread) order = stable
+        cl.start[c] = run;
+        for (int t = 0; t < n_threads; t++) {
+            const uint32_t v = hist[size_t(t) * C + c];
+            hist[size_t(t) * C + c] = run;
+            run += v;
+        }
+    }
+    cl.start[C] = run;
+    cl.sorted.resize(run);
+    Pool::get().run(n_threads, [&](int t) {
+        uint32_t lo, hi;
+        slice(t, lo, hi);
+        uint32_t* h = hist.data() + size_t(t) * C;
+        for (uint32_t i = lo; i < hi; i++)
+            if (cell[i] != 0xFFFFFFFFu) cl.sorted[h[cell[i]]++] = i;
+    });
+}
+}  // namespace
+
 uint64_t orc_baseline_run(const orc_grid* g, const double* ex, const double* ez, uint32_t n_ent, const double* cx,
                           const double* cz, const double* r, uint32_t q_begin, uint32_t q_end, int n_threads, int build) {
     static CellLists cached;
     static uint32_t cached_n = 0;
+    if (n_threads < 1) n_threads = 1;
     if (build || cached_n != n_ent) {
-        build_cell_lists(g, ex, ez, n_ent, cached);
+        if (build == 2) build_cell_lists(g, ex, ez, n_ent, cached);  // round-1 behaviour (serial build), kept for comparison
+        else build_cell_lists_mt(g, ex, ez, n_ent, cached, n_threads);
         cached_n = n_ent;
     }
     const CellLists& cl = cached;
-    if (n_threads < 1) n_threads = 1;
     std::vector<uint64_t> sums(size_t(n_threads), 0);
     auto work = [&](int tid) {
         std::vector<uint32_t> scratch;
@@ -583,10 +704,7 @@ uint64_t orc_baseline_run(const orc_grid* g, const double* ex, const double* ez,
         }
         sums[size_t(tid)] = acc;
     };
-    std::vector<std::thread> th;
-    for (int t = 1; t < n_threads; t++) th.emplace_back(work, t);
-    work(0);
-    for (auto& t : th) t.join();
+    Pool::get().run(n_threads, work);
     uint64_t total = 0;
     for (auto v : sums) total += v;
     return total;

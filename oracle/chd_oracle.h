@@ -65,7 +65,8 @@ enum {
     ORC_ERR_BAD_STEP = 2,     /* spatial.go:208-215,:240-247,:277-284 */
     ORC_ERR_NIL = 3,          /* spatial.go:183-185 */
     ORC_ERR_CAPACITY = 4,
-    ORC_ERR_ITER_BOUND = 5    /* oracle-only guard against the absorbed-step infinite loop */
+    ORC_ERR_ITER_BOUND = 5,   /* guard against the absorbed-step infinite loop / walks of > 2^24 samples (same rule in the CUDA path) */
+    ORC_ERR_ANGLE_RANGE = 6   /* |cone angle| >= 2^29 (Go: Payne-Hanek reduction, not restated); same rule in the CUDA path */
 };
 
 /* spatial.go:134-139 */
@@ -159,7 +160,8 @@ int orc_sphere_tick(const orc_grid* g, const double* ex, const double* ez, uint3
 
 /* Timed CPU baseline: for queries [q_begin,q_end) run the per-query map-building QueryChannelIds and
  * copy every visible entity index into a per-thread scratch list (the work the reference's fan-out
- * implies), using cell lists built from all n_ent entities (build is included when build!=0).
+ * implies), using cell lists built from all n_ent entities (build != 0: rebuilt inside the call, in parallel over n_threads;
+ * build == 2: rebuilt serially, the round-1 behaviour, kept for comparison).  Threads come from a persistent pool.
  * Returns a checksum (sum of visible counts + pair counts) so the work cannot be optimised away. */
 uint64_t orc_baseline_run(const orc_grid* g, const double* ex, const double* ez, uint32_t n_ent,
                           const double* cx, const double* cz, const double* r, uint32_t q_begin, uint32_t q_end,

@@ -1,0 +1,228 @@
+"""GPU tests of the capacity / error rules of the C ABI (include/chd_gpu.h, CHD_OVF_*): an overflow or a malformed
+query never corrupts the engine's state.  Findings of the round-1 review, each reproduced here."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+S0 = 65536
+MS = 1_000_000
+
+
+@pytest.fixture(scope="module")
+def chd():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from channeld_b200 import capi, engine, synth
+
+    capi.lib()
+
+    class NS:
+        pass
+
+    ns = NS()
+    ns.capi, ns.engine, ns.synth = capi, engine, synth
+    return ns
+
+
+def _small_world(chd, n_sub=64, **lim):
+    """8x8 grid of 100x100 cells at the origin; n_sub subscribers with sphere AOIs."""
+    cfg = chd.engine.grid_cfg(0, 0, 100, 100, 8, 8)
+    e = chd.engine.Engine(cfg, 1024, n_sub, **lim)
+    rng = np.random.default_rng(7)
+    ex, ez = rng.uniform(0, 800, 1000), rng.uniform(0, 800, 1000)
+    e.set_entities(ex, ez)
+    e.set_subscribers(np.arange(1, n_sub + 1, dtype=np.uint32))
+    return e, rng
+
+
+def _state(e):
+    p = e.get_pairs()
+    return {k: v.copy() for k, v in p.items()}
+
+
+def _same_state(a, b):
+    """Subscriptions and fan-out state equal (PF_NEW only says whether the LAST update created the pair)."""
+    def norm(k, v):
+        return v & ~np.uint8(2) if k == "flags" else v
+    return all(np.array_equal(norm(k, a[k]), norm(k, b[k])) for k in a)
+
+
+def test_window_overflow_leaves_state_untouched(chd):
+    """A few huge AOIs exhaust max_window_cells: those queries fail with CHD_Q_ERR_CAPACITY, their subscribers keep their
+    subscriptions, everybody else is updated, nothing is written out of bounds (review finding: chd_query.cuh OVF_WINDOW)."""
+    capi = chd.capi
+    n = 64
+    e, rng = _small_world(chd, n, max_window_cells=320)
+    cx, cz = rng.uniform(150, 650, n), rng.uniform(150, 650, n)
+    r = np.full(n, 30.0)
+    b, keep = chd.engine.make_batch(n, sphere=(cx, cz, r))
+    s = e.tick(b, 1 * MS)
+    assert s.overflow == 0 and s.n_query_errors == 0
+    before = _state(e)
+    # second update: small moves for everybody, but the last 8 subscribers ask for the whole world (64 cells each: only the
+    # first one or two of them can still fit the 320-cell scratch once the small windows are placed)
+    cx2, cz2 = cx + 40.0, cz + 40.0
+    r2 = r.copy()
+    r2[-8:] = 2000.0
+    b2, keep2 = chd.engine.make_batch(n, sphere=(cx2, cz2, r2))
+    with pytest.raises(chd.capi.ChdError) as ei:
+        e.tick(b2, 2 * MS)
+    assert ei.value.status == capi.ERR_CAPACITY
+    st = e.get_query_status(n)
+    failed = np.nonzero(st == capi.Q_ERR_CAPACITY)[0]
+    assert len(failed) >= 1 and set(st.tolist()) <= {capi.Q_OK, capi.Q_ERR_CAPACITY}
+    after = _state(e)
+    want_status, want_off, want_id, want_dist = e.query_channel_ids(chd.engine.make_batch(n, sphere=(cx2, cz2, np.full(n, 30.0)))[0])
+    for j in range(n):
+        got = after["channel"][after["off"][j]:after["off"][j + 1]]
+        if st[j] == capi.Q_ERR_CAPACITY:  # untouched
+            np.testing.assert_array_equal(got, before["channel"][before["off"][j]:before["off"][j + 1]])
+        elif r2[j] == 30.0:  # applied
+            np.testing.assert_array_equal(got, want_id[want_off[j]:want_off[j + 1]])
+    # the engine keeps working: a third, sane update is applied in full
+    s3 = e.tick(b, 3 * MS)
+    assert s3.overflow == 0 and s3.n_query_errors == 0
+    assert _same_state({k: v for k, v in _state(e).items() if k in ("off", "channel", "dist")},
+                       {k: v for k, v in before.items() if k in ("off", "channel", "dist")})
+    e.close()
+
+
+def test_pair_overflow_is_transactional(chd):
+    """An interest update whose pair total exceeds max_pairs is not applied at all (review finding: the pair buffers were
+    flipped over garbage)."""
+    capi = chd.capi
+    n = 64
+    e, rng = _small_world(chd, n, max_pairs=200, max_window_cells=1 << 16)
+    cx, cz = rng.uniform(150, 650, n), rng.uniform(150, 650, n)
+    b, keep = chd.engine.make_batch(n, sphere=(cx, cz, np.full(n, 30.0)))
+    s = e.tick(b, 1 * MS)
+    assert s.overflow == 0 and s.n_pairs <= 200
+    before = _state(e)
+    big, keep2 = chd.engine.make_batch(n, sphere=(cx, cz, np.full(n, 400.0)))  # dozens of cells each: thousands of pairs
+    with pytest.raises(chd.capi.ChdError) as ei:
+        e.tick(big, 2 * MS)
+    assert ei.value.status == capi.ERR_CAPACITY
+    s2 = chd.capi.TickSummary()
+    e.L.chd_summary(e.h, C.byref(s2))
+    assert _same_state(_state(e), before)
+    # the next sane update diffs against the untouched state: everything is "kept"
+    s3 = e.tick(b, 3 * MS)
+    assert s3.overflow == 0 and s3.n_kept == s3.n_pairs == s.n_pairs and s3.n_sub_new == 0 and s3.n_unsub == 0
+    e.close()
+
+
+def test_due_overflow_is_transactional(chd, oracle):
+    """Decisions that do not fit max_due are neither delivered nor committed: the pairs stay due and catch up at the next
+    tick (review finding: fan-out state was committed for dropped decisions)."""
+    capi = chd.capi
+    n = 64
+    e, rng = _small_world(chd, n, max_due=16)
+    cx, cz = rng.uniform(150, 650, n), rng.uniform(150, 650, n)
+    b, keep = chd.engine.make_batch(n, sphere=(cx, cz, np.full(n, 30.0)))
+    cells = 64
+    e.set_rings(np.zeros(cells + 1, np.uint32), np.zeros(0, np.int64), np.zeros(0, np.uint32), np.zeros(0, np.uint64))
+    s = e.tick(b, 0)
+    P = int(s.n_pairs)
+    assert P > 16
+    # 100 ms later every pair is due for its first (FULL) fan-out: P decisions, capacity 16
+    with pytest.raises(chd.capi.ChdError) as ei:
+        e.tick(None, 100 * MS, capi.TICK_FANOUT)
+    assert ei.value.status == capi.ERR_CAPACITY
+    st = _state(e)
+    had = (st["flags"] & capi.PF_HAD_FIRST) != 0
+    due = e.get_due(16)
+    real = due[due["kind"] != capi.DUE_VOID]
+    assert had.sum() == len(real) <= 16 and (real["kind"] == 0).all()
+    # every later tick delivers up to 16 more; nothing is lost, nothing is delivered twice
+    delivered = set(zip(real["sub"].tolist(), real["channel_id"].tolist()))
+    t = 100 * MS
+    for _ in range(P):
+        if len(delivered) == P:
+            break
+        t += 1 * MS
+        try:
+            s = e.tick(None, t, capi.TICK_FANOUT)
+            n_due = s.n_due
+        except chd.capi.ChdError as ex:
+            assert ex.status == capi.ERR_CAPACITY
+            n_due = 16
+        due = e.get_due(min(n_due, 16))
+        real = due[due["kind"] == 0]
+        new = set(zip(real["sub"].tolist(), real["channel_id"].tolist()))
+        assert not (new & delivered)
+        delivered |= new
+    assert len(delivered) == P
+    e.close()
+
+
+def test_missing_kind_arrays_are_a_query_error(chd):
+    """A kind bit without its arrays is a per-query error, not a null dereference on the device."""
+    capi = chd.capi
+    e, rng = _small_world(chd, 4)
+    kind = np.array([capi.AOI_SPHERE, capi.AOI_BOX, capi.AOI_SPHERE | capi.AOI_CONE, capi.AOI_SPHERE], np.uint8)
+    b, keep = chd.engine.make_batch(4, kind=kind, sphere=(np.full(4, 400.0), np.full(4, 400.0), np.full(4, 30.0)))
+    status, off, ids, dist = e.query_channel_ids(b)
+    assert status.tolist() == [capi.Q_OK, capi.Q_ERR_MISSING_ARRAY, capi.Q_ERR_MISSING_ARRAY, capi.Q_OK]
+    assert off[1] == off[2] == off[3] and off[4] > off[3]
+    e.close()
+
+
+def test_stateless_queries_do_not_disturb_interest_statuses(chd):
+    capi = chd.capi
+    e, rng = _small_world(chd, 4)
+    cx = np.array([400.0, -50.0, 400.0, 400.0])  # query 1: centre out of the world
+    b, keep = chd.engine.make_batch(4, sphere=(cx, np.full(4, 400.0), np.full(4, 30.0)))
+    e.tick(b, 1 * MS)
+    want = e.get_query_status(4).copy()
+    assert want[1] == capi.Q_ERR_OUT_OF_WORLD
+    ok, keep2 = chd.engine.make_batch(4, sphere=(np.full(4, 100.0), np.full(4, 100.0), np.full(4, 10.0)))
+    st, *_ = e.query_channel_ids(ok)
+    assert (st == 0).all()
+    np.testing.assert_array_equal(e.get_query_status(4), want)
+    e.close()
+
+
+def test_cell_of_valid_with_id_start_zero(chd):
+    cfg = chd.engine.grid_cfg(0, 0, 10, 10, 4, 4, id_start=0)
+    e = chd.engine.Engine(cfg, 16, 4)
+    ids, ok = e.cell_of(np.array([5.0, -1.0, 35.0]), np.array([5.0, 5.0, 35.0]), with_valid=True)
+    assert ids.tolist() == [0, 0, 15] and ok.tolist() == [True, False, True]
+    e.close()
+
+
+def test_iteration_guards_match_the_oracle(chd, oracle):
+    """Absorbed steps and oversized walks are rejected identically on both sides; |angle| >= 2^29 likewise."""
+    from tests._oracle import make_grid
+
+    capi = chd.capi
+    cfg = chd.engine.grid_cfg(-1e6, -1e6, 20, 20, 100, 100)
+    e = chd.engine.Engine(cfg, 16, 8)
+    og = make_grid(-1e6, -1e6, 20, 20, 100, 100, 1, 1)
+    cases = [
+        dict(sphere=(1e17, 0.0, 5.0)),         # x + 2.5 == x: absorbed
+        dict(sphere=(0.0, -3e18, 1.0)),        # z absorbed
+        dict(sphere=(0.0, 0.0, 45000.0)),      # 4500^2 = 2e7 samples > 2^24
+        dict(sphere=(0.0, 0.0, 20000.0)),      # 1.6e7 samples < 2^24: walked to the end (centre outside the world)
+        dict(cone=(-999000.0, -999000.0, 1.0, 0.0, float(1 << 29), 50.0)),
+        dict(cone=(-999000.0, -999000.0, 1.0, 0.0, float((1 << 29) - 1), 50.0)),
+    ]
+    for c in cases:
+        if "sphere" in c:
+            cx, cz, r = c["sphere"]
+            b, keep = chd.engine.make_batch(1, sphere=(np.array([cx]), np.array([cz]), np.array([r])))
+            want, wst = oracle.query(og, sphere=(cx, cz, r))
+        else:
+            cx, cz, dx, dz, ang, r = c["cone"]
+            b, keep = chd.engine.make_batch(1, kind=np.array([capi.AOI_CONE], np.uint8),
+                                            cone=tuple(np.array([v]) for v in (cx, cz, dx, dz, ang, r)))
+            want, wst = oracle.query(og, cone=(cx, cz, dx, dz, ang, r))
+        st, off, ids, dist = e.query_channel_ids(b, cap=1 << 16)
+        assert int(st[0]) == int(wst), (c, st, wst)
+        if wst == 0:
+            assert dict(zip(ids.tolist(), dist.tolist())) == want
+    e.close()

@@ -148,6 +148,78 @@ __global__ void __launch_bounds__(THREADS) stage_once_kernel(const uint32_t* __r
     bulk_wait_read<0>();
 }
 
+
+// ---- C2: like C, but the lane 0 of every warp issues a share of the bulk stores (is one issuing thread a bottleneck?)
+__global__ void __launch_bounds__(THREADS) stage_once_mw_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint64_t n_groups,
+                                                                uint32_t repeat) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t* buf = reinterpret_cast<uint32_t*>(smem_raw);  // [2][SEG_ENTRIES]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * SEG_ENTRIES * 4);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+    }
+    __syncthreads();
+    uint32_t phase[2] = {0, 0};
+    int st = 0;
+    for (uint64_t gidx = blockIdx.x; gidx < n_groups; gidx += gridDim.x) {
+        uint32_t* b = buf + (size_t)st * SEG_ENTRIES;
+        if (lane == 0) bulk_wait_read<1>();  // this warp's stores out of this stage (two groups ago) have read shared memory
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bars[st], SEG_ENTRIES * 4);
+            bulk_g2s(b, src + (uint64_t)cell_of_segment(gidx) * SEG_ENTRIES, SEG_ENTRIES * 4, &bars[st]);
+        }
+        mbar_wait(&bars[st], phase[st]);
+        phase[st] ^= 1;
+        if (lane == 0) {
+            for (uint32_t r = w; r < repeat; r += WARPS) bulk_s2g(dst + (gidx * repeat + r) * SEG_ENTRIES, b, SEG_ENTRIES * 4);
+            bulk_commit();
+        }
+        st ^= 1;
+    }
+    if (lane == 0) bulk_wait_read<0>();
+}
+
+// ---- E: stage once (bulk load), then the THREADS store the staged segment: LDS.128 -> STG.128 streaming stores, no L2 reads
+__global__ void __launch_bounds__(THREADS) stage_once_stg_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint64_t n_groups,
+                                                                 uint32_t repeat) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t* buf = reinterpret_cast<uint32_t*>(smem_raw);  // [2][SEG_ENTRIES]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * SEG_ENTRIES * 4);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+    }
+    __syncthreads();
+    uint32_t phase[2] = {0, 0};
+    int st = 0;
+    uint64_t gidx = blockIdx.x;
+    if (threadIdx.x == 0 && gidx < n_groups) {
+        mbar_expect_tx(&bars[0], SEG_ENTRIES * 4);
+        bulk_g2s(buf, src + (uint64_t)cell_of_segment(gidx) * SEG_ENTRIES, SEG_ENTRIES * 4, &bars[0]);
+    }
+    for (; gidx < n_groups; gidx += gridDim.x) {
+        const uint64_t nxt = gidx + gridDim.x;
+        __syncthreads();  // everybody is done reading the other stage
+        if (threadIdx.x == 0 && nxt < n_groups) {
+            mbar_expect_tx(&bars[st ^ 1], SEG_ENTRIES * 4);
+            bulk_g2s(buf + (size_t)(st ^ 1) * SEG_ENTRIES, src + (uint64_t)cell_of_segment(nxt) * SEG_ENTRIES, SEG_ENTRIES * 4, &bars[st ^ 1]);
+        }
+        mbar_wait(&bars[st], phase[st]);
+        phase[st] ^= 1;
+        const uint4* s4 = reinterpret_cast<const uint4*>(buf + (size_t)st * SEG_ENTRIES);
+        for (uint32_t r = w; r < repeat; r += WARPS) {
+            uint4* d4 = reinterpret_cast<uint4*>(dst + (gidx * repeat + r) * SEG_ENTRIES);
+#pragma unroll 8
+            for (uint32_t i = lane; i < SEG_ENTRIES / 4; i += 32) __stcs(d4 + i, s4[i]);
+        }
+        st ^= 1;
+    }
+}
+
 // ---- D: write-only
 __global__ void __launch_bounds__(THREADS, 4) fill_kernel(uint32_t* __restrict__ dst, uint64_t n_tiles) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -225,6 +297,25 @@ int main() {
         const uint64_t groups = n_segs / repeat;
         ms = best_ms([&] { stage_once_kernel<<<sms * 6, THREADS, smem_c>>>(src, dst, groups, repeat); });
         printf(", \"stage_once_r%u_ms\": %.4f, \"stage_once_r%u_write_gbs\": %.0f", repeat, ms, repeat, groups * repeat * SEG_ENTRIES * 4.0 / 1e9 / ms * 1e3);
+    }
+
+    for (uint32_t repeat : {16u, 64u}) {
+        const uint64_t groups = n_segs / repeat;
+        for (int bps : {1, 2, 4}) {
+            ms = best_ms([&] { stage_once_kernel<<<sms * bps, THREADS, smem_c>>>(src, dst, groups, repeat); });
+            printf(", \"stage_once_r%u_g%d_ms\": %.4f", repeat, bps, ms);
+        }
+    }
+    CK(cudaFuncSetAttribute(stage_once_mw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+    CK(cudaFuncSetAttribute(stage_once_stg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+    for (uint32_t repeat : {8u, 16u, 64u}) {
+        const uint64_t groups = n_segs / repeat;
+        for (int bps : {1, 2, 4}) {
+            ms = best_ms([&] { stage_once_mw_kernel<<<sms * bps, THREADS, smem_c>>>(src, dst, groups, repeat); });
+            printf(", \"stage_once_mw_r%u_g%d_ms\": %.4f", repeat, bps, ms);
+            ms = best_ms([&] { stage_once_stg_kernel<<<sms * bps, THREADS, smem_c>>>(src, dst, groups, repeat); });
+            printf(", \"stage_once_stg_r%u_g%d_ms\": %.4f", repeat, bps, ms);
+        }
     }
     ms = best_ms([&] { CK(cudaMemcpyAsync(dst, dst + out_entries / 2, out_entries * 2, cudaMemcpyDeviceToDevice)); });
     printf(", \"memcpy_d2d_ms\": %.4f, \"memcpy_d2d_copy_gbs\": %.0f}\n", ms, out_entries * 2 * 2.0 / 1e9 / ms * 1e3);
