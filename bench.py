@@ -62,7 +62,7 @@ def world_config(args):
     if args.entities or args.subscribers:
         wc = synth.scaled(wc, args.entities or wc.n_entities, args.subscribers or wc.n_subscribers)
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.scaling == "weak" and world > 1 and args.impl == "ours":
+    if args.scaling == "weak" and world > 1:
         import copy
 
         wc = copy.copy(wc)
@@ -71,6 +71,16 @@ def world_config(args):
         wc.n_entities *= world
         wc.n_subscribers *= world
     return wc
+
+
+def config_dict(wc, world, scaling):
+    """The workload description both arms print (identical dicts: the driver compares them)."""
+    return {"workload": wc.name, "entities": wc.n_entities, "subscribers": wc.n_subscribers, "radius": wc.radius,
+            "grid": "%dx%d" % (wc.cols, wc.rows), "parallelism": "xslab%d" % world if world > 1 else "single",
+            "scaling": scaling if world > 1 else "strong",
+            "tick": "build+query+interest-diff+emit-visible+fanout, positions change every step",
+            "l2": "inputs larger than L2 in effect: every step streams the expanded visible list (4 bytes x V, about 1.95 GB on the "
+                  "1M/100K workload) through the 126 MB L2, evicting the step's inputs; no explicit flush"}
 
 
 def oracle_grid(wc):
@@ -126,15 +136,23 @@ def run_reference(args):
         orc.baseline_run(g, s["x"], s["z"], s["cx"], s["cz"], s["r"], 0, q_per_step, cores, True)
     dt = time.perf_counter() - t0
     val = q_per_step * args.steps / dt
+    # round 1's arm rebuilt the cell lists on ONE thread (Amdahl-bound): printed once for comparison
+    t0 = time.perf_counter()
+    for i in range(3):
+        s = snaps[i % 2]
+        orc.baseline_run(g, s["x"], s["z"], s["cx"], s["cz"], s["r"], 0, q_per_step, cores, 2)
+    serial = {"value": q_per_step * 3 / (time.perf_counter() - t0), "note": "same run with the round-1 single-threaded build"}
     sample = "%d of %d subscribers per step (full build of %d entities every step), %d steps" % (q_per_step, S, wc.n_entities, args.steps)
     out = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": args.scaling if int(os.environ.get("WORLD_SIZE", "1")) > 1 else "strong",
         "vs_baseline": None, "dtype": "f64+u32", "data": "synthetic",
-        "config": {"workload": wc.name, "entities": wc.n_entities, "subscribers": wc.n_subscribers, "radius": wc.radius,
-                   "grid": "%dx%d" % (wc.cols, wc.rows)},
+        "config": config_dict(wc, int(os.environ.get("WORLD_SIZE", "1")), args.scaling),
         "cpu_baseline": {"value": val, "unit": "queries/s", "cores": cores, "kind": "port",
-                         "sample": sample + "; C++ restatement of channeld's Go path (no Go toolchain in the image)"},
+                         "sample": sample + "; C++ restatement of channeld's Go path (no Go toolchain in the image), persistent thread "
+                                            "pool, per-cell entity lists rebuilt in parallel every step",
+                         "serial_build_variant": serial},
         "e2e": {"value": val, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -234,7 +252,15 @@ def run_ours(args):
                       max_ring_entries=wc.cells * args.ring_len + 1024, max_due=int(max(S, 1) * 8 + 4096))
     e.set_stream(stream.cuda_stream)
     if world > 1:
-        e.set_slab(col_lo, col_hi, halo)
+        # the exchange lives behind the C ABI (chd_comm_init / chd_tick_sharded: NCCL inside libchd_b200.so); torch.distributed
+        # only carries the 128-byte bootstrap id and the timing reductions
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(engine.Engine.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        e.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world, halo, border_cap)
+        info = e.comm_info()
+        assert (info["col_lo"], info["col_hi"]) == (col_lo, col_hi), (info, col_lo, col_hi)
         e.set_entity_ids(gid)
     e.set_subscribers(conn if S else np.zeros(0, np.uint32))
     sub_idx = np.arange(S, dtype=np.uint32)
@@ -276,10 +302,6 @@ def run_ours(args):
         rings_host.append(hh)
         rings_dev.append({k: (v.to(dev) if k != "n" else v) for k, v in hh.items()})
 
-    if world > 1:
-        rec_local = torch.full((border_cap * 2,), -1, dtype=torch.int32, device=dev)
-        rec_all = torch.empty((border_cap * 2 * world,), dtype=torch.int32, device=dev)
-
     keep = []
 
     def batch_of(src):
@@ -310,13 +332,10 @@ def run_ours(args):
         t_ns = (i + 1) * TICK_NS
         ck(L.chd_set_rings(e.h, capi.ptr(rg["off"]), rg["n"], capi.ptr(rg["arr"]), capi.ptr(rg["snd"]), capi.ptr(rg["idx"]), capi.ptr(rg["cmi"])))
         if world > 1:
-            # interest + fan-out do not need positions: start them on the engine's second stream, then exchange borders
-            ck(L.chd_begin_interest(e.h, C.byref(batches[i % 2]), t_ns, 1))
+            # one library call: interest + fan-out start on the engine's second stream, border records are selected, ONE
+            # ncclAllGather over NVLink, halo import, build + emit, join (chd_tick_sharded)
             ck(L.chd_set_entities(e.h, capi.ptr(d["x"]), capi.ptr(d["z"]), n_own))
-            e.export_border(rec_local, border_cap, want_count=False)  # also pads the buffer
-            dist.all_gather_into_tensor(rec_all, rec_local)
-            e.import_halo(rec_all, border_cap * world, rank * border_cap, border_cap)
-            ck(L.chd_tick(e.h, None, t_ns, capi.TICK_ALL, None))
+            ck(L.chd_tick_sharded(e.h, C.byref(batches[i % 2]), t_ns, capi.TICK_ALL, None))
         else:
             ck(L.chd_set_entities(e.h, capi.ptr(d["x"]), capi.ptr(d["z"]), n_own))
             ck(L.chd_tick(e.h, C.byref(batches[i % 2]), t_ns, capi.TICK_ALL, None))
@@ -330,24 +349,38 @@ def run_ours(args):
         gate = None
         step(0, dev_in, batches_dev, rings_dev)
         s0 = e.summary()
-        if world == 1 and not args.no_gate:
+        if not args.no_gate:
+            # every rank checks a 1 % sample of ITS subscribers against the oracle run over the FULL snapshot: (cell, dist) pairs
+            # bit-identical, visible lists identical as sets of global entity ids (per subscriber; within a cell the order of
+            # halo entities depends on the exchange, the canonical order is defined on one GPU only)
             from tests import _oracle
 
             orc = _oracle.load()
-            m = max(1, S // 100)
-            sel = np.linspace(0, S - 1, m).astype(np.int64)
+            m = max(1, S // 100) if S else 0
+            sel = np.linspace(0, S - 1, m).astype(np.int64) if S else np.zeros(0, np.int64)
             a = snaps[0]
-            want = orc.sphere_tick(oracle_grid(wc), a["x"], a["z"], a["cx"][sel], a["cz"][sel], a["r"][sel])
+            gsel = sub_mine[sel]
+            want = orc.sphere_tick(oracle_grid(wc), a["x"], a["z"], a["cx"][gsel], a["cz"][gsel], a["r"][gsel])
             pairs = e.get_pairs(s0.n_pairs)
-            ok = True
+            bad = 0
             for k, j in enumerate(sel):
                 sl = slice(pairs["off"][j], pairs["off"][j + 1])
-                ok &= np.array_equal(pairs["channel"][sl], want["pair_cell"][want["pair_off"][k]:want["pair_off"][k + 1]])
+                ok = np.array_equal(pairs["channel"][sl], want["pair_cell"][want["pair_off"][k]:want["pair_off"][k + 1]])
                 ok &= np.array_equal(pairs["dist"][sl], want["pair_dist"][want["pair_off"][k]:want["pair_off"][k + 1]])
-                ok &= np.array_equal(e.get_visible_slot(int(j)), want["vis_entity"][want["vis_off"][k]:want["vis_off"][k + 1]])
-            if not ok:
-                raise SystemExit("parity gate FAILED: GPU results differ from the oracle")
-            gate = "%d of %d subscribers: (cell,dist) pairs and visible lists bit-identical to the oracle" % (m, S)
+                got_vis = e.get_visible_slot(int(j))
+                want_vis = want["vis_entity"][want["vis_off"][k]:want["vis_off"][k + 1]]
+                ok &= np.array_equal(got_vis, want_vis) if world == 1 else np.array_equal(np.sort(got_vis), np.sort(want_vis))
+                bad += 0 if ok else 1
+            counts = torch.tensor([float(m), float(bad)], dtype=torch.float64, device=dev)
+            per_rank = [counts.clone() for _ in range(world)]
+            if world > 1:
+                dist.all_gather(per_rank, counts)
+            per_rank = [[int(v[0]), int(v[1])] for v in per_rank]
+            if sum(v[1] for v in per_rank):
+                raise SystemExit("parity gate FAILED: GPU results differ from the oracle (checked, mismatches per rank: %r)" % per_rank)
+            gate = {"checked_per_rank": [v[0] for v in per_rank], "mismatches": 0,
+                    "what": "(cell,dist) pairs bit-identical and visible lists identical (exact order on 1 GPU, as sets of global ids "
+                            "per subscriber on N GPUs) to the oracle run over the full snapshot"}
 
         # ---- value: device-resident inputs, device time
         for i in range(1, args.warmup + 1):
@@ -435,6 +468,11 @@ def run_ours(args):
         rb.handover_entity, rb.handover_src, rb.handover_dst, rb.handover_cap = (*[capi.ptr(t) for t in r_ho], max_ent)
         rb.query_status, rb.status_cap = capi.ptr(r_status), S
         rb.vis_off = capi.ptr(r_voff)
+        # the cell CSR makes the host result LOSSLESS: visible(s) = concatenation over the subscriber's pairs (ascending channel
+        # id) of sorted_entity[cell_start[c] : cell_start[c + 1]] — the expanded list itself (1.95 GB) stays in HBM
+        r_cs, _ = pinned((wc.cells + 1,), torch.int32)
+        r_se, _ = pinned((max_ent,), torch.int32)
+        rb.cell_start, rb.sorted_entity, rb.entity_cap = capi.ptr(r_cs), capi.ptr(r_se), max_ent
         r_vis_keep = []
 
         phase_acc = {}
@@ -456,18 +494,19 @@ def run_ours(args):
             tp0 = time.perf_counter()
             if pipelined:
                 ck(L.chd_adopt_prefetched(e.h))  # rings + queries + positions of this step went up during the previous one
-                ck(L.chd_begin_interest(e.h, None, t_ns, 1))
+                if world == 1:
+                    ck(L.chd_begin_interest(e.h, None, t_ns, 1))  # (chd_tick_sharded starts the adopted batch itself)
             else:
                 ck(L.chd_set_rings(e.h, capi.ptr(rg["off"]), rg["n"], capi.ptr(rg["arr"]), capi.ptr(rg["snd"]), capi.ptr(rg["idx"]), capi.ptr(rg["cmi"])))
                 # queries + rings go up first and the interest / fan-out stages start on the second stream while the
                 # (much larger) position upload is still in flight
                 ck(L.chd_begin_interest(e.h, C.byref(batches_host[i % 2]), t_ns, 1))
                 ck(L.chd_set_entities(e.h, capi.ptr(d["x"]), capi.ptr(d["z"]), n_own))
+            tick_flags = capi.TICK_ALL | (capi.TICK_EARLY_RESULTS if early else 0)
             if world > 1:
-                e.export_border(rec_local, border_cap, want_count=False)  # also pads the buffer
-                dist.all_gather_into_tensor(rec_all, rec_local)
-                e.import_halo(rec_all, border_cap * world, rank * border_cap, border_cap)
-            ck(L.chd_tick(e.h, None, t_ns, capi.TICK_ALL | (capi.TICK_EARLY_RESULTS if early else 0), None))
+                ck(L.chd_tick_sharded(e.h, None, t_ns, tick_flags, None))
+            else:
+                ck(L.chd_tick(e.h, None, t_ns, tick_flags, None))
             tp1 = time.perf_counter()
             if pipelined:  # the next step's inputs go up while this tick's kernels run
                 prefetch_inputs(i + 1)
@@ -483,7 +522,8 @@ def run_ours(args):
             phase_acc["n"] = phase_acc.get("n", 0) + 1
             h2d = 16 * n_own + 24 * S + (wc.cells + 1) * 4 + rg["n"] * 20 + wc.cells * 8
             d2h = (C.sizeof(capi.TickSummary) + (S + 1) * 4 + 12 * int(summ.n_pairs) + 8 * (int(summ.n_sub_new) + int(summ.n_unsub))
-                   + 48 * int(summ.n_due) + 12 * int(summ.n_handover) + 4 * S + (S + 1) * 8 + (4 * int(summ.n_visible) if expanded else 0))
+                   + 48 * int(summ.n_due) + 12 * int(summ.n_handover) + 4 * S + (S + 1) * 8 + (wc.cells + 1) * 4 + 4 * int(summ.n_entities_in_world)
+                   + (4 * int(summ.n_visible) if expanded else 0))
             return h2d, d2h
 
         base = args.warmup + 1 + args.steps
@@ -553,13 +593,20 @@ def run_ours(args):
             peak_src = "fallback 6.65 TB/s (B200_PROFILING.md)"
         ms_step = ms / args.steps
         value = S_total * args.steps / (ms * 1e-3)
-        # roofline of the dominant kernel (emit_visible): algorithmic bytes = 8 per visible entry (read 4 + write 4)
+        # Roofline of the dominant kernel (emit_visible), DRAM basis.  Algorithmic DRAM bytes per launch = 4 V (every visible
+        # entry written once) + 4 N (the cell CSR payload read once; its re-reads are L2 hits by design: 16 MB of phase copies
+        # against a 126 MB L2).  SURVEY §8d's 8 V counts the L2-side re-reads as well: reported as l2_side_gbs, not as the
+        # fraction.  `traffic` = dram__bytes_read.sum + dram__bytes_write.sum of one launch from an `ncu --set full` pass over
+        # this tree (profiles/r2_emit_traffic.json names the commit it was taken on), null if that file is absent.
         v_rank = float(sm.n_visible)
+        n_sorted = float(sm.n_entities_in_world)
         ek_ms = stage["emit_kernel"]
-        achieved = (8.0 * v_rank / (ek_ms * 1e-3)) / 1e9 if ek_ms > 0 else 0.0
-        traffic = None
+        dram_bytes = 4.0 * v_rank + 4.0 * n_sorted
+        achieved = (dram_bytes / (ek_ms * 1e-3)) / 1e9 if ek_ms > 0 else 0.0
+        traffic, traffic_src = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "emit_traffic.json")))["dram_bytes_per_launch"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_emit_traffic.json")))
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj.get("source")
         except Exception:
             pass
         out = {
@@ -567,10 +614,7 @@ def run_ours(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling if world > 1 else "strong", "vs_baseline": None,
             "dtype": "f64+u32",
             "data": "synthetic",
-            "config": {"workload": wc.name, "entities": N_total, "subscribers": S_total, "radius": wc.radius,
-                       "grid": "%dx%d" % (wc.cols, wc.rows), "parallelism": "xslab%d" % world if world > 1 else "single",
-                       "tick": "build+query+interest-diff+emit-visible+fanout, positions change every step",
-                       "l2": "each step streams %.2f GB of output through the 126 MB L2, evicting the inputs; no explicit flush" % (4 * tot_vis / world / 1e9)},
+            "config": config_dict(wc, world, args.scaling),
             "clocks": clocks,
             "e2e": {"value": S_total * n_e2e / e2e_dt, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_dt / n_e2e * 1e3,
@@ -581,15 +625,20 @@ def run_ours(args):
                     "serial": {"value": S_total * n_e2e / e2e_serial_dt, "ms_per_step": e2e_serial_dt / n_e2e * 1e3,
                                "note": "no overlap between steps: upload -> tick -> read-back, one after the other (per-tick latency)"},
                     "result": "chd_fetch_results: summary + (cell,dist,interval) pairs + sub/unsub lists + fan-out due list + handover "
-                              "list + query statuses + visible offsets; the expanded list stays in HBM for GPU-side consumers (see e2e_expanded)"},
+                              "list + query statuses + visible offsets + the cell CSR (cell_start, sorted_entity): LOSSLESS — every "
+                              "visible list is the concatenation of its pairs' cell lists; the 4-bytes-per-entry expansion itself stays in "
+                              "HBM for GPU-side consumers (e2e_expanded copies it as well)"},
             "e2e_expanded": e2e_exp,
             "gpu_launches": int(launches),
+            "collectives": {"nccl_all_gathers_issued_by_the_library_rank0": e.collective_count(), "where": "chd_tick_sharded (libchd_b200.so)"} if world > 1 else None,
             "roofline": {"bound": "hbm", "kernel": "emit_visible_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": 8.0 * v_rank, "kernel_ms": ek_ms,
-                         "dram_write_gbs": (4.0 * v_rank / (ek_ms * 1e-3)) / 1e9 if ek_ms > 0 else None, "write_only_peak_gbs_this_run": wp,
-                         "note": "reads hit the L2-resident cell CSR, so DRAM traffic is the 4 B/entry write stream: compare dram_write_gbs "
-                                 "with write_only_peak_gbs_this_run (torch fill_ of the same size, best of 6)"},
+                         "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "algorithmic_dram_bytes_per_launch": dram_bytes, "algorithmic_dram_bytes": "4*V + 4*N (writes + one read of the CSR)",
+                         "kernel_ms": ek_ms, "l2_side_gbs": (8.0 * v_rank / (ek_ms * 1e-3)) / 1e9 if ek_ms > 0 else None,
+                         "write_only_peak_gbs_this_run": wp,
+                         "frac_of_write_only_peak": (achieved / wp) if wp else None,
+                         "note": "DRAM basis; the kernel is a write stream on the DRAM side, so the tighter ceiling is the write-only "
+                                 "one measured in this run (torch fill_ of the same size, best of 6)"},
             "stage_ms": stage,
             "last_tick_timeline_ms": timeline,
             "per_tick": {"pairs": tot_pairs, "visible": tot_vis, "fanout_decisions": tot_due, "handover": int(sm.n_handover),
@@ -625,10 +674,19 @@ def run_ours(args):
                 single = {"value": qn * reps1 / dt1, "cores": 1, "sample": "%d ticks x %d subscribers, build included" % (reps1, qn)}
             except Exception as ex_:  # noqa: BLE001  (never lose the result line over the extra baseline)
                 print("single-thread baseline failed: %r" % (ex_,), file=sys.stderr)
+            serial = None
+            try:  # round 1's arm rebuilt the cell lists on ONE thread: printed for comparison
+                t0 = time.perf_counter()
+                for k in range(3):
+                    s_ = snaps[k % 2]
+                    orc.baseline_run(g, s_["x"], s_["z"], s_["cx"], s_["cz"], s_["r"], 0, qn, cores, 2)
+                serial = {"value": qn * 3 / (time.perf_counter() - t0), "note": "same threads, round-1 single-threaded build"}
+            except Exception as ex_:  # noqa: BLE001
+                print("serial-build baseline failed: %r" % (ex_,), file=sys.stderr)
             out["cpu_baseline"] = {"value": qn * reps / dtc, "unit": "queries/s", "cores": cores, "kind": "port",
-                                   "sample": "%d ticks x %d of %d subscribers (build of %d entities included each tick); C++ restatement of "
-                                             "channeld's Go path, all host threads" % (reps, qn, S_total, N_total),
-                                   "single_thread": single}
+                                   "sample": "%d ticks x %d of %d subscribers (parallel build of %d entities included each tick); C++ "
+                                             "restatement of channeld's Go path, persistent pool over all host threads" % (reps, qn, S_total, N_total),
+                                   "single_thread": single, "serial_build_variant": serial}
         _emit_line(_OUT_FD, json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -18,6 +18,7 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr",
     "-Xcompiler", "-fPIC,-O2,-Wall",
     "-shared", "-cudart", "shared",
+    "-ldl",                   # NCCL is dlopen'ed on first multi-GPU use (chd_shard.cu): no link-time dependency on it
 ]
 
 
@@ -39,17 +40,19 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps())
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """extra_flags / out: experiment builds (tools/), e.g. -DCHD_EMIT_ROWS=8 into another file; the product is LIB."""
+    if out is None and not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-I", os.path.join(ROOT, "include"), "-o", LIB] + sources()
+    cmd = ([nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-I", os.path.join(ROOT, "include"), "-o", out or LIB]
+           + sources())
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
         sys.stderr.write(r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

@@ -118,6 +118,7 @@ SYMBOLS = [
     "chd_set_slab", "chd_set_entity_ids", "chd_export_border", "chd_import_halo", "chd_due_classes", "chd_set_subscriber_types", "chd_adjacent_broadcast", "chd_get_adjacent_channels",
     "chd_get_regions", "chd_damping_interval_ms", "chd_launch_count", "chd_profile_enable", "chd_profile_get", "chd_profile_timeline", "chd_enable_graphs",
     "chd_graph_launch_count",
+    "chd_add_subscribers", "chd_remove_subscribers", "chd_set_payload_bytes", "chd_assemble_payloads", "chd_frame_packets", "chd_comm_unique_id", "chd_comm_init", "chd_comm_info", "chd_comm_destroy", "chd_tick_sharded", "chd_collective_count", "chd_migrate_out", "chd_migrate_in", "chd_get_rehome",
 ]
 STAGE_BUILD, STAGE_INTEREST, STAGE_EMIT, STAGE_EMIT_KERNEL, STAGE_FANOUT, STAGE_TICK = range(6)
 
@@ -130,6 +131,8 @@ def lib():
     if _lib is not None:
         return _lib
     path = _build.build()
+    if os.environ.get("CHD_EXPERIMENT_LIB"):  # tools/ only: an experiment build of the same sources (different tile constants)
+        path = os.environ["CHD_EXPERIMENT_LIB"]
     L = C.CDLL(path)
     vp = C.c_void_p
     L.chd_abi_version.restype = C.c_uint32
@@ -241,6 +244,34 @@ def lib():
     L.chd_profile_timeline.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.chd_profile_get.restype = C.c_int
     L.chd_profile_get.argtypes = [vp, C.c_int, C.POINTER(C.c_double), u64p]
+    L.chd_set_payload_bytes.restype = C.c_int
+    L.chd_set_payload_bytes.argtypes = [vp, vp, C.c_uint32, vp, vp, vp, C.c_char_p, C.c_uint32]
+    L.chd_assemble_payloads.restype = C.c_int
+    L.chd_assemble_payloads.argtypes = [vp, u32p, vp, C.c_uint32, vp, C.c_uint64, u64p]
+    L.chd_frame_packets.restype = C.c_int
+    L.chd_frame_packets.argtypes = [vp, vp, vp, vp, vp, vp, C.c_uint64, u64p, u32p]
+    L.chd_add_subscribers.restype = C.c_int
+    L.chd_add_subscribers.argtypes = [vp, vp, vp, C.c_uint32]
+    L.chd_remove_subscribers.restype = C.c_int
+    L.chd_remove_subscribers.argtypes = [vp, vp, C.c_uint32]
+    L.chd_comm_unique_id.restype = C.c_int
+    L.chd_comm_unique_id.argtypes = [vp]
+    L.chd_comm_init.restype = C.c_int
+    L.chd_comm_init.argtypes = [vp, vp, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.chd_migrate_out.restype = C.c_int
+    L.chd_migrate_out.argtypes = [vp, vp, C.c_uint32]
+    L.chd_migrate_in.restype = C.c_int
+    L.chd_migrate_in.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32]
+    L.chd_get_rehome.restype = C.c_int
+    L.chd_get_rehome.argtypes = [vp, vp, vp, C.c_uint32, u32p]
+    L.chd_comm_info.restype = C.c_int
+    L.chd_comm_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), u32p, u32p, u32p, C.POINTER(C.c_int)]
+    L.chd_comm_destroy.restype = C.c_int
+    L.chd_comm_destroy.argtypes = [vp]
+    L.chd_tick_sharded.restype = C.c_int
+    L.chd_tick_sharded.argtypes = [vp, C.POINTER(QueryBatch), C.c_int64, C.c_uint32, C.POINTER(TickSummary)]
+    L.chd_collective_count.restype = C.c_uint64
+    L.chd_collective_count.argtypes = [vp]
     _lib = L
     return L
 

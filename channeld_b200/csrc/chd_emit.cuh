@@ -3,12 +3,11 @@
 // HBM term of a tick (8V bytes algorithmic: read 4V + write 4V; V ~ 4.9e8 on the benchmark config).
 //
 // Decomposition: the OUTPUT array is cut into fixed tiles of EMIT_TILE entries (load-balanced regardless of
-// how entities are distributed over cells).  A partition pass records the first pair of each tile; a
-// persistent grid (multiple of the SM count) then walks tiles round-robin, one tile per WARP.  Every lane moves
-// 16-byte chunks: stores are fully coalesced and 128 B-aligned (tile bases are multiples of 1024 entries); loads are co-aligned
-// 16-byte reads out of the L2-resident phase copies of the cell CSR (4 x 4 B x N: 16 MB at 1 M entities, far
-// below the 126 MB L2).  v1 of this kernel moved 4 bytes per thread-iteration and was instruction-issue bound
-// (ncu: 73 % issue-active, 30 % DRAM): see profiles/r1_v1_emit_ncu_details.txt.
+// how entities are distributed over cells).  A partition pass records the first pair of each tile; one CTA copies one
+// tile.  Every thread moves 16-byte chunks: stores are fully coalesced; loads are co-aligned 16-byte reads out of the
+// L2-resident phase copies of the cell CSR (4 x 4 B x N: 16 MB at 1 M entities, far below the 126 MB L2).
+// History (profiles/README.md): v1 4-byte moves, issue-bound, 0.75 ms -> v2/v3 phase-matched 16-byte moves on a persistent
+// grid of warp tiles, 0.355 ms -> this shape (round 2).
 #pragma once
 #include "chd_types.cuh"
 
@@ -25,11 +24,12 @@ struct PairVcountIn {
     }
 };
 
-// first_pair[t] = the pair whose output interval [voff[p], voff[p+1]) contains entry t*EMIT_TILE;
-// also vis_off[s] = voff[pair_off[s]] and the V / overflow bookkeeping (one launch instead of two)
+// tile descriptors + first_pair[t] (the pair whose output interval [voff[p], voff[p+1]) contains entry t*EMIT_TILE);
+// also vis_off[s] = voff[pair_off[s]] and the V / overflow bookkeeping (one launch)
 __global__ void __launch_bounds__(256)
     emit_partition_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, const uint64_t* __restrict__ voff,
-                          uint32_t* __restrict__ first_pair, uint64_t max_tiles, uint32_t n_slots, const uint32_t* __restrict__ pair_off,
+                          const uint32_t* __restrict__ pair_cell, const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ first_pair,
+                          TileDesc* __restrict__ desc, uint64_t max_tiles, uint32_t n_slots, const uint32_t* __restrict__ pair_off,
                           uint64_t* __restrict__ vis_off, uint64_t vis_cap, Counters* __restrict__ ctr, unsigned long long* bump_epoch) {
     const uint64_t n = min((uint64_t)*n_pairs_ptr, pair_cap);
     // last kernel of the emit preparation: open the NEXT execution's scan epoch (the scan of this one has completed)
@@ -43,95 +43,151 @@ __global__ void __launch_bounds__(256)
             if (V > vis_cap) atomicOr(&ctr->overflow, (uint32_t)CHD_OVF_VISIBLE);
         }
     }
+    const uint64_t V = voff[n];
     for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < n; p += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t b = voff[p], e = voff[p + 1];
         if (e == b) continue;
-        for (uint64_t t = (b + EMIT_TILE - 1) / EMIT_TILE; t * EMIT_TILE < e && t < max_tiles; t++) first_pair[t] = (uint32_t)p;
+        const uint32_t cs = cell_start[pair_cell[p]];
+        for (uint64_t t = (b + EMIT_TILE - 1) / EMIT_TILE; t * EMIT_TILE < e && t < max_tiles; t++) {
+            const uint64_t base = t * EMIT_TILE;
+            const uint32_t tile_len = (uint32_t)min((uint64_t)EMIT_TILE, V - base);
+            TileDesc d;
+            d.p0 = (uint32_t)p;
+            d.src0 = cs + (uint32_t)(base - b);
+            const uint32_t end0 = (uint32_t)min((uint64_t)EMIT_TILE, e - base);
+            uint32_t end1 = end0;
+            d.src1 = 0;
+            if (end0 < tile_len) {  // the pair ends inside this tile: the second segment is the next non-empty pair
+                uint64_t q = p + 1;
+                while (q < n && voff[q + 1] == e) q++;
+                if (q < n) {
+                    d.src1 = cell_start[pair_cell[q]];
+                    end1 = (uint32_t)min((uint64_t)EMIT_TILE, voff[q + 1] - base);
+                }
+            }
+            d.ends = end0 | (end1 << 16) | (end1 < tile_len ? 0x80000000u : 0u);
+            desc[t] = d;
+            first_pair[t] = (uint32_t)p;
+        }
     }
 }
 
-// v3: every WARP owns whole tiles (no block barrier anywhere): the segment table of a tile lives in a warp-private
-// slice of shared memory guarded by __syncwarp.  Output stores are streaming (st.global.cs) so the 1.95 GB write
-// stream does not evict the L2-resident phase copies the loads come from.
-__global__ void __launch_bounds__(EMIT_THREADS, 4)
-    emit_visible_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, const uint64_t* __restrict__ voff,
-                        const uint32_t* __restrict__ pair_cell, const uint32_t* __restrict__ cell_start,
-                        const uint32_t* __restrict__ sorted4, uint32_t stride, const uint32_t* __restrict__ first_pair,
-                        uint32_t* __restrict__ vis_entity, uint64_t vis_cap) {
-    __shared__ uint32_t s_end_all[EMIT_WARPS][EMIT_SMEM_PAIRS];  // end of pair (p0+k) relative to the tile base, clamped to EMIT_TILE
-    __shared__ uint32_t s_src_all[EMIT_WARPS][EMIT_SMEM_PAIRS];  // source index of the pair's entry that lands on max(voff[p], tile base)
+// General path of one tile: more than two pairs' lists intersect it (cells smaller than a tile).  Kept out of line so that its
+// registers do not count against the occupancy of the common two-segment path.
+__device__ __noinline__ void emit_tile_general(uint64_t t, uint64_t n_tiles, uint64_t V, uint32_t p0, const uint32_t* __restrict__ n_pairs_ptr,
+                                               uint64_t pair_cap, const uint64_t* __restrict__ voff, const uint32_t* __restrict__ pair_cell,
+                                               const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ sorted4, uint32_t stride,
+                                               const uint32_t* __restrict__ first_pair, uint32_t* __restrict__ vis_entity, uint32_t* s_end,
+                                               uint32_t* s_src) {
+    const uint32_t tid = threadIdx.x;
+    const uint64_t base = t * EMIT_TILE;
+    const uint32_t tile_len = (uint32_t)min((uint64_t)EMIT_TILE, V - base);
+    uint32_t* __restrict__ out = vis_entity + base;
     const uint64_t np = min((uint64_t)*n_pairs_ptr, pair_cap);
-    if (np == 0) return;
-    const uint64_t V = voff[np];
-    if (V > vis_cap) return;
+    const uint32_t p1 = (t + 1 < n_tiles) ? first_pair[t + 1] : (uint32_t)(np - 1);
+    const uint32_t cnt = p1 - p0 + 1;
+    if (cnt <= EMIT_SMEM_PAIRS) {
+        __syncthreads();  // the previous tile's readers are done (only when the loop runs more than once)
+        if (tid < cnt) {
+            const uint64_t b = voff[p0 + tid], e = voff[p0 + tid + 1];
+            const uint32_t c = pair_cell[p0 + tid];
+            s_end[tid] = (uint32_t)min((uint64_t)EMIT_TILE, e > base ? e - base : 0);
+            s_src[tid] = cell_start[c] + (uint32_t)(b < base ? base - b : 0);
+        }
+        __syncthreads();
+        for (int r = 0; r < EMIT_ROWS; r++) {
+            const uint32_t o = (r * EMIT_THREADS + tid) * 4;  // first entry of this 16-byte chunk
+            if (o >= tile_len) continue;
+            uint32_t lo = 0, hi = cnt - 1;  // first k with s_end[k] > o (exists: s_end[cnt-1] >= tile_len > o)
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (s_end[mid] > o) hi = mid; else lo = mid + 1;
+            }
+            const uint32_t k = lo;
+            const uint32_t beg = k == 0 ? 0u : s_end[k - 1];
+            const uint32_t sidx = s_src[k] + (o - beg);
+            if (o + 4 <= s_end[k]) {
+                const uint32_t ph = (0u - sidx) & 3u;  // whole chunk inside one segment: phase copy (-sidx) & 3
+                __stcs(reinterpret_cast<uint4*>(out + o), __ldg(reinterpret_cast<const uint4*>(sorted4 + ph * stride + ph + sidx)));
+            } else {
+                uint32_t kk = k;  // the chunk straddles a segment boundary (or the end of the list): entry by entry
+                for (uint32_t j = 0; j < 4 && o + j < tile_len; j++) {
+                    while (s_end[kk] <= o + j) kk++;
+                    const uint32_t bb = kk == 0 ? 0u : s_end[kk - 1];
+                    out[o + j] = __ldg(sorted4 + s_src[kk] + (o + j - bb));
+                }
+            }
+        }
+    } else {
+        // more than EMIT_SMEM_PAIRS pairs inside one tile (tiny / empty cells): per-entry binary search
+        for (uint32_t o = tid; o < tile_len; o += EMIT_THREADS) {
+            const uint64_t go = base + o;
+            uint64_t lo = p0, hi = p1;  // last p in [p0,p1] with voff[p] <= go
+            while (lo < hi) {
+                const uint64_t mid = (lo + hi + 1) >> 1;
+                if (voff[mid] <= go) lo = mid; else hi = mid - 1;
+            }
+            const uint32_t c = pair_cell[lo];
+            vis_entity[go] = sorted4[cell_start[c] + (uint32_t)(go - voff[lo])];
+        }
+    }
+}
+
+// One CTA per 16 KB tile of the output (EMIT_TILE = 4096 entries: EMIT_ROWS rows of 256 x 16 bytes), dispatched by the
+// hardware block scheduler.  Measured on B200 (tools/write_probe.cu, profiles/r2_write_probe.json): the same streaming copy
+// out of an L2-resident pool runs at 6.96 TB/s of writes with one CTA per 16 KB chunk, against 6.2 TB/s with a persistent
+// grid that walks the chunks round-robin (the round-1 shape) and 7.48 TB/s for a pure fill; 4 rows per thread beat 1 (more
+// loads in flight), streaming stores (st.global.cs) beat write-back ones by 15 % (the write stream does not evict the
+// L2-resident sources).  The loop over tiles only runs more than once if the host under-estimated the tile count.
+// Segment table of the tile (the pairs whose lists intersect it) in shared memory; a thread finds its row's segment by
+// binary search; every move is a co-aligned LDG.128 -> STG.128 out of the phase copy whose 16-byte phase matches the
+// destination (a chunk that straddles a pair boundary goes entry by entry).
+__global__ void __launch_bounds__(EMIT_THREADS, CHD_EMIT_MIN_BLOCKS)
+    emit_visible_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, const unsigned long long* __restrict__ n_visible_ptr,
+                        const uint64_t* __restrict__ voff, const uint32_t* __restrict__ pair_cell, const uint32_t* __restrict__ cell_start,
+                        const uint32_t* __restrict__ sorted4, uint32_t stride, const uint32_t* __restrict__ first_pair,
+                        const TileDesc* __restrict__ desc, uint32_t* __restrict__ vis_entity, uint64_t vis_cap) {
+    __shared__ uint32_t s_end[EMIT_SMEM_PAIRS];  // end of pair (p0+k) relative to the tile base, clamped to EMIT_TILE
+    __shared__ uint32_t s_src[EMIT_SMEM_PAIRS];  // source index of the pair's entry that lands on max(voff[p], tile base)
+    // V was published by the partition pass: the first load of a CTA does not depend on any other
+    const uint64_t V = *n_visible_ptr;
+    if (V == 0 || V > vis_cap) return;
     const uint64_t n_tiles = (V + EMIT_TILE - 1) / EMIT_TILE;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint32_t* s_end = s_end_all[w];
-    uint32_t* s_src = s_src_all[w];
-    const uint64_t warp_id = (uint64_t)blockIdx.x * EMIT_WARPS + w, n_warps = (uint64_t)gridDim.x * EMIT_WARPS;
-    for (uint64_t t = warp_id; t < n_tiles; t += n_warps) {
+    const uint32_t tid = threadIdx.x;
+    for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const uint64_t base = t * EMIT_TILE;
-        const uint32_t p0 = first_pair[t];
-        const uint32_t p1 = (t + 1 < n_tiles) ? first_pair[t + 1] : (uint32_t)(np - 1);
-        const uint32_t cnt = p1 - p0 + 1;
         const uint32_t tile_len = (uint32_t)min((uint64_t)EMIT_TILE, V - base);
         uint32_t* __restrict__ out = vis_entity + base;
-        if (cnt <= EMIT_SMEM_PAIRS) {
-            __syncwarp();  // the previous tile's readers are done
-            for (uint32_t k = lane; k < cnt; k += 32) {
-                const uint64_t b = voff[p0 + k], e = voff[p0 + k + 1];
-                const uint32_t c = pair_cell[p0 + k];
-                s_end[k] = (uint32_t)min((uint64_t)EMIT_TILE, e > base ? e - base : 0);
-                s_src[k] = cell_start[c] + (uint32_t)(b < base ? base - b : 0);
-            }
-            __syncwarp();
-            uint32_t k = 0;  // segment cursor of this lane (its chunks ascend)
-            uint32_t src[EMIT_CHUNKS];  // element index into sorted4 (multiple of 4), or 0xFFFFFFFF
-            // phase 1: resolve every chunk's source (nullptr = handled element-wise / out of range)
+        const uint4 dw = __ldg(reinterpret_cast<const uint4*>(desc + t));  // one broadcast load: {src0, src1, ends, p0}
+        if (!(dw.z & 0x80000000u)) {
+            // simple tile: at most two segments, everything a thread needs is in the descriptor
+            const uint32_t end0 = dw.z & 0x7FFFu, end1 = (dw.z >> 16) & 0x7FFFu;
+            uint32_t src[EMIT_ROWS];
 #pragma unroll
-            for (int it = 0; it < EMIT_CHUNKS; it++) {
-                const uint32_t o = (it * 32 + lane) * 4;  // first entry of this 16-byte chunk
-                src[it] = 0xFFFFFFFFu;
+            for (int r = 0; r < EMIT_ROWS; r++) {
+                const uint32_t o = (r * EMIT_THREADS + tid) * 4;
+                src[r] = 0xFFFFFFFFu;
                 if (o < tile_len) {
-                    while (s_end[k] <= o) k++;  // terminates: s_end[cnt-1] >= tile_len > o
-                    const uint32_t beg = k == 0 ? 0u : s_end[k - 1];
-                    const uint32_t sidx = s_src[k] + (o - beg);
-                    if (o + 4 <= s_end[k]) {
-                        // whole chunk inside one segment: co-aligned 16-byte move out of phase copy (-sidx)&3
-                        const uint32_t ph = (0u - sidx) & 3u;
-                        src[it] = ph * stride + ph + sidx;
+                    if (o + 4 <= end0 || (o >= end0 && o + 4 <= end1)) {
+                        const uint32_t sidx = o < end0 ? dw.x + o : dw.y + (o - end0);
+                        const uint32_t ph = (0u - sidx) & 3u;  // phase copy whose 16-byte phase matches the destination
+                        src[r] = ph * stride + ph + sidx;
                     } else {
-                        // the chunk straddles a segment boundary (or the end of the list): entry by entry
-                        uint32_t kk = k;
-                        for (uint32_t j = 0; j < 4 && o + j < tile_len; j++) {
-                            while (s_end[kk] <= o + j) kk++;
-                            const uint32_t bb = kk == 0 ? 0u : s_end[kk - 1];
-                            out[o + j] = __ldg(sorted4 + s_src[kk] + (o + j - bb));
-                        }
+                        for (uint32_t j = 0; j < 4 && o + j < tile_len; j++)  // the chunk straddles the boundary / the end
+                            out[o + j] = __ldg(sorted4 + (o + j < end0 ? dw.x + o + j : dw.y + (o + j - end0)));
                     }
                 }
             }
-            // phase 2: all loads in flight, phase 3: streaming stores
-            uint4 v[EMIT_CHUNKS];
+            uint4 v[EMIT_ROWS];
 #pragma unroll
-            for (int it = 0; it < EMIT_CHUNKS; it++)
-                if (src[it] != 0xFFFFFFFFu) v[it] = __ldg(reinterpret_cast<const uint4*>(sorted4 + src[it]));
+            for (int r = 0; r < EMIT_ROWS; r++)
+                if (src[r] != 0xFFFFFFFFu) v[r] = __ldg(reinterpret_cast<const uint4*>(sorted4 + src[r]));
 #pragma unroll
-            for (int it = 0; it < EMIT_CHUNKS; it++)
-                if (src[it] != 0xFFFFFFFFu) __stcs(reinterpret_cast<uint4*>(out + (it * 32 + lane) * 4), v[it]);
-        } else {
-            // more than EMIT_SMEM_PAIRS pairs inside one tile (tiny / empty cells): per-entry binary search
-            for (uint32_t o = lane; o < tile_len; o += 32) {
-                const uint64_t go = base + o;
-                uint64_t lo = p0, hi = p1;  // last p in [p0,p1] with voff[p] <= go
-                while (lo < hi) {
-                    const uint64_t mid = (lo + hi + 1) >> 1;
-                    if (voff[mid] <= go) lo = mid; else hi = mid - 1;
-                }
-                const uint32_t c = pair_cell[lo];
-                vis_entity[go] = sorted4[cell_start[c] + (uint32_t)(go - voff[lo])];
-            }
+            for (int r = 0; r < EMIT_ROWS; r++)
+                if (src[r] != 0xFFFFFFFFu) __stcs(reinterpret_cast<uint4*>(out + (r * EMIT_THREADS + tid) * 4), v[r]);
+            continue;
         }
+        emit_tile_general(t, n_tiles, V, dw.w, n_pairs_ptr, pair_cap, voff, pair_cell, cell_start, sorted4, stride, first_pair, vis_entity, s_end, s_src);
     }
 }
 

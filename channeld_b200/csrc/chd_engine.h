@@ -103,6 +103,12 @@ struct chd_engine {
     // ---- subscribers / pairs
     uint32_t n_slots = 0;
     uint32_t* d_conn = nullptr;
+    // lifecycle: pending per-slot changes (SLOT_*), applied by the next interest update; source record of an immigrant;
+    // staging for the slot / connection-id lists of chd_add_subscribers / chd_remove_subscribers / chd_migrate_*
+    uint8_t* d_slot_ctl = nullptr;
+    uint32_t *d_slot_src = nullptr, *d_lc_slot = nullptr, *d_lc_aux = nullptr;
+    bool lifecycle_used = false;  // the interest kernels look at d_slot_ctl only once a lifecycle call has been made
+    MigView mig{nullptr, 0, 0, 0};  // gathered migration blobs of this tick (chd_shard.cu)
     PairBuf pairs[2];
     int cur = 0;
     // ---- query scratch
@@ -146,6 +152,7 @@ struct chd_engine {
     uint32_t *d_new_sub = nullptr, *d_new_ch = nullptr, *d_gone_sub = nullptr, *d_gone_ch = nullptr;
     // emit
     uint32_t *d_vcnt = nullptr, *d_first_pair = nullptr, *d_vis = nullptr;
+    TileDesc* d_tile_desc = nullptr;  // per-tile copy descriptors (chd_emit.cuh)
     uint32_t* d_pair_ch = nullptr;  // channel id of every current pair (written by interest_fill_kernel)
     // ---- window classes of the due list (chd_due_classes): keys written by the fan-out kernel, scratch allocated on first use
     DueKey* d_due_key = nullptr;
@@ -160,6 +167,20 @@ struct chd_engine {
     uint64_t bc_msg_cap = 0, bc_out_cap = 0;
     ScanSite site_bcast{};
     bool pair_ch_valid = false;
+    // ---- payload assembly + framing (chd_payload.cu): optional stage, buffers grown on demand
+    struct Payload {
+        uint64_t *d_entry_off = nullptr, *d_full_off = nullptr, *d_cls_off = nullptr, *d_conn_off = nullptr;
+        uint8_t *d_entry_bytes = nullptr, *d_full_bytes = nullptr, *d_url = nullptr, *d_blob = nullptr, *d_out = nullptr, *d_stage = nullptr, *d_comp = nullptr;
+        uint32_t *d_cls_len = nullptr, *d_fc_cnt = nullptr, *d_fc_off = nullptr, *d_fc_cursor = nullptr, *d_fc_idx = nullptr, *d_conn_cap = nullptr,
+                 *d_conn_len = nullptr, *d_conn_frames = nullptr, *d_ndrop = nullptr;
+        uint64_t cap_entry_off = 0, cap_entry_bytes = 0, cap_full_off = 0, cap_full_bytes = 0, cap_url = 0, cap_cls = 0, cap_cls_off = 0, cap_blob = 0,
+                 cap_fc = 0, cap_fc_off = 0, cap_fc_cur = 0, cap_fc_idx = 0, cap_conn_cap = 0, cap_conn_off = 0, cap_conn_len = 0, cap_conn_frames = 0,
+                 cap_comp = 0, cap_ndrop = 0, cap_out = 0, cap_stage = 0, cap_site_cls = 0, cap_site_fc = 0, cap_site_conn = 0;
+        ScanSite site_cls{}, site_fc{}, site_conn{};
+        uint32_t url_len = 0, msg_type = 8, n_entries = 0, n_classes = 0;
+        uint64_t blob_len = 0;
+        bool have_input = false, assembled = false;
+    } pl;
     // chd_fetch_results reads back on its own stream as soon as the aux chain (pairs, diff, due list) and the emit
     // preparation (visible offsets) are done, i.e. while the emit kernel is still streaming
     cudaStream_t dl_stream = nullptr, dl_stream_b = nullptr;  // phase A / phase B of the early read-back
@@ -172,6 +193,7 @@ struct chd_engine {
     cudaEvent_t wait_before_emit_kernel = nullptr;
     uint64_t *d_voff = nullptr, *d_vis_off = nullptr;
     uint64_t max_tiles = 0;
+    uint64_t vis_estimate = 0;  // n_visible of the last summary the host decoded (0 = none yet): sizes the emit grid
     // fanout
     uint32_t *d_ring_off = nullptr, *d_ring_sender = nullptr;
     int64_t* d_ring_arrival = nullptr;
@@ -188,6 +210,16 @@ struct chd_engine {
     // counters
     Counters* d_ctr = nullptr;
     Counters* h_ctr = nullptr;  // pinned
+    // multi-GPU exchange (chd_comm_init): NCCL communicator (opaque here), engine-owned record buffers
+    void* comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    uint32_t border_cap = 0;
+    uint32_t rec_per_rank = 0;        // border records per rank in the gathered buffer (0: plain contiguous records)
+    uint64_t rec_stride_words = 0;    // words one rank contributes to the all-gather (border records + migration blob)
+    uint32_t mig_subs = 0, mig_pairs = 0;  // migration blob capacities (0: no subscriber migration)
+    bool mig_packed = false;          // chd_migrate_out was called for the coming tick
+    uint32_t *d_rec_local = nullptr, *d_rec_all = nullptr;
+    uint64_t n_collectives = 0;
     // border export scratch
     uint32_t *d_bflag = nullptr, *d_boff = nullptr;
     uint32_t* h_u32 = nullptr;  // pinned scalar
@@ -255,7 +287,7 @@ static bool dalloc(chd_engine* e, T** p, uint64_t count) {
     return true;
 }
 
-enum { EP_BUILD = 0, EP_QUERY, EP_EMIT, EP_FANOUT, EP_BORDER, EP_BCAST, EP_CLASS, EP_COUNT };  // d_epoch has 8 slots
+enum { EP_BUILD = 0, EP_QUERY, EP_EMIT, EP_FANOUT, EP_BORDER, EP_BCAST, EP_CLASS, EP_PAYLOAD, EP_COUNT };  // d_epoch has 8 slots
 
 // ---- helpers shared by the translation units (C linkage only so that definitions may sit inside their extern "C" blocks)
 extern "C" {
@@ -274,6 +306,8 @@ chd_status chd_note_pos_read(chd_engine* e);
 // Called on the host wherever a stage's epoch is about to be bumped on the device: every 2^20 executions of a stage the
 // descriptors of its scan sites are cleared, so no descriptor can survive until the 22-bit epoch repeats.
 chd_status chd_epoch_tick(chd_engine* e, int stage);
+// lifecycle / migration calls may name slots beyond the current count: extends the slot table (new slots hold no pairs)
+chd_status chd_grow_slots(chd_engine* e, uint32_t new_n);
 // one stable LSD radix pass (histogram, look-back scan, scatter) over 32-bit keys; chd_entities.cu
 chd_status chd_sort_pass_any(chd_engine* e, uint32_t* hist, const ScanSite& site, const uint32_t* key_in, const uint32_t* val_in, uint32_t n,
                              const uint32_t* n_ptr, uint32_t per_block, uint32_t nblocks, uint32_t shift, uint32_t bits, uint32_t* key_out,

@@ -54,8 +54,75 @@ chd_status chd_set_subscribers(chd_engine* e, const uint32_t* conn_id, uint32_t 
     CU(e, cudaMemsetAsync(e->pairs[0].off, 0, ((uint64_t)e->lim.max_subscribers + 1) * 4, e->stream));
     CU(e, cudaMemsetAsync(e->pairs[1].off, 0, ((uint64_t)e->lim.max_subscribers + 1) * 4, e->stream));
     CU(e, cudaMemsetAsync(e->d_vis_off, 0, ((uint64_t)e->lim.max_subscribers + 1) * 8, e->stream));
+    CU(e, cudaMemsetAsync(e->d_slot_ctl, 0, e->lim.max_subscribers, e->stream));
+    if (n < e->lim.max_subscribers) CU(e, cudaMemsetAsync(e->d_conn + n, 0, sizeof(uint32_t) * (e->lim.max_subscribers - n), e->stream));
     e->n_slots = n;
     e->cur = 0;
+    return CHD_OK;
+}
+
+// slots (+ an optional per-slot value) of a lifecycle call -> device staging; slot lists are control-plane sized
+static chd_status upload_slot_list(chd_engine* e, const uint32_t* slot, const uint32_t* aux, uint32_t n, uint32_t* max_slot) {
+    if (n > e->lim.max_subscribers) {
+        e->fail("lifecycle call with %u slots > max_subscribers %u", n, e->lim.max_subscribers);
+        return CHD_ERR_CAPACITY;
+    }
+    *max_slot = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (slot[i] >= e->lim.max_subscribers) {
+            e->fail("slot %u >= max_subscribers %u", slot[i], e->lim.max_subscribers);
+            return CHD_ERR_INVALID;
+        }
+        if (slot[i] > *max_slot) *max_slot = slot[i];
+    }
+    // the host arrays are plain pageable memory in general: a synchronous copy keeps the cgo pointer rules trivially true
+    CU(e, cudaMemcpyAsync(e->d_lc_slot, slot, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, e->stream));
+    if (aux) CU(e, cudaMemcpyAsync(e->d_lc_aux, aux, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    return CHD_OK;
+}
+
+chd_status chd_grow_slots(chd_engine* e, uint32_t new_n) {
+    if (new_n <= e->n_slots) return CHD_OK;
+    const uint32_t old_n = e->n_slots;
+    extend_offsets_kernel<<<blocks_for(new_n - old_n, 256), 256, 0, e->stream>>>(e->pairs[e->cur].off, old_n, new_n);
+    KCHECK(e);
+    CU(e, cudaMemsetAsync(e->d_vis_off + old_n + 1, 0, sizeof(uint64_t) * (new_n - old_n), e->stream));  // refreshed by the next emit
+    e->n_slots = new_n;
+    return CHD_OK;
+}
+
+chd_status chd_add_subscribers(chd_engine* e, const uint32_t* slot, const uint32_t* conn_id, uint32_t n) {
+    if (!e || (n && (!slot || !conn_id))) return CHD_ERR_INVALID;
+    if (n == 0) return CHD_OK;
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
+    CU(e, cudaSetDevice(e->device));
+    uint32_t max_slot = 0;
+    chd_status st = upload_slot_list(e, slot, conn_id, n, &max_slot);
+    if (st != CHD_OK) return st;
+    slot_ctl_set_kernel<<<blocks_for(n, 256), 256, 0, e->stream>>>(e->d_lc_slot, e->d_lc_aux, n, (uint8_t)SLOT_NORMAL, 0u, e->d_slot_ctl, e->d_slot_src, e->d_conn);
+    KCHECK(e);
+    st = chd_grow_slots(e, max_slot + 1);
+    if (st != CHD_OK) return st;
+    e->lifecycle_used = true;
+    return CHD_OK;
+}
+
+chd_status chd_remove_subscribers(chd_engine* e, const uint32_t* slot, uint32_t n) {
+    if (!e || (n && !slot)) return CHD_ERR_INVALID;
+    if (n == 0) return CHD_OK;
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
+    CU(e, cudaSetDevice(e->device));
+    uint32_t max_slot = 0;
+    chd_status st = upload_slot_list(e, slot, nullptr, n, &max_slot);
+    if (st != CHD_OK) return st;
+    if (max_slot >= e->n_slots) {
+        e->fail("chd_remove_subscribers: slot %u is not in use (%u slots)", max_slot, e->n_slots);
+        return CHD_ERR_INVALID;
+    }
+    slot_ctl_set_kernel<<<blocks_for(n, 256), 256, 0, e->stream>>>(e->d_lc_slot, nullptr, n, (uint8_t)SLOT_REMOVE, 0u, e->d_slot_ctl, e->d_slot_src, nullptr);
+    KCHECK(e);
+    e->lifecycle_used = true;
     return CHD_OK;
 }
 
@@ -216,12 +283,14 @@ static chd_status interest_enqueue(chd_engine* e, const QueryDev& d, int part) {
         slot_scatter_kernel<<<blocks_for(n, 256), 256, 0, s>>>(d.sub, n, S, e->d_slot_query);
         KCHECK(e);
     }
-    SCAN(e, exclusive_scan_fn<SlotCountIn, uint32_t>(SlotCountIn{slot_query, n, e->d_status, e->d_qcount, prev.off}, e->d_noff, S, e->site_slot, s));
+    const uint8_t* ctl_in = e->lifecycle_used ? e->d_slot_ctl : nullptr;
+    SCAN(e, exclusive_scan_fn<SlotCountIn, uint32_t>(SlotCountIn{slot_query, n, e->d_status, e->d_qcount, prev, ctl_in, e->d_slot_src, e->mig}, e->d_noff, S,
+                                                     e->site_slot, s));
     if (S) {
         interest_fill_kernel<<<blocks_for(S, 128), 128, 0, s>>>(e->g, S, slot_query, n, e->d_status, e->d_bbox, e->d_win_off, e->d_window,
                                                                 e->d_side_cell, e->d_side_dist, e->d_side_cnt, d.spot_off, prev, cur, e->d_noff, P,
                                                                 e->d_time, DiffOut{e->d_new_sub, e->d_new_ch, e->d_gone_sub, e->d_gone_ch}, e->d_pair_ch, e->d_win_cursor,
-                                                                e->d_ctr);
+                                                                e->d_ctr, e->lifecycle_used ? e->d_slot_ctl : nullptr, e->d_slot_src, e->d_conn, e->mig);
         e->pair_ch_valid = true;
         e->by_cell_valid = true;
         KCHECK(e);
@@ -293,6 +362,7 @@ chd_status chd_update_interest(chd_engine* e, const chd_query_batch* q, int64_t 
     KCHECK(e);
     // the graph bakes in which staging arrays are live, the batch size and the pair-buffer parity
     uint64_t key = mix_key(mix_key(mix_key(0x696e74ull, d.n), e->n_slots), (uint64_t)e->cur);
+    key = mix_key(mix_key(key, e->lifecycle_used), (uint64_t)(uintptr_t)e->mig.base);
     const void* baked[] = {d.sub, d.kind, d.sph_cx, d.sph_cz, d.sph_r, d.box_cx, d.box_cz, d.box_ex, d.box_ez, d.cone_cx, d.cone_cz,
                            d.cone_dx, d.cone_dz, d.cone_angle, d.cone_r, d.spot_off, d.spot_ndist, d.spot_x, d.spot_z, d.spot_dist};
     for (const void* p : baked) key = mix_key(key, (uint64_t)(uintptr_t)p);  // pointers are baked into the captured launches

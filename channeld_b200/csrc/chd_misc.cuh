@@ -33,5 +33,10 @@ static __global__ void stage_begin_kernel(int64_t* dst, int64_t v, unsigned long
     if (zero_u64) *zero_u64 = 0;
 }
 static __global__ void set_u32_kernel(uint32_t* dst, uint32_t v) { *dst = v; }
+// the slot table grew from old_n to new_n slots: the new slots hold no pairs (CSR offsets continue at the total)
+static __global__ void extend_offsets_kernel(uint32_t* __restrict__ off, uint32_t old_n, uint32_t new_n) {
+    const uint32_t i = old_n + 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= new_n) off[i] = off[old_n];
+}
 
 }  // namespace chd

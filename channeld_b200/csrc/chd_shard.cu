@@ -1,7 +1,62 @@
-// chd_shard.cu — multi-GPU X-slab sharding: border export, halo import.
+// chd_shard.cu — multi-GPU X-slab sharding: border export, halo import, and the per-tick exchange itself:
+// ONE ncclAllGather of (entity id, cell) border records over NVLink / NVSwitch, issued by the library on the engine's
+// stream (chd_tick_sharded), so a host needs no NCCL binding of its own.
+//
+// NCCL is loaded with dlopen on first use (libnccl.so.2; a copy already in the process, e.g. torch's, is reused): a
+// single-GPU deployment needs no NCCL at all and the library keeps its link-time dependencies to libcudart.
 #include "chd_engine.h"
 
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only; every call goes through the table below
+
 #include "chd_shard.cuh"
+
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    decltype(&ncclGetVersion) GetVersion = nullptr;
+    std::string err;
+};
+NcclApi* nccl_api() {
+    static std::mutex mu;
+    static NcclApi* api = nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (api && api->lib) return api;
+    if (!api) api = new NcclApi();
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // a copy the process already loaded (torch bundles one)
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+        const char* m = dlerror();
+        api->err = std::string("cannot load libnccl.so.2: ") + (m ? m : "?");
+        return api;
+    }
+#define SYM(name)                                                          \
+    api->name = (decltype(api->name))dlsym(h, "nccl" #name);              \
+    if (!api->name) {                                                      \
+        api->err = "libnccl.so.2 lacks nccl" #name;                        \
+        return api;                                                        \
+    }
+    SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(AllGather) SYM(GetErrorString) SYM(GetVersion)
+#undef SYM
+    api->lib = h;
+    return api;
+}
+}  // namespace
+
+#define NC(e, api, call)                                                                                         \
+    do {                                                                                                         \
+        ncclResult_t _r = (call);                                                                                \
+        if (_r != ncclSuccess) {                                                                                 \
+            (e)->fail("%s failed: %s (%s:%d)", #call, (api)->GetErrorString(_r), __FILE__, __LINE__);            \
+            return CHD_ERR_CUDA;                                                                                 \
+        }                                                                                                        \
+    } while (0)
 
 extern "C" {
 
@@ -89,15 +144,18 @@ chd_status chd_import_halo(chd_engine* e, const uint32_t* d_records, uint32_t n_
         if (st0 != CHD_OK) return st0;
         const int slot = e->d_key == e->d_key_a ? 0 : 1;  // the halo keys are appended to the current key buffer
         uint64_t key = mix_key(mix_key(mix_key(0x696d706full, n_records), skip_first), skip_count);
+        key = mix_key(mix_key(key, e->rec_per_rank), e->rec_stride_words);
         key = mix_key(mix_key(mix_key(key, (uint64_t)(uintptr_t)d_records), e->n_own), (uint64_t)(uintptr_t)e->d_key);
         key = mix_key(mix_key(mix_key(key, e->g.col_lo), e->g.col_hi), e->g.halo);
         chd_status st = run_stage(e, e->g_import[slot], key, [&]() -> chd_status {
-            halo_flag_kernel<<<blocks_for(n_records ? n_records : 1, 256), 256, 0, s>>>(e->g, d_records, n_records, skip_first, skip_count,
+            const RecView rv{d_records, e->rec_per_rank ? e->rec_per_rank : (n_records ? n_records : 1u),
+                             e->rec_per_rank ? e->rec_stride_words : 2ull * (n_records ? n_records : 1u)};
+            halo_flag_kernel<<<blocks_for(n_records ? n_records : 1, 256), 256, 0, s>>>(e->g, rv, n_records, skip_first, skip_count,
                                                                                         e->d_bflag, e->d_epoch + EP_BORDER);
             KCHECK(e);
             SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_bflag, e->d_boff, n_records, e->site_border, s));
             // no host round trip: the kept count and the build length stay on the device (overflow -> CHD_OVF_BORDER)
-            halo_append_kernel<<<blocks_for(n_records ? n_records : 1, 256), 256, 0, s>>>(d_records, n_records, e->d_bflag, e->d_boff, e->n_own,
+            halo_append_kernel<<<blocks_for(n_records ? n_records : 1, 256), 256, 0, s>>>(rv, n_records, e->d_bflag, e->d_boff, e->n_own,
                                                                                           e->lim.max_entities, e->d_key, e->d_gid, e->d_n_build,
                                                                                           e->d_ctr);
             KCHECK(e);
@@ -110,4 +168,219 @@ chd_status chd_import_halo(chd_engine* e, const uint32_t* d_records, uint32_t n_
     e->entities_dirty = true;
     return CHD_OK;
 }
+
+/* ------------------------------------------------------------------ the exchange behind the ABI ---- */
+
+chd_status chd_comm_unique_id(void* out_id) {
+    if (!out_id) return CHD_ERR_INVALID;
+    NcclApi* api = nccl_api();
+    if (!api->lib) return CHD_ERR_CUDA;
+    ncclUniqueId id;
+    if (api->GetUniqueId(&id) != ncclSuccess) return CHD_ERR_CUDA;
+    static_assert(sizeof(ncclUniqueId) == CHD_COMM_ID_BYTES, "CHD_COMM_ID_BYTES must match ncclUniqueId");
+    memcpy(out_id, &id, sizeof id);
+    return CHD_OK;
+}
+
+chd_status chd_comm_init(chd_engine* e, const void* unique_id, int rank, int world, uint32_t halo_cols, uint32_t border_capacity,
+                         uint32_t migrate_subscribers, uint32_t migrate_pairs) {
+    if (!e || !unique_id || world < 1 || rank < 0 || rank >= world || border_capacity == 0) return CHD_ERR_INVALID;
+    if (world >= 4096 || migrate_subscribers >= (1u << 20)) return CHD_ERR_INVALID;  // (slot_src packs rank:12 | record:20)
+    if (e->comm) {
+        e->fail("chd_comm_init: already initialised");
+        return CHD_ERR_STATE;
+    }
+    if ((uint32_t)world > e->g.cols) {
+        e->fail("chd_comm_init: %d ranks > %u grid columns (a slab is at least one column)", world, e->g.cols);
+        return CHD_ERR_INVALID;
+    }
+    CU(e, cudaSetDevice(e->device));
+    NcclApi* api = nccl_api();
+    if (!api->lib) {
+        e->fail("%s", api->err.c_str());
+        return CHD_ERR_CUDA;
+    }
+    if ((uint64_t)border_capacity * (uint64_t)world + 1 > e->lim.max_entities) {
+        e->fail("chd_comm_init: border_capacity %u x %d ranks does not fit the halo scratch (max_entities %u)", border_capacity, world,
+                e->lim.max_entities);
+        return CHD_ERR_CAPACITY;
+    }
+    ncclUniqueId id;
+    memcpy(&id, unique_id, sizeof id);
+    ncclComm_t comm = nullptr;
+    NC(e, api, api->CommInitRank(&comm, world, id, rank));
+    e->comm = comm;
+    e->comm_rank = rank;
+    e->comm_world = world;
+    e->border_cap = border_capacity;
+    // one contribution per rank and tick = its border records followed by its migration blob (subscriber state in flight)
+    e->mig_subs = (migrate_subscribers + 1u) & ~1u;
+    e->mig_pairs = (migrate_pairs + 1u) & ~1u;
+    if (e->mig_subs && !e->mig_pairs) e->mig_pairs = 16 * e->mig_subs;
+    const uint64_t blob_words = e->mig_subs ? ((MigView::words(e->mig_subs, e->mig_pairs) + 3ull) & ~3ull) : 0ull;
+    e->rec_per_rank = border_capacity;
+    e->rec_stride_words = 2ull * border_capacity + blob_words;
+    if (!dalloc(e, &e->d_rec_local, e->rec_stride_words) || !dalloc(e, &e->d_rec_all, e->rec_stride_words * (uint64_t)world)) return CHD_ERR_CUDA;
+    CU(e, cudaMemsetAsync(e->d_rec_local, 0, e->rec_stride_words * 4, e->stream));
+    CU(e, cudaMemsetAsync(e->d_rec_all, 0, e->rec_stride_words * 4 * (uint64_t)world, e->stream));
+    // X-slabs by grid column: rank g of G owns columns [floor(g*cols/G), floor((g+1)*cols/G))
+    const uint32_t lo = (uint32_t)(((uint64_t)rank * e->g.cols) / (uint64_t)world), hi = (uint32_t)(((uint64_t)(rank + 1) * e->g.cols) / (uint64_t)world);
+    return chd_set_slab(e, lo, hi, halo_cols);
+}
+
+chd_status chd_comm_info(const chd_engine* e, int* rank, int* world, uint32_t* col_lo, uint32_t* col_hi, uint32_t* halo_cols, int* nccl_version) {
+    if (!e) return CHD_ERR_INVALID;
+    if (rank) *rank = e->comm ? e->comm_rank : 0;
+    if (world) *world = e->comm ? e->comm_world : 1;
+    if (col_lo) *col_lo = e->g.col_lo;
+    if (col_hi) *col_hi = e->g.col_hi;
+    if (halo_cols) *halo_cols = e->g.halo;
+    if (nccl_version) {
+        *nccl_version = 0;
+        NcclApi* api = nccl_api();
+        if (api->lib) api->GetVersion(nccl_version);
+    }
+    return CHD_OK;
+}
+
+chd_status chd_comm_destroy(chd_engine* e) {
+    if (!e) return CHD_ERR_INVALID;
+    if (!e->comm) return CHD_OK;
+    CU(e, cudaSetDevice(e->device));
+    CU(e, cudaStreamSynchronize(e->stream));
+    NcclApi* api = nccl_api();
+    if (api->lib) api->CommDestroy((ncclComm_t)e->comm);
+    e->comm = nullptr;
+    return CHD_OK;
+}
+
+// One sharded tick: interest + fan-out start on the second stream (they do not need positions), this rank's border records
+// are selected, ONE all-gather moves every rank's records over NVLink, the records this slab needs are appended as halo
+// entities, then build + emit run over own + halo entities and the streams join.  Nothing synchronises with the host.
+chd_status chd_tick_sharded(chd_engine* e, const chd_query_batch* q, int64_t t_ns, uint32_t flags, chd_tick_summary* out) {
+    if (!e) return CHD_ERR_INVALID;
+    if (!e->comm) {
+        e->fail("chd_tick_sharded before chd_comm_init");
+        return CHD_ERR_STATE;
+    }
+    chd_status st;
+    const bool has_batch = q || e->have_adopted_q;
+    // Without subscriber migration the interest update does not depend on the exchange: it starts first and overlaps it.
+    // With migration the immigrants' previous state arrives in the all-gather, so the update starts right after it.
+    if (has_batch && !e->mig_subs) {
+        st = chd_begin_interest(e, q, t_ns, (flags & CHD_TICK_FANOUT) ? 1 : 0);
+        if (st != CHD_OK) return st;
+    }
+    const uint32_t cap = e->border_cap;
+    if (e->mig_subs && !e->mig_packed) CU(e, cudaMemsetAsync(e->d_rec_local + 2ull * cap, 0, 16, e->stream));  // empty blob header
+    e->mig_packed = false;
+    st = chd_export_border(e, e->d_rec_local, cap, nullptr);
+    if (st != CHD_OK) return st;
+    NcclApi* api = nccl_api();
+    NC(e, api, api->AllGather(e->d_rec_local, e->d_rec_all, e->rec_stride_words, ncclUint32, (ncclComm_t)e->comm, e->stream));
+    e->n_collectives++;
+    if (e->mig_subs) {
+        e->mig = MigView{e->d_rec_all + 2ull * cap, e->rec_stride_words, e->mig_subs, e->mig_pairs};
+        if (has_batch) {
+            st = chd_begin_interest(e, q, t_ns, (flags & CHD_TICK_FANOUT) ? 1 : 0);
+            if (st != CHD_OK) return st;
+        }
+    }
+    st = chd_import_halo(e, e->d_rec_all, cap * (uint32_t)e->comm_world, (uint32_t)e->comm_rank * cap, cap);
+    if (st != CHD_OK) return st;
+    return chd_tick(e, nullptr, t_ns, flags, out);
+}
+
+/* ---- subscriber migration between ranks (state travels in the tick's all-gather) */
+
+chd_status chd_migrate_out(chd_engine* e, const uint32_t* slot, uint32_t n) {
+    if (!e || (n && !slot)) return CHD_ERR_INVALID;
+    if (!e->comm || !e->mig_subs) {
+        e->fail("chd_migrate_out: chd_comm_init was not given a migration capacity");
+        return CHD_ERR_STATE;
+    }
+    if (n > e->mig_subs) {
+        e->fail("chd_migrate_out: %u subscribers > migration capacity %u", n, e->mig_subs);
+        return CHD_ERR_CAPACITY;
+    }
+    if (e->mig_packed) {
+        e->fail("chd_migrate_out: one call per tick (pass every emigrant at once)");
+        return CHD_ERR_STATE;
+    }
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
+    CU(e, cudaSetDevice(e->device));
+    for (uint32_t i = 0; i < n; i++)
+        if (slot[i] >= e->n_slots) {
+            e->fail("chd_migrate_out: slot %u is not in use (%u slots)", slot[i], e->n_slots);
+            return CHD_ERR_INVALID;
+        }
+    CU(e, cudaMemcpyAsync(e->d_lc_slot, slot, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    uint32_t* blob = e->d_rec_local + 2ull * e->border_cap;
+    const MigView lay{blob, e->rec_stride_words, e->mig_subs, e->mig_pairs};
+    mig_pack_kernel<<<1, 256, 0, e->stream>>>(e->d_lc_slot, n, e->pairs[e->cur], e->d_conn, blob, lay, e->d_ctr);
+    KCHECK(e);
+    if (n) {
+        slot_ctl_mark_kernel<<<blocks_for(n, 256), 256, 0, e->stream>>>(e->d_lc_slot, n, (uint8_t)SLOT_DROP, e->d_slot_ctl);
+        KCHECK(e);
+    }
+    e->mig_packed = true;
+    e->lifecycle_used = true;
+    return CHD_OK;
+}
+
+chd_status chd_migrate_in(chd_engine* e, uint32_t src_rank, uint32_t first_index, const uint32_t* slot, const uint32_t* conn_id, uint32_t n) {
+    if (!e || (n && (!slot || !conn_id))) return CHD_ERR_INVALID;
+    if (!e->comm || !e->mig_subs) {
+        e->fail("chd_migrate_in: chd_comm_init was not given a migration capacity");
+        return CHD_ERR_STATE;
+    }
+    if ((int)src_rank >= e->comm_world || (uint64_t)first_index + n > e->mig_subs) return CHD_ERR_INVALID;
+    if (n == 0) return CHD_OK;
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
+    CU(e, cudaSetDevice(e->device));
+    uint32_t max_slot = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (slot[i] >= e->lim.max_subscribers) return CHD_ERR_INVALID;
+        if (slot[i] > max_slot) max_slot = slot[i];
+    }
+    CU(e, cudaMemcpyAsync(e->d_lc_slot, slot, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, e->stream));
+    CU(e, cudaMemcpyAsync(e->d_lc_aux, conn_id, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    slot_import_mark_kernel<<<blocks_for(n, 256), 256, 0, e->stream>>>(e->d_lc_slot, e->d_lc_aux, n, src_rank, first_index, e->d_slot_ctl, e->d_slot_src,
+                                                                      e->d_conn);
+    KCHECK(e);
+    chd_status st = chd_grow_slots(e, max_slot + 1);
+    if (st != CHD_OK) return st;
+    e->lifecycle_used = true;
+    return CHD_OK;
+}
+
+chd_status chd_get_rehome(chd_engine* e, uint32_t* global_id, uint32_t* dst_rank, uint32_t cap, uint32_t* count) {
+    if (!e || !count) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    if (!e->assigned) {
+        e->fail("chd_get_rehome before the tick's cell assignment");
+        return CHD_ERR_STATE;
+    }
+    cudaStream_t s = e->stream;
+    const uint32_t n = e->n_own, world = e->comm ? (uint32_t)e->comm_world : 1u;
+    // scratch: the radix sort's temporaries are free between builds
+    CU(e, cudaMemsetAsync(e->d_boff, 0, 4, s));
+    if (n) {
+        rehome_kernel<<<blocks_for(n, 256), 256, 0, s>>>(e->g, e->d_key, e->have_gid ? e->d_gid : nullptr, n, world, e->d_tmp_key, e->d_tmp_val,
+                                                         e->lim.max_entities, e->d_boff);
+        KCHECK(e);
+    }
+    chd_status st = chd_read_u32(e, e->d_boff, count);
+    if (st != CHD_OK) return st;
+    const uint32_t m = *count < cap ? *count : cap;
+    if (m && global_id) CU(e, cudaMemcpyAsync(global_id, e->d_tmp_key, 4ull * m, cudaMemcpyDefault, s));
+    if (m && dst_rank) CU(e, cudaMemcpyAsync(dst_rank, e->d_tmp_val, 4ull * m, cudaMemcpyDefault, s));
+    CU(e, cudaStreamSynchronize(s));
+    return CHD_OK;
+}
+
+uint64_t chd_collective_count(const chd_engine* e) { return e ? e->n_collectives : 0; }
+
 }  // extern "C"

@@ -27,7 +27,7 @@ chd_status chd_emit_visible(chd_engine* e) {
     st = run_stage(e, e->g_emit_prep[e->cur], key, [&]() -> chd_status {
         // per-pair visible counts are computed by the scan itself; the partition pass opens the next epoch
         SCAN(e, exclusive_scan_fn<PairVcountIn, uint64_t>(PairVcountIn{pb.cell, e->d_cell_start}, e->d_voff, P, e->site_voff, s, pb.off + S));
-        emit_partition_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, e->d_voff, e->d_first_pair, e->max_tiles, S, pb.off, e->d_vis_off,
+        emit_partition_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_first_pair, e->d_tile_desc, e->max_tiles, S, pb.off, e->d_vis_off,
                                                    e->lim.max_visible, e->d_ctr, e->d_epoch + EP_EMIT);
         KCHECK(e);
         return CHD_OK;
@@ -40,8 +40,14 @@ chd_status chd_emit_visible(chd_engine* e) {
     CU(e, cudaEventRecord(e->ev_prep_done, s));  // visible offsets + counters are final; only the expanded list is still to come
     {
         StageTimer kt(e, CHD_STAGE_EMIT_KERNEL);
-        emit_visible_kernel<<<(unsigned)e->sm_count * 4, EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4, e->phase_stride,
-                                                                                e->d_first_pair, e->d_vis, e->lim.max_visible);
+        // One CTA per 16 KB tile.  The tile count lives on the device; the grid is sized from the last visible count the host
+        // has seen (+3 %: the kernel loops if that was too few, surplus CTAs exit at once), from the capacity before that.
+        const uint64_t cap_tiles = (e->lim.max_visible + EMIT_TILE - 1) / EMIT_TILE;
+        uint64_t tiles = e->vis_estimate ? std::min<uint64_t>(cap_tiles, (e->vis_estimate + e->vis_estimate / 32) / EMIT_TILE + 64) : cap_tiles;
+        if (tiles == 0) tiles = 1;
+        if (tiles > 0x7fffffffull) tiles = 0x7fffffffull;
+        emit_visible_kernel<<<(unsigned)tiles, EMIT_THREADS, 0, s>>>(pb.off + S, P, &e->d_ctr->n_visible, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4, e->phase_stride,
+                                                                                e->d_first_pair, e->d_tile_desc, e->d_vis, e->lim.max_visible);
         KCHECK(e);
     }
     return CHD_OK;
@@ -215,6 +221,7 @@ chd_status chd_decode_summary(chd_engine* e, chd_tick_summary* out) {
     out->n_due = c.n_due; out->n_handover = c.n_handover; out->overflow = c.overflow; out->required_pairs = c.required_pairs;
     out->required_window_cells = c.required_window_cells; out->required_visible = c.required_visible; out->required_due = c.n_due;
     out->reserved = 0;
+    e->vis_estimate = c.n_visible;  // sizes the next emit grid
     if (c.overflow) {
         e->fail("capacity overflow mask 0x%x (pairs %llu, window cells %llu, visible %llu, due %u required)", c.overflow,
                 (unsigned long long)c.required_pairs, (unsigned long long)c.required_window_cells,

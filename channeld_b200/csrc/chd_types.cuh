@@ -11,10 +11,27 @@ constexpr int BUILD_ROUNDS = 8;
 constexpr int BUILD_TILE = BUILD_THREADS * BUILD_ROUNDS;  // 2048 entities per tile
 constexpr int BUILD_MAX_BINS = 1024;
 constexpr int EMIT_THREADS = 256;
-constexpr int EMIT_WARPS = EMIT_THREADS / 32;
-constexpr int EMIT_CHUNKS = 8;                   // 16-byte chunks per lane per tile
-constexpr int EMIT_TILE = 32 * EMIT_CHUNKS * 4;  // 1024 entries = 4 KB of output per WARP tile
-constexpr int EMIT_SMEM_PAIRS = 64;              // pairs per warp tile staged in shared memory
+#ifndef CHD_EMIT_ROWS
+#define CHD_EMIT_ROWS 4
+#endif
+#ifndef CHD_EMIT_MIN_BLOCKS
+#define CHD_EMIT_MIN_BLOCKS 6
+#endif
+constexpr int EMIT_ROWS = CHD_EMIT_ROWS;                    // 16-byte chunks per thread per tile
+constexpr int EMIT_TILE = EMIT_THREADS * 4 * EMIT_ROWS;     // 4096 entries = 16 KB of output per CTA
+constexpr int EMIT_SMEM_PAIRS = 256;                        // pairs per tile staged in shared memory (one per thread)
+
+// Per-tile copy descriptor written by the partition pass: the emit kernel needs ONE 16-byte load (broadcast to the CTA)
+// before it can issue its data loads, instead of a chain of three dependent index loads (first pair -> offsets / cell ->
+// cell start).  A tile is "simple" if at most two pairs' lists intersect it (always the case when cells hold more entities
+// than a tile: 4 444 vs 4 096 on the benchmark config); other tiles take the general path (segment table in shared memory).
+struct TileDesc {
+    uint32_t src0;  // source index (phase copy 0) of the entry that lands on the tile's first slot
+    uint32_t src1;  // source index of the first entry of the second segment
+    uint32_t ends;  // end0 | end1 << 16 (relative to the tile base, <= EMIT_TILE); bit 31 = not simple
+    uint32_t p0;    // the pair that owns the tile's first slot (general path)
+};
+static_assert(EMIT_TILE <= 0x7FFF, "segment ends are packed into 15 bits");
 
 struct QueryDev {
     uint32_t n;
@@ -49,6 +66,33 @@ struct Counters {  // device mirror of chd_tick_summary's counters
     uint32_t n_entities_in_world, n_query_errors, n_sub_new, n_unsub, n_kept, n_due, n_handover, overflow;
     unsigned long long required_pairs, required_window_cells, required_visible;
     uint32_t required_due, reserved;
+};
+
+// Pending lifecycle change of a subscriber slot, applied by the next interest update (chd_interest.cuh):
+enum : uint8_t {
+    SLOT_NORMAL = 0,
+    SLOT_REMOVE = 1,  // chd_remove_subscribers: every subscription of the slot is reported as unsubscribed, the slot is freed
+    SLOT_DROP = 2,    // chd_migrate_out: the slot's state was packed for another rank; its run vanishes without unsub entries
+    SLOT_IMPORT = 3   // chd_migrate_in: the slot's previous run comes out of the gathered migration blob (MigView)
+};
+
+// Subscriber state in flight between ranks: every rank contributes one fixed-size blob to the tick's all-gather (after its
+// border records).  Word layout of a blob (u32 words; Ms = max_subs, Mp = max_pairs, both even):
+//   [0] n_sub  [1] n_pairs  [2..3] pad | off[Ms+2] | conn[Ms] | cell[Mp] | dist[Mp] | interval[Mp] | flags[Mp] |
+//   last[Mp] (i64) | last_index[Mp] (u64)
+struct MigView {
+    const uint32_t* base;   // nullptr: no migration data this tick
+    uint64_t stride_words;  // distance between the blobs of consecutive ranks
+    uint32_t max_subs, max_pairs;
+    __host__ __device__ static uint64_t words(uint32_t ms, uint32_t mp) { return 4ull + (ms + 2ull) + ms + 4ull * mp + 4ull * mp; }
+    __host__ __device__ uint64_t o_off() const { return 4; }
+    __host__ __device__ uint64_t o_conn() const { return o_off() + max_subs + 2ull; }
+    __host__ __device__ uint64_t o_cell() const { return o_conn() + max_subs; }
+    __host__ __device__ uint64_t o_dist() const { return o_cell() + max_pairs; }
+    __host__ __device__ uint64_t o_interval() const { return o_dist() + max_pairs; }
+    __host__ __device__ uint64_t o_flags() const { return o_interval() + max_pairs; }
+    __host__ __device__ uint64_t o_last() const { return o_flags() + max_pairs; }
+    __host__ __device__ uint64_t o_lidx() const { return o_last() + 2ull * max_pairs; }
 };
 
 struct DiffOut {  // the two interest-diff lists of a tick: (subscriber slot, channel id)

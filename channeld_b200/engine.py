@@ -165,6 +165,17 @@ class Engine:
         self._ck(self.L.chd_set_subscribers(self.h, ptr(conn_id), len(conn_id)))
         self.n_slots = len(conn_id)
 
+    def add_subscribers(self, slots, conn_ids):
+        slots = np.ascontiguousarray(slots, np.uint32)
+        conn_ids = np.ascontiguousarray(conn_ids, np.uint32)
+        self._ck(self.L.chd_add_subscribers(self.h, ptr(slots), ptr(conn_ids), len(slots)))
+        if len(slots):
+            self.n_slots = max(self.n_slots, int(slots.max()) + 1)
+
+    def remove_subscribers(self, slots):
+        slots = np.ascontiguousarray(slots, np.uint32)
+        self._ck(self.L.chd_remove_subscribers(self.h, ptr(slots), len(slots)))
+
     def query_channel_ids(self, batch, cap=None):
         """-> (status[n], off[n+1], channel_id[], dist[])"""
         n = batch.n
@@ -339,6 +350,52 @@ class Engine:
         a, b = C.c_double(), C.c_double()
         self._ck(self.L.chd_profile_timeline(self.h, int(stage), C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    # ---- multi-GPU: the NCCL exchange behind the C ABI
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_uint8 * 128)()
+        st = capi.lib().chd_comm_unique_id(buf)
+        if st != capi.OK:
+            raise ChdError(st, "chd_comm_unique_id failed (libnccl.so.2 missing?)")
+        return bytes(buf)
+
+    def comm_init(self, unique_id, rank, world, halo_cols, border_capacity, migrate_subscribers=0, migrate_pairs=0):
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        self._ck(self.L.chd_comm_init(self.h, buf, int(rank), int(world), int(halo_cols), int(border_capacity), int(migrate_subscribers),
+                                      int(migrate_pairs)))
+
+    def migrate_out(self, slots):
+        slots = np.ascontiguousarray(slots, np.uint32)
+        self._ck(self.L.chd_migrate_out(self.h, ptr(slots), len(slots)))
+
+    def migrate_in(self, src_rank, first_index, slots, conn_ids):
+        slots = np.ascontiguousarray(slots, np.uint32)
+        conn_ids = np.ascontiguousarray(conn_ids, np.uint32)
+        self._ck(self.L.chd_migrate_in(self.h, int(src_rank), int(first_index), ptr(slots), ptr(conn_ids), len(slots)))
+        if len(slots):
+            self.n_slots = max(self.n_slots, int(slots.max()) + 1)
+
+    def get_rehome(self, cap=1 << 20):
+        gid, dst, n = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32), C.c_uint32()
+        self._ck(self.L.chd_get_rehome(self.h, ptr(gid), ptr(dst), cap, C.byref(n)))
+        k = min(n.value, cap)
+        return gid[:k].copy(), dst[:k].copy(), n.value
+
+    def comm_info(self):
+        r, w, ver = C.c_int(), C.c_int(), C.c_int()
+        lo, hi, halo = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self._ck(self.L.chd_comm_info(self.h, C.byref(r), C.byref(w), C.byref(lo), C.byref(hi), C.byref(halo), C.byref(ver)))
+        return dict(rank=r.value, world=w.value, col_lo=lo.value, col_hi=hi.value, halo=halo.value, nccl_version=ver.value)
+
+    def tick_sharded(self, batch, t_ns, flags=capi.TICK_ALL, want_summary=True):
+        s = TickSummary() if want_summary else None
+        self._ck(self.L.chd_tick_sharded(self.h, C.byref(batch) if batch is not None else None, int(t_ns), int(flags),
+                                         C.byref(s) if s is not None else None))
+        return s
+
+    def collective_count(self):
+        return int(self.L.chd_collective_count(self.h))
 
     # ---- multi-GPU slab
     def set_slab(self, col_lo, col_hi, halo):

@@ -128,6 +128,20 @@ chd_status chd_build(chd_engine* e);
  * data.go:240).  Resets all subscriptions. */
 chd_status chd_set_subscribers(chd_engine* e, const uint32_t* conn_id, uint32_t n);
 
+/* ---- subscriber lifecycle: slots are managed by the HOST (it owns the connection table, connection.go).  Neither call
+ * disturbs any other slot's subscriptions or fan-out state (lastFanOutTime, hadFirstFanOut, lastMessageIndex).
+ *   chd_add_subscribers    slot[i] (free: never used, or removed before) becomes connection conn_id[i]; it has no subscriptions
+ *                          until its first query (SubscribeToChannel then starts it like any new pair, subscription.go:60-87)
+ *   chd_remove_subscribers UnsubscribeFromChannel for every spatial channel of the slot (subscription.go:104-125; also what
+ *                          tickConnections does for a closed connection, channel.go:414-475): applied by the NEXT
+ *                          chd_update_interest / chd_tick with a batch (an empty batch will do) — the slot's subscriptions appear
+ *                          in that update's unsub list, a query for the slot in the same batch is ignored, the slot is free
+ *                          afterwards.
+ * slot / conn_id are HOST arrays (copied before the call returns).  Slots may exceed the count given to chd_set_subscribers
+ * (up to chd_limits.max_subscribers). */
+chd_status chd_add_subscribers(chd_engine* e, const uint32_t* slot, const uint32_t* conn_id, uint32_t n);
+chd_status chd_remove_subscribers(chd_engine* e, const uint32_t* slot, uint32_t n);
+
 enum { CHD_AOI_SPOTS = 1, CHD_AOI_BOX = 2, CHD_AOI_SPHERE = 4, CHD_AOI_CONE = 8 };
 
 /* A batch of SpatialInterestQuery (channeld.proto:436-469), SoA.  Arrays of kinds no query uses may be
@@ -339,6 +353,50 @@ chd_status chd_set_entity_ids(chd_engine* e, const uint32_t* global_id, uint32_t
 chd_status chd_export_border(chd_engine* e, uint32_t* d_records, uint32_t cap_records, uint32_t* out_count);
 chd_status chd_import_halo(chd_engine* e, const uint32_t* d_records, uint32_t n_records, uint32_t skip_first, uint32_t skip_count);
 
+/* ---- the exchange behind the ABI: NCCL over NVLink / NVSwitch, one process per GPU.  libnccl.so.2 is loaded on first use
+ * (a copy the process already holds is reused); a host needs no NCCL binding of its own.
+ *   rank 0:      chd_comm_unique_id(id)            -> the host distributes the 128 bytes by any means (TCP, a file, MPI, ...)
+ *   every rank:  chd_comm_init(e, id, rank, world, halo_cols, border_capacity, migrate_subscribers, migrate_pairs)   (collective;
+ *                also sets this rank's slab: columns [floor(rank*cols/world), floor((rank+1)*cols/world)), halo_cols =
+ *                ceil(max radius / grid_width); migrate_* = capacity of the per-tick subscriber migration blob, 0 = none)
+ *   every tick:  chd_set_rings / chd_set_entities (this rank's entities, global ids via chd_set_entity_ids) ...
+ *                chd_tick_sharded(e, q, t_ns, flags, summary) = chd_begin_interest + chd_export_border + ONE ncclAllGather of
+ *                (entity id, cell) records (border_capacity records per rank, padded) + chd_import_halo + chd_tick: collective,
+ *                stream-ordered, no host synchronisation unless summary != NULL.
+ * border_capacity bounds the records ONE rank exports per tick (entities in its outermost halo_cols columns on each side
+ * plus entities that left its slab); border_capacity * world must fit chd_limits.max_entities together with the own
+ * entities.  Exceeding it raises CHD_OVF_BORDER. */
+#define CHD_COMM_ID_BYTES 128
+chd_status chd_comm_unique_id(void* out_id);
+chd_status chd_comm_init(chd_engine* e, const void* unique_id, int rank, int world, uint32_t halo_cols, uint32_t border_capacity,
+                         uint32_t migrate_subscribers, uint32_t migrate_pairs);
+chd_status chd_comm_info(const chd_engine* e, int* rank, int* world, uint32_t* col_lo, uint32_t* col_hi, uint32_t* halo_cols, int* nccl_version);
+chd_status chd_comm_destroy(chd_engine* e);
+chd_status chd_tick_sharded(chd_engine* e, const chd_query_batch* q, int64_t t_ns, uint32_t flags, chd_tick_summary* out);
+uint64_t chd_collective_count(const chd_engine* e); /* NCCL collectives issued so far */
+
+/* ---- re-homing.  ENTITIES: an entity that leaves its owner's slab is still exported by that owner and adopted, for this tick, by
+ * every rank that needs it (visibility stays exact whatever the ownership); chd_get_rehome lists the own entities whose column
+ * now belongs to another rank (global id, destination rank) so the host can re-route their position feed — the sender drops
+ * them from its next chd_set_entities, the receiver includes them (the reference moves an entity between spatial channels the
+ * same way, spatial.go:683-736).
+ * SUBSCRIBERS live on the rank that owns their centre's column (the host routes each query there).  When that owner changes
+ * from rank A to rank B the subscriber's subscriptions and fan-out state (lastFanOutTime, hadFirstFanOut, lastMessageIndex per
+ * channel) travel INSIDE the tick's all-gather, so nothing is reset and nobody is re-sent FULL channel data:
+ *   on A, before chd_tick_sharded:  chd_migrate_out(eA, slot[], n)          record i of A's blob = state of slot[i]; A's slots are
+ *                                                                           freed by this tick's interest update (no unsub entries)
+ *   on B, before chd_tick_sharded:  chd_migrate_in(eB, A, first_index, slot[], conn_id[], n)
+ *                                   B's slot[i] becomes connection conn_id[i] with the state of record first_index + i of A's blob;
+ *                                   its query in this tick's batch is diffed against that state.
+ * Both ranks pass a query batch (an empty one will do) to the same chd_tick_sharded.  One chd_migrate_out per tick and rank;
+ * any number of chd_migrate_in.  Capacities: chd_comm_init's migrate_* (overflow: CHD_OVF_BORDER, the cut-off subscribers arrive
+ * without state).  slot / conn_id are HOST arrays. */
+chd_status chd_migrate_out(chd_engine* e, const uint32_t* slot, uint32_t n);
+chd_status chd_migrate_in(chd_engine* e, uint32_t src_rank, uint32_t first_index, const uint32_t* slot, const uint32_t* conn_id, uint32_t n);
+/* own entities (of the last cell assignment) whose column lies outside this rank's slab: global id + the rank that owns the
+ * column now.  Synchronous.  *count = how many there are (copies min(count, cap)). */
+chd_status chd_get_rehome(chd_engine* e, uint32_t* global_id, uint32_t* dst_rank, uint32_t cap, uint32_t* count);
+
 /* ---- window classes of the last fan-out pass (payload assembly).  The reference merges the selected
  * update window afresh for every subscriber (data.go:248-252); decisions of one channel whose merged payload is
  * necessarily identical are grouped so the host merges / frames each distinct payload once:
@@ -352,6 +410,32 @@ chd_status chd_import_halo(chd_engine* e, const uint32_t* d_records, uint32_t n_
  * Any output may be NULL.  CHD_ERR_CAPACITY if there are more than cap_classes classes.  Synchronous. */
 chd_status chd_due_classes(chd_engine* e, uint32_t* out_class_of, uint32_t* out_class_rep, uint32_t* out_class_count,
                            uint32_t cap_classes, uint32_t* out_n_classes);
+
+/* ---- the BYTE half of the fan-out: per window class the wire bytes of its CHANNEL_DATA_UPDATE
+ * message are assembled ONCE on the device (the reference re-merges and marshals three times per subscriber: data.go:246-256,
+ * :295, connection.go:58, :671), then every connection's packets are laid out framed — 'C' 'H' size_hi size_lo compressionType
+ * + marshalled Packet, optionally snappy-compressed (connection.go:626-714) — ready for conn.Write.
+ *   chd_set_payload_bytes   per-tick input next to chd_set_rings: serialized updateMsg of every ring entry (CSR entry_off[n_entries+1]
+ *                           in the ring order of chd_set_rings) and serialized full data message of every channel (full_off[cells+1]),
+ *                           the Any type URL of the channel data type and the message type (MessageType_CHANNEL_DATA_UPDATE = 8).
+ *   chd_assemble_payloads   after chd_fanout_tick / chd_tick: window classes (chd_due_classes) + for class k the bytes
+ *                           blob[class_off[k] .. class_off[k+1]) = one Packet.messages entry (0x0A len MessagePack{channelId,
+ *                           msgType, msgBody = ChannelDataUpdateMessage{data = Any{type_url, value}}}) where value = the
+ *                           concatenation of the selected ring entries' bytes (= proto.Merge of them, by the protobuf encoding
+ *                           rules) or the channel's full data for a FULL send.  Outputs may be NULL (results stay on the GPU).
+ *   chd_frame_packets       per connection (subscriber slot s): bytes out[conn_off[s] .. conn_off[s] + conn_len[s]) = its packets
+ *                           back to back, each 5-byte tag + body; a packet holds as many of the connection's messages as fit
+ *                           MaxPacketSize (0xffff), a single message >= MaxPacketSize - 5 is dropped (connection.go:73-77; counted
+ *                           in *n_dropped); compression[s] = 1 -> snappy block format (decodes with any snappy decoder; the bytes
+ *                           differ from Go's encoder).  conn_off is spaced for the worst case; conn_frames[s] = packets written.
+ * Valid for channel data types merged by the default reflection merge without ChannelDataMergeOptions (data.go:326-388);
+ * types with a custom Merge stay on the host.  Synchronous; buffers of this stage grow on demand. */
+chd_status chd_set_payload_bytes(chd_engine* e, const uint64_t* entry_off, uint32_t n_entries, const uint8_t* entry_bytes, const uint64_t* full_off,
+                                 const uint8_t* full_bytes, const char* type_url, uint32_t msg_type);
+chd_status chd_assemble_payloads(chd_engine* e, uint32_t* n_classes, uint64_t* class_off, uint32_t cap_classes, uint8_t* blob, uint64_t blob_cap,
+                                 uint64_t* blob_len);
+chd_status chd_frame_packets(chd_engine* e, const uint8_t* compression, uint64_t* conn_off, uint32_t* conn_len, uint32_t* conn_frames, uint8_t* out,
+                             uint64_t out_cap, uint64_t* out_len, uint32_t* n_dropped);
 
 /* ---- BroadcastType_ADJACENT_CHANNELS recipient sets, batched (message.go:188-239).
  * For message m sent to spatial channel channel_id[m] with BroadcastType mask broadcast[m] (channeld.proto: ALL_BUT_SENDER 4,

@@ -1,12 +1,19 @@
-"""Multi-GPU parity check (run under torchrun on a GPU box, one rank per GPU, NCCL):
+"""Multi-GPU parity run (one rank per GPU, launched by tests/test_multigpu.py or by hand):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
         tests/run_multigpu_parity.py
 
-Every rank owns an X-slab, exchanges border entity records with ONE all-gather per tick, rebuilds its cell CSR
-over own + halo entities and answers the subscribers whose centre lies in its slab.  Each rank checks its
-subscribers' (cell, dist) pairs and visible-entity lists against the single-process oracle: the union over ranks
-equals the single-GPU / oracle answer (SURVEY.md §8e parity row)."""
+Every rank owns an X-slab and drives the SHARDED engine through the library's own exchange (chd_comm_init /
+chd_tick_sharded: one ncclAllGather per tick issued inside libchd_b200.so).  Entities and subscribers move for several ticks
+and are RE-HOMED as they cross slab borders:
+  * entities: the owner keeps exporting an entity that left its slab (visibility stays exact); chd_get_rehome tells the hosts,
+    which hand it over for the next tick (sender drops, receiver adopts);
+  * subscribers: the host routes every subscriber to the owner of its centre's column; chd_migrate_out / chd_migrate_in move the
+    subscriptions + fan-out state inside the same all-gather.
+Oracle: every rank also runs a plain single-GPU engine over the WHOLE world (itself parity-tested against the CPU oracle by
+tests/test_gpu_parity.py) and compares, for EVERY local subscriber on EVERY tick: (channel, dist, interval, flags, lastFanOutTime,
+lastMessageIndex) of every pair bit-identical, visible lists identical as sets of global ids, fan-out decisions identical.
+The first tick is also checked against the CPU oracle directly."""
 import os
 import sys
 
@@ -20,6 +27,13 @@ sys.path.insert(0, ROOT)
 from channeld_b200 import capi, engine, sharding, synth  # noqa: E402
 from tests import _oracle  # noqa: E402
 
+TICK = 33_000_000
+
+
+def due_set(due, conn_of_slot):
+    return {(int(conn_of_slot[d["sub"]]), int(d["channel_id"]), int(d["kind"]), int(d["n_selected"]), int(d["first_sel"]), int(d["last_sel"]),
+             int(d["sel_hash"]), int(d["last_message_index"]), int(d["window_hi"])) for d in due}
+
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -28,72 +42,169 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     orc = _oracle.load()
     failures = 0
+    n_ticks = int(os.environ.get("CHD_PARITY_TICKS", "6"))
     # the 2x2 grid gives every rank of a 2-GPU run a ONE-column slab (empty interior, as at 8 GPUs on 15 columns)
-    for name, n_ent, n_sub, radius, max_move in (("benchmark", 120_000, 6_000, 50.0, 60.0), ("benchmark", 60_000, 3_000, 2500.0, 900.0),
-                                                 ("handover", 200_000, 4_000, 50.0, 120.0), ("2x2", 50_000, 2_000, 50.0, 60.0),
+    for name, n_ent, n_sub, radius, max_move in (("benchmark", 120_000, 6_000, 50.0, 700.0), ("benchmark", 60_000, 3_000, 2500.0, 900.0),
+                                                 ("handover", 200_000, 4_000, 50.0, 120.0), ("2x2", 50_000, 2_000, 50.0, 400.0),
                                                  ("2x2", 50_000, 2_000, 500.0, 300.0)):
         wc = synth.scaled(synth.CONFIGS[name], n_ent, n_sub)
         if world > wc.cols:
             continue
         og = _oracle.make_grid(wc.offx, wc.offz, wc.w, wc.h, wc.cols, wc.rows, wc.server_cols, wc.server_rows)
-        ex, ez = synth.entities(wc)
+        x, z = synth.entities(wc)
         halo = sharding.halo_columns(radius, wc.w)
         lo, hi = sharding.slab_columns(wc.cols, world, rank)
-        ent_col = sharding.column_of(ex, wc.offx, wc.w, wc.cols)
-        mine = np.nonzero(((ent_col >= lo) & (ent_col < hi)) | ((ent_col < 0) & (rank == 0)))[0]
+        ent_owner = sharding.owner_of_column(sharding.column_of(x, wc.offx, wc.w, wc.cols), wc.cols, world)
+        mine = np.nonzero(ent_owner == rank)[0]
         cap = n_ent  # generous border capacity for the test
-        e = engine.Engine(wc.cfg(), len(mine) + cap * world + 16, n_sub, device=local, max_visible=1 << 27)
         stream = torch.cuda.Stream(device=dev)
+        # ---- the sharded engine
+        e = engine.Engine(wc.cfg(), n_ent + cap * world + 16, n_sub, device=local, max_visible=1 << 27, max_pairs=n_sub * 64 + 1024)
         e.set_stream(stream.cuda_stream)
-        e.set_slab(lo, hi, halo)
-        e.set_entity_ids(mine.astype(np.uint32))
-        rec_local = torch.full((cap * 2,), -1, dtype=torch.int32, device=dev)
-        rec_all = torch.empty((cap * 2 * world,), dtype=torch.int32, device=dev)
-        x, z = ex.copy(), ez.copy()
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(engine.Engine.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        e.comm_init(uid.cpu().numpy().tobytes(), rank, world, halo, cap, migrate_subscribers=n_sub, migrate_pairs=n_sub * 16)
+        info = e.comm_info()
+        assert (info["col_lo"], info["col_hi"], info["world"]) == (lo, hi, world)
+        # ---- the single-GPU reference engine over the whole world (slot j = subscriber j)
+        e1 = engine.Engine(wc.cfg(), n_ent, n_sub, device=local, max_visible=1 << 28, max_pairs=n_sub * 64 + 1024)
+        e1.set_stream(stream.cuda_stream)
+        conn, cx, cz, r = synth.subscribers(wc, x, z, radius)
+        e1.set_subscribers(conn)
+        # host-side routing tables: subscriber j -> (owner rank, local slot on that rank); every process computes all of them
+        owner = np.full(n_sub, -1, np.int64)
+        slot_of = np.full(n_sub, -1, np.int64)
+        free = [list() for _ in range(world)]
+        used = [0] * world
+        sub_at = [dict() for _ in range(world)]  # per rank: local slot -> subscriber j
+        ring_state = None
+        n_mig_total = n_rehome_total = 0
         with torch.cuda.stream(stream):
-            for tick in range(3):
-                x, z = synth.move_entities(wc, x, z, tick, max_move)  # entities drift across slab borders
-                e.set_entities(x[mine], z[mine])
-                n_exp = e.export_border(rec_local, cap)
-                dist.all_gather_into_tensor(rec_all, rec_local)
-                e.import_halo(rec_all, cap * world, rank * cap, cap)
+            for tick in range(n_ticks):
+                t_ns = (tick + 1) * TICK
+                if tick:
+                    x, z = synth.move_entities(wc, x, z, tick, max_move)  # entities (and the subscribers standing on them) drift
                 conn, cx, cz, r = synth.subscribers(wc, x, z, radius)
-                sub_col = sharding.column_of(cx, wc.offx, wc.w, wc.cols)
-                smine = np.nonzero((sub_col >= lo) & (sub_col < hi))[0]
-                e.set_subscribers(conn[smine]) if tick == 0 else None
-                if tick == 0:
-                    s0 = smine  # subscriber placement is static; follow the same subscribers afterwards
-                q = s0
-                batch, keep = engine.make_batch(len(q), sub=np.arange(len(q), dtype=np.uint32), sphere=(cx[q], cz[q], r[q]))
-                s = e.tick(batch, (tick + 1) * 33_000_000, capi.TICK_BUILD | capi.TICK_EMIT)
-                want = orc.sphere_tick(og, x, z, cx[q], cz[q], r[q])
-                pairs = e.get_pairs(s.n_pairs)
+                col = sharding.column_of(cx, wc.offx, wc.w, wc.cols)
+                new_owner = np.where(col >= 0, sharding.owner_of_column(col, wc.cols, world), np.where(owner >= 0, owner, 0))
+                # ---- subscriber routing / migration (identical decisions on every rank)
+                arrivals = [[] for _ in range(world)]      # first placement: (j)
+                moves = {}                                  # (src, dst) -> [j...]
+                for j in np.nonzero(new_owner != owner)[0]:
+                    if owner[j] < 0:
+                        arrivals[new_owner[j]].append(int(j))
+                    else:
+                        moves.setdefault((int(owner[j]), int(new_owner[j])), []).append(int(j))
+                out_lists = {a: [] for a in range(world)}   # per source rank: emigrants in record order (grouped by destination)
+                in_calls = []                               # (dst, src, first_index, [j...])
+                for (a, b) in sorted(moves):
+                    in_calls.append((b, a, len(out_lists[a]), moves[(a, b)]))
+                    out_lists[a] += moves[(a, b)]
+
+                def take_slot(rk):
+                    if free[rk]:
+                        return free[rk].pop()
+                    used[rk] += 1
+                    return used[rk] - 1
+
+                # frees happen after this tick's update: a slot vacated now is reusable from the next tick on
+                vacated = {a: [int(slot_of[j]) for j in out_lists[a]] for a in range(world)}
+                if rank in out_lists and out_lists[rank]:
+                    e.migrate_out(np.array(vacated[rank], np.uint32))
+                for a in range(world):
+                    for j in out_lists[a]:
+                        del sub_at[a][int(slot_of[j])]
+                for (b, a, first, js) in in_calls:
+                    slots = [take_slot(b) for _ in js]
+                    for j, s_ in zip(js, slots):
+                        owner[j], slot_of[j] = b, s_
+                        sub_at[b][s_] = j
+                    if b == rank:
+                        e.migrate_in(a, first, np.array(slots, np.uint32), conn[js])
+                for b in range(world):
+                    if arrivals[b]:
+                        slots = [take_slot(b) for _ in arrivals[b]]
+                        for j, s_ in zip(arrivals[b], slots):
+                            owner[j], slot_of[j] = b, s_
+                            sub_at[b][s_] = j
+                        if b == rank:
+                            e.add_subscribers(np.array(slots, np.uint32), conn[arrivals[b]])
+                n_mig_total += sum(len(v) for v in out_lists.values())
+                # ---- update rings (global cells, same on every rank)
+                ring_state, roff, rarr, rsnd, ridx, rcmi = synth.update_rings(wc, tick, t_ns, TICK, 6, n_sub, ring_len=32, state=ring_state)
+                e.set_rings(roff, rarr, rsnd, ridx, rcmi)
+                e1.set_rings(roff, rarr, rsnd, ridx, rcmi)
+                # ---- the sharded tick
+                e.set_entities(x[mine], z[mine])
+                e.set_entity_ids(mine.astype(np.uint32))
+                my_slots = np.array(sorted(sub_at[rank]), np.uint32)
+                my_subs = np.array([sub_at[rank][int(s_)] for s_ in my_slots], np.int64)
+                batch, keep = engine.make_batch(len(my_slots), sub=my_slots, sphere=(cx[my_subs], cz[my_subs], r[my_subs]))
+                s = e.tick_sharded(batch, t_ns, capi.TICK_ALL)
+                for a in range(world):
+                    free[a] += vacated[a]
+                # ---- the single-GPU reference tick
+                e1.set_entities(x, z)
+                b1, k1 = engine.make_batch(n_sub, sphere=(cx, cz, r))
+                s1 = e1.tick(b1, t_ns, capi.TICK_ALL)
+                # ---- compare every local subscriber
+                p, p1 = e.get_pairs(s.n_pairs), e1.get_pairs(s1.n_pairs)
                 voff, vis = e.get_visible()
-                # a subscriber that drifted more than `halo` columns out of this slab would need re-homing: skip those
-                col_now = sharding.column_of(cx[q], wc.offx, wc.w, wc.cols)
-                ok_sub = (col_now >= lo - 0) & (col_now < hi + 0) if halo < 2 else (col_now >= lo - 1) & (col_now < hi + 1)
+                voff1, vis1 = e1.get_visible()
                 bad = 0
-                for k in np.nonzero(ok_sub)[0]:
-                    a = slice(pairs["off"][k], pairs["off"][k + 1])
-                    b = slice(int(want["pair_off"][k]), int(want["pair_off"][k + 1]))
-                    if not (np.array_equal(pairs["channel"][a], want["pair_cell"][b]) and np.array_equal(pairs["dist"][a], want["pair_dist"][b])):
-                        bad += 1
-                        continue
-                    got = vis[int(voff[k]):int(voff[k + 1])]
-                    exp = want["vis_entity"][int(want["vis_off"][k]):int(want["vis_off"][k + 1])]
-                    # halo entities of one cell come from one owner in its id order; own and halo never mix inside a
-                    # cell unless an entity left its owner's slab: compare as sets per cell => sort within the list
-                    if not np.array_equal(np.sort(got), np.sort(exp)):
+                for s_, j in zip(my_slots.tolist(), my_subs.tolist()):
+                    a, b = slice(p["off"][s_], p["off"][s_ + 1]), slice(p1["off"][j], p1["off"][j + 1])
+                    ok = all(np.array_equal(p[k][a], p1[k][b]) for k in ("channel", "dist", "interval", "flags", "last", "last_index"))
+                    ok = ok and np.array_equal(np.sort(vis[int(voff[s_]):int(voff[s_ + 1])]), np.sort(vis1[int(voff1[j]):int(voff1[j + 1])]))
+                    bad += 0 if ok else 1
+                # slots that are not in use hold no pairs
+                in_use = np.zeros(e.n_slots + 1, bool)
+                in_use[my_slots] = True
+                stray = int(((p["off"][1:] - p["off"][:-1])[~in_use[:-1][: len(p["off"]) - 1]]).sum()) if e.n_slots else 0
+                bad += stray
+                conn_of_slot = np.zeros(max(e.n_slots, 1), np.uint32)
+                conn_of_slot[my_slots] = conn[my_subs]
+                got_due = due_set(e.get_due(s.n_due), conn_of_slot)
+                mine_conn = set(conn[my_subs].tolist())
+                want_due = {d for d in due_set(e1.get_due(s1.n_due), conn) if d[0] in mine_conn}
+                if got_due != want_due:
+                    bad += 1 + len(got_due ^ want_due)
+                if tick == 0:  # the reference engine itself against the CPU oracle (whole world)
+                    want = orc.sphere_tick(og, x, z, cx, cz, r)
+                    if not (np.array_equal(p1["channel"], want["pair_cell"]) and np.array_equal(vis1, want["vis_entity"])):
                         bad += 1
                 failures += bad
-                print("rank %d %s r=%g tick %d: own=%d exported=%d subs=%d checked=%d mismatches=%d" %
-                      (rank, name, radius, tick, len(mine), n_exp, len(q), int(ok_sub.sum()), bad), flush=True)
+                # ---- entity re-homing for the next tick: sender drops, receiver adopts
+                g_id, g_dst, g_n = e.get_rehome()
+                allre = [None] * world
+                dist.all_gather_object(allre, (g_id.tolist(), g_dst.tolist()))
+                leaving = set(allre[rank][0])
+                adopt = [g for (ids, dsts) in allre for g, d_ in zip(ids, dsts) if d_ == rank]
+                if leaving or adopt:
+                    mine = np.array(sorted((set(mine.tolist()) - leaving) | set(adopt)), np.int64)
+                n_rehome_total += sum(len(v[0]) for v in allre)
+                print("rank %d %s r=%g tick %d: own=%d subs=%d/%d checked=%d mismatches=%d migrated=%d rehomed=%d" %
+                      (rank, name, radius, tick, len(mine), len(my_slots), n_sub, len(my_slots), bad,
+                       sum(len(v) for v in out_lists.values()), sum(len(v[0]) for v in allre)), flush=True)
+                # ownership invariant after re-homing: every in-world entity sits on the owner of its column
+                ent_owner = sharding.owner_of_column(sharding.column_of(x, wc.offx, wc.w, wc.cols), wc.cols, world)
+                in_world = sharding.column_of(x, wc.offx, wc.w, wc.cols) >= 0
+                z_ok = (sharding.column_of(z, wc.offz, wc.h, wc.rows) >= 0)
+                ok_mask = in_world & z_ok
+                if not np.array_equal(np.nonzero((ent_owner == rank) & ok_mask)[0], mine[ok_mask[mine]]):
+                    failures += 1
+                    print("rank %d: ownership invariant violated" % rank, flush=True)
+        if n_mig_total == 0 and name != "2x2":
+            print("rank %d %s: WARNING no subscriber migrated" % (rank, name), flush=True)
         e.close()
+        e1.close()
     t = torch.tensor([failures], device=dev)
     dist.all_reduce(t)
     dist.destroy_process_group()
     if int(t[0]) != 0:
-        raise SystemExit("multi-GPU parity FAILED: %d mismatching subscribers" % int(t[0]))
+        raise SystemExit("multi-GPU parity FAILED: %d mismatches" % int(t[0]))
     if rank == 0:
         print("multi-GPU parity OK")
 

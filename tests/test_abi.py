@@ -94,7 +94,8 @@ sys.path.insert(0, %r)
 from channeld_b200 import capi
 L = capi.lib()
 no_handle = {"chd_abi_version", "chd_default_limits", "chd_create", "chd_destroy", "chd_last_error", "chd_alloc_pinned", "chd_free_pinned",
-             "chd_get_adjacent_channels", "chd_get_regions", "chd_damping_interval_ms", "chd_launch_count", "chd_graph_launch_count"}
+             "chd_get_adjacent_channels", "chd_get_regions", "chd_damping_interval_ms", "chd_launch_count", "chd_graph_launch_count",
+             "chd_collective_count"}
 bad = []
 for name in capi.SYMBOLS:
     if name in no_handle:
@@ -105,7 +106,7 @@ for name in capi.SYMBOLS:
     if f(*args) != capi.ERR_INVALID:
         bad.append(name)
 L.chd_destroy(None)
-assert L.chd_launch_count(None) == 0 and L.chd_graph_launch_count(None) == 0
+assert L.chd_launch_count(None) == 0 and L.chd_graph_launch_count(None) == 0 and L.chd_collective_count(None) == 0
 print("BAD", bad)
 ''' % ROOT
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)

@@ -226,3 +226,121 @@ def test_iteration_guards_match_the_oracle(chd, oracle):
         if wst == 0:
             assert dict(zip(ids.tolist(), dist.tolist())) == want
     e.close()
+
+
+def test_subscriber_churn_parity(chd, oracle):
+    """chd_add_subscribers / chd_remove_subscribers over 12 ticks of moving subscribers: the removed slots' subscriptions come
+    back as unsub entries (UnsubscribeFromChannel, subscription.go:104-125), re-used slots start afresh, and the fan-out state of
+    every OTHER pair stays bit-identical to the literal tickData emulation (one oracle channel per cell) — the round-1 engine
+    could only reset everybody (chd_set_subscribers)."""
+    from tests._oracle import make_grid
+
+    g = (-300.0, -250.0, 100.0, 100.0, 6, 5)
+    og = make_grid(*g)
+    rng = np.random.default_rng(2024)
+    S, N = 48, 300
+    e = chd.engine.Engine(chd.engine.grid_cfg(*g), N, S + 16, max_visible=1 << 20)
+    conn = np.zeros(S + 16, np.uint32)
+    conn[:S] = np.arange(101, 101 + S)
+    e.set_subscribers(conn[:S])
+    e.set_entities(rng.uniform(-300, 300, N), rng.uniform(-250, 250, N))
+    e.build()
+    cells = g[4] * g[5]
+    chans = [oracle.channel() for _ in range(cells)]
+    rings = [[] for _ in range(cells)]
+    msg_index = np.zeros(cells, np.uint64)
+    n_slots = S + 16
+    cx, cz = rng.uniform(-280, 280, n_slots), rng.uniform(-230, 230, n_slots)
+    rad = rng.choice([30.0, 60.0, 120.0], n_slots)
+    active = np.zeros(n_slots, bool)
+    active[:S] = True
+    subs_now = [dict() for _ in range(n_slots)]
+    next_conn = 1000
+    t = 0
+    seen_removed = seen_added = 0
+    for tick in range(12):
+        t += 33 * MS if tick % 3 else 80 * MS
+        cx += rng.uniform(-40, 40, n_slots)
+        cz += rng.uniform(-40, 40, n_slots)
+        # ---- churn before the update: some connections close, some new ones arrive (into free slots, incl. ones beyond S)
+        want_un = set()
+        if tick >= 2:
+            leave = rng.choice(np.nonzero(active)[0], size=int(rng.integers(1, 5)), replace=False)
+            e.remove_subscribers(leave)
+            for j in leave:
+                for c in list(subs_now[j].keys()):
+                    want_un.add((int(j), int(c)))
+                    chans[c - S0].unsubscribe(int(conn[j]))
+                subs_now[j].clear()
+                active[j] = False
+                seen_removed += 1
+            free = np.nonzero(~active)[0]
+            free = free[~np.isin(free, leave)]  # a slot removed this tick is free only after the update
+            join = rng.choice(free, size=min(len(free), int(rng.integers(0, 4))), replace=False)
+            if len(join):
+                ids = np.arange(next_conn, next_conn + len(join), dtype=np.uint32)
+                next_conn += len(join)
+                e.add_subscribers(join, ids)
+                conn[join] = ids
+                active[join] = True
+                seen_added += len(join)
+        else:
+            leave = np.zeros(0, np.int64)
+        moving = active & (rng.random(n_slots) < 0.8)
+        qi = np.nonzero(moving | np.isin(np.arange(n_slots), leave))[0].astype(np.uint32)  # removed slots' queries are ignored
+        batch, keep = chd.engine.make_batch(len(qi), sub=qi, sphere=(cx[qi], cz[qi], rad[qi]))
+        e.update_interest(batch, t)
+        s = e.summary()
+        (new_s, new_c), (un_s, un_c) = e.get_diff(s.n_sub_new, s.n_unsub)
+        want_new = set()
+        for j in qi:
+            if not moving[j]:
+                continue
+            res, st = oracle.query(og, sphere=(cx[j], cz[j], rad[j]))
+            if st != 0:
+                continue
+            un, sn, kp = oracle.interest_diff(list(subs_now[j].keys()), list(res.keys()))
+            for c in un:
+                want_un.add((int(j), int(c)))
+                chans[c - S0].unsubscribe(int(conn[j]))
+                del subs_now[j][int(c)]
+            for c in list(sn) + list(kp):
+                chans[c - S0].subscribe(int(conn[j]), t, oracle.damping(res[int(c)], 20), 0, True, False)
+                subs_now[j][int(c)] = res[int(c)]
+            want_new |= {(int(j), int(c)) for c in sn}
+        assert set(zip(new_s.tolist(), new_c.tolist())) == want_new
+        assert set(zip(un_s.tolist(), un_c.tolist())) == want_un
+        pairs = e.get_pairs()
+        assert len(pairs["off"]) == e.n_slots + 1
+        for j in range(e.n_slots):
+            sl = slice(pairs["off"][j], pairs["off"][j + 1])
+            assert dict(zip(pairs["channel"][sl].tolist(), pairs["dist"][sl].tolist())) == subs_now[j], (tick, j)
+        # ---- updates + fan-out
+        for _ in range(int(rng.integers(5, 30))):
+            c = int(rng.integers(0, cells))
+            arrival = t - int(rng.integers(0, 60)) * MS
+            sender = int(rng.choice(conn[active])) if rng.random() < 0.5 else 7
+            msg_index[c] += 1
+            rings[c].append((arrival, sender, int(msg_index[c])))
+            chans[c].on_update(arrival, sender)
+        ring_off = np.concatenate([[0], np.cumsum([len(r) for r in rings])]).astype(np.uint32)
+        flat = [x for r in rings for x in r]
+        e.set_rings(ring_off, np.array([f[0] for f in flat], np.int64), np.array([f[1] for f in flat], np.uint32),
+                    np.array([f[2] for f in flat], np.uint64), msg_index)
+        e.fanout_tick(t)
+        s = e.summary()
+        due = e.get_due(s.n_due)
+        want = []
+        for c in range(cells):
+            for d in chans[c].tick_data_ex(t):
+                want.append((d["conn"], S0 + c, d["kind"], d["n"], d["first"], d["last"], d["hash"], d["last_index"], d["window_hi"]))
+        got = [(int(conn[d["sub"]]), int(d["channel_id"]), int(d["kind"]), int(d["n_selected"]), int(d["first_sel"]), int(d["last_sel"]),
+                int(d["sel_hash"]), int(d["last_message_index"]), int(d["window_hi"])) for d in due]
+        assert sorted(got) == sorted(want), tick
+        pairs = e.get_pairs()
+        for j in range(e.n_slots):
+            for p in range(pairs["off"][j], pairs["off"][j + 1]):
+                last, had, idx = chans[int(pairs["channel"][p]) - S0].state(int(conn[j]))
+                assert (int(pairs["last"][p]), bool(pairs["flags"][p] & 1), int(pairs["last_index"][p])) == (last, had, idx), (tick, j)
+    assert seen_removed >= 10 and seen_added >= 5
+    e.close()

@@ -141,6 +141,65 @@ __global__ void __launch_bounds__(256) copy_cta_rows(const uint4* __restrict__ s
     }
 }
 
+// persistent CTAs that pull chunk numbers from a global ticket (dynamic order, like the hardware block scheduler)
+template <int OP, int ROWS>
+__global__ void __launch_bounds__(256) fill_ticket(uint4* __restrict__ dst, uint64_t n_chunks, unsigned long long* ticket) {
+    __shared__ unsigned long long s_c;
+    const uint4 v = make_uint4(1, 2, 3, 4);
+    for (;;) {
+        if (threadIdx.x == 0) s_c = atomicAdd(ticket, 1ull);
+        __syncthreads();
+        const uint64_t c = s_c;
+        __syncthreads();
+        if (c >= n_chunks) return;
+        uint4* d = dst + c * (256 * ROWS);
+#pragma unroll
+        for (int i = 0; i < ROWS; i++) st16<OP>(d + i * 256 + threadIdx.x, v);
+    }
+}
+// the same as a copy out of the L2-resident pool; the next ticket is requested before the current chunk is copied
+template <int OP, int ROWS>
+__global__ void __launch_bounds__(256) copy_ticket(const uint4* __restrict__ src, uint4* __restrict__ dst, uint64_t n_chunks, unsigned long long* ticket) {
+    __shared__ unsigned long long s_c[2];
+    constexpr uint32_t CPS = SEG_V / (256 * ROWS);
+    if (threadIdx.x == 0) s_c[0] = atomicAdd(ticket, 1ull);
+    __syncthreads();
+    int b = 0;
+    for (;;) {
+        const uint64_t c = s_c[b];
+        if (threadIdx.x == 0) s_c[b ^ 1] = atomicAdd(ticket, 1ull);  // in flight while this chunk is copied
+        if (c >= n_chunks) return;
+        const uint4* s = src + (uint64_t)cell_of_segment(c / CPS) * SEG_V + (c % CPS) * (256 * ROWS);
+        uint4* d = dst + c * (256 * ROWS);
+        uint4 v[ROWS];
+#pragma unroll
+        for (int i = 0; i < ROWS; i++) v[i] = __ldg(s + i * 256 + threadIdx.x);
+#pragma unroll
+        for (int i = 0; i < ROWS; i++) st16<OP>(d + i * 256 + threadIdx.x, v[i]);
+        __syncthreads();
+        b ^= 1;
+    }
+}
+// non-persistent copy whose source comes from a per-chunk descriptor in memory (one dependent load, like the emit kernel)
+template <int OP, int ROWS>
+__global__ void __launch_bounds__(256) copy_grid_desc(const uint4* __restrict__ src, uint4* __restrict__ dst, const uint4* __restrict__ desc) {
+    const uint64_t c = blockIdx.x;
+    const uint4 dw = __ldg(desc + c);
+    const uint4* s = src + dw.x;
+    uint4* d = dst + c * (256 * ROWS);
+    uint4 v[ROWS];
+#pragma unroll
+    for (int i = 0; i < ROWS; i++) v[i] = __ldg(s + i * 256 + threadIdx.x);
+#pragma unroll
+    for (int i = 0; i < ROWS; i++) st16<OP>(d + i * 256 + threadIdx.x, v[i]);
+}
+template <int ROWS>
+__global__ void make_desc(uint4* desc, uint64_t n_chunks) {
+    constexpr uint32_t CPS = SEG_V / (256 * ROWS);
+    const uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (c < n_chunks) desc[c] = make_uint4((uint32_t)((uint64_t)cell_of_segment(c / CPS) * SEG_V + (c % CPS) * (256 * ROWS)), 0, 0, 0);
+}
+
 template <typename F>
 static double best_ms(F&& launch, int reps = 7) {
     cudaEvent_t a, b;
@@ -200,6 +259,23 @@ int main() {
     CG_(OP_WB, 1); CG_(OP_WB, 2); CG_(OP_WB, 4); CG_(OP_CS, 1); CG_(OP_CS, 4); CG_(OP_CG, 2);
 #define CC(OP, R, BPS) out("copy_cta_" #OP "_r" #R "_b" #BPS, best_ms([&] { copy_cta_rows<OP, R><<<sms * BPS, 256>>>(src, dst, n_v / (256 * R)); }), gb)
     CC(OP_WB, 4, 8); CC(OP_WB, 2, 8); CC(OP_CS, 4, 8); CC(OP_WB, 4, 4);
+    unsigned long long* ticket = nullptr;
+    CK(cudaMalloc(&ticket, 8));
+#define FT(OP, R, BPS) out("fill_ticket_" #OP "_r" #R "_b" #BPS, best_ms([&] { CK(cudaMemsetAsync(ticket, 0, 8)); fill_ticket<OP, R><<<sms * BPS, 256>>>(dst, n_v / (256 * R), ticket); }), gb)
+    FT(OP_WB, 4, 8); FT(OP_WB, 4, 4); FT(OP_WB, 16, 4); FT(OP_CS, 4, 8);
+#define CT(OP, R, BPS) out("copy_ticket_" #OP "_r" #R "_b" #BPS, best_ms([&] { CK(cudaMemsetAsync(ticket, 0, 8)); copy_ticket<OP, R><<<sms * BPS, 256>>>(src, dst, n_v / (256 * R), ticket); }), gb)
+    CT(OP_CS, 4, 8); CT(OP_CS, 4, 6); CT(OP_CS, 4, 4); CT(OP_CS, 2, 8);
+    {
+        uint4* desc = nullptr;
+        CK(cudaMalloc(&desc, (n_v / 256) * 16));
+        make_desc<4><<<(unsigned)((n_v / 1024 + 255) / 256), 256>>>(desc, n_v / 1024);
+        out("copy_grid_desc_OP_CS_r4", best_ms([&] { copy_grid_desc<OP_CS, 4><<<(unsigned)(n_v / 1024), 256>>>(src, dst, desc); }), gb);
+        make_desc<2><<<(unsigned)((n_v / 512 + 255) / 256), 256>>>(desc, n_v / 512);
+        out("copy_grid_desc_OP_CS_r2", best_ms([&] { copy_grid_desc<OP_CS, 2><<<(unsigned)(n_v / 512), 256>>>(src, dst, desc); }), gb);
+        make_desc<1><<<(unsigned)((n_v / 256 + 255) / 256), 256>>>(desc, n_v / 256);
+        out("copy_grid_desc_OP_CS_r1", best_ms([&] { copy_grid_desc<OP_CS, 1><<<(unsigned)(n_v / 256), 256>>>(src, dst, desc); }), gb);
+    }
+    CG_(OP_CS, 2);
     out("memcpy_d2d_half", best_ms([&] { CK(cudaMemcpyAsync(dst, dst + n_v / 2, bytes / 2, cudaMemcpyDeviceToDevice)); }), gb);
     printf("}\n");
     return 0;
