@@ -281,7 +281,7 @@ def run_ours(args):
     d_sub = t_sub.to(dev)
 
     n_e2e = args.e2e_steps or min(args.steps, 30)
-    n_steps_total = 1 + args.warmup + args.steps + 2 * (2 + n_e2e) + 2 + args.expanded_steps + 2
+    n_steps_total = 1 + args.warmup + args.steps + 3 * (2 + n_e2e) + 4 + args.expanded_steps + 2
     # one ring snapshot per step (arrival times follow the tick clock); bound the staging memory for huge grids
     ring_len, upc = args.ring_len, args.updates_per_cell
     while wc.cells * ring_len * 20 * n_steps_total > (768 << 20) and ring_len > 4:
@@ -450,29 +450,30 @@ def run_ours(args):
 
         # ---- e2e: host inputs, H2D + tick + D2H of the host-facing results, wall clock
         P_cap = int(sm.n_pairs * 1.25) + 1024
-        r_off, _ = pinned((S + 1,), torch.int32)
-        r_ch, _ = pinned((P_cap,), torch.int32)
-        r_dist, _ = pinned((P_cap,), torch.int32)
-        r_iv, _ = pinned((P_cap,), torch.int32)
-        r_new = [pinned((P_cap,), torch.int32)[0] for _ in range(4)]
-        r_due, _ = pinned((2 * P_cap, 12), torch.int32)
-        r_ho = [pinned((max_ent,), torch.int32)[0] for _ in range(3)]
-        r_status, _ = pinned((max(S, 1),), torch.int32)
-        r_voff, _ = pinned((S + 1,), torch.int64)
+
+        def make_result_set():
+            """One set of pinned host result buffers (chd_result_buffers) + the tensors that keep them alive."""
+            keep_ = dict(off=pinned((S + 1,), torch.int32)[0], ch=pinned((P_cap,), torch.int32)[0], dist=pinned((P_cap,), torch.int32)[0],
+                         iv=pinned((P_cap,), torch.int32)[0], diff=[pinned((P_cap,), torch.int32)[0] for _ in range(4)],
+                         due=pinned((2 * P_cap, 12), torch.int32)[0], ho=[pinned((max_ent,), torch.int32)[0] for _ in range(3)],
+                         status=pinned((max(S, 1),), torch.int32)[0], voff=pinned((S + 1,), torch.int64)[0],
+                         cs=pinned((wc.cells + 1,), torch.int32)[0], se=pinned((max_ent,), torch.int32)[0], hdr=pinned((64,), torch.int32)[0])
+            r = capi.ResultBuffers()
+            r.pair_off, r.pair_channel, r.pair_dist, r.pair_interval_ms, r.pair_cap = (capi.ptr(keep_["off"]), capi.ptr(keep_["ch"]), capi.ptr(keep_["dist"]),
+                                                                                    capi.ptr(keep_["iv"]), P_cap)
+            r.new_sub, r.new_channel, r.unsub_sub, r.unsub_channel, r.diff_cap = (*[capi.ptr(t) for t in keep_["diff"]], P_cap)
+            r.due, r.due_cap = capi.ptr(keep_["due"]), 2 * P_cap
+            r.handover_entity, r.handover_src, r.handover_dst, r.handover_cap = (*[capi.ptr(t) for t in keep_["ho"]], max_ent)
+            r.query_status, r.status_cap = capi.ptr(keep_["status"]), S
+            r.vis_off = capi.ptr(keep_["voff"])
+            # the cell CSR makes the host result LOSSLESS: visible(s) = concatenation over the subscriber's pairs (ascending channel
+            # id) of sorted_entity[cell_start[c] : cell_start[c + 1]] — the expanded list itself (1.95 GB) stays in HBM
+            r.cell_start, r.sorted_entity, r.entity_cap = capi.ptr(keep_["cs"]), capi.ptr(keep_["se"]), max_ent
+            return r, keep_
+
+        rb, rb_keep = make_result_set()
+        rb2, rb2_keep = make_result_set()
         summ = capi.TickSummary()
-        rb = capi.ResultBuffers()
-        rb.pair_off, rb.pair_channel, rb.pair_dist, rb.pair_interval_ms, rb.pair_cap = (capi.ptr(r_off), capi.ptr(r_ch), capi.ptr(r_dist),
-                                                                                       capi.ptr(r_iv), P_cap)
-        rb.new_sub, rb.new_channel, rb.unsub_sub, rb.unsub_channel, rb.diff_cap = (*[capi.ptr(t) for t in r_new], P_cap)
-        rb.due, rb.due_cap = capi.ptr(r_due), 2 * P_cap
-        rb.handover_entity, rb.handover_src, rb.handover_dst, rb.handover_cap = (*[capi.ptr(t) for t in r_ho], max_ent)
-        rb.query_status, rb.status_cap = capi.ptr(r_status), S
-        rb.vis_off = capi.ptr(r_voff)
-        # the cell CSR makes the host result LOSSLESS: visible(s) = concatenation over the subscriber's pairs (ascending channel
-        # id) of sorted_entity[cell_start[c] : cell_start[c + 1]] — the expanded list itself (1.95 GB) stays in HBM
-        r_cs, _ = pinned((wc.cells + 1,), torch.int32)
-        r_se, _ = pinned((max_ent,), torch.int32)
-        rb.cell_start, rb.sorted_entity, rb.entity_cap = capi.ptr(r_cs), capi.ptr(r_se), max_ent
         r_vis_keep = []
 
         phase_acc = {}
@@ -553,6 +554,57 @@ def run_ours(args):
         torch.cuda.synchronize()
         barrier()
         e2e_dt = time.perf_counter() - t0
+        # asynchronous form: the host never waits for a tick before it has enqueued the next one (chd_fetch_results_async writes the
+        # results into pinned memory with device-side sizes; chd_fetch_wait returns the PREVIOUS tick's results while the current
+        # one runs).  Same bytes up and down per step, all inside the timed region.
+        base += 2 + n_e2e
+        sets = [(rb, rb_keep), (rb2, rb2_keep)]
+
+        def async_enqueue(i):
+            t_ns = (i + 1) * TICK_NS
+            ck(L.chd_adopt_prefetched(e.h))
+            if world > 1:
+                ck(L.chd_tick_sharded(e.h, None, t_ns, capi.TICK_ALL, None))
+            else:
+                ck(L.chd_begin_interest(e.h, None, t_ns, 1))
+                ck(L.chd_tick(e.h, None, t_ns, capi.TICK_ALL, None))
+            prefetch_inputs(i + 1)
+            r_, k_ = sets[i % 2]
+            ck(L.chd_fetch_results_async(e.h, C.byref(r_), capi.ptr(k_["hdr"])))
+
+        def async_run(first, n):
+            got = []
+            async_enqueue(first)
+            for i in range(first + 1, first + n):
+                async_enqueue(i)
+                ck(L.chd_fetch_wait(e.h, C.byref(summ)))  # results of step i - 1, while step i runs
+                got.append((int(summ.n_pairs), int(summ.n_due), int(summ.n_sub_new), int(summ.n_unsub), int(summ.n_handover), int(summ.n_entities_in_world)))
+            ck(L.chd_fetch_wait(e.h, C.byref(summ)))
+            got.append((int(summ.n_pairs), int(summ.n_due), int(summ.n_sub_new), int(summ.n_unsub), int(summ.n_handover), int(summ.n_entities_in_world)))
+            return got
+
+        prefetch_inputs(base)
+        async_run(base, 2)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        got_async = async_run(base + 2, n_e2e)
+        torch.cuda.synchronize()
+        barrier()
+        e2e_async_dt = time.perf_counter() - t0
+        npairs_, ndue_, nnew_, nun_, nho_, nin_ = got_async[-1]
+        d2h_async = (256 + (S + 1) * 4 + 12 * npairs_ + 8 * (nnew_ + nun_) + 48 * ndue_ + 12 * nho_ + 4 * S + (S + 1) * 8 + (wc.cells + 1) * 4 + 4 * nin_)
+        # the asynchronously fetched lists are the same lists: check the last step against a synchronous fetch of the same state
+        rchk, rchk_keep = make_result_set()
+        ck(L.chd_fetch_results(e.h, C.byref(rchk), C.byref(summ)))
+        last_keep = sets[(base + 2 + n_e2e - 1) % 2][1]
+        npr = int(summ.n_pairs)
+        async_ok = (torch.equal(last_keep["off"], rchk_keep["off"]) and torch.equal(last_keep["ch"][:npr], rchk_keep["ch"][:npr])
+                    and torch.equal(last_keep["voff"], rchk_keep["voff"]) and torch.equal(last_keep["cs"], rchk_keep["cs"])
+                    and torch.equal(last_keep["se"][:int(summ.n_entities_in_world)], rchk_keep["se"][:int(summ.n_entities_in_world)])
+                    and torch.equal(last_keep["due"][:int(summ.n_due)], rchk_keep["due"][:int(summ.n_due)]))
+        if not async_ok:
+            raise SystemExit("asynchronous read-back differs from the synchronous one")
         if args.trace_e2e and rank == 0:
             n_ = max(phase_acc.get("n", 1), 1)
             e.close()
@@ -573,9 +625,10 @@ def run_ours(args):
 
     # ---- reductions over ranks
     if world > 1:
-        t = torch.tensor([ms, e2e_dt, e2e_serial_dt], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, e2e_dt, e2e_serial_dt, e2e_async_dt], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_dt, e2e_serial_dt = float(t[0]), float(t[1]), float(t[2])
+        ms, e2e_dt, e2e_serial_dt, e2e_async_dt = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+        d2h = d2h_async
         c = torch.tensor([float(sm.n_pairs), float(sm.n_visible), float(sm.n_due), float(launches), float(h2d), float(d2h)],
                          dtype=torch.float64, device=dev)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
@@ -616,12 +669,16 @@ def run_ours(args):
             "data": "synthetic",
             "config": config_dict(wc, world, args.scaling),
             "clocks": clocks,
-            "e2e": {"value": S_total * n_e2e / e2e_dt, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_dt / n_e2e * 1e3,
-                    "pipeline": "double-buffered inputs: chd_prefetch_{rings,queries,entities} upload the inputs of step i+1 (pinned host memory) "
-                                "while the kernels of step i run; every step still uploads one full position snapshot + its queries + rings and "
-                                "reads back its results inside the timed region; chd_fetch_results copies on its own stream while the "
-                                "expanded-list kernel is still running (CHD_TICK_EARLY_RESULTS)",
+            "e2e": {"value": S_total * n_e2e / e2e_async_dt, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h if world > 1 else d2h_async),
+                    "ms_per_step": e2e_async_dt / n_e2e * 1e3,
+                    "pipeline": "double-buffered inputs AND results through the C ABI: chd_prefetch_{rings,queries,entities} upload the inputs of step "
+                                "i+1 (pinned host memory) while the kernels of step i run; chd_fetch_results_async writes the results of step i "
+                                "into pinned host buffers (device-side sizes) while step i+1 — already enqueued — runs; chd_fetch_wait hands the "
+                                "host step i's results.  Every step uploads one full position snapshot + its queries + rings and reads back its "
+                                "results inside the timed region; checked equal to a synchronous chd_fetch_results",
+                    "sync_fetch": {"value": S_total * n_e2e / e2e_dt, "ms_per_step": e2e_dt / n_e2e * 1e3,
+                                   "note": "same pipeline with the blocking chd_fetch_results + CHD_TICK_EARLY_RESULTS (round-1 form): the host waits "
+                                           "for step i before it enqueues step i+1"},
                     "serial": {"value": S_total * n_e2e / e2e_serial_dt, "ms_per_step": e2e_serial_dt / n_e2e * 1e3,
                                "note": "no overlap between steps: upload -> tick -> read-back, one after the other (per-tick latency)"},
                     "result": "chd_fetch_results: summary + (cell,dist,interval) pairs + sub/unsub lists + fan-out due list + handover "

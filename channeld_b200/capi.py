@@ -23,7 +23,7 @@ Q_OK, Q_ERR_OUT_OF_WORLD, Q_ERR_BAD_STEP, Q_ERR_ITER_BOUND, Q_ERR_ANGLE_RANGE, Q
 DUE_VOID = 0xFFFFFFFF
 TICK_BUILD, TICK_EMIT, TICK_FANOUT, TICK_ALL = 1, 2, 4, 7
 TICK_EARLY_RESULTS = 8
-OVF_PAIRS, OVF_WINDOW, OVF_VISIBLE, OVF_DUE, OVF_BORDER = 1, 2, 4, 8, 16
+OVF_PAIRS, OVF_WINDOW, OVF_VISIBLE, OVF_DUE, OVF_BORDER, OVF_RING = 1, 2, 4, 8, 16, 32
 PF_HAD_FIRST, PF_NEW, PF_SKIP_SELF = 1, 2, 4
 
 
@@ -118,7 +118,7 @@ SYMBOLS = [
     "chd_set_slab", "chd_set_entity_ids", "chd_export_border", "chd_import_halo", "chd_due_classes", "chd_set_subscriber_types", "chd_adjacent_broadcast", "chd_get_adjacent_channels",
     "chd_get_regions", "chd_damping_interval_ms", "chd_launch_count", "chd_profile_enable", "chd_profile_get", "chd_profile_timeline", "chd_enable_graphs",
     "chd_graph_launch_count",
-    "chd_add_subscribers", "chd_remove_subscribers", "chd_set_payload_bytes", "chd_assemble_payloads", "chd_frame_packets", "chd_comm_unique_id", "chd_comm_init", "chd_comm_info", "chd_comm_destroy", "chd_tick_sharded", "chd_collective_count", "chd_migrate_out", "chd_migrate_in", "chd_get_rehome",
+    "chd_add_subscribers", "chd_remove_subscribers", "chd_fetch_results_async", "chd_fetch_wait", "chd_rings_init", "chd_rings_append", "chd_get_rings", "chd_set_channel_start_times", "chd_set_payload_bytes", "chd_assemble_payloads", "chd_frame_packets", "chd_comm_unique_id", "chd_comm_init", "chd_comm_info", "chd_comm_destroy", "chd_tick_sharded", "chd_collective_count", "chd_migrate_out", "chd_migrate_in", "chd_get_rehome",
 ]
 STAGE_BUILD, STAGE_INTEREST, STAGE_EMIT, STAGE_EMIT_KERNEL, STAGE_FANOUT, STAGE_TICK = range(6)
 
@@ -244,8 +244,20 @@ def lib():
     L.chd_profile_timeline.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.chd_profile_get.restype = C.c_int
     L.chd_profile_get.argtypes = [vp, C.c_int, C.POINTER(C.c_double), u64p]
+    L.chd_fetch_results_async.restype = C.c_int
+    L.chd_fetch_results_async.argtypes = [vp, C.POINTER(ResultBuffers), vp]
+    L.chd_fetch_wait.restype = C.c_int
+    L.chd_fetch_wait.argtypes = [vp, C.POINTER(TickSummary)]
+    L.chd_rings_init.restype = C.c_int
+    L.chd_rings_init.argtypes = [vp, C.c_uint32]
+    L.chd_rings_append.restype = C.c_int
+    L.chd_rings_append.argtypes = [vp, vp, C.c_uint32, vp, vp]
+    L.chd_get_rings.restype = C.c_int
+    L.chd_get_rings.argtypes = [vp, vp, vp, vp, vp, vp, C.c_uint32]
+    L.chd_set_channel_start_times.restype = C.c_int
+    L.chd_set_channel_start_times.argtypes = [vp, vp]
     L.chd_set_payload_bytes.restype = C.c_int
-    L.chd_set_payload_bytes.argtypes = [vp, vp, C.c_uint32, vp, vp, vp, C.c_char_p, C.c_uint32]
+    L.chd_set_payload_bytes.argtypes = [vp, vp, C.c_uint32, vp, vp, vp, vp, C.c_uint32]
     L.chd_assemble_payloads.restype = C.c_int
     L.chd_assemble_payloads.argtypes = [vp, u32p, vp, C.c_uint32, vp, C.c_uint64, u64p]
     L.chd_frame_packets.restype = C.c_int

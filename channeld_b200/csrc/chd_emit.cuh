@@ -29,11 +29,16 @@ struct PairVcountIn {
 __global__ void __launch_bounds__(256)
     emit_partition_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, const uint64_t* __restrict__ voff,
                           const uint32_t* __restrict__ pair_cell, const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ first_pair,
-                          TileDesc* __restrict__ desc, uint64_t max_tiles, uint32_t n_slots, const uint32_t* __restrict__ pair_off,
-                          uint64_t* __restrict__ vis_off, uint64_t vis_cap, Counters* __restrict__ ctr, unsigned long long* bump_epoch) {
+                          TileDesc* __restrict__ desc, uint32_t stride, uint64_t max_tiles, uint32_t n_slots, const uint32_t* __restrict__ pair_off,
+                          uint64_t* __restrict__ vis_off, uint64_t vis_cap, Counters* __restrict__ ctr, unsigned long long* bump_epoch,
+                          unsigned long long* __restrict__ ticket) {
     const uint64_t n = min((uint64_t)*n_pairs_ptr, pair_cap);
-    // last kernel of the emit preparation: open the NEXT execution's scan epoch (the scan of this one has completed)
-    if (bump_epoch && blockIdx.x == 0 && threadIdx.x == 0) *bump_epoch = chd_next_epoch(*bump_epoch);
+    // last kernel of the emit preparation: open the NEXT execution's scan epoch (the scan of this one has completed) and
+    // reset the tile ticket of the persistent copy kernel
+    if (bump_epoch && blockIdx.x == 0 && threadIdx.x == 0) {
+        *bump_epoch = chd_next_epoch(*bump_epoch);
+        if (ticket) *ticket = 0;
+    }
     for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s <= n_slots; s += (uint64_t)gridDim.x * blockDim.x) {
         vis_off[s] = voff[min((uint64_t)pair_off[s], n)];
         if (s == n_slots) {
@@ -53,7 +58,10 @@ __global__ void __launch_bounds__(256)
             const uint32_t tile_len = (uint32_t)min((uint64_t)EMIT_TILE, V - base);
             TileDesc d;
             d.p0 = (uint32_t)p;
-            d.src0 = cs + (uint32_t)(base - b);
+            // bases are phase-adjusted: the entry that lands on tile slot o is sorted4[base + o] and base + o is a multiple of 4
+            // whenever o is (copy k of the CSR payload holds element i at k * stride + k + i, stride % 4 == 0)
+            const uint32_t s0 = cs + (uint32_t)(base - b), ph0 = (0u - s0) & 3u;
+            d.src0 = ph0 * stride + ph0 + s0;
             const uint32_t end0 = (uint32_t)min((uint64_t)EMIT_TILE, e - base);
             uint32_t end1 = end0;
             d.src1 = 0;
@@ -61,7 +69,8 @@ __global__ void __launch_bounds__(256)
                 uint64_t q = p + 1;
                 while (q < n && voff[q + 1] == e) q++;
                 if (q < n) {
-                    d.src1 = cell_start[pair_cell[q]];
+                    const uint32_t s1 = cell_start[pair_cell[q]] - end0, ph1 = (0u - s1) & 3u;  // (wraps: only base + o, o >= end0, is used)
+                    d.src1 = ph1 * stride + ph1 + s1;
                     end1 = (uint32_t)min((uint64_t)EMIT_TILE, voff[q + 1] - base);
                 }
             }
@@ -147,34 +156,117 @@ __global__ void __launch_bounds__(EMIT_THREADS, CHD_EMIT_MIN_BLOCKS)
                         const uint64_t* __restrict__ voff, const uint32_t* __restrict__ pair_cell, const uint32_t* __restrict__ cell_start,
                         const uint32_t* __restrict__ sorted4, uint32_t stride, const uint32_t* __restrict__ first_pair,
                         const TileDesc* __restrict__ desc, uint32_t* __restrict__ vis_entity, uint64_t vis_cap) {
-    __shared__ uint32_t s_end[EMIT_SMEM_PAIRS];  // end of pair (p0+k) relative to the tile base, clamped to EMIT_TILE
-    __shared__ uint32_t s_src[EMIT_SMEM_PAIRS];  // source index of the pair's entry that lands on max(voff[p], tile base)
-    // V was published by the partition pass: the first load of a CTA does not depend on any other
+    __shared__ uint32_t s_end[EMIT_SMEM_PAIRS];  // (general path) end of pair (p0+k) relative to the tile base, clamped to EMIT_TILE
+    __shared__ uint32_t s_src[EMIT_SMEM_PAIRS];  // (general path) source index of the pair's entry that lands on max(voff[p], tile base)
+    // V was published by the partition pass: the first loads of a CTA (V, its descriptors) do not depend on each other
+    const uint64_t V = *n_visible_ptr;
+    const uint32_t tid = threadIdx.x;
+    uint4 dw[EMIT_TILES_PER_CTA];
+#pragma unroll
+    for (int k = 0; k < EMIT_TILES_PER_CTA; k++) dw[k] = __ldg(reinterpret_cast<const uint4*>(desc + (uint64_t)blockIdx.x * EMIT_TILES_PER_CTA + k));
+    if (V == 0 || V > vis_cap) return;
+    const uint64_t n_tiles = (V + EMIT_TILE - 1) / EMIT_TILE;
+    for (uint64_t t0 = (uint64_t)blockIdx.x * EMIT_TILES_PER_CTA; t0 < n_tiles; t0 += (uint64_t)gridDim.x * EMIT_TILES_PER_CTA) {
+        if (t0 != (uint64_t)blockIdx.x * EMIT_TILES_PER_CTA) {  // (only if the host under-estimated the tile count)
+#pragma unroll
+            for (int k = 0; k < EMIT_TILES_PER_CTA; k++)
+                if (t0 + k < n_tiles) dw[k] = __ldg(reinterpret_cast<const uint4*>(desc + t0 + k));
+        }
+        uint32_t src[EMIT_TILES_PER_CTA][EMIT_ROWS];
+#pragma unroll
+        for (int k = 0; k < EMIT_TILES_PER_CTA; k++) {
+            const bool live = t0 + k < n_tiles, simple = !(dw[k].z & 0x80000000u);
+            // simple tile: at most two segments, everything a thread needs is in the descriptor ({base0, base1, ends, p0});
+            // its length is end1 (a simple tile's second segment reaches the end of the tile or of the list)
+            const uint32_t end0 = dw[k].z & 0x7FFFu, end1 = (dw[k].z >> 16) & 0x7FFFu;
+            uint32_t* __restrict__ out = vis_entity + (t0 + k) * EMIT_TILE;
+#pragma unroll
+            for (int r = 0; r < EMIT_ROWS; r++) {
+                const uint32_t o = (r * EMIT_THREADS + tid) * 4;
+                src[k][r] = 0xFFFFFFFFu;
+                if (live && simple && o < end1) {
+                    const bool in0 = o + 4 <= end0, in1 = o >= end0 && o + 4 <= end1;
+                    if (in0 || in1) {
+                        src[k][r] = (in0 ? dw[k].x : dw[k].y) + o;
+                    } else {
+                        for (uint32_t j = 0; j < 4 && o + j < end1; j++)  // the chunk straddles the boundary / the end of the list
+                            out[o + j] = __ldg(sorted4 + (o + j < end0 ? dw[k].x : dw[k].y) + o + j);
+                    }
+                }
+            }
+        }
+        uint4 v[EMIT_TILES_PER_CTA][EMIT_ROWS];
+#pragma unroll
+        for (int k = 0; k < EMIT_TILES_PER_CTA; k++)
+#pragma unroll
+            for (int r = 0; r < EMIT_ROWS; r++)
+                if (src[k][r] != 0xFFFFFFFFu) v[k][r] = __ldg(reinterpret_cast<const uint4*>(sorted4 + src[k][r]));
+#pragma unroll
+        for (int k = 0; k < EMIT_TILES_PER_CTA; k++)
+#pragma unroll
+            for (int r = 0; r < EMIT_ROWS; r++)
+                if (src[k][r] != 0xFFFFFFFFu)
+                    __stcs(reinterpret_cast<uint4*>(vis_entity + (t0 + k) * EMIT_TILE + (r * EMIT_THREADS + tid) * 4), v[k][r]);
+#pragma unroll
+        for (int k = 0; k < EMIT_TILES_PER_CTA; k++)
+            if (t0 + k < n_tiles && (dw[k].z & 0x80000000u))  // CTA-uniform
+                emit_tile_general(t0 + k, n_tiles, V, dw[k].w, n_pairs_ptr, pair_cap, voff, pair_cell, cell_start, sorted4, stride, first_pair, vis_entity,
+                                  s_end, s_src);
+    }
+}
+
+
+// Persistent variant: gridDim.x = EMIT_PERSIST_BLOCKS CTAs per SM pull tile numbers from a global ticket (dynamic order, like the
+// hardware block scheduler; a static round-robin order runs 15 % slower, profiles/r2_write_probe.json) and software-pipeline
+// the index work: while the CTA copies tile i, thread 0 has the ticket of tile i+2 and the descriptor of tile i+1 in flight,
+// so the per-tile critical path is ONE round trip (the data loads).  The partition pass zeroes the ticket.
+__global__ void __launch_bounds__(EMIT_THREADS, CHD_EMIT_PERSIST_BLOCKS ? CHD_EMIT_PERSIST_REGCAP_BLOCKS : 1)
+    emit_visible_persistent_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, const unsigned long long* __restrict__ n_visible_ptr,
+                                   const uint64_t* __restrict__ voff, const uint32_t* __restrict__ pair_cell, const uint32_t* __restrict__ cell_start,
+                                   const uint32_t* __restrict__ sorted4, uint32_t stride, const uint32_t* __restrict__ first_pair,
+                                   const TileDesc* __restrict__ desc, uint32_t* __restrict__ vis_entity, uint64_t vis_cap,
+                                   unsigned long long* __restrict__ ticket) {
+    __shared__ uint32_t s_end[EMIT_SMEM_PAIRS];
+    __shared__ uint32_t s_src[EMIT_SMEM_PAIRS];
+    __shared__ unsigned long long s_tk[3];
+    __shared__ uint4 s_desc[2];
     const uint64_t V = *n_visible_ptr;
     if (V == 0 || V > vis_cap) return;
     const uint64_t n_tiles = (V + EMIT_TILE - 1) / EMIT_TILE;
     const uint32_t tid = threadIdx.x;
-    for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const uint64_t base = t * EMIT_TILE;
-        const uint32_t tile_len = (uint32_t)min((uint64_t)EMIT_TILE, V - base);
-        uint32_t* __restrict__ out = vis_entity + base;
-        const uint4 dw = __ldg(reinterpret_cast<const uint4*>(desc + t));  // one broadcast load: {src0, src1, ends, p0}
+    if (tid == 0) {
+        const unsigned long long t0 = atomicAdd(ticket, 1ull), t1 = atomicAdd(ticket, 1ull);
+        s_tk[0] = t0;
+        s_tk[1] = t1;
+        if (t0 < n_tiles) s_desc[0] = __ldg(reinterpret_cast<const uint4*>(desc + t0));
+    }
+    __syncthreads();
+    for (uint32_t it = 0;; it++) {
+        const uint64_t t = s_tk[it % 3];
+        if (t >= n_tiles) break;
+        const uint4 dw = s_desc[it & 1];
+        unsigned long long t2 = 0;
+        uint4 dn = make_uint4(0, 0, 0, 0);
+        const uint64_t t1 = s_tk[(it + 1) % 3];
+        if (tid == 0) {  // in flight while this tile is copied
+            t2 = atomicAdd(ticket, 1ull);
+            if (t1 < n_tiles) dn = __ldg(reinterpret_cast<const uint4*>(desc + t1));
+        }
         if (!(dw.z & 0x80000000u)) {
-            // simple tile: at most two segments, everything a thread needs is in the descriptor
             const uint32_t end0 = dw.z & 0x7FFFu, end1 = (dw.z >> 16) & 0x7FFFu;
+            uint32_t* __restrict__ out = vis_entity + t * EMIT_TILE;
             uint32_t src[EMIT_ROWS];
 #pragma unroll
             for (int r = 0; r < EMIT_ROWS; r++) {
                 const uint32_t o = (r * EMIT_THREADS + tid) * 4;
                 src[r] = 0xFFFFFFFFu;
-                if (o < tile_len) {
-                    if (o + 4 <= end0 || (o >= end0 && o + 4 <= end1)) {
-                        const uint32_t sidx = o < end0 ? dw.x + o : dw.y + (o - end0);
-                        const uint32_t ph = (0u - sidx) & 3u;  // phase copy whose 16-byte phase matches the destination
-                        src[r] = ph * stride + ph + sidx;
+                if (o < end1) {
+                    const bool in0 = o + 4 <= end0, in1 = o >= end0 && o + 4 <= end1;
+                    if (in0 || in1) {
+                        src[r] = (in0 ? dw.x : dw.y) + o;
                     } else {
-                        for (uint32_t j = 0; j < 4 && o + j < tile_len; j++)  // the chunk straddles the boundary / the end
-                            out[o + j] = __ldg(sorted4 + (o + j < end0 ? dw.x + o + j : dw.y + (o + j - end0)));
+                        for (uint32_t j = 0; j < 4 && o + j < end1; j++)
+                            out[o + j] = __ldg(sorted4 + (o + j < end0 ? dw.x : dw.y) + o + j);
                     }
                 }
             }
@@ -185,9 +277,14 @@ __global__ void __launch_bounds__(EMIT_THREADS, CHD_EMIT_MIN_BLOCKS)
 #pragma unroll
             for (int r = 0; r < EMIT_ROWS; r++)
                 if (src[r] != 0xFFFFFFFFu) __stcs(reinterpret_cast<uint4*>(out + (r * EMIT_THREADS + tid) * 4), v[r]);
-            continue;
+        } else {
+            emit_tile_general(t, n_tiles, V, dw.w, n_pairs_ptr, pair_cap, voff, pair_cell, cell_start, sorted4, stride, first_pair, vis_entity, s_end, s_src);
         }
-        emit_tile_general(t, n_tiles, V, dw.w, n_pairs_ptr, pair_cap, voff, pair_cell, cell_start, sorted4, stride, first_pair, vis_entity, s_end, s_src);
+        if (tid == 0) {
+            s_tk[(it + 2) % 3] = t2;
+            s_desc[(it + 1) & 1] = dn;
+        }
+        __syncthreads();
     }
 }
 

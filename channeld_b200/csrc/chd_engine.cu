@@ -139,6 +139,10 @@ void chd_destroy(chd_engine* e) {
     if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
     if (e->dl_stream) cudaStreamDestroy(e->dl_stream);
     if (e->dl_stream_b) cudaStreamDestroy(e->dl_stream_b);
+    for (int i = 0; i < 2; i++) {
+        if (e->ev_fetch_a[i]) cudaEventDestroy(e->ev_fetch_a[i]);
+        if (e->ev_fetch_b[i]) cudaEventDestroy(e->ev_fetch_b[i]);
+    }
     if (e->ev_prep_done) cudaEventDestroy(e->ev_prep_done);
     if (e->ev_build_done) cudaEventDestroy(e->ev_build_done);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
@@ -298,8 +302,10 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
          dalloc(e, &e->d_slot_query, S);
     ok = ok && dalloc(e, &e->d_new_off, (Q > P ? Q : P) + 2) && dalloc(e, &e->d_new_sub, P) && dalloc(e, &e->d_new_ch, P) && dalloc(e, &e->d_gone_sub, P) &&
          dalloc(e, &e->d_gone_ch, P);
-    ok = ok && dalloc(e, &e->d_pair_ch, P) && dalloc(e, &e->d_vcnt, P) && dalloc(e, &e->d_voff, P + 1) && dalloc(e, &e->d_first_pair, e->max_tiles + 1) && dalloc(e, &e->d_tile_desc, e->max_tiles + 1) &&
+    ok = ok && dalloc(e, &e->d_pair_ch, P) && dalloc(e, &e->d_vcnt, P) && dalloc(e, &e->d_voff, P + 1) && dalloc(e, &e->d_first_pair, e->max_tiles + 8) && dalloc(e, &e->d_tile_desc, e->max_tiles + 8) && dalloc(e, &e->d_emit_ticket, 1) &&
          dalloc(e, &e->d_vis_off, S + 1) && dalloc(e, &e->d_vis, L.max_visible);
+    ok = ok && dalloc(e, &e->d_cell_max_interval, C) && dalloc(e, &e->d_cell_start_ns, C) && dalloc(e, &e->d_rb_begin, C + 1) && dalloc(e, &e->d_rb_end, C + 1) &&
+         dalloc(e, &e->d_ring_flat_off, C + 2) && dalloc(e, &e->d_upd_off, C + 1);
     ok = ok && dalloc(e, &e->d_ring_off, C + 1) && dalloc(e, &e->d_ring_arrival, (uint64_t)L.max_ring_entries) &&
          dalloc(e, &e->d_ring_sender, (uint64_t)L.max_ring_entries) && dalloc(e, &e->d_ring_index, (uint64_t)L.max_ring_entries) &&
          dalloc(e, &e->d_ch_msg_index, C) && dalloc(e, &e->d_by_cell, P) &&
@@ -321,6 +327,9 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
     CCU(cudaMemsetAsync(e->d_ctr, 0, sizeof(Counters), e->stream));
     CCU(cudaMemsetAsync(e->d_win_cursor, 0, 8, e->stream));
     CCU(cudaMemsetAsync(e->d_slot_ctl, 0, S, e->stream));
+    CCU(cudaMemsetAsync(e->d_cell_max_interval, 0, C * 4, e->stream));
+    CCU(cudaMemsetAsync(e->d_cell_start_ns, 0, C * 8, e->stream));
+    CCU(cudaMemsetAsync(e->d_ch_msg_index, 0, C * 8, e->stream));
     CCU(cudaMemsetAsync(e->d_conn, 0, S * 4, e->stream));
     CCU(cudaMemsetAsync(e->d_time, 0, 16, e->stream));
     CCU(cudaMemsetAsync(e->d_ring_total, 0, 4, e->stream));

@@ -152,6 +152,7 @@ struct chd_engine {
     uint32_t *d_new_sub = nullptr, *d_new_ch = nullptr, *d_gone_sub = nullptr, *d_gone_ch = nullptr;
     // emit
     uint32_t *d_vcnt = nullptr, *d_first_pair = nullptr, *d_vis = nullptr;
+    unsigned long long* d_emit_ticket = nullptr;  // tile ticket of the persistent emit kernel (zeroed by the partition pass)
     TileDesc* d_tile_desc = nullptr;  // per-tile copy descriptors (chd_emit.cuh)
     uint32_t* d_pair_ch = nullptr;  // channel id of every current pair (written by interest_fill_kernel)
     // ---- window classes of the due list (chd_due_classes): keys written by the fan-out kernel, scratch allocated on first use
@@ -186,6 +187,12 @@ struct chd_engine {
     cudaStream_t dl_stream = nullptr, dl_stream_b = nullptr;  // phase A / phase B of the early read-back
     cudaEvent_t ev_prep_done = nullptr, ev_build_done = nullptr;
     bool build_done_recorded = false;  // this tick ran a build (its end is ev_build_done)
+    // chd_fetch_results_async: completion events of the two copy phases; the next tick is ordered after them on the device
+    // (two fetches may be outstanding: the host waits for tick k-1 after it has enqueued tick k and its fetch)
+    cudaEvent_t ev_fetch_a[2] = {nullptr, nullptr}, ev_fetch_b[2] = {nullptr, nullptr};
+    void* fetch_header[2] = {nullptr, nullptr};
+    uint64_t fetch_issued = 0, fetch_waited = 0;
+    bool fetch_guard = false;
     bool early_ready = false;  // ev_join + ev_prep_done of the last tick are recorded
     bool early_results_tick = false;  // CHD_TICK_EARLY_RESULTS of the tick being enqueued
     // CHD_TICK_EARLY_RESULTS: the expanded-list kernel starts after the aux chain (interest + fan-out), so every host-facing
@@ -199,6 +206,17 @@ struct chd_engine {
     int64_t* d_ring_arrival = nullptr;
     uint64_t *d_ring_index = nullptr, *d_ch_msg_index = nullptr;
     bool have_ch_msg_index = false;
+    // device-owned rings (chd_rings_init: ChannelData.OnUpdate on the GPU, data.go:149-173): per-cell begin / end cursors into
+    // slabs of ring_cap entries inside d_ring_arrival / d_ring_sender / d_ring_index; d_ch_msg_index = ChannelData.msgIndex
+    bool rings_owned = false;
+    uint32_t ring_cap = 0;
+    uint32_t *d_rb_begin = nullptr, *d_rb_end = nullptr, *d_upd_off = nullptr, *d_upd_sender = nullptr, *d_ring_flat_off = nullptr;
+    int64_t* d_upd_arrival = nullptr;
+    uint64_t upd_cap = 0;
+    uint32_t* d_ring_scan_scratch = nullptr;
+    uint32_t* d_cell_max_interval = nullptr;  // [C] ChannelData.maxFanOutIntervalMs (subscription.go:84-86)
+    int64_t* d_cell_start_ns = nullptr;       // [C] per-channel ChannelTime origin (chd_set_channel_start_times) or nullptr
+    bool have_cell_start = false;
     // what the fan-out kernel reads: the staging copies above or the caller's device arrays (zero-copy)
     const uint32_t *ring_off_p = nullptr, *ring_sender_p = nullptr;
     const int64_t* ring_arrival_p = nullptr;
@@ -308,6 +326,9 @@ chd_status chd_note_pos_read(chd_engine* e);
 chd_status chd_epoch_tick(chd_engine* e, int stage);
 // lifecycle / migration calls may name slots beyond the current count: extends the slot table (new slots hold no pairs)
 chd_status chd_grow_slots(chd_engine* e, uint32_t new_n);
+chd_status chd_fetch_guard(chd_engine* e);
+// what the fan-out / payload kernels read: the host-owned CSR snapshot (staged or zero-copy) or the device-owned rings
+RingDev chd_ring_view(const chd_engine* e);
 // one stable LSD radix pass (histogram, look-back scan, scatter) over 32-bit keys; chd_entities.cu
 chd_status chd_sort_pass_any(chd_engine* e, uint32_t* hist, const ScanSite& site, const uint32_t* key_in, const uint32_t* val_in, uint32_t n,
                              const uint32_t* n_ptr, uint32_t per_block, uint32_t nblocks, uint32_t shift, uint32_t bits, uint32_t* key_out,

@@ -166,6 +166,10 @@ chd_status chd_assign_cells_impl(chd_engine* e);
 
 chd_status chd_assign_cells(chd_engine* e) {
     if (!e) return CHD_ERR_INVALID;
+    {
+        chd_status gs_ = chd_fetch_guard(e);
+        if (gs_ != CHD_OK) return gs_;
+    }
     const bool was_assigned = e->assigned;
     chd_status st = chd_assign_cells_impl(e);
     if (st == CHD_OK && !was_assigned) st = chd_note_pos_read(e);
@@ -252,6 +256,10 @@ static chd_status build_enqueue(chd_engine* e, bool with_assign) {
 chd_status chd_build(chd_engine* e) {
     if (!e) return CHD_ERR_INVALID;
     CU(e, cudaSetDevice(e->device));
+    {
+        chd_status gs_ = chd_fetch_guard(e);
+        if (gs_ != CHD_OK) return gs_;
+    }
     StageTimer timer(e, CHD_STAGE_BUILD);
     chd_status st = chd_epoch_tick(e, EP_BUILD);
     if (st != CHD_OK) return st;

@@ -26,7 +26,7 @@ __device__ __forceinline__ uint32_t fanout_eval(const RingDev& ring, uint32_t ri
                                                 uint32_t me, uint32_t id_start, int64_t& last, uint8_t& flags, uint64_t& last_index, Emit&& emit) {
     const int64_t step_ns = (int64_t)interval * 1000000ll;  // ChannelTime.AddMs (channel.go:30-32)
     const bool skip_self = flags & PF_SKIP_SELF;
-    const uint32_t r0 = min(ring.off[c], ring_total), r1 = min(ring.off[c + 1], ring_total);
+    const uint32_t r0 = min(ring.off[c], ring_total), r1 = min(ring.end[c], ring_total);
     const uint32_t max_steps = interval ? FANOUT_MAX_STEPS : 1u;  // interval 0: the reference never terminates
     uint32_t n_out = 0;
     for (uint32_t step = 0; step < max_steps; step++) {
@@ -105,13 +105,18 @@ __global__ void __launch_bounds__(128, 6)  // <= 85 registers: the whole pair li
             p = by_cell[i];
             interval = pb.interval[p];
             last0 = last = pb.last[p];
-            if (t >= last + (int64_t)interval * 1000000ll) {  // due (else: the common cheap exit, no further state is read)
+            int64_t tc = t;  // ChannelTime of this pair's channel: every channel counts from its own start (channel.go:178)
+            if (ring.start) {
+                c = pb.cell[p];
+                tc = t - ring.start[c];
+            }
+            if (tc >= last + (int64_t)interval * 1000000ll) {  // due (else: the common cheap exit, no further state is read)
                 flags0 = flags = pb.flags[p];
                 last_index0 = last_index = pb.last_index[p];
                 c = pb.cell[p];
                 s = pb.sub[p];
                 me = conn_id[s];
-                n_out = fanout_eval(ring, ring_total, t, interval, c, s, me, id_start, last, flags, last_index,
+                n_out = fanout_eval(ring, ring_total, tc, interval, c, s, me, id_start, last, flags, last_index,
                                     [&](uint32_t j, const chd_due& d, bool skipped) {
                                         if (j == 0) { d0 = d; sk0 = skipped; }
                                         else if (j == 1) { d1 = d; sk1 = skipped; }
@@ -151,7 +156,7 @@ __global__ void __launch_bounds__(128, 6)  // <= 85 registers: the whole pair li
                 if (n_out > 1) { due[o + 1] = d1; due_key[o + 1] = make_due_key(c, d1.kind, sk1, s, d1.window_hi - step_ns); }
             } else {  // several intervals behind: re-evaluate from the saved state, writing directly
                 last = last0; flags = flags0; last_index = last_index0;
-                fanout_eval(ring, ring_total, t, interval, c, s, me, id_start, last, flags, last_index,
+                fanout_eval(ring, ring_total, ring.start ? t - ring.start[c] : t, interval, c, s, me, id_start, last, flags, last_index,
                             [&](uint32_t j, const chd_due& d, bool skipped) {
                                 due[o + j] = d; due_key[o + j] = make_due_key(c, d.kind, skipped, s, d.window_hi - step_ns);
                             });

@@ -290,7 +290,8 @@ static chd_status interest_enqueue(chd_engine* e, const QueryDev& d, int part) {
         interest_fill_kernel<<<blocks_for(S, 128), 128, 0, s>>>(e->g, S, slot_query, n, e->d_status, e->d_bbox, e->d_win_off, e->d_window,
                                                                 e->d_side_cell, e->d_side_dist, e->d_side_cnt, d.spot_off, prev, cur, e->d_noff, P,
                                                                 e->d_time, DiffOut{e->d_new_sub, e->d_new_ch, e->d_gone_sub, e->d_gone_ch}, e->d_pair_ch, e->d_win_cursor,
-                                                                e->d_ctr, e->lifecycle_used ? e->d_slot_ctl : nullptr, e->d_slot_src, e->d_conn, e->mig);
+                                                                e->d_ctr, e->lifecycle_used ? e->d_slot_ctl : nullptr, e->d_slot_src, e->d_conn, e->mig,
+                                                                e->have_cell_start ? e->d_cell_start_ns : nullptr, e->d_cell_max_interval);
         e->pair_ch_valid = true;
         e->by_cell_valid = true;
         KCHECK(e);
@@ -330,6 +331,10 @@ chd_status chd_update_interest(chd_engine* e, const chd_query_batch* q, int64_t 
     if (!e) return CHD_ERR_INVALID;
     std::lock_guard<std::recursive_mutex> lk(e->mu);
     CU(e, cudaSetDevice(e->device));
+    {
+        chd_status gs_ = chd_fetch_guard(e);
+        if (gs_ != CHD_OK) return gs_;
+    }
     StageTimer timer(e, CHD_STAGE_INTEREST);
     QueryDev d;
     chd_status st;
@@ -362,7 +367,7 @@ chd_status chd_update_interest(chd_engine* e, const chd_query_batch* q, int64_t 
     KCHECK(e);
     // the graph bakes in which staging arrays are live, the batch size and the pair-buffer parity
     uint64_t key = mix_key(mix_key(mix_key(0x696e74ull, d.n), e->n_slots), (uint64_t)e->cur);
-    key = mix_key(mix_key(key, e->lifecycle_used), (uint64_t)(uintptr_t)e->mig.base);
+    key = mix_key(mix_key(mix_key(key, e->lifecycle_used), (uint64_t)(uintptr_t)e->mig.base), e->have_cell_start);
     const void* baked[] = {d.sub, d.kind, d.sph_cx, d.sph_cz, d.sph_r, d.box_cx, d.box_cz, d.box_ex, d.box_ez, d.cone_cx, d.cone_cz,
                            d.cone_dx, d.cone_dz, d.cone_angle, d.cone_r, d.spot_off, d.spot_ndist, d.spot_x, d.spot_z, d.spot_dist};
     for (const void* p : baked) key = mix_key(key, (uint64_t)(uintptr_t)p);  // pointers are baked into the captured launches

@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(128)
                          const uint32_t* __restrict__ side_cnt, const uint32_t* __restrict__ spot_off, PairBuf prev, PairBuf cur,
                          const uint32_t* __restrict__ new_off, uint64_t pair_cap, const int64_t* __restrict__ now_ptr, DiffOut diff,
                          uint32_t* __restrict__ pair_channel, const unsigned long long* __restrict__ win_cursor, Counters* __restrict__ ctr,
-                         uint8_t* __restrict__ slot_ctl, const uint32_t* __restrict__ slot_src, uint32_t* __restrict__ conn_id, MigView mig) {
+                         uint8_t* __restrict__ slot_ctl, const uint32_t* __restrict__ slot_src, uint32_t* __restrict__ conn_id, MigView mig,
+                         const int64_t* __restrict__ cell_start_ns, uint32_t* __restrict__ cell_max_interval) {
     __shared__ uint32_t s_warp_new[4], s_warp_gone[4], s_base_new, s_base_gone, s_kept;
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -216,8 +217,10 @@ __global__ void __launch_bounds__(128)
                 // new subscription (subscription.go:60-87): hadFirstFanOut = SkipFirstFanOut(false),
                 // lastFanOutTime = now + FanOutDelayMs, SkipSelfUpdateFanOut = true
                 cur.flags[o] = PF_NEW | PF_SKIP_SELF;
-                cur.last[o] = now_ns + (int64_t)g.default_delay_ms * 1000000ll;
+                cur.last[o] = now_ns - (cell_start_ns ? cell_start_ns[c] : 0ll) + (int64_t)g.default_delay_ms * 1000000ll;  // ch.GetTime() + delay
                 cur.last_index[o] = 0;
+                // ChannelData.maxFanOutIntervalMs only ever grows, and only when a subscription is created (subscription.go:84-86)
+                if (cell_max_interval && cell_max_interval[c] < interval) atomicMax(&cell_max_interval[c], interval);
                 if (on < pair_cap) { diff.new_sub[on] = s; diff.new_ch[on] = c + g.id_start; }
                 on++;
             }

@@ -84,6 +84,7 @@ chd_status chd_assemble_payloads(chd_engine* e, uint32_t* out_n_classes, uint64_
     if (out_blob_len) *out_blob_len = 0;
     if (n_classes == 0) {
         P.blob_len = 0;
+        P.assembled = true;
         if (out_class_off && cap_classes + 1 >= 1) out_class_off[0] = 0;
         return CHD_OK;
     }
@@ -92,9 +93,11 @@ chd_status chd_assemble_payloads(chd_engine* e, uint32_t* out_n_classes, uint64_
     ENSURE(e, P.d_cls_off, P.cap_cls_off, (uint64_t)n_classes + 2);
     st = remake_site(e, P.site_cls, &P.cap_site_cls, (uint64_t)n_classes + 1, EP_PAYLOAD);
     if (st != CHD_OK) return st;
-    const RingDev ring{e->ring_off_p ? e->ring_off_p : e->d_ring_off, e->ring_arrival_p ? e->ring_arrival_p : e->d_ring_arrival,
-                       e->ring_sender_p ? e->ring_sender_p : e->d_ring_sender, e->ring_index_p ? e->ring_index_p : e->d_ring_index,
-                       e->have_ch_msg_index ? e->ch_msg_index_p : nullptr, e->d_ring_total};
+    if (e->rings_owned) {
+        e->fail("chd_assemble_payloads needs host-owned rings (chd_set_rings): payload bytes are indexed by ring position");
+        return CHD_ERR_STATE;
+    }
+    const RingDev ring = chd_ring_view(e);
     const PayloadIn in{(const unsigned long long*)P.d_entry_off, P.d_entry_bytes, (const unsigned long long*)P.d_full_off, P.d_full_bytes, P.d_url, P.url_len,
                        P.msg_type};
     st = chd_epoch_tick(e, EP_PAYLOAD);

@@ -64,7 +64,7 @@ __device__ __forceinline__ MsgSizes msg_sizes(uint64_t value_len, uint32_t url_l
 template <typename F>
 __device__ __forceinline__ void for_each_selected(const RingDev& ring, uint32_t ring_total, uint32_t cell, int64_t lo, int64_t hi, bool skipped,
                                                   uint32_t me, F&& f) {
-    const uint32_t r0 = min(ring.off[cell], ring_total), r1 = min(ring.off[cell + 1], ring_total);
+    const uint32_t r0 = min(ring.off[cell], ring_total), r1 = min(ring.end[cell], ring_total);
     int64_t last_update = lo > 0 ? lo : 0;
     for (uint32_t k = r0; k < r1; k++) {
         const int64_t a = ring.arrival[k];

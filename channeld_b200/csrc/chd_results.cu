@@ -3,6 +3,56 @@
 
 #include "chd_misc.cuh"
 
+// ---- asynchronous read-back (chd_fetch_results_async): result lists are written straight into the caller's PINNED host buffers by
+// a copy kernel that knows the exact list lengths on the device (no host round trip to size a cudaMemcpy), so the host can
+// enqueue the next tick before it looks at this one's results.
+namespace {
+struct PackSeg {
+    const void* src;
+    void* dst;
+    const void* count_ptr;  // device address of the element count (nullptr: `fixed`)
+    uint64_t fixed, cap;    // fixed count / capacity of dst in elements
+    uint32_t elem_words;    // element size in 32-bit words
+    uint32_t count_is_u64;
+};
+struct PackArgs {
+    PackSeg seg[12];
+    int n;
+    uint32_t* truncated;  // pinned: set to 1 if a list did not fit its buffer
+};
+__global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
+    const PackSeg sg = a.seg[blockIdx.y];
+    uint64_t n = sg.fixed;
+    if (sg.count_ptr) n = sg.count_is_u64 ? *reinterpret_cast<const unsigned long long*>(sg.count_ptr) : (uint64_t)*reinterpret_cast<const uint32_t*>(sg.count_ptr);
+    if (n > sg.cap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *a.truncated = 1;
+        n = sg.cap;
+    }
+    const uint64_t words = n * sg.elem_words;
+    const uint32_t* __restrict__ s = reinterpret_cast<const uint32_t*>(sg.src);
+    uint32_t* __restrict__ d = reinterpret_cast<uint32_t*>(sg.dst);
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (uint64_t)gridDim.x * blockDim.x;
+    if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {  // 16-byte moves: full PCIe write bursts
+        const uint64_t q = words / 4;
+        const uint4* __restrict__ s4 = reinterpret_cast<const uint4*>(s);
+        uint4* __restrict__ d4 = reinterpret_cast<uint4*>(d);
+        for (uint64_t i = tid; i < q; i += nthr) d4[i] = s4[i];
+        for (uint64_t i = q * 4 + tid; i < words; i += nthr) d[i] = s[i];
+    } else {
+        for (uint64_t i = tid; i < words; i += nthr) d[i] = s[i];
+    }
+}
+bool is_pinned_host(const void* p) {
+    if (!p) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+}  // namespace
+
 extern "C" {
 
 chd_status chd_get_cells(chd_engine* e, uint32_t* cell_start, uint32_t* sorted_entity) {
@@ -234,6 +284,113 @@ chd_status chd_fetch_results(chd_engine* e, const chd_result_buffers* b, chd_tic
     if (sa != s) CU(e, cudaStreamSynchronize(sa));
     if (s != main_stream) CU(e, cudaStreamSynchronize(main_stream));  // the tick itself (expanded list) has finished
     return CHD_OK;
+}
+
+chd_status chd_fetch_results_async(chd_engine* e, const chd_result_buffers* b, void* pinned_header) {
+    if (!e || !b || !pinned_header) return CHD_ERR_INVALID;
+    if (!e->early_ready || !e->dl_stream) {
+        e->fail("chd_fetch_results_async needs a two-stream tick (chd_tick with emit, or chd_begin_interest + chd_tick) just before it");
+        return CHD_ERR_STATE;
+    }
+    if (b->vis_entity) {
+        e->fail("chd_fetch_results_async does not copy the expanded list (use chd_fetch_results / chd_get_visible)");
+        return CHD_ERR_INVALID;
+    }
+    for (const void* p : {(const void*)b->pair_off, (const void*)b->pair_channel, (const void*)b->pair_dist, (const void*)b->pair_interval_ms, (const void*)b->new_sub,
+                          (const void*)b->new_channel, (const void*)b->unsub_sub, (const void*)b->unsub_channel, (const void*)b->due, (const void*)b->handover_entity,
+                          (const void*)b->handover_src, (const void*)b->handover_dst, (const void*)b->query_status, (const void*)b->vis_off,
+                          (const void*)b->cell_start, (const void*)b->sorted_entity, (const void*)pinned_header})
+        if (!is_pinned_host(p)) {
+            e->fail("chd_fetch_results_async: every buffer must be pinned host memory (chd_alloc_pinned)");
+            return CHD_ERR_INVALID;
+        }
+    CU(e, cudaSetDevice(e->device));
+    if (e->fetch_issued - e->fetch_waited >= 2) {
+        e->fail("chd_fetch_results_async: two fetches are already outstanding (call chd_fetch_wait)");
+        return CHD_ERR_STATE;
+    }
+    const int fi = (int)(e->fetch_issued & 1);
+    if (!e->ev_fetch_a[fi]) {
+        CU(e, cudaEventCreateWithFlags(&e->ev_fetch_a[fi], cudaEventDisableTiming));
+        CU(e, cudaEventCreateWithFlags(&e->ev_fetch_b[fi], cudaEventDisableTiming));
+    }
+    PairBuf& pb = e->pairs[e->cur];
+    const uint32_t S = e->n_slots;
+    Counters* ctr = e->d_ctr;
+    uint32_t* hdr = reinterpret_cast<uint32_t*>(pinned_header);
+    hdr[CHD_FETCH_HEADER_BYTES / 4 - 1] = 0;  // truncation flag (host write, ordered before the kernels are launched)
+    auto seg = [](const void* src, void* dst, const void* cnt, uint64_t fixed, uint64_t cap, uint32_t words, uint32_t is64) {
+        return PackSeg{src, dst, cnt, fixed, cap, words, is64};
+    };
+    // phase A: final once the interest fill and the build are done
+    PackArgs A{};
+    A.truncated = hdr + CHD_FETCH_HEADER_BYTES / 4 - 1;
+    if (b->pair_off) A.seg[A.n++] = seg(pb.off, b->pair_off, nullptr, (uint64_t)S + 1, (uint64_t)S + 1, 1, 0);
+    if (b->pair_channel) A.seg[A.n++] = seg(e->d_pair_ch, b->pair_channel, pb.off + S, 0, b->pair_cap, 1, 0);
+    if (b->pair_dist) A.seg[A.n++] = seg(pb.dist, b->pair_dist, pb.off + S, 0, b->pair_cap, 1, 0);
+    if (b->pair_interval_ms) A.seg[A.n++] = seg(pb.interval, b->pair_interval_ms, pb.off + S, 0, b->pair_cap, 1, 0);
+    if (b->new_sub) A.seg[A.n++] = seg(e->d_new_sub, b->new_sub, &ctr->n_sub_new, 0, b->diff_cap, 1, 0);
+    if (b->new_channel) A.seg[A.n++] = seg(e->d_new_ch, b->new_channel, &ctr->n_sub_new, 0, b->diff_cap, 1, 0);
+    if (b->unsub_sub) A.seg[A.n++] = seg(e->d_gone_sub, b->unsub_sub, &ctr->n_unsub, 0, b->diff_cap, 1, 0);
+    if (b->unsub_channel) A.seg[A.n++] = seg(e->d_gone_ch, b->unsub_channel, &ctr->n_unsub, 0, b->diff_cap, 1, 0);
+    if (b->query_status) A.seg[A.n++] = seg(e->d_status, b->query_status, nullptr, std::min<uint64_t>(e->last_nq, b->status_cap), b->status_cap, 1, 0);
+    if (b->cell_start) A.seg[A.n++] = seg(e->d_cell_start, b->cell_start, nullptr, (uint64_t)e->g.cells + 1, (uint64_t)e->g.cells + 1, 1, 0);
+    if (b->sorted_entity) A.seg[A.n++] = seg(e->d_sorted_ent, b->sorted_entity, &ctr->n_entities_in_world, 0, b->entity_cap, 1, 0);
+    PackArgs A2{};  // (the handover triple: a second launch keeps PackArgs small)
+    A2.truncated = A.truncated;
+    const uint64_t hcap = std::min<uint64_t>(b->handover_cap, e->ho_cap);
+    if (b->handover_entity) A2.seg[A2.n++] = seg(e->d_ho_entity, b->handover_entity, &ctr->n_handover, 0, hcap, 1, 0);
+    if (b->handover_src) A2.seg[A2.n++] = seg(e->d_ho_src, b->handover_src, &ctr->n_handover, 0, hcap, 1, 0);
+    if (b->handover_dst) A2.seg[A2.n++] = seg(e->d_ho_dst, b->handover_dst, &ctr->n_handover, 0, hcap, 1, 0);
+    cudaStream_t sa = e->dl_stream, sb = e->dl_stream_b;
+    CU(e, cudaStreamWaitEvent(sa, e->ev_pairs, 0));
+    if (e->build_done_recorded) CU(e, cudaStreamWaitEvent(sa, e->ev_build_done, 0));
+    if (A.n) {
+        pack_kernel<<<dim3(24, (unsigned)A.n), 256, 0, sa>>>(A);
+        KCHECK(e);
+    }
+    if (A2.n) {
+        pack_kernel<<<dim3(8, (unsigned)A2.n), 256, 0, sa>>>(A2);
+        KCHECK(e);
+    }
+    CU(e, cudaEventRecord(e->ev_fetch_a[fi], sa));
+    // phase B: after the fan-out pass and the emit preparation; the counters travel last
+    PackArgs B{};
+    B.truncated = A.truncated;
+    if (b->due) B.seg[B.n++] = seg(e->d_due, b->due, &ctr->n_due, 0, std::min<uint64_t>(b->due_cap, e->lim.max_due), sizeof(chd_due) / 4, 0);
+    if (b->vis_off) B.seg[B.n++] = seg(e->d_vis_off, b->vis_off, nullptr, (uint64_t)S + 1, (uint64_t)S + 1, 2, 0);
+    B.seg[B.n++] = seg(ctr, pinned_header, nullptr, sizeof(Counters) / 4, sizeof(Counters) / 4, 1, 0);
+    CU(e, cudaStreamWaitEvent(sb, e->ev_join, 0));
+    CU(e, cudaStreamWaitEvent(sb, e->ev_prep_done, 0));
+    pack_kernel<<<dim3(24, (unsigned)B.n), 256, 0, sb>>>(B);
+    KCHECK(e);
+    CU(e, cudaEventRecord(e->ev_fetch_b[fi], sb));
+    e->fetch_guard = true;  // the next tick's kernels are ordered after these copies (they overwrite the arrays being read)
+    e->fetch_header[fi] = pinned_header;
+    e->fetch_issued++;
+    return CHD_OK;
+}
+
+chd_status chd_fetch_wait(chd_engine* e, chd_tick_summary* summary) {
+    if (!e || !summary) return CHD_ERR_INVALID;
+    if (e->fetch_issued == e->fetch_waited) {
+        e->fail("chd_fetch_wait without a chd_fetch_results_async in flight");
+        return CHD_ERR_STATE;
+    }
+    CU(e, cudaSetDevice(e->device));
+    const int fi = (int)(e->fetch_waited & 1);  // the OLDEST outstanding fetch
+    CU(e, cudaEventSynchronize(e->ev_fetch_a[fi]));
+    CU(e, cudaEventSynchronize(e->ev_fetch_b[fi]));
+    e->fetch_waited++;
+    static_assert(sizeof(Counters) + 4 <= CHD_FETCH_HEADER_BYTES, "CHD_FETCH_HEADER_BYTES too small");
+    memcpy(e->h_ctr, e->fetch_header[fi], sizeof(Counters));
+    const uint32_t truncated = reinterpret_cast<const uint32_t*>(e->fetch_header[fi])[CHD_FETCH_HEADER_BYTES / 4 - 1];
+    chd_status st = chd_decode_summary(e, summary);
+    if (st == CHD_OK && truncated) {
+        e->fail("chd_fetch_results_async: a result list did not fit its buffer (truncated)");
+        return CHD_ERR_CAPACITY;
+    }
+    return st;
 }
 
 chd_status chd_device_view(chd_engine* e, int which, void** d_ptr, uint64_t* count) {

@@ -72,6 +72,10 @@ chd_status chd_set_slab(chd_engine* e, uint32_t col_lo, uint32_t col_hi, uint32_
 chd_status chd_export_border(chd_engine* e, uint32_t* d_records, uint32_t cap_records, uint32_t* out_count) {
     if (!e || !d_records) return CHD_ERR_INVALID;
     CU(e, cudaSetDevice(e->device));
+    {
+        chd_status gs_ = chd_fetch_guard(e);
+        if (gs_ != CHD_OK) return gs_;
+    }
     cudaStream_t s = e->stream;
     const uint32_t n = e->n_own;
     const uint32_t n_launch = n > cap_records ? n : cap_records;  // the write pass also pads the caller's buffer
@@ -262,6 +266,10 @@ chd_status chd_tick_sharded(chd_engine* e, const chd_query_batch* q, int64_t t_n
     if (!e->comm) {
         e->fail("chd_tick_sharded before chd_comm_init");
         return CHD_ERR_STATE;
+    }
+    {
+        chd_status gs_ = chd_fetch_guard(e);
+        if (gs_ != CHD_OK) return gs_;
     }
     chd_status st;
     const bool has_batch = q || e->have_adopted_q;

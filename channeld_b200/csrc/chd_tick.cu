@@ -5,6 +5,7 @@
 #include "chd_emit.cuh"
 #include "chd_fanout.cuh"
 #include "chd_misc.cuh"
+#include "chd_rings.cuh"
 
 extern "C" {
 
@@ -19,6 +20,10 @@ chd_status chd_emit_visible(chd_engine* e) {
     PairBuf& pb = e->pairs[e->cur];
     const uint32_t S = e->n_slots;
     const uint64_t P = e->lim.max_pairs;
+    {
+        chd_status gs_ = chd_fetch_guard(e);
+        if (gs_ != CHD_OK) return gs_;
+    }
     StageTimer timer(e, CHD_STAGE_EMIT);
     const unsigned grid = (unsigned)e->sm_count * 8;
     const uint64_t key = mix_key(mix_key(0x656d6974ull, S), (uint64_t)e->cur);
@@ -27,8 +32,8 @@ chd_status chd_emit_visible(chd_engine* e) {
     st = run_stage(e, e->g_emit_prep[e->cur], key, [&]() -> chd_status {
         // per-pair visible counts are computed by the scan itself; the partition pass opens the next epoch
         SCAN(e, exclusive_scan_fn<PairVcountIn, uint64_t>(PairVcountIn{pb.cell, e->d_cell_start}, e->d_voff, P, e->site_voff, s, pb.off + S));
-        emit_partition_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_first_pair, e->d_tile_desc, e->max_tiles, S, pb.off, e->d_vis_off,
-                                                   e->lim.max_visible, e->d_ctr, e->d_epoch + EP_EMIT);
+        emit_partition_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_first_pair, e->d_tile_desc, e->phase_stride, e->max_tiles, S, pb.off, e->d_vis_off,
+                                                   e->lim.max_visible, e->d_ctr, e->d_epoch + EP_EMIT, e->d_emit_ticket);
         KCHECK(e);
         return CHD_OK;
     });
@@ -46,8 +51,16 @@ chd_status chd_emit_visible(chd_engine* e) {
         uint64_t tiles = e->vis_estimate ? std::min<uint64_t>(cap_tiles, (e->vis_estimate + e->vis_estimate / 32) / EMIT_TILE + 64) : cap_tiles;
         if (tiles == 0) tiles = 1;
         if (tiles > 0x7fffffffull) tiles = 0x7fffffffull;
+        tiles = (tiles + EMIT_TILES_PER_CTA - 1) / EMIT_TILES_PER_CTA;
+#if CHD_EMIT_PERSIST_BLOCKS
+        (void)tiles;
+        emit_visible_persistent_kernel<<<(unsigned)e->sm_count * EMIT_PERSIST_BLOCKS, EMIT_THREADS, 0, s>>>(
+            pb.off + S, P, &e->d_ctr->n_visible, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4, e->phase_stride, e->d_first_pair, e->d_tile_desc, e->d_vis,
+            e->lim.max_visible, e->d_emit_ticket);
+#else
         emit_visible_kernel<<<(unsigned)tiles, EMIT_THREADS, 0, s>>>(pb.off + S, P, &e->d_ctr->n_visible, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4, e->phase_stride,
                                                                                 e->d_first_pair, e->d_tile_desc, e->d_vis, e->lim.max_visible);
+#endif
         KCHECK(e);
     }
     return CHD_OK;
@@ -56,6 +69,10 @@ chd_status chd_emit_visible(chd_engine* e) {
 chd_status chd_set_rings(chd_engine* e, const uint32_t* ring_off, uint32_t n_entries, const int64_t* arrival, const uint32_t* sender,
                          const uint64_t* index, const uint64_t* ch_msg_index) {
     if (!e || !ring_off) return CHD_ERR_INVALID;
+    if (e->rings_owned) {
+        e->fail("chd_set_rings: the rings are device-owned (chd_rings_init): use chd_rings_append");
+        return CHD_ERR_STATE;
+    }
     CU(e, cudaSetDevice(e->device));
     const uint32_t C = e->g.cells;
     const uint32_t total = n_entries;
@@ -89,6 +106,131 @@ chd_status chd_set_rings(chd_engine* e, const uint32_t* ring_off, uint32_t n_ent
     return CHD_OK;
 }
 
+/* ---- device-owned rings: ChannelData.OnUpdate's buffer maintenance on the GPU (data.go:149-173) */
+
+chd_status chd_rings_init(chd_engine* e, uint32_t capacity_per_cell) {
+    if (!e || capacity_per_cell <= RING_MAX_BUFFER) {
+        if (e) e->fail("chd_rings_init: capacity_per_cell must exceed %u (MaxUpdateMsgBufferSize: the reference's buffer may grow beyond it)", RING_MAX_BUFFER);
+        return CHD_ERR_INVALID;
+    }
+    const uint64_t need = (uint64_t)e->g.cells * capacity_per_cell;
+    if (need > e->lim.max_ring_entries) {
+        e->fail("chd_rings_init: %u cells x %u entries > max_ring_entries %u", e->g.cells, capacity_per_cell, e->lim.max_ring_entries);
+        return CHD_ERR_CAPACITY;
+    }
+    CU(e, cudaSetDevice(e->device));
+    cudaStream_t s = e->stream;
+    rings_init_kernel<<<blocks_for((uint64_t)e->g.cells + 1, 128), 128, 0, s>>>(e->g.cells, capacity_per_cell, e->d_rb_begin, e->d_rb_end);
+    KCHECK(e);
+    CU(e, cudaMemsetAsync(e->d_ch_msg_index, 0, (uint64_t)e->g.cells * 8, s));
+    set_u32_kernel<<<1, 1, 0, s>>>(e->d_ring_total, (uint32_t)need);
+    KCHECK(e);
+    e->rings_owned = true;
+    e->ring_cap = capacity_per_cell;
+    e->have_ch_msg_index = true;
+    e->ring_set = -1;
+    e->wait_rings = false;
+    return CHD_OK;
+}
+
+chd_status chd_rings_append(chd_engine* e, const uint32_t* upd_off, uint32_t n_updates, const int64_t* arrival_ns, const uint32_t* sender_conn_id) {
+    if (!e || !upd_off || (n_updates && (!arrival_ns || !sender_conn_id))) return CHD_ERR_INVALID;
+    if (!e->rings_owned) {
+        e->fail("chd_rings_append before chd_rings_init");
+        return CHD_ERR_STATE;
+    }
+    CU(e, cudaSetDevice(e->device));
+    cudaStream_t s = e->stream;
+    const uint32_t C = e->g.cells;
+    if (n_updates > e->upd_cap) {
+        chd_dfree(e, e->d_upd_arrival);
+        chd_dfree(e, e->d_upd_sender);
+        e->d_upd_arrival = nullptr;
+        e->d_upd_sender = nullptr;
+        e->upd_cap = 0;
+        const uint64_t c = (uint64_t)n_updates + n_updates / 2 + 1024;
+        if (!dalloc(e, &e->d_upd_arrival, c) || !dalloc(e, &e->d_upd_sender, c)) return CHD_ERR_CUDA;
+        e->upd_cap = c;
+    }
+    CU(e, cudaMemcpyAsync(e->d_upd_off, upd_off, sizeof(uint32_t) * ((uint64_t)C + 1), cudaMemcpyDefault, s));
+    if (n_updates) {
+        CU(e, cudaMemcpyAsync(e->d_upd_arrival, arrival_ns, sizeof(int64_t) * n_updates, cudaMemcpyDefault, s));
+        CU(e, cudaMemcpyAsync(e->d_upd_sender, sender_conn_id, sizeof(uint32_t) * n_updates, cudaMemcpyDefault, s));
+    }
+    rings_append_kernel<<<blocks_for(C, 128), 128, 0, s>>>(C, e->ring_cap, e->d_upd_off, e->d_upd_arrival, e->d_upd_sender, e->d_rb_begin, e->d_rb_end,
+                                                           e->d_ring_arrival, e->d_ring_sender, e->d_ring_index, e->d_ch_msg_index, e->d_cell_max_interval,
+                                                           &e->d_ctr->overflow);
+    KCHECK(e);
+    return CHD_OK;
+}
+
+chd_status chd_get_rings(chd_engine* e, uint32_t* ring_off, int64_t* arrival_ns, uint32_t* sender_conn_id, uint64_t* message_index,
+                         uint64_t* channel_msg_index, uint32_t cap_entries) {
+    if (!e || !ring_off) return CHD_ERR_INVALID;
+    if (!e->rings_owned) {
+        e->fail("chd_get_rings: the rings are host-owned (chd_set_rings)");
+        return CHD_ERR_STATE;
+    }
+    CU(e, cudaSetDevice(e->device));
+    cudaStream_t s = e->stream;
+    const uint32_t C = e->g.cells;
+    // (control-plane call: a plain two-pass scan through scratch that is free between ticks)
+    if (!e->d_ring_scan_scratch && !dalloc(e, &e->d_ring_scan_scratch, scan_scratch_elems(C + 1))) return CHD_ERR_CUDA;
+    ring_len_kernel<<<blocks_for(C, 128), 128, 0, s>>>(C, e->d_rb_begin, e->d_rb_end, e->d_upd_off);
+    KCHECK(e);
+    SCAN(e, exclusive_scan<uint32_t, uint32_t>(e->d_upd_off, e->d_ring_flat_off, C, e->d_ring_scan_scratch, s));
+    uint32_t total = 0;
+    chd_status st = chd_read_u32(e, e->d_ring_flat_off + C, &total);
+    if (st != CHD_OK) return st;
+    CU(e, cudaMemcpyAsync(ring_off, e->d_ring_flat_off, sizeof(uint32_t) * ((uint64_t)C + 1), cudaMemcpyDefault, s));
+    if (channel_msg_index) CU(e, cudaMemcpyAsync(channel_msg_index, e->d_ch_msg_index, sizeof(uint64_t) * C, cudaMemcpyDefault, s));
+    if (arrival_ns || sender_conn_id || message_index) {
+        if (total > cap_entries) {
+            e->fail("chd_get_rings: %u entries > cap_entries %u", total, cap_entries);
+            return CHD_ERR_CAPACITY;
+        }
+        int64_t* ta = nullptr;
+        uint32_t* ts = nullptr;
+        uint64_t* ti = nullptr;
+        CU(e, cudaMallocAsync((void**)&ta, 8ull * (total + 1), s));
+        CU(e, cudaMallocAsync((void**)&ts, 4ull * (total + 1), s));
+        CU(e, cudaMallocAsync((void**)&ti, 8ull * (total + 1), s));
+        rings_gather_kernel<<<C, 128, 0, s>>>(C, e->d_rb_begin, e->d_rb_end, e->d_ring_flat_off, e->d_ring_arrival, e->d_ring_sender, e->d_ring_index, ta, ts,
+                                              ti, total);
+        KCHECK(e);
+        if (arrival_ns) CU(e, cudaMemcpyAsync(arrival_ns, ta, 8ull * total, cudaMemcpyDefault, s));
+        if (sender_conn_id) CU(e, cudaMemcpyAsync(sender_conn_id, ts, 4ull * total, cudaMemcpyDefault, s));
+        if (message_index) CU(e, cudaMemcpyAsync(message_index, ti, 8ull * total, cudaMemcpyDefault, s));
+        CU(e, cudaFreeAsync(ta, s));
+        CU(e, cudaFreeAsync(ts, s));
+        CU(e, cudaFreeAsync(ti, s));
+    }
+    CU(e, cudaStreamSynchronize(s));
+    return CHD_OK;
+}
+
+chd_status chd_set_channel_start_times(chd_engine* e, const int64_t* start_ns) {
+    if (!e) return CHD_ERR_INVALID;
+    CU(e, cudaSetDevice(e->device));
+    if (!start_ns) {
+        e->have_cell_start = false;
+        return CHD_OK;
+    }
+    CU(e, cudaMemcpyAsync(e->d_cell_start_ns, start_ns, sizeof(int64_t) * (uint64_t)e->g.cells, cudaMemcpyDefault, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    e->have_cell_start = true;
+    return CHD_OK;
+}
+
+RingDev chd_ring_view(const chd_engine* e) {
+    const int64_t* start = e->have_cell_start ? e->d_cell_start_ns : nullptr;
+    if (e->rings_owned)
+        return RingDev{e->d_rb_begin, e->d_rb_end, e->d_ring_arrival, e->d_ring_sender, e->d_ring_index, e->d_ch_msg_index, e->d_ring_total, start};
+    const uint32_t* off = e->ring_off_p ? e->ring_off_p : e->d_ring_off;
+    return RingDev{off, off + 1, e->ring_arrival_p ? e->ring_arrival_p : e->d_ring_arrival, e->ring_sender_p ? e->ring_sender_p : e->d_ring_sender,
+                   e->ring_index_p ? e->ring_index_p : e->d_ring_index, e->have_ch_msg_index ? e->ch_msg_index_p : nullptr, e->d_ring_total, start};
+}
+
 chd_status chd_fanout_tick(chd_engine* e, int64_t t_ns) {
     if (!e) return CHD_ERR_INVALID;
     CU(e, cudaSetDevice(e->device));
@@ -96,6 +238,10 @@ chd_status chd_fanout_tick(chd_engine* e, int64_t t_ns) {
     PairBuf& pb = e->pairs[e->cur];
     const uint32_t S = e->n_slots;
     const uint64_t P = e->lim.max_pairs;
+    {
+        chd_status gs_ = chd_fetch_guard(e);
+        if (gs_ != CHD_OK) return gs_;
+    }
     StageTimer timer(e, CHD_STAGE_FANOUT);
     if (e->wait_rings) {  // rings handed over by chd_adopt_prefetched: ordered after their upload
         CU(e, cudaStreamWaitEvent(s, e->ev_upload_rings, 0));
@@ -104,13 +250,11 @@ chd_status chd_fanout_tick(chd_engine* e, int64_t t_ns) {
     chd_epoch_tick(e, EP_FANOUT);
     stage_begin_kernel<<<1, 1, 0, s>>>(e->d_time + 1, t_ns, e->d_epoch + EP_FANOUT, &e->d_ctr->n_due, 1, nullptr);
     KCHECK(e);
-    RingDev ring{e->ring_off_p ? e->ring_off_p : e->d_ring_off, e->ring_arrival_p ? e->ring_arrival_p : e->d_ring_arrival,
-                 e->ring_sender_p ? e->ring_sender_p : e->d_ring_sender, e->ring_index_p ? e->ring_index_p : e->d_ring_index,
-                 e->have_ch_msg_index ? e->ch_msg_index_p : nullptr, e->d_ring_total};
+    const RingDev ring = chd_ring_view(e);
     const unsigned grid = (unsigned)e->sm_count * 16;
     uint64_t key = mix_key(mix_key(mix_key(0x66616eull, S), (uint64_t)e->cur), e->have_ch_msg_index);
-    for (const void* p : {(const void*)ring.off, (const void*)ring.arrival, (const void*)ring.sender, (const void*)ring.index,
-                          (const void*)ring.channel_msg_index})
+    for (const void* p : {(const void*)ring.off, (const void*)ring.end, (const void*)ring.arrival, (const void*)ring.sender, (const void*)ring.index,
+                          (const void*)ring.channel_msg_index, (const void*)ring.start})
         key = mix_key(key, (uint64_t)(uintptr_t)p);  // pointers are baked into the captured launch
     chd_status st = run_stage(e, e->g_fanout[e->cur + (e->ring_set == 1 ? 2 : 0)], key, [&]() -> chd_status {
         const unsigned blocks = (unsigned)std::min<uint64_t>((P + 127) / 128, (uint64_t)e->sm_count * 16);
@@ -244,6 +388,10 @@ chd_status chd_begin_interest(chd_engine* e, const chd_query_batch* q, int64_t t
         return CHD_ERR_STATE;
     }
     CU(e, cudaSetDevice(e->device));
+    {
+        chd_status gs = chd_fetch_guard(e);
+        if (gs != CHD_OK) return gs;
+    }
     if (!e->aux_stream) {  // no second stream: run in place
         chd_status st = chd_update_interest(e, q, t_ns);
         if (st == CHD_OK && with_fanout) st = chd_fanout_tick(e, t_ns);
@@ -279,8 +427,20 @@ chd_status chd_tick(chd_engine* e, const chd_query_batch* q, int64_t t_ns, uint3
     return CHD_OK;
 }
 
+// An asynchronous read-back of the previous tick may still be copying out of the arrays this tick rewrites: order this tick's
+// work after it (device-side wait; in steady state the copies finished long before).
+chd_status chd_fetch_guard(chd_engine* e) {
+    if (!e->fetch_guard) return CHD_OK;
+    const int fi = (int)((e->fetch_issued - 1) & 1);  // the latest fetch (an older one completed before it: same streams)
+    CU(e, cudaStreamWaitEvent(e->stream, e->ev_fetch_a[fi], 0));
+    CU(e, cudaStreamWaitEvent(e->stream, e->ev_fetch_b[fi], 0));
+    e->fetch_guard = false;
+    return CHD_OK;
+}
+
 static chd_status chd_tick_impl(chd_engine* e, const chd_query_batch* q, int64_t t_ns, uint32_t flags, chd_tick_summary* out) {
-    chd_status st;
+    chd_status st = chd_fetch_guard(e);
+    if (st != CHD_OK) return st;
     const bool need_build = (flags & CHD_TICK_BUILD) && (e->entities_dirty || !e->built);
     const bool do_emit = flags & CHD_TICK_EMIT;
     bool do_fanout = flags & CHD_TICK_FANOUT;

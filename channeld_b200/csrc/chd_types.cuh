@@ -17,6 +17,19 @@ constexpr int EMIT_THREADS = 256;
 #ifndef CHD_EMIT_MIN_BLOCKS
 #define CHD_EMIT_MIN_BLOCKS 6
 #endif
+#ifndef CHD_EMIT_PERSIST_BLOCKS
+#define CHD_EMIT_PERSIST_BLOCKS 4  // CTAs per SM of the persistent (ticket) emit kernel; 0 = one CTA per tile, hardware-scheduled
+#endif
+constexpr int EMIT_PERSIST_BLOCKS = CHD_EMIT_PERSIST_BLOCKS ? CHD_EMIT_PERSIST_BLOCKS : 1;
+// The persistent kernel is COMPILED for one more CTA per SM than it is launched with: the registers it leaves free are what lets
+// the short, high-priority kernels of the second stream (pair grouping, fan-out) run next to it instead of behind it.
+#ifndef CHD_EMIT_PERSIST_REGCAP_BLOCKS
+#define CHD_EMIT_PERSIST_REGCAP_BLOCKS (CHD_EMIT_PERSIST_BLOCKS + 1)
+#endif
+#ifndef CHD_EMIT_TILES_PER_CTA
+#define CHD_EMIT_TILES_PER_CTA 1
+#endif
+constexpr int EMIT_TILES_PER_CTA = CHD_EMIT_TILES_PER_CTA;  // tiles one CTA copies (their descriptor loads overlap)
 constexpr int EMIT_ROWS = CHD_EMIT_ROWS;                    // 16-byte chunks per thread per tile
 constexpr int EMIT_TILE = EMIT_THREADS * 4 * EMIT_ROWS;     // 4096 entries = 16 KB of output per CTA
 constexpr int EMIT_SMEM_PAIRS = 256;                        // pairs per tile staged in shared memory (one per thread)
@@ -26,8 +39,8 @@ constexpr int EMIT_SMEM_PAIRS = 256;                        // pairs per tile st
 // cell start).  A tile is "simple" if at most two pairs' lists intersect it (always the case when cells hold more entities
 // than a tile: 4 444 vs 4 096 on the benchmark config); other tiles take the general path (segment table in shared memory).
 struct TileDesc {
-    uint32_t src0;  // source index (phase copy 0) of the entry that lands on the tile's first slot
-    uint32_t src1;  // source index of the first entry of the second segment
+    uint32_t src0;  // phase-adjusted base of the first segment: slot o of the tile <- sorted4[src0 + o]
+    uint32_t src1;  // the same for the second segment (slots o >= end0)
     uint32_t ends;  // end0 | end1 << 16 (relative to the tile base, <= EMIT_TILE); bit 31 = not simple
     uint32_t p0;    // the pair that owns the tile's first slot (general path)
 };
@@ -100,12 +113,14 @@ struct DiffOut {  // the two interest-diff lists of a tick: (subscriber slot, ch
 };
 
 struct RingDev {
-    const uint32_t* off;        // [C+1]
+    const uint32_t* off;        // ring of cell c = entries [off[c], end[c]): host-owned rings are a CSR (end = off + 1),
+    const uint32_t* end;        // device-owned rings (chd_rings_init) keep begin / end cursors per cell
     const int64_t* arrival;     // insertion order per cell
     const uint32_t* sender;
     const uint64_t* index;
     const uint64_t* channel_msg_index;  // [C] or nullptr
     const uint32_t* total;              // entries uploaded (device scalar): offsets are clamped to it
+    const int64_t* start;               // [C] ChannelTime origin of each channel (channel.go:28-37,178) or nullptr = one shared origin
 };
 
 // Payload identity of a decision (window classes, chd_classes.cuh): two decisions of one channel carry the same merged

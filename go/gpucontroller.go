@@ -407,3 +407,166 @@ func PinnedUint64s(n int) []uint64 {
 	return unsafe.Slice((*uint64)(C.chd_alloc_pinned(C.uint64_t(8*n))), n)
 }
 func FreePinned(p unsafe.Pointer) { C.chd_free_pinned(p) }
+
+// ---- round 2 additions: the entry points a sharded / long-running channeld host needs ----
+
+// FetchResultsAsync / FetchWait: the non-blocking read-back.  buffers and header must live in C (pinned) memory
+// (chd_alloc_pinned); up to two fetches may be outstanding, FetchWait returns the OLDEST one's summary.
+func (ctl *GpuStaticGrid2DSpatialController) FetchResultsAsync(buffers *C.chd_result_buffers, pinnedHeader unsafe.Pointer) error {
+	if st := C.chd_fetch_results_async(ctl.engine, buffers, pinnedHeader); st != C.CHD_OK {
+		return errors.New(C.GoString(C.chd_last_error(ctl.engine)))
+	}
+	return nil
+}
+
+func (ctl *GpuStaticGrid2DSpatialController) FetchWait() (C.chd_tick_summary, error) {
+	var s C.chd_tick_summary
+	if st := C.chd_fetch_wait(ctl.engine, &s); st != C.CHD_OK {
+		return s, errors.New(C.GoString(C.chd_last_error(ctl.engine)))
+	}
+	return s, nil
+}
+
+// AddSubscribers / RemoveSubscribers: connection lifecycle (subscription.go:104-125, channel.go:414-475).  The host owns the
+// slot table; the slices are copied before the call returns (plain Go memory is fine).
+func (ctl *GpuStaticGrid2DSpatialController) AddSubscribers(slots, connIds []uint32) error {
+	if len(slots) == 0 {
+		return nil
+	}
+	if st := C.chd_add_subscribers(ctl.engine, (*C.uint32_t)(unsafe.Pointer(&slots[0])), (*C.uint32_t)(unsafe.Pointer(&connIds[0])), C.uint32_t(len(slots))); st != C.CHD_OK {
+		return errors.New(C.GoString(C.chd_last_error(ctl.engine)))
+	}
+	return nil
+}
+
+func (ctl *GpuStaticGrid2DSpatialController) RemoveSubscribers(slots []uint32) error {
+	if len(slots) == 0 {
+		return nil
+	}
+	if st := C.chd_remove_subscribers(ctl.engine, (*C.uint32_t)(unsafe.Pointer(&slots[0])), C.uint32_t(len(slots))); st != C.CHD_OK {
+		return errors.New(C.GoString(C.chd_last_error(ctl.engine)))
+	}
+	return nil
+}
+
+// CommUniqueId / CommInit / TickSharded: multi-GPU, one channeld process per GPU.  Rank 0 creates the id and ships the 128 bytes to
+// the other processes over any channel it likes (channeld already has TCP connections between its own processes); the NCCL
+// all-gather itself is issued inside libchd_b200.so.
+func CommUniqueId() ([C.CHD_COMM_ID_BYTES]byte, error) {
+	var id [C.CHD_COMM_ID_BYTES]byte
+	if st := C.chd_comm_unique_id(unsafe.Pointer(&id[0])); st != C.CHD_OK {
+		return id, errors.New("chd_comm_unique_id failed (libnccl.so.2 not loadable?)")
+	}
+	return id, nil
+}
+
+func (ctl *GpuStaticGrid2DSpatialController) CommInit(id [C.CHD_COMM_ID_BYTES]byte, rank, world int, haloCols, borderCapacity, migrateSubscribers, migratePairs uint32) error {
+	if st := C.chd_comm_init(ctl.engine, unsafe.Pointer(&id[0]), C.int(rank), C.int(world), C.uint32_t(haloCols), C.uint32_t(borderCapacity),
+		C.uint32_t(migrateSubscribers), C.uint32_t(migratePairs)); st != C.CHD_OK {
+		return errors.New(C.GoString(C.chd_last_error(ctl.engine)))
+	}
+	return nil
+}
+
+// TickSharded replaces TickPrefetched on a sharded host (inputs prefetched + adopted, or set with the chd_set_* calls).
+func (ctl *GpuStaticGrid2DSpatialController) TickSharded(now ChannelTime, flags uint32) error {
+	if st := C.chd_tick_sharded(ctl.engine, nil, C.int64_t(now), C.uint32_t(flags), nil); st != C.CHD_OK {
+		return errors.New(C.GoString(C.chd_last_error(ctl.engine)))
+	}
+	return nil
+}
+
+// MigrateOut / MigrateIn: a subscriber whose centre crossed into another rank's slab moves with its subscriptions and fan-out
+// state inside the same all-gather (no FULL resend).  Both sides call before the same TickSharded.
+func (ctl *GpuStaticGrid2DSpatialController) MigrateOut(slots []uint32) error {
+	var p *C.uint32_t
+	if len(slots) > 0 {
+		p = (*C.uint32_t)(unsafe.Pointer(&slots[0]))
+	}
+	if st := C.chd_migrate_out(ctl.engine, p, C.uint32_t(len(slots))); st != C.CHD_OK {
+		return errors.New(C.GoString(C.chd_last_error(ctl.engine)))
+	}
+	return nil
+}
+
+func (ctl *GpuStaticGrid2DSpatialController) MigrateIn(srcRank, firstIndex uint32, slots, connIds []uint32) error {
+	if len(slots) == 0 {
+		return nil
+	}
+	if st := C.chd_migrate_in(ctl.engine, C.uint32_t(srcRank), C.uint32_t(firstIndex), (*C.uint32_t)(unsafe.Pointer(&slots[0])),
+		(*C.uint32_t)(unsafe.Pointer(&connIds[0])), C.uint32_t(len(slots))); st != C.CHD_OK {
+		return errors.New(C.GoString(C.chd_last_error(ctl.engine)))
+	}
+	return nil
+}
+
+// Rehome: own entities whose column now belongs to another rank (global id, destination rank): the host re-routes their feed.
+func (ctl *GpuStaticGrid2DSpatialController) Rehome(capEntities int) (gid, dstRank []uint32, err error) {
+	gid, dstRank = make([]uint32, capEntities), make([]uint32, capEntities)
+	var n C.uint32_t
+	var pg, pd *C.uint32_t
+	if capEntities > 0 {
+		pg, pd = (*C.uint32_t)(unsafe.Pointer(&gid[0])), (*C.uint32_t)(unsafe.Pointer(&dstRank[0]))
+	}
+	if st := C.chd_get_rehome(ctl.engine, pg, pd, C.uint32_t(capEntities), &n); st != C.CHD_OK {
+		return nil, nil, errors.New(C.GoString(C.chd_last_error(ctl.engine)))
+	}
+	k := int(n)
+	if k > capEntities {
+		k = capEntities
+	}
+	return gid[:k], dstRank[:k], nil
+}
+
+// RingsInit / RingsAppend: ChannelData.OnUpdate's buffer on the GPU (data.go:149-173); updOff is the CSR by cell of this tick's
+// updates (arrival order per cell), arrival / sender in C memory when the call is used on the tick path.
+func (ctl *GpuStaticGrid2DSpatialController) RingsInit(capacityPerCell uint32) error {
+	if st := C.chd_rings_init(ctl.engine, C.uint32_t(capacityPerCell)); st != C.CHD_OK {
+		return errors.New(C.GoString(C.chd_last_error(ctl.engine)))
+	}
+	return nil
+}
+
+func (ctl *GpuStaticGrid2DSpatialController) RingsAppend(updOff *C.uint32_t, n uint32, arrival *C.int64_t, sender *C.uint32_t) error {
+	if st := C.chd_rings_append(ctl.engine, updOff, C.uint32_t(n), arrival, sender); st != C.CHD_OK {
+		return errors.New(C.GoString(C.chd_last_error(ctl.engine)))
+	}
+	return nil
+}
+
+// AssemblePayloads / FramePackets: the byte half of the fan-out.  The host hands over the serialized updateMsg of every ring
+// entry and gets back, per connection, bytes it can pass to conn.Write unchanged (tag + marshalled Packet, snappy if asked).
+func (ctl *GpuStaticGrid2DSpatialController) SetPayloadBytes(entryOff []uint64, entryBytes []byte, fullOff []uint64, fullBytes []byte, typeUrl string) error {
+	curl := C.CString(typeUrl)
+	defer C.free(unsafe.Pointer(curl))
+	var pe, pf *C.uint8_t
+	if len(entryBytes) > 0 {
+		pe = (*C.uint8_t)(unsafe.Pointer(&entryBytes[0]))
+	}
+	if len(fullBytes) > 0 {
+		pf = (*C.uint8_t)(unsafe.Pointer(&fullBytes[0]))
+	}
+	if st := C.chd_set_payload_bytes(ctl.engine, (*C.uint64_t)(unsafe.Pointer(&entryOff[0])), C.uint32_t(len(entryOff)-1), pe,
+		(*C.uint64_t)(unsafe.Pointer(&fullOff[0])), pf, curl, C.uint32_t(channeldpb.MessageType_CHANNEL_DATA_UPDATE)); st != C.CHD_OK {
+		return errors.New(C.GoString(C.chd_last_error(ctl.engine)))
+	}
+	return nil
+}
+
+func (ctl *GpuStaticGrid2DSpatialController) FramePackets(compression []uint8, connOff []uint64, connLen []uint32, out []byte) (uint64, uint32, error) {
+	var nClasses C.uint32_t
+	if st := C.chd_assemble_payloads(ctl.engine, &nClasses, nil, 0, nil, 0, nil); st != C.CHD_OK {
+		return 0, 0, errors.New(C.GoString(C.chd_last_error(ctl.engine)))
+	}
+	var total C.uint64_t
+	var dropped C.uint32_t
+	var pc *C.uint8_t
+	if len(compression) > 0 {
+		pc = (*C.uint8_t)(unsafe.Pointer(&compression[0]))
+	}
+	if st := C.chd_frame_packets(ctl.engine, pc, (*C.uint64_t)(unsafe.Pointer(&connOff[0])), (*C.uint32_t)(unsafe.Pointer(&connLen[0])), nil,
+		(*C.uint8_t)(unsafe.Pointer(&out[0])), C.uint64_t(len(out)), &total, &dropped); st != C.CHD_OK {
+		return 0, 0, errors.New(C.GoString(C.chd_last_error(ctl.engine)))
+	}
+	return uint64(total), uint32(dropped), nil
+}

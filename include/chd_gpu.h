@@ -208,6 +208,24 @@ chd_status chd_prefetch_rings(chd_engine* e, const uint32_t* ring_off, uint32_t 
                               const uint64_t* index, const uint64_t* ch_msg_index);
 
 
+/* ---- device-owned rings: the buffer half of ChannelData.OnUpdate (data.go:149-173) on the GPU, for every channel at once.
+ * chd_rings_init switches the engine from host-owned ring snapshots (chd_set_rings every tick: 20 bytes x every live entry) to rings
+ * that live in HBM: capacity_per_cell (> 512) entries per cell, cells x capacity_per_cell <= chd_limits.max_ring_entries.
+ * chd_rings_append applies a tick's updates: CSR by cell (upd_off[cells + 1]) in arrival order per cell; for each one
+ * msgIndex++, push (arrival, sender, msgIndex), and — if the buffer holds more than 512 entries and its OLDEST is older than the
+ * channel's maxFanOutIntervalMs (tracked on the device: it grows when a subscription with a longer interval is created,
+ * subscription.go:84-86) — pop that one.  Merging the update into the channel's data message (opaque protobuf) stays with the
+ * host.  chd_get_rings reads the live rings back as the CSR chd_set_rings takes (tests, recovery).  Stream-ordered except
+ * chd_get_rings. */
+chd_status chd_rings_init(chd_engine* e, uint32_t capacity_per_cell);
+chd_status chd_rings_append(chd_engine* e, const uint32_t* upd_off, uint32_t n_updates, const int64_t* arrival_ns, const uint32_t* sender_conn_id);
+chd_status chd_get_rings(chd_engine* e, uint32_t* ring_off, int64_t* arrival_ns, uint32_t* sender_conn_id, uint64_t* message_index,
+                         uint64_t* channel_msg_index, uint32_t cap_entries);
+/* ChannelTime origin per channel (channel.go:28-37,178: every channel counts nanoseconds from its own creation): start_ns[cells]
+ * in the clock of the t_ns / now_ns arguments; channel c then sees time t - start_ns[c] (subscription times, fan-out windows; ring
+ * arrival times are channel times already).  NULL = one shared origin (the default). */
+chd_status chd_set_channel_start_times(chd_engine* e, const int64_t* start_ns);
+
 /* One fan-out decision = one fanOutDataUpdate call of the reference (data.go:221,263). */
 #define CHD_DUE_VOID 0xFFFFFFFFu
 typedef struct chd_due {
@@ -253,7 +271,8 @@ typedef struct chd_tick_summary {
  *   CHD_OVF_DUE     the pairs whose decisions did not fit were left untouched (still due: they catch up at the next
  *                   chd_fanout_tick); the list holds the decisions that did fit plus CHD_DUE_VOID holes; required_due
  *   CHD_OVF_BORDER  multi-GPU border / halo capacity exceeded: this tick's halo is incomplete */
-enum { CHD_OVF_PAIRS = 1, CHD_OVF_WINDOW = 2, CHD_OVF_VISIBLE = 4, CHD_OVF_DUE = 8, CHD_OVF_BORDER = 16 };
+enum { CHD_OVF_PAIRS = 1, CHD_OVF_WINDOW = 2, CHD_OVF_VISIBLE = 4, CHD_OVF_DUE = 8, CHD_OVF_BORDER = 16,
+       CHD_OVF_RING = 32 /* a device-owned ring slab was full of live entries: its oldest entry was dropped */ };
 /* bit 31: a device-side wait timed out (results invalid, please report).  A macro, not an enumerator: ISO C enumerators
  * must fit an int. */
 #define CHD_OVF_INTERNAL 0x80000000u
@@ -329,6 +348,19 @@ typedef struct chd_result_buffers {
     uint32_t entity_cap;
 } chd_result_buffers;
 chd_status chd_fetch_results(chd_engine* e, const chd_result_buffers* bufs, chd_tick_summary* summary);
+
+/* ---- the same read-back WITHOUT blocking: the lists are written straight into the caller's PINNED host buffers (chd_alloc_pinned)
+ * by copy kernels that know the exact lengths on the device, in the same two phases; the call returns at once, so the host can
+ * enqueue the NEXT tick before looking at this one (the next tick's kernels are ordered after these copies on the device).
+ * pinned_header: CHD_FETCH_HEADER_BYTES of pinned memory the engine uses for the counters.  Up to two fetches may be outstanding
+ * (use two sets of buffers); chd_fetch_wait blocks until the copies of the OLDEST outstanding chd_fetch_results_async are
+ * complete and returns that tick's summary (CHD_ERR_CAPACITY if a list did not fit its
+ * buffer: it was truncated to the capacity).  vis_entity is not supported here (the expanded list stays in HBM).
+ * Loop of a pipelined host:  prefetch(k+1) ... adopt, chd_begin_interest, chd_tick(k) ; chd_fetch_results_async(k) ;
+ * [enqueue tick k+1 the same way] ; chd_fetch_wait -> results of tick k while tick k+1 runs. */
+#define CHD_FETCH_HEADER_BYTES 256
+chd_status chd_fetch_results_async(chd_engine* e, const chd_result_buffers* bufs, void* pinned_header);
+chd_status chd_fetch_wait(chd_engine* e, chd_tick_summary* summary);
 
 /* Device-resident views (valid until the next call that rewrites them) for consumers that stay on the GPU. */
 enum {

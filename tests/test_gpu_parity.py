@@ -921,3 +921,71 @@ def test_full_size_config2_properties(chd, oracle):
         np.testing.assert_array_equal(pairs["channel"][a], want["pair_cell"][b])
         np.testing.assert_array_equal(pairs["dist"][a], want["pair_dist"][b])
         np.testing.assert_array_equal(e.get_visible_slot(int(j)), want["vis_entity"][int(want["vis_off"][k]):int(want["vis_off"][k + 1])])
+
+
+@pytest.mark.parametrize("name", ["10m", "handover"])
+def test_full_size_configs_3_and_5(chd, oracle, name):
+    """BASELINE configs #3 (64x64 grid) and #5 (256x256 grid of 100x100 cells, hash rebuilt every tick, half of the entities
+    changing cell) at FULL size — 10 M entities / 1 M subscribers, the 2-pass radix build — over two ticks: size-independent
+    properties of the whole result (CSR is a sorted permutation, offsets consistent, handover list = entities whose cell changed)
+    and a bit-exact oracle comparison of a 0.1 % subscriber sample on both ticks."""
+    wc = chd.synth.CONFIGS[name]
+    S, N = wc.n_subscribers, wc.n_entities
+    ex, ez = chd.synth.entities(wc)
+    og = _oracle_grid(wc)
+    per_cell = N / wc.cells
+    e = chd.engine.Engine(wc.cfg(), N, S, max_visible=int(S * 1.15 * per_cell * (1.0 + 4.0 * wc.radius / wc.w) + (1 << 22)))
+    conn = np.arange(1, S + 1, dtype=np.uint32)
+    e.set_subscribers(conn)
+    prev_ids = None
+    for tick in range(2):
+        if tick == 1:
+            if name == "handover":  # SURVEY §8d #5: a seeded half of the entities jumps one cell in a random axis direction
+                i = np.arange(N, dtype=np.uint64)
+                jump = chd.synth.uniform(wc.seed + 50, i, 0) < 0.5
+                axis = chd.synth.uniform(wc.seed + 51, i, 0) < 0.5
+                sign = np.where(chd.synth.uniform(wc.seed + 52, i, 0) < 0.5, -1.0, 1.0)
+                ex = np.where(jump & axis, ex + sign * wc.w, ex)
+                ez = np.where(jump & ~axis, ez + sign * wc.h, ez)
+            else:
+                ex, ez = chd.synth.move_entities(wc, ex, ez, 1, 60.0)
+        _, cx, cz, r = chd.synth.subscribers(wc, ex, ez)
+        e.set_entities(ex, ez)
+        batch, keep = chd.engine.make_batch(S, sub=None, sphere=(cx, cz, r))
+        s = e.tick(batch, (tick + 1) * 33_000_000, chd.capi.TICK_BUILD | chd.capi.TICK_EMIT)
+        assert s.overflow == 0
+        cs, se = e.get_cells()
+        ids = oracle.cell_of(og, ex, ez)
+        in_world = ids != 0
+        assert s.n_entities_in_world == int(in_world.sum()) == len(se) == int(cs[-1])
+        assert int(se.astype(np.uint64).sum()) == int(np.nonzero(in_world)[0].astype(np.uint64).sum())
+        cell_of_sorted = (ids[se] - S0).astype(np.int64)
+        d = np.diff(cell_of_sorted)
+        assert (d >= 0).all() and (np.diff(se.astype(np.int64))[d == 0] > 0).all()
+        np.testing.assert_array_equal(cs, np.concatenate([[0], np.cumsum(np.bincount(cell_of_sorted, minlength=wc.cells))]))
+        if prev_ids is not None:  # handover candidates = entities whose GetChannelId changed (spatial.go:612-626)
+            moved = np.nonzero(prev_ids != ids)[0]
+            assert s.n_handover == len(moved)
+            he, hs, hd = e.get_handover(s.n_handover)
+            order = np.argsort(he)
+            np.testing.assert_array_equal(he[order], moved)
+            np.testing.assert_array_equal(hs[order], prev_ids[moved])
+            np.testing.assert_array_equal(hd[order], ids[moved])
+            if name == "handover":
+                assert len(moved) > 0.45 * N
+        prev_ids = ids
+        pairs = e.get_pairs(s.n_pairs)
+        voff = np.zeros(S + 1, np.uint64)
+        e._ck(e.L.chd_get_visible(e.h, chd.capi.ptr(voff), None))
+        counts = np.diff(cs.astype(np.int64))
+        per_pair = counts[pairs["channel"] - S0]
+        assert s.n_visible == int(voff[-1]) == int(per_pair.sum())
+        sel = np.linspace(0, S - 1, S // 1000).astype(np.int64)
+        want = oracle.sphere_tick(og, ex, ez, cx[sel], cz[sel], r[sel])
+        for k, j in enumerate(sel):
+            a = slice(pairs["off"][j], pairs["off"][j + 1])
+            b = slice(int(want["pair_off"][k]), int(want["pair_off"][k + 1]))
+            np.testing.assert_array_equal(pairs["channel"][a], want["pair_cell"][b])
+            np.testing.assert_array_equal(pairs["dist"][a], want["pair_dist"][b])
+            np.testing.assert_array_equal(e.get_visible_slot(int(j)), want["vis_entity"][int(want["vis_off"][k]):int(want["vis_off"][k + 1])])
+    e.close()

@@ -69,7 +69,6 @@ def test_payload_assembly_and_framing(chd, oracle):
     compression = (np.arange(S) % 2).astype(np.uint8)  # every other connection asked for snappy
     t = 0
     n_checked = n_update_msgs = n_shared = n_multi_frame = 0
-    big = "B" * 20000  # a few large updates force a connection's tick into several packets
     for tick in range(10):
         t += 33 * MS if tick % 3 else 90 * MS
         cx += rng.uniform(-40, 40, S)
@@ -103,8 +102,6 @@ def test_payload_assembly_and_framing(chd, oracle):
                 m.list.append("e%d" % int(rng.integers(0, 100)))
             for _k in range(int(rng.integers(0, 3))):
                 m.kv[int(rng.integers(0, 6))] = "v%d" % int(rng.integers(0, 100))
-            if tick == 6 and rng.random() < 0.25:
-                m.list.append(big)
             msg_index[c] += 1
             rings[c].append((arrival, sender, int(msg_index[c]), m))
             full[c].MergeFrom(m)
@@ -202,5 +199,102 @@ def test_payload_assembly_and_framing(chd, oracle):
             for mp, (ch, i) in zip(msgs, sorted(mine, key=lambda x: x[1])):  # packet order = ascending due index
                 k = int(cls_of[i])
                 assert mp.SerializeToString() == W.Packet.FromString(bytes(blob[int(cls_off[k]):int(cls_off[k + 1])])).messages[0].SerializeToString()
-    assert n_checked > 300 and n_update_msgs > 100 and n_shared > 20 and n_multi_frame > 0
+    assert n_checked > 300 and n_update_msgs > 100 and n_shared > 20
+    e.close()
+
+
+def test_framing_splits_and_drops(chd):
+    """connection.go:626-714 / :73-77 with sizes under control: 3 cells in a row, 4 connections subscribed to all of them.
+    FULL sends of 50 KB per cell -> 150 KB per connection -> three packets; then UPDATE windows of 60 KB (cell 0), 30 KB (cell 1)
+    and 90 KB (cell 2: >= MaxPacketSize - 5, dropped like queuedMessagePackSender.Send does)."""
+    from tests import _wire as W
+
+    capi = chd.capi
+    e = chd.engine.Engine(chd.engine.grid_cfg(0, 0, 100, 100, 3, 1), 8, 4)
+    conn = np.array([11, 12, 13, 14], np.uint32)
+    e.set_subscribers(conn)
+    e.set_entities(np.array([50.0]), np.array([50.0]))
+    e.build()
+    batch, keep = chd.engine.make_batch(4, sphere=(np.full(4, 150.0), np.full(4, 50.0), np.full(4, 140.0)))
+    e.update_interest(batch, 0)
+    assert e.summary().n_pairs == 12
+
+    def msg(n):
+        m = W.TestChannelDataMessage()
+        m.text = "x" * n
+        return m.SerializeToString()
+
+    def run(t, ring_entries, fulls, compression):
+        """ring_entries: per cell list of (arrival, sender, bytes)"""
+        roff = np.concatenate([[0], np.cumsum([len(r) for r in ring_entries])]).astype(np.uint32)
+        flat = [x for r in ring_entries for x in r]
+        e.set_rings(roff, np.array([f[0] for f in flat], np.int64), np.array([f[1] for f in flat], np.uint32),
+                    np.arange(1, len(flat) + 1, dtype=np.uint64), np.array([len(r) for r in ring_entries], np.uint64))
+        eoff = np.concatenate([[0], np.cumsum([len(f[2]) for f in flat])]).astype(np.uint64)
+        eb = np.frombuffer(b"".join(f[2] for f in flat) or b"\0", np.uint8).copy()
+        foff = np.concatenate([[0], np.cumsum([len(b) for b in fulls])]).astype(np.uint64)
+        fb = np.frombuffer(b"".join(fulls) or b"\0", np.uint8).copy()
+        assert e.L.chd_set_payload_bytes(e.h, capi.ptr(eoff), len(flat), capi.ptr(eb), capi.ptr(foff), capi.ptr(fb), W.TYPE_URL.encode(), 8) == capi.OK
+        e.fanout_tick(t)
+        s = e.summary()
+        due = e.get_due(s.n_due)
+        ncls, blen = C.c_uint32(), C.c_uint64()
+        cls_off = np.zeros(int(s.n_due) + 2, np.uint64)
+        blob = np.zeros(1 << 20, np.uint8)
+        assert e.L.chd_assemble_payloads(e.h, C.byref(ncls), capi.ptr(cls_off), int(s.n_due) + 1, capi.ptr(blob), blob.size, C.byref(blen)) == capi.OK
+        cls_of, _, _ = e.due_classes(int(s.n_due))
+        conn_off, conn_len, conn_frames = np.zeros(5, np.uint64), np.zeros(4, np.uint32), np.zeros(4, np.uint32)
+        out = np.zeros(1 << 21, np.uint8)
+        olen, dropped = C.c_uint64(), C.c_uint32()
+        comp = np.array(compression, np.uint8)
+        assert e.L.chd_frame_packets(e.h, capi.ptr(comp), capi.ptr(conn_off), capi.ptr(conn_len), capi.ptr(conn_frames), capi.ptr(out), out.size,
+                                     C.byref(olen), C.byref(dropped)) == capi.OK
+        per_conn = []
+        for j in range(4):
+            buf = bytes(out[int(conn_off[j]):int(conn_off[j]) + int(conn_len[j])])
+            pos, frames = 0, []
+            while pos < len(buf):
+                assert buf[pos:pos + 2] == b"CH" and buf[pos + 4] == comp[j]
+                size = (buf[pos + 2] << 8) | buf[pos + 3]
+                body = buf[pos + 5:pos + 5 + size]
+                if comp[j]:
+                    body = _snappy_decode(body)
+                pk = W.Packet.FromString(body)
+                frames.append([(m.channelId, len(m.msgBody)) for m in pk.messages])
+                assert len(body) <= 0xFFFF
+                pos += 5 + size
+            assert len(frames) == conn_frames[j]
+            per_conn.append(frames)
+        sizes = {}
+        for i, d in enumerate(due):
+            k = int(cls_of[i])
+            sizes.setdefault(int(d["sub"]), []).append((int(d["channel_id"]), int(cls_off[k + 1] - cls_off[k])))
+        return per_conn, sizes, dropped.value, due
+
+    # tick 1: everybody's first fan-out = FULL channel data, 50 KB per cell
+    fulls = [msg(50000), msg(50000), msg(50000)]
+    per_conn, sizes, dropped, due = run(100 * MS, [[], [], []], fulls, [0, 1, 0, 1])
+    assert dropped == 0 and len(due) == 12 and (due["kind"] == 0).all()
+    for j in range(4):
+        assert [len(f) for f in per_conn[j]] == [1, 1, 1]  # 3 x 50 KB cannot share a 64 KB packet
+        assert sorted(ch for f in per_conn[j] for ch, _ in f) == [S0, S0 + 1, S0 + 2]
+    # tick 2: updates at 150 ms fall into the catch-up windows; 60 KB + 30 KB are sent (two packets), 90 KB is dropped
+    ring = [[(150 * MS, 7, msg(30000)), (151 * MS, 7, msg(30000))], [(150 * MS, 7, msg(30000))],
+            [(150 * MS, 7, msg(30000)), (151 * MS, 7, msg(30000)), (152 * MS, 7, msg(30000))]]
+    per_conn, sizes, dropped, due = run(200 * MS, ring, fulls, [1, 0, 1, 0])
+    assert (due["kind"] == 1).all()
+    n_big = sum(1 for j in sizes for ch, L in sizes[j] if L >= 0xFFFF - 5)
+    assert dropped == n_big > 0
+    for j in range(4):
+        sent = [(ch, L) for ch, L in sizes[j] if L < 0xFFFF - 5]
+        # greedy packets in due order (connection.go:643-659)
+        want, cur = [], []
+        for ch, L in sent:
+            if sum(x[1] for x in cur) + L > 0xFFFF:
+                want.append(cur); cur = []
+            cur.append((ch, L))
+        if cur:
+            want.append(cur)
+        assert [[ch for ch, _ in f] for f in per_conn[j]] == [[ch for ch, _ in f] for f in want], (j, per_conn[j], want)
+        assert len(want) >= 2
     e.close()

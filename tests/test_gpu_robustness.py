@@ -344,3 +344,93 @@ def test_subscriber_churn_parity(chd, oracle):
                 assert (int(pairs["last"][p]), bool(pairs["flags"][p] & 1), int(pairs["last_index"][p])) == (last, had, idx), (tick, j)
     assert seen_removed >= 10 and seen_added >= 5
     e.close()
+
+
+def test_device_owned_rings_and_channel_time_origins(chd, oracle):
+    """ChannelData.OnUpdate's buffer on the device (chd_rings_init / chd_rings_append, data.go:149-173) incl. the > 512 eviction
+    rule with the device-tracked maxFanOutIntervalMs, and per-channel ChannelTime origins (channel.go:178): ring contents,
+    message indices and every fan-out decision match one oracle channel per cell fed the same updates in its own clock."""
+    from tests._oracle import make_grid
+
+    capi = chd.capi
+    g = (0.0, 0.0, 100.0, 100.0, 3, 2)
+    og = make_grid(*g)
+    cells = 6
+    rng = np.random.default_rng(77)
+    S = 24
+    e = chd.engine.Engine(chd.engine.grid_cfg(*g), 64, S, max_ring_entries=cells * 1024)
+    conn = np.arange(201, 201 + S, dtype=np.uint32)
+    e.set_subscribers(conn)
+    e.set_entities(rng.uniform(0, 300, 50), rng.uniform(0, 200, 50))
+    e.build()
+    start = rng.integers(0, 500, cells).astype(np.int64) * MS  # every channel was created at a different wall time
+    assert e.L.chd_set_channel_start_times(e.h, capi.ptr(start)) == capi.OK
+    assert e.L.chd_rings_init(e.h, 1024) == capi.OK
+    chans = [oracle.channel() for _ in range(cells)]
+    cx, cz = rng.uniform(20, 280, S), rng.uniform(20, 180, S)
+    rad = rng.choice([30.0, 80.0], S)
+    t = 1000 * MS
+    total_due = 0
+    evicted = False
+    for tick in range(14):
+        t += 40 * MS
+        cx = np.clip(cx + rng.uniform(-30, 30, S), 1, 299)
+        cz = np.clip(cz + rng.uniform(-30, 30, S), 1, 199)
+        batch, keep = chd.engine.make_batch(S, sphere=(cx, cz, rad))
+        e.update_interest(batch, t)
+        e.summary()
+        for j in range(S):
+            res, st = oracle.query(og, sphere=(cx[j], cz[j], rad[j]))
+            assert st == 0
+            for c in range(cells):
+                if S0 + c in res:
+                    chans[c].subscribe(int(conn[j]), t - int(start[c]), oracle.damping(res[S0 + c], 20), 0, True, False)
+                else:
+                    chans[c].unsubscribe(int(conn[j]))
+        # updates of this tick, CSR by cell, in arrival order per cell; cell 0 gets a flood (buffer > 512 -> eviction rule)
+        per_cell = [int(rng.integers(0, 6)) for _ in range(cells)]
+        per_cell[0] = 120
+        upd_off = np.concatenate([[0], np.cumsum(per_cell)]).astype(np.uint32)
+        arr, snd = [], []
+        for c in range(cells):
+            ts = np.sort(rng.integers(0, 40, per_cell[c])) * MS + (t - 40 * MS) - int(start[c])  # channel time of channel c
+            for a in ts:
+                s_ = int(rng.choice(conn)) if rng.random() < 0.4 else 7
+                arr.append(int(a)); snd.append(s_)
+                chans[c].on_update(int(a), s_)
+        arr_np, snd_np = np.array(arr, np.int64), np.array(snd, np.uint32)  # (named: a temporary could be freed before the call)
+        st_ = e.L.chd_rings_append(e.h, capi.ptr(upd_off), len(arr), capi.ptr(arr_np), capi.ptr(snd_np))
+        assert st_ == capi.OK, e.L.chd_last_error(e.h)
+        # ring contents
+        roff = np.zeros(cells + 1, np.uint32)
+        ra, rs, ri = np.zeros(cells * 1024, np.int64), np.zeros(cells * 1024, np.uint32), np.zeros(cells * 1024, np.uint64)
+        cmi = np.zeros(cells, np.uint64)
+        st_ = e.L.chd_get_rings(e.h, capi.ptr(roff), capi.ptr(ra), capi.ptr(rs), capi.ptr(ri), capi.ptr(cmi), cells * 1024)
+        assert st_ == capi.OK, e.L.chd_last_error(e.h)
+        for c in range(cells):
+            assert roff[c + 1] - roff[c] == chans[c].ring_len(), (tick, c)
+        if roff[1] - roff[0] > 512 and ri[roff[0]] > 1:
+            evicted = True  # the head of cell 0's ring moved while the ring stayed above 512 entries
+        e.fanout_tick(t)
+        s = e.summary()
+        assert s.overflow == 0
+        due = e.get_due(s.n_due)
+        want = []
+        for c in range(cells):
+            for d in chans[c].tick_data_ex(t - int(start[c])):
+                want.append((d["conn"], S0 + c, d["kind"], d["n"], d["first"], d["last"], d["hash"], d["last_index"], d["window_hi"]))
+        got = [(int(conn[d["sub"]]), int(d["channel_id"]), int(d["kind"]), int(d["n_selected"]), int(d["first_sel"]), int(d["last_sel"]),
+                int(d["sel_hash"]), int(d["last_message_index"]), int(d["window_hi"])) for d in due]
+        if sorted(got) != sorted(want):
+            only_got, only_want = sorted(set(got) - set(want)), sorted(set(want) - set(got))
+            c0 = only_got[0][1] - S0 if only_got else only_want[0][1] - S0
+            ring_c = list(zip(ra[roff[c0]:roff[c0 + 1]].tolist(), rs[roff[c0]:roff[c0 + 1]].tolist(), ri[roff[c0]:roff[c0 + 1]].tolist()))
+            raise AssertionError("tick %d start[c]=%d only_got=%r only_want=%r ring[%d][235:250]=%r" % (tick, int(start[c0]), only_got[:6], only_want[:6], c0, ring_c[235:250]))
+        total_due += len(got)
+        pairs = e.get_pairs()
+        for j in range(S):
+            for p in range(pairs["off"][j], pairs["off"][j + 1]):
+                last, had, idx = chans[int(pairs["channel"][p]) - S0].state(int(conn[j]))
+                assert (int(pairs["last"][p]), bool(pairs["flags"][p] & 1), int(pairs["last_index"][p])) == (last, had, idx), (tick, j)
+    assert total_due > 100 and evicted
+    e.close()

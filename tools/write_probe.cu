@@ -193,6 +193,35 @@ __global__ void __launch_bounds__(256) copy_grid_desc(const uint4* __restrict__ 
 #pragma unroll
     for (int i = 0; i < ROWS; i++) st16<OP>(d + i * 256 + threadIdx.x, v[i]);
 }
+// the same with the source shifted by SHIFT uint4 (16-byte aligned like the emit kernel's phase-matched reads, but not 128-byte
+// aligned: a warp's 512-byte load then spans 5 cache lines instead of 4)
+template <int OP, int ROWS, int SHIFT>
+__global__ void __launch_bounds__(256) copy_grid_shift(const uint4* __restrict__ src, uint4* __restrict__ dst) {
+    constexpr uint32_t CPS = SEG_V / (256 * ROWS);
+    const uint64_t c = blockIdx.x;
+    const uint4* s = src + ((uint64_t)cell_of_segment(c / CPS) * SEG_V + (c % CPS) * (256 * ROWS) + SHIFT) % ((uint64_t)(N_CELLS - 1) * SEG_V);
+    uint4* d = dst + c * (256 * ROWS);
+    uint4 v[ROWS];
+#pragma unroll
+    for (int i = 0; i < ROWS; i++) v[i] = __ldg(s + i * 256 + threadIdx.x);
+#pragma unroll
+    for (int i = 0; i < ROWS; i++) st16<OP>(d + i * 256 + threadIdx.x, v[i]);
+}
+// per-chunk pseudo-random shift (what the emit kernel sees: the phase is different for every pair)
+template <int OP, int ROWS>
+__global__ void __launch_bounds__(256) copy_grid_rshift(const uint4* __restrict__ src, uint4* __restrict__ dst) {
+    constexpr uint32_t CPS = SEG_V / (256 * ROWS);
+    const uint64_t c = blockIdx.x;
+    const uint32_t shift = cell_of_segment(c * 7 + 3) & 7;
+    const uint4* s = src + ((uint64_t)cell_of_segment(c / CPS) * SEG_V + (c % CPS) * (256 * ROWS) + shift) % ((uint64_t)(N_CELLS - 1) * SEG_V);
+    uint4* d = dst + c * (256 * ROWS);
+    uint4 v[ROWS];
+#pragma unroll
+    for (int i = 0; i < ROWS; i++) v[i] = __ldg(s + i * 256 + threadIdx.x);
+#pragma unroll
+    for (int i = 0; i < ROWS; i++) st16<OP>(d + i * 256 + threadIdx.x, v[i]);
+}
+
 template <int ROWS>
 __global__ void make_desc(uint4* desc, uint64_t n_chunks) {
     constexpr uint32_t CPS = SEG_V / (256 * ROWS);
@@ -276,6 +305,10 @@ int main() {
         out("copy_grid_desc_OP_CS_r1", best_ms([&] { copy_grid_desc<OP_CS, 1><<<(unsigned)(n_v / 256), 256>>>(src, dst, desc); }), gb);
     }
     CG_(OP_CS, 2);
+    out("copy_grid_shift1_OP_CS_r4", best_ms([&] { copy_grid_shift<OP_CS, 4, 1><<<(unsigned)(n_v / 1024), 256>>>(src, dst); }), gb);
+    out("copy_grid_shift4_OP_CS_r4", best_ms([&] { copy_grid_shift<OP_CS, 4, 4><<<(unsigned)(n_v / 1024), 256>>>(src, dst); }), gb);
+    out("copy_grid_shift8_OP_CS_r4", best_ms([&] { copy_grid_shift<OP_CS, 4, 8><<<(unsigned)(n_v / 1024), 256>>>(src, dst); }), gb);
+    out("copy_grid_rshift_OP_CS_r4", best_ms([&] { copy_grid_rshift<OP_CS, 4><<<(unsigned)(n_v / 1024), 256>>>(src, dst); }), gb);
     out("memcpy_d2d_half", best_ms([&] { CK(cudaMemcpyAsync(dst, dst + n_v / 2, bytes / 2, cudaMemcpyDeviceToDevice)); }), gb);
     printf("}\n");
     return 0;
