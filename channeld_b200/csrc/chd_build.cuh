@@ -53,6 +53,59 @@ __global__ void __launch_bounds__(256) assign_cells_kernel(GridDev g, const doub
     }
 }
 
+// assign_cells_kernel + the first pass's radix_hist_kernel in ONE launch (single-GPU build: one launch and one pass over the keys
+// less on the critical path of a tick).  Same block decomposition as radix_hist_kernel: block b owns the contiguous slice
+// [b * per_block, (b + 1) * per_block); handover candidates are appended with one global atomic per 256-entity step.
+template <int BINS>
+__global__ void __launch_bounds__(BUILD_THREADS)
+    assign_hist_kernel(GridDev g, const double* __restrict__ x, const double* __restrict__ z, uint32_t n, uint32_t* __restrict__ key,
+                       const uint32_t* __restrict__ prev_key, HandoverOut ho, uint32_t per_block, uint32_t mask, uint32_t* __restrict__ hist,
+                       uint32_t nblocks, unsigned long long* bump_epoch) {
+    __shared__ uint32_t s_hist[BINS];
+    __shared__ uint32_t s_cnt, s_base;
+    if (bump_epoch && blockIdx.x == 0 && threadIdx.x == 0) *bump_epoch = chd_next_epoch(*bump_epoch);
+    for (int d = threadIdx.x; d < BINS; d += BUILD_THREADS) s_hist[d] = 0;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const uint32_t lo = min(n, blockIdx.x * per_block);
+    const uint32_t hi = min(n, lo + per_block);
+    for (uint32_t base = lo; base < hi; base += BUILD_THREADS) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t c = g.cells, p = g.cells, my = 0;
+        bool moved = false;
+        if (i < hi) {
+            c = cell_index(g, x[i], z[i]);
+            if (c == CHD_INVALID_CELL) c = g.cells;
+            key[i] = c;
+            atomicAdd(&s_hist[c & mask], 1u);
+            if (prev_key) {
+                p = prev_key[i];
+                moved = p != c;
+            }
+        }
+        if (prev_key) {  // block-aggregated append of the entities whose cell changed (prefix of Notify, spatial.go:612-626)
+            if (moved) my = atomicAdd(&s_cnt, 1u);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                s_base = s_cnt ? atomicAdd(ho.count, s_cnt) : 0u;
+                s_cnt = 0;
+            }
+            __syncthreads();
+            if (moved) {
+                const uint32_t slot = s_base + my;
+                if (slot < ho.cap) {
+                    ho.entity[slot] = i;
+                    ho.src_cell[slot] = p >= g.cells ? 0u : p + g.id_start;
+                    ho.dst_cell[slot] = c >= g.cells ? 0u : c + g.id_start;
+                }
+            }
+            __syncthreads();  // s_base is rewritten in the next step
+        }
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < BINS; d += BUILD_THREADS) hist[(uint32_t)d * nblocks + blockIdx.x] = s_hist[d];
+}
+
 // per-block digit histogram; hist layout [digit][block]
 template <int BINS>
 __global__ void __launch_bounds__(BUILD_THREADS)
@@ -142,6 +195,120 @@ __global__ void __launch_bounds__(BUILD_THREADS)
         }
         __syncthreads();
         for (int d = threadIdx.x; d < BINS; d += BUILD_THREADS) s_base[d] += s_tot[d];
+        __syncthreads();
+    }
+}
+
+// The same pass for the bandwidth-bound regime (N >> 1 M): the tile is first reordered by digit in SHARED memory, then written
+// out in sorted order, so consecutive threads store to consecutive addresses of a digit's run (full 32-byte sectors instead of
+// one 4-byte store per sector: the plain scatter above writes 8x the DRAM sectors it needs at 65 536 cells).  Stable, same result.
+template <int BINS>
+__global__ void __launch_bounds__(BUILD_THREADS)
+    radix_scatter_sorted_kernel(const uint32_t* __restrict__ key_in, const uint32_t* __restrict__ val_in, uint32_t n,
+                                const uint32_t* __restrict__ n_ptr, uint32_t per_block, uint32_t shift, uint32_t mask,
+                                const uint32_t* __restrict__ hist_scanned, uint32_t nblocks, uint32_t* __restrict__ key_out, uint32_t* val_out,
+                                ScatterExtras ex) {
+    __shared__ uint32_t s_base[BINS];   // global position of the next element of each digit
+    __shared__ uint32_t s_lofs[BINS];   // exclusive prefix of the tile's digit counts = local position of each digit's run
+    __shared__ uint16_t s_wcnt[BUILD_WARPS][BINS];
+    __shared__ uint32_t s_key[BUILD_TILE], s_val[BUILD_TILE];
+    __shared__ uint32_t s_scan[BUILD_WARPS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    constexpr int DPT = BINS / BUILD_THREADS;  // digits per thread in the prefix step
+    if (n_ptr) n = min(n, *n_ptr);
+    for (int d = threadIdx.x; d < BINS; d += BUILD_THREADS) {
+        const uint32_t b = hist_scanned[(uint32_t)d * nblocks + blockIdx.x];
+        s_base[d] = b;
+        if (ex.cell_start && blockIdx.x == 0) {
+            if ((uint32_t)d <= ex.cells) ex.cell_start[d] = b;
+            if ((uint32_t)d == ex.cells) *ex.n_in_world = b;
+            if (d == 0) ex.cell_start[ex.cells + 1] = n;
+        }
+    }
+    const uint32_t lo = min(n, blockIdx.x * per_block);
+    const uint32_t hi = min(n, lo + per_block);
+    for (uint32_t tile = lo; tile < hi; tile += BUILD_TILE) {
+        for (int d = threadIdx.x; d < BINS * BUILD_WARPS; d += BUILD_THREADS) (&s_wcnt[0][0])[d] = 0;
+        __syncthreads();
+        uint32_t k[BUILD_ROUNDS], v[BUILD_ROUNDS], rk[BUILD_ROUNDS];
+#pragma unroll
+        for (int r = 0; r < BUILD_ROUNDS; r++) {
+            const uint32_t i = tile + w * (32 * BUILD_ROUNDS) + r * 32 + lane;
+            const bool valid = i < hi;
+            k[r] = valid ? key_in[i] : 0u;
+            v[r] = valid ? (val_in ? val_in[i] : i) : 0u;
+            const uint32_t d = valid ? ((k[r] >> shift) & mask) : 0xFFFFFFFFu;
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            const uint32_t rank = __popc(peers & lt_mask);
+            uint32_t cnt = 0;
+            if (valid) cnt = s_wcnt[w][d];
+            __syncwarp();
+            if (valid && rank == 0) s_wcnt[w][d] = (uint16_t)(cnt + __popc(peers));
+            __syncwarp();
+            rk[r] = cnt + rank;
+        }
+        __syncthreads();
+        // per digit: warp counts -> exclusive offsets across warps; tile totals -> exclusive prefix across digits
+        uint32_t tot[DPT], sum = 0;
+#pragma unroll
+        for (int q = 0; q < DPT; q++) {
+            const int d = threadIdx.x * DPT + q;
+            uint32_t run = 0;
+#pragma unroll
+            for (int ww = 0; ww < BUILD_WARPS; ww++) {
+                const uint32_t c = s_wcnt[ww][d];
+                s_wcnt[ww][d] = (uint16_t)run;
+                run += c;
+            }
+            tot[q] = run;
+            sum += run;
+        }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_scan[w] = incl;
+        __syncthreads();
+        uint32_t pre = incl - sum;
+        for (int ww = 0; ww < w; ww++) pre += s_scan[ww];
+#pragma unroll
+        for (int q = 0; q < DPT; q++) {
+            s_lofs[threadIdx.x * DPT + q] = pre;
+            pre += tot[q];
+        }
+        __syncthreads();
+        const uint32_t count = min((uint32_t)BUILD_TILE, hi - tile);
+#pragma unroll
+        for (int r = 0; r < BUILD_ROUNDS; r++) {
+            const uint32_t i = tile + w * (32 * BUILD_ROUNDS) + r * 32 + lane;
+            if (i < hi) {
+                const uint32_t d = (k[r] >> shift) & mask;
+                const uint32_t lp = s_lofs[d] + s_wcnt[w][d] + rk[r];
+                s_key[lp] = k[r];
+                s_val[lp] = v[r];
+            }
+        }
+        __syncthreads();
+        for (uint32_t j = threadIdx.x; j < count; j += BUILD_THREADS) {
+            const uint32_t kk = s_key[j], d = (kk >> shift) & mask;
+            const uint32_t dst = s_base[d] + (j - s_lofs[d]);
+            val_out[dst] = s_val[j];
+            if (key_out) key_out[dst] = kk;
+            if (ex.phase_stride) {
+#pragma unroll
+                for (uint32_t ph = 1; ph < 4; ph++) val_out[(size_t)ph * ex.phase_stride + ph + dst] = s_val[j];
+            }
+        }
+        __syncthreads();
+        // advance the global bases by the tile's digit totals (= next digit's local offset - this digit's)
+#pragma unroll
+        for (int q = 0; q < DPT; q++) {
+            const int d = threadIdx.x * DPT + q;
+            s_base[d] += tot[q];
+        }
         __syncthreads();
     }
 }

@@ -4,26 +4,49 @@
 #include "chd_build.cuh"
 #include "chd_misc.cuh"
 
+// assign: when set, the pass's histogram kernel also computes the keys from the positions (first pass of a single-GPU build)
+struct FusedAssign {
+    const double *x, *z;
+    uint32_t* key;
+    const uint32_t* prev;
+    HandoverOut ho;
+};
 template <int BINS>
 static chd_status sort_pass(chd_engine* e, uint32_t* hist, const ScanSite& site, const uint32_t* key_in, const uint32_t* val_in, uint32_t n,
                             const uint32_t* n_ptr, uint32_t per_block, uint32_t nblocks, uint32_t shift, uint32_t bits, uint32_t* key_out,
-                            uint32_t* val_out, ScatterExtras ex, unsigned long long* bump) {
+                            uint32_t* val_out, ScatterExtras ex, unsigned long long* bump, const FusedAssign* assign = nullptr) {
     const uint32_t mask = (1u << bits) - 1u;
-    radix_hist_kernel<BINS><<<nblocks, BUILD_THREADS, 0, e->stream>>>(key_in, n, n_ptr, per_block, shift, mask, hist, nblocks, bump);
+    if (assign)
+        assign_hist_kernel<BINS><<<nblocks, BUILD_THREADS, 0, e->stream>>>(e->g, assign->x, assign->z, n, assign->key, assign->prev, assign->ho, per_block, mask,
+                                                                           hist, nblocks, bump);
+    else
+        radix_hist_kernel<BINS><<<nblocks, BUILD_THREADS, 0, e->stream>>>(key_in, n, n_ptr, per_block, shift, mask, hist, nblocks, bump);
     KCHECK(e);
     SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(hist, hist, (uint64_t)BINS * nblocks, site, e->stream));
-    radix_scatter_kernel<BINS><<<nblocks, BUILD_THREADS, 0, e->stream>>>(key_in, val_in, n, n_ptr, per_block, shift, mask, hist, nblocks,
-                                                                        key_out, val_out, ex);
+    // bandwidth-bound regime: reorder each tile by digit in shared memory first (coalesced runs); small inputs are latency-bound
+    // and take the plain scatter (fewer barriers per tile)
+    if (n > (2u << 20))
+        radix_scatter_sorted_kernel<BINS><<<nblocks, BUILD_THREADS, 0, e->stream>>>(key_in, val_in, n, n_ptr, per_block, shift, mask, hist, nblocks,
+                                                                                   key_out, val_out, ex);
+    else
+        radix_scatter_kernel<BINS><<<nblocks, BUILD_THREADS, 0, e->stream>>>(key_in, val_in, n, n_ptr, per_block, shift, mask, hist, nblocks,
+                                                                            key_out, val_out, ex);
     KCHECK(e);
     return CHD_OK;
+}
+
+static chd_status sort_pass_fused(chd_engine* e, uint32_t* hist, const ScanSite& site, const uint32_t* key_in, const uint32_t* val_in, uint32_t n,
+                                  const uint32_t* n_ptr, uint32_t per_block, uint32_t nblocks, uint32_t shift, uint32_t bits, uint32_t* key_out,
+                                  uint32_t* val_out, ScatterExtras ex, unsigned long long* bump, const FusedAssign* assign) {
+    if (bits <= 8) return sort_pass<256>(e, hist, site, key_in, val_in, n, n_ptr, per_block, nblocks, shift, bits, key_out, val_out, ex, bump, assign);
+    return sort_pass<1024>(e, hist, site, key_in, val_in, n, n_ptr, per_block, nblocks, shift, bits, key_out, val_out, ex, bump, assign);
 }
 
 chd_status chd_sort_pass_any(chd_engine* e, uint32_t* hist, const ScanSite& site, const uint32_t* key_in, const uint32_t* val_in,
                                 uint32_t n, const uint32_t* n_ptr, uint32_t per_block, uint32_t nblocks, uint32_t shift, uint32_t bits,
                                 uint32_t* key_out, uint32_t* val_out, ScatterExtras ex,
                                 unsigned long long* bump) {
-    if (bits <= 8) return sort_pass<256>(e, hist, site, key_in, val_in, n, n_ptr, per_block, nblocks, shift, bits, key_out, val_out, ex, bump);
-    return sort_pass<1024>(e, hist, site, key_in, val_in, n, n_ptr, per_block, nblocks, shift, bits, key_out, val_out, ex, bump);
+    return sort_pass_fused(e, hist, site, key_in, val_in, n, n_ptr, per_block, nblocks, shift, bits, key_out, val_out, ex, bump, nullptr);
 }
 
 extern "C" {
@@ -176,11 +199,9 @@ chd_status chd_assign_cells(chd_engine* e) {
     return st;
 }
 
-chd_status chd_assign_cells_impl(chd_engine* e) {
-    CU(e, cudaSetDevice(e->device));
-    if (e->assigned) return CHD_OK;
-    // handover detection compares against the keys of the previous assignment (same entity count):
-    // the buffers are swapped, never copied.
+// host-side half of a cell assignment: the key buffers swap (handover detection compares against the keys of the previous
+// assignment, same entity count; swapped, never copied), the handover counter is zeroed.  Returns the previous keys or nullptr.
+static chd_status assign_prepare(chd_engine* e, uint32_t** prev_out, HandoverOut* ho) {
     uint32_t* prev = nullptr;
     if (e->have_prev_key) {
         uint32_t* t = e->d_key;
@@ -188,8 +209,19 @@ chd_status chd_assign_cells_impl(chd_engine* e) {
         e->d_prev_key = t;
         prev = e->d_prev_key;
     }
-    HandoverOut ho{e->d_ho_entity, e->d_ho_src, e->d_ho_dst, &e->d_ctr->n_handover, e->ho_cap};
+    *ho = HandoverOut{e->d_ho_entity, e->d_ho_src, e->d_ho_dst, &e->d_ctr->n_handover, e->ho_cap};
     CU(e, cudaMemsetAsync(&e->d_ctr->n_handover, 0, 4, e->stream));
+    *prev_out = prev;
+    return CHD_OK;
+}
+
+chd_status chd_assign_cells_impl(chd_engine* e) {
+    CU(e, cudaSetDevice(e->device));
+    if (e->assigned) return CHD_OK;
+    uint32_t* prev = nullptr;
+    HandoverOut ho{};
+    chd_status st = assign_prepare(e, &prev, &ho);
+    if (st != CHD_OK) return st;
     if (e->n_own) {
         assign_cells_kernel<<<blocks_for(e->n_own, 256), 256, 0, e->stream>>>(e->g, e->pos_x ? e->pos_x : e->d_x, e->pos_z ? e->pos_z : e->d_z,
                                                                               e->n_own, e->d_key, prev, ho);
@@ -203,9 +235,24 @@ chd_status chd_assign_cells_impl(chd_engine* e) {
 
 static chd_status build_enqueue(chd_engine* e, bool with_assign) {
     chd_status st;
+    FusedAssign fa{};
+    const FusedAssign* fap = nullptr;
     if (with_assign) {
-        st = chd_assign_cells_impl(e);
-        if (st != CHD_OK) return st;
+        if (!e->assigned && e->n_own && !e->halo_on_device) {
+            // single-GPU build: GetChannelId per entity is fused into the first pass's histogram kernel
+            uint32_t* prev = nullptr;
+            HandoverOut ho{};
+            st = assign_prepare(e, &prev, &ho);
+            if (st != CHD_OK) return st;
+            fa = FusedAssign{e->pos_x ? e->pos_x : e->d_x, e->pos_z ? e->pos_z : e->d_z, e->d_key, prev, ho};
+            fap = &fa;
+            e->have_prev_key = true;
+            e->n_halo = 0;
+            e->assigned = true;
+        } else {
+            st = chd_assign_cells_impl(e);
+            if (st != CHD_OK) return st;
+        }
     }
     // multi-GPU: the halo count stays on the device (d_n_build = own + kept halo records); launches are sized for
     // the entity capacity and blocks beyond the live length idle.
@@ -226,17 +273,20 @@ static chd_status build_enqueue(chd_engine* e, bool with_assign) {
     // Phase copies: fused into the final scatter when the build is latency-bound (small N: one launch less), written by
     // a separate fully-coalesced pass when it is bandwidth-bound (large N: the fused variant does 4 scattered 4-byte
     // stores per entity; measured 325 us vs 175 + ~30 us at N = 10 M).
-    const bool fuse_phases = n <= (2u << 20);
+#ifndef CHD_BUILD_FUSE_PHASES_MAX_N
+#define CHD_BUILD_FUSE_PHASES_MAX_N (2u << 20)
+#endif
+    const bool fuse_phases = n <= (uint32_t)CHD_BUILD_FUSE_PHASES_MAX_N;
     const uint32_t fused_stride = fuse_phases ? e->phase_stride : 0u;
     if (passes == 1) {
         // single pass: digit == key, so the scatter also publishes the CSR offsets
         ScatterExtras ex{fused_stride, e->d_cell_start, C, &e->d_ctr->n_entities_in_world};
-        st = chd_sort_pass_any(e, e->d_hist, e->site_hist, e->d_key, vals, n, n_ptr, per_block, nblocks, 0, bits0, nullptr, e->d_sorted_ent, ex,
-                           e->d_epoch + EP_BUILD);
+        st = sort_pass_fused(e, e->d_hist, e->site_hist, e->d_key, vals, n, n_ptr, per_block, nblocks, 0, bits0, nullptr, e->d_sorted_ent, ex,
+                             e->d_epoch + EP_BUILD, fap);
         if (st != CHD_OK) return st;
     } else {
-        st = chd_sort_pass_any(e, e->d_hist, e->site_hist, e->d_key, vals, n, n_ptr, per_block, nblocks, 0, bits0, e->d_tmp_key, e->d_tmp_val,
-                           ScatterExtras{0, nullptr, 0, nullptr}, e->d_epoch + EP_BUILD);
+        st = sort_pass_fused(e, e->d_hist, e->site_hist, e->d_key, vals, n, n_ptr, per_block, nblocks, 0, bits0, e->d_tmp_key, e->d_tmp_val,
+                             ScatterExtras{0, nullptr, 0, nullptr}, e->d_epoch + EP_BUILD, fap);
         if (st != CHD_OK) return st;
         ScatterExtras ex{fused_stride, nullptr, C, nullptr};
         st = chd_sort_pass_any(e, e->d_hist, e->site_hist_b, e->d_tmp_key, e->d_tmp_val, n, n_ptr, per_block, nblocks, bits0, bits1, e->d_sorted_key,

@@ -34,24 +34,70 @@ def column_of(x, offx: float, w: float, cols: int):
     return np.where((c >= 0) & (c < cols), c, -1).astype(np.int64)
 
 
-class ShardedTick:
-    """One tick of the sharded pipeline on this rank.
+class SlotTable:
+    """Host-managed subscriber slots of every rank (the engine's slots are the host's to assign: chd_add_subscribers /
+    chd_migrate_in name them).  Every process of a multi-rank host keeps the tables of ALL ranks (routing decisions are a pure
+    function of the subscribers' positions, so they are computed identically everywhere: no host communication)."""
 
-    engine   : object with set_entities/export_border/import_halo/build (channeld_b200.engine.Engine, or a CPU
-               stand-in in the gloo tests)
-    gather   : callable(local_records [cap,2] -> all_records [world*cap,2]) — torch.distributed all_gather
-    """
+    def __init__(self, world: int):
+        self.world = world
+        self.owner = {}                              # subscriber -> rank
+        self.slot = {}                               # subscriber -> local slot on its rank
+        self.at = [dict() for _ in range(world)]     # per rank: slot -> subscriber
+        self._free = [list() for _ in range(world)]
+        self._used = [0] * world
 
-    def __init__(self, engine, rank, world, border_cap, gather):
-        self.e, self.rank, self.world, self.cap, self.gather = engine, rank, world, border_cap, gather
+    def take(self, rank: int) -> int:
+        if self._free[rank]:
+            return self._free[rank].pop()
+        self._used[rank] += 1
+        return self._used[rank] - 1
 
-    def step(self, x, z, records_local):
-        self.e.set_entities(x, z)
-        if self.world > 1:
-            n = self.e.export_border(records_local, self.cap)
-            allrec = self.gather(records_local)
-            self.e.import_halo(allrec, self.cap * self.world, self.rank * self.cap, self.cap)
-        else:
-            n = 0
-        self.e.build()
-        return n
+    def release(self, rank: int, slots):
+        """Slots vacated by a tick's emigrants are reusable from the NEXT tick on (the engine frees them in that tick's update)."""
+        self._free[rank] += list(slots)
+
+    def place(self, j, rank: int) -> int:
+        s = self.take(rank)
+        self.owner[j], self.slot[j] = rank, s
+        self.at[rank][s] = j
+        return s
+
+    def remove(self, j):
+        rank, s = self.owner.pop(j), self.slot.pop(j)
+        del self.at[rank][s]
+        return rank, s
+
+
+def plan_migrations(table: SlotTable, new_owner):
+    """One tick's routing changes.  new_owner: dict / sequence subscriber -> rank that owns its centre's column NOW.
+    Returns (arrivals, out_lists, in_calls, vacated):
+      arrivals[rank]   = [(subscriber, slot)] first placements                      -> chd_add_subscribers
+      out_lists[rank]  = [subscriber] emigrants in blob-record order                -> chd_migrate_out(vacated[rank])
+      in_calls         = [(dst, src, first_index, [(subscriber, slot)])]            -> chd_migrate_in(dst: src, first_index, slots, conns)
+      vacated[rank]    = the emigrants' old slots (release them after the tick)
+    and applies the changes to `table`.  Records of one source rank are grouped by destination, so each (src, dst) pair is one
+    contiguous run of src's blob."""
+    world = table.world
+    items = new_owner.items() if hasattr(new_owner, "items") else enumerate(new_owner)
+    arrivals = [[] for _ in range(world)]
+    moves = {}
+    for j, r in items:
+        r = int(r)
+        if j not in table.owner:
+            arrivals[r].append(j)
+        elif table.owner[j] != r:
+            moves.setdefault((table.owner[j], r), []).append(j)
+    out_lists = [[] for _ in range(world)]
+    in_calls = []
+    for (a, b) in sorted(moves):
+        in_calls.append([b, a, len(out_lists[a]), list(moves[(a, b)])])
+        out_lists[a] += moves[(a, b)]
+    vacated = [[table.slot[j] for j in out_lists[a]] for a in range(world)]
+    for a in range(world):
+        for j in out_lists[a]:
+            table.remove(j)
+    for call in in_calls:
+        call[3] = [(j, table.place(j, call[0])) for j in call[3]]
+    arrivals = [[(j, table.place(j, r)) for j in arrivals[r]] for r in range(world)]
+    return arrivals, out_lists, [tuple(c) for c in in_calls], vacated

@@ -73,12 +73,9 @@ def main():
         e1.set_stream(stream.cuda_stream)
         conn, cx, cz, r = synth.subscribers(wc, x, z, radius)
         e1.set_subscribers(conn)
-        # host-side routing tables: subscriber j -> (owner rank, local slot on that rank); every process computes all of them
-        owner = np.full(n_sub, -1, np.int64)
-        slot_of = np.full(n_sub, -1, np.int64)
-        free = [list() for _ in range(world)]
-        used = [0] * world
-        sub_at = [dict() for _ in range(world)]  # per rank: local slot -> subscriber j
+        # host-side routing (channeld_b200/sharding.py): subscriber j -> (owner rank, local slot); every process computes all ranks' tables
+        table = sharding.SlotTable(world)
+        last_owner = np.zeros(n_sub, np.int64)
         ring_state = None
         n_mig_total = n_rehome_total = 0
         with torch.cuda.stream(stream):
@@ -88,50 +85,18 @@ def main():
                     x, z = synth.move_entities(wc, x, z, tick, max_move)  # entities (and the subscribers standing on them) drift
                 conn, cx, cz, r = synth.subscribers(wc, x, z, radius)
                 col = sharding.column_of(cx, wc.offx, wc.w, wc.cols)
-                new_owner = np.where(col >= 0, sharding.owner_of_column(col, wc.cols, world), np.where(owner >= 0, owner, 0))
+                new_owner = np.where(col >= 0, sharding.owner_of_column(col, wc.cols, world), last_owner)  # out of the world: stays where it was
+                last_owner = new_owner
                 # ---- subscriber routing / migration (identical decisions on every rank)
-                arrivals = [[] for _ in range(world)]      # first placement: (j)
-                moves = {}                                  # (src, dst) -> [j...]
-                for j in np.nonzero(new_owner != owner)[0]:
-                    if owner[j] < 0:
-                        arrivals[new_owner[j]].append(int(j))
-                    else:
-                        moves.setdefault((int(owner[j]), int(new_owner[j])), []).append(int(j))
-                out_lists = {a: [] for a in range(world)}   # per source rank: emigrants in record order (grouped by destination)
-                in_calls = []                               # (dst, src, first_index, [j...])
-                for (a, b) in sorted(moves):
-                    in_calls.append((b, a, len(out_lists[a]), moves[(a, b)]))
-                    out_lists[a] += moves[(a, b)]
-
-                def take_slot(rk):
-                    if free[rk]:
-                        return free[rk].pop()
-                    used[rk] += 1
-                    return used[rk] - 1
-
-                # frees happen after this tick's update: a slot vacated now is reusable from the next tick on
-                vacated = {a: [int(slot_of[j]) for j in out_lists[a]] for a in range(world)}
-                if rank in out_lists and out_lists[rank]:
+                arrivals, out_lists, in_calls, vacated = sharding.plan_migrations(table, new_owner)
+                if out_lists[rank]:
                     e.migrate_out(np.array(vacated[rank], np.uint32))
-                for a in range(world):
-                    for j in out_lists[a]:
-                        del sub_at[a][int(slot_of[j])]
-                for (b, a, first, js) in in_calls:
-                    slots = [take_slot(b) for _ in js]
-                    for j, s_ in zip(js, slots):
-                        owner[j], slot_of[j] = b, s_
-                        sub_at[b][s_] = j
-                    if b == rank:
-                        e.migrate_in(a, first, np.array(slots, np.uint32), conn[js])
-                for b in range(world):
-                    if arrivals[b]:
-                        slots = [take_slot(b) for _ in arrivals[b]]
-                        for j, s_ in zip(arrivals[b], slots):
-                            owner[j], slot_of[j] = b, s_
-                            sub_at[b][s_] = j
-                        if b == rank:
-                            e.add_subscribers(np.array(slots, np.uint32), conn[arrivals[b]])
-                n_mig_total += sum(len(v) for v in out_lists.values())
+                for (dst, src, first, pairs_) in in_calls:
+                    if dst == rank:
+                        e.migrate_in(src, first, np.array([s_ for _, s_ in pairs_], np.uint32), conn[[j for j, _ in pairs_]])
+                if arrivals[rank]:
+                    e.add_subscribers(np.array([s_ for _, s_ in arrivals[rank]], np.uint32), conn[[j for j, _ in arrivals[rank]]])
+                n_mig_total += sum(len(v) for v in out_lists)
                 # ---- update rings (global cells, same on every rank)
                 ring_state, roff, rarr, rsnd, ridx, rcmi = synth.update_rings(wc, tick, t_ns, TICK, 6, n_sub, ring_len=32, state=ring_state)
                 e.set_rings(roff, rarr, rsnd, ridx, rcmi)
@@ -139,12 +104,12 @@ def main():
                 # ---- the sharded tick
                 e.set_entities(x[mine], z[mine])
                 e.set_entity_ids(mine.astype(np.uint32))
-                my_slots = np.array(sorted(sub_at[rank]), np.uint32)
-                my_subs = np.array([sub_at[rank][int(s_)] for s_ in my_slots], np.int64)
+                my_slots = np.array(sorted(table.at[rank]), np.uint32)
+                my_subs = np.array([table.at[rank][int(s_)] for s_ in my_slots], np.int64)
                 batch, keep = engine.make_batch(len(my_slots), sub=my_slots, sphere=(cx[my_subs], cz[my_subs], r[my_subs]))
                 s = e.tick_sharded(batch, t_ns, capi.TICK_ALL)
                 for a in range(world):
-                    free[a] += vacated[a]
+                    table.release(a, vacated[a])
                 # ---- the single-GPU reference tick
                 e1.set_entities(x, z)
                 b1, k1 = engine.make_batch(n_sub, sphere=(cx, cz, r))
@@ -187,7 +152,7 @@ def main():
                 n_rehome_total += sum(len(v[0]) for v in allre)
                 print("rank %d %s r=%g tick %d: own=%d subs=%d/%d checked=%d mismatches=%d migrated=%d rehomed=%d" %
                       (rank, name, radius, tick, len(mine), len(my_slots), n_sub, len(my_slots), bad,
-                       sum(len(v) for v in out_lists.values()), sum(len(v[0]) for v in allre)), flush=True)
+                       sum(len(v) for v in out_lists), sum(len(v[0]) for v in allre)), flush=True)
                 # ownership invariant after re-homing: every in-world entity sits on the owner of its column
                 ent_owner = sharding.owner_of_column(sharding.column_of(x, wc.offx, wc.w, wc.cols), wc.cols, world)
                 in_world = sharding.column_of(x, wc.offx, wc.w, wc.cols) >= 0

@@ -1,9 +1,8 @@
-"""N>1 control flow on CPU: X-slab placement + border all-gather + halo import, world_size 2 over gloo.
-
-The engine is replaced by a CPU stand-in that implements the same four calls with the oracle (the checker);
-the thing under test is the host logic in channeld_b200/sharding.py — slab ownership, the exported border set,
-the skip-own-segment convention and that the union over ranks of per-subscriber visible sets equals the
-single-rank answer."""
+"""N>1 host logic on CPU, world_size 2 over gloo (channeld_b200/sharding.py: the code tests/run_multigpu_parity.py and a sharded
+host run around chd_tick_sharded): slab ownership, the exported border set and the skip-own-segment convention (the engine is
+replaced by a CPU stand-in that implements export / import / build with the oracle, the checker), that the union over ranks of
+per-subscriber visible sets equals the single-rank answer, and the subscriber routing plan (SlotTable / plan_migrations):
+identical on every rank without communication, every subscriber on the owner of its column, state carried through blobs."""
 import os
 import socket
 
@@ -105,9 +104,12 @@ def _worker(rank, world, port, q):
             dist.all_gather_into_tensor(out, t)
             return out.numpy().view(np.uint32).reshape(-1, 2)
 
-        tick = sharding.ShardedTick(eng, rank, world, cap, gather)
         rec = np.zeros((cap, 2), np.uint32)
-        n_exported = tick.step(ex2[mine], ez2[mine], rec)
+        # the sequence chd_tick_sharded runs inside the library: assign -> export border -> ONE all-gather -> import halo -> build
+        eng.set_entities(ex2[mine], ez2[mine])
+        n_exported = eng.export_border(rec, cap)
+        eng.import_halo(gather(rec), cap * world, rank * cap, cap)
+        eng.build()
         # subscribers whose centre column (after the move) is in this slab are answered here
         conn, cx, cz, r = synth.subscribers(wc, ex2, ez2, radius)
         sub_col = sharding.column_of(cx, wc.offx, wc.w, wc.cols)
@@ -142,3 +144,84 @@ def test_sharded_tick_world2_gloo():
     assert all(r[1] for r in res), res
     assert all(r[2] > 0 and r[4] > 0 for r in res), res  # both ranks exported and adopted border entities
     assert sum(r[3] for r in res) > 250  # (nearly) every subscriber was answered by exactly one rank
+
+
+def _migration_worker(rank, world, port, q):
+    import pickle
+
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cols, n_sub = 15, 400
+        rng = np.random.default_rng(11)  # same stream on every rank: routing needs no communication
+        col = rng.integers(0, cols, n_sub)
+        table = sharding.SlotTable(world)
+        state = {}          # this rank's "engine": slot -> (subscriber, fan-out state token)
+        plans = []
+        for tick in range(8):
+            if tick:
+                col = np.clip(col + rng.integers(-2, 3, n_sub), 0, cols - 1)
+            new_owner = sharding.owner_of_column(col, cols, world)
+            arrivals, out_lists, in_calls, vacated = sharding.plan_migrations(table, new_owner)
+            plans.append((arrivals, out_lists, in_calls, vacated))
+            # what chd_migrate_out / the all-gather / chd_migrate_in do, with python objects: blob = emigrants' state in record order
+            blob = [state.pop(s_) for s_ in vacated[rank]]
+            assert [b[0] for b in blob] == out_lists[rank]
+            blobs = [None] * world
+            dist.all_gather_object(blobs, blob)
+            for (dst, src, first, pairs_) in in_calls:
+                if dst == rank:
+                    for k, (j, s_) in enumerate(pairs_):
+                        rec = blobs[src][first + k]
+                        assert rec[0] == j and s_ not in state
+                        state[s_] = rec
+            for (j, s_) in arrivals[rank]:
+                assert s_ not in state
+                state[s_] = (j, "born@%d" % tick)
+            for a in range(world):
+                table.release(a, vacated[a])
+            # invariants: every subscriber on the owner of its column, tables and engine agree, nobody lost or duplicated
+            mine = {j for j in range(n_sub) if new_owner[j] == rank}
+            assert {v[0] for v in state.values()} == mine == set(table.at[rank].values())
+            assert all(table.at[rank][s_] == v[0] for s_, v in state.items())
+            assert all(v[1].startswith("born@") for v in state.values())  # state travelled intact
+        # the plan is the same on every rank
+        digests = [None] * world
+        dist.all_gather_object(digests, pickle.dumps(plans))
+        q.put((rank, len(set(digests)) == 1, sum(len(p[1][rank]) for p in plans)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_migration_plan_world2_gloo():
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_migration_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), res
+    assert all(r[2] > 10 for r in res), res  # both ranks sent subscribers away
+
+
+def test_plan_migrations_groups_records_by_destination():
+    t = sharding.SlotTable(3)
+    arrivals, out_lists, in_calls, vacated = sharding.plan_migrations(t, {10: 0, 11: 0, 12: 1, 13: 2})
+    assert [len(a) for a in arrivals] == [2, 1, 1] and not any(out_lists) and not in_calls
+    arrivals, out_lists, in_calls, vacated = sharding.plan_migrations(t, {10: 2, 11: 1, 12: 1, 13: 0})
+    assert out_lists == [[11, 10], [], [13]]  # rank 0's records: destination 1 first, then destination 2
+    assert [(d, s_, f, [j for j, _ in p]) for d, s_, f, p in in_calls] == [(1, 0, 0, [11]), (2, 0, 1, [10]), (0, 2, 0, [13])]
+    assert vacated == [[1, 0], [], [0]] and t.owner == {10: 2, 11: 1, 12: 1, 13: 0}
+    # a slot vacated this tick is not reused in the same tick
+    assert t.slot[13] == 2 and t.slot[10] == 1 and t.slot[11] == 1
