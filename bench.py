@@ -221,6 +221,22 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # run the tick driver on the GPU's socket: pinned staging memory is then node-local by first touch (what `numactl
+    # --cpunodebind` does for a production host); the CPU baseline leg gets the full mask back
+    full_mask, numa = os.sched_getaffinity(0), None
+    try:
+        node = capi.lib().chd_device_numa_node(local)
+        if node >= 0:
+            cpus = set()
+            for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus |= set(range(int(a), int(b or a) + 1))
+            cpus &= full_mask
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                numa = {"gpu_numa_node": node, "driver_cpus": len(cpus)}
+    except Exception as ex_:  # noqa: BLE001
+        print("numa binding skipped: %r" % (ex_,), file=sys.stderr)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -703,6 +719,8 @@ def run_ours(args):
                          "window_classes_rank0": n_classes, "window_classes_call_ms": classes_ms},
             "parity_gate": gate,
         }
+        out["host"] = numa
+        os.sched_setaffinity(0, full_mask)  # the CPU legs use every host thread
         if world == 1 and not args.no_cpu_baseline:
             from tests import _oracle
 

@@ -111,7 +111,7 @@ class TickSummary(C.Structure):
 # every symbol include/chd_gpu.h declares (checked by tests/test_abi.py against the header text)
 SYMBOLS = [
     "chd_abi_version", "chd_default_limits", "chd_create", "chd_destroy", "chd_last_error", "chd_set_stream", "chd_sync",
-    "chd_alloc_pinned", "chd_free_pinned", "chd_cell_of", "chd_cell_of_valid", "chd_set_entities", "chd_prefetch_entities", "chd_prefetch_queries", "chd_prefetch_rings", "chd_adopt_prefetched", "chd_entity_buffers", "chd_set_entity_count",
+    "chd_alloc_pinned", "chd_free_pinned", "chd_device_numa_node", "chd_cell_of", "chd_cell_of_valid", "chd_set_entities", "chd_prefetch_entities", "chd_prefetch_queries", "chd_prefetch_rings", "chd_adopt_prefetched", "chd_entity_buffers", "chd_set_entity_count",
     "chd_assign_cells", "chd_build", "chd_set_subscribers", "chd_query_channel_ids", "chd_update_interest",
     "chd_emit_visible", "chd_set_rings", "chd_fanout_tick", "chd_summary", "chd_tick", "chd_begin_interest", "chd_get_cells", "chd_get_pairs",
     "chd_get_query_status", "chd_get_diff", "chd_get_visible", "chd_get_visible_slot", "chd_get_due", "chd_fetch_results", "chd_get_handover", "chd_device_view",
@@ -150,6 +150,8 @@ def lib():
     L.chd_sync.argtypes = [vp]
     L.chd_alloc_pinned.restype = vp
     L.chd_alloc_pinned.argtypes = [C.c_uint64]
+    L.chd_device_numa_node.restype = C.c_int
+    L.chd_device_numa_node.argtypes = [C.c_int]
     L.chd_free_pinned.restype = None
     L.chd_free_pinned.argtypes = [vp]
     L.chd_cell_of.restype = C.c_int

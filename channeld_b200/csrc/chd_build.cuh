@@ -313,6 +313,21 @@ __global__ void __launch_bounds__(BUILD_THREADS)
     }
 }
 
+// single-pass builds: the cell CSR offsets straight from the scanned histogram (block 0's bases are the global exclusive counts
+// per key), published BEFORE the scatter runs so that the emit preparation can overlap it
+__global__ void __launch_bounds__(256) publish_cell_start_kernel(const uint32_t* __restrict__ hist_scanned, uint32_t nblocks, uint32_t cells, uint32_t n,
+                                                                 const uint32_t* __restrict__ n_ptr, uint32_t* __restrict__ cell_start,
+                                                                 uint32_t* __restrict__ n_in_world) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_ptr) n = min(n, *n_ptr);
+    if (d <= cells) {
+        const uint32_t b = hist_scanned[d * nblocks];
+        cell_start[d] = b;
+        if (d == cells) *n_in_world = b;  // keys == cells mark out-of-world entities
+    }
+    if (d == 0) cell_start[cells + 1] = n;
+}
+
 // cell_start[c] = first sorted position whose key >= c, for c in [0, C+1]; cell_start[C+1] = n.
 __global__ void __launch_bounds__(256)
     cell_bounds_kernel(const uint32_t* __restrict__ sorted_key, uint32_t n, const uint32_t* __restrict__ n_ptr, uint32_t cells,

@@ -31,14 +31,10 @@ __global__ void __launch_bounds__(256)
                           const uint32_t* __restrict__ pair_cell, const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ first_pair,
                           TileDesc* __restrict__ desc, uint32_t stride, uint64_t max_tiles, uint32_t n_slots, const uint32_t* __restrict__ pair_off,
                           uint64_t* __restrict__ vis_off, uint64_t vis_cap, Counters* __restrict__ ctr, unsigned long long* bump_epoch,
-                          unsigned long long* __restrict__ ticket) {
+                          uint32_t tile) {
     const uint64_t n = min((uint64_t)*n_pairs_ptr, pair_cap);
-    // last kernel of the emit preparation: open the NEXT execution's scan epoch (the scan of this one has completed) and
-    // reset the tile ticket of the persistent copy kernel
-    if (bump_epoch && blockIdx.x == 0 && threadIdx.x == 0) {
-        *bump_epoch = chd_next_epoch(*bump_epoch);
-        if (ticket) *ticket = 0;
-    }
+    // last kernel of the emit preparation: open the NEXT execution's scan epoch (the scan of this one has completed)
+    if (bump_epoch && blockIdx.x == 0 && threadIdx.x == 0) *bump_epoch = chd_next_epoch(*bump_epoch);
     for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s <= n_slots; s += (uint64_t)gridDim.x * blockDim.x) {
         vis_off[s] = voff[min((uint64_t)pair_off[s], n)];
         if (s == n_slots) {
@@ -52,17 +48,21 @@ __global__ void __launch_bounds__(256)
     for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < n; p += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t b = voff[p], e = voff[p + 1];
         if (e == b) continue;
+        if (!desc) {  // warp-tile kernel: only the first pair of every tile
+            for (uint64_t t = (b + tile - 1) / tile; t * tile < e && t < max_tiles; t++) first_pair[t] = (uint32_t)p;
+            continue;
+        }
         const uint32_t cs = cell_start[pair_cell[p]];
-        for (uint64_t t = (b + EMIT_TILE - 1) / EMIT_TILE; t * EMIT_TILE < e && t < max_tiles; t++) {
-            const uint64_t base = t * EMIT_TILE;
-            const uint32_t tile_len = (uint32_t)min((uint64_t)EMIT_TILE, V - base);
+        for (uint64_t t = (b + tile - 1) / tile; t * tile < e && t < max_tiles; t++) {
+            const uint64_t base = t * tile;
+            const uint32_t tile_len = (uint32_t)min((uint64_t)tile, V - base);
             TileDesc d;
             d.p0 = (uint32_t)p;
             // bases are phase-adjusted: the entry that lands on tile slot o is sorted4[base + o] and base + o is a multiple of 4
             // whenever o is (copy k of the CSR payload holds element i at k * stride + k + i, stride % 4 == 0)
             const uint32_t s0 = cs + (uint32_t)(base - b), ph0 = (0u - s0) & 3u;
             d.src0 = ph0 * stride + ph0 + s0;
-            const uint32_t end0 = (uint32_t)min((uint64_t)EMIT_TILE, e - base);
+            const uint32_t end0 = (uint32_t)min((uint64_t)tile, e - base);
             uint32_t end1 = end0;
             d.src1 = 0;
             if (end0 < tile_len) {  // the pair ends inside this tile: the second segment is the next non-empty pair
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256)
                 if (q < n) {
                     const uint32_t s1 = cell_start[pair_cell[q]] - end0, ph1 = (0u - s1) & 3u;  // (wraps: only base + o, o >= end0, is used)
                     d.src1 = ph1 * stride + ph1 + s1;
-                    end1 = (uint32_t)min((uint64_t)EMIT_TILE, voff[q + 1] - base);
+                    end1 = (uint32_t)min((uint64_t)tile, voff[q + 1] - base);
                 }
             }
             d.ends = end0 | (end1 << 16) | (end1 < tile_len ? 0x80000000u : 0u);
@@ -216,76 +216,91 @@ __global__ void __launch_bounds__(EMIT_THREADS, CHD_EMIT_MIN_BLOCKS)
 }
 
 
-// Persistent variant: gridDim.x = EMIT_PERSIST_BLOCKS CTAs per SM pull tile numbers from a global ticket (dynamic order, like the
-// hardware block scheduler; a static round-robin order runs 15 % slower, profiles/r2_write_probe.json) and software-pipeline
-// the index work: while the CTA copies tile i, thread 0 has the ticket of tile i+2 and the descriptor of tile i+1 in flight,
-// so the per-tile critical path is ONE round trip (the data loads).  The partition pass zeroes the ticket.
-__global__ void __launch_bounds__(EMIT_THREADS, CHD_EMIT_PERSIST_BLOCKS ? CHD_EMIT_PERSIST_REGCAP_BLOCKS : 1)
-    emit_visible_persistent_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, const unsigned long long* __restrict__ n_visible_ptr,
-                                   const uint64_t* __restrict__ voff, const uint32_t* __restrict__ pair_cell, const uint32_t* __restrict__ cell_start,
-                                   const uint32_t* __restrict__ sorted4, uint32_t stride, const uint32_t* __restrict__ first_pair,
-                                   const TileDesc* __restrict__ desc, uint32_t* __restrict__ vis_entity, uint64_t vis_cap,
-                                   unsigned long long* __restrict__ ticket) {
-    __shared__ uint32_t s_end[EMIT_SMEM_PAIRS];
-    __shared__ uint32_t s_src[EMIT_SMEM_PAIRS];
-    __shared__ unsigned long long s_tk[3];
-    __shared__ uint4 s_desc[2];
-    const uint64_t V = *n_visible_ptr;
-    if (V == 0 || V > vis_cap) return;
-    const uint64_t n_tiles = (V + EMIT_TILE - 1) / EMIT_TILE;
-    const uint32_t tid = threadIdx.x;
-    if (tid == 0) {
-        const unsigned long long t0 = atomicAdd(ticket, 1ull), t1 = atomicAdd(ticket, 1ull);
-        s_tk[0] = t0;
-        s_tk[1] = t1;
-        if (t0 < n_tiles) s_desc[0] = __ldg(reinterpret_cast<const uint4*>(desc + t0));
-    }
-    __syncthreads();
-    for (uint32_t it = 0;; it++) {
-        const uint64_t t = s_tk[it % 3];
-        if (t >= n_tiles) break;
-        const uint4 dw = s_desc[it & 1];
-        unsigned long long t2 = 0;
-        uint4 dn = make_uint4(0, 0, 0, 0);
-        const uint64_t t1 = s_tk[(it + 1) % 3];
-        if (tid == 0) {  // in flight while this tile is copied
-            t2 = atomicAdd(ticket, 1ull);
-            if (t1 < n_tiles) dn = __ldg(reinterpret_cast<const uint4*>(desc + t1));
-        }
-        if (!(dw.z & 0x80000000u)) {
-            const uint32_t end0 = dw.z & 0x7FFFu, end1 = (dw.z >> 16) & 0x7FFFu;
-            uint32_t* __restrict__ out = vis_entity + t * EMIT_TILE;
-            uint32_t src[EMIT_ROWS];
+// General kernel (round 1's shape): a persistent grid, every WARP owns whole 4 KB tiles (no block barrier anywhere), the segment
+// table of a tile lives in a warp-private slice of shared memory.  Used when cells are small against a 16 KB tile (many segments
+// per tile: config #5's 152 entities per cell) or when the CSR payload does not fit the L2 (config #3: the copy is then DRAM-bound
+// on both sides and this shape reaches 0.95 of the copy peak, where the CTA-tile kernel above reaches 0.80).
+__global__ void __launch_bounds__(EMIT_THREADS, 4)
+    emit_visible_warp_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, const uint64_t* __restrict__ voff,
+                        const uint32_t* __restrict__ pair_cell, const uint32_t* __restrict__ cell_start,
+                        const uint32_t* __restrict__ sorted4, uint32_t stride, const uint32_t* __restrict__ first_pair,
+                        uint32_t* __restrict__ vis_entity, uint64_t vis_cap) {
+    __shared__ uint32_t s_end_all[EMIT_WARP_WARPS][EMIT_WARP_SMEM_PAIRS];  // end of pair (p0+k) relative to the tile base, clamped to EMIT_WARP_TILE
+    __shared__ uint32_t s_src_all[EMIT_WARP_WARPS][EMIT_WARP_SMEM_PAIRS];  // source index of the pair's entry that lands on max(voff[p], tile base)
+    const uint64_t np = min((uint64_t)*n_pairs_ptr, pair_cap);
+    if (np == 0) return;
+    const uint64_t V = voff[np];
+    if (V > vis_cap) return;
+    const uint64_t n_tiles = (V + EMIT_WARP_TILE - 1) / EMIT_WARP_TILE;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t* s_end = s_end_all[w];
+    uint32_t* s_src = s_src_all[w];
+    const uint64_t warp_id = (uint64_t)blockIdx.x * EMIT_WARP_WARPS + w, n_warps = (uint64_t)gridDim.x * EMIT_WARP_WARPS;
+    for (uint64_t t = warp_id; t < n_tiles; t += n_warps) {
+        const uint64_t base = t * EMIT_WARP_TILE;
+        const uint32_t p0 = first_pair[t];
+        const uint32_t p1 = (t + 1 < n_tiles) ? first_pair[t + 1] : (uint32_t)(np - 1);
+        const uint32_t cnt = p1 - p0 + 1;
+        const uint32_t tile_len = (uint32_t)min((uint64_t)EMIT_WARP_TILE, V - base);
+        uint32_t* __restrict__ out = vis_entity + base;
+        if (cnt <= EMIT_WARP_SMEM_PAIRS) {
+            __syncwarp();  // the previous tile's readers are done
+            for (uint32_t k = lane; k < cnt; k += 32) {
+                const uint64_t b = voff[p0 + k], e = voff[p0 + k + 1];
+                const uint32_t c = pair_cell[p0 + k];
+                s_end[k] = (uint32_t)min((uint64_t)EMIT_WARP_TILE, e > base ? e - base : 0);
+                s_src[k] = cell_start[c] + (uint32_t)(b < base ? base - b : 0);
+            }
+            __syncwarp();
+            uint32_t k = 0;  // segment cursor of this lane (its chunks ascend)
+            uint32_t src[EMIT_WARP_CHUNKS];  // element index into sorted4 (multiple of 4), or 0xFFFFFFFF
+            // phase 1: resolve every chunk's source (nullptr = handled element-wise / out of range)
 #pragma unroll
-            for (int r = 0; r < EMIT_ROWS; r++) {
-                const uint32_t o = (r * EMIT_THREADS + tid) * 4;
-                src[r] = 0xFFFFFFFFu;
-                if (o < end1) {
-                    const bool in0 = o + 4 <= end0, in1 = o >= end0 && o + 4 <= end1;
-                    if (in0 || in1) {
-                        src[r] = (in0 ? dw.x : dw.y) + o;
+            for (int it = 0; it < EMIT_WARP_CHUNKS; it++) {
+                const uint32_t o = (it * 32 + lane) * 4;  // first entry of this 16-byte chunk
+                src[it] = 0xFFFFFFFFu;
+                if (o < tile_len) {
+                    while (s_end[k] <= o) k++;  // terminates: s_end[cnt-1] >= tile_len > o
+                    const uint32_t beg = k == 0 ? 0u : s_end[k - 1];
+                    const uint32_t sidx = s_src[k] + (o - beg);
+                    if (o + 4 <= s_end[k]) {
+                        // whole chunk inside one segment: co-aligned 16-byte move out of phase copy (-sidx)&3
+                        const uint32_t ph = (0u - sidx) & 3u;
+                        src[it] = ph * stride + ph + sidx;
                     } else {
-                        for (uint32_t j = 0; j < 4 && o + j < end1; j++)
-                            out[o + j] = __ldg(sorted4 + (o + j < end0 ? dw.x : dw.y) + o + j);
+                        // the chunk straddles a segment boundary (or the end of the list): entry by entry
+                        uint32_t kk = k;
+                        for (uint32_t j = 0; j < 4 && o + j < tile_len; j++) {
+                            while (s_end[kk] <= o + j) kk++;
+                            const uint32_t bb = kk == 0 ? 0u : s_end[kk - 1];
+                            out[o + j] = __ldg(sorted4 + s_src[kk] + (o + j - bb));
+                        }
                     }
                 }
             }
-            uint4 v[EMIT_ROWS];
+            // phase 2: all loads in flight, phase 3: streaming stores
+            uint4 v[EMIT_WARP_CHUNKS];
 #pragma unroll
-            for (int r = 0; r < EMIT_ROWS; r++)
-                if (src[r] != 0xFFFFFFFFu) v[r] = __ldg(reinterpret_cast<const uint4*>(sorted4 + src[r]));
+            for (int it = 0; it < EMIT_WARP_CHUNKS; it++)
+                if (src[it] != 0xFFFFFFFFu) v[it] = __ldg(reinterpret_cast<const uint4*>(sorted4 + src[it]));
 #pragma unroll
-            for (int r = 0; r < EMIT_ROWS; r++)
-                if (src[r] != 0xFFFFFFFFu) __stcs(reinterpret_cast<uint4*>(out + (r * EMIT_THREADS + tid) * 4), v[r]);
+            for (int it = 0; it < EMIT_WARP_CHUNKS; it++)
+                if (src[it] != 0xFFFFFFFFu) __stcs(reinterpret_cast<uint4*>(out + (it * 32 + lane) * 4), v[it]);
         } else {
-            emit_tile_general(t, n_tiles, V, dw.w, n_pairs_ptr, pair_cap, voff, pair_cell, cell_start, sorted4, stride, first_pair, vis_entity, s_end, s_src);
+            // more than EMIT_WARP_SMEM_PAIRS pairs inside one tile (tiny / empty cells): per-entry binary search
+            for (uint32_t o = lane; o < tile_len; o += 32) {
+                const uint64_t go = base + o;
+                uint64_t lo = p0, hi = p1;  // last p in [p0,p1] with voff[p] <= go
+                while (lo < hi) {
+                    const uint64_t mid = (lo + hi + 1) >> 1;
+                    if (voff[mid] <= go) lo = mid; else hi = mid - 1;
+                }
+                const uint32_t c = pair_cell[lo];
+                vis_entity[go] = sorted4[cell_start[c] + (uint32_t)(go - voff[lo])];
+            }
         }
-        if (tid == 0) {
-            s_tk[(it + 2) % 3] = t2;
-            s_desc[(it + 1) & 1] = dn;
-        }
-        __syncthreads();
     }
 }
+
 
 }  // namespace chd

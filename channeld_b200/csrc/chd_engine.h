@@ -53,7 +53,7 @@ struct chd_engine {
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_interest = nullptr, ev_pairs = nullptr;
     bool interest_pending = false, pending_fanout = false;  // chd_begin_interest issued, not yet joined by chd_tick
-    GraphSlot g_build[4], g_interest[4], g_interest_b[4], g_emit_prep[2], g_fanout[4], g_export[4], g_import[2];  // build / export: [key buffer][position buffer]
+    GraphSlot g_build[4], g_build_b[4], g_interest[4], g_interest_b[4], g_emit_prep[2], g_fanout[4], g_export[4], g_import[2];  // build / export: [key buffer][position buffer]
     uint64_t graph_launches = 0, graph_captures = 0;
     uint32_t* d_key_a = nullptr;  // identity of the first key buffer (graph slot selection)
     int64_t* d_time = nullptr;      // [0] = now_ns of the last update_interest, [1] = t_ns of the last fanout_tick
@@ -152,7 +152,6 @@ struct chd_engine {
     uint32_t *d_new_sub = nullptr, *d_new_ch = nullptr, *d_gone_sub = nullptr, *d_gone_ch = nullptr;
     // emit
     uint32_t *d_vcnt = nullptr, *d_first_pair = nullptr, *d_vis = nullptr;
-    unsigned long long* d_emit_ticket = nullptr;  // tile ticket of the persistent emit kernel (zeroed by the partition pass)
     TileDesc* d_tile_desc = nullptr;  // per-tile copy descriptors (chd_emit.cuh)
     uint32_t* d_pair_ch = nullptr;  // channel id of every current pair (written by interest_fill_kernel)
     // ---- window classes of the due list (chd_due_classes): keys written by the fan-out kernel, scratch allocated on first use
@@ -186,6 +185,10 @@ struct chd_engine {
     // preparation (visible offsets) are done, i.e. while the emit kernel is still streaming
     cudaStream_t dl_stream = nullptr, dl_stream_b = nullptr;  // phase A / phase B of the early read-back
     cudaEvent_t ev_prep_done = nullptr, ev_build_done = nullptr;
+    // ev_counts: the cell CSR offsets of the build in flight are final (recorded between the two halves of a single-pass build);
+    // prep_stream: where the emit preparation runs when it overlaps the build's scatter
+    cudaEvent_t ev_counts = nullptr;
+    cudaStream_t prep_stream = nullptr;
     bool build_done_recorded = false;  // this tick ran a build (its end is ev_build_done)
     // chd_fetch_results_async: completion events of the two copy phases; the next tick is ordered after them on the device
     // (two fetches may be outstanding: the host waits for tick k-1 after it has enqueued tick k and its fetch)

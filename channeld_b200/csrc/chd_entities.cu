@@ -14,8 +14,11 @@ struct FusedAssign {
 template <int BINS>
 static chd_status sort_pass(chd_engine* e, uint32_t* hist, const ScanSite& site, const uint32_t* key_in, const uint32_t* val_in, uint32_t n,
                             const uint32_t* n_ptr, uint32_t per_block, uint32_t nblocks, uint32_t shift, uint32_t bits, uint32_t* key_out,
-                            uint32_t* val_out, ScatterExtras ex, unsigned long long* bump, const FusedAssign* assign = nullptr) {
+                            uint32_t* val_out, ScatterExtras ex, unsigned long long* bump, const FusedAssign* assign = nullptr, int half = 0) {
+    // half: 0 = the whole pass, 1 = histogram + scan only, 2 = scatter only (single-pass builds are split so that the emit
+    // preparation, which needs only the cell counts, overlaps the scatter)
     const uint32_t mask = (1u << bits) - 1u;
+    if (half == 2) goto scatter;
     if (assign)
         assign_hist_kernel<BINS><<<nblocks, BUILD_THREADS, 0, e->stream>>>(e->g, assign->x, assign->z, n, assign->key, assign->prev, assign->ho, per_block, mask,
                                                                            hist, nblocks, bump);
@@ -23,6 +26,8 @@ static chd_status sort_pass(chd_engine* e, uint32_t* hist, const ScanSite& site,
         radix_hist_kernel<BINS><<<nblocks, BUILD_THREADS, 0, e->stream>>>(key_in, n, n_ptr, per_block, shift, mask, hist, nblocks, bump);
     KCHECK(e);
     SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(hist, hist, (uint64_t)BINS * nblocks, site, e->stream));
+    if (half == 1) return CHD_OK;
+scatter:
     // bandwidth-bound regime: reorder each tile by digit in shared memory first (coalesced runs); small inputs are latency-bound
     // and take the plain scatter (fewer barriers per tile)
     if (n > (2u << 20))
@@ -37,9 +42,9 @@ static chd_status sort_pass(chd_engine* e, uint32_t* hist, const ScanSite& site,
 
 static chd_status sort_pass_fused(chd_engine* e, uint32_t* hist, const ScanSite& site, const uint32_t* key_in, const uint32_t* val_in, uint32_t n,
                                   const uint32_t* n_ptr, uint32_t per_block, uint32_t nblocks, uint32_t shift, uint32_t bits, uint32_t* key_out,
-                                  uint32_t* val_out, ScatterExtras ex, unsigned long long* bump, const FusedAssign* assign) {
-    if (bits <= 8) return sort_pass<256>(e, hist, site, key_in, val_in, n, n_ptr, per_block, nblocks, shift, bits, key_out, val_out, ex, bump, assign);
-    return sort_pass<1024>(e, hist, site, key_in, val_in, n, n_ptr, per_block, nblocks, shift, bits, key_out, val_out, ex, bump, assign);
+                                  uint32_t* val_out, ScatterExtras ex, unsigned long long* bump, const FusedAssign* assign, int half = 0) {
+    if (bits <= 8) return sort_pass<256>(e, hist, site, key_in, val_in, n, n_ptr, per_block, nblocks, shift, bits, key_out, val_out, ex, bump, assign, half);
+    return sort_pass<1024>(e, hist, site, key_in, val_in, n, n_ptr, per_block, nblocks, shift, bits, key_out, val_out, ex, bump, assign, half);
 }
 
 chd_status chd_sort_pass_any(chd_engine* e, uint32_t* hist, const ScanSite& site, const uint32_t* key_in, const uint32_t* val_in,
@@ -233,7 +238,9 @@ chd_status chd_assign_cells_impl(chd_engine* e) {
     return CHD_OK;
 }
 
-static chd_status build_enqueue(chd_engine* e, bool with_assign) {
+// part: 0 = the whole build; single-pass builds only: 1 = cell assignment + histogram + scan + CSR offsets, 2 = scatter (+ phase
+// copies).  The cell CSR offsets are final after part 1.
+static chd_status build_enqueue(chd_engine* e, bool with_assign, int part = 0) {
     chd_status st;
     FusedAssign fa{};
     const FusedAssign* fap = nullptr;
@@ -270,15 +277,25 @@ static chd_status build_enqueue(chd_engine* e, bool with_assign) {
     uint32_t nblocks = (n + per_block - 1) / per_block;
     if (nblocks == 0) nblocks = 1;
     const uint32_t* vals = e->have_gid ? e->d_gid : nullptr;
-    // Phase copies: fused into the final scatter when the build is latency-bound (small N: one launch less), written by
-    // a separate fully-coalesced pass when it is bandwidth-bound (large N: the fused variant does 4 scattered 4-byte
-    // stores per entity; measured 325 us vs 175 + ~30 us at N = 10 M).
-#ifndef CHD_BUILD_FUSE_PHASES_MAX_N
-#define CHD_BUILD_FUSE_PHASES_MAX_N (2u << 20)
-#endif
-    const bool fuse_phases = n <= (uint32_t)CHD_BUILD_FUSE_PHASES_MAX_N;
+    // Phase copies: written by a separate fully-coalesced pass after the scatter.  (Fusing them into the scatter saves a launch but
+    // does 4 scattered 4-byte stores per entity: measured slower at every size — 69 vs 59 us per build at N = 1 M, 325 vs 205 us
+    // at N = 10 M.)
+    const bool fuse_phases = false;
     const uint32_t fused_stride = fuse_phases ? e->phase_stride : 0u;
-    if (passes == 1) {
+    if (passes == 1 && part != 0) {
+        if (part == 1) {
+            st = sort_pass_fused(e, e->d_hist, e->site_hist, e->d_key, vals, n, n_ptr, per_block, nblocks, 0, bits0, nullptr, e->d_sorted_ent,
+                                 ScatterExtras{0, nullptr, C, nullptr}, e->d_epoch + EP_BUILD, fap, 1);
+            if (st != CHD_OK) return st;
+            publish_cell_start_kernel<<<blocks_for((uint64_t)C + 2, 256), 256, 0, e->stream>>>(e->d_hist, nblocks, C, n, n_ptr, e->d_cell_start,
+                                                                                                 &e->d_ctr->n_entities_in_world);
+            KCHECK(e);
+            return CHD_OK;
+        }
+        st = sort_pass_fused(e, e->d_hist, e->site_hist, e->d_key, vals, n, n_ptr, per_block, nblocks, 0, bits0, nullptr, e->d_sorted_ent,
+                             ScatterExtras{fused_stride, nullptr, C, nullptr}, nullptr, nullptr, 2);
+        if (st != CHD_OK) return st;
+    } else if (passes == 1) {
         // single pass: digit == key, so the scatter also publishes the CSR offsets
         ScatterExtras ex{fused_stride, e->d_cell_start, C, &e->d_ctr->n_entities_in_world};
         st = sort_pass_fused(e, e->d_hist, e->site_hist, e->d_key, vals, n, n_ptr, per_block, nblocks, 0, bits0, nullptr, e->d_sorted_ent, ex,
@@ -313,6 +330,7 @@ chd_status chd_build(chd_engine* e) {
     StageTimer timer(e, CHD_STAGE_BUILD);
     chd_status st = chd_epoch_tick(e, EP_BUILD);
     if (st != CHD_OK) return st;
+    bool counts_recorded = false;
     if (!e->assigned && !e->halo_on_device) {
         // single-GPU flow: assign + sort as one replayable graph.  The key buffers swap every assignment
         // (handover detection compares against the previous keys), so there are two graph variants.
@@ -320,7 +338,10 @@ chd_status chd_build(chd_engine* e) {
         const int slot = (target == e->d_key_a ? 0 : 1) + 2 * e->pos_buf;
         uint64_t key = mix_key(mix_key(mix_key(0x6275696c64ull, e->n_own), e->have_gid), e->have_prev_key);
         key = mix_key(mix_key(key, (uint64_t)(uintptr_t)target), (uint64_t)(uintptr_t)e->pos_x ^ ((uint64_t)(uintptr_t)e->pos_z << 1));
-        st = run_stage(e, e->g_build[slot], key, [&]() { return build_enqueue(e, true); });
+        // single-pass builds (<= 1023 cells) run as two replayable halves with an event in between: the cell CSR offsets are
+        // final after the first (assignment + histogram + scan), so the emit preparation overlaps the scatter
+        const bool split = e->g.cells + 1 <= BUILD_MAX_BINS && e->n_own > 0;
+        st = run_stage(e, e->g_build[slot], key, [&]() { return build_enqueue(e, true, split ? 1 : 0); });
         if (st == CHD_OK && !e->assigned) {  // replayed graph: mirror the host-side bookkeeping of chd_assign_cells
             if (e->have_prev_key) {
                 uint32_t* t = e->d_key;
@@ -330,6 +351,11 @@ chd_status chd_build(chd_engine* e) {
             if (e->n_own) e->have_prev_key = true;
             e->n_halo = 0;
             e->assigned = true;
+        }
+        if (st == CHD_OK && split) {
+            CU(e, cudaEventRecord(e->ev_counts, e->stream));
+            counts_recorded = true;
+            st = run_stage(e, e->g_build_b[slot], mix_key(key, 0x62), [&]() { return build_enqueue(e, false, 2); });
         }
         if (st == CHD_OK) st = chd_note_pos_read(e);
     } else if (e->assigned && e->halo_on_device) {
@@ -344,6 +370,7 @@ chd_status chd_build(chd_engine* e) {
         if (st == CHD_OK && with_assign) st = chd_note_pos_read(e);
     }
     if (st != CHD_OK) return st;
+    if (!counts_recorded) CU(e, cudaEventRecord(e->ev_counts, e->stream));  // (cell counts final = build done)
     e->n_sorted = e->n_own + e->n_halo;
     e->built = true;
     e->entities_dirty = false;

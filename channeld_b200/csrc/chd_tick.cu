@@ -9,6 +9,62 @@
 
 extern "C" {
 
+// Which copy kernel (host-known inputs only: nothing here waits for the device):
+//   CTA tiles + per-tile descriptors  when cells are large against a 16 KB tile (<= 2 segments per tile is the common case)
+//                                     AND the CSR's four phase copies stay L2-resident (the copy is then a pure write stream);
+//   warp tiles (round 1's kernel)     otherwise: many segments per tile (config #5) or sources streamed from DRAM (config #3).
+static bool emit_uses_cta_tiles(const chd_engine* e) {
+    const uint64_t n_build = (uint64_t)e->n_own + (e->halo_on_device ? (uint64_t)e->border_cap : (uint64_t)e->n_halo);
+    const uint64_t own_cells = (uint64_t)(e->g.col_hi - e->g.col_lo) * e->g.rows;  // (the whole grid on one GPU, the slab on N)
+    return (uint64_t)e->n_own / (own_cells ? own_cells : 1) >= (uint64_t)EMIT_TILE / 2 && n_build * 16ull <= (64ull << 20);
+}
+
+// emit preparation on e->stream: per-pair output offsets (scan), per-tile first pairs / descriptors, per-subscriber offsets, V
+static chd_status emit_prep_enqueue(chd_engine* e, bool cta_tiles) {
+    cudaStream_t s = e->stream;
+    PairBuf& pb = e->pairs[e->cur];
+    const uint32_t S = e->n_slots;
+    const uint64_t P = e->lim.max_pairs;
+    const unsigned grid = (unsigned)e->sm_count * 8;
+    const uint32_t tile = cta_tiles ? (uint32_t)EMIT_TILE : (uint32_t)EMIT_WARP_TILE;
+    const uint64_t key = mix_key(mix_key(mix_key(mix_key(0x656d6974ull, S), (uint64_t)e->cur), cta_tiles), (uint64_t)(uintptr_t)s);
+    chd_status st = chd_epoch_tick(e, EP_EMIT);
+    if (st != CHD_OK) return st;
+    return run_stage(e, e->g_emit_prep[e->cur], key, [&]() -> chd_status {
+        // per-pair visible counts are computed by the scan itself; the partition pass opens the next epoch
+        SCAN(e, exclusive_scan_fn<PairVcountIn, uint64_t>(PairVcountIn{pb.cell, e->d_cell_start}, e->d_voff, P, e->site_voff, s, pb.off + S));
+        emit_partition_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_first_pair, cta_tiles ? e->d_tile_desc : nullptr,
+                                                   e->phase_stride, e->max_tiles, S, pb.off, e->d_vis_off, e->lim.max_visible, e->d_ctr, e->d_epoch + EP_EMIT, tile);
+        KCHECK(e);
+        return CHD_OK;
+    });
+}
+
+static chd_status emit_kernel_enqueue(chd_engine* e, bool cta_tiles) {
+    cudaStream_t s = e->stream;
+    PairBuf& pb = e->pairs[e->cur];
+    const uint32_t S = e->n_slots;
+    const uint64_t P = e->lim.max_pairs;
+    StageTimer kt(e, CHD_STAGE_EMIT_KERNEL);
+    if (cta_tiles) {
+        // One CTA per 16 KB tile, dispatched by the hardware block scheduler.  The tile count lives on the device; the grid is
+        // sized from the last visible count the host has seen (+3 %: the kernel loops if that was too few, surplus CTAs exit
+        // at once), from the capacity before that.
+        const uint64_t cap_tiles = (e->lim.max_visible + EMIT_TILE - 1) / EMIT_TILE;
+        uint64_t tiles = e->vis_estimate ? std::min<uint64_t>(cap_tiles, (e->vis_estimate + e->vis_estimate / 32) / EMIT_TILE + 64) : cap_tiles;
+        if (tiles == 0) tiles = 1;
+        if (tiles > 0x7fffffffull) tiles = 0x7fffffffull;
+        tiles = (tiles + EMIT_TILES_PER_CTA - 1) / EMIT_TILES_PER_CTA;
+        emit_visible_kernel<<<(unsigned)tiles, EMIT_THREADS, 0, s>>>(pb.off + S, P, &e->d_ctr->n_visible, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4,
+                                                                     e->phase_stride, e->d_first_pair, e->d_tile_desc, e->d_vis, e->lim.max_visible);
+    } else {
+        emit_visible_warp_kernel<<<(unsigned)e->sm_count * 4, EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4,
+                                                                                    e->phase_stride, e->d_first_pair, e->d_vis, e->lim.max_visible);
+    }
+    KCHECK(e);
+    return CHD_OK;
+}
+
 chd_status chd_emit_visible(chd_engine* e) {
     if (!e) return CHD_ERR_INVALID;
     CU(e, cudaSetDevice(e->device));
@@ -16,54 +72,51 @@ chd_status chd_emit_visible(chd_engine* e) {
         e->fail("chd_emit_visible before chd_build");
         return CHD_ERR_STATE;
     }
-    cudaStream_t s = e->stream;
-    PairBuf& pb = e->pairs[e->cur];
-    const uint32_t S = e->n_slots;
-    const uint64_t P = e->lim.max_pairs;
     {
         chd_status gs_ = chd_fetch_guard(e);
         if (gs_ != CHD_OK) return gs_;
     }
     StageTimer timer(e, CHD_STAGE_EMIT);
-    const unsigned grid = (unsigned)e->sm_count * 8;
-    const uint64_t key = mix_key(mix_key(0x656d6974ull, S), (uint64_t)e->cur);
-    chd_status st = chd_epoch_tick(e, EP_EMIT);
-    if (st != CHD_OK) return st;
-    st = run_stage(e, e->g_emit_prep[e->cur], key, [&]() -> chd_status {
-        // per-pair visible counts are computed by the scan itself; the partition pass opens the next epoch
-        SCAN(e, exclusive_scan_fn<PairVcountIn, uint64_t>(PairVcountIn{pb.cell, e->d_cell_start}, e->d_voff, P, e->site_voff, s, pb.off + S));
-        emit_partition_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_first_pair, e->d_tile_desc, e->phase_stride, e->max_tiles, S, pb.off, e->d_vis_off,
-                                                   e->lim.max_visible, e->d_ctr, e->d_epoch + EP_EMIT, e->d_emit_ticket);
-        KCHECK(e);
-        return CHD_OK;
-    });
+    const bool cta_tiles = emit_uses_cta_tiles(e);
+    chd_status st = emit_prep_enqueue(e, cta_tiles);
     if (st != CHD_OK) return st;
     if (e->wait_before_emit_kernel) {
-        CU(e, cudaStreamWaitEvent(s, e->wait_before_emit_kernel, 0));
+        CU(e, cudaStreamWaitEvent(e->stream, e->wait_before_emit_kernel, 0));
         e->wait_before_emit_kernel = nullptr;
     }
-    CU(e, cudaEventRecord(e->ev_prep_done, s));  // visible offsets + counters are final; only the expanded list is still to come
-    {
-        StageTimer kt(e, CHD_STAGE_EMIT_KERNEL);
-        // One CTA per 16 KB tile.  The tile count lives on the device; the grid is sized from the last visible count the host
-        // has seen (+3 %: the kernel loops if that was too few, surplus CTAs exit at once), from the capacity before that.
-        const uint64_t cap_tiles = (e->lim.max_visible + EMIT_TILE - 1) / EMIT_TILE;
-        uint64_t tiles = e->vis_estimate ? std::min<uint64_t>(cap_tiles, (e->vis_estimate + e->vis_estimate / 32) / EMIT_TILE + 64) : cap_tiles;
-        if (tiles == 0) tiles = 1;
-        if (tiles > 0x7fffffffull) tiles = 0x7fffffffull;
-        tiles = (tiles + EMIT_TILES_PER_CTA - 1) / EMIT_TILES_PER_CTA;
-#if CHD_EMIT_PERSIST_BLOCKS
-        (void)tiles;
-        emit_visible_persistent_kernel<<<(unsigned)e->sm_count * EMIT_PERSIST_BLOCKS, EMIT_THREADS, 0, s>>>(
-            pb.off + S, P, &e->d_ctr->n_visible, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4, e->phase_stride, e->d_first_pair, e->d_tile_desc, e->d_vis,
-            e->lim.max_visible, e->d_emit_ticket);
-#else
-        emit_visible_kernel<<<(unsigned)tiles, EMIT_THREADS, 0, s>>>(pb.off + S, P, &e->d_ctr->n_visible, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4, e->phase_stride,
-                                                                                e->d_first_pair, e->d_tile_desc, e->d_vis, e->lim.max_visible);
-#endif
-        KCHECK(e);
+    CU(e, cudaEventRecord(e->ev_prep_done, e->stream));  // visible offsets + counters are final; only the expanded list is still to come
+    return emit_kernel_enqueue(e, cta_tiles);
+}
+
+// The emit of a two-stream tick: the preparation needs the new pairs (`pairs_ev`, second stream) and the cell CSR OFFSETS
+// (ev_counts: recorded between the two halves of a single-pass build), not the sorted entity array — it runs on its own stream
+// next to the build's scatter; the copy kernel follows on the main stream when both are done.
+static chd_status emit_overlapped(chd_engine* e, cudaEvent_t pairs_ev) {
+    if (!e->built) {
+        e->fail("chd_tick: emit before any build");
+        return CHD_ERR_STATE;
     }
-    return CHD_OK;
+    const bool cta_tiles = emit_uses_cta_tiles(e);
+    cudaStream_t main_stream = e->stream, ps = e->prep_stream;
+    CU(e, cudaStreamWaitEvent(ps, e->ev_fork, 0));    // the previous tick's copy kernel (it reads what the preparation rewrites)
+    CU(e, cudaStreamWaitEvent(ps, e->ev_counts, 0));
+    CU(e, cudaStreamWaitEvent(ps, pairs_ev, 0));
+    chd_status st;
+    {
+        std::lock_guard<std::recursive_mutex> redirect(e->mu);  // `stream` is redirected while the preparation is enqueued
+        e->stream = ps;
+        st = emit_prep_enqueue(e, cta_tiles);
+        e->stream = main_stream;
+    }
+    if (st != CHD_OK) return st;
+    CU(e, cudaEventRecord(e->ev_prep_done, ps));
+    StageTimer timer(e, CHD_STAGE_EMIT);
+    CU(e, cudaStreamWaitEvent(main_stream, e->ev_prep_done, 0));
+    if (e->wait_before_emit_kernel) {
+        CU(e, cudaStreamWaitEvent(main_stream, e->wait_before_emit_kernel, 0));
+        e->wait_before_emit_kernel = nullptr;
+    }
+    return emit_kernel_enqueue(e, cta_tiles);
 }
 
 chd_status chd_set_rings(chd_engine* e, const uint32_t* ring_off, uint32_t n_entries, const int64_t* arrival, const uint32_t* sender,
@@ -461,10 +514,9 @@ static chd_status chd_tick_impl(chd_engine* e, const chd_query_batch* q, int64_t
             CU(e, cudaEventRecord(e->ev_build_done, main_stream));
             e->build_done_recorded = true;
         }
-        CU(e, cudaStreamWaitEvent(main_stream, e->ev_pairs, 0));
         if (do_emit) {
             if (e->early_results_tick) e->wait_before_emit_kernel = e->ev_join;
-            st = chd_emit_visible(e);
+            st = emit_overlapped(e, e->ev_pairs);
             if (st != CHD_OK) return st;
         }
         CU(e, cudaStreamWaitEvent(main_stream, e->ev_join, 0));
@@ -504,9 +556,8 @@ static chd_status chd_tick_impl(chd_engine* e, const chd_query_batch* q, int64_t
             e->build_done_recorded = true;
         }
         if (do_emit) {
-            CU(e, cudaStreamWaitEvent(main_stream, !q ? e->ev_interest : e->ev_pairs, 0));
             if (e->early_results_tick) e->wait_before_emit_kernel = e->ev_join;
-            st = chd_emit_visible(e);
+            st = emit_overlapped(e, !q ? e->ev_interest : e->ev_pairs);
             if (st != CHD_OK) return st;
         }
         CU(e, cudaStreamWaitEvent(main_stream, e->ev_join, 0));

@@ -17,15 +17,6 @@ constexpr int EMIT_THREADS = 256;
 #ifndef CHD_EMIT_MIN_BLOCKS
 #define CHD_EMIT_MIN_BLOCKS 6
 #endif
-#ifndef CHD_EMIT_PERSIST_BLOCKS
-#define CHD_EMIT_PERSIST_BLOCKS 4  // CTAs per SM of the persistent (ticket) emit kernel; 0 = one CTA per tile, hardware-scheduled
-#endif
-constexpr int EMIT_PERSIST_BLOCKS = CHD_EMIT_PERSIST_BLOCKS ? CHD_EMIT_PERSIST_BLOCKS : 1;
-// The persistent kernel is COMPILED for one more CTA per SM than it is launched with: the registers it leaves free are what lets
-// the short, high-priority kernels of the second stream (pair grouping, fan-out) run next to it instead of behind it.
-#ifndef CHD_EMIT_PERSIST_REGCAP_BLOCKS
-#define CHD_EMIT_PERSIST_REGCAP_BLOCKS (CHD_EMIT_PERSIST_BLOCKS + 1)
-#endif
 #ifndef CHD_EMIT_TILES_PER_CTA
 #define CHD_EMIT_TILES_PER_CTA 1
 #endif
@@ -33,6 +24,11 @@ constexpr int EMIT_TILES_PER_CTA = CHD_EMIT_TILES_PER_CTA;  // tiles one CTA cop
 constexpr int EMIT_ROWS = CHD_EMIT_ROWS;                    // 16-byte chunks per thread per tile
 constexpr int EMIT_TILE = EMIT_THREADS * 4 * EMIT_ROWS;     // 4096 entries = 16 KB of output per CTA
 constexpr int EMIT_SMEM_PAIRS = 256;                        // pairs per tile staged in shared memory (one per thread)
+// the general (warp-tile) kernel: 8 x 16 bytes per lane = 4 KB of output per warp tile
+constexpr int EMIT_WARP_WARPS = EMIT_THREADS / 32;
+constexpr int EMIT_WARP_CHUNKS = 8;
+constexpr int EMIT_WARP_TILE = 32 * EMIT_WARP_CHUNKS * 4;   // 1024 entries
+constexpr int EMIT_WARP_SMEM_PAIRS = 64;
 
 // Per-tile copy descriptor written by the partition pass: the emit kernel needs ONE 16-byte load (broadcast to the CTA)
 // before it can issue its data loads, instead of a chain of three dependent index loads (first pair -> offsets / cell ->

@@ -1,6 +1,7 @@
 /* tick_loop.c — the C ABI as a host sees it (plain C99; what the cgo shim in go/gpucontroller.go does, minus Go).
  * One engine, the pipelined tick loop of INTEGRATION.md §2: while tick k runs on the GPU the inputs of tick k+1 are
- * uploaded, and the results of tick k are read back while its expanded-list kernel is still running.
+ * uploaded, and the results of tick k-1 are consumed (chd_fetch_results_async / chd_fetch_wait: the host never waits for a tick
+ * before it has enqueued the next one).
  *
  *   gcc -std=c99 -Iinclude examples/tick_loop.c -Lchanneld_b200 -lchd_b200 -Wl,-rpath,$PWD/channeld_b200 -lm -o tick_loop
  *
@@ -85,23 +86,32 @@ int main(void) {
     for (uint32_t j = 0; j < n_subs; j++) conn[j] = j + 1; /* connection id of subscriber slot j */
     CHECK(chd_set_subscribers(e, conn, n_subs));
 
-    /* result buffers (pinned: the read-back is then asynchronous to the kernels) */
-    chd_result_buffers rb;
-    memset(&rb, 0, sizeof rb);
-    rb.pair_cap = rb.diff_cap = lim.max_pairs;
-    rb.due_cap = lim.max_due;
-    rb.pair_off = chd_alloc_pinned(4ull * (n_subs + 1));
-    rb.pair_channel = chd_alloc_pinned(4ull * rb.pair_cap);
-    rb.pair_interval_ms = chd_alloc_pinned(4ull * rb.pair_cap);
-    rb.new_sub = chd_alloc_pinned(4ull * rb.diff_cap);
-    rb.new_channel = chd_alloc_pinned(4ull * rb.diff_cap);
-    rb.unsub_sub = chd_alloc_pinned(4ull * rb.diff_cap);
-    rb.unsub_channel = chd_alloc_pinned(4ull * rb.diff_cap);
-    rb.due = chd_alloc_pinned(sizeof(chd_due) * (uint64_t)rb.due_cap);
-    rb.handover_cap = n_entities;
-    rb.handover_entity = chd_alloc_pinned(4ull * n_entities);
-    rb.handover_src = chd_alloc_pinned(4ull * n_entities);
-    rb.handover_dst = chd_alloc_pinned(4ull * n_entities);
+    /* two sets of PINNED result buffers: the read-back of tick k (chd_fetch_results_async) overlaps tick k+1 */
+    chd_result_buffers rb[2];
+    void* hdr[2];
+    for (int k = 0; k < 2; k++) {
+        memset(&rb[k], 0, sizeof rb[k]);
+        rb[k].pair_cap = rb[k].diff_cap = lim.max_pairs;
+        rb[k].due_cap = lim.max_due;
+        rb[k].pair_off = chd_alloc_pinned(4ull * (n_subs + 1));
+        rb[k].pair_channel = chd_alloc_pinned(4ull * rb[k].pair_cap);
+        rb[k].pair_interval_ms = chd_alloc_pinned(4ull * rb[k].pair_cap);
+        rb[k].new_sub = chd_alloc_pinned(4ull * rb[k].diff_cap);
+        rb[k].new_channel = chd_alloc_pinned(4ull * rb[k].diff_cap);
+        rb[k].unsub_sub = chd_alloc_pinned(4ull * rb[k].diff_cap);
+        rb[k].unsub_channel = chd_alloc_pinned(4ull * rb[k].diff_cap);
+        rb[k].due = chd_alloc_pinned(sizeof(chd_due) * (uint64_t)rb[k].due_cap);
+        rb[k].handover_cap = n_entities;
+        rb[k].handover_entity = chd_alloc_pinned(4ull * n_entities);
+        rb[k].handover_src = chd_alloc_pinned(4ull * n_entities);
+        rb[k].handover_dst = chd_alloc_pinned(4ull * n_entities);
+        /* the cell CSR makes the result lossless: visible(s) = concatenation of sorted_entity[cell_start[c] .. cell_start[c+1]) over
+         * the subscriber's pairs */
+        rb[k].cell_start = chd_alloc_pinned(4ull * (cells + 1));
+        rb[k].entity_cap = n_entities;
+        rb[k].sorted_entity = chd_alloc_pinned(4ull * n_entities);
+        hdr[k] = chd_alloc_pinned(CHD_FETCH_HEADER_BYTES);
+    }
 
 #define PREFETCH(s)                                                                                                       \
     do {                                                                                                                  \
@@ -116,22 +126,26 @@ int main(void) {
 
     fill_inputs(&st[0], n_entities, n_subs, cells, 0);
     PREFETCH(&st[0]);
+    chd_tick_summary sum;
     for (int tick = 0; tick < 100; tick++) {
         const int64_t now = (int64_t)(tick + 1) * tick_ns;
         CHECK(chd_adopt_prefetched(e));            /* inputs of this tick were uploaded during the previous one */
         CHECK(chd_begin_interest(e, NULL, now, 1)); /* interest diff + fan-out pass start on the second stream */
-        CHECK(chd_tick(e, NULL, now, CHD_TICK_ALL | CHD_TICK_EARLY_RESULTS, NULL)); /* asynchronous */
+        CHECK(chd_tick(e, NULL, now, CHD_TICK_ALL, NULL)); /* asynchronous */
         staging* next = &st[(tick + 1) & 1];
         fill_inputs(next, n_entities, n_subs, cells, tick + 1); /* the host collects tick k+1 while tick k runs */
         PREFETCH(next);
-        chd_tick_summary sum;
-        CHECK(chd_fetch_results(e, &rb, &sum)); /* returns when the tick is done; lists were copied as they became final */
-        /* apply: sum.n_sub_new x handleSubToChannel(rb.new_sub[i], rb.new_channel[i]), sum.n_unsub x handleUnsubFromChannel,
-         * sum.n_due x fanOutDataUpdate(rb.due[i]), sum.n_handover x the orchestration half of Notify */
-        if (tick % 25 == 0)
-            printf("tick %d: %llu pairs, %llu visible entries, +%u/-%u subscriptions, %u sends, %u handovers\n", tick,
+        CHECK(chd_fetch_results_async(e, &rb[tick & 1], hdr[tick & 1])); /* returns at once: device-side sizes, pinned targets */
+        if (tick == 0) continue;
+        /* results of tick - 1, while tick runs on the GPU */
+        CHECK(chd_fetch_wait(e, &sum));
+        /* apply from rb[(tick - 1) & 1]: sum.n_sub_new x handleSubToChannel(new_sub[i], new_channel[i]), sum.n_unsub x
+         * handleUnsubFromChannel, sum.n_due x fanOutDataUpdate(due[i]), sum.n_handover x the orchestration half of Notify */
+        if ((tick - 1) % 25 == 0)
+            printf("tick %d: %llu pairs, %llu visible entries, +%u/-%u subscriptions, %u sends, %u handovers\n", tick - 1,
                    (unsigned long long)sum.n_pairs, (unsigned long long)sum.n_visible, sum.n_sub_new, sum.n_unsub, sum.n_due, sum.n_handover);
     }
+    CHECK(chd_fetch_wait(e, &sum)); /* the last tick */
     chd_destroy(e);
     free(conn);
     return 0;

@@ -86,6 +86,9 @@ chd_status chd_sync(chd_engine* e);
 
 /* Pinned host memory for the per-tick staging buffers (plain C memory, legal to hold from Go). */
 void* chd_alloc_pinned(uint64_t bytes);
+/* NUMA node of the GPU (from sysfs; -1 = unknown).  Pinned memory is placed by first touch: run the tick driver (the thread that
+ * calls chd_alloc_pinned) on that node's cores and the per-tick uploads cross no socket interconnect. */
+int chd_device_numa_node(int device);
 void chd_free_pinned(void* p);
 
 /* ---- GetChannelId, batched (spatial.go:161-180; the batch form is handleQuerySpatialChannel,

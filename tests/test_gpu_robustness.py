@@ -409,8 +409,8 @@ def test_device_owned_rings_and_channel_time_origins(chd, oracle):
         assert st_ == capi.OK, e.L.chd_last_error(e.h)
         for c in range(cells):
             assert roff[c + 1] - roff[c] == chans[c].ring_len(), (tick, c)
-        if roff[1] - roff[0] > 512 and ri[roff[0]] > 1:
-            evicted = True  # the head of cell 0's ring moved while the ring stayed above 512 entries
+        if roff[1] - roff[0] >= 512 and ri[roff[0]] > 1:
+            evicted = True  # the head of cell 0's ring moved: entries older than maxFanOutIntervalMs left once the buffer passed 512
         e.fanout_tick(t)
         s = e.summary()
         assert s.overflow == 0
