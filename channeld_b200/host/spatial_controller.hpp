@@ -159,6 +159,66 @@ class GpuStaticGrid2DSpatialController {
     }
     void FetchResults(const chd_result_buffers& buffers, chd_tick_summary* summary) { check(chd_fetch_results(engine_, &buffers, summary)); }
 
+    // Non-blocking read-back: FetchResultsAsync(k) right after Tick(k), enqueue tick k+1, then FetchWait() = results of tick k.
+    // `pinned_header` is CHD_FETCH_HEADER_BYTES of pinned host memory that stays valid until the matching FetchWait.
+    void FetchResultsAsync(const chd_result_buffers& buffers, void* pinned_header) { check(chd_fetch_results_async(engine_, &buffers, pinned_header)); }
+    chd_tick_summary FetchWait() {
+        chd_tick_summary s{};
+        check(chd_fetch_wait(engine_, &s));
+        return s;
+    }
+
+    // Subscriber lifecycle (subscription.go:34-125): AddConnection = a fresh subscriber in a free slot; RemoveConnection =
+    // UnsubscribeFromChannel on every spatial channel of the slot (what connection close does, channel.go:414-475).
+    void AddConnections(const std::vector<uint32_t>& slot, const std::vector<uint32_t>& conn_id) {
+        if (slot.size() != conn_id.size()) throw SpatialError("AddConnections: array sizes differ");
+        check(chd_add_subscribers(engine_, slot.data(), conn_id.data(), (uint32_t)slot.size()));
+    }
+    void RemoveConnections(const std::vector<uint32_t>& slot) { check(chd_remove_subscribers(engine_, slot.data(), (uint32_t)slot.size())); }
+
+    // ChannelData.OnUpdate's buffer kept on the device (data.go:149-173): append a tick's updates (CSR by cell, arrival order).
+    void InitUpdateBuffers(uint32_t capacity_per_cell) { check(chd_rings_init(engine_, capacity_per_cell)); }
+    void OnUpdates(const std::vector<uint32_t>& upd_off, const std::vector<int64_t>& arrival_ns, const std::vector<uint32_t>& sender_conn_id) {
+        if (arrival_ns.size() != sender_conn_id.size()) throw SpatialError("OnUpdates: array sizes differ");
+        check(chd_rings_append(engine_, upd_off.data(), (uint32_t)arrival_ns.size(), arrival_ns.data(), sender_conn_id.data()));
+    }
+    // Channel.startTime of every spatial channel (channel.go:178): ChannelTime = t - start.
+    void SetChannelStartTimes(const std::vector<int64_t>& start_ns) {
+        if (start_ns.size() != (size_t)cfg_.grid_cols * cfg_.grid_rows) throw SpatialError("SetChannelStartTimes: one entry per cell");
+        check(chd_set_channel_start_times(engine_, start_ns.data()));
+    }
+
+    // N GPUs, one process per GPU: X-slab of this rank + ONE all-gather of border records per tick inside TickSharded.
+    static std::vector<uint8_t> CommUniqueId() {
+        std::vector<uint8_t> id(128);
+        if (chd_comm_unique_id(id.data()) != CHD_OK) throw SpatialError(chd_last_error(nullptr));
+        return id;
+    }
+    void CommInit(const std::vector<uint8_t>& unique_id, int rank, int world, uint32_t halo_cols, uint32_t border_capacity,
+                  uint32_t migrate_subscribers = 0, uint32_t migrate_pairs = 0) {
+        if (unique_id.size() != 128) throw SpatialError("CommInit: the id is 128 bytes");
+        check(chd_comm_init(engine_, unique_id.data(), rank, world, halo_cols, border_capacity, migrate_subscribers, migrate_pairs));
+    }
+    chd_tick_summary TickSharded(const chd_query_batch* batch, int64_t t_ns, uint32_t flags = CHD_TICK_ALL) {
+        chd_tick_summary s{};
+        check(chd_tick_sharded(engine_, batch, t_ns, flags, &s));
+        return s;
+    }
+    void MigrateOut(const std::vector<uint32_t>& slot) { check(chd_migrate_out(engine_, slot.data(), (uint32_t)slot.size())); }
+    void MigrateIn(uint32_t src_rank, uint32_t first_index, const std::vector<uint32_t>& slot, const std::vector<uint32_t>& conn_id) {
+        if (slot.size() != conn_id.size()) throw SpatialError("MigrateIn: array sizes differ");
+        check(chd_migrate_in(engine_, src_rank, first_index, slot.data(), conn_id.data(), (uint32_t)slot.size()));
+    }
+    // own entities whose column now belongs to another rank: (global id, new owner)
+    std::vector<std::pair<uint32_t, uint32_t>> GetRehome(uint32_t cap) {
+        std::vector<uint32_t> id(cap ? cap : 1), dst(cap ? cap : 1);
+        uint32_t n = 0;
+        check(chd_get_rehome(engine_, id.data(), dst.data(), cap, &n));
+        std::vector<std::pair<uint32_t, uint32_t>> r;
+        for (uint32_t i = 0; i < n && i < cap; i++) r.emplace_back(id[i], dst[i]);
+        return r;
+    }
+
     // Recipients of BroadcastType_ADJACENT_CHANNELS messages (message.go:188-239), batched: CSR of subscriber slots.
     struct BroadcastSets {
         std::vector<uint32_t> status, off, slot;
