@@ -47,6 +47,10 @@ def parse():
     ap.add_argument("--no-gate", action="store_true")
     ap.add_argument("--trace-e2e", action="store_true", help="diagnostics: host-side phase times of the pipelined e2e step on stderr")
     ap.add_argument("--no-early", action="store_true", help="e2e ticks without CHD_TICK_EARLY_RESULTS")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: border exchange through the peer windows (stores over NVLink + flags) or one ncclAllGather per tick")
+    ap.add_argument("--positions", default="f32", choices=["f32", "f64"],
+                    help="e2e upload format of the (float32-valued) entity positions: the floats (chd_prefetch_entities_f32) or doubles")
     ap.add_argument("--updates-per-cell", type=int, default=8)
     ap.add_argument("--ring-len", type=int, default=64)
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
@@ -79,6 +83,7 @@ def config_dict(wc, world, scaling):
             "grid": "%dx%d" % (wc.cols, wc.rows), "parallelism": "xslab%d" % world if world > 1 else "single",
             "scaling": scaling if world > 1 else "strong",
             "tick": "build+query+interest-diff+emit-visible+fanout, positions change every step",
+            "positions": "float32-valued (unrealpb.FVector widened by float64(), pkg/unrealpb/extension.go:10-24), computed on as float64",
             "l2": "inputs larger than L2 in effect: every step streams the expanded visible list (4 bytes x V, about 1.95 GB on the "
                   "1M/100K workload) through the 126 MB L2, evicting the step's inputs; no explicit flush"}
 
@@ -90,11 +95,18 @@ def oracle_grid(wc):
 
 
 def make_snapshots(wc):
-    """Two position snapshots (A, B): B = A displaced by up to 60 units per axis (SURVEY §8d #3 velocity)."""
+    """Two position snapshots (A, B): B = A displaced by up to 60 units per axis (SURVEY §8d #3 velocity).  Entity positions are
+    float32-VALUED doubles: in channeld they arrive as unrealpb.FVector floats and are widened by float64(*vec.X)
+    (pkg/unrealpb/extension.go:10-24).  Both arms compute on the same doubles; the e2e leg of the GPU arm uploads the floats."""
     from channeld_b200 import synth
 
+    def f32v(a):
+        return a.astype(np.float32).astype(np.float64)
+
     ax, az = synth.entities(wc)
+    ax, az = f32v(ax), f32v(az)
     bx, bz = synth.move_entities(wc, ax, az, 1, 60.0)
+    bx, bz = f32v(bx), f32v(bz)
     snaps = []
     for x, z in ((ax, az), (bx, bz)):
         conn, cx, cz, r = synth.subscribers(wc, x, z)
@@ -275,6 +287,8 @@ def run_ours(args):
             uid.copy_(torch.frombuffer(bytearray(engine.Engine.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
         e.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world, halo, border_cap)
+        if args.exchange == "nccl":
+            e.use_collective(True)
         info = e.comm_info()
         assert (info["col_lo"], info["col_hi"]) == (col_lo, col_hi), (info, col_lo, col_hi)
         e.set_entity_ids(gid)
@@ -290,14 +304,19 @@ def run_ours(args):
             t, a = pinned((len(src),), torch.float64)
             a[:] = src
             h[k] = t
-        host_in.append(h)
         dev_in.append({k: v.to(dev) for k, v in h.items()})
+        for k in ("x", "z"):  # the same positions as the floats they are at the source (e2e upload: 8 bytes per entity)
+            t, a = pinned((len(h[k]),), torch.float32)
+            a[:] = h[k].numpy()
+            assert np.array_equal(a.astype(np.float64), h[k].numpy()), "bench positions must be float32-valued"
+            h[k + "f"] = t
+        host_in.append(h)
     t_sub, a_sub = pinned((S,), torch.int32)
     a_sub[:] = sub_idx.view(np.int32)
     d_sub = t_sub.to(dev)
 
     n_e2e = args.e2e_steps or min(args.steps, 30)
-    n_steps_total = 1 + args.warmup + args.steps + 3 * (2 + n_e2e) + 4 + args.expanded_steps + 2
+    n_steps_total = 1 + args.warmup + args.steps + 4 * (2 + n_e2e) + 4 + args.expanded_steps + 2
     # one ring snapshot per step (arrival times follow the tick clock); bound the staging memory for huge grids
     ring_len, upc = args.ring_len, args.updates_per_cell
     while wc.cells * ring_len * 20 * n_steps_total > (768 << 20) and ring_len > 4:
@@ -451,7 +470,8 @@ def run_ours(args):
             pass
         stage = {}
         for name, sid in (("build", capi.STAGE_BUILD), ("interest", capi.STAGE_INTEREST), ("emit", capi.STAGE_EMIT),
-                          ("emit_kernel", capi.STAGE_EMIT_KERNEL), ("fanout", capi.STAGE_FANOUT)):
+                          ("emit_kernel", capi.STAGE_EMIT_KERNEL), ("fanout", capi.STAGE_FANOUT)) + (
+                (("export", capi.STAGE_EXPORT), ("exchange", capi.STAGE_EXCHANGE), ("import", capi.STAGE_IMPORT)) if world > 1 else ()):
             tot, n = e.profile_get(sid)
             stage[name] = tot / max(n, 1)
         timeline = {}
@@ -494,11 +514,16 @@ def run_ours(args):
 
         phase_acc = {}
 
+        pos_f32 = [args.positions == "f32"]
+
         def prefetch_inputs(i):
             dn, rn = host_in[i % 2], rings_host[i]
             ck(L.chd_prefetch_rings(e.h, capi.ptr(rn["off"]), rn["n"], capi.ptr(rn["arr"]), capi.ptr(rn["snd"]), capi.ptr(rn["idx"]), capi.ptr(rn["cmi"])))
             ck(L.chd_prefetch_queries(e.h, C.byref(batches_host[i % 2])))
-            ck(L.chd_prefetch_entities(e.h, capi.ptr(dn["x"]), capi.ptr(dn["z"]), n_own))
+            if pos_f32[0]:
+                ck(L.chd_prefetch_entities_f32(e.h, capi.ptr(dn["xf"]), capi.ptr(dn["zf"]), n_own))
+            else:
+                ck(L.chd_prefetch_entities(e.h, capi.ptr(dn["x"]), capi.ptr(dn["z"]), n_own))
 
         def e2e_step(i, expanded=False, pipelined=False, early=not args.no_early):
             """Host inputs -> H2D -> one batched tick -> D2H of everything a channeld host consumes (chd_fetch_results).
@@ -518,7 +543,10 @@ def run_ours(args):
                 # queries + rings go up first and the interest / fan-out stages start on the second stream while the
                 # (much larger) position upload is still in flight
                 ck(L.chd_begin_interest(e.h, C.byref(batches_host[i % 2]), t_ns, 1))
-                ck(L.chd_set_entities(e.h, capi.ptr(d["x"]), capi.ptr(d["z"]), n_own))
+                if pos_f32[0]:
+                    ck(L.chd_set_entities_f32(e.h, capi.ptr(d["xf"]), capi.ptr(d["zf"]), n_own))
+                else:
+                    ck(L.chd_set_entities(e.h, capi.ptr(d["x"]), capi.ptr(d["z"]), n_own))
             tick_flags = capi.TICK_ALL | (capi.TICK_EARLY_RESULTS if early else 0)
             if world > 1:
                 ck(L.chd_tick_sharded(e.h, None, t_ns, tick_flags, None))
@@ -537,7 +565,7 @@ def run_ours(args):
             for k_, v_ in (("launch", tp1 - tp0), ("prefetch", tp2 - tp1), ("fetch", tp3 - tp2)):
                 phase_acc[k_] = phase_acc.get(k_, 0.0) + v_
             phase_acc["n"] = phase_acc.get("n", 0) + 1
-            h2d = 16 * n_own + 24 * S + (wc.cells + 1) * 4 + rg["n"] * 20 + wc.cells * 8
+            h2d = (8 if pos_f32[0] else 16) * n_own + 24 * S + (wc.cells + 1) * 4 + rg["n"] * 20 + wc.cells * 8
             d2h = (C.sizeof(capi.TickSummary) + (S + 1) * 4 + 12 * int(summ.n_pairs) + 8 * (int(summ.n_sub_new) + int(summ.n_unsub))
                    + 48 * int(summ.n_due) + 12 * int(summ.n_handover) + 4 * S + (S + 1) * 8 + (wc.cells + 1) * 4 + 4 * int(summ.n_entities_in_world)
                    + (4 * int(summ.n_visible) if expanded else 0))
@@ -576,24 +604,36 @@ def run_ours(args):
         base += 2 + n_e2e
         sets = [(rb, rb_keep), (rb2, rb2_keep)]
 
+        host_acc = {"tick": 0.0, "prefetch": 0.0, "fetch_async": 0.0, "fetch_wait": 0.0, "n": 0}
+
         def async_enqueue(i):
             t_ns = (i + 1) * TICK_NS
+            h0 = time.perf_counter()
             ck(L.chd_adopt_prefetched(e.h))
             if world > 1:
                 ck(L.chd_tick_sharded(e.h, None, t_ns, capi.TICK_ALL, None))
             else:
                 ck(L.chd_begin_interest(e.h, None, t_ns, 1))
                 ck(L.chd_tick(e.h, None, t_ns, capi.TICK_ALL, None))
+            h1 = time.perf_counter()
             prefetch_inputs(i + 1)
+            h2 = time.perf_counter()
             r_, k_ = sets[i % 2]
             ck(L.chd_fetch_results_async(e.h, C.byref(r_), capi.ptr(k_["hdr"])))
+            h3 = time.perf_counter()
+            host_acc["tick"] += h1 - h0
+            host_acc["prefetch"] += h2 - h1
+            host_acc["fetch_async"] += h3 - h2
+            host_acc["n"] += 1
 
         def async_run(first, n):
             got = []
             async_enqueue(first)
             for i in range(first + 1, first + n):
                 async_enqueue(i)
+                h0 = time.perf_counter()
                 ck(L.chd_fetch_wait(e.h, C.byref(summ)))  # results of step i - 1, while step i runs
+                host_acc["fetch_wait"] += time.perf_counter() - h0
                 got.append((int(summ.n_pairs), int(summ.n_due), int(summ.n_sub_new), int(summ.n_unsub), int(summ.n_handover), int(summ.n_entities_in_world)))
             ck(L.chd_fetch_wait(e.h, C.byref(summ)))
             got.append((int(summ.n_pairs), int(summ.n_due), int(summ.n_sub_new), int(summ.n_unsub), int(summ.n_handover), int(summ.n_entities_in_world)))
@@ -604,10 +644,28 @@ def run_ours(args):
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
+        for k_ in host_acc:
+            host_acc[k_] = 0
         got_async = async_run(base + 2, n_e2e)
         torch.cuda.synchronize()
         barrier()
         e2e_async_dt = time.perf_counter() - t0
+        host_phases = {k_: round(v_ / max(host_acc["n"], 1) * 1e3, 4) for k_, v_ in host_acc.items() if k_ != "n"}
+        e2e_async_f64_dt = None
+        if pos_f32[0]:  # the same loop uploading the positions as doubles (16 bytes per entity), for comparison
+            pos_f32[0] = False
+            base2 = base + 2 + n_e2e
+            prefetch_inputs(base2)
+            async_run(base2, 2)
+            barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            got_async = async_run(base2 + 2, n_e2e)
+            torch.cuda.synchronize()
+            barrier()
+            e2e_async_f64_dt = time.perf_counter() - t0
+            pos_f32[0] = True
+            base = base2
         npairs_, ndue_, nnew_, nun_, nho_, nin_ = got_async[-1]
         d2h_async = (256 + (S + 1) * 4 + 12 * npairs_ + 8 * (nnew_ + nun_) + 48 * ndue_ + 12 * nho_ + 4 * S + (S + 1) * 8 + (wc.cells + 1) * 4 + 4 * nin_)
         # the asynchronously fetched lists are the same lists: check the last step against a synchronous fetch of the same state
@@ -641,9 +699,10 @@ def run_ours(args):
 
     # ---- reductions over ranks
     if world > 1:
-        t = torch.tensor([ms, e2e_dt, e2e_serial_dt, e2e_async_dt], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, e2e_dt, e2e_serial_dt, e2e_async_dt, e2e_async_f64_dt or 0.0], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_dt, e2e_serial_dt, e2e_async_dt = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+        e2e_async_f64_dt = float(t[4]) or None
         d2h = d2h_async
         c = torch.tensor([float(sm.n_pairs), float(sm.n_visible), float(sm.n_due), float(launches), float(h2d), float(d2h)],
                          dtype=torch.float64, device=dev)
@@ -687,11 +746,17 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": S_total * n_e2e / e2e_async_dt, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h if world > 1 else d2h_async),
                     "ms_per_step": e2e_async_dt / n_e2e * 1e3,
+                    "host_ms_per_step": host_phases,
                     "pipeline": "double-buffered inputs AND results through the C ABI: chd_prefetch_{rings,queries,entities} upload the inputs of step "
                                 "i+1 (pinned host memory) while the kernels of step i run; chd_fetch_results_async writes the results of step i "
                                 "into pinned host buffers (device-side sizes) while step i+1 — already enqueued — runs; chd_fetch_wait hands the "
                                 "host step i's results.  Every step uploads one full position snapshot + its queries + rings and reads back its "
                                 "results inside the timed region; checked equal to a synchronous chd_fetch_results",
+                    "positions": ("uploaded as the float32 values they are at the source (unrealpb.FVector), 8 bytes per entity, widened exactly "
+                                  "on the device (chd_prefetch_entities_f32)") if args.positions == "f32" else "uploaded as float64, 16 bytes per entity",
+                    "f64_upload": ({"value": S_total * n_e2e / e2e_async_f64_dt, "ms_per_step": e2e_async_f64_dt / n_e2e * 1e3,
+                                    "h2d_bytes_per_step": int(h2d) + 8 * int(N_total if world > 1 else n_own),
+                                    "note": "same loop with chd_prefetch_entities (16 bytes per entity on PCIe)"} if e2e_async_f64_dt else None),
                     "sync_fetch": {"value": S_total * n_e2e / e2e_dt, "ms_per_step": e2e_dt / n_e2e * 1e3,
                                    "note": "same pipeline with the blocking chd_fetch_results + CHD_TICK_EARLY_RESULTS (round-1 form): the host waits "
                                            "for step i before it enqueues step i+1"},
@@ -703,7 +768,8 @@ def run_ours(args):
                               "HBM for GPU-side consumers (e2e_expanded copies it as well)"},
             "e2e_expanded": e2e_exp,
             "gpu_launches": int(launches),
-            "collectives": {"nccl_all_gathers_issued_by_the_library_rank0": e.collective_count(), "where": "chd_tick_sharded (libchd_b200.so)"} if world > 1 else None,
+            "collectives": {"exchange": {0: None, 1: "one ncclAllGather per tick", 2: "peer windows: stores over NVLink into CUDA-IPC-mapped receive buffers + 64-bit flags, no collective call on the tick path"}[e.exchange_mode()],
+                            "nccl_all_gathers_issued_by_the_library_rank0": e.collective_count(), "where": "chd_tick_sharded (libchd_b200.so)"} if world > 1 else None,
             "roofline": {"bound": "hbm", "kernel": "emit_visible_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_dram_bytes_per_launch": dram_bytes, "algorithmic_dram_bytes": "4*V + 4*N (writes + one read of the CSR)",

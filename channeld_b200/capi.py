@@ -111,16 +111,16 @@ class TickSummary(C.Structure):
 # every symbol include/chd_gpu.h declares (checked by tests/test_abi.py against the header text)
 SYMBOLS = [
     "chd_abi_version", "chd_default_limits", "chd_create", "chd_destroy", "chd_last_error", "chd_set_stream", "chd_sync",
-    "chd_alloc_pinned", "chd_free_pinned", "chd_device_numa_node", "chd_cell_of", "chd_cell_of_valid", "chd_set_entities", "chd_prefetch_entities", "chd_prefetch_queries", "chd_prefetch_rings", "chd_adopt_prefetched", "chd_entity_buffers", "chd_set_entity_count",
+    "chd_alloc_pinned", "chd_free_pinned", "chd_device_numa_node", "chd_cell_of", "chd_cell_of_valid", "chd_set_entities", "chd_prefetch_entities", "chd_set_entities_f32", "chd_prefetch_entities_f32", "chd_prefetch_queries", "chd_prefetch_rings", "chd_adopt_prefetched", "chd_entity_buffers", "chd_set_entity_count",
     "chd_assign_cells", "chd_build", "chd_set_subscribers", "chd_query_channel_ids", "chd_update_interest",
     "chd_emit_visible", "chd_set_rings", "chd_fanout_tick", "chd_summary", "chd_tick", "chd_begin_interest", "chd_get_cells", "chd_get_pairs",
     "chd_get_query_status", "chd_get_diff", "chd_get_visible", "chd_get_visible_slot", "chd_get_due", "chd_fetch_results", "chd_get_handover", "chd_device_view",
     "chd_set_slab", "chd_set_entity_ids", "chd_export_border", "chd_import_halo", "chd_due_classes", "chd_set_subscriber_types", "chd_adjacent_broadcast", "chd_get_adjacent_channels",
     "chd_get_regions", "chd_damping_interval_ms", "chd_launch_count", "chd_profile_enable", "chd_profile_get", "chd_profile_timeline", "chd_enable_graphs",
     "chd_graph_launch_count",
-    "chd_add_subscribers", "chd_remove_subscribers", "chd_fetch_results_async", "chd_fetch_wait", "chd_rings_init", "chd_rings_append", "chd_get_rings", "chd_set_channel_start_times", "chd_set_payload_bytes", "chd_assemble_payloads", "chd_frame_packets", "chd_comm_unique_id", "chd_comm_init", "chd_comm_info", "chd_comm_destroy", "chd_tick_sharded", "chd_collective_count", "chd_migrate_out", "chd_migrate_in", "chd_get_rehome",
+    "chd_add_subscribers", "chd_remove_subscribers", "chd_fetch_results_async", "chd_fetch_wait", "chd_rings_init", "chd_rings_append", "chd_get_rings", "chd_set_channel_start_times", "chd_set_payload_bytes", "chd_assemble_payloads", "chd_frame_packets", "chd_comm_unique_id", "chd_comm_init", "chd_comm_info", "chd_comm_destroy", "chd_tick_sharded", "chd_collective_count", "chd_comm_exchange_mode", "chd_comm_use_collective", "chd_migrate_out", "chd_migrate_in", "chd_get_rehome",
 ]
-STAGE_BUILD, STAGE_INTEREST, STAGE_EMIT, STAGE_EMIT_KERNEL, STAGE_FANOUT, STAGE_TICK = range(6)
+STAGE_BUILD, STAGE_INTEREST, STAGE_EMIT, STAGE_EMIT_KERNEL, STAGE_FANOUT, STAGE_TICK, STAGE_EXPORT, STAGE_EXCHANGE, STAGE_IMPORT = range(9)
 
 _lib = None
 
@@ -162,6 +162,10 @@ def lib():
     L.chd_set_entities.argtypes = [vp, vp, vp, C.c_uint32]
     L.chd_prefetch_entities.restype = C.c_int
     L.chd_prefetch_entities.argtypes = [vp, vp, vp, C.c_uint32]
+    L.chd_set_entities_f32.restype = C.c_int
+    L.chd_set_entities_f32.argtypes = [vp, vp, vp, C.c_uint32]
+    L.chd_prefetch_entities_f32.restype = C.c_int
+    L.chd_prefetch_entities_f32.argtypes = [vp, vp, vp, C.c_uint32]
     L.chd_prefetch_queries.restype = C.c_int
     L.chd_prefetch_queries.argtypes = [vp, vp]
     L.chd_prefetch_rings.restype = C.c_int
@@ -286,6 +290,10 @@ def lib():
     L.chd_tick_sharded.argtypes = [vp, C.POINTER(QueryBatch), C.c_int64, C.c_uint32, C.POINTER(TickSummary)]
     L.chd_collective_count.restype = C.c_uint64
     L.chd_collective_count.argtypes = [vp]
+    L.chd_comm_exchange_mode.restype = C.c_int
+    L.chd_comm_exchange_mode.argtypes = [vp]
+    L.chd_comm_use_collective.restype = C.c_int
+    L.chd_comm_use_collective.argtypes = [vp, C.c_int]
     _lib = L
     return L
 

@@ -18,9 +18,11 @@ namespace chd {
 // the prefix of Notify, spatial.go:612-626: GetChannelId(old) != GetChannelId(new)).
 __global__ void __launch_bounds__(256) assign_cells_kernel(GridDev g, const double* __restrict__ x, const double* __restrict__ z,
                                                            uint32_t n, uint32_t* __restrict__ key,
-                                                           const uint32_t* __restrict__ prev_key, HandoverOut ho) {
+                                                           const uint32_t* __restrict__ prev_key, HandoverOut ho,
+                                                           unsigned long long* bump_epoch) {
     __shared__ uint32_t s_cnt, s_base;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bump_epoch && i == 0) *bump_epoch = chd_next_epoch(*bump_epoch);  // (the border export's compaction follows in the same graph)
     if (prev_key) {
         if (threadIdx.x == 0) s_cnt = 0;
         __syncthreads();
@@ -357,6 +359,27 @@ __global__ void __launch_bounds__(256)
     const uint32_t v = src[i];
 #pragma unroll
     for (uint32_t k = 1; k < 4; k++) dst4[(size_t)k * stride + k + i] = v;  // copy 0 is src itself (dst4 == src)
+}
+
+// float -> double widening of a position upload (chd_set_entities_f32): channeld's entity positions arrive as unrealpb.FVector
+// (three floats, pkg/unrealpb/unreal_common.proto:55-59) and become SpatialInfo doubles by float64(*vec.X)
+// (pkg/unrealpb/extension.go:10-24).  That conversion is exact, so doing it here instead of on the host halves the bytes a
+// position snapshot costs on PCIe without changing a single result bit.
+__global__ void __launch_bounds__(256) widen_positions_kernel(const float* __restrict__ xf, const float* __restrict__ zf, double* x, double* z, uint32_t n) {
+    const uint32_t i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    if (i4 >= n) return;
+    if (i4 + 4 <= n) {  // cudaMalloc'd buffers: 16-byte aligned at i4
+        const float4 a = *reinterpret_cast<const float4*>(xf + i4), b = *reinterpret_cast<const float4*>(zf + i4);
+        *reinterpret_cast<double2*>(x + i4) = make_double2((double)a.x, (double)a.y);
+        *reinterpret_cast<double2*>(x + i4 + 2) = make_double2((double)a.z, (double)a.w);
+        *reinterpret_cast<double2*>(z + i4) = make_double2((double)b.x, (double)b.y);
+        *reinterpret_cast<double2*>(z + i4 + 2) = make_double2((double)b.z, (double)b.w);
+    } else {
+        for (uint32_t i = i4; i < n; i++) {
+            x[i] = (double)xf[i];
+            z[i] = (double)zf[i];
+        }
+    }
 }
 
 }  // namespace chd

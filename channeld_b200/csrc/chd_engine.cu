@@ -159,9 +159,11 @@ void chd_destroy(chd_engine* e) {
     if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
     if (e->dl_stream) cudaStreamDestroy(e->dl_stream);
     if (e->dl_stream_b) cudaStreamDestroy(e->dl_stream_b);
+    if (e->dl_stream_c) cudaStreamDestroy(e->dl_stream_c);
     for (int i = 0; i < 2; i++) {
         if (e->ev_fetch_a[i]) cudaEventDestroy(e->ev_fetch_a[i]);
         if (e->ev_fetch_b[i]) cudaEventDestroy(e->ev_fetch_b[i]);
+        if (e->ev_fetch_done[i]) cudaEventDestroy(e->ev_fetch_done[i]);
     }
     if (e->ev_prep_done) cudaEventDestroy(e->ev_prep_done);
     if (e->ev_build_done) cudaEventDestroy(e->ev_build_done);

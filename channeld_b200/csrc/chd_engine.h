@@ -53,7 +53,7 @@ struct chd_engine {
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_interest = nullptr, ev_pairs = nullptr;
     bool interest_pending = false, pending_fanout = false;  // chd_begin_interest issued, not yet joined by chd_tick
-    GraphSlot g_build[4], g_build_b[4], g_interest[4], g_interest_b[4], g_emit_prep[2], g_fanout[4], g_export[4], g_import[2];  // build / export: [key buffer][position buffer]
+    GraphSlot g_build[4], g_build_b[4], g_interest[4], g_interest_b[4], g_emit_prep[2], g_fanout[4], g_export[8], g_import[4];  // build / export: [key buffer][position buffer]
     uint64_t graph_launches = 0, graph_captures = 0;
     uint32_t* d_key_a = nullptr;  // identity of the first key buffer (graph slot selection)
     int64_t* d_time = nullptr;      // [0] = now_ns of the last update_interest, [1] = t_ns of the last fanout_tick
@@ -74,6 +74,7 @@ struct chd_engine {
     // chd_prefetch_entities: the BACK buffers receive the next tick's positions on `up_stream` while the current tick runs;
     // chd_adopt_prefetched swaps front and back.  ev_pos_read[b] = last assign_cells that read buffer pair b.
     double *d_xb[2] = {nullptr, nullptr}, *d_zb[2] = {nullptr, nullptr};
+    float* d_pos_f32[2] = {nullptr, nullptr};  // float staging of chd_set_entities_f32 [0] / chd_prefetch_entities_f32 [1]: x then z
     int pos_buf = 0;
     cudaStream_t up_stream = nullptr;
     cudaEvent_t ev_upload = nullptr, ev_pos_read[2] = {nullptr, nullptr};
@@ -193,6 +194,12 @@ struct chd_engine {
     // chd_fetch_results_async: completion events of the two copy phases; the next tick is ordered after them on the device
     // (two fetches may be outstanding: the host waits for tick k-1 after it has enqueued tick k and its fetch)
     cudaEvent_t ev_fetch_a[2] = {nullptr, nullptr}, ev_fetch_b[2] = {nullptr, nullptr};
+    // chd_fetch_results_async is two hops: result arrays -> a device-side snapshot (ev_fetch_a/b: the next tick may overwrite the
+    // arrays) -> pinned host memory at PCIe speed on its own stream (ev_fetch_done: chd_fetch_wait)
+    cudaEvent_t ev_fetch_done[2] = {nullptr, nullptr};
+    cudaStream_t dl_stream_c = nullptr;
+    uint8_t* d_fetch_stage[2] = {nullptr, nullptr};
+    uint64_t fetch_stage_bytes[2] = {0, 0};
     void* fetch_header[2] = {nullptr, nullptr};
     uint64_t fetch_issued = 0, fetch_waited = 0;
     bool fetch_guard = false;
@@ -240,6 +247,14 @@ struct chd_engine {
     uint32_t mig_subs = 0, mig_pairs = 0;  // migration blob capacities (0: no subscriber migration)
     bool mig_packed = false;          // chd_migrate_out was called for the coming tick
     uint32_t *d_rec_local = nullptr, *d_rec_all = nullptr;
+    unsigned long long* assign_bump = nullptr;  // epoch the next assign_cells_kernel launch bumps for its caller (border export)
+    // peer exchange (chd_shard.cuh): this rank's window, the peers' windows mapped with CUDA IPC, device-side sequence / counts
+    bool peer_push = false, peer_mapped = false;
+    uint32_t* d_peer_win = nullptr;
+    void* peer_base[16] = {};
+    unsigned long long* d_xchg_seq = nullptr;
+    uint32_t *d_push_done = nullptr, *d_peer_count = nullptr;
+    uint64_t xchg_seq = 0;  // host mirror of the device sequence (selects the window buffer a graph variant is captured for)
     uint64_t n_collectives = 0;
     // border export scratch
     uint32_t *d_bflag = nullptr, *d_boff = nullptr;

@@ -80,7 +80,7 @@ chd_status chd_cell_of_valid(chd_engine* e, const double* x, const double* z, ui
         const uint32_t m = n - b < chunk ? n - b : chunk;
         CU(e, cudaMemcpyAsync(dx, x + b, sizeof(double) * m, cudaMemcpyDefault, e->stream));
         CU(e, cudaMemcpyAsync(dz, z + b, sizeof(double) * m, cudaMemcpyDefault, e->stream));
-        assign_cells_kernel<<<blocks_for(m, 256), 256, 0, e->stream>>>(e->g, dx, dz, m, dk, nullptr, ho);
+        assign_cells_kernel<<<blocks_for(m, 256), 256, 0, e->stream>>>(e->g, dx, dz, m, dk, nullptr, ho, nullptr);
         KCHECK(e);
         cell_key_to_id_kernel<<<blocks_for(m, 256), 256, 0, e->stream>>>(dk, m, e->g.cells, e->g.id_start, dv);
         KCHECK(e);
@@ -139,6 +139,72 @@ chd_status chd_prefetch_entities(chd_engine* e, const double* x, const double* z
     if (e->pos_read_recorded[back]) CU(e, cudaStreamWaitEvent(e->up_stream, e->ev_pos_read[back], 0));
     CU(e, cudaMemcpyAsync(e->d_xb[back], x, sizeof(double) * n, cudaMemcpyDefault, e->up_stream));
     CU(e, cudaMemcpyAsync(e->d_zb[back], z, sizeof(double) * n, cudaMemcpyDefault, e->up_stream));
+    CU(e, cudaEventRecord(e->ev_upload, e->up_stream));
+    e->staged = true;
+    e->staged_n = n;
+    return CHD_OK;
+}
+
+// float uploads (see widen_positions_kernel): the floats land in a staging buffer (or are read in place when they already live on
+// the device) and are widened into the double buffers on the same stream, so everything downstream is unchanged.
+static chd_status widen_upload(chd_engine* e, int which, const float* x, const float* z, uint32_t n, double* dx, double* dz, cudaStream_t s) {
+    if (!n) return CHD_OK;
+    const float *sx = x, *sz = z;
+    if (!(chd_is_device_ptr(e, x) && chd_is_device_ptr(e, z))) {
+        if (!e->d_pos_f32[which] && !dalloc(e, &e->d_pos_f32[which], 2ull * e->lim.max_entities + 8)) return CHD_ERR_CUDA;
+        float* stage_x = e->d_pos_f32[which];
+        float* stage_z = stage_x + (((size_t)e->lim.max_entities + 3) & ~(size_t)3);
+        CU(e, cudaMemcpyAsync(stage_x, x, sizeof(float) * n, cudaMemcpyDefault, s));
+        CU(e, cudaMemcpyAsync(stage_z, z, sizeof(float) * n, cudaMemcpyDefault, s));
+        sx = stage_x;
+        sz = stage_z;
+    } else if ((((uintptr_t)x) | ((uintptr_t)z)) & 15) {
+        e->fail("float positions on the device must be 16-byte aligned");
+        return CHD_ERR_INVALID;
+    }
+    widen_positions_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, s>>>(sx, sz, dx, dz, n);
+    KCHECK(e);
+    return CHD_OK;
+}
+
+chd_status chd_set_entities_f32(chd_engine* e, const float* x, const float* z, uint32_t n) {
+    if (!e || (n && (!x || !z))) return CHD_ERR_INVALID;
+    if (n > e->lim.max_entities) {
+        e->fail("chd_set_entities_f32: %u > max_entities %u", n, e->lim.max_entities);
+        return CHD_ERR_CAPACITY;
+    }
+    CU(e, cudaSetDevice(e->device));
+    if (n != e->n_own) e->have_prev_key = false;
+    chd_status st = widen_upload(e, 0, x, z, n, e->d_x, e->d_z, e->stream);
+    if (st != CHD_OK) return st;
+    e->pos_x = e->d_x;
+    e->pos_z = e->d_z;
+    e->n_own = n;
+    e->n_halo = 0;
+    e->halo_on_device = false;
+    e->assigned = false;
+    e->entities_dirty = true;
+    return CHD_OK;
+}
+
+chd_status chd_prefetch_entities_f32(chd_engine* e, const float* x, const float* z, uint32_t n) {
+    if (!e || (n && (!x || !z))) return CHD_ERR_INVALID;
+    if (n > e->lim.max_entities) {
+        e->fail("chd_prefetch_entities_f32: %u > max_entities %u", n, e->lim.max_entities);
+        return CHD_ERR_CAPACITY;
+    }
+    CU(e, cudaSetDevice(e->device));
+    const int back = e->pos_buf ^ 1;
+    {
+        chd_status st = chd_ensure_upload_stream(e);
+        if (st != CHD_OK) return st;
+    }
+    if (!e->d_xb[back]) {
+        if (!dalloc(e, &e->d_xb[back], e->lim.max_entities) || !dalloc(e, &e->d_zb[back], e->lim.max_entities)) return CHD_ERR_CUDA;
+    }
+    if (e->pos_read_recorded[back]) CU(e, cudaStreamWaitEvent(e->up_stream, e->ev_pos_read[back], 0));
+    chd_status st = widen_upload(e, 1, x, z, n, e->d_xb[back], e->d_zb[back], e->up_stream);
+    if (st != CHD_OK) return st;
     CU(e, cudaEventRecord(e->ev_upload, e->up_stream));
     e->staged = true;
     e->staged_n = n;
@@ -229,9 +295,10 @@ chd_status chd_assign_cells_impl(chd_engine* e) {
     if (st != CHD_OK) return st;
     if (e->n_own) {
         assign_cells_kernel<<<blocks_for(e->n_own, 256), 256, 0, e->stream>>>(e->g, e->pos_x ? e->pos_x : e->d_x, e->pos_z ? e->pos_z : e->d_z,
-                                                                              e->n_own, e->d_key, prev, ho);
+                                                                              e->n_own, e->d_key, prev, ho, e->assign_bump);
         KCHECK(e);
         e->have_prev_key = true;
+        e->assign_bump = nullptr;  // consumed
     }
     e->n_halo = 0;
     e->assigned = true;

@@ -16,7 +16,7 @@ struct PackSeg {
     uint32_t count_is_u64;
 };
 struct PackArgs {
-    PackSeg seg[12];
+    PackSeg seg[16];
     int n;
     uint32_t* truncated;  // pinned: set to 1 if a list did not fit its buffer
 };
@@ -342,29 +342,97 @@ chd_status chd_fetch_results_async(chd_engine* e, const chd_result_buffers* b, v
     if (b->handover_entity) A2.seg[A2.n++] = seg(e->d_ho_entity, b->handover_entity, &ctr->n_handover, 0, hcap, 1, 0);
     if (b->handover_src) A2.seg[A2.n++] = seg(e->d_ho_src, b->handover_src, &ctr->n_handover, 0, hcap, 1, 0);
     if (b->handover_dst) A2.seg[A2.n++] = seg(e->d_ho_dst, b->handover_dst, &ctr->n_handover, 0, hcap, 1, 0);
-    cudaStream_t sa = e->dl_stream, sb = e->dl_stream_b;
-    CU(e, cudaStreamWaitEvent(sa, e->ev_pairs, 0));
-    if (e->build_done_recorded) CU(e, cudaStreamWaitEvent(sa, e->ev_build_done, 0));
-    if (A.n) {
-        pack_kernel<<<dim3(24, (unsigned)A.n), 256, 0, sa>>>(A);
-        KCHECK(e);
-    }
-    if (A2.n) {
-        pack_kernel<<<dim3(8, (unsigned)A2.n), 256, 0, sa>>>(A2);
-        KCHECK(e);
-    }
-    CU(e, cudaEventRecord(e->ev_fetch_a[fi], sa));
-    // phase B: after the fan-out pass and the emit preparation; the counters travel last
+    // phase B: final after the fan-out pass and the emit preparation; the counters travel last
     PackArgs B{};
     B.truncated = A.truncated;
     if (b->due) B.seg[B.n++] = seg(e->d_due, b->due, &ctr->n_due, 0, std::min<uint64_t>(b->due_cap, e->lim.max_due), sizeof(chd_due) / 4, 0);
     if (b->vis_off) B.seg[B.n++] = seg(e->d_vis_off, b->vis_off, nullptr, (uint64_t)S + 1, (uint64_t)S + 1, 2, 0);
     B.seg[B.n++] = seg(ctr, pinned_header, nullptr, sizeof(Counters) / 4, sizeof(Counters) / 4, 1, 0);
+    // ---- hop 1: snapshot into device staging (microseconds: the next tick is ordered after THIS, not after the PCIe transfer);
+    //      hop 2: staging -> the caller's pinned buffers on a stream of its own, sized by the snapshot's own copy of the counts
+    auto up16 = [](uint64_t v) { return (v + 15) & ~(uint64_t)15; };
+    uint64_t need = 0;
+    PackArgs* sets[3] = {&A, &A2, &B};
+    for (PackArgs* pa : sets)
+        for (int k = 0; k < pa->n; k++) need += up16(std::max<uint64_t>(pa->seg[k].cap, pa->seg[k].fixed) * pa->seg[k].elem_words * 4);
+    need += 2 * up16(sizeof(Counters)) + 64;
+    if (e->fetch_stage_bytes[fi] < need) {
+        chd_dfree(e, e->d_fetch_stage[fi]);
+        e->d_fetch_stage[fi] = nullptr;
+        e->fetch_stage_bytes[fi] = 0;
+        if (!dalloc(e, &e->d_fetch_stage[fi], need)) return CHD_ERR_CUDA;
+        e->fetch_stage_bytes[fi] = need;
+    }
+    if (!e->dl_stream_c) {  // high priority like the other read-back streams: its CTAs must not queue behind the emit kernel's grid
+        int lo_p = 0, hi_p = 0;
+        CU(e, cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+        CU(e, cudaStreamCreateWithPriority(&e->dl_stream_c, cudaStreamNonBlocking, hi_p));
+    }
+    if (!e->ev_fetch_done[fi]) CU(e, cudaEventCreateWithFlags(&e->ev_fetch_done[fi], cudaEventDisableTiming));
+    uint8_t* cursor = e->d_fetch_stage[fi];
+    auto carve = [&](uint64_t bytes) {
+        uint8_t* p = cursor;
+        cursor += up16(bytes);
+        return p;
+    };
+    Counters* ctr_a = reinterpret_cast<Counters*>(carve(sizeof(Counters)));  // the counts as they stand when phase A / B is final
+    Counters* ctr_b = reinterpret_cast<Counters*>(carve(sizeof(Counters)));
+    uint32_t* npairs_s = reinterpret_cast<uint32_t*>(carve(16));
+    auto staged_count = [&](const void* cnt, Counters* snap) -> const void* {
+        if (!cnt) return nullptr;
+        if (cnt == (const void*)(pb.off + S)) return npairs_s;
+        const uintptr_t o = (uintptr_t)cnt - (uintptr_t)ctr;
+        return o < sizeof(Counters) ? (const void*)((const uint8_t*)snap + o) : cnt;
+    };
+    PackArgs H[3] = {};  // hop 2 of A, A2, B
+    for (int j = 0; j < 3; j++) {
+        PackArgs* pa = sets[j];
+        H[j].truncated = pa->truncated;
+        H[j].n = pa->n;
+        for (int k = 0; k < pa->n; k++) {
+            PackSeg& d1 = pa->seg[k];
+            void* st = carve(std::max<uint64_t>(d1.cap, d1.fixed) * d1.elem_words * 4);
+            H[j].seg[k] = d1;
+            H[j].seg[k].src = st;
+            H[j].seg[k].count_ptr = staged_count(d1.count_ptr, j == 2 ? ctr_b : ctr_a);
+            d1.dst = st;  // hop 1 writes the snapshot
+        }
+    }
+    // hop 1 also snapshots the counts themselves
+    A.seg[A.n++] = seg(ctr, ctr_a, nullptr, sizeof(Counters) / 4, sizeof(Counters) / 4, 1, 0);
+    A.seg[A.n++] = seg(pb.off + S, npairs_s, nullptr, 1, 1, 1, 0);
+    B.seg[B.n++] = seg(ctr, ctr_b, nullptr, sizeof(Counters) / 4, sizeof(Counters) / 4, 1, 0);
+    // (B's own copy of the counters to the pinned header reads the snapshot in hop 2)
+    for (int k = 0; k < H[2].n; k++)
+        if (H[2].seg[k].dst == pinned_header) H[2].seg[k].src = ctr_b;
+    cudaStream_t sa = e->dl_stream, sb = e->dl_stream_b, sc = e->dl_stream_c;
+    CU(e, cudaStreamWaitEvent(sa, e->ev_pairs, 0));
+    if (e->build_done_recorded) CU(e, cudaStreamWaitEvent(sa, e->ev_build_done, 0));
+    pack_kernel<<<dim3(24, (unsigned)A.n), 256, 0, sa>>>(A);
+    KCHECK(e);
+    if (A2.n) {
+        pack_kernel<<<dim3(8, (unsigned)A2.n), 256, 0, sa>>>(A2);
+        KCHECK(e);
+    }
+    CU(e, cudaEventRecord(e->ev_fetch_a[fi], sa));
+    CU(e, cudaStreamWaitEvent(sc, e->ev_fetch_a[fi], 0));
+    if (H[0].n) {
+        pack_kernel<<<dim3(24, (unsigned)H[0].n), 256, 0, sc>>>(H[0]);
+        KCHECK(e);
+    }
+    if (H[1].n) {
+        pack_kernel<<<dim3(8, (unsigned)H[1].n), 256, 0, sc>>>(H[1]);
+        KCHECK(e);
+    }
     CU(e, cudaStreamWaitEvent(sb, e->ev_join, 0));
     CU(e, cudaStreamWaitEvent(sb, e->ev_prep_done, 0));
     pack_kernel<<<dim3(24, (unsigned)B.n), 256, 0, sb>>>(B);
     KCHECK(e);
     CU(e, cudaEventRecord(e->ev_fetch_b[fi], sb));
+    CU(e, cudaStreamWaitEvent(sc, e->ev_fetch_b[fi], 0));
+    pack_kernel<<<dim3(24, (unsigned)H[2].n), 256, 0, sc>>>(H[2]);
+    KCHECK(e);
+    CU(e, cudaEventRecord(e->ev_fetch_done[fi], sc));
     e->fetch_guard = true;  // the next tick's kernels are ordered after these copies (they overwrite the arrays being read)
     e->fetch_header[fi] = pinned_header;
     e->fetch_issued++;
@@ -379,8 +447,7 @@ chd_status chd_fetch_wait(chd_engine* e, chd_tick_summary* summary) {
     }
     CU(e, cudaSetDevice(e->device));
     const int fi = (int)(e->fetch_waited & 1);  // the OLDEST outstanding fetch
-    CU(e, cudaEventSynchronize(e->ev_fetch_a[fi]));
-    CU(e, cudaEventSynchronize(e->ev_fetch_b[fi]));
+    CU(e, cudaEventSynchronize(e->ev_fetch_done[fi]));
     e->fetch_waited++;
     static_assert(sizeof(Counters) + 4 <= CHD_FETCH_HEADER_BYTES, "CHD_FETCH_HEADER_BYTES too small");
     memcpy(e->h_ctr, e->fetch_header[fi], sizeof(Counters));

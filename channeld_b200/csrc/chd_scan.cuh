@@ -153,36 +153,21 @@ struct ScanPtrIn {
     __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return (uint64_t)p[i]; }
 };
 
-template <typename InFn, typename TOut>
-__global__ void __launch_bounds__(SCAN_THREADS)
-    scan_lookback_kernel(InFn in, TOut* __restrict__ out, uint64_t n, const uint32_t* __restrict__ n_ptr, ScanSite site) {
+// The look-back itself (first warp of the block): publishes this tile's aggregate, sums the predecessors' and publishes the
+// inclusive prefix; every thread gets the tile's exclusive prefix back (one __syncthreads inside).
+__device__ __forceinline__ unsigned long long scan_lookback_prefix(const ScanSite& site, uint64_t tile, unsigned long long epoch, unsigned long long total) {
     __shared__ unsigned long long s_prefix;
     volatile unsigned long long* desc = site.desc;
-    if (n_ptr) n = min(n, (uint64_t)*n_ptr);
-    const uint64_t tile = blockIdx.x;
-    if (!(tile * SCAN_TILE < n || (n == 0 && tile == 0))) return;  // beyond the live length: nothing to publish
-    const unsigned long long epoch = *site.epoch;
-    const uint64_t base = tile * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
-    TOut v[SCAN_ITEMS];
-    TOut acc = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        const uint64_t i = base + k;
-        v[k] = i < n ? (TOut)in(i) : TOut(0);
-        acc += v[k];
-    }
-    TOut total;
-    TOut pre = block_excl_scan<TOut>(acc, total);
     if (threadIdx.x < 32) {
         // warp-parallel look-back: 32 predecessor descriptors per hop
         const int lane = threadIdx.x;
         if (tile == 0) {
             if (lane == 0) {
                 s_prefix = 0;
-                desc[0] = scan_pack(epoch, SCAN_FLAG_PREFIX, (unsigned long long)total);
+                desc[0] = scan_pack(epoch, SCAN_FLAG_PREFIX, total);
             }
         } else {
-            if (lane == 0) desc[tile] = scan_pack(epoch, SCAN_FLAG_AGG, (unsigned long long)total);
+            if (lane == 0) desc[tile] = scan_pack(epoch, SCAN_FLAG_AGG, total);
             unsigned long long run = 0;
             int64_t start = (int64_t)tile - 1;
             uint32_t spins = 0;
@@ -214,12 +199,33 @@ __global__ void __launch_bounds__(SCAN_THREADS)
             }
             if (lane == 0) {
                 s_prefix = run;
-                desc[tile] = scan_pack(epoch, SCAN_FLAG_PREFIX, run + (unsigned long long)total);
+                desc[tile] = scan_pack(epoch, SCAN_FLAG_PREFIX, run + total);
             }
         }
     }
     __syncthreads();
-    pre += (TOut)s_prefix;
+    return s_prefix;
+}
+
+template <typename InFn, typename TOut>
+__global__ void __launch_bounds__(SCAN_THREADS)
+    scan_lookback_kernel(InFn in, TOut* __restrict__ out, uint64_t n, const uint32_t* __restrict__ n_ptr, ScanSite site) {
+    if (n_ptr) n = min(n, (uint64_t)*n_ptr);
+    const uint64_t tile = blockIdx.x;
+    if (!(tile * SCAN_TILE < n || (n == 0 && tile == 0))) return;  // beyond the live length: nothing to publish
+    const unsigned long long epoch = *site.epoch;
+    const uint64_t base = tile * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    TOut v[SCAN_ITEMS];
+    TOut acc = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        const uint64_t i = base + k;
+        v[k] = i < n ? (TOut)in(i) : TOut(0);
+        acc += v[k];
+    }
+    TOut total;
+    TOut pre = block_excl_scan<TOut>(acc, total);
+    pre += (TOut)scan_lookback_prefix(site, tile, epoch, (unsigned long long)total);
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
         const uint64_t i = base + k;
@@ -241,6 +247,44 @@ template <typename InFn, typename TOut>
 inline int exclusive_scan_fn(InFn in, TOut* out, uint64_t n, const ScanSite& site, cudaStream_t st, const uint32_t* n_ptr = nullptr) {
     const uint64_t tiles = n == 0 ? 1 : (n + SCAN_TILE - 1) / SCAN_TILE;
     scan_lookback_kernel<InFn, TOut><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, out, n, n_ptr, site);
+    return 1;
+}
+
+// Single-pass stream compaction on the same machinery: flag(i) in {0,1} is computed on the fly, sink(i, k) is called for every
+// flagged element with its rank k among the flagged ones (input order: deterministic), sink.total(count) once.  Replaces the
+// flag kernel + prefix sum + scatter kernel triple of a classic compaction by ONE launch.
+template <typename FlagFn, typename SinkFn>
+__global__ void __launch_bounds__(SCAN_THREADS)
+    compact_lookback_kernel(FlagFn flag, SinkFn sink, uint64_t n, const uint32_t* __restrict__ n_ptr, ScanSite site) {
+    if (n_ptr) n = min(n, (uint64_t)*n_ptr);
+    const uint64_t tile = blockIdx.x;
+    if (!(tile * SCAN_TILE < n || (n == 0 && tile == 0))) return;
+    const unsigned long long epoch = *site.epoch;
+    const uint64_t base = tile * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t bits = 0, acc = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        const uint64_t i = base + k;
+        const uint32_t f = (i < n && flag(i)) ? 1u : 0u;
+        bits |= f << k;
+        acc += f;
+    }
+    uint32_t total;
+    uint32_t pre = block_excl_scan<uint32_t>(acc, total);
+    pre += (uint32_t)scan_lookback_prefix(site, tile, epoch, (unsigned long long)total);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        const uint64_t i = base + k;
+        if ((bits >> k) & 1u) sink(i, pre++);
+        if (i + 1 == n) sink.total(pre);
+    }
+    if (n == 0 && threadIdx.x == 0) sink.total(0u);
+}
+
+template <typename FlagFn, typename SinkFn>
+inline int compact_1p(FlagFn flag, SinkFn sink, uint64_t n, const ScanSite& site, cudaStream_t st, const uint32_t* n_ptr = nullptr) {
+    const uint64_t tiles = n == 0 ? 1 : (n + SCAN_TILE - 1) / SCAN_TILE;  // <= site.tiles by construction of the site
+    compact_lookback_kernel<FlagFn, SinkFn><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(flag, sink, n, n_ptr, site);
     return 1;
 }
 

@@ -78,16 +78,29 @@ chd_status chd_export_border(chd_engine* e, uint32_t* d_records, uint32_t cap_re
     }
     cudaStream_t s = e->stream;
     const uint32_t n = e->n_own;
-    const uint32_t n_launch = n > cap_records ? n : cap_records;  // the write pass also pads the caller's buffer
+    // inside chd_tick_sharded with the peer exchange the records go straight into the peers' windows afterwards: no padding needed
+    const bool to_peers = e->peer_push && d_records == e->d_rec_local;
     auto enqueue = [&]() -> chd_status {
+        const bool bump_in_assign = !e->assigned && n;
+        if (bump_in_assign) e->assign_bump = e->d_epoch + EP_BORDER;
         chd_status st = chd_assign_cells_impl(e);
         if (st != CHD_OK) return st;
-        border_flag_kernel<<<blocks_for(n ? n : 1, 256), 256, 0, s>>>(e->g, e->d_key, n, e->d_bflag, e->d_epoch + EP_BORDER);
-        KCHECK(e);
-        SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_bflag, e->d_boff, n, e->site_border, s));
-        border_write_kernel<<<blocks_for(n_launch ? n_launch : 1, 256), 256, 0, s>>>(e->d_key, e->have_gid ? e->d_gid : nullptr, n, e->d_bflag,
-                                                                                      e->d_boff, d_records, cap_records, e->d_ctr);
-        KCHECK(e);
+        if (!bump_in_assign) {
+            bump_epoch_kernel<<<1, 1, 0, s>>>(e->d_epoch + EP_BORDER);
+            KCHECK(e);
+        }
+        if (!to_peers) CU(e, cudaMemsetAsync(d_records, 0xFF, 8ull * cap_records, s));  // unused records read as "no cell"
+        SCAN(e, compact_1p(BorderFlag{e->g, e->d_key}, BorderSink{e->d_key, e->have_gid ? e->d_gid : nullptr, d_records, cap_records, e->d_boff + n, e->d_ctr},
+                           n, e->site_border, s));
+        if (to_peers) {
+            PeerWindows pw{};
+            for (int r = 0; r < e->comm_world; r++) pw.base[r] = (uint32_t*)e->peer_base[r];
+            const uint64_t blob_words = e->rec_stride_words - 2ull * e->rec_per_rank;
+            peer_push_kernel<<<(unsigned)std::min<uint64_t>((uint64_t)e->sm_count, 8 + (2ull * cap_records * e->comm_world) / 8192), 256, 0, s>>>(
+                d_records, e->d_boff + n, cap_records, blob_words, e->rec_stride_words, pw, (uint32_t)e->comm_world, (uint32_t)e->comm_rank, e->d_xchg_seq,
+                e->d_push_done, e->d_epoch + EP_BORDER);
+            KCHECK(e);
+        }
         return CHD_OK;
     };
     chd_status st = chd_epoch_tick(e, EP_BORDER);
@@ -100,7 +113,8 @@ chd_status chd_export_border(chd_engine* e, uint32_t* d_records, uint32_t cap_re
         key = mix_key(mix_key(key, (uint64_t)(uintptr_t)target), (uint64_t)(uintptr_t)e->pos_x ^ ((uint64_t)(uintptr_t)e->pos_z << 1));
         key = mix_key(mix_key(key, (uint64_t)(uintptr_t)d_records), cap_records);
         key = mix_key(mix_key(mix_key(key, e->g.col_lo), e->g.col_hi), e->g.halo);
-        st = run_stage(e, e->g_export[slot], key, enqueue);
+        key = mix_key(key, to_peers ? 1 : 0);
+        st = run_stage(e, e->g_export[slot + (to_peers ? 4 : 0)], key, enqueue);
         if (st == CHD_OK && !e->assigned) {  // replayed graph: mirror the host-side bookkeeping of chd_assign_cells
             if (e->have_prev_key) {
                 uint32_t* t = e->d_key;
@@ -147,22 +161,26 @@ chd_status chd_import_halo(chd_engine* e, const uint32_t* d_records, uint32_t n_
         chd_status st0 = chd_epoch_tick(e, EP_BORDER);
         if (st0 != CHD_OK) return st0;
         const int slot = e->d_key == e->d_key_a ? 0 : 1;  // the halo keys are appended to the current key buffer
+        // peer exchange: the records sit in this tick's buffer of the own window, the live counts come from the flags
+        const bool from_peers = e->peer_push && d_records >= e->d_peer_win && d_records < e->d_peer_win + 2ull * e->comm_world * e->rec_stride_words;
+        const int parity = from_peers && d_records != e->d_peer_win ? 1 : 0;
         uint64_t key = mix_key(mix_key(mix_key(0x696d706full, n_records), skip_first), skip_count);
         key = mix_key(mix_key(key, e->rec_per_rank), e->rec_stride_words);
         key = mix_key(mix_key(mix_key(key, (uint64_t)(uintptr_t)d_records), e->n_own), (uint64_t)(uintptr_t)e->d_key);
         key = mix_key(mix_key(mix_key(key, e->g.col_lo), e->g.col_hi), e->g.halo);
-        chd_status st = run_stage(e, e->g_import[slot], key, [&]() -> chd_status {
+        key = mix_key(key, from_peers ? 1 : 0);
+        chd_status st = run_stage(e, e->g_import[slot + 2 * parity], key, [&]() -> chd_status {
             const RecView rv{d_records, e->rec_per_rank ? e->rec_per_rank : (n_records ? n_records : 1u),
                              e->rec_per_rank ? e->rec_stride_words : 2ull * (n_records ? n_records : 1u)};
-            halo_flag_kernel<<<blocks_for(n_records ? n_records : 1, 256), 256, 0, s>>>(e->g, rv, n_records, skip_first, skip_count,
-                                                                                        e->d_bflag, e->d_epoch + EP_BORDER);
+            if (from_peers) {  // (the push kernel of this tick has bumped the compaction site's epoch)
+                peer_wait_kernel<<<1, 32, 0, s>>>(e->d_peer_win, e->rec_stride_words, (uint32_t)e->comm_world, e->d_xchg_seq, e->d_peer_count, e->d_ctr);
+            } else {
+                bump_epoch_kernel<<<1, 1, 0, s>>>(e->d_epoch + EP_BORDER);
+            }
             KCHECK(e);
-            SCAN(e, exclusive_scan_1p<uint32_t, uint32_t>(e->d_bflag, e->d_boff, n_records, e->site_border, s));
             // no host round trip: the kept count and the build length stay on the device (overflow -> CHD_OVF_BORDER)
-            halo_append_kernel<<<blocks_for(n_records ? n_records : 1, 256), 256, 0, s>>>(rv, n_records, e->d_bflag, e->d_boff, e->n_own,
-                                                                                          e->lim.max_entities, e->d_key, e->d_gid, e->d_n_build,
-                                                                                          e->d_ctr);
-            KCHECK(e);
+            SCAN(e, compact_1p(HaloFlag{e->g, rv, from_peers ? e->d_peer_count : nullptr, skip_first, skip_count},
+                               HaloSink{rv, e->n_own, e->lim.max_entities, e->d_key, e->d_gid, e->d_n_build, e->d_ctr}, n_records, e->site_border, s));
             return CHD_OK;
         });
         if (st != CHD_OK) return st;
@@ -216,6 +234,7 @@ chd_status chd_comm_init(chd_engine* e, const void* unique_id, int rank, int wor
     e->comm = comm;
     e->comm_rank = rank;
     e->comm_world = world;
+    border_capacity = (border_capacity + 1u) & ~1u;  // (16-byte alignment of everything that follows the records)
     e->border_cap = border_capacity;
     // one contribution per rank and tick = its border records followed by its migration blob (subscriber state in flight)
     e->mig_subs = (migrate_subscribers + 1u) & ~1u;
@@ -227,6 +246,65 @@ chd_status chd_comm_init(chd_engine* e, const void* unique_id, int rank, int wor
     if (!dalloc(e, &e->d_rec_local, e->rec_stride_words) || !dalloc(e, &e->d_rec_all, e->rec_stride_words * (uint64_t)world)) return CHD_ERR_CUDA;
     CU(e, cudaMemsetAsync(e->d_rec_local, 0, e->rec_stride_words * 4, e->stream));
     CU(e, cudaMemsetAsync(e->d_rec_all, 0, e->rec_stride_words * 4 * (uint64_t)world, e->stream));
+    // ---- peer exchange: every rank's receive window is mapped into every other rank (CUDA IPC); the tick then moves the border
+    // records with plain stores over NVLink and 64-bit flags (chd_shard.cuh).  NCCL carries the handles once, here.  If any rank
+    // cannot map a peer (no P2P path, more ranks than CHD_MAX_PEERS) ALL ranks keep the ncclAllGather exchange.
+    {
+        const uint64_t win_words = 2ull * world * e->rec_stride_words + 4ull * world + 8;
+        uint32_t* hbuf = nullptr;
+        if (!dalloc(e, &e->d_peer_win, win_words) || !dalloc(e, &e->d_xchg_seq, 1) || !dalloc(e, &e->d_push_done, 4) ||
+            !dalloc(e, &e->d_peer_count, CHD_MAX_PEERS) || !dalloc(e, &hbuf, 32ull * (uint64_t)world))
+            return CHD_ERR_CUDA;
+        CU(e, cudaMemsetAsync(e->d_peer_win, 0, win_words * 4, e->stream));
+        CU(e, cudaMemsetAsync(e->d_xchg_seq, 0, 8, e->stream));
+        CU(e, cudaMemsetAsync(e->d_push_done, 0, 16, e->stream));
+        CU(e, cudaMemsetAsync(e->d_peer_count, 0, 4 * CHD_MAX_PEERS, e->stream));
+        CU(e, cudaStreamSynchronize(e->stream));  // the window is clean before any peer can learn its address
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+        struct Slot { cudaIpcMemHandle_t h; uint32_t ok, pad[15]; } mine{};  // 128 bytes per rank
+        mine.ok = (world <= CHD_MAX_PEERS && cudaIpcGetMemHandle(&mine.h, e->d_peer_win) == cudaSuccess) ? 1u : 0u;
+        cudaGetLastError();
+        std::vector<Slot> all((size_t)world);
+        auto gather = [&]() -> chd_status {  // all-gather of one Slot per rank through hbuf
+            CU(e, cudaMemcpyAsync(hbuf + 32ull * rank, &mine, sizeof mine, cudaMemcpyHostToDevice, e->stream));
+            NC(e, api, api->AllGather(hbuf + 32ull * rank, hbuf, 32, ncclUint32, comm, e->stream));
+            CU(e, cudaMemcpyAsync(all.data(), hbuf, sizeof(Slot) * (size_t)world, cudaMemcpyDeviceToHost, e->stream));
+            CU(e, cudaStreamSynchronize(e->stream));
+            return CHD_OK;
+        };
+        chd_status gs = gather();
+        if (gs != CHD_OK) return gs;
+        bool ok = true;
+        for (int r = 0; r < world; r++) ok = ok && all[(size_t)r].ok;
+        if (ok) {
+            for (int r = 0; r < world && ok; r++) {
+                if (r == rank) {
+                    e->peer_base[r] = e->d_peer_win;
+                    continue;
+                }
+                void* p = nullptr;
+                if (cudaIpcOpenMemHandle(&p, all[(size_t)r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    cudaGetLastError();
+                    ok = false;
+                } else {
+                    e->peer_base[r] = p;
+                }
+            }
+        }
+        mine.ok = ok ? 1u : 0u;  // second round: did EVERY rank map every peer?
+        gs = gather();
+        if (gs != CHD_OK) return gs;
+        for (int r = 0; r < world; r++) ok = ok && all[(size_t)r].ok;
+        if (!ok)
+            for (int r = 0; r < world; r++) {
+                if (r != rank && e->peer_base[r]) cudaIpcCloseMemHandle(e->peer_base[r]);
+                e->peer_base[r] = nullptr;
+            }
+        e->peer_mapped = ok;
+        e->peer_push = ok;
+        e->xchg_seq = 0;
+        chd_dfree(e, hbuf);
+    }
     // X-slabs by grid column: rank g of G owns columns [floor(g*cols/G), floor((g+1)*cols/G))
     const uint32_t lo = (uint32_t)(((uint64_t)rank * e->g.cols) / (uint64_t)world), hi = (uint32_t)(((uint64_t)(rank + 1) * e->g.cols) / (uint64_t)world);
     return chd_set_slab(e, lo, hi, halo_cols);
@@ -252,6 +330,11 @@ chd_status chd_comm_destroy(chd_engine* e) {
     if (!e->comm) return CHD_OK;
     CU(e, cudaSetDevice(e->device));
     CU(e, cudaStreamSynchronize(e->stream));
+    for (int r = 0; r < e->comm_world && r < CHD_MAX_PEERS; r++) {
+        if (r != e->comm_rank && e->peer_base[r]) cudaIpcCloseMemHandle(e->peer_base[r]);
+        e->peer_base[r] = nullptr;
+    }
+    e->peer_push = e->peer_mapped = false;
     NcclApi* api = nccl_api();
     if (api->lib) api->CommDestroy((ncclComm_t)e->comm);
     e->comm = nullptr;
@@ -282,19 +365,35 @@ chd_status chd_tick_sharded(chd_engine* e, const chd_query_batch* q, int64_t t_n
     const uint32_t cap = e->border_cap;
     if (e->mig_subs && !e->mig_packed) CU(e, cudaMemsetAsync(e->d_rec_local + 2ull * cap, 0, 16, e->stream));  // empty blob header
     e->mig_packed = false;
-    st = chd_export_border(e, e->d_rec_local, cap, nullptr);
+    {
+        StageTimer tm(e, CHD_STAGE_EXPORT);  // (with the peer exchange: assignment + border selection + the push into the peers' windows)
+        st = chd_export_border(e, e->d_rec_local, cap, nullptr);
+    }
     if (st != CHD_OK) return st;
-    NcclApi* api = nccl_api();
-    NC(e, api, api->AllGather(e->d_rec_local, e->d_rec_all, e->rec_stride_words, ncclUint32, (ncclComm_t)e->comm, e->stream));
-    e->n_collectives++;
+    const uint32_t* gathered = e->d_rec_all;
+    if (e->peer_push) {
+        e->xchg_seq++;
+        gathered = e->d_peer_win + (e->xchg_seq & 1ull) * (uint64_t)e->comm_world * e->rec_stride_words;
+    } else {
+        NcclApi* api = nccl_api();
+        StageTimer tm(e, CHD_STAGE_EXCHANGE);
+        NC(e, api, api->AllGather(e->d_rec_local, e->d_rec_all, e->rec_stride_words, ncclUint32, (ncclComm_t)e->comm, e->stream));
+        e->n_collectives++;
+    }
+    {
+        // the halo import comes first: with the peer exchange its first kernel is the one that waits for the peers' records, and the
+        // immigrants' state (read by the interest update below) sits in the same window
+        StageTimer tm(e, CHD_STAGE_IMPORT);
+        st = chd_import_halo(e, gathered, cap * (uint32_t)e->comm_world, (uint32_t)e->comm_rank * cap, cap);
+    }
+    if (st != CHD_OK) return st;
     if (e->mig_subs) {
-        e->mig = MigView{e->d_rec_all + 2ull * cap, e->rec_stride_words, e->mig_subs, e->mig_pairs};
+        e->mig = MigView{const_cast<uint32_t*>(gathered) + 2ull * cap, e->rec_stride_words, e->mig_subs, e->mig_pairs};
         if (has_batch) {
             st = chd_begin_interest(e, q, t_ns, (flags & CHD_TICK_FANOUT) ? 1 : 0);
             if (st != CHD_OK) return st;
         }
     }
-    st = chd_import_halo(e, e->d_rec_all, cap * (uint32_t)e->comm_world, (uint32_t)e->comm_rank * cap, cap);
     if (st != CHD_OK) return st;
     return chd_tick(e, nullptr, t_ns, flags, out);
 }
@@ -390,5 +489,17 @@ chd_status chd_get_rehome(chd_engine* e, uint32_t* global_id, uint32_t* dst_rank
 }
 
 uint64_t chd_collective_count(const chd_engine* e) { return e ? e->n_collectives : 0; }
+
+int chd_comm_exchange_mode(const chd_engine* e) { return !e || !e->comm ? 0 : (e->peer_push ? 2 : 1); }
+
+chd_status chd_comm_use_collective(chd_engine* e, int on) {
+    if (!e) return CHD_ERR_INVALID;
+    if (!e->comm) {
+        e->fail("chd_comm_use_collective before chd_comm_init");
+        return CHD_ERR_STATE;
+    }
+    e->peer_push = !on && e->peer_mapped;
+    return CHD_OK;
+}
 
 }  // extern "C"

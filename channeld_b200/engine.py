@@ -131,6 +131,23 @@ class Engine:
         self._keep_prefetch = [x, z]
         self._ck(self.L.chd_prefetch_entities(self.h, ptr(x), ptr(z), int(n)))
 
+    def set_entities_f32(self, x, z, n=None):
+        """Positions that are floats at the source (unrealpb.FVector): uploaded as floats, widened exactly on the device."""
+        if isinstance(x, np.ndarray):
+            x = np.ascontiguousarray(x, np.float32)
+            z = np.ascontiguousarray(z, np.float32)
+        n = len(x) if n is None else n
+        self._keep = [x, z]
+        self._ck(self.L.chd_set_entities_f32(self.h, ptr(x), ptr(z), int(n)))
+
+    def prefetch_entities_f32(self, x, z, n=None):
+        if isinstance(x, np.ndarray):
+            x = np.ascontiguousarray(x, np.float32)
+            z = np.ascontiguousarray(z, np.float32)
+        n = len(x) if n is None else n
+        self._keep_prefetch = [x, z]
+        self._ck(self.L.chd_prefetch_entities_f32(self.h, ptr(x), ptr(z), int(n)))
+
     def adopt_prefetched(self):
         self._ck(self.L.chd_adopt_prefetched(self.h))
         self._keep = getattr(self, "_keep_prefetch", None)
@@ -396,6 +413,13 @@ class Engine:
 
     def collective_count(self):
         return int(self.L.chd_collective_count(self.h))
+
+    def exchange_mode(self):
+        """0 no communicator, 1 ncclAllGather per tick, 2 peer windows (stores over NVLink + flags, no collective on the tick path)."""
+        return int(self.L.chd_comm_exchange_mode(self.h))
+
+    def use_collective(self, on=True):
+        self._ck(self.L.chd_comm_use_collective(self.h, 1 if on else 0))
 
     # ---- multi-GPU slab
     def set_slab(self, col_lo, col_hi, halo):

@@ -221,6 +221,9 @@ func (ctl *GpuStaticGrid2DSpatialController) cCfg() C.chd_grid_cfg {
 // the returned window for kind 1), chd_get_handover -> the orchestration half of Notify (spatial.go:628-858).
 type GpuTickInput struct {
 	EntityX, EntityZ []float64 // index = entity slot
+	// Alternative to EntityX/EntityZ for hosts whose positions are still the FVector floats of the entity updates
+	// (unrealpb.FVector; extension.go:10-24 widens them with float64(*vec.X)): half the PCIe bytes, same results.
+	EntityXf, EntityZf []float32
 	ConnSlot         []uint32  // per query: subscriber slot
 	SphX, SphZ, SphR []float64
 	RingOff          []uint32 // [cells+1]
@@ -244,7 +247,13 @@ func (ctl *GpuStaticGrid2DSpatialController) TickBatch(in *GpuTickInput, now Cha
 		pin.Pin(&in.SphZ[0])
 		pin.Pin(&in.SphR[0])
 	}
-	if n := len(in.EntityX); n > 0 {
+	if n := len(in.EntityXf); n > 0 {
+		pin.Pin(&in.EntityXf[0])
+		pin.Pin(&in.EntityZf[0])
+		if st := C.chd_set_entities_f32(e, (*C.float)(unsafe.Pointer(&in.EntityXf[0])), (*C.float)(unsafe.Pointer(&in.EntityZf[0])), C.uint32_t(n)); st != C.CHD_OK {
+			return sum, errors.New(C.GoString(C.chd_last_error(e)))
+		}
+	} else if n := len(in.EntityX); n > 0 {
 		if st := C.chd_set_entities(e, (*C.double)(unsafe.Pointer(&in.EntityX[0])), (*C.double)(unsafe.Pointer(&in.EntityZ[0])), C.uint32_t(n)); st != C.CHD_OK {
 			return sum, errors.New(C.GoString(C.chd_last_error(e)))
 		}
@@ -309,7 +318,11 @@ func (ctl *GpuStaticGrid2DSpatialController) PrefetchTick(in *GpuTickInput) erro
 			return fail()
 		}
 	}
-	if n := len(in.EntityX); n > 0 {
+	if n := len(in.EntityXf); n > 0 {
+		if st := C.chd_prefetch_entities_f32(e, (*C.float)(unsafe.Pointer(&in.EntityXf[0])), (*C.float)(unsafe.Pointer(&in.EntityZf[0])), C.uint32_t(n)); st != C.CHD_OK {
+			return fail()
+		}
+	} else if n := len(in.EntityX); n > 0 {
 		if st := C.chd_prefetch_entities(e, (*C.double)(unsafe.Pointer(&in.EntityX[0])), (*C.double)(unsafe.Pointer(&in.EntityZ[0])), C.uint32_t(n)); st != C.CHD_OK {
 			return fail()
 		}

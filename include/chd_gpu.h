@@ -110,6 +110,13 @@ chd_status chd_set_entities(chd_engine* e, const double* x, const double* z, uin
  * prefetched positions the current ones (replaces chd_set_entities for that tick; CHD_ERR_STATE if nothing was
  * prefetched).  The second buffer pair is allocated on the first prefetch. */
 chd_status chd_prefetch_entities(chd_engine* e, const double* x, const double* z, uint32_t n);
+/* The same two calls for positions that ARE floats at the source: channeld's entities move as unrealpb.FVector (three floats,
+ * pkg/unrealpb/unreal_common.proto:55-59) and only become SpatialInfo doubles by float64(*vec.X) (pkg/unrealpb/extension.go:10-24;
+ * x = FVector.X, z = FVector.Y).  The widening is exact and is done on the device behind the copy, so a snapshot costs 8 instead of
+ * 16 bytes per entity on PCIe and every result is bit-identical to chd_set_entities fed with the widened values.  Device-resident
+ * float arrays (16-byte aligned) are widened in place of the copy. */
+chd_status chd_set_entities_f32(chd_engine* e, const float* x, const float* z, uint32_t n);
+chd_status chd_prefetch_entities_f32(chd_engine* e, const float* x, const float* z, uint32_t n);
 /* (chd_prefetch_queries / chd_prefetch_rings, declared after chd_set_rings, do the same for the other per-tick inputs.) */
 chd_status chd_adopt_prefetched(chd_engine* e);
 /* Device pointers of the resident position arrays, for producers that write positions on the GPU. */
@@ -409,6 +416,14 @@ chd_status chd_comm_info(const chd_engine* e, int* rank, int* world, uint32_t* c
 chd_status chd_comm_destroy(chd_engine* e);
 chd_status chd_tick_sharded(chd_engine* e, const chd_query_batch* q, int64_t t_ns, uint32_t flags, chd_tick_summary* out);
 uint64_t chd_collective_count(const chd_engine* e); /* NCCL collectives issued so far */
+/* How chd_tick_sharded moves the border records: 2 = PEER WINDOWS (default when every rank could map every other rank's receive
+ * window with CUDA IPC at chd_comm_init: the export kernel's successor stores the live records straight into the peers' memory over
+ * NVLink and publishes a 64-bit flag; the import's first kernel polls the local flags — no collective call on the tick path),
+ * 1 = one ncclAllGather per tick (ranks without a P2P path, more than 16 ranks), 0 = no communicator.
+ * chd_comm_use_collective(e, 1) selects the NCCL exchange even when peer windows are mapped (every rank must make the same choice,
+ * between ticks); (e, 0) returns to the peer windows. */
+int chd_comm_exchange_mode(const chd_engine* e);
+chd_status chd_comm_use_collective(chd_engine* e, int on);
 
 /* ---- re-homing.  ENTITIES: an entity that leaves its owner's slab is still exported by that owner and adopted, for this tick, by
  * every rank that needs it (visibility stays exact whatever the ownership); chd_get_rehome lists the own entities whose column
@@ -510,7 +525,9 @@ uint32_t chd_damping_interval_ms(uint32_t dist, uint32_t default_ms);
  * makes every stage record a CUDA-event pair on the engine stream (the last 1024 samples are kept);
  * chd_profile_get synchronises and returns the summed device time of a stage.  CHD_STAGE_EMIT_KERNEL brackets
  * exactly the emit_visible kernel (the dominant HBM term; bench.py's roofline uses it). */
-enum { CHD_STAGE_BUILD = 0, CHD_STAGE_INTEREST, CHD_STAGE_EMIT, CHD_STAGE_EMIT_KERNEL, CHD_STAGE_FANOUT, CHD_STAGE_TICK, CHD_STAGE_COUNT };
+enum { CHD_STAGE_BUILD = 0, CHD_STAGE_INTEREST, CHD_STAGE_EMIT, CHD_STAGE_EMIT_KERNEL, CHD_STAGE_FANOUT, CHD_STAGE_TICK,
+       CHD_STAGE_EXPORT, CHD_STAGE_EXCHANGE, CHD_STAGE_IMPORT, /* the three steps of chd_tick_sharded before the tick proper */
+       CHD_STAGE_COUNT };
 uint64_t chd_launch_count(const chd_engine* e);
 /* The launch-bound stages (build, interest update, emit preparation, fan-out) are replayed as CUDA graphs once
  * their shape (entity / query / subscriber counts) has been stable for two ticks.  chd_enable_graphs(e, 0) forces

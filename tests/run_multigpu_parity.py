@@ -44,9 +44,11 @@ def main():
     failures = 0
     n_ticks = int(os.environ.get("CHD_PARITY_TICKS", "6"))
     # the 2x2 grid gives every rank of a 2-GPU run a ONE-column slab (empty interior, as at 8 GPUs on 15 columns)
-    for name, n_ent, n_sub, radius, max_move in (("benchmark", 120_000, 6_000, 50.0, 700.0), ("benchmark", 60_000, 3_000, 2500.0, 900.0),
-                                                 ("handover", 200_000, 4_000, 50.0, 120.0), ("2x2", 50_000, 2_000, 50.0, 400.0),
-                                                 ("2x2", 50_000, 2_000, 500.0, 300.0)):
+    # last field: exchange through the peer windows (stores over NVLink + flags, the default) or through one ncclAllGather per tick
+    for name, n_ent, n_sub, radius, max_move, collective in (("benchmark", 120_000, 6_000, 50.0, 700.0, False), ("benchmark", 60_000, 3_000, 2500.0, 900.0, True),
+                                                             ("benchmark", 60_000, 3_000, 2500.0, 900.0, False), ("handover", 200_000, 4_000, 50.0, 120.0, False),
+                                                             ("2x2", 50_000, 2_000, 50.0, 400.0, False), ("2x2", 50_000, 2_000, 500.0, 300.0, True),
+                                                             ("2x2", 50_000, 2_000, 500.0, 300.0, False)):
         wc = synth.scaled(synth.CONFIGS[name], n_ent, n_sub)
         if world > wc.cols:
             continue
@@ -68,6 +70,12 @@ def main():
         e.comm_init(uid.cpu().numpy().tobytes(), rank, world, halo, cap, migrate_subscribers=n_sub, migrate_pairs=n_sub * 16)
         info = e.comm_info()
         assert (info["col_lo"], info["col_hi"], info["world"]) == (lo, hi, world)
+        if collective:
+            e.use_collective(True)
+        mode = e.exchange_mode()
+        assert mode == (1 if collective else mode) and mode in (1, 2)
+        if rank == 0:
+            print("%s r=%g: exchange mode %d (%s)" % (name, radius, mode, "peer windows" if mode == 2 else "ncclAllGather"), flush=True)
         # ---- the single-GPU reference engine over the whole world (slot j = subscriber j)
         e1 = engine.Engine(wc.cfg(), n_ent, n_sub, device=local, max_visible=1 << 28, max_pairs=n_sub * 64 + 1024)
         e1.set_stream(stream.cuda_stream)
@@ -161,6 +169,10 @@ def main():
                 if not np.array_equal(np.nonzero((ent_owner == rank) & ok_mask)[0], mine[ok_mask[mine]]):
                     failures += 1
                     print("rank %d: ownership invariant violated" % rank, flush=True)
+        n_coll = e.collective_count()
+        if (mode == 2 and n_coll != 0) or (mode == 1 and n_coll != n_ticks):
+            failures += 1
+            print("rank %d: %d collectives in mode %d" % (rank, n_coll, mode), flush=True)
         if n_mig_total == 0 and name != "2x2":
             print("rank %d %s: WARNING no subscriber migrated" % (rank, name), flush=True)
         e.close()

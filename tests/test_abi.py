@@ -95,7 +95,7 @@ from channeld_b200 import capi
 L = capi.lib()
 no_handle = {"chd_abi_version", "chd_default_limits", "chd_create", "chd_destroy", "chd_last_error", "chd_alloc_pinned", "chd_free_pinned", "chd_device_numa_node",
              "chd_get_adjacent_channels", "chd_get_regions", "chd_damping_interval_ms", "chd_launch_count", "chd_graph_launch_count",
-             "chd_collective_count"}
+             "chd_collective_count", "chd_comm_exchange_mode"}
 bad = []
 for name in capi.SYMBOLS:
     if name in no_handle:

@@ -605,6 +605,122 @@ def test_fetch_results_matches_getters(chd, early):
     assert e.L.chd_fetch_results(e.h, C.byref(rb), C.byref(s)) == chd.capi.ERR_CAPACITY
 
 
+def test_async_fetch_matches_getters_while_the_next_tick_runs(chd):
+    """chd_fetch_results_async / chd_fetch_wait: tick k+1 is enqueued (and overwrites the engine's result arrays) BEFORE the host
+    waits for tick k's results; what arrives in the pinned buffers equals what a second engine's getters return for tick k.  Also:
+    a third outstanding fetch is refused."""
+    import ctypes as C
+
+    import torch
+
+    wc = chd.synth.scaled(chd.synth.CONFIGS["benchmark"], 50_000, 4_000)
+    ex, ez = chd.synth.entities(wc)
+    conn, _, _, _ = chd.synth.subscribers(wc, ex, ez)
+    frames, ring_state = [], None
+    for tick in range(6):
+        t = (tick + 1) * 33_000_000
+        ex, ez = chd.synth.move_entities(wc, ex, ez, tick, 400.0)
+        _, cx, cz, r = chd.synth.subscribers(wc, ex, ez)
+        ring_state, off, arr, snd, idx, cmi = chd.synth.update_rings(wc, tick, t, 33_000_000, 4, len(conn), ring_len=16, state=ring_state)
+        frames.append(dict(t=t, x=ex.copy(), z=ez.copy(), q=(cx, cz, r), rings=(off, arr, snd, idx, cmi)))
+    S, cap = len(conn), 1 << 17
+
+    def pin(n, dt):
+        t_ = torch.zeros(n, dtype=dt).pin_memory()
+        return t_, t_.numpy()
+
+    def result_set():
+        k = {n_: pin(cap, torch.int32) for n_ in ("ch", "dist", "iv", "ns", "nc", "us", "uc", "he", "hs", "hd", "st", "se")}
+        k["off"], k["voff"], k["cs"] = pin(S + 1, torch.int32), pin(S + 1, torch.int64), pin(wc.cells + 1, torch.int32)
+        k["due"], k["hdr"] = pin(cap * 12, torch.int32), pin(64, torch.int32)
+        rb = chd.capi.ResultBuffers()
+        P = lambda n_: chd.capi.ptr(k[n_][0])  # noqa: E731
+        rb.pair_off, rb.pair_channel, rb.pair_dist, rb.pair_interval_ms, rb.pair_cap = P("off"), P("ch"), P("dist"), P("iv"), cap
+        rb.new_sub, rb.new_channel, rb.unsub_sub, rb.unsub_channel, rb.diff_cap = P("ns"), P("nc"), P("us"), P("uc"), cap
+        rb.due, rb.due_cap = P("due"), cap
+        rb.handover_entity, rb.handover_src, rb.handover_dst, rb.handover_cap = P("he"), P("hs"), P("hd"), cap
+        rb.query_status, rb.status_cap = P("st"), cap
+        rb.vis_off, rb.vis_entity, rb.vis_cap = P("voff"), None, 0
+        rb.cell_start, rb.sorted_entity, rb.entity_cap = P("cs"), P("se"), cap
+        return rb, k
+
+    # the plain engine: one synchronous tick at a time, getters
+    e1 = chd.engine.Engine(wc.cfg(), wc.n_entities, wc.n_subscribers, max_visible=1 << 24)
+    e1.set_subscribers(conn)
+    want = []
+    for f in frames:
+        e1.set_rings(*f["rings"])
+        e1.set_entities(f["x"], f["z"])
+        batch, keep = chd.engine.make_batch(S, sub=None, sphere=f["q"])
+        s = e1.tick(batch, f["t"], chd.capi.TICK_ALL)
+        voff, _ = e1.get_visible()
+        cs, se = e1.get_cells()
+        want.append(dict(s=s.as_dict(), pairs=e1.get_pairs(s.n_pairs), diff=e1.get_diff(s.n_sub_new, s.n_unsub), due=e1.get_due(s.n_due),
+                         ho=e1.get_handover(s.n_handover), st=e1.get_query_status(S), voff=voff, cs=cs, se=se))
+    e1.close()
+
+    e = chd.engine.Engine(wc.cfg(), wc.n_entities, wc.n_subscribers, max_visible=1 << 24)
+    e.set_subscribers(conn)
+    sets = [result_set(), result_set()]
+    ck = e._ck
+
+    def prefetch(f):
+        batch, keep = chd.engine.make_batch(S, sub=None, sphere=f["q"])
+        e.prefetch_rings(*f["rings"])
+        e.prefetch_queries(batch, keep)
+        e.prefetch_entities(f["x"], f["z"])
+
+    def enqueue(i):
+        e.adopt_prefetched()
+        e.begin_interest(None, frames[i]["t"])
+        ck(e.L.chd_tick(e.h, None, frames[i]["t"], chd.capi.TICK_ALL, None))
+        if i + 1 < len(frames):
+            prefetch(frames[i + 1])
+        rb, k = sets[i % 2]
+        ck(e.L.chd_fetch_results_async(e.h, C.byref(rb), chd.capi.ptr(k["hdr"][0])))
+
+    def check(i, s):
+        w, k = want[i], sets[i % 2][1]
+        assert s.as_dict() == w["s"], i
+        n = s.n_pairs
+        np.testing.assert_array_equal(k["off"][1].view(np.uint32), w["pairs"]["off"])
+        for a, b in (("ch", "channel"), ("dist", "dist"), ("iv", "interval")):
+            np.testing.assert_array_equal(k[a][1][:n].view(np.uint32), w["pairs"][b])
+        (a, b), (c, d) = w["diff"]
+        # (the sub / unsub lists are appended block by block: sets of (subscriber, channel), compared in a canonical order)
+        canon = lambda u, v: np.sort(u.astype(np.uint64) << np.uint64(32) | v.astype(np.uint64))  # noqa: E731
+        np.testing.assert_array_equal(canon(k["ns"][1][:s.n_sub_new].view(np.uint32), k["nc"][1][:s.n_sub_new].view(np.uint32)), canon(a, b))
+        np.testing.assert_array_equal(canon(k["us"][1][:s.n_unsub].view(np.uint32), k["uc"][1][:s.n_unsub].view(np.uint32)), canon(c, d))
+        got_due = k["due"][1][:s.n_due * 12].view(chd.capi.DUE_DTYPE)
+        key = lambda d_: d_[np.lexsort((d_["window_hi"], d_["channel_id"], d_["sub"]))]  # noqa: E731
+        np.testing.assert_array_equal(key(got_due), key(w["due"]))
+        ho_g = np.stack([k[a][1][:s.n_handover].view(np.uint32) for a in ("he", "hs", "hd")], 1)
+        ho_w = np.stack(w["ho"], 1)
+        srt = lambda h: h[np.lexsort((h[:, 2], h[:, 1], h[:, 0]))]  # noqa: E731
+        np.testing.assert_array_equal(srt(ho_g), srt(ho_w))
+        np.testing.assert_array_equal(k["st"][1][:S].view(np.uint32), w["st"])
+        np.testing.assert_array_equal(k["voff"][1].view(np.uint64), w["voff"])
+        np.testing.assert_array_equal(k["cs"][1].view(np.uint32), w["cs"])
+        np.testing.assert_array_equal(k["se"][1][:s.n_entities_in_world].view(np.uint32), w["se"])
+
+    s = chd.capi.TickSummary()
+    prefetch(frames[0])
+    enqueue(0)
+    for i in range(1, len(frames)):
+        enqueue(i)  # overwrites the engine's arrays while tick i-1's results are still travelling
+        if i == 2:
+            with pytest.raises(chd.capi.ChdError):  # two fetches outstanding: refused, nothing enqueued
+                ck(e.L.chd_fetch_results_async(e.h, C.byref(sets[0][0]), chd.capi.ptr(sets[0][1]["hdr"][0])))
+        ck(e.L.chd_fetch_wait(e.h, C.byref(s)))
+        check(i - 1, s)
+    ck(e.L.chd_fetch_wait(e.h, C.byref(s)))
+    check(len(frames) - 1, s)
+    assert sum(w["s"]["n_handover"] for w in want) > 100 and sum(w["s"]["n_due"] for w in want) > 1000
+    with pytest.raises(chd.capi.ChdError):
+        ck(e.L.chd_fetch_wait(e.h, C.byref(s)))  # nothing in flight
+    e.close()
+
+
 def test_zero_copy_device_inputs_match_host_inputs(chd):
     """Device-resident positions / queries / rings are consumed in place; results equal the host-input path."""
     import torch
@@ -712,6 +828,66 @@ def test_prefetched_inputs_match_direct_upload(chd):
         for i in (2, 3, 4, 5):
             np.testing.assert_array_equal(a[i], b[i])
     assert sum(r[0]["n_handover"] for r in out["direct"]) > 100 and sum(r[0]["n_due"] for r in out["direct"]) > 1000
+
+
+def test_float_positions_match_widened_doubles(chd, oracle):
+    """chd_set_entities_f32 / chd_prefetch_entities_f32 (positions that are FVector floats at the source, pkg/unrealpb/extension.go:10-24:
+    info.X = float64(*vec.X)) give bit-identical results to chd_set_entities fed with the widened doubles, and to the oracle; odd
+    entity counts exercise the kernel's scalar tail; device-resident float arrays are widened in place."""
+    import torch
+
+    wc = chd.synth.scaled(chd.synth.CONFIGS["benchmark"], 60_001, 5_000)
+    og = _oracle_grid(wc)
+    ex, ez = chd.synth.entities(wc)
+    conn, _, _, _ = chd.synth.subscribers(wc, ex, ez)
+    frames = []
+    for tick in range(4):
+        ex, ez = chd.synth.move_entities(wc, ex, ez, tick, 400.0)
+        xf, zf = ex.astype(np.float32), ez.astype(np.float32)
+        xd, zd = xf.astype(np.float64), zf.astype(np.float64)
+        _, cx, cz, r = chd.synth.subscribers(wc, xd, zd)
+        frames.append(dict(t=(tick + 1) * 33_000_000, xf=xf, zf=zf, xd=xd, zd=zd, q=(cx, cz, r)))
+    out = {}
+    for mode in ("f64", "f32", "f32_prefetch", "f32_device"):
+        e = chd.engine.Engine(wc.cfg(), wc.n_entities, wc.n_subscribers, max_visible=1 << 24)
+        e.set_subscribers(conn)
+        res = []
+        if mode == "f32_prefetch":
+            e.prefetch_entities_f32(frames[0]["xf"], frames[0]["zf"])
+        for tick, f in enumerate(frames):
+            batch, keep = chd.engine.make_batch(len(f["q"][0]), sub=None, sphere=f["q"])
+            if mode == "f64":
+                e.set_entities(f["xd"], f["zd"])
+            elif mode == "f32":
+                e.set_entities_f32(f["xf"], f["zf"])
+            elif mode == "f32_device":
+                dx, dz = torch.from_numpy(f["xf"]).cuda(), torch.from_numpy(f["zf"]).cuda()
+                torch.cuda.synchronize()
+                e.set_entities_f32(dx, dz, len(f["xf"]))
+            else:
+                e.adopt_prefetched()
+                if tick + 1 < len(frames):
+                    e.prefetch_entities_f32(frames[tick + 1]["xf"], frames[tick + 1]["zf"])
+            s = e.tick(batch, f["t"], chd.capi.TICK_ALL)
+            pairs = e.get_pairs(s.n_pairs)
+            voff, vis = e.get_visible()
+            ho = np.stack(e.get_handover(s.n_handover), 1)
+            ho = ho[np.lexsort((ho[:, 2], ho[:, 1], ho[:, 0]))]
+            res.append((s.as_dict(), pairs, voff, vis, ho))
+        out[mode] = res
+        e.close()
+    for mode in ("f32", "f32_prefetch", "f32_device"):
+        for a, b in zip(out["f64"], out[mode]):
+            assert a[0] == b[0], mode
+            for k in a[1]:
+                np.testing.assert_array_equal(a[1][k], b[1][k])
+            for i in (2, 3, 4):
+                np.testing.assert_array_equal(a[i], b[i])
+    f = frames[-1]
+    want = oracle.sphere_tick(og, f["xd"], f["zd"], *f["q"])
+    np.testing.assert_array_equal(out["f32"][-1][1]["channel"], want["pair_cell"])
+    np.testing.assert_array_equal(out["f32"][-1][3], want["vis_entity"])
+    assert sum(r[0]["n_handover"] for r in out["f64"]) > 100
 
 
 def test_adjacent_broadcast_sets_parity(chd, oracle):
