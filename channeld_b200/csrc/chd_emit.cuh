@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256)
                           const uint32_t* __restrict__ pair_cell, const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ first_pair,
                           TileDesc* __restrict__ desc, uint32_t stride, uint64_t max_tiles, uint32_t n_slots, const uint32_t* __restrict__ pair_off,
                           uint64_t* __restrict__ vis_off, uint64_t vis_cap, Counters* __restrict__ ctr, unsigned long long* bump_epoch,
-                          uint32_t tile) {
+                          uint32_t tile, uint32_t* __restrict__ general_tiles, uint32_t* __restrict__ n_general) {
     const uint64_t n = min((uint64_t)*n_pairs_ptr, pair_cap);
     // last kernel of the emit preparation: open the NEXT execution's scan epoch (the scan of this one has completed)
     if (bump_epoch && blockIdx.x == 0 && threadIdx.x == 0) *bump_epoch = chd_next_epoch(*bump_epoch);
@@ -77,13 +77,13 @@ __global__ void __launch_bounds__(256)
             d.ends = end0 | (end1 << 16) | (end1 < tile_len ? 0x80000000u : 0u);
             desc[t] = d;
             first_pair[t] = (uint32_t)p;
+            if (end1 < tile_len) general_tiles[atomicAdd(n_general, 1u)] = (uint32_t)t;  // more than two segments: the general pass
         }
     }
 }
 
-// General path of one tile: more than two pairs' lists intersect it (cells smaller than a tile).  Kept out of line so that its
-// registers do not count against the occupancy of the common two-segment path.
-__device__ __noinline__ void emit_tile_general(uint64_t t, uint64_t n_tiles, uint64_t V, uint32_t p0, const uint32_t* __restrict__ n_pairs_ptr,
+// General path of one tile: more than two pairs' lists intersect it (cells smaller than a tile).
+__device__ __forceinline__ void emit_tile_general(uint64_t t, uint64_t n_tiles, uint64_t V, uint32_t p0, const uint32_t* __restrict__ n_pairs_ptr,
                                                uint64_t pair_cap, const uint64_t* __restrict__ voff, const uint32_t* __restrict__ pair_cell,
                                                const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ sorted4, uint32_t stride,
                                                const uint32_t* __restrict__ first_pair, uint32_t* __restrict__ vis_entity, uint32_t* s_end,
@@ -147,71 +147,87 @@ __device__ __noinline__ void emit_tile_general(uint64_t t, uint64_t n_tiles, uin
 // out of an L2-resident pool runs at 6.96 TB/s of writes with one CTA per 16 KB chunk, against 6.2 TB/s with a persistent
 // grid that walks the chunks round-robin (the round-1 shape) and 7.48 TB/s for a pure fill; 4 rows per thread beat 1 (more
 // loads in flight), streaming stores (st.global.cs) beat write-back ones by 15 % (the write stream does not evict the
-// L2-resident sources).  The loop over tiles only runs more than once if the host under-estimated the tile count.
-// Segment table of the tile (the pairs whose lists intersect it) in shared memory; a thread finds its row's segment by
-// binary search; every move is a co-aligned LDG.128 -> STG.128 out of the phase copy whose 16-byte phase matches the
-// destination (a chunk that straddles a pair boundary goes entry by entry).
+// L2-resident sources).
+// This kernel copies the SIMPLE tiles only (at most two segments: everything a thread needs is the 16-byte descriptor
+// {base0, base1, ends, p0}; the bases are phase-adjusted so every move is a co-aligned LDG.128 -> STG.128) and nothing else
+// lives in it, so that it fits 32 registers = 8 CTAs (all 64 warps) per SM; tiles with more segments are listed by the
+// partition pass and copied by emit_visible_general_kernel.  The loop only runs more than once if the host under-estimated
+// the tile count when it sized the grid.
 __global__ void __launch_bounds__(EMIT_THREADS, CHD_EMIT_MIN_BLOCKS)
-    emit_visible_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, const unsigned long long* __restrict__ n_visible_ptr,
-                        const uint64_t* __restrict__ voff, const uint32_t* __restrict__ pair_cell, const uint32_t* __restrict__ cell_start,
-                        const uint32_t* __restrict__ sorted4, uint32_t stride, const uint32_t* __restrict__ first_pair,
-                        const TileDesc* __restrict__ desc, uint32_t* __restrict__ vis_entity, uint64_t vis_cap) {
-    __shared__ uint32_t s_end[EMIT_SMEM_PAIRS];  // (general path) end of pair (p0+k) relative to the tile base, clamped to EMIT_TILE
-    __shared__ uint32_t s_src[EMIT_SMEM_PAIRS];  // (general path) source index of the pair's entry that lands on max(voff[p], tile base)
-    // V was published by the partition pass: the first loads of a CTA (V, its descriptors) do not depend on each other
+    emit_visible_kernel(const unsigned long long* __restrict__ n_visible_ptr, const uint32_t* __restrict__ sorted4, const TileDesc* __restrict__ desc,
+                        uint32_t* __restrict__ vis_entity, uint64_t vis_cap) {
+    // V (published by the partition pass) and the CTA's descriptor are loaded back to back: two independent round trips to L2 in
+    // flight at once (volatile asm: the compiler would otherwise sink the descriptor load below the early exits)
     const uint64_t V = *n_visible_ptr;
-    const uint32_t tid = threadIdx.x;
-    uint4 dw[EMIT_TILES_PER_CTA];
-#pragma unroll
-    for (int k = 0; k < EMIT_TILES_PER_CTA; k++) dw[k] = __ldg(reinterpret_cast<const uint4*>(desc + (uint64_t)blockIdx.x * EMIT_TILES_PER_CTA + k));
+    uint4 dw;
+    {
+        const TileDesc* dp = desc + blockIdx.x;
+        asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(dw.x), "=r"(dw.y), "=r"(dw.z), "=r"(dw.w) : "l"(dp));
+    }
     if (V == 0 || V > vis_cap) return;
-    const uint64_t n_tiles = (V + EMIT_TILE - 1) / EMIT_TILE;
-    for (uint64_t t0 = (uint64_t)blockIdx.x * EMIT_TILES_PER_CTA; t0 < n_tiles; t0 += (uint64_t)gridDim.x * EMIT_TILES_PER_CTA) {
-        if (t0 != (uint64_t)blockIdx.x * EMIT_TILES_PER_CTA) {  // (only if the host under-estimated the tile count)
+    const uint32_t n_tiles = (uint32_t)((V + EMIT_TILE - 1) / EMIT_TILE);
+    const uint32_t tid4 = threadIdx.x * 4;
+    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        if (t != blockIdx.x) dw = __ldg(reinterpret_cast<const uint4*>(desc + t));
+        if (dw.z & 0x80000000u) continue;  // CTA-uniform: a general tile
+        const uint32_t end0 = dw.z & 0x7FFFu, end1 = (dw.z >> 16) & 0x7FFFu;  // a simple tile's second segment reaches the end of the tile / list
+        uint32_t* __restrict__ out = vis_entity + (uint64_t)t * EMIT_TILE;
+        uint4 v[EMIT_ROWS];
+        uint32_t whole = 0;
 #pragma unroll
-            for (int k = 0; k < EMIT_TILES_PER_CTA; k++)
-                if (t0 + k < n_tiles) dw[k] = __ldg(reinterpret_cast<const uint4*>(desc + t0 + k));
-        }
-        uint32_t src[EMIT_TILES_PER_CTA][EMIT_ROWS];
-#pragma unroll
-        for (int k = 0; k < EMIT_TILES_PER_CTA; k++) {
-            const bool live = t0 + k < n_tiles, simple = !(dw[k].z & 0x80000000u);
-            // simple tile: at most two segments, everything a thread needs is in the descriptor ({base0, base1, ends, p0});
-            // its length is end1 (a simple tile's second segment reaches the end of the tile or of the list)
-            const uint32_t end0 = dw[k].z & 0x7FFFu, end1 = (dw[k].z >> 16) & 0x7FFFu;
-            uint32_t* __restrict__ out = vis_entity + (t0 + k) * EMIT_TILE;
-#pragma unroll
-            for (int r = 0; r < EMIT_ROWS; r++) {
-                const uint32_t o = (r * EMIT_THREADS + tid) * 4;
-                src[k][r] = 0xFFFFFFFFu;
-                if (live && simple && o < end1) {
-                    const bool in0 = o + 4 <= end0, in1 = o >= end0 && o + 4 <= end1;
-                    if (in0 || in1) {
-                        src[k][r] = (in0 ? dw[k].x : dw[k].y) + o;
-                    } else {
-                        for (uint32_t j = 0; j < 4 && o + j < end1; j++)  // the chunk straddles the boundary / the end of the list
-                            out[o + j] = __ldg(sorted4 + (o + j < end0 ? dw[k].x : dw[k].y) + o + j);
-                    }
-                }
+        for (int r = 0; r < EMIT_ROWS; r++) {
+            const uint32_t o = r * (EMIT_THREADS * 4) + tid4;
+            const bool in0 = o + 4 <= end0, in1 = o >= end0 && o + 4 <= end1;
+            if (in0 || in1) {
+                // 32-bit index arithmetic ON PURPOSE: base1 is stored minus end0 and may have wrapped below zero; base1 + o wraps back
+                const uint32_t si = (in0 ? dw.x : dw.y) + o;
+                v[r] = __ldg(reinterpret_cast<const uint4*>(sorted4 + si));
+                whole |= 1u << r;
             }
         }
-        uint4 v[EMIT_TILES_PER_CTA][EMIT_ROWS];
 #pragma unroll
-        for (int k = 0; k < EMIT_TILES_PER_CTA; k++)
+        for (int r = 0; r < EMIT_ROWS; r++)
+            if (whole & (1u << r)) __stcs(reinterpret_cast<uint4*>(out + r * (EMIT_THREADS * 4) + tid4), v[r]);
 #pragma unroll
-            for (int r = 0; r < EMIT_ROWS; r++)
-                if (src[k][r] != 0xFFFFFFFFu) v[k][r] = __ldg(reinterpret_cast<const uint4*>(sorted4 + src[k][r]));
-#pragma unroll
-        for (int k = 0; k < EMIT_TILES_PER_CTA; k++)
-#pragma unroll
-            for (int r = 0; r < EMIT_ROWS; r++)
-                if (src[k][r] != 0xFFFFFFFFu)
-                    __stcs(reinterpret_cast<uint4*>(vis_entity + (t0 + k) * EMIT_TILE + (r * EMIT_THREADS + tid) * 4), v[k][r]);
-#pragma unroll
-        for (int k = 0; k < EMIT_TILES_PER_CTA; k++)
-            if (t0 + k < n_tiles && (dw[k].z & 0x80000000u))  // CTA-uniform
-                emit_tile_general(t0 + k, n_tiles, V, dw[k].w, n_pairs_ptr, pair_cap, voff, pair_cell, cell_start, sorted4, stride, first_pair, vis_entity,
-                                  s_end, s_src);
+        for (int r = 0; r < EMIT_ROWS; r++) {
+            const uint32_t o = r * (EMIT_THREADS * 4) + tid4;
+            if (!(whole & (1u << r)) && o < end1)  // the chunk straddles the segment boundary / the end of the list: entry by entry
+                for (uint32_t j = 0; j < 4 && o + j < end1; j++) {
+                    const uint32_t si = (o + j < end0 ? dw.x : dw.y) + o + j;  // (32-bit wrap, as above)
+                    out[o + j] = __ldg(sorted4 + si);
+                }
+        }
+    }
+}
+
+// The tiles the partition pass listed as general (more than two segments): segment table in shared memory, binary search per row.
+__global__ void __launch_bounds__(EMIT_THREADS)
+    emit_visible_general_kernel(const uint32_t* __restrict__ general_tiles, uint32_t* __restrict__ n_general_ptr,
+                                const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, const unsigned long long* __restrict__ n_visible_ptr,
+                                const uint64_t* __restrict__ voff, const uint32_t* __restrict__ pair_cell, const uint32_t* __restrict__ cell_start,
+                                const uint32_t* __restrict__ sorted4, uint32_t stride, const uint32_t* __restrict__ first_pair,
+                                uint32_t* __restrict__ vis_entity, uint64_t vis_cap) {
+    __shared__ uint32_t s_end[EMIT_SMEM_PAIRS];  // end of pair (p0+k) relative to the tile base, clamped to EMIT_TILE
+    __shared__ uint32_t s_src[EMIT_SMEM_PAIRS];  // source index of the pair's entry that lands on max(voff[p], tile base)
+    // n_general_ptr[0] = list length (appended by the partition pass), [1] = blocks that have read it: the last one to arrive
+    // empties the list for the next partition pass (which is ordered after this kernel)
+    __shared__ uint32_t s_n;
+    if (threadIdx.x == 0) {
+        s_n = n_general_ptr[0];
+        __threadfence();
+        if (atomicAdd(n_general_ptr + 1, 1u) == gridDim.x - 1) {
+            n_general_ptr[0] = 0;
+            n_general_ptr[1] = 0;
+        }
+    }
+    __syncthreads();
+    const uint32_t n_general = s_n;
+    const uint64_t V = *n_visible_ptr;
+    if (n_general == 0 || V == 0 || V > vis_cap) return;
+    const uint64_t n_tiles = (V + EMIT_TILE - 1) / EMIT_TILE;
+    for (uint32_t i = blockIdx.x; i < n_general; i += gridDim.x) {
+        const uint32_t t = general_tiles[i];
+        emit_tile_general(t, n_tiles, V, first_pair[t], n_pairs_ptr, pair_cap, voff, pair_cell, cell_start, sorted4, stride, first_pair, vis_entity, s_end, s_src);
     }
 }
 

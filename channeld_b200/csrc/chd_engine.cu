@@ -329,6 +329,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
     ok = ok && dalloc(e, &e->d_new_off, (Q > P ? Q : P) + 2) && dalloc(e, &e->d_new_sub, P) && dalloc(e, &e->d_new_ch, P) && dalloc(e, &e->d_gone_sub, P) &&
          dalloc(e, &e->d_gone_ch, P);
     ok = ok && dalloc(e, &e->d_pair_ch, P) && dalloc(e, &e->d_vcnt, P) && dalloc(e, &e->d_voff, P + 1) && dalloc(e, &e->d_first_pair, e->max_tiles + 8) && dalloc(e, &e->d_tile_desc, (L.max_visible + EMIT_TILE - 1) / EMIT_TILE + 8) &&
+         dalloc(e, &e->d_general_tiles, (L.max_visible + EMIT_TILE - 1) / EMIT_TILE + 8) && dalloc(e, &e->d_n_general, 4) &&
          dalloc(e, &e->d_vis_off, S + 1) && dalloc(e, &e->d_vis, L.max_visible);
     ok = ok && dalloc(e, &e->d_cell_max_interval, C) && dalloc(e, &e->d_cell_start_ns, C) && dalloc(e, &e->d_rb_begin, C + 1) && dalloc(e, &e->d_rb_end, C + 1) &&
          dalloc(e, &e->d_ring_flat_off, C + 2) && dalloc(e, &e->d_upd_off, C + 1);
@@ -352,6 +353,7 @@ chd_status chd_create(const chd_grid_cfg* cfg, const chd_limits* lim_in, int dev
     CCU(cudaHostAlloc((void**)&e->h_get, 64, cudaHostAllocDefault));
     CCU(cudaMemsetAsync(e->d_ctr, 0, sizeof(Counters), e->stream));
     CCU(cudaMemsetAsync(e->d_win_cursor, 0, 8, e->stream));
+    CCU(cudaMemsetAsync(e->d_n_general, 0, 16, e->stream));
     CCU(cudaMemsetAsync(e->d_slot_ctl, 0, S, e->stream));
     CCU(cudaMemsetAsync(e->d_cell_max_interval, 0, C * 4, e->stream));
     CCU(cudaMemsetAsync(e->d_cell_start_ns, 0, C * 8, e->stream));
@@ -411,7 +413,7 @@ chd_status chd_profile_enable(chd_engine* e, int on) {
     }
     CU(e, cudaStreamSynchronize(e->stream));
     for (int s = 0; s < CHD_STAGE_COUNT; s++) e->stage_n[s] = 0;
-    e->profiling = on != 0;
+    e->profiling = on == 2 ? 2 : (on != 0 ? 1 : 0);
     return CHD_OK;
 }
 

@@ -59,7 +59,7 @@ struct chd_engine {
     int64_t* d_time = nullptr;      // [0] = now_ns of the last update_interest, [1] = t_ns of the last fanout_tick
     uint32_t* d_ring_total = nullptr;
     // optional per-stage CUDA-event timing (chd_profile_*): [stage][0=start,1=stop]
-    bool profiling = false;
+    int profiling = 0;  // 0 off, 1 every stage, 2 the emit kernel only
     static constexpr int EV_RING = 1024;
     cudaEvent_t* ev = nullptr;  // [CHD_STAGE_COUNT][EV_RING][2]
     uint64_t stage_n[CHD_STAGE_COUNT] = {};
@@ -74,6 +74,7 @@ struct chd_engine {
     // chd_prefetch_entities: the BACK buffers receive the next tick's positions on `up_stream` while the current tick runs;
     // chd_adopt_prefetched swaps front and back.  ev_pos_read[b] = last assign_cells that read buffer pair b.
     double *d_xb[2] = {nullptr, nullptr}, *d_zb[2] = {nullptr, nullptr};
+    uint32_t *d_general_tiles = nullptr, *d_n_general = nullptr;  // tiles with more than two segments: list, {length, consumer ticket}
     float* d_pos_f32[2] = {nullptr, nullptr};  // float staging of chd_set_entities_f32 [0] / chd_prefetch_entities_f32 [1]: x then z
     int pos_buf = 0;
     cudaStream_t up_stream = nullptr;
@@ -298,11 +299,12 @@ struct chd_engine {
 struct StageTimer {  // records a CUDA-event pair around a stage on the engine stream when profiling is on
     chd_engine* e;
     int stage;
-    StageTimer(chd_engine* e_, int stage_) : e(e_), stage(stage_) {
-        if (e->profiling) cudaEventRecord(e->evt(stage, e->stage_n[stage], 0), e->stream);
+    bool on;
+    StageTimer(chd_engine* e_, int stage_) : e(e_), stage(stage_), on(e_->profiling == 1 || (e_->profiling == 2 && stage_ == CHD_STAGE_EMIT_KERNEL)) {
+        if (on) cudaEventRecord(e->evt(stage, e->stage_n[stage], 0), e->stream);
     }
     ~StageTimer() {
-        if (e->profiling) {
+        if (on) {
             cudaEventRecord(e->evt(stage, e->stage_n[stage], 1), e->stream);
             e->stage_n[stage]++;
         }

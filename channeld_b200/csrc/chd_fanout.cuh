@@ -21,8 +21,27 @@ constexpr uint32_t FANOUT_SLOTS = 2;            // decisions per pair kept by th
 // The per-pair state machine of tickData.  Decisions are handed to `emit(j, decision, skipped)`; skipped = an own update
 // fell into the decision's window and was left out.  (The window's lower end is window_hi - interval: not passed.)
 // Returns the number of decisions; the final state is left in (last, flags, last_index).
-template <typename Emit>
-__device__ __forceinline__ uint32_t fanout_eval(const RingDev& ring, uint32_t ring_total, int64_t t, uint32_t interval, uint32_t c, uint32_t s,
+// Where the ring entries are read from: global memory, or the block's shared-memory copy of the span its pairs' cells cover.
+struct RingGlobal {
+    const int64_t* __restrict__ arr;
+    const uint32_t* __restrict__ snd;
+    const uint64_t* __restrict__ idx;
+    __device__ __forceinline__ int64_t arrival(uint32_t k) const { return arr[k]; }
+    __device__ __forceinline__ uint32_t sender(uint32_t k) const { return snd[k]; }
+    __device__ __forceinline__ uint64_t index(uint32_t k) const { return idx[k]; }
+};
+struct RingShared {
+    const int64_t* arr;  // shared memory
+    const uint32_t* snd;
+    const uint64_t* idx;
+    uint32_t first;  // global index of the first staged entry
+    __device__ __forceinline__ int64_t arrival(uint32_t k) const { return arr[k - first]; }
+    __device__ __forceinline__ uint32_t sender(uint32_t k) const { return snd[k - first]; }
+    __device__ __forceinline__ uint64_t index(uint32_t k) const { return idx[k - first]; }
+};
+
+template <typename Ring, typename Emit>
+__device__ __forceinline__ uint32_t fanout_eval(const RingDev& ring, const Ring& rg, uint32_t ring_total, int64_t t, uint32_t interval, uint32_t c, uint32_t s,
                                                 uint32_t me, uint32_t id_start, int64_t& last, uint8_t& flags, uint64_t& last_index, Emit&& emit) {
     const int64_t step_ns = (int64_t)interval * 1000000ll;  // ChannelTime.AddMs (channel.go:30-32)
     const bool skip_self = flags & PF_SKIP_SELF;
@@ -49,8 +68,8 @@ __device__ __forceinline__ uint32_t fanout_eval(const RingDev& ring, uint32_t ri
             uint64_t hash = 0;
             bool skipped = false;  // an own update fell into the window and was left out (data.go:239-242)
             for (uint32_t k = r0; k < r1; k++) {
-                const int64_t a = ring.arrival[k];
-                if (skip_self && ring.sender[k] == me) {
+                const int64_t a = rg.arrival(k);
+                if (skip_self && rg.sender(k) == me) {
                     skipped |= a >= last_update && a <= next;
                     continue;
                 }
@@ -58,7 +77,7 @@ __device__ __forceinline__ uint32_t fanout_eval(const RingDev& ring, uint32_t ri
                     if (!nsel) first = k - r0;
                     lastsel = k - r0;
                     nsel++;
-                    const uint64_t mi = ring.index[k];
+                    const uint64_t mi = rg.index(k);
                     hash += mi;
                     last_update = a;
                     last_index = mi;
@@ -81,47 +100,70 @@ __device__ __forceinline__ uint32_t fanout_eval(const RingDev& ring, uint32_t ri
 // registers), a block-wide scan turns the decision counts into offsets, one atomicAdd per block reserves the block's
 // range of the due list (the running total doubles as n_due), then the decisions are written and the state committed.
 // Pairs with more decisions (several intervals behind) re-evaluate from their saved state while writing.
+// Pairs are visited grouped by cell (ascending), so the 128 pairs of a block iteration touch the rings of one or two cells:
+// the block copies that span of the ring arrays into shared memory once (FANOUT_STAGE entries; wider spans are read from
+// global memory) and every thread's window scan runs out of it — the scan is a chain of dependent compares over <= 64
+// entries per interval step, i.e. bound by load latency, not by bandwidth.
 // The due list is therefore grouped by block and unordered across blocks: it is a SET of send decisions (the
 // reference issues them from independent per-channel goroutines, i.e. in no global order either).
-__global__ void __launch_bounds__(128, 6)  // <= 85 registers: the whole pair list of config #2 (855 CTAs) stays one wave on 148 SMs
+constexpr uint32_t FANOUT_STAGE = 640;  // 12.5 KB of shared memory per block
+
+__global__ void __launch_bounds__(128, 8)  // <= 64 registers = 8192 per CTA: a fan-out CTA fits the slot ONE retiring emit CTA (256 x 32) frees
     fanout_kernel(const uint32_t* __restrict__ n_pairs_ptr, uint64_t pair_cap, PairBuf pb, const uint32_t* __restrict__ conn_id, RingDev ring,
                   const int64_t* __restrict__ t_ptr, uint32_t id_start, const uint32_t* __restrict__ by_cell, chd_due* __restrict__ due,
                   DueKey* __restrict__ due_key, uint32_t due_cap, Counters* __restrict__ ctr) {
-    __shared__ uint32_t s_warp[4], s_base;
+    __shared__ uint32_t s_warp[4], s_base, s_clo, s_chi;
+    __shared__ int64_t s_arr[FANOUT_STAGE];
+    __shared__ uint64_t s_idx[FANOUT_STAGE];
+    __shared__ uint32_t s_snd[FANOUT_STAGE];
     const uint64_t n = min((uint64_t)*n_pairs_ptr, pair_cap);
     const int64_t t = *t_ptr;  // device-resident so the launch can be replayed from a CUDA graph
     const uint32_t ring_total = *ring.total;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const RingGlobal rglob{ring.arrival, ring.sender, ring.index};
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t i = base + threadIdx.x;
-        // pairs are visited grouped by cell: neighbouring lanes walk the same ring (uniform-address loads)
         uint32_t n_out = 0, interval = 0, c = 0, s = 0, me = 0;
         uint64_t p = 0, last_index0 = 0, last_index = 0;
         int64_t last0 = 0, last = 0;
         uint8_t flags0 = 0, flags = 0;
         chd_due d0, d1;
-        bool sk0 = false, sk1 = false;
+        bool sk0 = false, sk1 = false, due_now = false;
+        int64_t tc = t;  // ChannelTime of this pair's channel: every channel counts from its own start (channel.go:178)
         if (i < n) {
             p = by_cell[i];
             interval = pb.interval[p];
             last0 = last = pb.last[p];
-            int64_t tc = t;  // ChannelTime of this pair's channel: every channel counts from its own start (channel.go:178)
-            if (ring.start) {
-                c = pb.cell[p];
-                tc = t - ring.start[c];
+            c = pb.cell[p];
+            if (ring.start) tc = t - ring.start[c];
+            due_now = tc >= last + (int64_t)interval * 1000000ll;  // (else: the common cheap exit, no further state is read)
+            if (threadIdx.x == 0) s_clo = c;
+            if (i + 1 == n || threadIdx.x == blockDim.x - 1) s_chi = c;
+        }
+        __syncthreads();  // also: the previous iteration's readers of the staged span / s_warp / s_base are done
+        // the ring entries of cells s_clo .. s_chi (ascending cells: ascending, disjoint entry ranges)
+        const uint32_t span0 = min(ring.off[s_clo], ring_total), span1 = min(ring.end[s_chi], ring_total);
+        const bool staged = span1 >= span0 && span1 - span0 <= FANOUT_STAGE;
+        if (staged) {
+            for (uint32_t k = span0 + threadIdx.x; k < span1; k += blockDim.x) {
+                s_arr[k - span0] = ring.arrival[k];
+                s_snd[k - span0] = ring.sender[k];
+                s_idx[k - span0] = ring.index[k];
             }
-            if (tc >= last + (int64_t)interval * 1000000ll) {  // due (else: the common cheap exit, no further state is read)
-                flags0 = flags = pb.flags[p];
-                last_index0 = last_index = pb.last_index[p];
-                c = pb.cell[p];
-                s = pb.sub[p];
-                me = conn_id[s];
-                n_out = fanout_eval(ring, ring_total, tc, interval, c, s, me, id_start, last, flags, last_index,
-                                    [&](uint32_t j, const chd_due& d, bool skipped) {
-                                        if (j == 0) { d0 = d; sk0 = skipped; }
-                                        else if (j == 1) { d1 = d; sk1 = skipped; }
-                                    });
-            }
+        }
+        __syncthreads();
+        const RingShared rsh{s_arr, s_snd, s_idx, span0};
+        if (due_now) {
+            flags0 = flags = pb.flags[p];
+            last_index0 = last_index = pb.last_index[p];
+            s = pb.sub[p];
+            me = conn_id[s];
+            auto keep = [&](uint32_t j, const chd_due& d, bool skipped) {
+                if (j == 0) { d0 = d; sk0 = skipped; }
+                else if (j == 1) { d1 = d; sk1 = skipped; }
+            };
+            n_out = staged ? fanout_eval(ring, rsh, ring_total, tc, interval, c, s, me, id_start, last, flags, last_index, keep)
+                           : fanout_eval(ring, rglob, ring_total, tc, interval, c, s, me, id_start, last, flags, last_index, keep);
         }
         // block-wide exclusive offsets of n_out (128 threads = 4 warps)
         uint32_t incl = n_out;
@@ -130,7 +172,6 @@ __global__ void __launch_bounds__(128, 6)  // <= 85 registers: the whole pair li
             const uint32_t a = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += a;
         }
-        __syncthreads();  // previous iteration's readers of s_warp / s_base are done
         if (lane == 31) s_warp[w] = incl;
         __syncthreads();
         uint32_t off = incl - n_out;
@@ -156,10 +197,11 @@ __global__ void __launch_bounds__(128, 6)  // <= 85 registers: the whole pair li
                 if (n_out > 1) { due[o + 1] = d1; due_key[o + 1] = make_due_key(c, d1.kind, sk1, s, d1.window_hi - step_ns); }
             } else {  // several intervals behind: re-evaluate from the saved state, writing directly
                 last = last0; flags = flags0; last_index = last_index0;
-                fanout_eval(ring, ring_total, ring.start ? t - ring.start[c] : t, interval, c, s, me, id_start, last, flags, last_index,
-                            [&](uint32_t j, const chd_due& d, bool skipped) {
-                                due[o + j] = d; due_key[o + j] = make_due_key(c, d.kind, skipped, s, d.window_hi - step_ns);
-                            });
+                auto put = [&](uint32_t j, const chd_due& d, bool skipped) {
+                    due[o + j] = d; due_key[o + j] = make_due_key(c, d.kind, skipped, s, d.window_hi - step_ns);
+                };
+                if (staged) fanout_eval(ring, rsh, ring_total, tc, interval, c, s, me, id_start, last, flags, last_index, put);
+                else fanout_eval(ring, rglob, ring_total, tc, interval, c, s, me, id_start, last, flags, last_index, put);
             }
         }
         if (i < n && fits && (n_out || last != last0)) {  // commit (steps without a decision still advance lastFanOutTime)

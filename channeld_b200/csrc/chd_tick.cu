@@ -34,7 +34,8 @@ static chd_status emit_prep_enqueue(chd_engine* e, bool cta_tiles) {
         // per-pair visible counts are computed by the scan itself; the partition pass opens the next epoch
         SCAN(e, exclusive_scan_fn<PairVcountIn, uint64_t>(PairVcountIn{pb.cell, e->d_cell_start}, e->d_voff, P, e->site_voff, s, pb.off + S));
         emit_partition_kernel<<<grid, 256, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_first_pair, cta_tiles ? e->d_tile_desc : nullptr,
-                                                   e->phase_stride, e->max_tiles, S, pb.off, e->d_vis_off, e->lim.max_visible, e->d_ctr, e->d_epoch + EP_EMIT, tile);
+                                                   e->phase_stride, e->max_tiles, S, pb.off, e->d_vis_off, e->lim.max_visible, e->d_ctr, e->d_epoch + EP_EMIT, tile,
+                                                   e->d_general_tiles, e->d_n_general);
         KCHECK(e);
         return CHD_OK;
     });
@@ -55,8 +56,11 @@ static chd_status emit_kernel_enqueue(chd_engine* e, bool cta_tiles) {
         if (tiles == 0) tiles = 1;
         if (tiles > 0x7fffffffull) tiles = 0x7fffffffull;
         tiles = (tiles + EMIT_TILES_PER_CTA - 1) / EMIT_TILES_PER_CTA;
-        emit_visible_kernel<<<(unsigned)tiles, EMIT_THREADS, 0, s>>>(pb.off + S, P, &e->d_ctr->n_visible, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4,
-                                                                     e->phase_stride, e->d_first_pair, e->d_tile_desc, e->d_vis, e->lim.max_visible);
+        emit_visible_kernel<<<(unsigned)tiles, EMIT_THREADS, 0, s>>>(&e->d_ctr->n_visible, e->d_sorted4, e->d_tile_desc, e->d_vis, e->lim.max_visible);
+        KCHECK(e);
+        emit_visible_general_kernel<<<(unsigned)e->sm_count * 2, EMIT_THREADS, 0, s>>>(e->d_general_tiles, e->d_n_general, pb.off + S, P, &e->d_ctr->n_visible,
+                                                                                       e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4, e->phase_stride,
+                                                                                       e->d_first_pair, e->d_vis, e->lim.max_visible);
     } else {
         emit_visible_warp_kernel<<<(unsigned)e->sm_count * 4, EMIT_THREADS, 0, s>>>(pb.off + S, P, e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4,
                                                                                     e->phase_stride, e->d_first_pair, e->d_vis, e->lim.max_visible);

@@ -15,7 +15,7 @@ constexpr int EMIT_THREADS = 256;
 #define CHD_EMIT_ROWS 4
 #endif
 #ifndef CHD_EMIT_MIN_BLOCKS
-#define CHD_EMIT_MIN_BLOCKS 6
+#define CHD_EMIT_MIN_BLOCKS 8
 #endif
 #ifndef CHD_EMIT_TILES_PER_CTA
 #define CHD_EMIT_TILES_PER_CTA 1

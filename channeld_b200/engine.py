@@ -356,7 +356,8 @@ class Engine:
         return int(self.L.chd_graph_launch_count(self.h))
 
     def profile_enable(self, on=True):
-        self._ck(self.L.chd_profile_enable(self.h, int(bool(on))))
+        """True / 1: every stage; 2: the emit kernel only; False / 0: off."""
+        self._ck(self.L.chd_profile_enable(self.h, 2 if on == 2 else int(bool(on))))
 
     def profile_get(self, stage):
         ms, n = C.c_double(), C.c_uint64()

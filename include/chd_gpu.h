@@ -524,7 +524,8 @@ uint32_t chd_damping_interval_ms(uint32_t dist, uint32_t default_ms);
 /* ---- instrumentation.  chd_launch_count: kernels launched by this engine so far.  chd_profile_enable(1)
  * makes every stage record a CUDA-event pair on the engine stream (the last 1024 samples are kept);
  * chd_profile_get synchronises and returns the summed device time of a stage.  CHD_STAGE_EMIT_KERNEL brackets
- * exactly the emit_visible kernel (the dominant HBM term; bench.py's roofline uses it). */
+ * exactly the emit_visible kernel (the dominant HBM term; bench.py's roofline uses it); chd_profile_enable(2) records that
+ * pair only (two events per tick instead of about twenty: what bench.py leaves on inside its timed region). */
 enum { CHD_STAGE_BUILD = 0, CHD_STAGE_INTEREST, CHD_STAGE_EMIT, CHD_STAGE_EMIT_KERNEL, CHD_STAGE_FANOUT, CHD_STAGE_TICK,
        CHD_STAGE_EXPORT, CHD_STAGE_EXCHANGE, CHD_STAGE_IMPORT, /* the three steps of chd_tick_sharded before the tick proper */
        CHD_STAGE_COUNT };

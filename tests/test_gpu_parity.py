@@ -1054,6 +1054,43 @@ def test_concurrent_stateless_queries_during_ticks(chd, oracle):
     assert not errors, errors[:3]
 
 
+def test_emit_descriptor_base_wraps_below_zero(chd, oracle):
+    """A tile whose second segment is a cell that starts EARLIER in the CSR than the first segment ends in the tile: the descriptor's
+    second base is stored minus that end and wraps below zero (32-bit arithmetic on purpose).  With the two ends congruent mod 4 the
+    copy of the second segment comes from phase 0 (no stride added to the base) and the 16-byte chunk across the boundary goes entry
+    by entry — the combination that used to be added in 64 bits (out-of-bounds read)."""
+    wc = chd.synth.CONFIGS["2x2"]
+    og = _oracle_grid(wc)
+    centres = [(wc.offx + (c + 0.5) * wc.w, wc.offz + (r + 0.5) * wc.h) for r in range(wc.rows) for c in range(wc.cols)]
+    ids = oracle.cell_of(og, np.array([c[0] for c in centres]), np.array([c[1] for c in centres]))
+    centres = [centres[k] for k in np.argsort(ids)]  # ascending cell index = CSR order
+    counts = [1001, 5000, 8192 + 2005, 0]  # cell 1 starts at 1001; the big cell ends 2005 entries into its third tile: 2005 % 4 == 1001 % 4
+    rng = np.random.default_rng(5)
+    xs, zs = [], []
+    for (cx_, cz_), n in zip(centres, counts):
+        xs.append(cx_ + rng.uniform(-0.4, 0.4, n) * wc.w)
+        zs.append(cz_ + rng.uniform(-0.4, 0.4, n) * wc.h)
+    ex, ez = np.concatenate(xs), np.concatenate(zs)
+    perm = rng.permutation(len(ex))
+    ex, ez = ex[perm], ez[perm]
+    # subscriber 0 sees the big cell only, subscriber 1 the 5000-entity cell only
+    cx = np.array([centres[2][0], centres[1][0]])
+    cz = np.array([centres[2][1], centres[1][1]])
+    r = np.array([50.0, 50.0])
+    e = chd.engine.Engine(wc.cfg(), len(ex), 2, max_visible=1 << 20)
+    e.set_entities(ex, ez)
+    e.set_subscribers(np.array([11, 12], np.uint32))
+    batch, keep = chd.engine.make_batch(2, sub=None, sphere=(cx, cz, r))
+    for tick in range(3):  # direct launches, then the replayed graphs
+        s = e.tick(batch, (tick + 1) * 33_000_000, chd.capi.TICK_BUILD | chd.capi.TICK_EMIT)
+        want = oracle.sphere_tick(og, ex, ez, cx, cz, r)
+        voff, vis = e.get_visible()
+        np.testing.assert_array_equal(voff, want["vis_off"])
+        np.testing.assert_array_equal(vis, want["vis_entity"])
+        assert s.n_visible == counts[2] + counts[1]
+    e.close()
+
+
 def test_full_size_config2_properties(chd, oracle):
     """BASELINE config #2 at FULL size (1 M entities / 100 K subscribers, r = 50): size-independent properties of the
     whole result + bit-exact oracle comparison on a 2 % subscriber sample."""

@@ -4,7 +4,7 @@ N=${1:-2}
 mkdir -p gpurun_out/r2
 nvidia-smi -L | head -8
 if [ -z "$2" ]; then
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 tests/run_multigpu_parity.py > gpurun_out/r2/mg_parity_n$N.txt 2>&1
+CHD_PARITY_TICKS=${CHD_PARITY_TICKS:-6} timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 tests/run_multigpu_parity.py > gpurun_out/r2/mg_parity_n$N.txt 2>&1
 echo "parity rc=$?"; grep -E "parity|mismatches=[1-9]|Error|error|exchange mode|collectives in" gpurun_out/r2/mg_parity_n$N.txt | tail -14; tail -3 gpurun_out/r2/mg_parity_n$N.txt
 fi
 run() {  # tag, extra args
@@ -21,5 +21,5 @@ except Exception as ex:
 PY
 }
 run peer --exchange peer
-run nccl --exchange nccl
+if [ "$N" = "2" ]; then run nccl --exchange nccl; fi
 run weak --exchange peer --scaling weak
