@@ -317,7 +317,7 @@ def run_ours(args):
 
     n_e2e = args.e2e_steps or min(args.steps, 30)
     n_prof = min(args.steps, 20)  # steps of the instrumented pass after the timed region
-    n_steps_total = 1 + args.warmup + args.steps + n_prof + 4 * (2 + n_e2e) + 4 + args.expanded_steps + 2
+    n_steps_total = 1 + args.warmup + args.steps + n_prof + 5 * (2 + n_e2e) + 4 + args.expanded_steps + 2
     # one ring snapshot per step (arrival times follow the tick clock); bound the staging memory for huge grids
     ring_len, upc = args.ring_len, args.updates_per_cell
     while wc.cells * ring_len * 20 * n_steps_total > (768 << 20) and ring_len > 4:
@@ -419,6 +419,7 @@ def run_ours(args):
                             "per subscriber on N GPUs) to the oracle run over the full snapshot"}
 
         # ---- value: device-resident inputs, device time
+        barrier()  # (the gate's CPU work takes a different time on every rank: start the ticks together)
         for i in range(1, args.warmup + 1):
             step(i, dev_in, batches_dev, rings_dev)
         e.summary()
@@ -657,6 +658,21 @@ def run_ours(args):
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
+        if args.trace_e2e:  # diagnostics: device-side stage times of the asynchronous loop itself (instrumented: not the reported run)
+            e.profile_enable(True)
+            async_run(base + 2, n_e2e)
+            torch.cuda.synchronize()
+            tr = {}
+            for name, sid in (("tick", capi.STAGE_TICK), ("build", capi.STAGE_BUILD), ("interest", capi.STAGE_INTEREST), ("emit", capi.STAGE_EMIT),
+                              ("emit_kernel", capi.STAGE_EMIT_KERNEL), ("fanout", capi.STAGE_FANOUT), ("readback_pcie_hop", capi.STAGE_READBACK)):
+                tot, n_ = e.profile_get(sid)
+                tr[name] = round(tot / max(n_, 1), 4)
+            e.profile_enable(False)
+            print("[bench] async e2e loop, device stage ms: %r" % (tr,), file=sys.stderr)
+            base += n_e2e
+            prefetch_inputs(base)
+            async_run(base, 2)
+            torch.cuda.synchronize()
         for k_ in host_acc:
             host_acc[k_] = 0
         got_async = async_run(base + 2, n_e2e)

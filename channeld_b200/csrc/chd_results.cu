@@ -416,6 +416,8 @@ chd_status chd_fetch_results_async(chd_engine* e, const chd_result_buffers* b, v
     }
     CU(e, cudaEventRecord(e->ev_fetch_a[fi], sa));
     CU(e, cudaStreamWaitEvent(sc, e->ev_fetch_a[fi], 0));
+    const bool prof = e->profiling == 1;
+    if (prof) CU(e, cudaEventRecord(e->evt(CHD_STAGE_READBACK, e->stage_n[CHD_STAGE_READBACK], 0), sc));
     if (H[0].n) {
         pack_kernel<<<dim3(24, (unsigned)H[0].n), 256, 0, sc>>>(H[0]);
         KCHECK(e);
@@ -433,6 +435,10 @@ chd_status chd_fetch_results_async(chd_engine* e, const chd_result_buffers* b, v
     pack_kernel<<<dim3(24, (unsigned)H[2].n), 256, 0, sc>>>(H[2]);
     KCHECK(e);
     CU(e, cudaEventRecord(e->ev_fetch_done[fi], sc));
+    if (prof) {
+        CU(e, cudaEventRecord(e->evt(CHD_STAGE_READBACK, e->stage_n[CHD_STAGE_READBACK], 1), sc));
+        e->stage_n[CHD_STAGE_READBACK]++;
+    }
     e->fetch_guard = true;  // the next tick's kernels are ordered after these copies (they overwrite the arrays being read)
     e->fetch_header[fi] = pinned_header;
     e->fetch_issued++;

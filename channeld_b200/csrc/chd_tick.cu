@@ -56,7 +56,7 @@ static chd_status emit_kernel_enqueue(chd_engine* e, bool cta_tiles) {
         if (tiles == 0) tiles = 1;
         if (tiles > 0x7fffffffull) tiles = 0x7fffffffull;
         tiles = (tiles + EMIT_TILES_PER_CTA - 1) / EMIT_TILES_PER_CTA;
-        emit_visible_kernel<<<(unsigned)tiles, EMIT_THREADS, 0, s>>>(&e->d_ctr->n_visible, e->d_sorted4, e->d_tile_desc, e->d_vis, e->lim.max_visible);
+        emit_visible_kernel<<<(unsigned)tiles, EMIT_THREADS, CHD_EMIT_DYN_SMEM, s>>>(&e->d_ctr->n_visible, e->d_sorted4, e->d_tile_desc, e->d_vis, e->lim.max_visible);
         KCHECK(e);
         emit_visible_general_kernel<<<(unsigned)e->sm_count * 2, EMIT_THREADS, 0, s>>>(e->d_general_tiles, e->d_n_general, pb.off + S, P, &e->d_ctr->n_visible,
                                                                                        e->d_voff, pb.cell, e->d_cell_start, e->d_sorted4, e->phase_stride,

@@ -17,6 +17,12 @@ constexpr int EMIT_THREADS = 256;
 #ifndef CHD_EMIT_MIN_BLOCKS
 #define CHD_EMIT_MIN_BLOCKS 8
 #endif
+// Dynamic shared memory the two-segment emit kernel asks for WITHOUT using it: 0 lets 8 CTAs (every warp slot and the whole
+// register file of an SM) be emit CTAs; 30 KB caps them at 7 per SM, which keeps one slot (256 threads, 8 K registers, 18 KB)
+// free for the latency-bound kernels of the second stream (fan-out pass) that run next to it.
+#ifndef CHD_EMIT_DYN_SMEM
+#define CHD_EMIT_DYN_SMEM 0
+#endif
 #ifndef CHD_EMIT_TILES_PER_CTA
 #define CHD_EMIT_TILES_PER_CTA 1
 #endif

@@ -528,6 +528,7 @@ uint32_t chd_damping_interval_ms(uint32_t dist, uint32_t default_ms);
  * pair only (two events per tick instead of about twenty: what bench.py leaves on inside its timed region). */
 enum { CHD_STAGE_BUILD = 0, CHD_STAGE_INTEREST, CHD_STAGE_EMIT, CHD_STAGE_EMIT_KERNEL, CHD_STAGE_FANOUT, CHD_STAGE_TICK,
        CHD_STAGE_EXPORT, CHD_STAGE_EXCHANGE, CHD_STAGE_IMPORT, /* the three steps of chd_tick_sharded before the tick proper */
+       CHD_STAGE_READBACK,                                     /* chd_fetch_results_async: the PCIe hop (snapshot -> pinned host) */
        CHD_STAGE_COUNT };
 uint64_t chd_launch_count(const chd_engine* e);
 /* The launch-bound stages (build, interest update, emit preparation, fan-out) are replayed as CUDA graphs once
