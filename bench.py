@@ -710,7 +710,6 @@ def run_ours(args):
             raise SystemExit("asynchronous read-back differs from the synchronous one")
         if args.trace_e2e and rank == 0:
             n_ = max(phase_acc.get("n", 1), 1)
-            e.close()
             print("[bench] pipelined e2e step, host view (us): " + ", ".join("%s %.1f" % (k_, phase_acc[k_] / n_ * 1e6)
                                                                               for k_ in ("launch", "prefetch", "fetch")), file=sys.stderr)
         e2e_exp = None
