@@ -359,9 +359,10 @@ typedef struct chd_result_buffers {
 } chd_result_buffers;
 chd_status chd_fetch_results(chd_engine* e, const chd_result_buffers* bufs, chd_tick_summary* summary);
 
-/* ---- the same read-back WITHOUT blocking: the lists are written straight into the caller's PINNED host buffers (chd_alloc_pinned)
- * by copy kernels that know the exact lengths on the device, in the same two phases; the call returns at once, so the host can
- * enqueue the NEXT tick before looking at this one (the next tick's kernels are ordered after these copies on the device).
+/* ---- the same read-back WITHOUT blocking: copy kernels that know the exact lengths on the device first snapshot the lists into a
+ * staging area in HBM (microseconds; the next tick's kernels are ordered after THIS, not after the PCIe transfer), then write the
+ * snapshot into the caller's PINNED host buffers (chd_alloc_pinned) on a stream of their own; the call returns at once, so the host
+ * can enqueue the NEXT tick before looking at this one.
  * pinned_header: CHD_FETCH_HEADER_BYTES of pinned memory the engine uses for the counters.  Up to two fetches may be outstanding
  * (use two sets of buffers); chd_fetch_wait blocks until the copies of the OLDEST outstanding chd_fetch_results_async are
  * complete and returns that tick's summary (CHD_ERR_CAPACITY if a list did not fit its
